@@ -1,0 +1,273 @@
+"""ctypes binding of include/gpupcg.h (libgpupcg_cuda.so).
+
+This is a thin test/benchmark driver over the C ABI -- the product is the shared library, the
+foam-extend adaptor (fluidstructureinteraction_b200/foam) is its production caller.  There is no
+fallback of any kind here: if the CUDA library is missing or no B200 is visible, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgpupcg_cuda.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+
+
+class GpuPcgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("gpupcg error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Perf(C.Structure):
+    _fields_ = [
+        ("initialResidual", C.c_double),
+        ("finalResidual", C.c_double),
+        ("normFactor", C.c_double),
+        ("nIterations", C.c_int),
+        ("converged", C.c_int),
+        ("singular", C.c_int),
+        ("reserved", C.c_int),
+        ("solve_ms", C.c_double),
+        ("h2d_ms", C.c_double),
+        ("d2h_ms", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [
+        ("nCells", C.c_int), ("nFaces", C.c_int), ("nRows", C.c_int), ("nSlices", C.c_int),
+        ("nLevels", C.c_int), ("maxLevelRows", C.c_int),
+        ("entriesUpper", C.c_longlong), ("entriesLower", C.c_longlong),
+        ("nInterfaceFaces", C.c_int), ("nInterfaces", C.c_int),
+        ("sweepGrid", C.c_int), ("streamGrid", C.c_int), ("numSMs", C.c_int), ("reserved", C.c_int),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+# every symbol include/gpupcg.h declares: (restype, argtypes)
+SYMBOLS = {
+    "gpupcg_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, c_int_p, c_int_p,
+                                C.c_int, c_int_p, C.POINTER(c_int_p), c_int_p]),
+    "gpupcg_destroy": (C.c_int, [C.c_void_p]),
+    "gpupcg_last_error": (C.c_char_p, [C.c_void_p]),
+    "gpupcg_get_plan_info": (C.c_int, [C.c_void_p, C.POINTER(PlanInfo)]),
+    "gpupcg_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gpupcg_set_matrix": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, C.POINTER(c_double_p)]),
+    "gpupcg_set_matrix_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gpupcg_solve": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_double, C.c_double, C.c_int, C.c_int,
+                               C.POINTER(Perf), c_double_p, C.c_int]),
+    "gpupcg_solve_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int,
+                                      C.c_int, C.POINTER(Perf), c_double_p, C.c_int]),
+    "gpupcg_amul": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p]),
+    "gpupcg_dic_factor": (C.c_int, [C.c_void_p, c_double_p]),
+    "gpupcg_precondition": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
+    "gpupcg_time_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]),
+    "gpupcg_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "gpupcg_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "gpupcg_host_register": (C.c_int, [C.c_void_p, C.c_ulonglong]),
+    "gpupcg_host_unregister": (C.c_int, [C.c_void_p]),
+    "gpupcg_plan_export": (C.c_int, [C.c_int, C.c_int, c_int_p, c_int_p, C.POINTER(PlanInfo), c_int_p, c_int_p,
+                                     c_int_p, c_int_p, c_int_p, c_int_p]),
+    "gpupcg_device_report": (C.c_int, [C.c_int, C.c_char_p, C.c_int]),
+}
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen libgpupcg_cuda.so and type every exported symbol.  Raises if it is not built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise FileNotFoundError(
+            "%s is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback." % p)
+    lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)     # AttributeError if the ABI lost a symbol
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_int_p) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class GpuPCG(object):
+    """One handle = one lduAddressing on one GPU (mirror of the lifetime foam-extend gives a mesh)."""
+
+    def __init__(self, lowerAddr, upperAddr, nCells, patchFaceCells=(), patchNbrRank=(), device=0):
+        self.lib = load_library()
+        self.l = _i32(lowerAddr)
+        self.u = _i32(upperAddr)
+        self.nCells = int(nCells)
+        self.nFaces = int(self.l.shape[0])
+        self.patchFaceCells = [_i32(fc) for fc in patchFaceCells]
+        nP = len(self.patchFaceCells)
+        sizes = _i32([fc.shape[0] for fc in self.patchFaceCells]) if nP else None
+        ptrs = (c_int_p * max(nP, 1))(*[_ip(fc) for fc in self.patchFaceCells]) if nP else None
+        nbr = _i32(list(patchNbrRank)) if nP else None
+        self.h = C.c_void_p()
+        rc = self.lib.gpupcg_create(C.byref(self.h), device, self.nCells, self.nFaces, _ip(self.l), _ip(self.u),
+                                    nP, _ip(sizes), ptrs, _ip(nbr))
+        if rc != 0:
+            msg = self.lib.gpupcg_last_error(None)
+            self.h = None
+            raise GpuPcgError(rc, msg.decode() if msg else "?")
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.gpupcg_last_error(self.h)
+            raise GpuPcgError(rc, msg.decode() if msg else "?")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gpupcg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def plan_info(self):
+        info = PlanInfo()
+        self._check(self.lib.gpupcg_get_plan_info(self.h, C.byref(info)))
+        return info.as_dict()
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.gpupcg_set_stream(self.h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    def set_matrix(self, diag, upper=None, lower=None, patchBouCoeffs=()):
+        diag = _f64(diag)
+        upper = _f64(upper) if upper is not None else None
+        lower_p = None
+        if lower is not None:
+            lower = _f64(lower)
+            lower_p = _dp(upper) if lower is upper else _dp(lower)
+        bc = [_f64(b) for b in patchBouCoeffs]
+        ptrs = (c_double_p * max(len(bc), 1))(*[_dp(b) for b in bc]) if bc else None
+        self._check(self.lib.gpupcg_set_matrix(self.h, _dp(diag), _dp(upper), lower_p, ptrs))
+
+    def set_matrix_device(self, d_diag, d_upper=None, d_bou=None):
+        self._check(self.lib.gpupcg_set_matrix_device(self.h, C.c_void_p(d_diag),
+                                                      C.c_void_p(d_upper) if d_upper else None,
+                                                      C.c_void_p(d_bou) if d_bou else None))
+
+    def solve(self, x, b, tolerance=1e-6, relTol=0.0, minIter=0, maxIter=1000, history=True):
+        """x: float64 array, updated in place (must be C-contiguous float64).  Returns (perf dict, history)."""
+        if not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.c_contiguous):
+            raise TypeError("x must be a C-contiguous float64 ndarray (it is the in/out psi component)")
+        b = _f64(b)
+        perf = Perf()
+        hist = np.zeros(max(maxIter, 1), dtype=np.float64) if history else None
+        self._check(self.lib.gpupcg_solve(self.h, _dp(x), _dp(b), tolerance, relTol, minIter, maxIter,
+                                          C.byref(perf), _dp(hist), hist.shape[0] if history else 0))
+        d = perf.as_dict()
+        return d, (hist[:min(d["nIterations"], hist.shape[0])].copy() if history else None)
+
+    def solve_device(self, d_x, d_b, tolerance=1e-6, relTol=0.0, minIter=0, maxIter=1000, history=False):
+        perf = Perf()
+        hist = np.zeros(max(maxIter, 1), dtype=np.float64) if history else None
+        self._check(self.lib.gpupcg_solve_device(self.h, C.c_void_p(d_x), C.c_void_p(d_b), tolerance, relTol,
+                                                 minIter, maxIter, C.byref(perf), _dp(hist),
+                                                 hist.shape[0] if history else 0))
+        d = perf.as_dict()
+        return d, (hist[:min(d["nIterations"], hist.shape[0])].copy() if history else None)
+
+    def amul(self, x, xNbr=None):
+        x = _f64(x)
+        Ax = np.empty(self.nCells, dtype=np.float64)
+        xn = _f64(xNbr) if xNbr is not None else None
+        self._check(self.lib.gpupcg_amul(self.h, _dp(x), _dp(Ax), _dp(xn)))
+        return Ax
+
+    def dic_factor(self):
+        rD = np.empty(self.nCells, dtype=np.float64)
+        self._check(self.lib.gpupcg_dic_factor(self.h, _dp(rD)))
+        return rD
+
+    def precondition(self, rA):
+        rA = _f64(rA)
+        wA = np.empty(self.nCells, dtype=np.float64)
+        self._check(self.lib.gpupcg_precondition(self.h, _dp(rA), _dp(wA)))
+        return wA
+
+    KERNELS = {"amul": 0, "dic": 1, "p_update": 2, "xr_update": 3, "dic_factor": 4}
+
+    def time_kernel(self, which, reps=10, flushL2=True):
+        ms = C.c_double(0.0)
+        self._check(self.lib.gpupcg_time_kernel(self.h, self.KERNELS[which], reps, 1 if flushL2 else 0, C.byref(ms)))
+        return ms.value
+
+    def comm_init(self, rank, nRanks, unique_id_bytes):
+        buf = C.create_string_buffer(bytes(unique_id_bytes), 128)
+        self._check(self.lib.gpupcg_comm_init(self.h, rank, nRanks, buf))
+
+
+def plan_export(lowerAddr, upperAddr, nCells):
+    """Host-only schedule export (no GPU): dict with info, rowOld, slices (nSlices,4), Ucol, UfaceOld, Lidx, Lcol."""
+    lib = load_library()
+    l, u = _i32(lowerAddr), _i32(upperAddr)
+    info = PlanInfo()
+    rc = lib.gpupcg_plan_export(int(nCells), l.shape[0], _ip(l), _ip(u), C.byref(info), None, None, None, None, None, None)
+    if rc != 0:
+        raise GpuPcgError(rc, lib.gpupcg_last_error(None).decode())
+    d = info.as_dict()
+    rowOld = np.empty(max(1, d["nRows"]), dtype=np.int32)
+    slices = np.empty((max(1, d["nSlices"]), 4), dtype=np.int32)
+    Ucol = np.empty(max(1, d["entriesUpper"]), dtype=np.int32)
+    UfaceOld = np.empty_like(Ucol)
+    Lidx = np.empty(max(1, d["entriesLower"]), dtype=np.int32)
+    Lcol = np.empty_like(Lidx)
+    rc = lib.gpupcg_plan_export(int(nCells), l.shape[0], _ip(l), _ip(u), C.byref(info), _ip(rowOld), _ip(slices),
+                                _ip(Ucol), _ip(UfaceOld), _ip(Lidx), _ip(Lcol))
+    if rc != 0:
+        raise GpuPcgError(rc, lib.gpupcg_last_error(None).decode())
+    return dict(info=d, rowOld=rowOld[:d["nRows"]], slices=slices[:d["nSlices"]], Ucol=Ucol[:d["entriesUpper"]],
+                UfaceOld=UfaceOld[:d["entriesUpper"]], Lidx=Lidx[:d["entriesLower"]], Lcol=Lcol[:d["entriesLower"]])
+
+
+def comm_unique_id():
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    rc = lib.gpupcg_comm_unique_id(buf)
+    if rc != 0:
+        raise GpuPcgError(rc, "ncclGetUniqueId failed (is libnccl.so.2 loadable?)")
+    return buf.raw
+
+
+def device_report(device=0):
+    lib = load_library()
+    buf = C.create_string_buffer(256)
+    rc = lib.gpupcg_device_report(device, buf, 256)
+    if rc != 0:
+        raise GpuPcgError(rc, "no CUDA device %d" % device)
+    return buf.value.decode()

@@ -1,0 +1,68 @@
+"""Synthetic benchmark inputs at the lduMatrix::solver boundary.
+
+cantilever_system() writes down, in closed form, the scalar LDU system that the first outer iteration
+of unsTotalLagrangianStress::evolve() (unsTotalLagrangianStress.C:846-859) hands to the solver for the
+loaded displacement component on the uniform orthogonal hex cantilever: -laplacian(2mu+lambda, D) with
+fixedDisplacement (0 0 0) at x=0, tractionDisplacement (0 0 tz) at x=L, traction-free sides, D0 = 0,
+gradDf = 0 (so every explicit term vanishes and deltaCoeffs = 1/h exactly).  It is an INPUT generator
+for solver tests and the roofline runs; the general assembly (non-orthogonal, explicit terms) is the
+GPU assembly path and its oracle.
+"""
+import numpy as np
+
+from .meshes import hex_ldu
+
+STEEL = dict(E=2.0e11, nu=0.3, rho=7854.0)      # run/stressFoam/plateHole/plateHole/constant/rheologyProperties:19-25
+
+
+def lame(E, nu, planeStress=False):
+    """constitutiveModel::mu / lambda (constitutiveModel.C:193-257)."""
+    mu = E/(2.0*(1.0 + nu))
+    if planeStress:
+        lam = nu*E/((1.0 + nu)*(1.0 - nu))
+    else:
+        lam = nu*E/((1.0 + nu)*(1.0 - 2.0*nu))
+    return mu, lam
+
+
+def cantilever_system(nx, ny, nz, L=2.0, W=0.5, H=1.0, E=STEEL["E"], nu=STEEL["nu"], tz=-1.0e4):
+    """Returns dict(l, u, diag, upper, b, nCells) for the z-displacement component."""
+    mu, lam = lame(E, nu)
+    gamma = 2.0*mu + lam
+    hx, hy, hz = L/nx, W/ny, H/nz
+    l, u = hex_ldu(nx, ny, nz)
+    n = nx*ny*nz
+    d = u.astype(np.int64) - l
+    # gamma*|Sf|*deltaCoeffs per direction
+    cx = gamma*(hy*hz)/hx
+    cy = gamma*(hx*hz)/hy
+    cz = gamma*(hx*hy)/hz
+    mx = d == 1
+    my = (d == nx) & ~mx & (ny > 1)
+    coef = np.where(mx, cx, np.where(my, cy, cz))
+    upper = -coef                                   # A = -laplacian  (A == B  ->  A - B)
+    # negSumDiag (owner pass then neighbour pass; bincount sums each bin in input order)
+    diag = np.bincount(l, weights=coef, minlength=n) + np.bincount(u, weights=coef, minlength=n)
+    c = np.arange(n, dtype=np.int64)
+    i = c % nx
+    # fixedDisplacement at x = 0: internalCoeffs = gamma*|Sf|*deltaCoeffs_b, deltaCoeffs_b = 1/(hx/2)
+    diag[i == 0] += gamma*(hy*hz)/(0.5*hx)
+    b = np.zeros(n, dtype=np.float64)
+    # tractionDisplacement at x = L: boundaryCoeffs = gamma*|Sf|*gradient, gradient = t/(2mu+lambda)
+    b[i == nx - 1] += gamma*(hy*hz)*(tz/gamma)
+    return dict(l=l, u=u, diag=diag, upper=upper, b=b, nCells=n, gamma=gamma)
+
+
+def amul_bytes(nCells, nFaces):
+    """Algorithmic bytes of one lduMatrix::Amul: 8(diag+x+Ax)N + (8+4+4)F."""
+    return 24*nCells + 16*nFaces
+
+
+def dic_bytes(nCells, nFaces):
+    """DIC precondition, forward + backward: 8(rD+rA+wA)N + 2(8+4+4)F."""
+    return 24*nCells + 32*nFaces
+
+
+def pcg_iteration_bytes(nCells, nFaces):
+    """One PCG iteration, reference data movement (unfused): Amul + DIC + 2 dots + pA update + x/r update."""
+    return amul_bytes(nCells, nFaces) + dic_bytes(nCells, nFaces) + 16*nCells + 24*nCells + 16*nCells + 48*nCells

@@ -1,0 +1,174 @@
+/*
+ * gpupcg.h -- C ABI of libgpupcg_cuda.so, the B200 (sm_100a) implementation of
+ * the segregated finite-volume displacement-equation solve that stressFoam,
+ * thermalStressFoam and the solid side of fsiFoam share.
+ *
+ * This header is the drop-in boundary.  Nothing in it is a foam-extend or a
+ * torch type: plain pointers, sizes and PODs, callable from C, C++, ctypes.
+ * Every entry point replaces one foam-extend-3.1 interface that the reference
+ * (chnrdu/fluidStructureInteraction) reaches through DEqn.solve():
+ *
+ *   reference call site                                  replaced interface [EXT = foam-extend-3.1]
+ *   ---------------------------------------------------  --------------------------------------------
+ *   unsTotalLagrangianStress.C:908  DEqn.solve()          fvMatrix<vector>::solve -> lduMatrix::solver::New
+ *   unsTotalLagrangianStressSolve.C:378,560               (same)
+ *   thermalStressFoam/TEqn.H:15     TEqn.solve()          fvScalarMatrix::solve   -> lduMatrix::solver::New
+ *   consistentIcoFlow.C:224         pEqn.solve()          (same)
+ *   run/.../system/fvSolution  "solver PCG; preconditioner DIC;"   PCG::solve + DICPreconditioner
+ *
+ * (paths relative to /root/reference/src/fluidStructureInteraction/stressModels/
+ *  unsTotalLagrangianStress/ unless they start with a directory name.)
+ *
+ * Threading: one handle per (process, GPU, lduAddressing).  Calls on a handle
+ * are synchronous with respect to the caller unless stated; a handle is not
+ * re-entrant (foam-extend calls a solver from one thread per MPI rank).
+ * Errors: every function returns 0 (GPUPCG_OK) or a negative code; the text is
+ * available from gpupcg_last_error().  No C++ exception crosses this boundary.
+ * There is no CPU fallback: without a usable sm_100 device gpupcg_create fails.
+ */
+#ifndef GPUPCG_H
+#define GPUPCG_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPUPCG_OK              0
+#define GPUPCG_ERR_ARG        -1   /* NULL / negative size / inconsistent arguments          */
+#define GPUPCG_ERR_ORDERING   -2   /* lowerAddr/upperAddr not in upper-triangular order      */
+#define GPUPCG_ERR_CUDA       -3   /* CUDA runtime error (text in gpupcg_last_error)         */
+#define GPUPCG_ERR_NODEVICE   -4   /* no CUDA device / not an sm_100 class device            */
+#define GPUPCG_ERR_STATE      -5   /* call sequence error (e.g. solve before set_matrix)     */
+#define GPUPCG_ERR_NCCL       -6   /* communicator error                                     */
+#define GPUPCG_ERR_UNSUPPORTED -7  /* asymmetric matrix, unknown preconditioner, ...         */
+
+typedef struct gpupcg_handle_s* gpupcg_handle;
+
+/* Mirror of lduMatrix::solverPerformance [EXT lduMatrix.H] plus timing. */
+typedef struct gpupcg_perf
+{
+    double initialResidual;
+    double finalResidual;
+    double normFactor;
+    int    nIterations;
+    int    converged;
+    int    singular;
+    int    reserved;
+    double solve_ms;        /* device time of the solve (CUDA events on the handle's stream) */
+    double h2d_ms;          /* host->device staging inside the call (0 for *_device entry points) */
+    double d2h_ms;
+} gpupcg_perf;
+
+/* Static description of what create() built: the wavefront schedule. */
+typedef struct gpupcg_plan_info
+{
+    int       nCells;
+    int       nFaces;
+    int       nRows;            /* rows after per-level padding to the warp width  */
+    int       nSlices;          /* nRows / 32                                      */
+    int       nLevels;          /* length of the DIC dependency chain              */
+    int       maxLevelRows;
+    long long entriesUpper;     /* SELL-32 storage incl. padding, owner side       */
+    long long entriesLower;     /* SELL-32 storage incl. padding, neighbour side   */
+    int       nInterfaceFaces;  /* coupled patch faces                             */
+    int       nInterfaces;
+    int       sweepGrid;        /* CTAs of the persistent DIC kernel               */
+    int       streamGrid;       /* CTAs of the streaming kernels                   */
+    int       numSMs;
+    int       reserved;
+} gpupcg_plan_info;
+
+/* ---- life cycle ----------------------------------------------------------------------------
+ * gpupcg_create: analogue of constructing lduAddressing-derived data once per mesh
+ * ([EXT] lduAddressing::{ownerStartAddr,losortAddr,losortStartAddr} + the DIC level schedule).
+ *   lowerAddr/upperAddr : lduAddr().lowerAddr()/upperAddr(), int32, upper-triangular order.
+ *   nPatches            : number of COUPLED interfaces (processor patches) of this sub-domain.
+ *   patchSizes[p]       : faces in interface p;  patchFaceCells[p] : lduAddr().patchAddr(p).
+ *   patchNbrRank[p]     : rank owning the other side (processorFvPatch::neighbProcNo()).
+ * The host arrays are copied; nothing is retained.                                            */
+int gpupcg_create(gpupcg_handle* h, int device,
+                  int nCells, int nFaces,
+                  const int* lowerAddr, const int* upperAddr,
+                  int nPatches, const int* patchSizes,
+                  const int* const* patchFaceCells, const int* patchNbrRank);
+int gpupcg_destroy(gpupcg_handle h);
+const char* gpupcg_last_error(gpupcg_handle h);   /* h may be NULL: last create() error */
+int gpupcg_get_plan_info(gpupcg_handle h, gpupcg_plan_info* info);
+
+/* Run all later work of this handle on an externally owned cudaStream_t (e.g. torch's
+ * current stream, so that the caller's CUDA events bracket the kernels).  NULL restores the
+ * handle's own stream.                                                                       */
+int gpupcg_set_stream(gpupcg_handle h, void* cudaStream);
+
+/* ---- matrix ---------------------------------------------------------------------------------
+ * gpupcg_set_matrix: the lduMatrix the solver object was constructed with:
+ *   diag = matrix.diag() (after fvMatrix::addBoundaryDiag for this component),
+ *   upper = matrix.upper(); lower must be NULL or == upper (symMatrix table only),
+ *   patchBouCoeffs[p] = coupleBouCoeffs[p] (interface coefficients used by Amul).
+ * upper == NULL keeps the coefficients of the previous call (the three components of one
+ * fvMatrix<vector>::solve share upper; only diag differs).  Host pointers.                    */
+int gpupcg_set_matrix(gpupcg_handle h, const double* diag, const double* upper,
+                      const double* lower_or_null, const double* const* patchBouCoeffs);
+/* Same with device pointers in the ORIGINAL cell / face order (output of gpupcg_assemble_*). */
+int gpupcg_set_matrix_device(gpupcg_handle h, const double* d_diag, const double* d_upper,
+                             const double* d_patchBouCoeffsConcat);
+
+/* ---- solve ----------------------------------------------------------------------------------
+ * gpupcg_solve == PCG::solve(x, b, cmpt) with the DIC preconditioner [EXT PCG.C,
+ * DICPreconditioner.C]; controls are lduMatrix::solver::readControls' tolerance, relTol,
+ * minIter, maxIter.  x is in/out, b is const, both double[nCells] on the HOST in the caller's
+ * cell order.  history (optional, host) receives finalResidual after every iteration, up to
+ * historyCap entries.  Multi-rank: collective over the communicator given to comm_init.       */
+int gpupcg_solve(gpupcg_handle h, double* x, const double* b,
+                 double tolerance, double relTol, int minIter, int maxIter,
+                 gpupcg_perf* perf, double* history_or_null, int historyCap);
+/* x, b are DEVICE pointers in the original cell order. */
+int gpupcg_solve_device(gpupcg_handle h, double* d_x, const double* d_b,
+                        double tolerance, double relTol, int minIter, int maxIter,
+                        gpupcg_perf* perf, double* history_or_null, int historyCap);
+
+/* ---- kernels in isolation (parity tests and roofline runs) -----------------------------------
+ * gpupcg_amul       : lduMatrix::Amul(Ax, x, coupleBouCoeffs, interfaces, cmpt)  [EXT lduMatrixATmul.C]
+ *                     xNbr_or_null = concatenated received patch-neighbour values (single-rank tests).
+ * gpupcg_dic_factor : DICPreconditioner::calcReciprocalD -> rD                    [EXT DICPreconditioner.C]
+ * gpupcg_precondition: DICPreconditioner::precondition(wA, rA)
+ * All pointers are HOST arrays in the caller's order.                                          */
+int gpupcg_amul(gpupcg_handle h, const double* x, double* Ax, const double* xNbr_or_null);
+int gpupcg_dic_factor(gpupcg_handle h, double* rD_out);
+int gpupcg_precondition(gpupcg_handle h, const double* rA, double* wA);
+
+/* Time `reps` back-to-back launches of one kernel class on resident data with CUDA events on
+ * the handle's stream; flushL2 != 0 writes a 256 MiB scratch buffer before every launch
+ * (excluded from the time).  which: 0 Amul, 1 DIC precondition (forward+backward),
+ * 2 pA update, 3 x/r update + residual norm, 4 DIC factor.  Returns mean ms per launch.        */
+int gpupcg_time_kernel(gpupcg_handle h, int which, int reps, int flushL2, double* ms_per_launch);
+
+/* ---- multi-GPU -------------------------------------------------------------------------------
+ * One handle per rank/GPU (decomposePar sub-domain).  ncclUniqueId is the 128-byte
+ * ncclUniqueId obtained on rank 0 (gpupcg_comm_unique_id) and broadcast by the host side
+ * (Pstream / torch.distributed / a file).  Halo swaps (processorFvPatchField::
+ * initInterfaceMatrixUpdate/updateInterfaceMatrix) and gSumProd/gSumMag/gAverage reductions
+ * then run over NCCL on the handle's stream.                                                   */
+int gpupcg_comm_unique_id(void* ncclUniqueId_128bytes);
+int gpupcg_comm_init(gpupcg_handle h, int rank, int nRanks, const void* ncclUniqueId_128bytes);
+
+/* ---- host memory helpers ----------------------------------------------------------------------
+ * Page-lock caller-owned arrays (scalarField storage) so that the staging copies are DMA.       */
+int gpupcg_host_register(void* ptr, unsigned long long bytes);
+int gpupcg_host_unregister(void* ptr);
+
+/* Host-only (no GPU needed): build the wavefront / SELL-32 schedule create() would build and copy it
+ * out, so that CPU tests can check the schedule against the reference face order.  Call once with
+ * NULL arrays to obtain the sizes in *info, then again with arrays of nRows, 4*nSlices,
+ * entriesUpper (x2) and entriesLower (x2) ints.                                                   */
+int gpupcg_plan_export(int nCells, int nFaces, const int* lowerAddr, const int* upperAddr,
+                       gpupcg_plan_info* info, int* rowOld, int* sliceInfo,
+                       int* Ucol, int* UfaceOld, int* Lidx, int* Lcol);
+
+/* Library / device report: fills a short text (device name, SM count, cc) into buf. */
+int gpupcg_device_report(int device, char* buf, int bufLen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPUPCG_H */

@@ -1,0 +1,176 @@
+"""ctypes binding of oracle/liboracle.so (gcc -O3 -ffp-contract=off; see oracle/Makefile)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+
+
+class Domain(C.Structure):
+    _fields_ = [
+        ("nCells", C.c_int), ("nFaces", C.c_int),
+        ("lowerAddr", ip), ("upperAddr", ip),
+        ("diag", dp), ("upper", dp),
+        ("nPatches", C.c_int),
+        ("patchStart", ip), ("patchFaceCells", ip), ("patchBouCoeffs", dp),
+        ("patchNbrDomain", ip), ("patchNbrPatch", ip),
+        ("x", dp), ("b", dp),
+    ]
+
+
+class Perf(C.Structure):
+    _fields_ = [
+        ("initialResidual", C.c_double), ("finalResidual", C.c_double), ("normFactor", C.c_double),
+        ("nIterations", C.c_int), ("converged", C.c_int), ("singular", C.c_int),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def load(build=True):
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build and not os.path.exists(LIB_PATH):
+        subprocess.check_call(["make", "-C", _HERE], stdout=subprocess.DEVNULL)
+    lib = C.CDLL(LIB_PATH)
+    lib.orc_amul.restype = None
+    lib.orc_amul.argtypes = [C.c_int, C.c_int, ip, ip, dp, dp, dp, dp, C.c_int, ip, ip, dp, dp]
+    lib.orc_sumA.restype = None
+    lib.orc_sumA.argtypes = [C.c_int, C.c_int, ip, ip, dp, dp, dp, C.c_int, ip, ip, dp, dp]
+    lib.orc_dic_calc_reciprocal_d.restype = None
+    lib.orc_dic_calc_reciprocal_d.argtypes = [C.c_int, C.c_int, ip, ip, dp, dp, dp]
+    lib.orc_dic_precondition.restype = None
+    lib.orc_dic_precondition.argtypes = [C.c_int, C.c_int, ip, ip, dp, dp, dp, dp]
+    lib.orc_pcg_solve.restype = C.c_int
+    lib.orc_pcg_solve.argtypes = [C.c_int, C.POINTER(Domain), C.c_double, C.c_double, C.c_int, C.c_int,
+                                  C.POINTER(Perf), dp, C.c_int]
+    lib.orc_bench_amul.restype = C.c_double
+    lib.orc_bench_amul.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, dp, dp, dp, dp]
+    lib.orc_bench_dic.restype = C.c_double
+    lib.orc_bench_dic.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, dp, dp, dp, dp]
+    lib.orc_num_threads.restype = C.c_int
+    lib.orc_set_num_threads.argtypes = [C.c_int]
+    _lib = lib
+    return lib
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _dp(a):
+    return a.ctypes.data_as(dp)
+
+
+def _ip(a):
+    return a.ctypes.data_as(ip)
+
+
+def _patch_arrays(patchFaceCells, patchBouCoeffs):
+    sizes = [len(fc) for fc in patchFaceCells]
+    start = _i(np.concatenate([[0], np.cumsum(sizes)]))
+    fc = _i(np.concatenate(patchFaceCells)) if sizes and sum(sizes) else _i(np.zeros(1))
+    bc = _f(np.concatenate(patchBouCoeffs)) if sizes and sum(sizes) else _f(np.zeros(1))
+    return start, fc, bc
+
+
+def amul(l, u, diag, upper, x, patchFaceCells=(), patchBouCoeffs=(), xNbr=None):
+    lib = load()
+    l, u, diag, upper, x = _i(l), _i(u), _f(diag), _f(upper), _f(x)
+    Ax = np.empty_like(x)
+    start, fc, bc = _patch_arrays(list(patchFaceCells), list(patchBouCoeffs))
+    xn = _f(xNbr) if xNbr is not None else _f(np.zeros(max(1, int(start[-1]))))
+    lib.orc_amul(x.shape[0], l.shape[0], _ip(l), _ip(u), _dp(diag), _dp(upper), _dp(x), _dp(Ax),
+                 len(patchFaceCells), _ip(start), _ip(fc), _dp(bc), _dp(xn))
+    return Ax
+
+
+def dic_factor(l, u, diag, upper):
+    lib = load()
+    l, u, diag, upper = _i(l), _i(u), _f(diag), _f(upper)
+    rD = np.empty_like(diag)
+    lib.orc_dic_calc_reciprocal_d(diag.shape[0], l.shape[0], _ip(l), _ip(u), _dp(diag), _dp(upper), _dp(rD))
+    return rD
+
+
+def precondition(l, u, upper, rD, rA):
+    lib = load()
+    l, u, upper, rD, rA = _i(l), _i(u), _f(upper), _f(rD), _f(rA)
+    wA = np.empty_like(rA)
+    lib.orc_dic_precondition(rA.shape[0], l.shape[0], _ip(l), _ip(u), _dp(upper), _dp(rD), _dp(rA), _dp(wA))
+    return wA
+
+
+def pcg_solve_multi(domains, tolerance=1e-6, relTol=0.0, minIter=0, maxIter=1000):
+    """domains: list of dict(l, u, diag, upper, x, b, patchFaceCells=[], patchBouCoeffs=[], patchNbrDomain=[],
+    patchNbrPatch=[]).  x arrays are updated in place.  Returns (perf dict, residual history)."""
+    lib = load()
+    nD = len(domains)
+    arr = (Domain * nD)()
+    keep = []
+    for d, dom in enumerate(domains):
+        l, u, diag, upper = _i(dom["l"]), _i(dom["u"]), _f(dom["diag"]), _f(dom["upper"])
+        x = dom["x"]
+        assert isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.c_contiguous
+        b = _f(dom["b"])
+        pfc = list(dom.get("patchFaceCells", []))
+        pbc = list(dom.get("patchBouCoeffs", []))
+        start, fc, bc = _patch_arrays(pfc, pbc)
+        nbrD = _i(dom.get("patchNbrDomain", [])) if pfc else _i(np.zeros(1))
+        nbrP = _i(dom.get("patchNbrPatch", [])) if pfc else _i(np.zeros(1))
+        keep.append((l, u, diag, upper, b, start, fc, bc, nbrD, nbrP))
+        D = arr[d]
+        D.nCells, D.nFaces = x.shape[0], l.shape[0]
+        D.lowerAddr, D.upperAddr, D.diag, D.upper = _ip(l), _ip(u), _dp(diag), _dp(upper)
+        D.nPatches = len(pfc)
+        D.patchStart, D.patchFaceCells, D.patchBouCoeffs = _ip(start), _ip(fc), _dp(bc)
+        D.patchNbrDomain, D.patchNbrPatch = _ip(nbrD), _ip(nbrP)
+        D.x, D.b = _dp(x), _dp(b)
+    perf = Perf()
+    hist = np.zeros(max(1, maxIter), dtype=np.float64)
+    rc = lib.orc_pcg_solve(nD, arr, tolerance, relTol, minIter, maxIter, C.byref(perf), _dp(hist), hist.shape[0])
+    if rc != 0:
+        raise RuntimeError("orc_pcg_solve failed: %d" % rc)
+    p = perf.as_dict()
+    return p, hist[:p["nIterations"]].copy()
+
+
+def pcg_solve(l, u, diag, upper, x, b, tolerance=1e-6, relTol=0.0, minIter=0, maxIter=1000):
+    return pcg_solve_multi([dict(l=l, u=u, diag=diag, upper=upper, x=x, b=b)], tolerance, relTol, minIter, maxIter)
+
+
+def bench_amul(reps, l, u, diag, upper, x):
+    lib = load()
+    l, u, diag, upper, x = _i(l), _i(u), _f(diag), _f(upper), _f(x)
+    Ax = np.empty_like(x)
+    return lib.orc_bench_amul(reps, x.shape[0], l.shape[0], _ip(l), _ip(u), _dp(diag), _dp(upper), _dp(x), _dp(Ax))
+
+
+def bench_dic(reps, l, u, upper, rD, rA):
+    lib = load()
+    l, u, upper, rD, rA = _i(l), _i(u), _f(upper), _f(rD), _f(rA)
+    wA = np.empty_like(rA)
+    return lib.orc_bench_dic(reps, rA.shape[0], l.shape[0], _ip(l), _ip(u), _dp(upper), _dp(rD), _dp(rA), _dp(wA))
+
+
+def num_threads():
+    return load().orc_num_threads()
+
+
+def set_num_threads(n):
+    load().orc_set_num_threads(int(n))

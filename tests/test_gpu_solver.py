@@ -1,0 +1,181 @@
+"""GPU parity tests (-m gpu): the CUDA path through the C ABI against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): Amul / DIC factor / DIC apply bit-exact (same operand order, no FMA);
+PCG: identical iteration counts, per-iteration residual history within 1e-10 relative, final field within
+1e-9 relative L-infinity (only the global reductions are re-associated on the GPU)."""
+import numpy as np
+import pytest
+
+import oracle
+import fluidstructureinteraction_b200 as pkg
+from fluidstructureinteraction_b200 import cases, meshes
+from conftest import FIXTURE_MESHES, load_fixture_mesh, load_golden, synthetic_matrix
+
+pytestmark = pytest.mark.gpu
+
+HIST_RTOL = 1e-10
+FIELD_RTOL = 1e-9
+
+
+def check_kernels(l, u, n, diag, upper, b):
+    g = pkg.GpuPCG(l, u, n)
+    g.set_matrix(diag, upper)
+    xt = np.sin(0.37*np.arange(n))
+    assert np.array_equal(g.amul(xt), oracle.amul(l, u, diag, upper, xt))
+    rD = oracle.dic_factor(l, u, diag, upper)
+    assert np.array_equal(g.dic_factor(), rD)
+    assert np.array_equal(g.precondition(b), oracle.precondition(l, u, upper, rD, b))
+    return g
+
+
+def check_solve(g, l, u, diag, upper, b, x0, tol, relTol, minIter=0, maxIter=1000):
+    xg, xc = x0.copy(), x0.copy()
+    pg, hg = g.solve(xg, b, tol, relTol, minIter, maxIter)
+    pc, hc = oracle.pcg_solve(l, u, diag, upper, xc, b, tol, relTol, minIter, maxIter)
+    assert pg["nIterations"] == pc["nIterations"], (pg, pc)
+    assert pg["converged"] == pc["converged"] and pg["singular"] == pc["singular"]
+    assert pg["normFactor"] == pytest.approx(pc["normFactor"], rel=1e-13)
+    assert pg["initialResidual"] == pytest.approx(pc["initialResidual"], rel=HIST_RTOL, abs=1e-300)
+    if len(hc):
+        assert np.max(np.abs(hg - hc)/np.abs(hc)) < HIST_RTOL
+        assert pg["finalResidual"] == pytest.approx(pc["finalResidual"], rel=HIST_RTOL)
+    scale = np.max(np.abs(xc))
+    assert np.max(np.abs(xg - xc)) <= FIELD_RTOL*scale + 1e-300
+    return pg, pc
+
+
+@pytest.mark.parametrize("dims", [(1, 1, 1), (2, 1, 1), (33, 1, 1), (5, 4, 3), (24, 8, 12), (40, 10, 20)])
+def test_hex_kernels_and_solve(dims):
+    nx, ny, nz = dims
+    l, u = meshes.hex_ldu(nx, ny, nz)
+    n = nx*ny*nz
+    diag, upper, b, x0 = synthetic_matrix(l, u, n, 11)
+    g = check_kernels(l, u, n, diag, upper, b)
+    check_solve(g, l, u, diag, upper, b, x0, 1e-9, 0.0)
+    check_solve(g, l, u, diag, upper, b, x0, 1e-9, 0.01)
+    g.close()
+
+
+@pytest.mark.parametrize("name", FIXTURE_MESHES)
+def test_shipped_meshes_against_golden(name):
+    """The reference's own polyMeshes: CUDA path vs the committed golden vectors (and the live oracle)."""
+    m = load_fixture_mesh(name)
+    gold = load_golden(name)
+    l, u = m.lower_upper()
+    diag, upper, b, x0 = synthetic_matrix(l, u, m.nCells, int(gold["seed"]))
+    g = check_kernels(l, u, m.nCells, diag, upper, b)
+    xt = np.sin(0.37*np.arange(m.nCells))
+    assert np.array_equal(g.amul(xt), gold["Ax"])
+    assert np.array_equal(g.dic_factor(), gold["rD"])
+    assert np.array_equal(g.precondition(b), gold["wA"])
+    x = x0.copy()
+    pg, hg = g.solve(x, b, 1e-9, 0.0)
+    assert pg["nIterations"] == int(gold["nIterations"])
+    assert np.max(np.abs(hg - gold["history"])/gold["history"]) < HIST_RTOL
+    assert np.max(np.abs(x - gold["x"])) <= FIELD_RTOL*np.max(np.abs(gold["x"]))
+    # shipped fvSolution controls (beamInCrossFlow/solid/system/fvSolution:17-32): tol 1e-9, relTol 0.1
+    check_solve(g, l, u, diag, upper, b, x0, 1e-9, 0.1)
+    g.close()
+
+
+def test_cantilever_1M_slice_and_controls():
+    """The benchmark system (steel cantilever, traction load) at a size the oracle solves in seconds."""
+    s = cases.cantilever_system(100, 25, 50)        # 125 k cells, same aspect as the 1 M case
+    l, u, diag, upper, b, n = s["l"], s["u"], s["diag"], s["upper"], s["b"], s["nCells"]
+    g = check_kernels(l, u, n, diag, upper, b)
+    x0 = np.zeros(n)
+    pg, pc = check_solve(g, l, u, diag, upper, b, x0, 1e-9, 0.01)      # plateHole controls
+    assert pg["nIterations"] > 10
+    check_solve(g, l, u, diag, upper, b, x0, 1e-9, 0.1)                # FSI solid controls
+    # edge cases of stop(): zero rhs, maxIter cap, minIter
+    pz, _ = g.solve(np.zeros(n), np.zeros(n), 1e-9, 0.01)
+    assert pz["nIterations"] == 0 and pz["converged"] == 1 and pz["initialResidual"] == 0.0
+    check_solve(g, l, u, diag, upper, b, x0, 1e-30, 0.0, maxIter=5)
+    check_solve(g, l, u, diag, upper, b, x0, 1e-9, 0.999999, minIter=3)
+    check_solve(g, l, u, diag, upper, b, x0, 1e-9, 0.0, maxIter=13)    # not a multiple of the check batch
+    g.close()
+
+
+def test_component_reuse_upper_null():
+    """fvMatrix<vector>::solve: three component solves share upper, only diag/b change (upper=None)."""
+    s = cases.cantilever_system(20, 6, 10)
+    l, u, diag, upper, b, n = s["l"], s["u"], s["diag"], s["upper"], s["b"], s["nCells"]
+    g = pkg.GpuPCG(l, u, n)
+    g.set_matrix(diag, upper)
+    rng = np.random.default_rng(5)
+    for cmpt in range(3):
+        dc = diag*(1.0 + 0.1*cmpt) + rng.uniform(0, 1e6, n)
+        bc = rng.standard_normal(n)
+        g.set_matrix(dc, None)
+        check_solve(g, l, u, dc, upper, bc, np.zeros(n), 1e-9, 0.01)
+    g.close()
+
+
+def test_singular_and_errors():
+    s = cases.cantilever_system(8, 4, 4)
+    l, u, diag, upper, b, n = s["l"], s["u"], s["diag"], s["upper"], s["b"], s["nCells"]
+    g = pkg.GpuPCG(l, u, n)
+    with pytest.raises(pkg.GpuPcgError) as e:
+        g.solve(np.zeros(n), b)
+    assert e.value.code == -5                       # solve before set_matrix
+    # wApA underflows to 0 -> checkSingularity stops the loop before x is touched
+    g.set_matrix(np.ones(n), np.zeros_like(upper))
+    pg, pc = check_solve(g, l, u, np.ones(n), np.zeros_like(upper), np.full(n, 1e-301), np.zeros(n), 0.0, 0.0)
+    assert pg["singular"] == 1 and pg["nIterations"] == 0
+    with pytest.raises(pkg.GpuPcgError) as e:
+        g.set_matrix(diag, upper, lower=upper*0.5)
+    assert e.value.code == -7                       # asymmetric
+    g.close()
+    with pytest.raises(pkg.GpuPcgError) as e:
+        pkg.GpuPCG(np.array([0, 1, 0], dtype=np.int32), np.array([1, 2, 2], dtype=np.int32), 3)
+    assert e.value.code == -2
+
+
+def test_tet_mesh_with_jitter():
+    m = meshes.tet_box(10, 4, 6, jitter=0.15)
+    l, u = m.lower_upper()
+    diag, upper, b, x0 = synthetic_matrix(l, u, m.nCells, 21)
+    g = check_kernels(l, u, m.nCells, diag, upper, b)
+    check_solve(g, l, u, diag, upper, b, x0, 1e-9, 0.0)
+    g.close()
+
+
+def test_amul_with_interface_coefficients():
+    """Processor-patch term of Amul with explicit neighbour values: Ax[fc[i]] -= bou[i]*xNbr[i] in patch order,
+    including a cell that touches two patches and a patch that hits one cell twice."""
+    s = cases.cantilever_system(6, 4, 4)
+    l, u, diag, upper, n = s["l"], s["u"], s["diag"], s["upper"], s["nCells"]
+    fcs = [np.array([0, 5, 5, 17], dtype=np.int32), np.array([5, 95, 3], dtype=np.int32)]
+    rng = np.random.default_rng(9)
+    bou = [rng.uniform(1, 2, fc.shape[0])*1e9 for fc in fcs]
+    xn = rng.standard_normal(sum(fc.shape[0] for fc in fcs))
+    g = pkg.GpuPCG(l, u, n, patchFaceCells=fcs, patchNbrRank=[1, 2])
+    g.set_matrix(diag, upper, patchBouCoeffs=bou)
+    xt = np.sin(0.37*np.arange(n))
+    ref = oracle.amul(l, u, diag, upper, xt, fcs, bou, xn)
+    assert np.array_equal(g.amul(xt, xn), ref)
+    g.close()
+
+
+def test_large_size_properties():
+    """At the full 1 M-cell benchmark size: size-independent properties instead of the (slow) oracle solve --
+    Amul linearity/symmetry, DIC exactness on the factor, and the true residual of the returned solution."""
+    s = cases.cantilever_system(200, 50, 100)
+    l, u, diag, upper, b, n = s["l"], s["u"], s["diag"], s["upper"], s["b"], s["nCells"]
+    g = pkg.GpuPCG(l, u, n)
+    g.set_matrix(diag, upper)
+    rng = np.random.default_rng(1)
+    v, w = rng.standard_normal(n), rng.standard_normal(n)
+    Av, Aw = g.amul(v), g.amul(w)
+    assert abs(np.dot(w, Av) - np.dot(v, Aw)) <= 1e-12*abs(np.dot(w, Av))          # symmetry
+    assert np.array_equal(Av, oracle.amul(l, u, diag, upper, v))                      # still bit-exact (oracle Amul is fast)
+    rD = g.dic_factor()
+    assert np.array_equal(rD, oracle.dic_factor(l, u, diag, upper))
+    assert np.array_equal(g.precondition(v), oracle.precondition(l, u, upper, rD, v))
+    x = np.zeros(n)
+    pg, hg = g.solve(x, b, 1e-9, 0.01)
+    assert pg["converged"] == 1 and 0 < pg["nIterations"] < 1000
+    r = b - g.amul(x)
+    assert np.sum(np.abs(r))/pg["normFactor"] == pytest.approx(pg["finalResidual"], rel=1e-6)
+    assert pg["finalResidual"] <= 0.01*pg["initialResidual"]
+    g.close()
