@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- D-equation PCG/DIC hot path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A STEP is one segregated D-equation solve, i.e. what one DEqn.solve() of unsTotalLagrangianStress::evolve()
+(unsTotalLagrangianStress.C:908) hands to the lduMatrix::solver boundary: three scalar PCG/DIC component
+solves (Dx, Dy, Dz) that share the laplacian coefficients, controls `tolerance 1e-9; relTol 0.01`
+(run/stressFoam/plateHole/plateHole/system/fvSolution:18-27), x0 = 0.
+
+Workload at N=1: BASELINE.json configs[1], the synthetic 3-D hex cantilever with 1 M cells (200x50x100),
+steel, fixedDisplacement at x=0, traction on x=L.  N>1: configs[2], the 64 M-cell (400^3... see --cells) box
+decomposed into one sub-domain per GPU with processor-patch halos and global reductions over NCCL.
+
+metric  : PCG cell-updates/s = cells x PCG iterations / time  (whole job, all ranks); solves/s beside it.
+value   : matrix, x0, b resident in HBM (gpupcg_set_matrix once, gpupcg_solve_device per component).
+e2e     : the same step through the reference-facing C-ABI calls with HOST buffers: gpupcg_set_matrix(diag,
+          upper) + gpupcg_solve(x, b) per component, pinned host memory, H2D/D2H inside the timed region.
+roofline: dominant kernel of the step by measured time, algorithmic bytes / CUDA-event time,
+          against MEASURED_PEAKS.json hbm_gbs; the Amul figure BASELINE.json names is in roofline_amul.
+cpu_baseline: the CPU oracle (port of the reference's foam-extend PCG/DIC loops, oracle/ldu_oracle.c) on a
+          bounded sample of the same system, serial.
+--impl reference: the oracle with every host core (one decomposePar-style sub-domain per thread).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+TOL, RELTOL = 1e-9, 0.01
+TRACTION = (0.5e4, 0.25e4, -1.0e4)          # all three components get a non-zero source
+METRIC = "D-eqn PCG cell-updates/s (cells x PCG iterations / s; 3 component solves per step)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", default=None, help="nx,ny,nz override (default: 200,50,100 at N=1; 400,400,400 at N>1)")
+    ap.add_argument("--cpu-maxiter", type=int, default=0,
+                    help="iteration cap of the bounded CPU sample (default: ~4e8 cell-updates per solve, 4..40)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_system(nx, ny, nz):
+    from fluidstructureinteraction_b200 import cases
+    s = cases.cantilever_system(nx, ny, nz, tz=1.0)       # unit traction; scaled per component below
+    return s
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm: the CPU oracle with all host threads (decomposed, one sub-domain per thread)
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args, nx, ny, nz):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from fluidstructureinteraction_b200 import decompose
+    cores = os.cpu_count() or 1
+    threads = 1
+    for t in (8, 4, 2, 1):
+        if t <= cores:
+            threads = t
+            break
+    s = build_system(nx, ny, nz)
+    n = s["nCells"]
+    px, py, pz = decompose.proc_grid(threads)
+    cellProc = decompose.simple_cell_proc(nx, ny, nz, px, py, pz)
+    oracle.set_num_threads(threads)
+    b = s["b"]*TRACTION[2]
+    times, iters = [], []
+    for it in range(args.warmup + args.steps):
+        doms = decompose.decompose_ldu(s["l"], s["u"], s["diag"], s["upper"], b, np.zeros(n), cellProc, threads)
+        t0 = time.perf_counter()
+        perf, _ = oracle.pcg_solve_multi(doms, TOL, RELTOL, 0, args.cpu_maxiter)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt); iters.append(perf["nIterations"])
+    tot = float(np.sum(times))
+    value = n*float(np.sum(iters))/tot
+    sample = ("one Dz component solve of the same %dx%dx%d system per step, capped at %d PCG iterations, "
+              "decomposed simple(%d %d %d), one sub-domain per OpenMP thread" % (nx, ny, nz, args.cpu_maxiter, px, py, pz))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3*tot/args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(nx, ny, nz, args.gpus), "cells": n, "tolerance": TOL, "relTol": RELTOL},
+        "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "iterations_per_step": float(np.mean(iters)), "host_cores": cores,
+    }
+    print(json.dumps(line))
+
+
+def workload_name(nx, ny, nz, gpus):
+    if gpus == 1:
+        return "configs[1]: synthetic 3-D hex cantilever %dx%dx%d = %d cells, linear-elastic D equation" % (nx, ny, nz, nx*ny*nz)
+    return "configs[2]: synthetic hex cantilever %dx%dx%d = %d cells decomposed simple over %d B200" % (nx, ny, nz, nx*ny*nz, gpus)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_baseline(s, n, maxiter):
+    import oracle
+    oracle.set_num_threads(1)
+    x = np.zeros(n)
+    t0 = time.perf_counter()
+    perf, _ = oracle.pcg_solve(s["l"], s["u"], s["diag"], s["upper"], x, s["b"]*TRACTION[2], TOL, RELTOL, 0, maxiter)
+    dt = time.perf_counter() - t0
+    return {"value": n*perf["nIterations"]/dt, "unit": "cell-updates/s", "cores": 1, "kind": "port",
+            "sample": "one Dz component solve of the same system, first %d PCG iterations (%.1f s), oracle/ldu_oracle.c serial"
+                      % (perf["nIterations"], dt),
+            "ms_per_iteration": 1e3*dt/max(1, perf["nIterations"])}
+
+
+def run_ours(args, nx, ny, nz):
+    import torch
+    import torch.distributed as dist
+    import fluidstructureinteraction_b200 as pkg
+    from fluidstructureinteraction_b200 import cases, decompose
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200: the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg.load_library()
+
+    s = build_system(nx, ny, nz)
+    nGlobal = s["nCells"]
+    if world > 1:
+        px, py, pz = decompose.proc_grid(world)
+        cellProc = decompose.simple_cell_proc(nx, ny, nz, px, py, pz)
+        dom = decompose.decompose_ldu(s["l"], s["u"], s["diag"], s["upper"], s["b"], np.zeros(nGlobal), cellProc, world)[rank]
+        g = pkg.GpuPCG(dom["l"], dom["u"], dom["cells"].shape[0], dom["patchFaceCells"], dom["patchNbrDomain"], device=local)
+        uid = [pkg.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        g.comm_init(rank, world, uid[0])
+        diag, upper, bunit, bou = dom["diag"], dom["upper"], dom["b"], dom["patchBouCoeffs"]
+        n = dom["cells"].shape[0]
+    else:
+        g = pkg.GpuPCG(s["l"], s["u"], nGlobal, device=local)
+        diag, upper, bunit, bou = s["diag"], s["upper"], s["b"], []
+        n = nGlobal
+    nF = upper.shape[0]
+    info = g.plan_info()
+    stream = torch.cuda.current_stream()
+    g.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm -------------------------------------------------------------------------------------
+    g.set_matrix(diag, upper, patchBouCoeffs=bou)
+    d_b = [torch.from_numpy(bunit*t).cuda() for t in TRACTION]
+    d_x = [torch.zeros(n, dtype=torch.float64, device="cuda") for _ in TRACTION]
+
+    def step_device():
+        its = 0
+        for c in range(3):
+            d_x[c].zero_()
+            perf, _ = g.solve_device(d_x[c].data_ptr(), d_b[c].data_ptr(), TOL, RELTOL, 0, 1000)
+            its += perf["nIterations"]
+        return its
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = g.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    iters = 0
+    for _ in range(args.steps):
+        iters += step_device()
+    e1.record()
+    barrier()
+    launches = g.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_dev = float(ms.item())
+
+    # ---- end-to-end arm: host buffers through gpupcg_set_matrix + gpupcg_solve ------------------------------------
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+
+    keep = []
+    _, h_diag = pinned(diag); keep.append(_)
+    _, h_upper = pinned(upper); keep.append(_)
+    h_b, h_x = [], []
+    for t in TRACTION:
+        tb, nb = pinned(bunit*t); keep.append(tb); h_b.append(nb)
+        tx, nxx = pinned(np.zeros(n)); keep.append(tx); h_x.append(nxx)
+
+    def step_e2e():
+        its = 0
+        for c in range(3):
+            g.set_matrix(h_diag, h_upper if c == 0 else None, patchBouCoeffs=bou)
+            h_x[c][:] = 0.0
+            perf, _ = g.solve(h_x[c], h_b[c], TOL, RELTOL, 0, 1000, history=False)
+            its += perf["nIterations"]
+        return its
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    e0.record()
+    iters_e2e = 0
+    for _ in range(args.steps):
+        iters_e2e += step_e2e()
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms2.item())
+    h2d = 3*8*n + 8*nF + 3*16*n
+    d2h = 3*8*n
+
+    # ---- per-kernel roofline (rank 0, live CUDA-event timing on the launching stream, L2 flushed) --------------
+    line = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        reps = 20
+        kb = {"amul": cases.amul_bytes(n, nF), "dic": cases.dic_bytes(n, nF), "p_update": 24*n, "xr_update": 48*n}
+        kern = {}
+        for k, nbytes in kb.items():
+            t = g.time_kernel(k, reps=reps, flushL2=True)
+            kern[k] = {"ms": t, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes/t/1e6, "frac": nbytes/t/1e6/peak}
+        tot = sum(v["ms"] for v in kern.values())
+        for v in kern.values():
+            v["share_of_iteration"] = v["ms"]/tot
+        dom_k = max(kern, key=lambda k: kern[k]["ms"])
+        names = {"amul": "k_amul (lduMatrix::Amul + wApA)", "dic": "k_dic_sweeps (DIC forward+backward + wArA)",
+                 "p_update": "k_p_update", "xr_update": "k_xr_update (+ sum|rA|)"}
+
+        def roof(k):
+            return {"kernel": names[k], "bound": "hbm", "achieved": kern[k]["achieved_gbs"], "peak": peak,
+                    "unit": "GB/s", "frac": kern[k]["frac"], "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": kern[k]["algorithmic_bytes"], "ms_per_launch": kern[k]["ms"],
+                    "share_of_iteration": kern[k]["share_of_iteration"]}
+
+        value = nGlobal*iters/(ms_dev*1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev/args.steps, "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(nx, ny, nz, world), "cells": nGlobal, "internal_faces": int(s["l"].shape[0]),
+                       "tolerance": TOL, "relTol": RELTOL, "solver": "gpuPCG", "preconditioner": "DIC",
+                       "parallelism": "1 sub-domain/GPU x %d" % world,
+                       "l2": "working set (%.0f MB) vs 126 MB L2: inputs larger than L2 at >= 1M cells; kernel timings flush L2" %
+                             (cases.pcg_iteration_bytes(n, nF)/1e6)},
+            "solves_per_s": 3*args.steps/(ms_dev*1e-3), "iterations_per_step": iters/args.steps,
+            "e2e": {"value": nGlobal*iters_e2e/(ms_e2e*1e-3), "unit": "cell-updates/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e/args.steps,
+                    "solves_per_s": 3*args.steps/(ms_e2e*1e-3)},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roof(dom_k), "roofline_amul": roof("amul"), "kernels": kern,
+            "plan": {k: info[k] for k in ("nRows", "nLevels", "maxLevelRows", "sweepGrid", "streamGrid")},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(s, nGlobal, args.cpu_maxiter)
+        elif world == 1:
+            line["cpu_baseline"] = None
+    g.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.cells:
+        nx, ny, nz = [int(v) for v in args.cells.split(",")]
+    elif args.gpus == 1:
+        nx, ny, nz = 200, 50, 100
+    else:
+        nx, ny, nz = 400, 400, 400
+    if args.cpu_maxiter <= 0:
+        args.cpu_maxiter = int(min(40, max(4, 4e8/(nx*ny*nz))))
+    if args.impl == "reference":
+        run_reference(args, nx, ny, nz)
+    else:
+        run_ours(args, nx, ny, nz)
+
+
+if __name__ == "__main__":
+    main()

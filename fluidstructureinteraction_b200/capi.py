@@ -46,7 +46,9 @@ class PlanInfo(C.Structure):
         ("nLevels", C.c_int), ("maxLevelRows", C.c_int),
         ("entriesUpper", C.c_longlong), ("entriesLower", C.c_longlong),
         ("nInterfaceFaces", C.c_int), ("nInterfaces", C.c_int),
-        ("sweepGrid", C.c_int), ("streamGrid", C.c_int), ("numSMs", C.c_int), ("reserved", C.c_int),
+        ("sweepGrid", C.c_int), ("streamGrid", C.c_int), ("numSMs", C.c_int),
+        ("nTiles", C.c_int), ("tileRowsMax", C.c_int), ("maxRounds", C.c_int), ("sweepSmemBytes", C.c_int),
+        ("extForward", C.c_int), ("extBackward", C.c_int), ("roundEntries", C.c_int),
     ]
 
     def as_dict(self):
@@ -60,6 +62,8 @@ SYMBOLS = {
     "gpupcg_destroy": (C.c_int, [C.c_void_p]),
     "gpupcg_last_error": (C.c_char_p, [C.c_void_p]),
     "gpupcg_get_plan_info": (C.c_int, [C.c_void_p, C.POINTER(PlanInfo)]),
+    "gpupcg_debug_tile_trace": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong)]),
+    "gpupcg_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong)]),
     "gpupcg_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gpupcg_set_matrix": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, C.POINTER(c_double_p)]),
     "gpupcg_set_matrix_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -75,8 +79,8 @@ SYMBOLS = {
     "gpupcg_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "gpupcg_host_register": (C.c_int, [C.c_void_p, C.c_ulonglong]),
     "gpupcg_host_unregister": (C.c_int, [C.c_void_p]),
-    "gpupcg_plan_export": (C.c_int, [C.c_int, C.c_int, c_int_p, c_int_p, C.POINTER(PlanInfo), c_int_p, c_int_p,
-                                     c_int_p, c_int_p, c_int_p, c_int_p]),
+    "gpupcg_plan_export": (C.c_int, [C.c_int, C.c_int, c_int_p, c_int_p, C.c_int, C.c_int, C.POINTER(PlanInfo),
+                                     C.POINTER(c_int_p)]),
     "gpupcg_device_report": (C.c_int, [C.c_int, C.c_char_p, C.c_int]),
 }
 
@@ -162,6 +166,17 @@ class GpuPCG(object):
         self._check(self.lib.gpupcg_get_plan_info(self.h, C.byref(info)))
         return info.as_dict()
 
+    def tile_trace(self):
+        n = self.plan_info()["nTiles"]
+        a = np.zeros(3*n, dtype=np.uint64)
+        self._check(self.lib.gpupcg_debug_tile_trace(self.h, a.ctypes.data_as(C.POINTER(C.c_ulonglong))))
+        return a.reshape(n, 3)
+
+    def launch_count(self):
+        n = C.c_longlong(0)
+        self._check(self.lib.gpupcg_launch_count(self.h, C.byref(n)))
+        return n.value
+
     def set_stream(self, cuda_stream_ptr):
         self._check(self.lib.gpupcg_set_stream(self.h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
 
@@ -232,27 +247,30 @@ class GpuPCG(object):
         self._check(self.lib.gpupcg_comm_init(self.h, rank, nRanks, buf))
 
 
-def plan_export(lowerAddr, upperAddr, nCells):
-    """Host-only schedule export (no GPU): dict with info, rowOld, slices (nSlices,4), Ucol, UfaceOld, Lidx, Lcol."""
+def plan_export(lowerAddr, upperAddr, nCells, tileRows=1024, tileMode=1):
+    """Host-only schedule export (no GPU): dict with info and every schedule array (see include/gpupcg.h)."""
     lib = load_library()
     l, u = _i32(lowerAddr), _i32(upperAddr)
     info = PlanInfo()
-    rc = lib.gpupcg_plan_export(int(nCells), l.shape[0], _ip(l), _ip(u), C.byref(info), None, None, None, None, None, None)
+    rc = lib.gpupcg_plan_export(int(nCells), l.shape[0], _ip(l), _ip(u), int(tileRows), int(tileMode), C.byref(info), None)
     if rc != 0:
         raise GpuPcgError(rc, lib.gpupcg_last_error(None).decode())
     d = info.as_dict()
-    rowOld = np.empty(max(1, d["nRows"]), dtype=np.int32)
-    slices = np.empty((max(1, d["nSlices"]), 4), dtype=np.int32)
-    Ucol = np.empty(max(1, d["entriesUpper"]), dtype=np.int32)
-    UfaceOld = np.empty_like(Ucol)
-    Lidx = np.empty(max(1, d["entriesLower"]), dtype=np.int32)
-    Lcol = np.empty_like(Lidx)
-    rc = lib.gpupcg_plan_export(int(nCells), l.shape[0], _ip(l), _ip(u), C.byref(info), _ip(rowOld), _ip(slices),
-                                _ip(Ucol), _ip(UfaceOld), _ip(Lidx), _ip(Lcol))
+    sizes = [("rowOld", d["nRows"]), ("slices", 4*d["nSlices"]), ("Ucol", d["entriesUpper"]),
+             ("UfaceOld", d["entriesUpper"]), ("Lidx", d["entriesLower"]), ("Lcol", d["entriesLower"]),
+             ("tileStart", d["nTiles"] + 1), ("tileRoundPtr", d["nTiles"] + 1), ("roundStart", d["roundEntries"]),
+             ("LcolTile", d["entriesLower"]), ("UcolTile", d["entriesUpper"]), ("extFPtr", d["nTiles"] + 1),
+             ("extFCol", d["extForward"]), ("extBPtr", d["nTiles"] + 1), ("extBCol", d["extBackward"])]
+    arrs = [np.zeros(max(1, n), dtype=np.int32) for _, n in sizes]
+    ptrs = (c_int_p * len(arrs))(*[_ip(a) for a in arrs])
+    rc = lib.gpupcg_plan_export(int(nCells), l.shape[0], _ip(l), _ip(u), int(tileRows), int(tileMode), C.byref(info), ptrs)
     if rc != 0:
         raise GpuPcgError(rc, lib.gpupcg_last_error(None).decode())
-    return dict(info=d, rowOld=rowOld[:d["nRows"]], slices=slices[:d["nSlices"]], Ucol=Ucol[:d["entriesUpper"]],
-                UfaceOld=UfaceOld[:d["entriesUpper"]], Lidx=Lidx[:d["entriesLower"]], Lcol=Lcol[:d["entriesLower"]])
+    out = dict(info=d)
+    for (name, n), a in zip(sizes, arrs):
+        out[name] = a[:n]
+    out["slices"] = out["slices"].reshape(-1, 4)
+    return out
 
 
 def comm_unique_id():

@@ -29,6 +29,7 @@ struct gpupcg_handle_s
     int nPatches = 0;
     int sweepGrid = 0, streamGrid = 0;
     bool haveMatrix = false;
+    long long launches = 0;
 
     // plan (device)
     SliceInfo* dSlices = nullptr;
@@ -36,6 +37,15 @@ struct gpupcg_handle_s
     int *dIfRow = nullptr, *dIfRowStart = nullptr, *dIfEntry = nullptr, *dIfFaceRow = nullptr;
     unsigned int* dIfMask = nullptr;
     int nIfRows = 0;
+    // tiling of the DIC sweeps (device)
+    int *dTileStart = nullptr, *dTileItemPtr = nullptr, *dItems = nullptr;
+    int *dLcolTile = nullptr, *dUcolTile = nullptr;
+    int *dExtFPtr = nullptr, *dExtFCol = nullptr, *dExtBPtr = nullptr, *dExtBCol = nullptr;
+    unsigned long long* dTileTicket = nullptr;
+    unsigned long long* dTileTrace = nullptr;
+    size_t smemFwd = 0, smemBwd = 0;
+    int partStride = MAXPART;
+    TileArgs tileF, tileB;
 
     // matrix + vectors (device, wavefront order unless noted)
     double *dDiag = nullptr, *dUval = nullptr, *dRD = nullptr;
@@ -65,6 +75,10 @@ struct gpupcg_handle_s
             return GPUPCG_ERR_CUDA;                                                                \
         }                                                                                          \
     } while (0)
+
+// every kernel launch of the library goes through here (counted: bench.py's gpu_launches)
+#define LAUNCH(kern, grid, strm, ...)                                                              \
+    do { h->launches++; kern<<<(grid), TPB, 0, (strm)>>>(__VA_ARGS__); } while (0)
 
 template <class T>
 static cudaError_t dalloc(T*& p, long long n)
@@ -135,7 +149,9 @@ extern "C" int gpupcg_destroy(gpupcg_handle h)
     void* ptrs[] = {h->dSlices, h->dUcol, h->dUfaceOld, h->dLidx, h->dLcol, h->dRowOld, h->dIfRow,
                     h->dIfRowStart, h->dIfEntry, h->dIfFaceRow, h->dIfMask, h->dDiag, h->dUval, h->dRD,
                     h->dX, h->dB, h->dRA, h->dWA, h->dPA, h->dY, h->dStageA, h->dStageB, h->dStageF,
-                    h->dBou, h->dXNbr, h->dSend, h->dPartials, h->dHistory, h->dState, h->dFlush};
+                    h->dBou, h->dXNbr, h->dSend, h->dPartials, h->dHistory, h->dState, h->dFlush,
+                    h->dTileStart, h->dTileItemPtr, h->dItems, h->dLcolTile, h->dUcolTile,
+                    h->dExtFPtr, h->dExtFCol, h->dExtBPtr, h->dExtBCol, h->dTileTicket};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->hState) cudaFreeHost(h->hState);
     if (h->hHistory) cudaFreeHost(h->hHistory);
@@ -173,22 +189,39 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     h->numSMs = prop.multiProcessorCount;
     h->nPatches = nPatches;
 
-    int rc = build_plan(nCells, nFaces, l, u, nPatches, patchSizes, patchFaceCells, patchNbrRank, h->plan, h->err);
-    if (rc != GPUPCG_OK) return rc;
+    // tile size: as large as the shared-memory carve-up of one CTA allows (several CTAs per SM wanted)
+    int tileRows = env_int("GPUPCG_TILE_ROWS", 512);
+    const size_t smemCap = (size_t)std::min<long long>(prop.sharedMemPerBlockOptin, 200*1024);
+    int rc;
+    while (true)
+    {
+        rc = build_plan(nCells, nFaces, l, u, nPatches, patchSizes, patchFaceCells, patchNbrRank, tileRows,
+                        env_int("GPUPCG_TILE_MODE", 2), h->plan, h->err);
+        if (rc != GPUPCG_OK) return rc;
+        const HostPlan& Q = h->plan;
+        h->smemFwd = sweep_layout(Q.tileRowsMax, Q.maxTileExtF, Q.maxItems).bytes;
+        h->smemBwd = sweep_layout(Q.tileRowsMax, Q.maxTileExtB, Q.maxItems).bytes;
+        if (std::max(h->smemFwd, h->smemBwd) <= smemCap || tileRows <= 32) break;
+        tileRows /= 2;
+    }
+    if (std::max(h->smemFwd, h->smemBwd) > smemCap)
+    {
+        h->err = "gpupcg_create: a single 32-row tile does not fit in shared memory (rows with too many faces)";
+        return GPUPCG_ERR_UNSUPPORTED;
+    }
     HostPlan& P = h->plan;
 
     CK(cudaStreamCreateWithFlags(&h->ownStream, cudaStreamNonBlocking));
     h->stream = h->ownStream;
     for (auto& e : h->ev) CK(cudaEventCreate(&e));
-
-    // persistent grids.  The dataflow kernels need every CTA resident: clamp by occupancy.
-    int occSweep = 0, occFactor = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occSweep, k_dic_sweeps, TPB, 0));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occFactor, k_dic_factor, TPB, 0));
-    int bps = env_int("GPUPCG_SWEEP_BPS", 2);
-    bps = std::max(1, std::min(bps, std::min(occSweep, occFactor)));
-    h->sweepGrid = h->numSMs*bps;
-    if (h->sweepGrid*WPB > P.nSlices) h->sweepGrid = std::max(1, (P.nSlices + WPB - 1)/WPB);
+    {
+        int ns = env_int("GPUPCG_SPIN_NS", 0);
+        CK(cudaMemcpyToSymbol(g_spinNs, &ns, sizeof(int)));
+    }
+    CK(cudaFuncSetAttribute(k_dic_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwd));
+    CK(cudaFuncSetAttribute(k_dic_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwd));
+    CK(cudaFuncSetAttribute(k_dic_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBwd));
+    h->sweepGrid = std::max(1, P.nTiles);
     int sbps = std::max(1, env_int("GPUPCG_STREAM_BPS", 8));
     h->streamGrid = std::min(h->numSMs*sbps, MAXPART);
 
@@ -203,6 +236,25 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     CK(upload(h->dIfRowStart, P.ifRowStart, s));
     CK(upload(h->dIfEntry, P.ifEntry, s));
     CK(upload(h->dIfFaceRow, P.ifFaceRow, s));
+    CK(upload(h->dTileStart, P.tileStart, s));
+    CK(upload(h->dTileItemPtr, P.tileItemPtr, s));
+    CK(upload(h->dItems, P.items, s));
+    CK(upload(h->dLcolTile, P.LcolTile, s));
+    CK(upload(h->dUcolTile, P.UcolTile, s));
+    CK(upload(h->dExtFPtr, P.extFPtr, s));
+    CK(upload(h->dExtFCol, P.extFCol, s));
+    CK(upload(h->dExtBPtr, P.extBPtr, s));
+    CK(upload(h->dExtBCol, P.extBCol, s));
+    if (env_int("GPUPCG_TILE_TRACE", 0))
+    {
+        unsigned long long* d = nullptr;
+        CK(dalloc(d, 3LL*std::max(1, P.nTiles)));
+        CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long)*3*std::max(1, P.nTiles), s));
+        CK(cudaMemcpyToSymbol(g_tileTimes, &d, sizeof(d)));
+        h->dTileTrace = d;
+    }
+    CK(dalloc(h->dTileTicket, 1));
+    CK(cudaMemsetAsync(h->dTileTicket, 0, sizeof(unsigned long long), s));
     h->nIfRows = (int)P.ifRow.size();
     {
         std::vector<unsigned int> mask(P.nSlices > 0 ? P.nSlices : 1, 0u);
@@ -217,7 +269,8 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     CK(dalloc(h->dWA, nR));    CK(dalloc(h->dPA, nR));           CK(dalloc(h->dY, nR));
     CK(dalloc(h->dStageA, nCells)); CK(dalloc(h->dStageB, nCells)); CK(dalloc(h->dStageF, nFaces));
     CK(dalloc(h->dBou, P.nIfaceFaces)); CK(dalloc(h->dXNbr, P.nIfaceFaces)); CK(dalloc(h->dSend, P.nIfaceFaces));
-    CK(dalloc(h->dPartials, 4LL*MAXPART));
+    h->partStride = std::max(MAXPART, P.nTiles);
+    CK(dalloc(h->dPartials, 4LL*h->partStride));
     h->historyCap = 4096;
     CK(dalloc(h->dHistory, h->historyCap));
     CK(dalloc(h->dState, 1));
@@ -228,9 +281,20 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     CK(cudaMemsetAsync(h->dXNbr, 0, sizeof(double)*std::max(1, P.nIfaceFaces), s));
     CK(cudaStreamSynchronize(s));
 
+    TileArgs T;
+    T.slices = h->dSlices; T.tileStart = h->dTileStart; T.tileItemPtr = h->dTileItemPtr; T.items = (const int2*)h->dItems;
+    T.nTiles = P.nTiles; T.tileRowsMax = P.tileRowsMax; T.maxItems = P.maxItems;
+    h->tileF = T; h->tileF.colTile = h->dLcolTile; h->tileF.extPtr = h->dExtFPtr; h->tileF.extCol = h->dExtFCol;
+    h->tileF.maxExt = P.maxTileExtF;
+    h->tileB = T; h->tileB.colTile = h->dUcolTile; h->tileB.extPtr = h->dExtBPtr; h->tileB.extCol = h->dExtBCol;
+    h->tileB.maxExt = P.maxTileExtB;
+
     // the big host index arrays are no longer needed
     std::vector<int>().swap(P.Ucol); std::vector<int>().swap(P.UfaceOld);
     std::vector<int>().swap(P.Lidx); std::vector<int>().swap(P.Lcol);
+    std::vector<int>().swap(P.LcolTile); std::vector<int>().swap(P.UcolTile);
+    std::vector<int>().swap(P.extFCol); std::vector<int>().swap(P.extBCol);
+    std::vector<int>().swap(P.roundStart); std::vector<int>().swap(P.items);
     return GPUPCG_OK;
 }
 
@@ -253,26 +317,38 @@ extern "C" int gpupcg_create(gpupcg_handle* out, int device, int nCells, int nFa
     return GPUPCG_OK;
 }
 
-extern "C" int gpupcg_plan_export(int nCells, int nFaces, const int* l, const int* u, gpupcg_plan_info* info,
-                                  int* rowOld, int* sliceInfo, int* Ucol, int* UfaceOld, int* Lidx, int* Lcol)
+static void fill_info(const HostPlan& P, gpupcg_plan_info* info)
+{
+    memset(info, 0, sizeof(*info));
+    info->nCells = P.nCells; info->nFaces = P.nFaces; info->nRows = P.nRows; info->nSlices = P.nSlices;
+    info->nLevels = P.nLevels; info->maxLevelRows = P.maxLevelRows;
+    info->entriesUpper = P.entriesU; info->entriesLower = P.entriesL;
+    info->nTiles = P.nTiles; info->tileRowsMax = P.tileRowsMax; info->maxRounds = P.maxRounds;
+    info->extForward = P.extFPtr.empty() ? 0 : P.extFPtr.back();
+    info->extBackward = P.extBPtr.empty() ? 0 : P.extBPtr.back();
+    info->roundEntries = (int)P.roundStart.size();
+}
+
+extern "C" int gpupcg_plan_export(int nCells, int nFaces, const int* l, const int* u, int tileRows, int tileMode,
+                                  gpupcg_plan_info* info, int** arrays)
 {
     HostPlan P;
     std::string err;
-    int rc = build_plan(nCells, nFaces, l, u, 0, nullptr, nullptr, nullptr, P, err);
+    int rc = build_plan(nCells, nFaces, l, u, 0, nullptr, nullptr, nullptr, tileRows, tileMode, P, err);
     if (rc != GPUPCG_OK) { g_createError = err; return rc; }
-    if (info)
+    if (info) fill_info(P, info);
+    if (arrays)
     {
-        memset(info, 0, sizeof(*info));
-        info->nCells = P.nCells; info->nFaces = P.nFaces; info->nRows = P.nRows; info->nSlices = P.nSlices;
-        info->nLevels = P.nLevels; info->maxLevelRows = P.maxLevelRows;
-        info->entriesUpper = P.entriesU; info->entriesLower = P.entriesL;
+        const std::vector<int>* src[GPUPCG_PLAN_NARRAYS] = {
+            &P.rowOld, nullptr, &P.Ucol, &P.UfaceOld, &P.Lidx, &P.Lcol, &P.tileStart, &P.tileRoundPtr,
+            &P.roundStart, &P.LcolTile, &P.UcolTile, &P.extFPtr, &P.extFCol, &P.extBPtr, &P.extBCol};
+        for (int k = 0; k < GPUPCG_PLAN_NARRAYS; k++)
+        {
+            if (!arrays[k]) continue;
+            if (k == 1) memcpy(arrays[k], P.slices.data(), sizeof(SliceInfo)*P.slices.size());
+            else if (!src[k]->empty()) memcpy(arrays[k], src[k]->data(), sizeof(int)*src[k]->size());
+        }
     }
-    if (rowOld) memcpy(rowOld, P.rowOld.data(), sizeof(int)*P.rowOld.size());
-    if (sliceInfo) memcpy(sliceInfo, P.slices.data(), sizeof(SliceInfo)*P.slices.size());
-    if (Ucol) memcpy(Ucol, P.Ucol.data(), sizeof(int)*P.Ucol.size());
-    if (UfaceOld) memcpy(UfaceOld, P.UfaceOld.data(), sizeof(int)*P.UfaceOld.size());
-    if (Lidx) memcpy(Lidx, P.Lidx.data(), sizeof(int)*P.Lidx.size());
-    if (Lcol) memcpy(Lcol, P.Lcol.data(), sizeof(int)*P.Lcol.size());
     return GPUPCG_OK;
 }
 
@@ -286,6 +362,25 @@ extern "C" int gpupcg_get_plan_info(gpupcg_handle h, gpupcg_plan_info* info)
     info->entriesUpper = P.entriesU; info->entriesLower = P.entriesL;
     info->nInterfaceFaces = P.nIfaceFaces; info->nInterfaces = h->nPatches;
     info->sweepGrid = h->sweepGrid; info->streamGrid = h->streamGrid; info->numSMs = h->numSMs;
+    info->nTiles = P.nTiles; info->tileRowsMax = P.tileRowsMax; info->maxRounds = P.maxRounds;
+    info->sweepSmemBytes = (int)std::max(h->smemFwd, h->smemBwd);
+    info->extForward = h->plan.extFPtr.empty() ? 0 : h->plan.extFPtr.back();
+    info->extBackward = h->plan.extBPtr.empty() ? 0 : h->plan.extBPtr.back();
+    return GPUPCG_OK;
+}
+
+// debug: per-tile {CTA start, staging done, sweep done} globaltimer stamps of the last forward sweep
+extern "C" int gpupcg_debug_tile_trace(gpupcg_handle h, unsigned long long* out3n)
+{
+    if (!h || !out3n || !h->dTileTrace) return GPUPCG_ERR_ARG;
+    CK(cudaMemcpy(out3n, h->dTileTrace, sizeof(unsigned long long)*3*h->plan.nTiles, cudaMemcpyDeviceToHost));
+    return GPUPCG_OK;
+}
+
+extern "C" int gpupcg_launch_count(gpupcg_handle h, long long* count)
+{
+    if (!h || !count) return GPUPCG_ERR_ARG;
+    *count = h->launches;
     return GPUPCG_OK;
 }
 
@@ -305,10 +400,10 @@ static int matrix_from_staging(gpupcg_handle h, bool haveUpper)
 {
     const HostPlan& P = h->plan;
     cudaStream_t s = h->stream;
-    k_rows_in<<<grid_for(P.nRows, h->streamGrid), TPB, 0, s>>>(h->dStageA, h->dDiag, h->dRowOld, P.nRows, 1.0);
+    LAUNCH(k_rows_in, grid_for(P.nRows, h->streamGrid), s, h->dStageA, h->dDiag, h->dRowOld, P.nRows, 1.0);
     if (haveUpper)
     {
-        k_coeffs_in<<<grid_for(P.entriesU, h->streamGrid), TPB, 0, s>>>(h->dStageF, h->dUval, h->dUfaceOld, P.entriesU);
+        LAUNCH(k_coeffs_in, grid_for(P.entriesU, h->streamGrid), s, h->dStageF, h->dUval, h->dUfaceOld, P.entriesU);
     }
     CK(cudaGetLastError());
     h->haveMatrix = true;
@@ -358,9 +453,9 @@ extern "C" int gpupcg_set_matrix_device(gpupcg_handle h, const double* d_diag, c
     const HostPlan& P = h->plan;
     CK(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
-    k_rows_in<<<grid_for(P.nRows, h->streamGrid), TPB, 0, s>>>(d_diag, h->dDiag, h->dRowOld, P.nRows, 1.0);
+    LAUNCH(k_rows_in, grid_for(P.nRows, h->streamGrid), s, d_diag, h->dDiag, h->dRowOld, P.nRows, 1.0);
     if (d_upper)
-        k_coeffs_in<<<grid_for(P.entriesU, h->streamGrid), TPB, 0, s>>>(d_upper, h->dUval, h->dUfaceOld, P.entriesU);
+        LAUNCH(k_coeffs_in, grid_for(P.entriesU, h->streamGrid), s, d_upper, h->dUval, h->dUfaceOld, P.entriesU);
     else if (!h->haveMatrix && P.nFaces > 0) { h->err = "gpupcg_set_matrix_device: no coefficients yet"; return GPUPCG_ERR_STATE; }
     if (d_bou && P.nIfaceFaces > 0)
         CK(cudaMemcpyAsync(h->dBou, d_bou, sizeof(double)*P.nIfaceFaces, cudaMemcpyDeviceToDevice, s));
@@ -374,7 +469,7 @@ extern "C" int gpupcg_set_matrix_device(gpupcg_handle h, const double* d_diag, c
 // ------------------------------------------------------------------------------------------------
 static inline void fill_sent(gpupcg_handle h, double* p)
 {
-    k_fill64<<<grid_for(h->plan.nRows, h->streamGrid), TPB, 0, h->stream>>>((unsigned long long*)p, SENT, h->plan.nRows);
+    LAUNCH(k_fill64, grid_for(h->plan.nRows, h->streamGrid), h->stream, (unsigned long long*)p, SENT, h->plan.nRows);
 }
 
 // halo: gather x[faceCells] -> exchange -> dXNbr.  Single rank: nothing to do.
@@ -382,7 +477,7 @@ static int halo_exchange(gpupcg_handle h, const double* x)
 {
     const HostPlan& P = h->plan;
     if (!h->comm.active() || P.nIfaceFaces == 0) return GPUPCG_OK;
-    k_iface_gather<<<grid_for(P.nIfaceFaces, h->streamGrid), TPB, 0, h->stream>>>(x, h->dIfFaceRow, h->dSend, P.nIfaceFaces);
+    LAUNCH(k_iface_gather, grid_for(P.nIfaceFaces, h->streamGrid), h->stream, x, h->dIfFaceRow, h->dSend, P.nIfaceFaces);
     if (h->comm.exchange(h->dSend, h->dXNbr, P.patchStart, P.patchNbrRank, h->stream, h->err) != 0) return GPUPCG_ERR_NCCL;
     return GPUPCG_OK;
 }
@@ -392,7 +487,7 @@ static int allreduce_step(gpupcg_handle h, int step, int count)
     if (!h->comm.active()) return GPUPCG_OK;
     if (h->comm.allreduce_sum((double*)((char*)h->dState + offsetof(DevState, red)), count, h->stream, h->err) != 0)
         return GPUPCG_ERR_NCCL;
-    k_scalar_step<<<1, 32, 0, h->stream>>>(h->dState, step, h->dHistory);
+    h->launches++; k_scalar_step<<<1, 32, 0, h->stream>>>(h->dState, step, h->dHistory);
     return GPUPCG_OK;
 }
 
@@ -407,40 +502,46 @@ static int enqueue_amul(gpupcg_handle h, int mode, const double* x, double* Ax, 
     if (ifaces && mode != 2 && !xNbrReady) { rc = halo_exchange(h, x); if (rc) return rc; }
     const unsigned int* mask = (ifaces && mode == 1) ? h->dIfMask : nullptr;
     if (mode == 0)
-        k_amul<0><<<g, TPB, 0, s>>>(h->dSlices, P.nSlices, h->dDiag, h->dUval, h->dUcol, h->dLidx, h->dLcol, h->dRowOld, mask, x, Ax, h->dPartials, h->dState);
+        LAUNCH(k_amul<0>, g, s, h->dSlices, P.nSlices, h->dDiag, h->dUval, h->dUcol, h->dLidx, h->dLcol, h->dRowOld, mask, x, Ax, h->dPartials, h->dState);
     else if (mode == 1)
-        k_amul<1><<<g, TPB, 0, s>>>(h->dSlices, P.nSlices, h->dDiag, h->dUval, h->dUcol, h->dLidx, h->dLcol, h->dRowOld, mask, x, Ax, h->dPartials, h->dState);
+        LAUNCH(k_amul<1>, g, s, h->dSlices, P.nSlices, h->dDiag, h->dUval, h->dUcol, h->dLidx, h->dLcol, h->dRowOld, mask, x, Ax, h->dPartials, h->dState);
     else
-        k_amul<2><<<g, TPB, 0, s>>>(h->dSlices, P.nSlices, h->dDiag, h->dUval, h->dUcol, h->dLidx, h->dLcol, h->dRowOld, mask, x, Ax, h->dPartials, h->dState);
+        LAUNCH(k_amul<2>, g, s, h->dSlices, P.nSlices, h->dDiag, h->dUval, h->dUcol, h->dLidx, h->dLcol, h->dRowOld, mask, x, Ax, h->dPartials, h->dState);
     if (ifaces)
     {
         const int gi = grid_for(h->nIfRows, h->streamGrid);
         if (mode == 1)
-            k_iface_update<1><<<gi, TPB, 0, s>>>(h->dIfRow, h->dIfRowStart, h->dIfEntry, h->nIfRows, h->dBou, h->dXNbr, 0, x, Ax, h->dPartials, h->dState, 1);
+            LAUNCH(k_iface_update<1>, gi, s, h->dIfRow, h->dIfRowStart, h->dIfEntry, h->nIfRows, h->dBou, h->dXNbr, 0, x, Ax, h->dPartials, h->dState, 1);
         else
-            k_iface_update<0><<<gi, TPB, 0, s>>>(h->dIfRow, h->dIfRowStart, h->dIfEntry, h->nIfRows, h->dBou, h->dXNbr, mode == 2 ? 1 : 0, x, Ax, h->dPartials, h->dState, 0);
+            LAUNCH(k_iface_update<0>, gi, s, h->dIfRow, h->dIfRowStart, h->dIfEntry, h->nIfRows, h->dBou, h->dXNbr, mode == 2 ? 1 : 0, x, Ax, h->dPartials, h->dState, 0);
     }
     CK(cudaGetLastError());
     return GPUPCG_OK;
 }
 
+#define LAUNCH_SWEEP(kern, smem, ...)                                                              \
+    do { h->launches++; kern<<<h->sweepGrid, SWEEP_TPB, (smem), h->stream>>>(__VA_ARGS__); } while (0)
+
 static int enqueue_factor(gpupcg_handle h, int gated)
 {
-    const HostPlan& P = h->plan;
+    if (h->plan.nTiles == 0) return GPUPCG_OK;
     fill_sent(h, h->dY);
-    k_dic_factor<<<h->sweepGrid, TPB, 0, h->stream>>>(h->dSlices, P.nSlices, h->dDiag, h->dUval, h->dLidx, h->dLcol,
-                                                      (unsigned long long*)h->dY, h->dRD, h->dState, gated);
+    LAUNCH_SWEEP(k_dic_tile<1>, h->smemFwd, h->tileF, h->dDiag, h->dUval, h->dLidx, nullptr, nullptr,
+                 (unsigned long long*)h->dY, h->dRD, h->dTileTicket, nullptr, 0, h->dState, gated);
     fill_sent(h, h->dY);
     CK(cudaGetLastError());
     return GPUPCG_OK;
 }
 
+// y (h->dY) and z must hold SENT on entry; y is re-armed by the backward kernel.
 static int enqueue_sweeps(gpupcg_handle h, const double* rA, double* z, bool reduce, int gated)
 {
-    const HostPlan& P = h->plan;
-    k_dic_sweeps<<<h->sweepGrid, TPB, 0, h->stream>>>(h->dSlices, P.nSlices, h->dRD, h->dUval, h->dUcol, h->dLidx, h->dLcol, rA,
-                                                      (unsigned long long*)h->dY, (unsigned long long*)z,
-                                                      reduce ? h->dPartials : nullptr, h->dState, gated);
+    if (h->plan.nTiles == 0) return GPUPCG_OK;
+    LAUNCH_SWEEP(k_dic_tile<0>, h->smemFwd, h->tileF, h->dRD, h->dUval, h->dLidx, rA, nullptr,
+                 (unsigned long long*)h->dY, nullptr, h->dTileTicket, nullptr, 0, h->dState, gated);
+    LAUNCH_SWEEP(k_dic_tile<2>, h->smemBwd, h->tileB, h->dRD, h->dUval, nullptr, rA, (unsigned long long*)h->dY,
+                 (unsigned long long*)z, nullptr, h->dTileTicket, reduce ? h->dPartials : nullptr, h->partStride,
+                 h->dState, gated);
     CK(cudaGetLastError());
     return GPUPCG_OK;
 }
@@ -469,11 +570,11 @@ static int solve_core(gpupcg_handle h, double tol, double relTol, int minIter, i
 
     // wA = A x ; rA = b - wA ; xRef = gAverage(x)
     rc = enqueue_amul(h, 0, h->dX, h->dWA, false); if (rc) return rc;
-    k_init_residual<<<gN, TPB, 0, s>>>(h->dB, h->dWA, h->dX, h->dRA, P.nRows, h->dPartials, h->dState);
+    LAUNCH(k_init_residual, gN, s, h->dB, h->dWA, h->dX, h->dRA, P.nRows, h->dPartials, h->dState);
     rc = allreduce_step(h, S_INIT, 1); if (rc) return rc;
     // pA = A (xRef field) ; normFactor ; initial residual ; stop()?
     rc = enqueue_amul(h, 2, h->dX, h->dPA, false); if (rc) return rc;
-    k_norm<<<gN, TPB, 0, s>>>(h->dWA, h->dPA, h->dB, h->dRA, P.nRows, h->dPartials, h->dState);
+    LAUNCH(k_norm, gN, s, h->dWA, h->dPA, h->dB, h->dRA, P.nRows, h->dPartials, h->dState);
     rc = allreduce_step(h, S_NORM, 2); if (rc) return rc;
     // preconditioner::New -> DIC: calcReciprocalD (skipped on device when already converged)
     rc = enqueue_factor(h, 1); if (rc) return rc;
@@ -492,10 +593,10 @@ static int solve_core(gpupcg_handle h, double tol, double relTol, int minIter, i
         {
             rc = enqueue_sweeps(h, h->dRA, h->dWA, true, 1); if (rc) return rc;
             rc = allreduce_step(h, S_SWEEP, 1); if (rc) return rc;
-            k_p_update<<<gN, TPB, 0, s>>>(h->dWA, h->dPA, P.nRows, h->dState);
+            LAUNCH(k_p_update, gN, s, h->dWA, h->dPA, P.nRows, h->dState);
             rc = enqueue_amul(h, 1, h->dPA, h->dWA, false); if (rc) return rc;
             rc = allreduce_step(h, S_AMUL, 1); if (rc) return rc;
-            k_xr_update<<<gN, TPB, 0, s>>>(h->dPA, (unsigned long long*)h->dWA, h->dX, h->dRA, P.nRows,
+            LAUNCH(k_xr_update, gN, s, h->dPA, (unsigned long long*)h->dWA, h->dX, h->dRA, P.nRows,
                                            h->dPartials, h->dState, h->dHistory);
             rc = allreduce_step(h, S_XR, 1); if (rc) return rc;
         }
@@ -536,11 +637,11 @@ extern "C" int gpupcg_solve_device(gpupcg_handle h, double* d_x, const double* d
     cudaStream_t s = h->stream;
     const int gN = grid_for(P.nRows, h->streamGrid);
     if (perf) memset(perf, 0, sizeof(*perf));
-    k_rows_in<<<gN, TPB, 0, s>>>(d_x, h->dX, h->dRowOld, P.nRows, 0.0);
-    k_rows_in<<<gN, TPB, 0, s>>>(d_b, h->dB, h->dRowOld, P.nRows, 0.0);
+    LAUNCH(k_rows_in, gN, s, d_x, h->dX, h->dRowOld, P.nRows, 0.0);
+    LAUNCH(k_rows_in, gN, s, d_b, h->dB, h->dRowOld, P.nRows, 0.0);
     int rc = solve_core(h, tol, relTol, minIter, maxIter, perf, history, historyCap);
     if (rc) return rc;
-    k_rows_out<<<gN, TPB, 0, s>>>(h->dX, d_x, h->dRowOld, P.nRows);
+    LAUNCH(k_rows_out, gN, s, h->dX, d_x, h->dRowOld, P.nRows);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
     return GPUPCG_OK;
@@ -585,7 +686,7 @@ extern "C" int gpupcg_amul(gpupcg_handle h, const double* x, double* Ax, const d
     cudaStream_t s = h->stream;
     const int gN = grid_for(P.nRows, h->streamGrid);
     CK(cudaMemcpyAsync(h->dStageA, x, sizeof(double)*P.nCells, cudaMemcpyHostToDevice, s));
-    k_rows_in<<<gN, TPB, 0, s>>>(h->dStageA, h->dX, h->dRowOld, P.nRows, 0.0);
+    LAUNCH(k_rows_in, gN, s, h->dStageA, h->dX, h->dRowOld, P.nRows, 0.0);
     bool nbrReady = false;
     if (P.nIfaceFaces > 0 && xNbr)
     {
@@ -593,7 +694,7 @@ extern "C" int gpupcg_amul(gpupcg_handle h, const double* x, double* Ax, const d
         nbrReady = true;
     }
     int rc = enqueue_amul(h, 0, h->dX, h->dWA, nbrReady); if (rc) return rc;
-    k_rows_out<<<gN, TPB, 0, s>>>(h->dWA, h->dStageB, h->dRowOld, P.nRows);
+    LAUNCH(k_rows_out, gN, s, h->dWA, h->dStageB, h->dRowOld, P.nRows);
     CK(cudaMemcpyAsync(Ax, h->dStageB, sizeof(double)*P.nCells, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
@@ -608,7 +709,7 @@ extern "C" int gpupcg_dic_factor(gpupcg_handle h, double* rD)
     CK(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     int rc = enqueue_factor(h, 0); if (rc) return rc;
-    k_rows_out<<<grid_for(P.nRows, h->streamGrid), TPB, 0, s>>>(h->dRD, h->dStageB, h->dRowOld, P.nRows);
+    LAUNCH(k_rows_out, grid_for(P.nRows, h->streamGrid), s, h->dRD, h->dStageB, h->dRowOld, P.nRows);
     CK(cudaMemcpyAsync(rD, h->dStageB, sizeof(double)*P.nCells, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
@@ -625,10 +726,10 @@ extern "C" int gpupcg_precondition(gpupcg_handle h, const double* rA, double* wA
     const int gN = grid_for(P.nRows, h->streamGrid);
     int rc = enqueue_factor(h, 0); if (rc) return rc;
     CK(cudaMemcpyAsync(h->dStageA, rA, sizeof(double)*P.nCells, cudaMemcpyHostToDevice, s));
-    k_rows_in<<<gN, TPB, 0, s>>>(h->dStageA, h->dRA, h->dRowOld, P.nRows, 0.0);
+    LAUNCH(k_rows_in, gN, s, h->dStageA, h->dRA, h->dRowOld, P.nRows, 0.0);
     fill_sent(h, h->dWA);
     rc = enqueue_sweeps(h, h->dRA, h->dWA, false, 0); if (rc) return rc;
-    k_rows_out<<<gN, TPB, 0, s>>>(h->dWA, h->dStageB, h->dRowOld, P.nRows);
+    LAUNCH(k_rows_out, gN, s, h->dWA, h->dStageB, h->dRowOld, P.nRows);
     CK(cudaMemcpyAsync(wA, h->dStageB, sizeof(double)*P.nCells, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
@@ -656,8 +757,8 @@ extern "C" int gpupcg_time_kernel(gpupcg_handle h, int which, int reps, int flus
     *h->hState = init;
     CK(cudaMemcpyAsync(h->dState, h->hState, sizeof(DevState), cudaMemcpyHostToDevice, s));
     int rc = enqueue_factor(h, 0); if (rc) return rc;
-    k_rows_in<<<gN, TPB, 0, s>>>(h->dStageA, h->dRA, h->dRowOld, P.nRows, 0.0);   // whatever the staging holds
-    k_rows_in<<<gN, TPB, 0, s>>>(h->dStageA, h->dPA, h->dRowOld, P.nRows, 0.0);
+    LAUNCH(k_rows_in, gN, s, h->dStageA, h->dRA, h->dRowOld, P.nRows, 0.0);   // whatever the staging holds
+    LAUNCH(k_rows_in, gN, s, h->dStageA, h->dPA, h->dRowOld, P.nRows, 0.0);
     CK(cudaMemsetAsync(h->dX, 0, sizeof(double)*P.nRows, s));
     fill_sent(h, h->dWA);
     CK(cudaStreamSynchronize(s));
@@ -667,14 +768,14 @@ extern "C" int gpupcg_time_kernel(gpupcg_handle h, int which, int reps, int flus
     {
         if (which == 1) fill_sent(h, h->dWA);
         if (which == 3) CK(cudaMemsetAsync(h->dWA, 0, sizeof(double)*P.nRows, s));
-        if (flushL2) k_flush<<<h->streamGrid, TPB, 0, s>>>(h->dFlush, h->flushN, (float)i);
+        if (flushL2) LAUNCH(k_flush, h->streamGrid, s, h->dFlush, h->flushN, (float)i);
         CK(cudaEventRecord(h->ev[0], s));
         switch (which)
         {
             case 0: rc = enqueue_amul(h, 1, h->dPA, h->dWA, true); break;
             case 1: rc = enqueue_sweeps(h, h->dRA, h->dWA, true, 0); break;
-            case 2: k_p_update<<<gN, TPB, 0, s>>>(h->dRA, h->dPA, P.nRows, h->dState); rc = 0; break;
-            case 3: k_xr_update<<<gN, TPB, 0, s>>>(h->dPA, (unsigned long long*)h->dWA, h->dX, h->dRA, P.nRows,
+            case 2: LAUNCH(k_p_update, gN, s, h->dRA, h->dPA, P.nRows, h->dState); rc = 0; break;
+            case 3: LAUNCH(k_xr_update, gN, s, h->dPA, (unsigned long long*)h->dWA, h->dX, h->dRA, P.nRows,
                                                    h->dPartials, h->dState, nullptr); rc = 0; break;
             case 4: rc = enqueue_factor(h, 0); break;
             default: h->err = "gpupcg_time_kernel: unknown kernel id"; return GPUPCG_ERR_ARG;

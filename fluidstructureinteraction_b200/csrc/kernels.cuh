@@ -29,7 +29,7 @@ static constexpr unsigned long long QNAN = 0x7FF8000000000000ULL;
 
 static constexpr int TPB = 256;             // threads per block of every kernel
 static constexpr int WPB = TPB/32;          // warps per block
-static constexpr int MAXPART = 4096;        // max CTAs of any reducing kernel
+static constexpr int MAXPART = 4096;        // max CTAs of any streaming (grid-stride) reducing kernel
 
 static constexpr double K_VSMALL = 1.0e-300;    // Foam::VSMALL
 static constexpr double K_SMALL  = 1.0e-15;     // Foam::SMALL
@@ -113,11 +113,12 @@ __device__ __forceinline__ void dev_scalar_step(DevState* st, int step, const do
 // partials in a fixed order and either advances the scalar recurrence (single rank) or parks the
 // local sums in st->red for the all-reduce (multi rank).
 // ------------------------------------------------------------------------------------------
-template <int NV>
-__device__ __forceinline__ void grid_reduce_finish(double (&v)[NV], double* partials, DevState* st,
-                                                   int step, double* history)
+template <int NV, int NT>
+__device__ __forceinline__ void grid_reduce_finish(double (&v)[NV], double* partials, int stride, int slot, int nSlots,
+                                                   DevState* st, int step, double* history)
 {
-    __shared__ double sm[NV][WPB];
+    constexpr int NW = NT/32;
+    __shared__ double sm[NV][NW];
     __shared__ bool amLast;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -136,23 +137,23 @@ __device__ __forceinline__ void grid_reduce_finish(double (&v)[NV], double* part
         {
             double a = sm[k][0];
 #pragma unroll
-            for (int w = 1; w < WPB; w++) a += sm[k][w];
-            __stcg(&partials[k*MAXPART + blockIdx.x], a);
+            for (int w = 1; w < NW; w++) a += sm[k][w];
+            __stcg(&partials[(size_t)k*stride + slot], a);
         }
         __threadfence();
         const unsigned int t = atomicAdd(&st->ticket, 1u);
-        amLast = (t == gridDim.x - 1);
+        amLast = (t == (unsigned int)nSlots - 1);
     }
     __syncthreads();
     if (!amLast) return;
     __threadfence();
-    // fixed-shape final sum: thread t takes partials t, t+TPB, ... then the same block tree
+    // fixed-shape final sum: thread t takes partials t, t+NT, ... then the same block tree
     double f[NV];
 #pragma unroll
     for (int k = 0; k < NV; k++)
     {
         double a = 0.0;
-        for (int i = threadIdx.x; i < (int)gridDim.x; i += TPB) a += __ldcg(&partials[k*MAXPART + i]);
+        for (int i = threadIdx.x; i < nSlots; i += NT) a += __ldcg(&partials[(size_t)k*stride + i]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         if (lane == 0) sm[k][warp] = a;
@@ -165,7 +166,7 @@ __device__ __forceinline__ void grid_reduce_finish(double (&v)[NV], double* part
         {
             double a = sm[k][0];
 #pragma unroll
-            for (int w = 1; w < WPB; w++) a += sm[k][w];
+            for (int w = 1; w < NW; w++) a += sm[k][w];
             f[k] = a;
         }
         st->ticket = 0;
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(TPB) k_iface_update(const int* __restrict__ if
         Ax[r] = acc;
         if (DOT) dot[0] += acc*x[r];
     }
-    if (DOT) grid_reduce_finish<1>(dot, partials + 2*MAXPART, st, S_AMUL, nullptr);
+    if (DOT) grid_reduce_finish<1, TPB>(dot, partials + 2*MAXPART, MAXPART, blockIdx.x, gridDim.x, st, S_AMUL, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -328,12 +329,22 @@ __global__ void __launch_bounds__(TPB) k_amul(const SliceInfo* __restrict__ slic
             if (!masked) dot[0] += acc*xr;
         }
     }
-    if (MODE == 1) grid_reduce_finish<1>(dot, partials, st, S_AMUL, nullptr);
+    if (MODE == 1) grid_reduce_finish<1, TPB>(dot, partials, MAXPART, blockIdx.x, gridDim.x, st, S_AMUL, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------
-// dataflow primitives of the wavefront sweeps: the value IS the flag.
+// dataflow primitives of the tiled sweeps: across tiles the value IS the flag (SENT = not yet).
 // ------------------------------------------------------------------------------------------
+__device__ int g_spinNs = 0;     // back-off of the global polls (0 = tight), set from GPUPCG_SPIN_NS
+__device__ unsigned long long* g_tileTimes = nullptr;   // debug: 3 x globaltimer per tile (GPUPCG_TILE_TRACE)
+
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 __device__ __forceinline__ unsigned long long peek64(const unsigned long long* p)
 {
     unsigned long long v;
@@ -341,15 +352,16 @@ __device__ __forceinline__ unsigned long long peek64(const unsigned long long* p
     return v;
 }
 
-__device__ __forceinline__ double wait_value(const unsigned long long* p, unsigned long long first)
+__device__ __forceinline__ unsigned long long wait_global(const unsigned long long* p)
 {
-    unsigned long long v = first;
+    unsigned long long v = peek64(p);
+    const int ns = g_spinNs;
     while (v == SENT)
     {
-        __nanosleep(20);
+        if (ns > 0) __nanosleep(ns);
         v = peek64(p);
     }
-    return __longlong_as_double((long long)v);
+    return v;
 }
 
 __device__ __forceinline__ void publish(unsigned long long* p, double v)
@@ -359,152 +371,389 @@ __device__ __forceinline__ void publish(unsigned long long* p, double v)
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(b) : "memory");
 }
 
-// ------------------------------------------------------------------------------------------
-// K9  DICPreconditioner::calcReciprocalD  [EXT DICPreconditioner.C], gather + dataflow form:
-//   d[row] = diag[row] - sum_{faces (l,row), ascending f} upper[f]*upper[f]/d[l];   rD = 1/d
-// dscratch must hold SENT on entry; it receives the un-inverted pivots.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) k_dic_factor(const SliceInfo* __restrict__ slices, int nSlices,
-                                                    const double* __restrict__ diag, const double* __restrict__ Uval,
-                                                    const int* __restrict__ Lidx, const int* __restrict__ Lcol,
-                                                    unsigned long long* dscratch, double* __restrict__ rD, DevState* st,
-                                                    int gated)
+__device__ __forceinline__ double wait_shared(const unsigned long long* p)
 {
-    if (gated && st->done) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int s = blockIdx.x + gridDim.x*warp; s < nSlices; s += gridDim.x*WPB)
+    unsigned long long v;
+    do { v = *(const volatile unsigned long long*)p; } while (v == SENT);
+    return __longlong_as_double((long long)v);
+}
+
+// Static description of the tiling handed to the sweep kernels.
+struct TileArgs
+{
+    const SliceInfo* slices;
+    const int* tileStart;       // [nTiles+1]
+    const int* tileItemPtr;     // [nTiles+1]
+    const int2* items;          // {first row, count | first<<16 | last<<17}
+    const int* colTile;         // LcolTile (forward/factor) or UcolTile (backward)
+    const int* extPtr;          // [nTiles+1]
+    const int* extCol;
+    int nTiles;
+    int tileRowsMax, maxExt, maxItems;      // shared-memory carve-up
+};
+
+static constexpr int SWEEP_TPB = 128;       // warp 0 sweeps, warps 1-3 fetch cross-tile values
+static constexpr int FETCHERS = SWEEP_TPB - 32;
+
+// Shared-memory carve-up of one sweep CTA (byte offsets, all 16 B aligned):
+//   vals  [NV]  doubles: [0,T) the tile's rows, [T,T+X) cross-tile inputs (SENT until a fetch warp delivers
+//               them), [T+X] a constant 1.0 that unused entry slots point at with a zero coefficient, so the
+//               round loop is branch-free (acc - 0*1 == acc and acc - 0/1 == acc exactly)
+//   rowF  [4T]  doubles: the first four coefficients of every row
+//   rowC  [4T]  ints   : their value indices
+//   items [I+2] int2   : work items
+//   ovf   [T]   bytes  : entries beyond the first four (walked from global memory; polyhedral cells only)
+struct SweepLayout
+{
+    int T, X, NV, one;
+    unsigned vals, rowF, rowC, items, ovf, slot, bytes;
+};
+
+__host__ __device__ inline SweepLayout sweep_layout(int T, int X, int I)
+{
+    SweepLayout L;
+    L.T = T; L.X = X;
+    L.NV = (T + X + 3) & ~1;
+    L.one = T + X;
+    L.vals = 0;
+    L.rowF = 8u*L.NV;
+    L.rowC = L.rowF + 32u*T;
+    L.items = L.rowC + 16u*T;
+    L.ovf = L.items + 8u*(I + 2);
+    L.slot = L.ovf + T;
+    L.bytes = L.slot + 16;
+    return L;
+}
+
+// shared-memory accessors on 32-bit shared addresses.  All volatile asm: the sweep loop is hand-scheduled and the
+// compiler must keep the order (prefetches of the NEXT item first, then the dependency loads of the current one).
+__device__ __forceinline__ double lds_f64(unsigned a)
+{
+    // ld.VOLATILE: this is the load the sweep warp polls cross-tile slots with.  A plain (weak) ld.shared lets
+    // ptxas assume no other warp writes the slot and delete the re-poll loop (seen in SASS, r1).
+    double v;
+    asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+// weak load of a value slot: ordered against the other lanes' stores by the __syncwarp between rounds; for a
+// cross-tile slot it returns either SENT or the final value (slots change exactly once), so it is a valid
+// first probe.  (ld.volatile serialises: four of them cost ~120 cycles per round instead of ~30.)
+__device__ __forceinline__ double lds_f64_weak(unsigned a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned a, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v));
+}
+__device__ __forceinline__ void sts_u64(unsigned a, unsigned long long v)
+{
+    asm volatile("st.volatile.shared.u64 [%0], %1;" :: "r"(a), "l"(v) : "memory");
+}
+__device__ __forceinline__ int4 lds_v4(unsigned a)
+{
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double2 lds_d2(unsigned a)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int2 lds_i2(unsigned a)
+{
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds_u8(unsigned a)
+{
+    int v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
+// Tiles are handed out in launch order through a never-reset ticket: CTA k of a launch gets tile
+// k mod nTiles (forward) or its mirror (backward).  A running CTA therefore only ever waits on tiles whose
+// CTAs are already running or finished: no deadlock, whatever the hardware's block scheduling order.
+__device__ __forceinline__ int take_tile(unsigned long long* tileTicket, int nTiles, int* slot, bool backward)
+{
+    if (threadIdx.x == 0)
     {
-        const SliceInfo si = slices[s];
-        const int r = s*32 + lane;
-        double d = diag[r];
-        for (int j0 = 0; j0 < si.widthL; j0 += 4)
-        {
-            int col[4]; double c[4]; unsigned long long dep[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-            {
-                col[k] = -1;
-                if (j0 + k < si.widthL)
-                {
-                    const int e = si.offL + (j0 + k)*32 + lane;
-                    col[k] = Lcol[e];
-                    if (col[k] >= 0) { c[k] = Uval[Lidx[e]]; dep[k] = peek64(dscratch + col[k]); }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-            {
-                if (col[k] >= 0)
-                {
-                    const double dl = wait_value(dscratch + col[k], dep[k]);
-                    d = __dsub_rn(d, __ddiv_rn(__dmul_rn(c[k], c[k]), dl));
-                }
-            }
-        }
-        publish(dscratch + r, d);
-        rD[r] = __ddiv_rn(1.0, d);
+        const unsigned long long t = atomicAdd(tileTicket, 1ULL);
+        const int k = (int)(t % (unsigned long long)nTiles);
+        *slot = backward ? nTiles - 1 - k : k;
+    }
+    __syncthreads();
+    return *slot;
+}
+
+// value index of a tile column code: >= 0 tile row, <= -2 cross-tile slot, -1 unused
+__device__ __forceinline__ int value_index(int code, int T, int one)
+{
+    return code >= 0 ? code : (code == -1 ? one : T + (-2 - code));
+}
+
+__device__ __forceinline__ bool is_sent(double v)
+{
+    return (unsigned long long)__double_as_longlong(v) == SENT;
+}
+
+// Static data of one row, fetched into registers one work item ahead of its use so that the only loads left on
+// the round-to-round dependency chain are the four value loads.
+struct RowRegs
+{
+    int q;              // tile-local row, -1 = this lane idles in this pass
+    int4 c;             // value indices of the first four entries
+    double f0, f1, f2, f3;
+    double acc0;
+    int ovf;
+};
+
+__device__ __forceinline__ RowRegs load_row(unsigned sb, const SweepLayout& L, int2 item, int lane)
+{
+    RowRegs R;
+    const bool active = lane < (item.y & 0xffff);
+    const int q = active ? item.x + lane : 0;
+    R.q = active ? q : -1;
+    R.c = lds_v4(sb + L.rowC + 16u*q);
+    const double2 fa = lds_d2(sb + L.rowF + 32u*q);
+    const double2 fb = lds_d2(sb + L.rowF + 32u*q + 16u);
+    R.acc0 = lds_f64_weak(sb + L.vals + 8u*q);
+    R.ovf = lds_u8(sb + L.ovf + q);
+    if (!active)        // idle lanes must not wait on anything: point them at the constant slot
+    {
+        R.c = make_int4(L.one, L.one, L.one, L.one);
+        R.ovf = 0;
+    }
+    R.f0 = fa.x; R.f1 = fa.y; R.f2 = fb.x; R.f3 = fb.y;
+    return R;
+}
+
+// the four register-resident dependencies of a row: four loads issued together, one combined readiness test.
+// Rows of the tile are final by construction of the rounds; cross-tile slots may still hold SENT.
+__device__ __forceinline__ void dep_values4(unsigned vb, const int4 c, double& v0, double& v1, double& v2, double& v3)
+{
+    v0 = lds_f64_weak(vb + 8u*c.x); v1 = lds_f64_weak(vb + 8u*c.y);
+    v2 = lds_f64_weak(vb + 8u*c.z); v3 = lds_f64_weak(vb + 8u*c.w);
+    while (is_sent(v0) | is_sent(v1) | is_sent(v2) | is_sent(v3))
+    {
+        v0 = lds_f64(vb + 8u*c.x); v1 = lds_f64(vb + 8u*c.y); v2 = lds_f64(vb + 8u*c.z); v3 = lds_f64(vb + 8u*c.w);
     }
 }
 
+__device__ __forceinline__ double dep_value(unsigned vb, int idx)
+{
+    double v = lds_f64(vb + 8u*idx);
+    while (is_sent(v)) v = lds_f64(vb + 8u*idx);
+    return v;
+}
+
 // ------------------------------------------------------------------------------------------
-// K10 DICPreconditioner::precondition(wA, rA)  [EXT DICPreconditioner.C] as ONE persistent dataflow
-// kernel: forward sweep into y, backward sweep into z (= wA), wArA = sum(wA*rA) fused in the tail.
-//   forward : y[row] = rD[row]*rA[row] - sum_{(l,row) asc f} (rD[row]*upper[f])*y[l]
-//   backward: z[row] = y[row]          - sum_{(row,u) desc f} (rD[row]*upper[f])*z[u]
-// y and z must hold SENT on entry.  y is re-armed (SENT) here; z is re-armed by k_xr_update.
-// Deadlock freedom: slices are in topological order, dealt round-robin to resident warps that walk
-// them in increasing (forward) / decreasing (backward) order, so the smallest unfinished slice
-// always has its inputs; requires all CTAs co-resident (grid <= occupancy x numSMs).
+// K9 / K10.  One CTA sweeps one tile.
+//   MODE 0: forward sweep of DICPreconditioner::precondition  [EXT DICPreconditioner.C]
+//           y[row] = rD[row]*rA[row] - sum_{(l,row) asc f} (rD[row]*upper[f])*y[l]        out = y (SENT on entry)
+//   MODE 1: DICPreconditioner::calcReciprocalD
+//           d[row] = diag[row] - sum_{(l,row) asc f} upper[f]*upper[f]/d[l];  rD = 1/d     out = pivots (scratch)
+//   MODE 2: backward sweep, tiles and rounds in reverse order
+//           z[row] = y[row] - sum_{(row,u) desc f} (rD[row]*upper[f])*z[u]                 out = z (= wA)
+//           y is complete (previous kernel) and is re-armed with SENT here for the next forward sweep; z is
+//           re-armed by k_xr_update.  wArA = sum(wA*rA) is fused: one partial per tile, summed in a fixed order.
+// Staging (all 128 threads, coalesced SELL reads): per-row {4 coefficients, 4 value indices}, start values and
+// the work-item table go to shared memory.  Then warp 0 walks the items (a round = one global dependency level
+// present in the tile, cut into passes of 32 rows) with __syncwarp between rounds, while warps 1-3 poll the
+// cross-tile inputs from global memory, in consumption order, into the value array.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) k_dic_sweeps(const SliceInfo* __restrict__ slices, int nSlices,
-                                                    const double* __restrict__ rD, const double* __restrict__ Uval,
-                                                    const int* __restrict__ Ucol, const int* __restrict__ Lidx,
-                                                    const int* __restrict__ Lcol, const double* __restrict__ rA,
-                                                    unsigned long long* y, unsigned long long* z,
-                                                    double* partials, DevState* st, int gated)
+template <int MODE>
+__global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double* __restrict__ diagOrRD,
+                                                        const double* __restrict__ Uval, const int* __restrict__ Lidx,
+                                                        const double* __restrict__ rA, unsigned long long* y,
+                                                        unsigned long long* out, double* __restrict__ rDout,
+                                                        unsigned long long* tileTicket, double* partials, int partStride,
+                                                        DevState* st, int gated)
 {
     if (gated && st->done) return;
+    constexpr bool BWD = (MODE == 2), FACTOR = (MODE == 1);
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    const SweepLayout L = sweep_layout(A.tileRowsMax, A.maxExt, A.maxItems);
+    const unsigned sb = (unsigned)__cvta_generic_to_shared(smemRaw);
+    const unsigned vb = sb + L.vals;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int s0 = blockIdx.x + gridDim.x*warp;
-    const int stride = gridDim.x*WPB;
+    const unsigned long long tBegin = (g_tileTimes && threadIdx.x == 0) ? gtime() : 0ULL;
+    const int tile = take_tile(tileTicket, A.nTiles, (int*)(smemRaw + L.slot), BWD);
+    const int r0 = A.tileStart[tile], nr = A.tileStart[tile + 1] - r0;
+    const int s0 = r0 >> 5, nsl = nr >> 5;
+    const int ip = A.tileItemPtr[tile], nItems = A.tileItemPtr[tile + 1] - ip;
+    const int xBase = A.extPtr[tile], nExt = A.extPtr[tile + 1] - xBase;
+    const int T = L.T;
 
-    // ---- forward
-    int s = s0;
-    for (; s < nSlices; s += stride)
+    // ---- staging
+    double* vals = (double*)(smemRaw + L.vals);
+    double* rowF = (double*)(smemRaw + L.rowF);
+    int* rowC = (int*)(smemRaw + L.rowC);
+    unsigned char* ovf = smemRaw + L.ovf;
+    for (int sl = warp; sl < nsl; sl += SWEEP_TPB/32)
     {
-        const SliceInfo si = slices[s];
-        const int r = s*32 + lane;
-        const double rd = rD[r];
-        double acc = __dmul_rn(rd, rA[r]);
-        for (int j0 = 0; j0 < si.widthL; j0 += 4)
+        const SliceInfo si = A.slices[s0 + sl];
+        const int off = BWD ? si.offU : si.offL, wid = BWD ? si.widthU : si.widthL;
+        const int q = sl*32 + lane;
+        const int r = r0 + q;
+        const double d = diagOrRD[r];
+        if (BWD) { vals[q] = __longlong_as_double((long long)y[r]); y[r] = SENT; }
+        else vals[q] = FACTOR ? d : __dmul_rn(d, rA[r]);
+        int nOver = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
         {
-            int col[4]; double c[4]; unsigned long long dep[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++)
+            int code = -1;
+            double cf = 0.0;
+            if (j < wid)
             {
-                col[k] = -1;
-                if (j0 + k < si.widthL)
+                const int e = off + j*32 + lane;
+                code = A.colTile[e];
+                if (code != -1)
                 {
-                    const int e = si.offL + (j0 + k)*32 + lane;
-                    col[k] = Lcol[e];
-                    if (col[k] >= 0) { c[k] = Uval[Lidx[e]]; dep[k] = peek64(y + col[k]); }
+                    const double c = BWD ? Uval[e] : Uval[Lidx[e]];
+                    cf = FACTOR ? __dmul_rn(c, c) : __dmul_rn(d, c);
                 }
             }
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-            {
-                if (col[k] >= 0)
-                {
-                    const double yl = wait_value(y + col[k], dep[k]);
-                    acc = __dsub_rn(acc, __dmul_rn(__dmul_rn(rd, c[k]), yl));
-                }
-            }
+            rowC[4*q + j] = value_index(code, T, L.one);
+            rowF[4*q + j] = cf;
         }
-        publish(y + r, acc);
+        for (int j = 4; j < wid; j++) nOver += (A.colTile[off + j*32 + lane] != -1);
+        ovf[q] = (unsigned char)nOver;
     }
+    {
+        int2* items = (int2*)(smemRaw + L.items);
+        for (int i = threadIdx.x; i < nItems + 2; i += SWEEP_TPB)
+            items[i] = (i < nItems) ? A.items[ip + (BWD ? nItems - 1 - i : i)] : make_int2(0, 0);
+        for (int i = threadIdx.x; i < nExt; i += SWEEP_TPB) ((unsigned long long*)vals)[T + i] = SENT;
+        if (threadIdx.x == 0) vals[L.one] = 1.0;
+    }
+    __syncthreads();
+    if (g_tileTimes && threadIdx.x == 0 && MODE == 0) { g_tileTimes[3*tile] = tBegin; g_tileTimes[3*tile + 1] = gtime(); }
 
-    // ---- backward, same slices in reverse
-    double dot[1] = {0.0};
-    for (s -= stride; s >= s0; s -= stride)
+    if (warp == 0)
     {
-        const SliceInfo si = slices[s];
-        const int r = s*32 + lane;
-        const double rd = rD[r];
-        const unsigned long long own = peek64(y + r);
-        double acc = 0.0;
-        bool first = true;
-        for (int j1 = si.widthU; j1 > 0; j1 -= 4)
+        // Software pipeline over the work items: in iteration i the descriptor of item i+2 and the static row data
+        // of item i+1 are requested first (consumed in later iterations); then the only wait of the iteration:
+        // the four dependency values of item i.  The item table was staged in sweep order (reversed for MODE 2).
+        const unsigned ib = sb + L.items;
+        const int syncBit = BWD ? (1 << 16) : (1 << 17);       // end of a round in sweep order
+        int2 d0 = lds_i2(ib), d1 = lds_i2(ib + 8u);
+        RowRegs cur = load_row(sb, L, d0, lane);
+        for (int i = 0; i < nItems; i++)
         {
-            int col[4]; double c[4]; unsigned long long dep[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++)
+            const int2 d2 = lds_i2(ib + 8u*(i + 2));
+            const RowRegs nxt = load_row(sb, L, d1, lane);
+            double v0, v1, v2, v3;
+            dep_values4(vb, cur.c, v0, v1, v2, v3);
+            double acc = cur.acc0;
+            if (BWD)
             {
-                col[k] = -1;
-                const int j = j1 - 1 - k;
-                if (j >= 0)
+                if (cur.ovf)        // more than four owner-side faces: the tail (descending) comes first
                 {
-                    const int e = si.offU + j*32 + lane;
-                    col[k] = Ucol[e];
-                    if (col[k] >= 0) { c[k] = Uval[e]; dep[k] = peek64(z + col[k]); }
+                    const int r = r0 + cur.q;
+                    const SliceInfo si = A.slices[r >> 5];
+                    const double d = diagOrRD[r];
+                    for (int j = si.widthU - 1; j >= 4; j--)
+                    {
+                        const int e = si.offU + j*32 + (r & 31);
+                        const int code = A.colTile[e];
+                        if (code == -1) continue;
+                        acc = __dsub_rn(acc, __dmul_rn(__dmul_rn(d, Uval[e]), dep_value(vb, value_index(code, T, L.one))));
+                    }
+                }
+                const double t0 = __dmul_rn(cur.f0, v0), t1 = __dmul_rn(cur.f1, v1);
+                const double t2 = __dmul_rn(cur.f2, v2), t3 = __dmul_rn(cur.f3, v3);
+                acc = __dsub_rn(__dsub_rn(__dsub_rn(__dsub_rn(acc, t3), t2), t1), t0);
+            }
+            else
+            {
+                double t0, t1, t2, t3;
+                if (FACTOR)
+                {
+                    // unused slots (coefficient 0, value 1) are exact no-ops: skip their ~250-cycle IEEE divisions
+                    t0 = (cur.c.x != L.one) ? __ddiv_rn(cur.f0, v0) : 0.0;
+                    t1 = (cur.c.y != L.one) ? __ddiv_rn(cur.f1, v1) : 0.0;
+                    t2 = (cur.c.z != L.one) ? __ddiv_rn(cur.f2, v2) : 0.0;
+                    t3 = (cur.c.w != L.one) ? __ddiv_rn(cur.f3, v3) : 0.0;
+                }
+                else
+                {
+                    t0 = __dmul_rn(cur.f0, v0); t1 = __dmul_rn(cur.f1, v1);
+                    t2 = __dmul_rn(cur.f2, v2); t3 = __dmul_rn(cur.f3, v3);
+                }
+                acc = __dsub_rn(__dsub_rn(__dsub_rn(__dsub_rn(acc, t0), t1), t2), t3);
+                if (cur.ovf)        // more than four neighbour-side faces: tail from global memory
+                {
+                    const int r = r0 + cur.q;
+                    const SliceInfo si = A.slices[r >> 5];
+                    const double d = diagOrRD[r];
+                    for (int j = 4; j < si.widthL; j++)
+                    {
+                        const int e = si.offL + j*32 + (r & 31);
+                        const int code = A.colTile[e];
+                        if (code == -1) break;
+                        const double c = Uval[Lidx[e]];
+                        const double vv = dep_value(vb, value_index(code, T, L.one));
+                        acc = FACTOR ? __dsub_rn(acc, __ddiv_rn(__dmul_rn(c, c), vv))
+                                     : __dsub_rn(acc, __dmul_rn(__dmul_rn(d, c), vv));
+                    }
                 }
             }
-            if (first) { acc = wait_value(y + r, own); first = false; }
-#pragma unroll
-            for (int k = 0; k < 4; k++)
+#ifdef GPUPCG_DEBUG_PRINT
+            if (MODE == 1 && tile == 1 && i < 3 && cur.q >= 0)
+                printf("tile %d item %d lane %d q %d c=(%d %d %d %d) f=(%g %g %g %g) v=(%g %g %g %g) acc0 %g acc %g one %d T %d\n",
+                       tile, i, lane, cur.q, cur.c.x, cur.c.y, cur.c.z, cur.c.w, cur.f0, cur.f1, cur.f2, cur.f3, v0, v1, v2, v3, cur.acc0, acc, L.one, T);
+#endif
+            if (cur.q >= 0)
             {
-                if (col[k] >= 0)
-                {
-                    const double zu = wait_value(z + col[k], dep[k]);
-                    acc = __dsub_rn(acc, __dmul_rn(__dmul_rn(rd, c[k]), zu));
-                }
+                sts_f64(vb + 8u*cur.q, acc);
+                publish(out + r0 + cur.q, acc);
             }
+            if (d0.y & syncBit) __syncwarp();
+            cur = nxt; d0 = d1; d1 = d2;
         }
-        if (first) acc = wait_value(y + r, own);
-        publish(z + r, acc);
-        y[r] = SENT;                 // every forward reader of y[r] has finished (they precede z[u])
-        dot[0] += acc*rA[r];
+        if (g_tileTimes && threadIdx.x == 0 && MODE == 0) g_tileTimes[3*tile + 2] = gtime();
     }
-    if (partials) grid_reduce_finish<1>(dot, partials, st, S_SWEEP, nullptr);
+    else
+    {
+        // Fetch lanes are independent state machines: each polls ITS current entry and delivers it the moment it
+        // arrives.  (A plain "wait, then store" loop reconverges the warp before the store, so an early entry was
+        // held back until the latest of its 32 warp-mates had arrived: 1.7 us per tile hop instead of ~0.5.)
+        int i = threadIdx.x - 32;
+        const unsigned long long* p = (i < nExt) ? out + A.extCol[xBase + i] : nullptr;
+        const int ns = g_spinNs;
+        while (i < nExt)
+        {
+            const unsigned long long v = peek64(p);
+            if (v != SENT)
+            {
+                sts_u64(vb + 8u*(T + i), v);
+                i += FETCHERS;
+                if (i < nExt) p = out + A.extCol[xBase + i];
+            }
+            else if (ns > 0) __nanosleep(ns);
+        }
+    }
+    if (FACTOR)
+    {
+        __syncthreads();
+        for (int q = threadIdx.x; q < nr; q += SWEEP_TPB) rDout[r0 + q] = __ddiv_rn(1.0, vals[q]);
+    }
+    if (BWD && partials)
+    {
+        __syncthreads();
+        double dot = 0.0;
+        for (int q = threadIdx.x; q < nr; q += SWEEP_TPB) dot += vals[q]*rA[r0 + q];
+        double v[1] = {dot};
+        grid_reduce_finish<1, SWEEP_TPB>(v, partials, partStride, tile, A.nTiles, st, S_SWEEP, nullptr);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -521,7 +770,7 @@ __global__ void __launch_bounds__(TPB) k_init_residual(const double* __restrict_
         rA[r] = __dsub_rn(b[r], wA[r]);
         v[0] += x[r];
     }
-    grid_reduce_finish<1>(v, partials, st, S_INIT, nullptr);
+    grid_reduce_finish<1, TPB>(v, partials, MAXPART, blockIdx.x, gridDim.x, st, S_INIT, nullptr);
 }
 
 // normFactor = sum(|Ax - t| + |b - t|) + small_ ;  sum|rA|
@@ -536,7 +785,7 @@ __global__ void __launch_bounds__(TPB) k_norm(const double* __restrict__ wA, con
         v[0] += __dadd_rn(fabs(__dsub_rn(wA[r], tr)), fabs(__dsub_rn(b[r], tr)));
         v[1] += fabs(rA[r]);
     }
-    grid_reduce_finish<2>(v, partials, st, S_NORM, nullptr);
+    grid_reduce_finish<2, TPB>(v, partials, MAXPART, blockIdx.x, gridDim.x, st, S_NORM, nullptr);
 }
 
 // pA = wA (first iteration) | wA + beta*pA,  beta = wArA/wArAold
@@ -570,7 +819,7 @@ __global__ void __launch_bounds__(TPB) k_xr_update(const double* __restrict__ pA
         v[0] += fabs(rr);
         wAbits[r] = SENT;
     }
-    grid_reduce_finish<1>(v, partials, st, S_XR, history);
+    grid_reduce_finish<1, TPB>(v, partials, MAXPART, blockIdx.x, gridDim.x, st, S_XR, history);
 }
 
 // L2 flush helper for the roofline timings

@@ -4,7 +4,9 @@
 
 #include <algorithm>
 #include <climits>
+#include <cmath>
 #include <cstdio>
+#include <queue>
 
 namespace gpupcg
 {
@@ -13,7 +15,7 @@ static const int W = 32;    // warp width == slice height
 
 int build_plan(int nCells, int nFaces, const int* l, const int* u,
                int nPatches, const int* patchSizes, const int* const* patchFaceCells,
-               const int* patchNbrRank, HostPlan& P, std::string& err)
+               const int* patchNbrRank, int tileRows, int tileMode, HostPlan& P, std::string& err)
 {
     if (nCells < 0 || nFaces < 0 || nPatches < 0 || (nFaces > 0 && (!l || !u)))
     {
@@ -25,78 +27,270 @@ int build_plan(int nCells, int nFaces, const int* l, const int* u,
         err = "gpupcg_create: nPatches > 0 but patchSizes/patchFaceCells is NULL";
         return GPUPCG_ERR_ARG;
     }
+    if (tileRows < W) tileRows = W;
+    tileRows = (tileRows/W)*W;
 
     P = HostPlan();
     P.nCells = nCells;
     P.nFaces = nFaces;
 
     // ---- validate upper-triangular order (what lduAddressing of an fvMesh guarantees) and
-    //      compute the forward dependency level of every row in the same pass:
+    //      compute the global dependency depth in the same pass (information only):
     //      level(u) = 1 + max level(l) over faces (l,u).  Valid in one ascending sweep because
     //      every face INTO row l has an owner < l and therefore a smaller face index.
     std::vector<int> level(nCells, 0);
-    int prevL = -1;
-    for (int f = 0; f < nFaces; f++)
     {
-        const int lo = l[f], up = u[f];
-        if (lo < 0 || up >= nCells || lo >= up)
+        int prevL = -1;
+        for (int f = 0; f < nFaces; f++)
         {
-            char buf[160];
-            snprintf(buf, sizeof(buf),
-                     "gpupcg_create: face %d has lowerAddr %d, upperAddr %d (need 0 <= l < u < nCells=%d)",
-                     f, lo, up, nCells);
-            err = buf;
-            return lo >= up && lo >= 0 && up < nCells ? GPUPCG_ERR_ORDERING : GPUPCG_ERR_ARG;
+            const int lo = l[f], up = u[f];
+            if (lo < 0 || up >= nCells || lo >= up)
+            {
+                char buf[160];
+                snprintf(buf, sizeof(buf),
+                         "gpupcg_create: face %d has lowerAddr %d, upperAddr %d (need 0 <= l < u < nCells=%d)",
+                         f, lo, up, nCells);
+                err = buf;
+                return lo >= up && lo >= 0 && up < nCells ? GPUPCG_ERR_ORDERING : GPUPCG_ERR_ARG;
+            }
+            if (lo < prevL)
+            {
+                char buf[160];
+                snprintf(buf, sizeof(buf),
+                         "gpupcg_create: lowerAddr not ascending at face %d (%d after %d): "
+                         "addressing is not in upper-triangular order", f, lo, prevL);
+                err = buf;
+                return GPUPCG_ERR_ORDERING;
+            }
+            prevL = lo;
+            if (level[up] < level[lo] + 1) level[up] = level[lo] + 1;
         }
-        if (lo < prevL)
-        {
-            char buf[160];
-            snprintf(buf, sizeof(buf),
-                     "gpupcg_create: lowerAddr not ascending at face %d (%d after %d): "
-                     "addressing is not in upper-triangular order", f, lo, prevL);
-            err = buf;
-            return GPUPCG_ERR_ORDERING;
-        }
-        prevL = lo;
-        if (level[up] < level[lo] + 1) level[up] = level[lo] + 1;
+        int nLevels = 0;
+        for (int c = 0; c < nCells; c++) nLevels = std::max(nLevels, level[c] + 1);
+        P.nLevels = nLevels;
+        std::vector<int> cnt(nLevels + 1, 0);
+        for (int c = 0; c < nCells; c++) cnt[level[c]]++;
+        for (int L = 0; L < nLevels; L++) P.maxLevelRows = std::max(P.maxLevelRows, cnt[L]);
     }
 
-    int nLevels = 0;
-    for (int c = 0; c < nCells; c++) nLevels = std::max(nLevels, level[c] + 1);
-    P.nLevels = nLevels;
-
-    // ---- counting sort of rows by level (stable in the original cell index), each level padded
-    //      to a whole number of slices so that a warp never straddles two levels.
-    std::vector<int> levelCount(nLevels + 1, 0);
-    for (int c = 0; c < nCells; c++) levelCount[level[c]]++;
-    P.levelSliceStart.assign(nLevels + 1, 0);
-    std::vector<long long> levelRowStart(nLevels + 1, 0);
-    for (int L = 0; L < nLevels; L++)
+    // ---- tiles: intervals of a TOPOLOGICAL ORDER of the rows => the tile graph is acyclic (a tile only ever
+    //      waits on earlier tiles).  Which topological order decides the tile shapes:
+    //        mode 0  natural cell order (l < u): tiles are index ranges -- pencils/slabs on a structured mesh,
+    //                ~1 cross-tile hop per mesh plane on the sweep's critical path;
+    //        mode 1  greedy breadth-first growth over READY rows (all lower neighbours already placed), seeded
+    //                at the lowest-level ready row: compact blobs, several times fewer hops on the critical path
+    //                and tiles created in wavefront order (the resident CTAs are the ones the wavefront needs).
+    //        mode 2  (auto when the numbering is a lexicographic structured block, i.e. every face joins c and
+    //                c+1, c+nx or c+nx*ny as blockMesh numbers a block): bricks bx x by x bz in brick-major order.
+    //                A monotone path crosses sum(n_d/b_d) brick faces instead of ~nz + ny/5 index ranges.
+    std::vector<int> order(nCells);
+    std::vector<int> cuts;                          // first position (in `order`) of every tile, + nCells
+    bool bricks = false;
+    if (tileMode == 2 && nFaces > 0)
     {
-        const int nSl = (levelCount[L] + W - 1)/W;
-        P.levelSliceStart[L + 1] = P.levelSliceStart[L] + nSl;
-        levelRowStart[L + 1] = levelRowStart[L] + (long long)nSl*W;
-        P.maxLevelRows = std::max(P.maxLevelRows, levelCount[L]);
-    }
-    if (levelRowStart[nLevels] > (long long)INT_MAX - W)
-    {
-        err = "gpupcg_create: padded row count exceeds int32";
-        return GPUPCG_ERR_ARG;
-    }
-    P.nRows = (int)levelRowStart[nLevels];
-    P.nSlices = P.nRows/W;
-    P.rowOld.assign(P.nRows, -1);
-    P.pos.assign(nCells, -1);
-    {
-        std::vector<long long> cursor(levelRowStart.begin(), levelRowStart.end() - 1);
-        for (int c = 0; c < nCells; c++)
+        // detect: at most three distinct strides u-l, 1 | nx | nx*ny, box completely filled
+        long long d[3] = {0, 0, 0};
+        int nd = 0;
+        bool ok = true;
+        for (int f = 0; f < nFaces && ok; f++)
         {
-            const int r = (int)cursor[level[c]]++;
-            P.rowOld[r] = c;
-            P.pos[c] = r;
+            const long long s = (long long)u[f] - l[f];
+            int k = 0;
+            while (k < nd && d[k] != s) k++;
+            if (k == nd) { if (nd == 3) ok = false; else d[nd++] = s; }
+        }
+        if (ok)
+        {
+            std::sort(d, d + nd);
+            long long nx = nCells, ny = 1, nz = 1;
+            if (nd >= 1 && d[0] != 1) ok = false;
+            if (ok && nd >= 2) { nx = d[1]; ny = (nd == 3) ? d[2]/d[1] : nCells/nx; if (nd == 3 && d[2] % d[1]) ok = false; }
+            if (ok) { nz = nCells/(nx*ny); if (nx*ny*nz != nCells || nx < 1 || ny < 1) ok = false; }
+            // every x-face must stay inside a mesh row etc.: count faces against the box formula
+            if (ok)
+            {
+                const long long expect = (nx - 1)*ny*nz + nx*(ny - 1)*nz + nx*ny*(nz - 1);
+                if (expect != nFaces) ok = false;
+            }
+            for (int f = 0; f < nFaces && ok; f++)
+            {
+                const long long s = (long long)u[f] - l[f], c = l[f];
+                if (s == 1 && nx > 1) { if (c % nx == nx - 1) ok = false; }
+                else if (s == nx && ny > 1) { if ((c/nx) % ny == ny - 1) ok = false; }
+            }
+            if (ok)
+            {
+                // brick edges ~ sqrt(n_d) (minimises sum n_d/b_d at fixed volume), volume <= tileRows
+                double w[3] = {std::sqrt((double)nx), std::sqrt((double)ny), std::sqrt((double)nz)};
+                double scale = std::cbrt((double)tileRows/(w[0]*w[1]*w[2]));
+                long long n3[3] = {nx, ny, nz};
+                int bb[3];
+                for (int k = 0; k < 3; k++) bb[k] = (int)std::max(1.0, std::min((double)n3[k], std::floor(w[k]*scale)));
+                for (bool grew = true; grew;)          // use up the slack left by flooring / clamping
+                {
+                    grew = false;
+                    for (int k = 0; k < 3; k++)
+                    {
+                        if (bb[k] < n3[k] && (long long)(bb[k] + 1)*bb[(k + 1) % 3]*bb[(k + 2) % 3] <= tileRows) { bb[k]++; grew = true; }
+                    }
+                }
+                const int bx = bb[0], by = bb[1], bz = bb[2];
+                // bricks in WAVEFRONT order (a+b+c ascending, then lexicographic): still topological at tile level,
+                // and the CTAs resident at any time are consecutive brick hyperplanes -- the ones the sweep is working
+                // on -- instead of a few z-layers whose tiles mostly wait (8 M cells: 5.5 ms -> see profiles/).
+                struct Brick { int s, c, b, a; };
+                std::vector<Brick> bl;
+                for (int c = 0; c*(long long)bz < nz; c++)
+                for (int b = 0; b*(long long)by < ny; b++)
+                for (int a = 0; a*(long long)bx < nx; a++) bl.push_back(Brick{a + b + c, c, b, a});
+                std::sort(bl.begin(), bl.end(), [](const Brick& x, const Brick& y)
+                          { return x.s != y.s ? x.s < y.s : (x.c != y.c ? x.c < y.c : (x.b != y.b ? x.b < y.b : x.a < y.a)); });
+                int p = 0;
+                for (const Brick& B : bl)
+                {
+                    const long long i0 = (long long)B.a*bx, j0 = (long long)B.b*by, k0 = (long long)B.c*bz;
+                    cuts.push_back(p);
+                    for (long long k = k0; k < std::min(nz, k0 + bz); k++)
+                    for (long long j = j0; j < std::min(ny, j0 + by); j++)
+                    for (long long i = i0; i < std::min(nx, i0 + bx); i++)
+                        order[p++] = (int)(i + nx*(j + ny*k));
+                }
+                cuts.push_back(p);
+                bricks = true;
+            }
+        }
+    }
+    if (bricks)
+    {
+    }
+    else if (tileMode == 0 || nFaces == 0)
+
+    {
+        for (int c = 0; c < nCells; c++) order[c] = c;
+    }
+    else
+    {
+        std::vector<int> ownerStart(nCells + 1, 0), indeg(nCells, 0);
+        for (int f = 0; f < nFaces; f++) { ownerStart[l[f] + 1]++; indeg[u[f]]++; }
+        for (int c = 0; c < nCells; c++) ownerStart[c + 1] += ownerStart[c];
+        typedef std::pair<int, int> Key;            // (level, cell)
+        std::priority_queue<Key, std::vector<Key>, std::greater<Key> > heap;
+        for (int c = 0; c < nCells; c++) if (indeg[c] == 0) heap.push(Key(level[c], c));
+        std::vector<int> q;                         // FIFO of the tile being grown
+        q.reserve(4*tileRows);
+        size_t head = 0;
+        int placed = 0, inTile = 0;
+        while (placed < nCells)
+        {
+            if (head == q.size())
+            {
+                q.clear(); head = 0;
+                q.push_back(heap.top().second);     // never empty here: the DAG always has a ready row
+                heap.pop();
+            }
+            const int r = q[head++];
+            order[placed++] = r;
+            for (int f = ownerStart[r]; f < ownerStart[r + 1]; f++)
+            {
+                if (--indeg[u[f]] == 0) q.push_back(u[f]);
+            }
+            if (++inTile == tileRows)
+            {
+                for (; head < q.size(); head++) heap.push(Key(level[q[head]], q[head]));
+                q.clear(); head = 0;
+                inTile = 0;
+            }
+        }
+    }
+    if (!bricks)
+    {
+        for (int p = 0; p < nCells; p += tileRows) cuts.push_back(p);
+        cuts.push_back(nCells);
+    }
+    const int nTiles = (int)cuts.size() - 1;
+    P.nTiles = nTiles;
+
+
+    // Round of a row = rank of its GLOBAL dependency level among the levels present in its tile.  Using the
+    // global level (not the tile-local depth) keeps all tiles marching in lock step with the global wavefront:
+    // a tile at level L only ever needs level L-1 of its neighbours, so a consumer tile trails its producer by
+    // one hand-off, however the tile boundaries cut the mesh rows (tile-local depths made tiles wait for values
+    // their predecessor produces o(tile) rounds later -- measured 10x slower, profiles/r1_dic_sweep_design.md).
+    std::vector<int> lvl(nCells, 0);
+    {
+        std::vector<int> present;
+        for (int t = 0; t < nTiles; t++)
+        {
+            const int i0 = cuts[t], i1 = cuts[t + 1];
+            present.clear();
+            for (int i = i0; i < i1; i++) present.push_back(level[order[i]]);
+            std::sort(present.begin(), present.end());
+            present.erase(std::unique(present.begin(), present.end()), present.end());
+            for (int i = i0; i < i1; i++)
+                lvl[order[i]] = (int)(std::lower_bound(present.begin(), present.end(), level[order[i]]) - present.begin());
         }
     }
     std::vector<int>().swap(level);
+
+    // ---- new numbering: tile-major, rows of a tile sorted by round (stable), tile padded to x32
+    P.tileStart.assign(nTiles + 1, 0);
+    P.tileRoundPtr.assign(nTiles + 1, 0);
+    P.pos.assign(nCells, -1);
+    {
+        long long row = 0;
+        std::vector<int> cnt;
+        for (int t = 0; t < nTiles; t++)
+        {
+            const int i0 = cuts[t], i1 = cuts[t + 1];
+            int K = 0;
+            for (int i = i0; i < i1; i++) K = std::max(K, lvl[order[i]] + 1);
+            cnt.assign(K + 1, 0);
+            for (int i = i0; i < i1; i++) cnt[lvl[order[i]] + 1]++;
+            for (int k = 0; k < K; k++) cnt[k + 1] += cnt[k];
+            const int padded = ((i1 - i0 + W - 1)/W)*W;
+            P.tileStart[t] = (int)row;
+            for (int k = 0; k < K; k++) P.roundStart.push_back(cnt[k]);
+            P.roundStart.push_back(padded);         // padding rows ride in the last round
+            P.tileRoundPtr[t + 1] = (int)P.roundStart.size();
+            P.maxRounds = std::max(P.maxRounds, K);
+            P.tileRowsMax = std::max(P.tileRowsMax, padded);
+            for (int i = i0; i < i1; i++) P.pos[order[i]] = (int)row + cnt[lvl[order[i]]]++;
+            row += padded;
+            if (row > (long long)INT_MAX - W)
+            {
+                err = "gpupcg_create: padded row count exceeds int32";
+                return GPUPCG_ERR_ARG;
+            }
+        }
+        P.tileStart[nTiles] = (int)row;
+        P.nRows = (int)row;
+        P.nSlices = P.nRows/W;
+    }
+    std::vector<int>().swap(order);
+    // work items: every round cut into passes of <= 32 rows; bit 16 = first pass of its round, bit 17 = last
+    P.tileItemPtr.assign(nTiles + 1, 0);
+    for (int t = 0; t < nTiles; t++)
+    {
+        const int* rs = &P.roundStart[P.tileRoundPtr[t]];
+        const int K = P.tileRoundPtr[t + 1] - P.tileRoundPtr[t] - 1;
+        for (int k = 0; k < K; k++)
+        {
+            for (int a = rs[k]; a < rs[k + 1]; a += W)
+            {
+                const int cnt = std::min(W, rs[k + 1] - a);
+                int flags = 0;
+                if (a == rs[k]) flags |= 1 << 16;
+                if (a + W >= rs[k + 1]) flags |= 1 << 17;
+                P.items.push_back(a);
+                P.items.push_back(cnt | flags);
+            }
+        }
+        P.tileItemPtr[t + 1] = (int)P.items.size()/2;
+        P.maxItems = std::max(P.maxItems, P.tileItemPtr[t + 1] - P.tileItemPtr[t]);
+    }
+    std::vector<int>().swap(lvl);
+    P.rowOld.assign(P.nRows, -1);
+    for (int c = 0; c < nCells; c++) P.rowOld[P.pos[c]] = c;
 
     // ---- per-row entry counts and per-slice widths
     std::vector<unsigned char> nU(P.nRows, 0), nL(P.nRows, 0);
@@ -141,25 +335,84 @@ int build_plan(int nCells, int nFaces, const int* l, const int* u,
     P.UfaceOld.assign(totU, -1);
     P.Lidx.assign(totL, -1);
     P.Lcol.assign(totL, -1);
-    std::vector<int> faceU(nFaces);
-    std::fill(nU.begin(), nU.end(), 0);
-    std::fill(nL.begin(), nL.end(), 0);
-    for (int f = 0; f < nFaces; f++)
     {
-        const int r = P.pos[l[f]];
-        const int j = nU[r]++;
-        const int idx = P.slices[r/W].offU + j*W + (r % W);
-        P.Ucol[idx] = P.pos[u[f]];
-        P.UfaceOld[idx] = f;
-        faceU[f] = idx;
+        std::vector<int> faceU(nFaces);
+        std::vector<unsigned char> cu(P.nRows, 0), cl(P.nRows, 0);
+        for (int f = 0; f < nFaces; f++)
+        {
+            const int r = P.pos[l[f]];
+            const int j = cu[r]++;
+            const int idx = P.slices[r/W].offU + j*W + (r % W);
+            P.Ucol[idx] = P.pos[u[f]];
+            P.UfaceOld[idx] = f;
+            faceU[f] = idx;
+        }
+        for (int f = 0; f < nFaces; f++)
+        {
+            const int r = P.pos[u[f]];
+            const int j = cl[r]++;
+            const int idx = P.slices[r/W].offL + j*W + (r % W);
+            P.Lidx[idx] = faceU[f];
+            P.Lcol[idx] = P.pos[l[f]];
+        }
     }
-    for (int f = 0; f < nFaces; f++)
+
+    // ---- tile view of the columns + external (cross-tile) lists in consumption order
+    P.LcolTile.assign(totL, -1);
+    P.UcolTile.assign(totU, -1);
+    P.extFPtr.assign(nTiles + 1, 0);
+    P.extBPtr.assign(nTiles + 1, 0);
+    for (int t = 0; t < nTiles; t++)
     {
-        const int r = P.pos[u[f]];
-        const int j = nL[r]++;
-        const int idx = P.slices[r/W].offL + j*W + (r % W);
-        P.Lidx[idx] = faceU[f];
-        P.Lcol[idx] = P.pos[l[f]];
+        const int r0 = P.tileStart[t], r1 = P.tileStart[t + 1];
+        const int s0 = r0/W, s1 = r1/W;
+        const int eL = (s1 < P.nSlices ? P.slices[s1].offL : (int)totL) - P.slices[s0].offL;
+        const int eU = (s1 < P.nSlices ? P.slices[s1].offU : (int)totU) - P.slices[s0].offU;
+        P.maxTileEntriesL = std::max(P.maxTileEntriesL, eL);
+        P.maxTileEntriesU = std::max(P.maxTileEntriesU, eU);
+        // forward: rounds ascending = rows ascending, entries ascending
+        const int baseF = (int)P.extFCol.size();
+        for (int r = r0; r < r1; r++)
+        {
+            const SliceInfo& si = P.slices[r/W];
+            for (int j = 0; j < nL[r]; j++)
+            {
+                const int e = si.offL + j*W + (r % W);
+                const int col = P.Lcol[e];
+                if (col >= r0 && col < r1) P.LcolTile[e] = col - r0;
+                else
+                {
+                    P.LcolTile[e] = -2 - ((int)P.extFCol.size() - baseF);
+                    P.extFCol.push_back(col);
+                }
+            }
+        }
+        P.extFPtr[t + 1] = (int)P.extFCol.size();
+        P.maxTileExtF = std::max(P.maxTileExtF, P.extFPtr[t + 1] - baseF);
+        // backward: rounds descending, rows of a round ascending, entries descending
+        const int baseB = (int)P.extBCol.size();
+        const int* rs = &P.roundStart[P.tileRoundPtr[t]];
+        const int K = P.tileRoundPtr[t + 1] - P.tileRoundPtr[t] - 1;
+        for (int k = K - 1; k >= 0; k--)
+        {
+            for (int r = r0 + rs[k]; r < r0 + rs[k + 1]; r++)
+            {
+                const SliceInfo& si = P.slices[r/W];
+                for (int j = nU[r] - 1; j >= 0; j--)
+                {
+                    const int e = si.offU + j*W + (r % W);
+                    const int col = P.Ucol[e];
+                    if (col >= r0 && col < r1) P.UcolTile[e] = col - r0;
+                    else
+                    {
+                        P.UcolTile[e] = -2 - ((int)P.extBCol.size() - baseB);
+                        P.extBCol.push_back(col);
+                    }
+                }
+            }
+        }
+        P.extBPtr[t + 1] = (int)P.extBCol.size();
+        P.maxTileExtB = std::max(P.maxTileExtB, P.extBPtr[t + 1] - baseB);
     }
 
     // ---- coupled interfaces

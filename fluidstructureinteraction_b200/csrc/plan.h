@@ -1,5 +1,5 @@
-// plan.h -- host-side analysis of an lduAddressing: the wavefront ("level") ordering of the DIC
-// dependency graph and the SELL-32 row storage every kernel of the solver walks.
+// plan.h -- host-side analysis of an lduAddressing: row tiling + per-tile wavefront schedule for the
+// DIC sweeps, and the SELL-32 row storage every kernel of the solver walks.
 //
 // Reference semantics being scheduled (foam-extend-3.1 [EXT], restated in SURVEY.md Appendix A):
 //   Amul           for f ascending: Ax[u[f]] += lower[f]*x[l[f]];  Ax[l[f]] += upper[f]*x[u[f]]
@@ -10,6 +10,14 @@
 // loops is: neighbour-side faces (u == row) ascending f, then owner-side faces (l == row)
 // ascending f.  The plan stores exactly those two lists per row, so a one-thread-per-row gather
 // reproduces the face loops bit for bit, whatever order the rows are scheduled in.
+//
+// Scheduling.  The triangular sweeps are a dependency chain as long as the mesh is "deep"
+// (nx+ny+nz-2 levels on a structured box).  A hand-off between SMs through L2 costs 0.3-4 us on
+// B200 (tools/hop_latency.cu, profiles/), a hand-off inside an SM through shared memory ~0.05 us.
+// So rows are grouped into TILES (intervals of a topological order => the tile graph is acyclic);
+// one CTA sweeps one tile round by round (round = tile-local dependency level) out of shared memory
+// and only the edges that cross tiles go through global memory.  Rows are renumbered tile-major,
+// round-sorted inside a tile; every vector of the solver lives in that numbering.
 #pragma once
 #include <vector>
 #include <string>
@@ -17,7 +25,7 @@
 namespace gpupcg
 {
 
-struct SliceInfo        // one warp-wide slice of 32 rows (all rows of a slice share a level)
+struct SliceInfo        // one warp-wide slice of 32 consecutive (new-numbering) rows
 {
     int offU;           // first entry of the owner-side block  (entry = offU + j*32 + lane)
     int widthU;         // owner-side entries per row in this slice (max over its 32 rows)
@@ -29,9 +37,9 @@ struct HostPlan
 {
     int nCells = 0;
     int nFaces = 0;
-    int nRows = 0;              // padded
+    int nRows = 0;              // padded (every tile is a whole number of slices)
     int nSlices = 0;
-    int nLevels = 0;
+    int nLevels = 0;            // global dependency depth (information only)
     int maxLevelRows = 0;
     long long entriesU = 0;
     long long entriesL = 0;
@@ -39,12 +47,31 @@ struct HostPlan
     std::vector<int> rowOld;    // [nRows]  new row -> original cell, -1 for padding rows
     std::vector<int> pos;       // [nCells] original cell -> new row
     std::vector<SliceInfo> slices;
-    std::vector<int> levelSliceStart;   // [nLevels+1]
 
     std::vector<int> Ucol;      // [entriesU] column (new numbering) of owner-side entry, -1 = pad
     std::vector<int> UfaceOld;  // [entriesU] original face id of that entry, -1 = pad
     std::vector<int> Lidx;      // [entriesL] index into the U value array of the same face, -1 = pad
     std::vector<int> Lcol;      // [entriesL] column (new numbering), -1 = pad
+
+    // ---- tiles
+    int tileRowsMax = 0;                // largest tile (rows, padded)
+    int nTiles = 0;
+    int maxRounds = 0;
+    int maxTileEntriesL = 0, maxTileEntriesU = 0;       // SELL entries (incl. padding) of the largest tile
+    int maxTileExtF = 0, maxTileExtB = 0;
+    std::vector<int> tileStart;         // [nTiles+1] first row of each tile (multiple of 32)
+    std::vector<int> tileRoundPtr;      // [nTiles+1] into roundStart (tile t owns K_t+1 entries)
+    std::vector<int> roundStart;        // tile-relative first row of each round, last = tile rows
+    // work items of the sweep warp: a round cut into passes of <= 32 rows.  item = {first row, count | flags}
+    std::vector<int> tileItemPtr;       // [nTiles+1]
+    std::vector<int> items;             // 2 ints per item
+    int maxItems = 0;
+    // per-entry column seen from the tile sweep: >= 0 tile-local row, -1 pad, <= -2 external: -2-k = k-th
+    // entry of the tile's external list (values fetched from global memory by the fetch warps)
+    std::vector<int> LcolTile;          // [entriesL]  (forward / factor)
+    std::vector<int> UcolTile;          // [entriesU]  (backward)
+    std::vector<int> extFPtr, extFCol;  // forward: [nTiles+1], global rows in consumption order
+    std::vector<int> extBPtr, extBCol;  // backward
 
     // coupled interfaces, grouped by row: for every row that owns interface faces, its entries in
     // (patch, face-in-patch) order -- the order updateMatrixInterfaces applies them in.
@@ -57,9 +84,10 @@ struct HostPlan
     std::vector<int> ifFaceRow;     // [nIfaceFaces] new row id of faceCells (send gather), concat order
 };
 
-// Returns 0 or a negative gpupcg error code; err receives the text.
+// tileRows: target rows per tile (multiple of 32); tileMode: 0 natural-order intervals, 1 greedy compact blobs.
+// Returns 0 or a negative gpupcg error code.
 int build_plan(int nCells, int nFaces, const int* lowerAddr, const int* upperAddr,
                int nPatches, const int* patchSizes, const int* const* patchFaceCells,
-               const int* patchNbrRank, HostPlan& plan, std::string& err);
+               const int* patchNbrRank, int tileRows, int tileMode, HostPlan& plan, std::string& err);
 
 } // namespace gpupcg

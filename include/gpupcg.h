@@ -72,10 +72,16 @@ typedef struct gpupcg_plan_info
     long long entriesLower;     /* SELL-32 storage incl. padding, neighbour side   */
     int       nInterfaceFaces;  /* coupled patch faces                             */
     int       nInterfaces;
-    int       sweepGrid;        /* CTAs of the persistent DIC kernel               */
+    int       sweepGrid;        /* CTAs of the DIC sweep kernels (= nTiles)        */
     int       streamGrid;       /* CTAs of the streaming kernels                   */
     int       numSMs;
-    int       reserved;
+    int       nTiles;           /* row tiles of the DIC sweeps (one CTA each)      */
+    int       tileRowsMax;
+    int       maxRounds;        /* longest tile-local dependency chain             */
+    int       sweepSmemBytes;   /* dynamic shared memory of a sweep CTA            */
+    int       extForward;       /* cross-tile dependencies, forward / backward     */
+    int       extBackward;
+    int       roundEntries;     /* length of the roundStart table                  */
 } gpupcg_plan_info;
 
 /* ---- life cycle ----------------------------------------------------------------------------
@@ -94,6 +100,13 @@ int gpupcg_create(gpupcg_handle* h, int device,
 int gpupcg_destroy(gpupcg_handle h);
 const char* gpupcg_last_error(gpupcg_handle h);   /* h may be NULL: last create() error */
 int gpupcg_get_plan_info(gpupcg_handle h, gpupcg_plan_info* info);
+
+/* Debug (GPUPCG_TILE_TRACE=1 at create): {CTA start, staging done, sweep done} %globaltimer stamps of every
+ * tile of the last forward sweep, 3*nTiles values.                                                       */
+int gpupcg_debug_tile_trace(gpupcg_handle h, unsigned long long* out3n);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches evidence). */
+int gpupcg_launch_count(gpupcg_handle h, long long* count);
 
 /* Run all later work of this handle on an externally owned cudaStream_t (e.g. torch's
  * current stream, so that the caller's CUDA events bracket the kernels).  NULL restores the
@@ -157,13 +170,17 @@ int gpupcg_comm_init(gpupcg_handle h, int rank, int nRanks, const void* ncclUniq
 int gpupcg_host_register(void* ptr, unsigned long long bytes);
 int gpupcg_host_unregister(void* ptr);
 
-/* Host-only (no GPU needed): build the wavefront / SELL-32 schedule create() would build and copy it
- * out, so that CPU tests can check the schedule against the reference face order.  Call once with
- * NULL arrays to obtain the sizes in *info, then again with arrays of nRows, 4*nSlices,
- * entriesUpper (x2) and entriesLower (x2) ints.                                                   */
-int gpupcg_plan_export(int nCells, int nFaces, const int* lowerAddr, const int* upperAddr,
-                       gpupcg_plan_info* info, int* rowOld, int* sliceInfo,
-                       int* Ucol, int* UfaceOld, int* Lidx, int* Lcol);
+/* Host-only (no GPU needed): build the tiling / SELL-32 schedule create() would build and copy it out, so
+ * that CPU tests can check the schedule against the reference face order.  Call once with arrays == NULL to
+ * obtain the sizes in *info, then with an array of GPUPCG_PLAN_NARRAYS int pointers (any may be NULL):
+ *  0 rowOld[nRows]  1 sliceInfo[4*nSlices]  2 Ucol  3 UfaceOld [entriesUpper]  4 Lidx  5 Lcol [entriesLower]
+ *  6 tileStart  7 tileRoundPtr [nTiles+1]  8 roundStart[roundEntries]  9 LcolTile[entriesLower]
+ * 10 UcolTile[entriesUpper]  11 extFPtr[nTiles+1]  12 extFCol[extForward]  13 extBPtr[nTiles+1]
+ * 14 extBCol[extBackward]                                                                              */
+#define GPUPCG_PLAN_NARRAYS 15
+int gpupcg_plan_export(int nCells, int nFaces, const int* lowerAddr, const int* upperAddr, int tileRows,
+                       int tileMode /* 0 natural-order intervals, 1 greedy compact blobs (create() default) */,
+                       gpupcg_plan_info* info, int** arrays);
 
 /* Library / device report: fills a short text (device name, SM count, cc) into buf. */
 int gpupcg_device_report(int device, char* buf, int bufLen);

@@ -47,9 +47,15 @@ def test_plan_rejects_non_upper_triangular():
 
 
 def emulate(plan, diag, upper, l, u):
-    """numpy emulation of the row walks of k_amul / k_dic_factor / k_dic_sweeps on the exported schedule."""
+    """numpy emulation of the row walks of k_amul / k_dic_fwd / k_dic_bwd on the exported schedule: tile by
+    tile, round by round, in-tile values from the tile-local array, cross-tile values through the external
+    lists -- exactly the indexing the kernels use."""
     rowOld, slices = plan["rowOld"], plan["slices"]
     Ucol, UfaceOld, Lidx, Lcol = plan["Ucol"], plan["UfaceOld"], plan["Lidx"], plan["Lcol"]
+    tileStart, tileRoundPtr, roundStart = plan["tileStart"], plan["tileRoundPtr"], plan["roundStart"]
+    LcolTile, UcolTile = plan["LcolTile"], plan["UcolTile"]
+    extFPtr, extFCol, extBPtr, extBCol = plan["extFPtr"], plan["extFCol"], plan["extBPtr"], plan["extBCol"]
+    nT = plan["info"]["nTiles"]
     nR = rowOld.shape[0]
     real = rowOld >= 0
     d = np.where(real, diag[np.maximum(rowOld, 0)], 1.0)
@@ -63,69 +69,117 @@ def emulate(plan, diag, upper, l, u):
         out[rowOld[real]] = v[real]
         return out
 
-    def entries(r):
-        s, lane = divmod(r, 32)
-        offU, wU, offL, wL = slices[s]
-        lo = [(Uval[Lidx[offL + j*32 + lane]], Lcol[offL + j*32 + lane]) for j in range(wL)
-              if Lcol[offL + j*32 + lane] >= 0]
-        up = [(Uval[offU + j*32 + lane], Ucol[offU + j*32 + lane]) for j in range(wU)
-              if Ucol[offU + j*32 + lane] >= 0]
-        return lo, up
-
     def amul(x):
         xp = rows_in(x)
         Ax = np.zeros(nR)
         for r in range(nR):
-            lo, up = entries(r)
+            s, lane = divmod(r, 32)
+            offU, wU, offL, wL = slices[s]
             acc = d[r]*xp[r]
-            for c, col in lo + up:
-                acc = acc + c*xp[col]
+            for j in range(wL):
+                e = offL + j*32 + lane
+                if Lcol[e] >= 0:
+                    acc = acc + Uval[Lidx[e]]*xp[Lcol[e]]
+            for j in range(wU):
+                e = offU + j*32 + lane
+                if Ucol[e] >= 0:
+                    acc = acc + Uval[e]*xp[Ucol[e]]
             Ax[r] = acc
         return rows_out(Ax)
 
+    def forward(init, coef_of, combine):
+        """generic forward tile sweep: out[r] = init[r] (-) combine(coef, dep)"""
+        out = np.full(nR, np.nan)
+        for t in range(nT):
+            r0, r1 = tileStart[t], tileStart[t + 1]
+            rs = roundStart[tileRoundPtr[t]:tileRoundPtr[t + 1]]
+            ext = extFCol[extFPtr[t]:extFPtr[t + 1]]
+            assert np.all(ext < r0)                              # cross-tile inputs come from earlier tiles
+            vs = init[r0:r1].copy()
+            for k in range(len(rs) - 1):
+                new = {}
+                for q in range(rs[k], rs[k + 1]):
+                    r = r0 + q
+                    s, lane = divmod(r, 32)
+                    offU, wU, offL, wL = slices[s]
+                    acc = vs[q]
+                    for j in range(wL):
+                        e = offL + j*32 + lane
+                        c = LcolTile[e]
+                        if c == -1:
+                            break
+                        if c >= 0:
+                            assert not any(rs[k] <= c < rs[k + 1] for _ in [0]), "dependency inside a round"
+                            v = vs[c]
+                        else:
+                            v = out[ext[-2 - c]]
+                            assert not np.isnan(v)
+                        acc = combine(acc, coef_of(r, Uval[Lidx[e]]), v)
+                    new[q] = acc
+                for q, a in new.items():
+                    vs[q] = a
+                    out[r0 + q] = a
+        return out
+
     def factor():
-        piv = np.zeros(nR)
-        for r in range(nR):             # rows are in topological order
-            lo, _ = entries(r)
-            acc = d[r]
-            for c, col in lo:
-                acc = acc - (c*c)/piv[col]
-            piv[r] = acc
+        piv = forward(d.copy(), lambda r, c: c*c, lambda acc, cf, v: acc - cf/v)
         return 1.0/piv
 
     def precondition(rD, rA):
         rp = rows_in(rA)
-        y = np.zeros(nR)
-        for r in range(nR):
-            lo, _ = entries(r)
-            acc = rD[r]*rp[r]
-            for c, col in lo:
-                acc = acc - (rD[r]*c)*y[col]
-            y[r] = acc
-        z = np.zeros(nR)
-        for r in range(nR - 1, -1, -1):
-            _, up = entries(r)
-            acc = y[r]
-            for c, col in reversed(up):
-                acc = acc - (rD[r]*c)*z[col]
-            z[r] = acc
+        y = forward(rD*rp, lambda r, c: rD[r]*c, lambda acc, cf, v: acc - cf*v)
+        z = np.full(nR, np.nan)
+        for t in range(nT - 1, -1, -1):
+            r0, r1 = tileStart[t], tileStart[t + 1]
+            rs = roundStart[tileRoundPtr[t]:tileRoundPtr[t + 1]]
+            ext = extBCol[extBPtr[t]:extBPtr[t + 1]]
+            assert np.all(ext >= r1)
+            vs = y[r0:r1].copy()
+            for k in range(len(rs) - 2, -1, -1):
+                new = {}
+                for q in range(rs[k], rs[k + 1]):
+                    r = r0 + q
+                    s, lane = divmod(r, 32)
+                    offU, wU, offL, wL = slices[s]
+                    acc = vs[q]
+                    for j in range(wU - 1, -1, -1):
+                        e = offU + j*32 + lane
+                        c = UcolTile[e]
+                        if c == -1:
+                            continue
+                        v = vs[c] if c >= 0 else z[ext[-2 - c]]
+                        assert not np.isnan(v)
+                        acc = acc - (rD[r]*Uval[e])*v
+                    new[q] = acc
+                for q, a in new.items():
+                    vs[q] = a
+                    z[r0 + q] = a
         return rows_out(z)
 
     return amul, factor, precondition, rows_out
 
 
-def check_schedule(l, u, n, seed=3):
-    plan = pkg.plan_export(l, u, n)
+def check_schedule(l, u, n, seed=3, tileRows=64, tileMode=1):
+    plan = pkg.plan_export(l, u, n, tileRows, tileMode)
     info = plan["info"]
     rowOld = plan["rowOld"]
-    # permutation is a bijection onto the real rows, levels are warp-aligned
+    # permutation is a bijection onto the real rows; tiles are whole slices
     real = rowOld[rowOld >= 0]
     assert np.array_equal(np.sort(real), np.arange(n))
     assert info["nRows"] % 32 == 0 and info["nSlices"]*32 == info["nRows"]
+    assert np.all(plan["tileStart"] % 32 == 0) and plan["tileStart"][-1] == info["nRows"]
     pos = np.empty(n, dtype=np.int64)
     pos[rowOld[rowOld >= 0]] = np.flatnonzero(rowOld >= 0)
-    # topological: every face goes from an earlier slice to a later one (so a warp never waits on itself)
-    assert np.all(pos[l] // 32 < pos[u] // 32)
+    # acyclic tile graph, and inside a tile every face goes from an earlier round to a later one
+    tile = np.searchsorted(plan["tileStart"], pos, side="right") - 1
+    assert np.all(tile[l] <= tile[u])
+    rnd = np.empty(n, dtype=np.int64)
+    for t in range(info["nTiles"]):
+        rs = plan["roundStart"][plan["tileRoundPtr"][t]:plan["tileRoundPtr"][t + 1]]
+        sel = tile == t
+        rnd[sel] = np.searchsorted(rs, pos[sel] - plan["tileStart"][t], side="right") - 1
+    same = tile[l] == tile[u]
+    assert np.all(rnd[l][same] < rnd[u][same])
     # every face appears exactly once on each side
     assert np.array_equal(np.sort(plan["UfaceOld"][plan["UfaceOld"] >= 0]), np.arange(l.shape[0]))
     assert int((plan["Lcol"] >= 0).sum()) == l.shape[0]
@@ -144,8 +198,9 @@ def check_schedule(l, u, n, seed=3):
 def test_schedule_reproduces_reference_order_hex(dims):
     nx, ny, nz = dims
     l, u = meshes.hex_ldu(nx, ny, nz)
-    info = check_schedule(l, u, nx*ny*nz)
-    assert info["nLevels"] == nx + ny + nz - 2        # hyperplanes i+j+k = const
+    for tileRows, tileMode in ((32, 0), (32, 1), (64, 1), (64, 2), (32, 2), (1024, 2)):
+        info = check_schedule(l, u, nx*ny*nz, tileRows=tileRows, tileMode=tileMode)
+        assert info["nLevels"] == nx + ny + nz - 2        # hyperplanes i+j+k = const
 
 
 def test_schedule_reproduces_reference_order_shipped_beam():
