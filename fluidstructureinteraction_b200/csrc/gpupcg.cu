@@ -33,19 +33,19 @@ struct gpupcg_handle_s
 
     // plan (device)
     SliceInfo* dSlices = nullptr;
-    int *dUcol = nullptr, *dUfaceOld = nullptr, *dLidx = nullptr, *dLcol = nullptr, *dRowOld = nullptr;
+    int *dUfaceOld = nullptr, *dRowOld = nullptr;
     int *dIfRow = nullptr, *dIfRowStart = nullptr, *dIfEntry = nullptr, *dIfFaceRow = nullptr;
     unsigned int* dIfMask = nullptr;
     int nIfRows = 0;
     // tiling of the DIC sweeps (device)
     int *dTileStart = nullptr, *dTileItemPtr = nullptr, *dItems = nullptr;
-    int *dLcolTile = nullptr, *dUcolTile = nullptr;
-    int *dExtFPtr = nullptr, *dExtFCol = nullptr, *dExtBPtr = nullptr, *dExtBCol = nullptr;
+    unsigned short *dColL16 = nullptr, *dIdxL16 = nullptr, *dColU16 = nullptr;
+    int *dExtFPtr = nullptr, *dExtFCol = nullptr, *dExtFIdx = nullptr, *dExtBPtr = nullptr, *dExtBCol = nullptr;
     unsigned long long* dTileTicket = nullptr;
     unsigned long long* dTileTrace = nullptr;
-    size_t smemFwd = 0, smemBwd = 0;
+    size_t smemFwd = 0, smemBwd = 0, smemAmul = 0;
     int partStride = MAXPART;
-    TileArgs tileF, tileB;
+    TileArgs tiles;
 
     // matrix + vectors (device, wavefront order unless noted)
     double *dDiag = nullptr, *dUval = nullptr, *dRD = nullptr;
@@ -146,12 +146,12 @@ extern "C" int gpupcg_destroy(gpupcg_handle h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->comm.destroy();
-    void* ptrs[] = {h->dSlices, h->dUcol, h->dUfaceOld, h->dLidx, h->dLcol, h->dRowOld, h->dIfRow,
+    void* ptrs[] = {h->dSlices, h->dUfaceOld, h->dRowOld, h->dIfRow,
                     h->dIfRowStart, h->dIfEntry, h->dIfFaceRow, h->dIfMask, h->dDiag, h->dUval, h->dRD,
                     h->dX, h->dB, h->dRA, h->dWA, h->dPA, h->dY, h->dStageA, h->dStageB, h->dStageF,
                     h->dBou, h->dXNbr, h->dSend, h->dPartials, h->dHistory, h->dState, h->dFlush,
-                    h->dTileStart, h->dTileItemPtr, h->dItems, h->dLcolTile, h->dUcolTile,
-                    h->dExtFPtr, h->dExtFCol, h->dExtBPtr, h->dExtBCol, h->dTileTicket};
+                    h->dTileStart, h->dTileItemPtr, h->dItems, h->dColL16, h->dIdxL16, h->dColU16,
+                    h->dExtFPtr, h->dExtFCol, h->dExtFIdx, h->dExtBPtr, h->dExtBCol, h->dTileTicket};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->hState) cudaFreeHost(h->hState);
     if (h->hHistory) cudaFreeHost(h->hHistory);
@@ -197,14 +197,17 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     {
         rc = build_plan(nCells, nFaces, l, u, nPatches, patchSizes, patchFaceCells, patchNbrRank, tileRows,
                         env_int("GPUPCG_TILE_MODE", 2), h->plan, h->err);
-        if (rc != GPUPCG_OK) return rc;
+        if (rc != GPUPCG_OK && rc != -100) return rc;
         const HostPlan& Q = h->plan;
-        h->smemFwd = sweep_layout(Q.tileRowsMax, Q.maxTileExtF, Q.maxItems).bytes;
-        h->smemBwd = sweep_layout(Q.tileRowsMax, Q.maxTileExtB, Q.maxItems).bytes;
-        if (std::max(h->smemFwd, h->smemBwd) <= smemCap || tileRows <= 32) break;
+        h->smemFwd = sweep_layout(Q.tileRowsMax, Q.maxTileExtF, Q.maxItems, std::max(Q.maxTileEntriesU, Q.maxTileEntriesL), Q.maxTileEntriesL).bytes;
+        h->smemBwd = sweep_layout(Q.tileRowsMax, Q.maxTileExtB, Q.maxItems, Q.maxTileEntriesU, Q.maxTileEntriesL).bytes;
+        h->smemAmul = amul_layout(Q.tileRowsMax, Q.maxTileEntriesU, Q.maxTileEntriesL, Q.maxTileExtF, Q.maxTileExtB).bytes;
+        const size_t need = std::max(h->smemAmul, std::max(h->smemFwd, h->smemBwd));
+        if (rc == GPUPCG_OK && need <= smemCap) break;
+        if (tileRows <= 32) break;
         tileRows /= 2;
     }
-    if (std::max(h->smemFwd, h->smemBwd) > smemCap)
+    if (rc != GPUPCG_OK || std::max(h->smemAmul, std::max(h->smemFwd, h->smemBwd)) > smemCap)
     {
         h->err = "gpupcg_create: a single 32-row tile does not fit in shared memory (rows with too many faces)";
         return GPUPCG_ERR_UNSUPPORTED;
@@ -221,16 +224,16 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     CK(cudaFuncSetAttribute(k_dic_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwd));
     CK(cudaFuncSetAttribute(k_dic_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwd));
     CK(cudaFuncSetAttribute(k_dic_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBwd));
+    CK(cudaFuncSetAttribute(k_amul_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemAmul));
+    CK(cudaFuncSetAttribute(k_amul_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemAmul));
+    CK(cudaFuncSetAttribute(k_amul_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemAmul));
     h->sweepGrid = std::max(1, P.nTiles);
     int sbps = std::max(1, env_int("GPUPCG_STREAM_BPS", 8));
     h->streamGrid = std::min(h->numSMs*sbps, MAXPART);
 
     cudaStream_t s = h->stream;
     CK(upload(h->dSlices, P.slices, s));
-    CK(upload(h->dUcol, P.Ucol, s));
     CK(upload(h->dUfaceOld, P.UfaceOld, s));
-    CK(upload(h->dLidx, P.Lidx, s));
-    CK(upload(h->dLcol, P.Lcol, s));
     CK(upload(h->dRowOld, P.rowOld, s));
     CK(upload(h->dIfRow, P.ifRow, s));
     CK(upload(h->dIfRowStart, P.ifRowStart, s));
@@ -239,10 +242,12 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     CK(upload(h->dTileStart, P.tileStart, s));
     CK(upload(h->dTileItemPtr, P.tileItemPtr, s));
     CK(upload(h->dItems, P.items, s));
-    CK(upload(h->dLcolTile, P.LcolTile, s));
-    CK(upload(h->dUcolTile, P.UcolTile, s));
+    CK(upload(h->dColL16, P.colL16, s));
+    CK(upload(h->dIdxL16, P.idxL16, s));
+    CK(upload(h->dColU16, P.colU16, s));
     CK(upload(h->dExtFPtr, P.extFPtr, s));
     CK(upload(h->dExtFCol, P.extFCol, s));
+    CK(upload(h->dExtFIdx, P.extFIdx, s));
     CK(upload(h->dExtBPtr, P.extBPtr, s));
     CK(upload(h->dExtBCol, P.extBCol, s));
     if (env_int("GPUPCG_TILE_TRACE", 0))
@@ -283,17 +288,20 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
 
     TileArgs T;
     T.slices = h->dSlices; T.tileStart = h->dTileStart; T.tileItemPtr = h->dTileItemPtr; T.items = (const int2*)h->dItems;
+    T.colL16 = h->dColL16; T.idxL16 = h->dIdxL16; T.colU16 = h->dColU16;
+    T.extFPtr = h->dExtFPtr; T.extFCol = h->dExtFCol; T.extFIdx = h->dExtFIdx;
+    T.extBPtr = h->dExtBPtr; T.extBCol = h->dExtBCol;
     T.nTiles = P.nTiles; T.tileRowsMax = P.tileRowsMax; T.maxItems = P.maxItems;
-    h->tileF = T; h->tileF.colTile = h->dLcolTile; h->tileF.extPtr = h->dExtFPtr; h->tileF.extCol = h->dExtFCol;
-    h->tileF.maxExt = P.maxTileExtF;
-    h->tileB = T; h->tileB.colTile = h->dUcolTile; h->tileB.extPtr = h->dExtBPtr; h->tileB.extCol = h->dExtBCol;
-    h->tileB.maxExt = P.maxTileExtB;
+    T.maxEU = P.maxTileEntriesU; T.maxEL = P.maxTileEntriesL; T.maxExtF = P.maxTileExtF; T.maxExtB = P.maxTileExtB;
+    h->tiles = T;
 
     // the big host index arrays are no longer needed
     std::vector<int>().swap(P.Ucol); std::vector<int>().swap(P.UfaceOld);
     std::vector<int>().swap(P.Lidx); std::vector<int>().swap(P.Lcol);
     std::vector<int>().swap(P.LcolTile); std::vector<int>().swap(P.UcolTile);
-    std::vector<int>().swap(P.extFCol); std::vector<int>().swap(P.extBCol);
+    std::vector<int>().swap(P.extFCol); std::vector<int>().swap(P.extBCol); std::vector<int>().swap(P.extFIdx);
+    std::vector<unsigned short>().swap(P.colL16); std::vector<unsigned short>().swap(P.idxL16);
+    std::vector<unsigned short>().swap(P.colU16);
     std::vector<int>().swap(P.roundStart); std::vector<int>().swap(P.items);
     return GPUPCG_OK;
 }
@@ -496,17 +504,20 @@ static int enqueue_amul(gpupcg_handle h, int mode, const double* x, double* Ax, 
 {
     const HostPlan& P = h->plan;
     cudaStream_t s = h->stream;
-    const int g = std::min(h->streamGrid, std::max(1, (P.nSlices + WPB - 1)/WPB));
     const bool ifaces = P.nIfaceFaces > 0;
     int rc;
     if (ifaces && mode != 2 && !xNbrReady) { rc = halo_exchange(h, x); if (rc) return rc; }
     const unsigned int* mask = (ifaces && mode == 1) ? h->dIfMask : nullptr;
-    if (mode == 0)
-        LAUNCH(k_amul<0>, g, s, h->dSlices, P.nSlices, h->dDiag, h->dUval, h->dUcol, h->dLidx, h->dLcol, h->dRowOld, mask, x, Ax, h->dPartials, h->dState);
-    else if (mode == 1)
-        LAUNCH(k_amul<1>, g, s, h->dSlices, P.nSlices, h->dDiag, h->dUval, h->dUcol, h->dLidx, h->dLcol, h->dRowOld, mask, x, Ax, h->dPartials, h->dState);
-    else
-        LAUNCH(k_amul<2>, g, s, h->dSlices, P.nSlices, h->dDiag, h->dUval, h->dUcol, h->dLidx, h->dLcol, h->dRowOld, mask, x, Ax, h->dPartials, h->dState);
+    if (P.nTiles > 0)
+    {
+        h->launches++;
+        if (mode == 0)
+            k_amul_tile<0><<<P.nTiles, AMUL_TPB, h->smemAmul, s>>>(h->tiles, h->dDiag, h->dUval, h->dRowOld, mask, x, Ax, h->dPartials, h->partStride, h->dState);
+        else if (mode == 1)
+            k_amul_tile<1><<<P.nTiles, AMUL_TPB, h->smemAmul, s>>>(h->tiles, h->dDiag, h->dUval, h->dRowOld, mask, x, Ax, h->dPartials, h->partStride, h->dState);
+        else
+            k_amul_tile<2><<<P.nTiles, AMUL_TPB, h->smemAmul, s>>>(h->tiles, h->dDiag, h->dUval, h->dRowOld, mask, x, Ax, h->dPartials, h->partStride, h->dState);
+    }
     if (ifaces)
     {
         const int gi = grid_for(h->nIfRows, h->streamGrid);
@@ -526,7 +537,7 @@ static int enqueue_factor(gpupcg_handle h, int gated)
 {
     if (h->plan.nTiles == 0) return GPUPCG_OK;
     fill_sent(h, h->dY);
-    LAUNCH_SWEEP(k_dic_tile<1>, h->smemFwd, h->tileF, h->dDiag, h->dUval, h->dLidx, nullptr, nullptr,
+    LAUNCH_SWEEP(k_dic_tile<1>, h->smemFwd, h->tiles, h->dDiag, h->dUval, nullptr, nullptr,
                  (unsigned long long*)h->dY, h->dRD, h->dTileTicket, nullptr, 0, h->dState, gated);
     fill_sent(h, h->dY);
     CK(cudaGetLastError());
@@ -537,9 +548,9 @@ static int enqueue_factor(gpupcg_handle h, int gated)
 static int enqueue_sweeps(gpupcg_handle h, const double* rA, double* z, bool reduce, int gated)
 {
     if (h->plan.nTiles == 0) return GPUPCG_OK;
-    LAUNCH_SWEEP(k_dic_tile<0>, h->smemFwd, h->tileF, h->dRD, h->dUval, h->dLidx, rA, nullptr,
+    LAUNCH_SWEEP(k_dic_tile<0>, h->smemFwd, h->tiles, h->dRD, h->dUval, rA, nullptr,
                  (unsigned long long*)h->dY, nullptr, h->dTileTicket, nullptr, 0, h->dState, gated);
-    LAUNCH_SWEEP(k_dic_tile<2>, h->smemBwd, h->tileB, h->dRD, h->dUval, nullptr, rA, (unsigned long long*)h->dY,
+    LAUNCH_SWEEP(k_dic_tile<2>, h->smemBwd, h->tiles, h->dRD, h->dUval, rA, (unsigned long long*)h->dY,
                  (unsigned long long*)z, nullptr, h->dTileTicket, reduce ? h->dPartials : nullptr, h->partStride,
                  h->dState, gated);
     CK(cudaGetLastError());

@@ -269,70 +269,6 @@ __global__ void __launch_bounds__(TPB) k_iface_update(const int* __restrict__ if
 }
 
 // ------------------------------------------------------------------------------------------
-// K8  lduMatrix::Amul  [EXT lduMatrixATmul.C], row-gather form.
-// MODE 0: Ax = A x                      (test entry, first residual)
-// MODE 1: Ax = A x and  sum(Ax*x)       (PCG: wA = A pA, wApA = gSumProd(wA, pA)); gated on st->done
-// MODE 2: Ax = A (xRef field)           (normFactor)
-// ifMask (may be null): bit k of ifMask[s] set = row owns coupled faces; such rows are left out of
-// the MODE-1 dot here and added by k_iface_update once the halo has arrived.
-// ------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(TPB) k_amul(const SliceInfo* __restrict__ slices, int nSlices,
-                                              const double* __restrict__ diag, const double* __restrict__ Uval,
-                                              const int* __restrict__ Ucol, const int* __restrict__ Lidx,
-                                              const int* __restrict__ Lcol, const int* __restrict__ rowOld,
-                                              const unsigned int* __restrict__ ifMask,
-                                              const double* __restrict__ x, double* __restrict__ Ax,
-                                              double* partials, DevState* st)
-{
-    if (MODE == 1 && st->done) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double xc = (MODE == 2) ? st->xRef : 0.0;
-    double dot[1] = {0.0};
-    for (int s = blockIdx.x + gridDim.x*warp; s < nSlices; s += gridDim.x*WPB)
-    {
-        const SliceInfo si = slices[s];
-        const int r = s*32 + lane;
-        double xr;
-        if (MODE == 2) xr = (rowOld[r] >= 0) ? xc : 0.0; else xr = x[r];
-        double acc = __dmul_rn(diag[r], xr);
-        // neighbour-side faces (u == row), ascending f
-#pragma unroll 4
-        for (int j = 0; j < si.widthL; j++)
-        {
-            const int e = si.offL + j*32 + lane;
-            const int col = Lcol[e];
-            if (col >= 0)
-            {
-                const double c = Uval[Lidx[e]];
-                const double xv = (MODE == 2) ? xc : x[col];
-                acc = __dadd_rn(acc, __dmul_rn(c, xv));
-            }
-        }
-        // owner-side faces (l == row), ascending f
-#pragma unroll 4
-        for (int j = 0; j < si.widthU; j++)
-        {
-            const int e = si.offU + j*32 + lane;
-            const int col = Ucol[e];
-            if (col >= 0)
-            {
-                const double c = Uval[e];
-                const double xv = (MODE == 2) ? xc : x[col];
-                acc = __dadd_rn(acc, __dmul_rn(c, xv));
-            }
-        }
-        Ax[r] = acc;
-        if (MODE == 1)
-        {
-            const bool masked = ifMask && ((ifMask[s] >> lane) & 1u);
-            if (!masked) dot[0] += acc*xr;
-        }
-    }
-    if (MODE == 1) grid_reduce_finish<1, TPB>(dot, partials, MAXPART, blockIdx.x, gridDim.x, st, S_AMUL, nullptr);
-}
-
-// ------------------------------------------------------------------------------------------
 // dataflow primitives of the tiled sweeps: across tiles the value IS the flag (SENT = not yet).
 // ------------------------------------------------------------------------------------------
 __device__ int g_spinNs = 0;     // back-off of the global polls (0 = tight), set from GPUPCG_SPIN_NS
@@ -378,38 +314,222 @@ __device__ __forceinline__ double wait_shared(const unsigned long long* p)
     return __longlong_as_double((long long)v);
 }
 
-// Static description of the tiling handed to the sweep kernels.
+// Static description of the tiling handed to the tile kernels (Amul, DIC factor, DIC sweeps).
+// Everything a tile needs lives in CONTIGUOUS global ranges (rows are numbered tile-major, the SELL blocks of a
+// tile are adjacent), so a tile is staged into shared memory with a handful of 1-D bulk copies (cp.async.bulk,
+// SASS UBLKCP) completing on one mbarrier -- no per-thread dependent index->value load chains.
 struct TileArgs
 {
     const SliceInfo* slices;
-    const int* tileStart;       // [nTiles+1]
-    const int* tileItemPtr;     // [nTiles+1]
-    const int2* items;          // {first row, count | first<<16 | last<<17}
-    const int* colTile;         // LcolTile (forward/factor) or UcolTile (backward)
-    const int* extPtr;          // [nTiles+1]
-    const int* extCol;
+    const int* tileStart;           // [nTiles+1]
+    const int* tileItemPtr;         // [nTiles+1]
+    const int2* items;              // {first row, count | first<<16 | last<<17}
+    const unsigned short* colL16;   // neighbour-side column codes   (0xFFFF pad, 0x8000|k cross-tile, else local row)
+    const unsigned short* idxL16;   // neighbour-side coefficient: index into the tile's U block (local owners)
+    const unsigned short* colU16;   // owner-side column codes
+    const int* extFPtr;             // [nTiles+1] cross-tile entries of the neighbour side ...
+    const int* extFCol;             //   their global rows
+    const int* extFIdx;             //   and the U-array index of their coefficient
+    const int* extBPtr;             // owner side
+    const int* extBCol;
     int nTiles;
-    int tileRowsMax, maxExt, maxItems;      // shared-memory carve-up
+    int tileRowsMax, maxEU, maxEL, maxExtF, maxExtB, maxItems;     // shared-memory carve-up
 };
+
+// ---- mbarrier + 1-D bulk copy (TMA) primitives
+__device__ __forceinline__ void mbar_init(unsigned bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar)
+{
+    if (bytes)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned phase)
+{
+    unsigned ok = 0;
+    while (!ok)
+    {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(phase) : "memory");
+    }
+}
+
+// Tiles are handed out in launch order through a never-reset ticket: CTA k of a launch gets tile
+// k mod nTiles (forward) or its mirror (backward).  A running CTA therefore only ever waits on tiles whose
+// CTAs are already running or finished: no deadlock, whatever the hardware's block scheduling order.
+__device__ __forceinline__ int take_tile(unsigned long long* tileTicket, int nTiles, int* slot, bool backward)
+{
+    if (threadIdx.x == 0)
+    {
+        const unsigned long long t = atomicAdd(tileTicket, 1ULL);
+        const int k = (int)(t % (unsigned long long)nTiles);
+        *slot = backward ? nTiles - 1 - k : k;
+    }
+    __syncthreads();
+    return *slot;
+}
+
+// ------------------------------------------------------------------------------------------
+// K8  lduMatrix::Amul  [EXT lduMatrixATmul.C], one CTA per tile, row-gather form out of shared memory.
+// MODE 0: Ax = A x                      (test entry, first residual)
+// MODE 1: Ax = A x and  sum(Ax*x)       (PCG: wA = A pA, wApA = gSumProd(wA, pA)); gated on st->done
+// MODE 2: Ax = A (xRef field)           (normFactor)
+// Bulk-staged per tile: U coefficient block, 16-bit column/coefficient codes, diag, x.  Cross-tile x values and
+// cross-tile neighbour-side coefficients are gathered (L2 hits: the owning tile streams them too).
+// Per-row operand order = reference face order: diag*x, neighbour-side faces ascending, owner-side ascending.
+// ifMask (may be null): rows that own coupled faces are left out of the MODE-1 dot here (k_iface_update adds them).
+// ------------------------------------------------------------------------------------------
+static constexpr int AMUL_TPB = 256;
+
+struct AmulLayout
+{
+    unsigned Ub, diag, xs, xF, cF, xB, colU, colL, idxL, sl, bar, bytes;
+};
+
+__host__ __device__ inline AmulLayout amul_layout(int T, int EU, int EL, int XF, int XB)
+{
+    AmulLayout L;
+    const unsigned xf = (XF + 1) & ~1, xb = (XB + 1) & ~1;
+    L.Ub = 0;
+    L.diag = L.Ub + 8u*EU;
+    L.xs = L.diag + 8u*T;
+    L.xF = L.xs + 8u*T;
+    L.cF = L.xF + 8u*xf;
+    L.xB = L.cF + 8u*xf;
+    L.colU = L.xB + 8u*xb;
+    L.colL = L.colU + 2u*EU;
+    L.idxL = L.colL + 2u*EL;
+    L.sl = L.idxL + 2u*EL;
+    L.bar = L.sl + 16u*(T/32 + 1);
+    L.bytes = L.bar + 16;
+    return L;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(AMUL_TPB) k_amul_tile(TileArgs A, const double* __restrict__ diag,
+                                                        const double* __restrict__ Uval, const int* __restrict__ rowOld,
+                                                        const unsigned int* __restrict__ ifMask,
+                                                        const double* __restrict__ x, double* __restrict__ Ax,
+                                                        double* partials, int partStride, DevState* st)
+{
+    if (MODE == 1 && st->done) return;
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    const AmulLayout L = amul_layout(A.tileRowsMax, A.maxEU, A.maxEL, A.maxExtF, A.maxExtB);
+    const unsigned sb = (unsigned)__cvta_generic_to_shared(smemRaw);
+    const int tile = blockIdx.x;
+    const int r0 = A.tileStart[tile], nr = A.tileStart[tile + 1] - r0;
+    const int s0 = r0 >> 5, nsl = nr >> 5;
+    const SliceInfo first = A.slices[s0], last = A.slices[s0 + nsl - 1];
+    const int eU0 = first.offU, nEU = last.offU + 32*last.widthU - eU0;
+    const int eL0 = first.offL, nEL = last.offL + 32*last.widthL - eL0;
+    const int fBase = A.extFPtr[tile], nXF = A.extFPtr[tile + 1] - fBase;
+    const int bBase = A.extBPtr[tile], nXB = A.extBPtr[tile + 1] - bBase;
+
+    if (threadIdx.x == 0)
+    {
+        mbar_init(sb + L.bar, 1);
+        const unsigned bytes = 8u*nEU + 2u*nEU + 4u*nEL + 8u*nr + (MODE == 2 ? 0u : 8u*nr) + 16u*nsl;
+        mbar_expect_tx(sb + L.bar, bytes);
+        bulk_g2s(sb + L.Ub, Uval + eU0, 8u*nEU, sb + L.bar);
+        bulk_g2s(sb + L.colU, A.colU16 + eU0, 2u*nEU, sb + L.bar);
+        bulk_g2s(sb + L.colL, A.colL16 + eL0, 2u*nEL, sb + L.bar);
+        bulk_g2s(sb + L.idxL, A.idxL16 + eL0, 2u*nEL, sb + L.bar);
+        bulk_g2s(sb + L.diag, diag + r0, 8u*nr, sb + L.bar);
+        if (MODE != 2) bulk_g2s(sb + L.xs, x + r0, 8u*nr, sb + L.bar);
+        bulk_g2s(sb + L.sl, A.slices + s0, 16u*nsl, sb + L.bar);
+    }
+    // meanwhile: cross-tile values (gathers, mostly L2 hits)
+    double* xF = (double*)(smemRaw + L.xF);
+    double* cF = (double*)(smemRaw + L.cF);
+    double* xB = (double*)(smemRaw + L.xB);
+    const double xc = (MODE == 2) ? st->xRef : 0.0;
+    for (int k = threadIdx.x; k < nXF; k += AMUL_TPB)
+    {
+        xF[k] = (MODE == 2) ? xc : x[A.extFCol[fBase + k]];
+        cF[k] = Uval[A.extFIdx[fBase + k]];
+    }
+    for (int k = threadIdx.x; k < nXB; k += AMUL_TPB) xB[k] = (MODE == 2) ? xc : x[A.extBCol[bBase + k]];
+    double* xs = (double*)(smemRaw + L.xs);
+    if (MODE == 2)
+    {
+        for (int q = threadIdx.x; q < nr; q += AMUL_TPB) xs[q] = (rowOld[r0 + q] >= 0) ? xc : 0.0;
+    }
+    __syncthreads();                    // mbarrier init + gathers visible
+    mbar_wait(sb + L.bar, 0);
+
+    const double* Ub = (const double*)(smemRaw + L.Ub);
+    const double* dg = (const double*)(smemRaw + L.diag);
+    const unsigned short* colU = (const unsigned short*)(smemRaw + L.colU);
+    const unsigned short* colL = (const unsigned short*)(smemRaw + L.colL);
+    const unsigned short* idxL = (const unsigned short*)(smemRaw + L.idxL);
+    const SliceInfo* sl = (const SliceInfo*)(smemRaw + L.sl);
+    double dot[1] = {0.0};
+    for (int q = threadIdx.x; q < nr; q += AMUL_TPB)
+    {
+        const SliceInfo si = sl[q >> 5];
+        const int ln = q & 31;
+        const double xr = xs[q];
+        double acc = __dmul_rn(dg[q], xr);
+        // neighbour-side faces (u == row), ascending f
+        for (int j = 0; j < si.widthL; j++)
+        {
+            const int e = si.offL - eL0 + j*32 + ln;
+            const unsigned c = colL[e];
+            if (c == 0xFFFFu) break;
+            double cf, xv;
+            if (c & 0x8000u) { cf = cF[c & 0x7FFFu]; xv = xF[c & 0x7FFFu]; }
+            else { cf = Ub[idxL[e]]; xv = xs[c]; }
+            acc = __dadd_rn(acc, __dmul_rn(cf, xv));
+        }
+        // owner-side faces (l == row), ascending f
+        for (int j = 0; j < si.widthU; j++)
+        {
+            const int e = si.offU - eU0 + j*32 + ln;
+            const unsigned c = colU[e];
+            if (c == 0xFFFFu) break;
+            const double xv = (c & 0x8000u) ? xB[c & 0x7FFFu] : xs[c];
+            acc = __dadd_rn(acc, __dmul_rn(Ub[e], xv));
+        }
+        Ax[r0 + q] = acc;
+        if (MODE == 1)
+        {
+            const int r = r0 + q;
+            const bool masked = ifMask && ((ifMask[r >> 5] >> (r & 31)) & 1u);
+            if (!masked) dot[0] += acc*xr;
+        }
+    }
+    if (MODE == 1) grid_reduce_finish<1, AMUL_TPB>(dot, partials, partStride, tile, A.nTiles, st, S_AMUL, nullptr);
+}
 
 static constexpr int SWEEP_TPB = 128;       // warp 0 sweeps, warps 1-3 fetch cross-tile values
 static constexpr int FETCHERS = SWEEP_TPB - 32;
 
-// Shared-memory carve-up of one sweep CTA (byte offsets, all 16 B aligned):
+// Shared-memory carve-up of one sweep CTA (byte offsets, all 16 B aligned).
+//  working set of the round loop:
 //   vals  [NV]  doubles: [0,T) the tile's rows, [T,T+X) cross-tile inputs (SENT until a fetch warp delivers
 //               them), [T+X] a constant 1.0 that unused entry slots point at with a zero coefficient, so the
 //               round loop is branch-free (acc - 0*1 == acc and acc - 0/1 == acc exactly)
 //   rowF  [4T]  doubles: the first four coefficients of every row
 //   rowC  [4T]  ints   : their value indices
 //   items [I+2] int2   : work items
-//   ovf   [T]   bytes  : entries beyond the first four (walked from global memory; polyhedral cells only)
+//   ovf   [T]   bytes  : entries beyond the first four (walked from the staged SELL block; polyhedral cells only)
+//  staging area (bulk copies land here; rowF/rowC are built from it):
+//   Ub [E] doubles, col [E] u16, idx [EL] u16, dv [T] (rD or diag), av [T] (rA or y), cX [X] cross-tile coefficients
 struct SweepLayout
 {
     int T, X, NV, one;
-    unsigned vals, rowF, rowC, items, ovf, slot, bytes;
+    unsigned vals, rowF, rowC, items, ovf, slot, Ub, col, idx, dv, av, cX, sl, bar, bytes;
 };
 
-__host__ __device__ inline SweepLayout sweep_layout(int T, int X, int I)
+__host__ __device__ inline SweepLayout sweep_layout(int T, int X, int I, int E, int EL)
 {
     SweepLayout L;
     L.T = T; L.X = X;
@@ -421,7 +541,15 @@ __host__ __device__ inline SweepLayout sweep_layout(int T, int X, int I)
     L.items = L.rowC + 16u*T;
     L.ovf = L.items + 8u*(I + 2);
     L.slot = L.ovf + T;
-    L.bytes = L.slot + 16;
+    L.Ub = (L.slot + 16 + 15) & ~15u;
+    L.dv = L.Ub + 8u*E;
+    L.av = L.dv + 8u*T;
+    L.cX = L.av + 8u*T;
+    L.col = L.cX + 8u*((X + 1) & ~1);
+    L.idx = L.col + 2u*E;
+    L.sl = L.idx + 2u*EL;
+    L.bar = L.sl + 16u*(T/32 + 1);
+    L.bytes = L.bar + 16;
     return L;
 }
 
@@ -477,25 +605,10 @@ __device__ __forceinline__ int lds_u8(unsigned a)
     return v;
 }
 
-// Tiles are handed out in launch order through a never-reset ticket: CTA k of a launch gets tile
-// k mod nTiles (forward) or its mirror (backward).  A running CTA therefore only ever waits on tiles whose
-// CTAs are already running or finished: no deadlock, whatever the hardware's block scheduling order.
-__device__ __forceinline__ int take_tile(unsigned long long* tileTicket, int nTiles, int* slot, bool backward)
+// value index of a 16-bit tile column code: local row, cross-tile slot, or the constant slot for a pad
+__device__ __forceinline__ int value_index16(unsigned code, int T, int one)
 {
-    if (threadIdx.x == 0)
-    {
-        const unsigned long long t = atomicAdd(tileTicket, 1ULL);
-        const int k = (int)(t % (unsigned long long)nTiles);
-        *slot = backward ? nTiles - 1 - k : k;
-    }
-    __syncthreads();
-    return *slot;
-}
-
-// value index of a tile column code: >= 0 tile row, <= -2 cross-tile slot, -1 unused
-__device__ __forceinline__ int value_index(int code, int T, int one)
-{
-    return code >= 0 ? code : (code == -1 ? one : T + (-2 - code));
+    return code == 0xFFFFu ? one : ((code & 0x8000u) ? T + (int)(code & 0x7FFFu) : (int)code);
 }
 
 __device__ __forceinline__ bool is_sent(double v)
@@ -563,14 +676,15 @@ __device__ __forceinline__ double dep_value(unsigned vb, int idx)
 //           z[row] = y[row] - sum_{(row,u) desc f} (rD[row]*upper[f])*z[u]                 out = z (= wA)
 //           y is complete (previous kernel) and is re-armed with SENT here for the next forward sweep; z is
 //           re-armed by k_xr_update.  wArA = sum(wA*rA) is fused: one partial per tile, summed in a fixed order.
-// Staging (all 128 threads, coalesced SELL reads): per-row {4 coefficients, 4 value indices}, start values and
-// the work-item table go to shared memory.  Then warp 0 walks the items (a round = one global dependency level
-// present in the tile, cut into passes of 32 rows) with __syncwarp between rounds, while warps 1-3 poll the
-// cross-tile inputs from global memory, in consumption order, into the value array.
+// Staging: thread 0 issues the bulk copies of the tile's blocks (coefficients, 16-bit codes, rD/diag, rA/y) onto
+// one mbarrier while all threads gather the cross-tile coefficients; then per-row {4 coefficients, 4 value
+// indices} and the start values are built in shared memory.  Then warp 0 walks the work items (a round = one
+// global dependency level present in the tile, cut into passes of 32 rows) with __syncwarp between rounds, while
+// warps 1-3 poll the cross-tile inputs from global memory, in consumption order, into the value array.
 // ------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double* __restrict__ diagOrRD,
-                                                        const double* __restrict__ Uval, const int* __restrict__ Lidx,
+                                                        const double* __restrict__ Uval,
                                                         const double* __restrict__ rA, unsigned long long* y,
                                                         unsigned long long* out, double* __restrict__ rDout,
                                                         unsigned long long* tileTicket, double* partials, int partStride,
@@ -578,8 +692,9 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
 {
     if (gated && st->done) return;
     constexpr bool BWD = (MODE == 2), FACTOR = (MODE == 1);
-    extern __shared__ __align__(16) unsigned char smemRaw[];
-    const SweepLayout L = sweep_layout(A.tileRowsMax, A.maxExt, A.maxItems);
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    const int X = BWD ? A.maxExtB : A.maxExtF;
+    const SweepLayout L = sweep_layout(A.tileRowsMax, X, A.maxItems, BWD ? A.maxEU : max(A.maxEU, A.maxEL), A.maxEL);
     const unsigned sb = (unsigned)__cvta_generic_to_shared(smemRaw);
     const unsigned vb = sb + L.vals;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -588,44 +703,36 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
     const int r0 = A.tileStart[tile], nr = A.tileStart[tile + 1] - r0;
     const int s0 = r0 >> 5, nsl = nr >> 5;
     const int ip = A.tileItemPtr[tile], nItems = A.tileItemPtr[tile + 1] - ip;
-    const int xBase = A.extPtr[tile], nExt = A.extPtr[tile + 1] - xBase;
+    const int xBase = BWD ? A.extBPtr[tile] : A.extFPtr[tile];
+    const int nExt = (BWD ? A.extBPtr[tile + 1] : A.extFPtr[tile + 1]) - xBase;
+    const int* extCol = BWD ? A.extBCol : A.extFCol;
     const int T = L.T;
+    const SliceInfo first = A.slices[s0], last = A.slices[s0 + nsl - 1];
+    const int eU0 = first.offU, nEU = last.offU + 32*last.widthU - eU0;
+    const int eL0 = first.offL, nEL = last.offL + 32*last.widthL - eL0;
 
-    // ---- staging
-    double* vals = (double*)(smemRaw + L.vals);
-    double* rowF = (double*)(smemRaw + L.rowF);
-    int* rowC = (int*)(smemRaw + L.rowC);
-    unsigned char* ovf = smemRaw + L.ovf;
-    for (int sl = warp; sl < nsl; sl += SWEEP_TPB/32)
+    // ---- staging: bulk copies (one mbarrier) + cross-tile coefficient gathers
+    if (threadIdx.x == 0)
     {
-        const SliceInfo si = A.slices[s0 + sl];
-        const int off = BWD ? si.offU : si.offL, wid = BWD ? si.widthU : si.widthL;
-        const int q = sl*32 + lane;
-        const int r = r0 + q;
-        const double d = diagOrRD[r];
-        if (BWD) { vals[q] = __longlong_as_double((long long)y[r]); y[r] = SENT; }
-        else vals[q] = FACTOR ? d : __dmul_rn(d, rA[r]);
-        int nOver = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++)
+        mbar_init(sb + L.bar, 1);
+        unsigned bytes = 8u*nEU + 8u*nr + 16u*nsl + (FACTOR ? 0u : 8u*nr) + (BWD ? 2u*nEU : 4u*nEL);
+        mbar_expect_tx(sb + L.bar, bytes);
+        bulk_g2s(sb + L.Ub, Uval + eU0, 8u*nEU, sb + L.bar);
+        bulk_g2s(sb + L.dv, diagOrRD + r0, 8u*nr, sb + L.bar);
+        if (!FACTOR) bulk_g2s(sb + L.av, BWD ? (const void*)(y + r0) : (const void*)(rA + r0), 8u*nr, sb + L.bar);
+        bulk_g2s(sb + L.sl, A.slices + s0, 16u*nsl, sb + L.bar);
+        if (BWD) bulk_g2s(sb + L.col, A.colU16 + eU0, 2u*nEU, sb + L.bar);
+        else
         {
-            int code = -1;
-            double cf = 0.0;
-            if (j < wid)
-            {
-                const int e = off + j*32 + lane;
-                code = A.colTile[e];
-                if (code != -1)
-                {
-                    const double c = BWD ? Uval[e] : Uval[Lidx[e]];
-                    cf = FACTOR ? __dmul_rn(c, c) : __dmul_rn(d, c);
-                }
-            }
-            rowC[4*q + j] = value_index(code, T, L.one);
-            rowF[4*q + j] = cf;
+            bulk_g2s(sb + L.col, A.colL16 + eL0, 2u*nEL, sb + L.bar);
+            bulk_g2s(sb + L.idx, A.idxL16 + eL0, 2u*nEL, sb + L.bar);
         }
-        for (int j = 4; j < wid; j++) nOver += (A.colTile[off + j*32 + lane] != -1);
-        ovf[q] = (unsigned char)nOver;
+    }
+    double* vals = (double*)(smemRaw + L.vals);
+    double* cX = (double*)(smemRaw + L.cX);
+    if (!BWD)
+    {
+        for (int k = threadIdx.x; k < nExt; k += SWEEP_TPB) cX[k] = Uval[A.extFIdx[xBase + k]];
     }
     {
         int2* items = (int2*)(smemRaw + L.items);
@@ -633,6 +740,49 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
             items[i] = (i < nItems) ? A.items[ip + (BWD ? nItems - 1 - i : i)] : make_int2(0, 0);
         for (int i = threadIdx.x; i < nExt; i += SWEEP_TPB) ((unsigned long long*)vals)[T + i] = SENT;
         if (threadIdx.x == 0) vals[L.one] = 1.0;
+    }
+    __syncthreads();
+    mbar_wait(sb + L.bar, 0);
+
+    // ---- build the round loop's working set from the staged blocks
+    const double* Ub = (const double*)(smemRaw + L.Ub);
+    const double* dv = (const double*)(smemRaw + L.dv);
+    const double* av = (const double*)(smemRaw + L.av);
+    const unsigned short* colS = (const unsigned short*)(smemRaw + L.col);
+    const unsigned short* idxS = (const unsigned short*)(smemRaw + L.idx);
+    const SliceInfo* sl = (const SliceInfo*)(smemRaw + L.sl);
+    double* rowF = (double*)(smemRaw + L.rowF);
+    int* rowC = (int*)(smemRaw + L.rowC);
+    unsigned char* ovf = smemRaw + L.ovf;
+    for (int q = threadIdx.x; q < nr; q += SWEEP_TPB)
+    {
+        const SliceInfo si = sl[q >> 5];
+        const int wid = BWD ? si.widthU : si.widthL;
+        const int off = (BWD ? si.offU - eU0 : si.offL - eL0) + (q & 31);
+        const double d = dv[q];
+        if (BWD) { vals[q] = av[q]; y[r0 + q] = SENT; }
+        else vals[q] = FACTOR ? d : __dmul_rn(d, av[q]);
+        int nOver = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+            unsigned code = 0xFFFFu;
+            double cf = 0.0;
+            if (j < wid)
+            {
+                const int e = off + j*32;
+                code = colS[e];
+                if (code != 0xFFFFu)
+                {
+                    const double c = BWD ? Ub[e] : ((code & 0x8000u) ? cX[code & 0x7FFFu] : Ub[idxS[e]]);
+                    cf = FACTOR ? __dmul_rn(c, c) : __dmul_rn(d, c);
+                }
+            }
+            rowC[4*q + j] = value_index16(code, T, L.one);
+            rowF[4*q + j] = cf;
+        }
+        for (int j = 4; j < wid; j++) nOver += (colS[off + j*32] != 0xFFFFu);
+        ovf[q] = (unsigned char)nOver;
     }
     __syncthreads();
     if (g_tileTimes && threadIdx.x == 0 && MODE == 0) { g_tileTimes[3*tile] = tBegin; g_tileTimes[3*tile + 1] = gtime(); }
@@ -657,15 +807,14 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
             {
                 if (cur.ovf)        // more than four owner-side faces: the tail (descending) comes first
                 {
-                    const int r = r0 + cur.q;
-                    const SliceInfo si = A.slices[r >> 5];
-                    const double d = diagOrRD[r];
+                    const SliceInfo si = sl[cur.q >> 5];
+                    const int off = si.offU - eU0 + (cur.q & 31);
+                    const double d = dv[cur.q];
                     for (int j = si.widthU - 1; j >= 4; j--)
                     {
-                        const int e = si.offU + j*32 + (r & 31);
-                        const int code = A.colTile[e];
-                        if (code == -1) continue;
-                        acc = __dsub_rn(acc, __dmul_rn(__dmul_rn(d, Uval[e]), dep_value(vb, value_index(code, T, L.one))));
+                        const unsigned code = colS[off + j*32];
+                        if (code == 0xFFFFu) continue;
+                        acc = __dsub_rn(acc, __dmul_rn(__dmul_rn(d, Ub[off + j*32]), dep_value(vb, value_index16(code, T, L.one))));
                     }
                 }
                 const double t0 = __dmul_rn(cur.f0, v0), t1 = __dmul_rn(cur.f1, v1);
@@ -689,28 +838,22 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
                     t2 = __dmul_rn(cur.f2, v2); t3 = __dmul_rn(cur.f3, v3);
                 }
                 acc = __dsub_rn(__dsub_rn(__dsub_rn(__dsub_rn(acc, t0), t1), t2), t3);
-                if (cur.ovf)        // more than four neighbour-side faces: tail from global memory
+                if (cur.ovf)        // more than four neighbour-side faces: tail from the staged SELL block
                 {
-                    const int r = r0 + cur.q;
-                    const SliceInfo si = A.slices[r >> 5];
-                    const double d = diagOrRD[r];
+                    const SliceInfo si = sl[cur.q >> 5];
+                    const int off = si.offL - eL0 + (cur.q & 31);
+                    const double d = dv[cur.q];
                     for (int j = 4; j < si.widthL; j++)
                     {
-                        const int e = si.offL + j*32 + (r & 31);
-                        const int code = A.colTile[e];
-                        if (code == -1) break;
-                        const double c = Uval[Lidx[e]];
-                        const double vv = dep_value(vb, value_index(code, T, L.one));
+                        const unsigned code = colS[off + j*32];
+                        if (code == 0xFFFFu) break;
+                        const double c = (code & 0x8000u) ? cX[code & 0x7FFFu] : Ub[idxS[off + j*32]];
+                        const double vv = dep_value(vb, value_index16(code, T, L.one));
                         acc = FACTOR ? __dsub_rn(acc, __ddiv_rn(__dmul_rn(c, c), vv))
                                      : __dsub_rn(acc, __dmul_rn(__dmul_rn(d, c), vv));
                     }
                 }
             }
-#ifdef GPUPCG_DEBUG_PRINT
-            if (MODE == 1 && tile == 1 && i < 3 && cur.q >= 0)
-                printf("tile %d item %d lane %d q %d c=(%d %d %d %d) f=(%g %g %g %g) v=(%g %g %g %g) acc0 %g acc %g one %d T %d\n",
-                       tile, i, lane, cur.q, cur.c.x, cur.c.y, cur.c.z, cur.c.w, cur.f0, cur.f1, cur.f2, cur.f3, v0, v1, v2, v3, cur.acc0, acc, L.one, T);
-#endif
             if (cur.q >= 0)
             {
                 sts_f64(vb + 8u*cur.q, acc);
@@ -725,9 +868,9 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
     {
         // Fetch lanes are independent state machines: each polls ITS current entry and delivers it the moment it
         // arrives.  (A plain "wait, then store" loop reconverges the warp before the store, so an early entry was
-        // held back until the latest of its 32 warp-mates had arrived: 1.7 us per tile hop instead of ~0.5.)
+        // held back until the latest of its 32 warp-mates had arrived: 1.7 us per tile hop instead of ~1.)
         int i = threadIdx.x - 32;
-        const unsigned long long* p = (i < nExt) ? out + A.extCol[xBase + i] : nullptr;
+        const unsigned long long* p = (i < nExt) ? out + extCol[xBase + i] : nullptr;
         const int ns = g_spinNs;
         while (i < nExt)
         {
@@ -736,7 +879,7 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
             {
                 sts_u64(vb + 8u*(T + i), v);
                 i += FETCHERS;
-                if (i < nExt) p = out + A.extCol[xBase + i];
+                if (i < nExt) p = out + extCol[xBase + i];
             }
             else if (ns > 0) __nanosleep(ns);
         }

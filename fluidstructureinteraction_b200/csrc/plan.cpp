@@ -1,6 +1,7 @@
 // plan.cpp -- see plan.h.  Pure host code, O(nCells + nFaces).
 #include "plan.h"
 #include "../../include/gpupcg.h"
+#define GPUPCG_ERR_TILE -100    /* internal: retry with smaller tiles */
 
 #include <algorithm>
 #include <climits>
@@ -360,6 +361,9 @@ int build_plan(int nCells, int nFaces, const int* l, const int* u,
     // ---- tile view of the columns + external (cross-tile) lists in consumption order
     P.LcolTile.assign(totL, -1);
     P.UcolTile.assign(totU, -1);
+    P.colL16.assign(totL, 0xFFFF);
+    P.idxL16.assign(totL, 0xFFFF);
+    P.colU16.assign(totU, 0xFFFF);
     P.extFPtr.assign(nTiles + 1, 0);
     P.extBPtr.assign(nTiles + 1, 0);
     for (int t = 0; t < nTiles; t++)
@@ -379,11 +383,19 @@ int build_plan(int nCells, int nFaces, const int* l, const int* u,
             {
                 const int e = si.offL + j*W + (r % W);
                 const int col = P.Lcol[e];
-                if (col >= r0 && col < r1) P.LcolTile[e] = col - r0;
+                if (col >= r0 && col < r1)
+                {
+                    P.LcolTile[e] = col - r0;
+                    P.colL16[e] = (unsigned short)(col - r0);
+                    P.idxL16[e] = (unsigned short)(P.Lidx[e] - P.slices[s0].offU);
+                }
                 else
                 {
-                    P.LcolTile[e] = -2 - ((int)P.extFCol.size() - baseF);
+                    const int k = (int)P.extFCol.size() - baseF;
+                    P.LcolTile[e] = -2 - k;
+                    P.colL16[e] = (unsigned short)(0x8000 | k);
                     P.extFCol.push_back(col);
+                    P.extFIdx.push_back(P.Lidx[e]);
                 }
             }
         }
@@ -402,10 +414,16 @@ int build_plan(int nCells, int nFaces, const int* l, const int* u,
                 {
                     const int e = si.offU + j*W + (r % W);
                     const int col = P.Ucol[e];
-                    if (col >= r0 && col < r1) P.UcolTile[e] = col - r0;
+                    if (col >= r0 && col < r1)
+                    {
+                        P.UcolTile[e] = col - r0;
+                        P.colU16[e] = (unsigned short)(col - r0);
+                    }
                     else
                     {
-                        P.UcolTile[e] = -2 - ((int)P.extBCol.size() - baseB);
+                        const int k = (int)P.extBCol.size() - baseB;
+                        P.UcolTile[e] = -2 - k;
+                        P.colU16[e] = (unsigned short)(0x8000 | k);
                         P.extBCol.push_back(col);
                     }
                 }
@@ -413,6 +431,12 @@ int build_plan(int nCells, int nFaces, const int* l, const int* u,
         }
         P.extBPtr[t + 1] = (int)P.extBCol.size();
         P.maxTileExtB = std::max(P.maxTileExtB, P.extBPtr[t + 1] - baseB);
+    }
+
+    if (P.tileRowsMax > 0x8000 || P.maxTileEntriesU > 0x8000 || P.maxTileExtF > 0x7FFE || P.maxTileExtB > 0x7FFE)
+    {
+        err = "gpupcg_create: tile too large for the 16-bit tile codes";
+        return GPUPCG_ERR_TILE;
     }
 
     // ---- coupled interfaces

@@ -71,6 +71,10 @@ struct HostPlan
     std::vector<int> LcolTile;          // [entriesL]  (forward / factor)
     std::vector<int> UcolTile;          // [entriesU]  (backward)
     std::vector<int> extFPtr, extFCol;  // forward: [nTiles+1], global rows in consumption order
+    std::vector<int> extFIdx;           // [extForward] U-array index of the coefficient of that cross-tile entry
+    // compact 16-bit tile codes (what the kernels stream): 0xFFFF pad, 0x8000|k = k-th cross-tile entry of the
+    // tile's list, else tile-local row (col*) / tile-local index into the tile's U block (idxL16)
+    std::vector<unsigned short> colL16, idxL16, colU16;
     std::vector<int> extBPtr, extBCol;  // backward
 
     // coupled interfaces, grouped by row: for every row that owns interface faces, its entries in
