@@ -81,6 +81,7 @@ SYMBOLS = {
     "gpupcg_host_unregister": (C.c_int, [C.c_void_p]),
     "gpupcg_plan_export": (C.c_int, [C.c_int, C.c_int, c_int_p, c_int_p, C.c_int, C.c_int, C.POINTER(PlanInfo),
                                      C.POINTER(c_int_p)]),
+    "gpupcg_device_count": (C.c_int, []),
     "gpupcg_device_report": (C.c_int, [C.c_int, C.c_char_p, C.c_int]),
 }
 

@@ -116,6 +116,13 @@ extern "C" const char* gpupcg_last_error(gpupcg_handle h)
     return h ? h->err.c_str() : g_createError.c_str();
 }
 
+extern "C" int gpupcg_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
 extern "C" int gpupcg_device_report(int device, char* buf, int bufLen)
 {
     int n = 0;
@@ -190,7 +197,7 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     h->nPatches = nPatches;
 
     // tile size: as large as the shared-memory carve-up of one CTA allows (several CTAs per SM wanted)
-    int tileRows = env_int("GPUPCG_TILE_ROWS", 512);
+    int tileRows = env_int("GPUPCG_TILE_ROWS", 256);
     const size_t smemCap = (size_t)std::min<long long>(prop.sharedMemPerBlockOptin, 200*1024);
     int rc;
     while (true)

@@ -182,6 +182,9 @@ int gpupcg_plan_export(int nCells, int nFaces, const int* lowerAddr, const int* 
                        int tileMode /* 0 natural-order intervals, 1 greedy compact blobs (create() default) */,
                        gpupcg_plan_info* info, int** arrays);
 
+/* Number of visible CUDA devices (0 if none / no driver). */
+int gpupcg_device_count(void);
+
 /* Library / device report: fills a short text (device name, SM count, cc) into buf. */
 int gpupcg_device_report(int device, char* buf, int bufLen);
 
