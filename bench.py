@@ -200,19 +200,20 @@ def run_ours(args, nx, ny, nz):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg.load_library()
 
-    s = build_system(nx, ny, nz)
-    nGlobal = s["nCells"]
+    nGlobal = nx*ny*nz
+    nFglobal = (nx - 1)*ny*nz + nx*(ny - 1)*nz + nx*ny*(nz - 1)
     if world > 1:
+        # one decomposePar `simple` sub-domain per rank, written down directly (no rank builds the global system)
         px, py, pz = decompose.proc_grid(world)
-        cellProc = decompose.simple_cell_proc(nx, ny, nz, px, py, pz)
-        dom = decompose.decompose_ldu(s["l"], s["u"], s["diag"], s["upper"], s["b"], np.zeros(nGlobal), cellProc, world)[rank]
-        g = pkg.GpuPCG(dom["l"], dom["u"], dom["cells"].shape[0], dom["patchFaceCells"], dom["patchNbrDomain"], device=local)
+        s = cases.cantilever_subdomain(nx, ny, nz, px, py, pz, rank, tz=1.0)
+        g = pkg.GpuPCG(s["l"], s["u"], s["nCells"], s["patchFaceCells"], s["patchNbrDomain"], device=local)
         uid = [pkg.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         g.comm_init(rank, world, uid[0])
-        diag, upper, bunit, bou = dom["diag"], dom["upper"], dom["b"], dom["patchBouCoeffs"]
-        n = dom["cells"].shape[0]
+        diag, upper, bunit, bou = s["diag"], s["upper"], s["b"], s["patchBouCoeffs"]
+        n = s["nCells"]
     else:
+        s = build_system(nx, ny, nz)
         g = pkg.GpuPCG(s["l"], s["u"], nGlobal, device=local)
         diag, upper, bunit, bou = s["diag"], s["upper"], s["b"], []
         n = nGlobal
@@ -326,12 +327,13 @@ def run_ours(args, nx, ny, nz):
             "metric": METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev/args.steps, "higher_is_better": True,
             "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(nx, ny, nz, world), "cells": nGlobal, "internal_faces": int(s["l"].shape[0]),
+            "config": {"workload": workload_name(nx, ny, nz, world), "cells": nGlobal, "internal_faces": int(nFglobal),
                        "tolerance": TOL, "relTol": RELTOL, "solver": "gpuPCG", "preconditioner": "DIC",
                        "parallelism": "1 sub-domain/GPU x %d" % world,
                        "l2": "working set (%.0f MB) vs 126 MB L2: inputs larger than L2 at >= 1M cells; kernel timings flush L2" %
                              (cases.pcg_iteration_bytes(n, nF)/1e6)},
             "solves_per_s": 3*args.steps/(ms_dev*1e-3), "iterations_per_step": iters/args.steps,
+            "cells_per_gpu": n,
             "e2e": {"value": nGlobal*iters_e2e/(ms_e2e*1e-3), "unit": "cell-updates/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e/args.steps,
                     "solves_per_s": 3*args.steps/(ms_e2e*1e-3)},

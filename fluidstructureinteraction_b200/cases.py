@@ -66,3 +66,54 @@ def dic_bytes(nCells, nFaces):
 def pcg_iteration_bytes(nCells, nFaces):
     """One PCG iteration, reference data movement (unfused): Amul + DIC + 2 dots + pA update + x/r update."""
     return amul_bytes(nCells, nFaces) + dic_bytes(nCells, nFaces) + 16*nCells + 24*nCells + 16*nCells + 48*nCells
+
+
+def cantilever_subdomain(nx, ny, nz, px, py, pz, rank, L=2.0, W=0.5, H=1.0, E=STEEL["E"], nu=STEEL["nu"], tz=-1.0e4):
+    """The sub-domain `rank` of cantilever_system() decomposed `simple (px py pz)`, written down directly (a rank
+    never builds the global 64 M-cell system).  Same layout as decompose.decompose_ldu: local cells in ascending
+    global id, one processor patch per neighbouring rank (ascending), faces in global face order, bouCoeffs = -upper."""
+    mu, lam = lame(E, nu)
+    gamma = 2.0*mu + lam
+    hx, hy, hz = L/nx, W/ny, H/nz
+    coef = (gamma*(hy*hz)/hx, gamma*(hx*hz)/hy, gamma*(hx*hy)/hz)
+    bi, bj, bk = rank % px, (rank // px) % py, rank // (px*py)
+
+    def block_range(n, p, b):
+        idx = np.arange(n)
+        blk = np.minimum(idx*p // n, p - 1)
+        sel = np.flatnonzero(blk == b)
+        return int(sel[0]), int(sel[-1]) + 1
+
+    i0, i1 = block_range(nx, px, bi)
+    j0, j1 = block_range(ny, py, bj)
+    k0, k1 = block_range(nz, pz, bk)
+    lx, ly, lz = i1 - i0, j1 - j0, k1 - k0
+    n = lx*ly*lz
+    l, u = hex_ldu(lx, ly, lz)
+    d = u.astype(np.int64) - l
+    mx = d == 1
+    my = (d == lx) & ~mx & (ly > 1)
+    upper = -np.where(mx, coef[0], np.where(my, coef[1], coef[2]))
+    c = np.arange(n, dtype=np.int64)
+    li, lj, lk = c % lx, (c // lx) % ly, c // (lx*ly)
+    gi, gj, gk = li + i0, lj + j0, lk + k0
+    diag = (coef[0]*((gi > 0).astype(np.float64) + (gi < nx - 1)) + coef[1]*((gj > 0).astype(np.float64) + (gj < ny - 1))
+            + coef[2]*((gk > 0).astype(np.float64) + (gk < nz - 1)))
+    diag[gi == 0] += gamma*(hy*hz)/(0.5*hx)
+    b = np.zeros(n)
+    b[gi == nx - 1] += gamma*(hy*hz)*(tz/gamma)
+    # processor patches, neighbours in ascending rank order: -z, -y, -x, +x, +y, +z
+    cand = []
+    if bk > 0: cand.append((rank - px*py, lk == 0, coef[2]))
+    if bj > 0: cand.append((rank - px, lj == 0, coef[1]))
+    if bi > 0: cand.append((rank - 1, li == 0, coef[0]))
+    if bi < px - 1: cand.append((rank + 1, li == lx - 1, coef[0]))
+    if bj < py - 1: cand.append((rank + px, lj == ly - 1, coef[1]))
+    if bk < pz - 1: cand.append((rank + px*py, lk == lz - 1, coef[2]))
+    cand.sort(key=lambda t: t[0])
+    pfc = [np.flatnonzero(m).astype(np.int32) for _, m, _ in cand]
+    pbc = [np.full(fc.shape[0], cf) for fc, (_, _, cf) in zip(pfc, cand)]
+    nbr = [r for r, _, _ in cand]
+    gid = (gi + nx*(gj + ny*gk))
+    return dict(l=l, u=u, diag=diag, upper=upper, b=b, nCells=n, cells=gid, patchFaceCells=pfc, patchBouCoeffs=pbc,
+                patchNbrDomain=nbr, gamma=gamma)

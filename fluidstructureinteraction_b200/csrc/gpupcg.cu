@@ -571,6 +571,11 @@ static int solve_core(gpupcg_handle h, double tol, double relTol, int minIter, i
                       gpupcg_perf* perf, double* history, int historyCap)
 {
     const HostPlan& P = h->plan;
+    if (P.nIfaceFaces > 0 && !h->comm.active())
+    {
+        h->err = "gpupcg_solve: this sub-domain has coupled interfaces but gpupcg_comm_init has not been called";
+        return GPUPCG_ERR_STATE;
+    }
     cudaStream_t s = h->stream;
     const int gN = grid_for(P.nRows, h->streamGrid);
     int rc;
@@ -613,7 +618,7 @@ static int solve_core(gpupcg_handle h, double tol, double relTol, int minIter, i
             rc = allreduce_step(h, S_SWEEP, 1); if (rc) return rc;
             LAUNCH(k_p_update, gN, s, h->dWA, h->dPA, P.nRows, h->dState);
             rc = enqueue_amul(h, 1, h->dPA, h->dWA, false); if (rc) return rc;
-            rc = allreduce_step(h, S_AMUL, 1); if (rc) return rc;
+            rc = allreduce_step(h, S_AMUL, 2); if (rc) return rc;
             LAUNCH(k_xr_update, gN, s, h->dPA, (unsigned long long*)h->dWA, h->dX, h->dRA, P.nRows,
                                            h->dPartials, h->dState, h->dHistory);
             rc = allreduce_step(h, S_XR, 1); if (rc) return rc;

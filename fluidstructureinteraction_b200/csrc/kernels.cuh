@@ -115,7 +115,7 @@ __device__ __forceinline__ void dev_scalar_step(DevState* st, int step, const do
 // ------------------------------------------------------------------------------------------
 template <int NV, int NT>
 __device__ __forceinline__ void grid_reduce_finish(double (&v)[NV], double* partials, int stride, int slot, int nSlots,
-                                                   DevState* st, int step, double* history)
+                                                   DevState* st, int step, double* history, int redSlot = 0)
 {
     constexpr int NW = NT/32;
     __shared__ double sm[NV][NW];
@@ -172,8 +172,11 @@ __device__ __forceinline__ void grid_reduce_finish(double (&v)[NV], double* part
         st->ticket = 0;
         if (st->multiRank)
         {
+            // park the local sums for the all-reduce; the Amul dot arrives in two parts (rows without / with
+            // coupled faces): slot 0 from k_amul_tile (which also clears slot 1), slot 1 from k_iface_update
 #pragma unroll
-            for (int k = 0; k < NV; k++) st->red[k] = f[k];
+            for (int k = 0; k < NV; k++) st->red[redSlot + k] = f[k];
+            if (step == S_AMUL && redSlot == 0) st->red[1] = 0.0;
         }
         else
         {
@@ -189,6 +192,7 @@ __global__ void k_scalar_step(DevState* st, int step, double* history)
     {
         if (st->done && step >= S_SWEEP) return;
         double v[4] = {st->red[0], st->red[1], st->red[2], st->red[3]};
+        if (step == S_AMUL) v[0] = v[0] + v[1];
         dev_scalar_step(st, step, v, history);
     }
 }
@@ -265,7 +269,8 @@ __global__ void __launch_bounds__(TPB) k_iface_update(const int* __restrict__ if
         Ax[r] = acc;
         if (DOT) dot[0] += acc*x[r];
     }
-    if (DOT) grid_reduce_finish<1, TPB>(dot, partials + 2*MAXPART, MAXPART, blockIdx.x, gridDim.x, st, S_AMUL, nullptr);
+    // multi-rank only (a sub-domain with coupled faces): second part of wApA, summed with the first after the all-reduce
+    if (DOT) grid_reduce_finish<1, TPB>(dot, partials, MAXPART, blockIdx.x, gridDim.x, st, S_AMUL, nullptr, 1);
 }
 
 // ------------------------------------------------------------------------------------------

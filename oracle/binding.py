@@ -59,6 +59,7 @@ def load(build=True):
     lib.orc_bench_amul.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, dp, dp, dp, dp]
     lib.orc_bench_dic.restype = C.c_double
     lib.orc_bench_dic.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, dp, dp, dp, dp]
+    lib.orc_set_sum_mode.argtypes = [C.c_int]
     lib.orc_num_threads.restype = C.c_int
     lib.orc_set_num_threads.argtypes = [C.c_int]
     _lib = lib
@@ -174,3 +175,9 @@ def num_threads():
 
 def set_num_threads(n):
     load().orc_set_num_threads(int(n))
+
+
+def set_sum_mode(mode):
+    """0: the reference's sequential sums (default).  1: pairwise summation of the same terms -- test-only, to measure
+    the sensitivity of a residual history to re-association of the reductions."""
+    load().orc_set_sum_mode(int(mode))

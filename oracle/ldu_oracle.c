@@ -248,8 +248,29 @@ void orc_dic_precondition
 /* Field reductions  [EXT] src/foam/fields/Fields/Field/FieldFunctions.C      */
 /* local sequential sum, then reduce(sumOp) = rank-ordered linear sum         */
 /* ------------------------------------------------------------------------- */
+/* Summation order.  0 (default) = the reference's sequential loops.  1 = pairwise (tree) summation of the same
+ * terms: NOT the reference order -- used by the tests only to measure how far the residual history of a given case
+ * moves when nothing but the association of the reductions changes (the GPU necessarily re-associates them).    */
+static int orc_sum_mode = 0;
+void orc_set_sum_mode(int m) { orc_sum_mode = m; }
+
+static double orc_pairwise(int n, const double* a, const double* b, int kind)
+{
+    if (n <= 64)
+    {
+        double s = 0.0;
+        if (kind == 0) for (int i = 0; i < n; i++) s += a[i]*b[i];
+        else if (kind == 1) for (int i = 0; i < n; i++) s += fabs(a[i]);
+        else for (int i = 0; i < n; i++) s += a[i];
+        return s;
+    }
+    const int h = n/2;
+    return orc_pairwise(h, a, b, kind) + orc_pairwise(n - h, a + h, b ? b + h : b, kind);
+}
+
 static double orc_sumProd(int n, const double* a, const double* b)
 {
+    if (orc_sum_mode) return orc_pairwise(n, a, b, 0);
     double s = 0.0;
     for (int i = 0; i < n; i++) s += a[i]*b[i];
     return s;
@@ -257,6 +278,7 @@ static double orc_sumProd(int n, const double* a, const double* b)
 
 static double orc_sumMag(int n, const double* a)
 {
+    if (orc_sum_mode) return orc_pairwise(n, a, 0, 1);
     double s = 0.0;
     for (int i = 0; i < n; i++) s += fabs(a[i]);
     return s;
@@ -264,6 +286,7 @@ static double orc_sumMag(int n, const double* a)
 
 static double orc_sum(int n, const double* a)
 {
+    if (orc_sum_mode) return orc_pairwise(n, a, 0, 2);
     double s = 0.0;
     for (int i = 0; i < n; i++) s += a[i];
     return s;

