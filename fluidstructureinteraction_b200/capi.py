@@ -77,6 +77,12 @@ SYMBOLS = {
     "gpupcg_time_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]),
     "gpupcg_comm_unique_id": (C.c_int, [C.c_void_p]),
     "gpupcg_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "gpupcg_mesh_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, C.c_int,
+                                     c_int_p, c_int_p, c_int_p] + [c_double_p]*7),
+    "gpupcg_mesh_destroy": (C.c_int, [C.c_void_p]),
+    "gpupcg_mesh_last_error": (C.c_char_p, [C.c_void_p]),
+    "gpupcg_assemble_D": (C.c_int, [C.c_void_p] + [c_double_p]*10 + [C.c_double, C.c_int] + [c_double_p]*6),
+    "gpupcg_sigma": (C.c_int, [C.c_void_p] + [c_double_p]*5),
     "gpupcg_host_register": (C.c_int, [C.c_void_p, C.c_ulonglong]),
     "gpupcg_host_unregister": (C.c_int, [C.c_void_p]),
     "gpupcg_plan_export": (C.c_int, [C.c_int, C.c_int, c_int_p, c_int_p, C.c_int, C.c_int, C.POINTER(PlanInfo),
@@ -246,6 +252,60 @@ class GpuPCG(object):
     def comm_init(self, rank, nRanks, unique_id_bytes):
         buf = C.create_string_buffer(bytes(unique_id_bytes), 128)
         self._check(self.lib.gpupcg_comm_init(self.h, rank, nRanks, buf))
+
+
+PATCH_TYPES = {"tractionDisplacement": 0, "fixedDisplacement": 1}
+
+
+class GpuMesh(object):
+    """Device copy of what foam-extend's fvMesh provides (addressing + geometry) for the assembly kernels."""
+
+    def __init__(self, mesh, geom, patchTypes, device=0):
+        self.lib = load_library()
+        self.mesh, self.geom = mesh, geom
+        self.nC, self.nF, self.nIF = mesh.nCells, mesh.nFaces, mesh.nInternalFaces
+        self.nBF = self.nF - self.nIF
+        ps = _i32([p["start"] for p in mesh.patches]); pz = _i32([p["size"] for p in mesh.patches])
+        pt = _i32([PATCH_TYPES[patchTypes[p["name"]]] for p in mesh.patches])
+        self._keep = [_f64(geom.Sf), _f64(geom.magSf), _f64(geom.Cf), _f64(geom.C), _f64(geom.V), _f64(geom.weights),
+                      _f64(geom.deltaCoeffs)]
+        self.h = C.c_void_p()
+        rc = self.lib.gpupcg_mesh_create(C.byref(self.h), device, self.nC, self.nF, self.nIF, _ip(_i32(mesh.owner)),
+                                         _ip(_i32(mesh.neighbour)), len(mesh.patches), _ip(ps), _ip(pz), _ip(pt),
+                                         *[_dp(a) for a in self._keep])
+        if rc != 0:
+            msg = self.lib.gpupcg_mesh_last_error(None)
+            self.h = None
+            raise GpuPcgError(rc, msg.decode() if msg else "?")
+
+    def _check(self, rc):
+        if rc != 0:
+            raise GpuPcgError(rc, self.lib.gpupcg_mesh_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gpupcg_mesh_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def assemble_D(self, mu, lam, rho, g, D, gradD, gradDf, traction, pressure, fixedValue, limitCoeff=1.0, reps=1):
+        a = [_f64(v) for v in (mu, lam, rho, g, D, gradD, gradDf, traction, pressure, fixedValue)]
+        upper = np.empty(self.nIF); diag = np.empty(self.nC); source = np.empty((self.nC, 3))
+        ic = np.empty((self.nBF, 3)); bc = np.empty((self.nBF, 3))
+        ms = C.c_double(0.0)
+        self._check(self.lib.gpupcg_assemble_D(self.h, *[_dp(v) for v in a], float(limitCoeff), int(reps), _dp(upper),
+                                               _dp(diag), _dp(source), _dp(ic), _dp(bc), C.byref(ms)))
+        return dict(upper=upper, diag=diag, source=source, internalCoeffs=ic, boundaryCoeffs=bc, kernel_ms=ms.value)
+
+    def sigma(self, mu, lam, gradD):
+        eps = np.empty((self.nC, 6)); sig = np.empty((self.nC, 6))
+        self._check(self.lib.gpupcg_sigma(self.h, _dp(_f64(mu)), _dp(_f64(lam)), _dp(_f64(gradD)), _dp(eps), _dp(sig)))
+        return eps, sig
 
 
 def plan_export(lowerAddr, upperAddr, nCells, tileRows=1024, tileMode=1):

@@ -1,0 +1,438 @@
+// assembly.cu -- GPU assembly of the D equation (K1-K5, K14): the face and cell loops that
+//   fvm::laplacian(2*muf+lambdaf, D) (gaussLaplacianScheme [EXT] + skewCorrectedSnGrad<vector>::correction,
+//   skewCorrectedVectorSnGrad.C:50-294), fvc::div(Sf & (...gradDf...)) (unsTotalLagrangianStress.C:850-857,
+//   fvc::surfaceIntegrate [EXT]) and the displacement boundary conditions (tractionDisplacementFvPatchVectorField.C:
+//   148-257, fixedDisplacementFvPatchVectorField.C:129-157) run on the CPU, as three streaming kernels:
+//     k_asm_faces   one thread per face : muf/lambdaf interpolation, gammaMagSf, upper, skew-correction flux, stress flux
+//     k_asm_cells   one thread per cell : negSumDiag + surfaceIntegrate of both fluxes in the reference face order
+//                                         (internal faces ascending, then boundary faces) -> diag, source
+//     k_asm_patches one thread per boundary face : internalCoeffs / boundaryCoeffs
+//   and k_sigma (epsilon = symm(gradD), sigma = 2 mu eps + lambda tr(eps) I, unsTotalLagrangianStress.C:975-990).
+// Every product / sum is a __d*_rn intrinsic in the operand order of the field expressions, so results are
+// bit-identical to the CPU evaluation (no FMA).  HBM-bound streaming kernels; no tensor cores.
+#include "../../include/gpupcg.h"
+
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace
+{
+
+constexpr int ATPB = 256;
+constexpr double A_SMALL = 1.0e-15;
+
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dvd(double a, double b) { return __ddiv_rn(a, b); }
+
+__device__ __forceinline__ double dot3(const double* a, const double* b)
+{
+    return add(add(mul(a[0], b[0]), mul(a[1], b[1])), mul(a[2], b[2]));
+}
+__device__ __forceinline__ double mag3(const double* a)
+{
+    return __dsqrt_rn(add(add(mul(a[0], a[0]), mul(a[1], a[1])), mul(a[2], a[2])));
+}
+// vector & tensor: r_j = v.x*T.xj + v.y*T.yj + v.z*T.zj
+__device__ __forceinline__ void vdotT(const double* v, const double* T, double* r)
+{
+    r[0] = add(add(mul(v[0], T[0]), mul(v[1], T[3])), mul(v[2], T[6]));
+    r[1] = add(add(mul(v[0], T[1]), mul(v[1], T[4])), mul(v[2], T[7]));
+    r[2] = add(add(mul(v[0], T[2]), mul(v[1], T[5])), mul(v[2], T[8]));
+}
+
+struct MeshDev
+{
+    int nCells, nFaces, nIF, nPatches;
+    const int *owner, *neighbour, *bfPatchType;      // bfPatchType[nFaces - nIF]
+    const int *cellFaceStart, *cellFace;              // CSR; face id, bit 31 set = the cell is the face's neighbour
+    const double *Sf, *magSf, *Cf, *C, *V, *weights, *deltaCoeffs;
+};
+
+__global__ void __launch_bounds__(ATPB) k_asm_faces(MeshDev M, const double* __restrict__ mu, const double* __restrict__ lambda,
+                                                    const double* __restrict__ D, const double* __restrict__ gradD,
+                                                    const double* __restrict__ gradDf, double limitCoeff,
+                                                    double* __restrict__ upper, double* __restrict__ Lup, double* __restrict__ gms,
+                                                    double* __restrict__ fluxE, double* __restrict__ fluxC)
+{
+    for (int f = blockIdx.x*ATPB + threadIdx.x; f < M.nFaces; f += gridDim.x*ATPB)
+    {
+        const int P = M.owner[f];
+        const bool internal = f < M.nIF;
+        const int N = internal ? M.neighbour[f] : P;
+        double muf, laf;
+        if (internal)
+        {
+            const double w = M.weights[f];
+            muf = add(mul(w, sub(mu[P], mu[N])), mu[N]);
+            laf = add(mul(w, sub(lambda[P], lambda[N])), lambda[N]);
+        }
+        else { muf = mu[P]; laf = lambda[P]; }
+        const double g = mul(add(mul(2.0, muf), laf), M.magSf[f]);
+        gms[f] = g;
+        double Sf[3] = {M.Sf[3*f], M.Sf[3*f + 1], M.Sf[3*f + 2]};
+        // explicit stress flux: Sf & ( -(muf+lambdaf)*G + muf*G.T() + lambdaf*(I*tr(G)) )
+        {
+            double G[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) G[k] = gradDf[9*(size_t)f + k];
+            const double a = -add(muf, laf);
+            const double tr = add(add(G[0], G[4]), G[8]);
+            const double sph = mul(laf, tr);
+            double T[9];
+            T[0] = add(add(mul(a, G[0]), mul(muf, G[0])), sph); T[1] = add(mul(a, G[1]), mul(muf, G[3])); T[2] = add(mul(a, G[2]), mul(muf, G[6]));
+            T[3] = add(mul(a, G[3]), mul(muf, G[1])); T[4] = add(add(mul(a, G[4]), mul(muf, G[4])), sph); T[5] = add(mul(a, G[5]), mul(muf, G[7]));
+            T[6] = add(mul(a, G[6]), mul(muf, G[2])); T[7] = add(mul(a, G[7]), mul(muf, G[5])); T[8] = add(add(mul(a, G[8]), mul(muf, G[8])), sph);
+            double fl[3];
+            vdotT(Sf, T, fl);
+            fluxE[3*(size_t)f] = fl[0]; fluxE[3*(size_t)f + 1] = fl[1]; fluxE[3*(size_t)f + 2] = fl[2];
+        }
+        if (internal)
+        {
+            const double dc = M.deltaCoeffs[f];
+            const double up = mul(dc, g);
+            Lup[f] = up;
+            upper[f] = sub(0.0, up);
+            // skewCorrectedSnGrad<vector>::correction
+            const double Cf[3] = {M.Cf[3*f], M.Cf[3*f + 1], M.Cf[3*f + 2]};
+            const double magSqrSf = add(add(mul(Sf[0], Sf[0]), mul(Sf[1], Sf[1])), mul(Sf[2], Sf[2]));
+            double kP[3], kN[3], a3[3], b3[3], ssf[3], t[3], GP[9], GN[9];
+#pragma unroll
+            for (int d = 0; d < 3; d++) kP[d] = sub(Cf[d], M.C[3*(size_t)P + d]);
+            {
+                const double s = dot3(Sf, kP);
+#pragma unroll
+                for (int d = 0; d < 3; d++) kP[d] = sub(kP[d], dvd(mul(Sf[d], s), magSqrSf));
+            }
+#pragma unroll
+            for (int d = 0; d < 3; d++) kN[d] = sub(Cf[d], M.C[3*(size_t)N + d]);
+            {
+                const double s = dot3(Sf, kN);
+#pragma unroll
+                for (int d = 0; d < 3; d++) kN[d] = sub(kN[d], dvd(mul(Sf[d], s), magSqrSf));
+            }
+#pragma unroll
+            for (int k = 0; k < 9; k++) { GP[k] = gradD[9*(size_t)P + k]; GN[k] = gradD[9*(size_t)N + k]; }
+            vdotT(kN, GN, a3);
+            vdotT(kP, GP, b3);
+#pragma unroll
+            for (int d = 0; d < 3; d++) ssf[d] = mul(sub(a3[d], b3[d]), dc);
+#pragma unroll
+            for (int d = 0; d < 3; d++) t[d] = add(mul(dc, sub(D[3*(size_t)N + d], D[3*(size_t)P + d])), ssf[d]);
+            double lim = dvd(mul(limitCoeff, mag3(t)), add(mul(sub(1.0, limitCoeff), mag3(ssf)), A_SMALL));
+            if (lim > 1.0) lim = 1.0;
+#pragma unroll
+            for (int d = 0; d < 3; d++) fluxC[3*(size_t)f + d] = mul(g, mul(ssf[d], lim));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ATPB) k_asm_cells(MeshDev M, const double* __restrict__ rho, double g0, double g1, double g2,
+                                                    const double* __restrict__ Lup, const double* __restrict__ fluxE,
+                                                    const double* __restrict__ fluxC, double* __restrict__ diag,
+                                                    double* __restrict__ source)
+{
+    for (int c = blockIdx.x*ATPB + threadIdx.x; c < M.nCells; c += gridDim.x*ATPB)
+    {
+        double Ld = 0.0, sE[3] = {0.0, 0.0, 0.0}, sC[3] = {0.0, 0.0, 0.0};
+        for (int k = M.cellFaceStart[c]; k < M.cellFaceStart[c + 1]; k++)
+        {
+            const int code = M.cellFace[k];
+            const int f = code & 0x7fffffff;
+            const bool nbr = code < 0;
+            if (f < M.nIF)
+            {
+                Ld = sub(Ld, Lup[f]);
+#pragma unroll
+                for (int d = 0; d < 3; d++)
+                {
+                    const double fc = fluxC[3*(size_t)f + d], fe = fluxE[3*(size_t)f + d];
+                    sC[d] = nbr ? sub(sC[d], fc) : add(sC[d], fc);
+                    sE[d] = nbr ? sub(sE[d], fe) : add(sE[d], fe);
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int d = 0; d < 3; d++) sE[d] = add(sE[d], fluxE[3*(size_t)f + d]);
+            }
+        }
+        diag[c] = sub(0.0, Ld);
+        const double V = M.V[c];
+        const double gv[3] = {g0, g1, g2};
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+        {
+            const double dcv = dvd(sC[d], V), de = dvd(sE[d], V);
+            const double rg = mul(rho[c], gv[d]);
+            const double R = sub(sub(sub(0.0, mul(V, dcv)), mul(V, de)), mul(V, rg));
+            source[3*(size_t)c + d] = sub(0.0, R);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ATPB) k_asm_patches(MeshDev M, const double* __restrict__ mu, const double* __restrict__ lambda,
+                                                      const double* __restrict__ gradD, const double* __restrict__ gradDf,
+                                                      const double* __restrict__ gms, const double* __restrict__ traction,
+                                                      const double* __restrict__ pressure, const double* __restrict__ fixedValue,
+                                                      double* __restrict__ internalCoeffs, double* __restrict__ boundaryCoeffs)
+{
+    const int nBF = M.nFaces - M.nIF;
+    for (int bf = blockIdx.x*ATPB + threadIdx.x; bf < nBF; bf += gridDim.x*ATPB)
+    {
+        const int f = M.nIF + bf, c = M.owner[f];
+        const double Sf[3] = {M.Sf[3*f], M.Sf[3*f + 1], M.Sf[3*f + 2]};
+        const double magSf = M.magSf[f], dcf = M.deltaCoeffs[f];
+        double n[3], gIC[3], gBC[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) n[d] = dvd(Sf[d], magSf);
+        if (M.bfPatchType[bf] == 1)
+        {
+            double delta[3], k[3], kg[3], G[9];
+#pragma unroll
+            for (int d = 0; d < 3; d++) delta[d] = sub(M.Cf[3*(size_t)f + d], M.C[3*(size_t)c + d]);
+            const double nd = dot3(n, delta);
+#pragma unroll
+            for (int d = 0; d < 3; d++) k[d] = sub(delta[d], mul(n[d], nd));
+#pragma unroll
+            for (int q = 0; q < 9; q++) G[q] = gradD[9*(size_t)c + q];
+            vdotT(k, G, kg);
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+            {
+                gIC[d] = -dcf;
+                gBC[d] = mul(dcf, sub(fixedValue[3*(size_t)bf + d], kg[d]));
+            }
+        }
+        else
+        {
+            const double m = mu[c], la = lambda[c];
+            double G[9], T[9], nT[3];
+#pragma unroll
+            for (int q = 0; q < 9; q++) G[q] = gradDf[9*(size_t)f + q];
+            const double ml = add(m, la);
+            T[0] = sub(mul(m, G[0]), mul(ml, G[0])); T[1] = sub(mul(m, G[3]), mul(ml, G[1])); T[2] = sub(mul(m, G[6]), mul(ml, G[2]));
+            T[3] = sub(mul(m, G[1]), mul(ml, G[3])); T[4] = sub(mul(m, G[4]), mul(ml, G[4])); T[5] = sub(mul(m, G[7]), mul(ml, G[5]));
+            T[6] = sub(mul(m, G[2]), mul(ml, G[6])); T[7] = sub(mul(m, G[5]), mul(ml, G[7])); T[8] = sub(mul(m, G[8]), mul(ml, G[8]));
+            vdotT(n, T, nT);
+            const double tr = add(add(G[0], G[4]), G[8]);
+            const double den = add(mul(2.0, m), la);
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+            {
+                const double t = sub(traction[3*(size_t)bf + d], mul(pressure[bf], n[d]));
+                gIC[d] = 0.0;
+                gBC[d] = dvd(sub(sub(t, nT[d]), mul(mul(n[d], la), tr)), den);
+            }
+        }
+        const double g = gms[f];
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+        {
+            internalCoeffs[3*(size_t)bf + d] = sub(0.0, mul(g, gIC[d]));
+            boundaryCoeffs[3*(size_t)bf + d] = sub(0.0, mul(-g, gBC[d]));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ATPB) k_sigma(int nCells, const double* __restrict__ mu, const double* __restrict__ lambda,
+                                                const double* __restrict__ gradD, double* __restrict__ epsilon, double* __restrict__ sigma)
+{
+    for (int c = blockIdx.x*ATPB + threadIdx.x; c < nCells; c += gridDim.x*ATPB)
+    {
+        double G[9], e[6];
+#pragma unroll
+        for (int q = 0; q < 9; q++) G[q] = gradD[9*(size_t)c + q];
+        e[0] = G[0]; e[1] = mul(0.5, add(G[1], G[3])); e[2] = mul(0.5, add(G[2], G[6]));
+        e[3] = G[4]; e[4] = mul(0.5, add(G[5], G[7])); e[5] = G[8];
+        const double tr = add(add(e[0], e[3]), e[5]);
+        const double sph = mul(lambda[c], tr);
+        const double tm = mul(2.0, mu[c]);
+#pragma unroll
+        for (int q = 0; q < 6; q++) epsilon[6*(size_t)c + q] = e[q];
+        sigma[6*(size_t)c + 0] = add(mul(tm, e[0]), sph); sigma[6*(size_t)c + 1] = mul(tm, e[1]); sigma[6*(size_t)c + 2] = mul(tm, e[2]);
+        sigma[6*(size_t)c + 3] = add(mul(tm, e[3]), sph); sigma[6*(size_t)c + 4] = mul(tm, e[4]); sigma[6*(size_t)c + 5] = add(mul(tm, e[5]), sph);
+    }
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------------------------
+struct gpupcg_mesh_s
+{
+    int device = 0, numSMs = 0;
+    MeshDev M{};
+    std::vector<void*> owned;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    // work arrays
+    double *dMu = nullptr, *dLambda = nullptr, *dRho = nullptr, *dD = nullptr, *dGradD = nullptr, *dGradDf = nullptr;
+    double *dTraction = nullptr, *dPressure = nullptr, *dFixed = nullptr;
+    double *dUpper = nullptr, *dLup = nullptr, *dGms = nullptr, *dFluxE = nullptr, *dFluxC = nullptr;
+    double *dDiag = nullptr, *dSource = nullptr, *dIC = nullptr, *dBC = nullptr, *dEps = nullptr, *dSig = nullptr;
+};
+
+static thread_local std::string g_meshErr;
+
+#define MCK(call)                                                                                   \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { char b_[400];                            \
+         snprintf(b_, sizeof(b_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+         m->err = b_; g_meshErr = b_; return GPUPCG_ERR_CUDA; } } while (0)
+
+template <class T>
+static cudaError_t up(gpupcg_mesh m, const T*& d, const T* h, size_t n)
+{
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1)*sizeof(T));
+    if (e != cudaSuccess) return e;
+    m->owned.push_back(p);
+    d = (const T*)p;
+    if (n) e = cudaMemcpyAsync(p, h, n*sizeof(T), cudaMemcpyHostToDevice, m->stream);
+    return e;
+}
+
+template <class T>
+static cudaError_t alloc(gpupcg_mesh m, T*& d, size_t n)
+{
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1)*sizeof(T));
+    if (e == cudaSuccess) { m->owned.push_back(p); d = (T*)p; }
+    return e;
+}
+
+extern "C" const char* gpupcg_mesh_last_error(gpupcg_mesh m) { return m ? m->err.c_str() : g_meshErr.c_str(); }
+
+extern "C" int gpupcg_mesh_destroy(gpupcg_mesh m)
+{
+    if (!m) return GPUPCG_ERR_ARG;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    for (void* p : m->owned) cudaFree(p);
+    if (m->ev0) cudaEventDestroy(m->ev0);
+    if (m->ev1) cudaEventDestroy(m->ev1);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+    return GPUPCG_OK;
+}
+
+extern "C" int gpupcg_mesh_create(gpupcg_mesh* out, int device, int nCells, int nFaces, int nInternalFaces,
+                                  const int* owner, const int* neighbour, int nPatches, const int* patchStart,
+                                  const int* patchSize, const int* patchType, const double* Sf, const double* magSf,
+                                  const double* Cf, const double* C, const double* V, const double* weights,
+                                  const double* deltaCoeffs)
+{
+    if (!out || nCells < 0 || nFaces < nInternalFaces || !owner || (nInternalFaces > 0 && !neighbour)) return GPUPCG_ERR_ARG;
+    *out = nullptr;
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0 || device >= nDev)
+    {
+        g_meshErr = "gpupcg_mesh_create: no CUDA device visible (this library has no CPU fallback)";
+        return GPUPCG_ERR_NODEVICE;
+    }
+    gpupcg_mesh m = new gpupcg_mesh_s();
+    m->device = device;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10)
+    {
+        g_meshErr = "gpupcg_mesh_create: not a Blackwell (sm_100) class GPU";
+        delete m;
+        return GPUPCG_ERR_NODEVICE;
+    }
+    m->numSMs = prop.multiProcessorCount;
+    MCK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    MCK(cudaEventCreate(&m->ev0)); MCK(cudaEventCreate(&m->ev1));
+    const int nIF = nInternalFaces, nBF = nFaces - nIF;
+    // cell -> faces in the order surfaceIntegrate / negSumDiag touch a cell: internal faces ascending, then boundary
+    std::vector<int> start(nCells + 1, 0);
+    for (int f = 0; f < nFaces; f++) start[owner[f] + 1]++;
+    for (int f = 0; f < nIF; f++) start[neighbour[f] + 1]++;
+    for (int c = 0; c < nCells; c++) start[c + 1] += start[c];
+    std::vector<int> cf(start[nCells]), cur(start.begin(), start.end() - 1);
+    for (int f = 0; f < nIF; f++)
+    {
+        cf[cur[owner[f]]++] = f;
+        cf[cur[neighbour[f]]++] = f | 0x80000000;
+    }
+    for (int f = nIF; f < nFaces; f++) cf[cur[owner[f]]++] = f;
+    std::vector<int> bft(nBF > 0 ? nBF : 1, 0);
+    for (int p = 0; p < nPatches; p++)
+        for (int i = 0; i < patchSize[p]; i++) bft[patchStart[p] + i - nIF] = patchType[p];
+    MeshDev& M = m->M;
+    M.nCells = nCells; M.nFaces = nFaces; M.nIF = nIF; M.nPatches = nPatches;
+    MCK(up(m, M.owner, owner, nFaces)); MCK(up(m, M.neighbour, neighbour, nIF)); MCK(up(m, M.bfPatchType, bft.data(), nBF));
+    MCK(up(m, M.cellFaceStart, start.data(), nCells + 1)); MCK(up(m, M.cellFace, cf.data(), cf.size()));
+    MCK(up(m, M.Sf, Sf, 3*(size_t)nFaces)); MCK(up(m, M.magSf, magSf, nFaces)); MCK(up(m, M.Cf, Cf, 3*(size_t)nFaces));
+    MCK(up(m, M.C, C, 3*(size_t)nCells)); MCK(up(m, M.V, V, nCells)); MCK(up(m, M.weights, weights, nIF));
+    MCK(up(m, M.deltaCoeffs, deltaCoeffs, nFaces));
+    MCK(alloc(m, m->dMu, nCells)); MCK(alloc(m, m->dLambda, nCells)); MCK(alloc(m, m->dRho, nCells));
+    MCK(alloc(m, m->dD, 3*(size_t)nCells)); MCK(alloc(m, m->dGradD, 9*(size_t)nCells)); MCK(alloc(m, m->dGradDf, 9*(size_t)nFaces));
+    MCK(alloc(m, m->dTraction, 3*(size_t)nBF)); MCK(alloc(m, m->dPressure, nBF)); MCK(alloc(m, m->dFixed, 3*(size_t)nBF));
+    MCK(alloc(m, m->dUpper, nIF)); MCK(alloc(m, m->dLup, nIF)); MCK(alloc(m, m->dGms, nFaces));
+    MCK(alloc(m, m->dFluxE, 3*(size_t)nFaces)); MCK(alloc(m, m->dFluxC, 3*(size_t)nIF));
+    MCK(alloc(m, m->dDiag, nCells)); MCK(alloc(m, m->dSource, 3*(size_t)nCells));
+    MCK(alloc(m, m->dIC, 3*(size_t)nBF)); MCK(alloc(m, m->dBC, 3*(size_t)nBF));
+    MCK(alloc(m, m->dEps, 6*(size_t)nCells)); MCK(alloc(m, m->dSig, 6*(size_t)nCells));
+    MCK(cudaStreamSynchronize(m->stream));
+    *out = m;
+    return GPUPCG_OK;
+}
+
+static int agrid(gpupcg_mesh m, long long n) { long long g = (n + ATPB - 1)/ATPB; return (int)std::max<long long>(1, std::min<long long>(g, m->numSMs*16)); }
+
+extern "C" int gpupcg_assemble_D(gpupcg_mesh m, const double* mu, const double* lambda, const double* rho, const double* g,
+                                 const double* D, const double* gradD, const double* gradDf, const double* traction,
+                                 const double* pressure, const double* fixedValue, double limitCoeff, int reps,
+                                 double* upper, double* diag, double* source, double* internalCoeffs,
+                                 double* boundaryCoeffs, double* kernel_ms)
+{
+    if (!m || !mu || !lambda || !rho || !g || !D || !gradD || !gradDf) return GPUPCG_ERR_ARG;
+    const MeshDev& M = m->M;
+    const int nC = M.nCells, nF = M.nFaces, nIF = M.nIF, nBF = nF - nIF;
+    MCK(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+    auto h2d = [&](double* d, const double* h, size_t n) { return n && h ? cudaMemcpyAsync(d, h, n*sizeof(double), cudaMemcpyHostToDevice, s) : cudaSuccess; };
+    MCK(h2d(m->dMu, mu, nC)); MCK(h2d(m->dLambda, lambda, nC)); MCK(h2d(m->dRho, rho, nC));
+    MCK(h2d(m->dD, D, 3*(size_t)nC)); MCK(h2d(m->dGradD, gradD, 9*(size_t)nC)); MCK(h2d(m->dGradDf, gradDf, 9*(size_t)nF));
+    MCK(h2d(m->dTraction, traction, 3*(size_t)nBF)); MCK(h2d(m->dPressure, pressure, nBF)); MCK(h2d(m->dFixed, fixedValue, 3*(size_t)nBF));
+    if (reps < 1) reps = 1;
+    MCK(cudaEventRecord(m->ev0, s));
+    for (int r = 0; r < reps; r++)
+    {
+        k_asm_faces<<<agrid(m, nF), ATPB, 0, s>>>(M, m->dMu, m->dLambda, m->dD, m->dGradD, m->dGradDf, limitCoeff,
+                                                  m->dUpper, m->dLup, m->dGms, m->dFluxE, m->dFluxC);
+        k_asm_cells<<<agrid(m, nC), ATPB, 0, s>>>(M, m->dRho, g[0], g[1], g[2], m->dLup, m->dFluxE, m->dFluxC, m->dDiag, m->dSource);
+        if (nBF > 0)
+            k_asm_patches<<<agrid(m, nBF), ATPB, 0, s>>>(M, m->dMu, m->dLambda, m->dGradD, m->dGradDf, m->dGms, m->dTraction,
+                                                         m->dPressure, m->dFixed, m->dIC, m->dBC);
+    }
+    MCK(cudaEventRecord(m->ev1, s));
+    MCK(cudaGetLastError());
+    auto d2h = [&](double* h, const double* d, size_t n) { return n && h ? cudaMemcpyAsync(h, d, n*sizeof(double), cudaMemcpyDeviceToHost, s) : cudaSuccess; };
+    MCK(d2h(upper, m->dUpper, nIF)); MCK(d2h(diag, m->dDiag, nC)); MCK(d2h(source, m->dSource, 3*(size_t)nC));
+    MCK(d2h(internalCoeffs, m->dIC, 3*(size_t)nBF)); MCK(d2h(boundaryCoeffs, m->dBC, 3*(size_t)nBF));
+    MCK(cudaStreamSynchronize(s));
+    if (kernel_ms) { float ms = 0.f; cudaEventElapsedTime(&ms, m->ev0, m->ev1); *kernel_ms = ms/reps; }
+    return GPUPCG_OK;
+}
+
+extern "C" int gpupcg_sigma(gpupcg_mesh m, const double* mu, const double* lambda, const double* gradD,
+                            double* epsilon, double* sigma)
+{
+    if (!m || !mu || !lambda || !gradD || !epsilon || !sigma) return GPUPCG_ERR_ARG;
+    const int nC = m->M.nCells;
+    MCK(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+    MCK(cudaMemcpyAsync(m->dMu, mu, sizeof(double)*nC, cudaMemcpyHostToDevice, s));
+    MCK(cudaMemcpyAsync(m->dLambda, lambda, sizeof(double)*nC, cudaMemcpyHostToDevice, s));
+    MCK(cudaMemcpyAsync(m->dGradD, gradD, sizeof(double)*9*(size_t)nC, cudaMemcpyHostToDevice, s));
+    k_sigma<<<agrid(m, nC), ATPB, 0, s>>>(nC, m->dMu, m->dLambda, m->dGradD, m->dEps, m->dSig);
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpyAsync(epsilon, m->dEps, sizeof(double)*6*(size_t)nC, cudaMemcpyDeviceToHost, s));
+    MCK(cudaMemcpyAsync(sigma, m->dSig, sizeof(double)*6*(size_t)nC, cudaMemcpyDeviceToHost, s));
+    MCK(cudaStreamSynchronize(s));
+    return GPUPCG_OK;
+}

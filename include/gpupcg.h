@@ -165,6 +165,36 @@ int gpupcg_time_kernel(gpupcg_handle h, int which, int reps, int flushL2, double
 int gpupcg_comm_unique_id(void* ncclUniqueId_128bytes);
 int gpupcg_comm_init(gpupcg_handle h, int rank, int nRanks, const void* ncclUniqueId_128bytes);
 
+/* ---- GPU assembly of the D equation ---------------------------------------------------------------
+ * What unsTotalLagrangianStress::evolve() builds per outer iteration before DEqn.solve()
+ * (unsTotalLagrangianStress.C:846-859, steadyState d2dt2, linear elasticity):
+ *   fvm::laplacian(2*muf+lambdaf, D) with the reference's `skewCorrected` snGrad scheme
+ *   (skewCorrectedVectorSnGrad.C:50-294), fvc::div(Sf & (...gradDf...)), rho*g, and the boundary
+ *   coefficients of tractionDisplacement (patchType 0) / fixedDisplacement (patchType 1) patches.
+ * gpupcg_mesh_create uploads what foam-extend's fvMesh provides once per mesh: owner/neighbour, the patch
+ * table and mesh.Sf(), magSf(), Cf(), C(), V(), weights(), deltaCoeffs() (boundary faces included).
+ * gpupcg_assemble_D: per-cell mu, lambda, rho, D[3], gradD[9]; per-face gradDf[9]; per boundary face
+ * traction[3], pressure, fixedValue[3]; g[3]; limitCoeff of the snGrad scheme.  Outputs (host, the caller's
+ * numbering): upper[nInternalFaces], diag[nCells] (before addBoundaryDiag), source[nCells*3] (before
+ * addBoundarySource), internalCoeffs / boundaryCoeffs[nBoundaryFaces*3].  reps > 1 repeats the three kernels
+ * for timing; kernel_ms (optional) = mean device time of one assembly.
+ * gpupcg_sigma: epsilon = symm(gradD), sigma = 2 mu eps + lambda tr(eps) I (symmTensor order xx xy xz yy yz zz). */
+typedef struct gpupcg_mesh_s* gpupcg_mesh;
+int gpupcg_mesh_create(gpupcg_mesh* m, int device, int nCells, int nFaces, int nInternalFaces,
+                       const int* owner, const int* neighbour, int nPatches, const int* patchStart,
+                       const int* patchSize, const int* patchType, const double* Sf, const double* magSf,
+                       const double* Cf, const double* C, const double* V, const double* weights,
+                       const double* deltaCoeffs);
+int gpupcg_mesh_destroy(gpupcg_mesh m);
+const char* gpupcg_mesh_last_error(gpupcg_mesh m);
+int gpupcg_assemble_D(gpupcg_mesh m, const double* mu, const double* lambda, const double* rho, const double* g,
+                      const double* D, const double* gradD, const double* gradDf, const double* traction,
+                      const double* pressure, const double* fixedValue, double limitCoeff, int reps,
+                      double* upper, double* diag, double* source, double* internalCoeffs,
+                      double* boundaryCoeffs, double* kernel_ms);
+int gpupcg_sigma(gpupcg_mesh m, const double* mu, const double* lambda, const double* gradD,
+                 double* epsilon, double* sigma);
+
 /* ---- host memory helpers ----------------------------------------------------------------------
  * Page-lock caller-owned arrays (scalarField storage) so that the staging copies are DMA.       */
 int gpupcg_host_register(void* ptr, unsigned long long bytes);

@@ -24,6 +24,12 @@ class Domain(C.Structure):
     ]
 
 
+class Mesh(C.Structure):
+    _fields_ = [("nCells", C.c_int), ("nFaces", C.c_int), ("nInternalFaces", C.c_int), ("nPatches", C.c_int),
+                ("owner", ip), ("neighbour", ip), ("patchStart", ip), ("patchSize", ip), ("patchType", ip),
+                ("Sf", dp), ("magSf", dp), ("Cf", dp), ("C", dp), ("V", dp), ("weights", dp), ("deltaCoeffs", dp)]
+
+
 class Perf(C.Structure):
     _fields_ = [
         ("initialResidual", C.c_double), ("finalResidual", C.c_double), ("normFactor", C.c_double),
@@ -60,6 +66,11 @@ def load(build=True):
     lib.orc_bench_dic.restype = C.c_double
     lib.orc_bench_dic.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, dp, dp, dp, dp]
     lib.orc_set_sum_mode.argtypes = [C.c_int]
+    lib.orc_lame.argtypes = [C.c_double, C.c_double, C.c_int, dp, dp]
+    lib.orc_assemble_D.restype = None
+    lib.orc_assemble_D.argtypes = [C.POINTER(Mesh)] + [dp]*10 + [C.c_double] + [dp]*5
+    lib.orc_sigma.restype = None
+    lib.orc_sigma.argtypes = [C.c_int, dp, dp, dp, dp, dp]
     lib.orc_num_threads.restype = C.c_int
     lib.orc_set_num_threads.argtypes = [C.c_int]
     _lib = lib
@@ -181,3 +192,46 @@ def set_sum_mode(mode):
     """0: the reference's sequential sums (default).  1: pairwise summation of the same terms -- test-only, to measure
     the sensitivity of a residual history to re-association of the reductions."""
     load().orc_set_sum_mode(int(mode))
+
+
+PATCH_TYPES = {"tractionDisplacement": 0, "fixedDisplacement": 1}
+
+
+def lame(E, nu, planeStress=False):
+    lib = load()
+    mu, lam = C.c_double(), C.c_double()
+    lib.orc_lame(E, nu, 1 if planeStress else 0, C.byref(mu), C.byref(lam))
+    return mu.value, lam.value
+
+
+def _mesh_struct(mesh, geom, patchTypes):
+    keep = dict(owner=_i(mesh.owner), neighbour=_i(mesh.neighbour), ps=_i([p["start"] for p in mesh.patches]),
+                pz=_i([p["size"] for p in mesh.patches]), pt=_i([PATCH_TYPES[patchTypes[p["name"]]] for p in mesh.patches]),
+                Sf=_f(geom.Sf), magSf=_f(geom.magSf), Cf=_f(geom.Cf), C=_f(geom.C), V=_f(geom.V), w=_f(geom.weights),
+                dc=_f(geom.deltaCoeffs))
+    M = Mesh()
+    M.nCells, M.nFaces, M.nInternalFaces, M.nPatches = mesh.nCells, mesh.nFaces, mesh.nInternalFaces, len(mesh.patches)
+    M.owner, M.neighbour = _ip(keep["owner"]), _ip(keep["neighbour"])
+    M.patchStart, M.patchSize, M.patchType = _ip(keep["ps"]), _ip(keep["pz"]), _ip(keep["pt"])
+    M.Sf, M.magSf, M.Cf, M.C, M.V = _dp(keep["Sf"]), _dp(keep["magSf"]), _dp(keep["Cf"]), _dp(keep["C"]), _dp(keep["V"])
+    M.weights, M.deltaCoeffs = _dp(keep["w"]), _dp(keep["dc"])
+    return M, keep
+
+
+def assemble_D(mesh, geom, patchTypes, mu, lam, rho, g, D, gradD, gradDf, traction, pressure, fixedValue, limitCoeff=1.0):
+    lib = load()
+    M, keep = _mesh_struct(mesh, geom, patchTypes)
+    a = [_f(v) for v in (mu, lam, rho, g, D, gradD, gradDf, traction, pressure, fixedValue)]
+    nC, nIF, nBF = mesh.nCells, mesh.nInternalFaces, mesh.nFaces - mesh.nInternalFaces
+    upper = np.empty(nIF); diag = np.empty(nC); source = np.empty((nC, 3)); ic = np.empty((nBF, 3)); bc = np.empty((nBF, 3))
+    lib.orc_assemble_D(C.byref(M), *[_dp(v) for v in a], float(limitCoeff), _dp(upper), _dp(diag), _dp(source), _dp(ic), _dp(bc))
+    return dict(upper=upper, diag=diag, source=source, internalCoeffs=ic, boundaryCoeffs=bc)
+
+
+def sigma(mu, lam, gradD):
+    lib = load()
+    mu, lam, gradD = _f(mu), _f(lam), _f(gradD)
+    n = mu.shape[0]
+    eps = np.empty((n, 6)); sig = np.empty((n, 6))
+    lib.orc_sigma(n, _dp(mu), _dp(lam), _dp(gradD), _dp(eps), _dp(sig))
+    return eps, sig

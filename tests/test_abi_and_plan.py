@@ -17,7 +17,7 @@ def test_library_exports_every_declared_symbol():
     lib = pkg.load_library()
     with open(os.path.join(ROOT, "include", "gpupcg.h")) as f:
         header = f.read()
-    declared = set(re.findall(r"\b(gpupcg_[a-z_0-9]+)\s*\(", header))
+    declared = set(re.findall(r"\b(gpupcg_[A-Za-z_0-9]+)\s*\(", header))
     assert declared, "no prototypes found in include/gpupcg.h"
     assert declared == set(capi.SYMBOLS), (declared ^ set(capi.SYMBOLS))
     for name in declared:

@@ -1,0 +1,126 @@
+"""D-equation assembly: the oracle against closed forms on the orthogonal hex cantilever (CPU), and the GPU kernels
+against the oracle bit for bit on hex and jittered-tet meshes (GPU)."""
+import numpy as np
+import pytest
+
+import oracle
+import fluidstructureinteraction_b200 as pkg
+from fluidstructureinteraction_b200 import cases, geometry, meshes
+
+PATCHES = {"fixed": "fixedDisplacement", "loaded": "tractionDisplacement", "free": "tractionDisplacement"}
+
+
+def fields(mesh, seed, scale=1e-4):
+    rng = np.random.default_rng(seed)
+    nC, nF, nBF = mesh.nCells, mesh.nFaces, mesh.nFaces - mesh.nInternalFaces
+    mu, lam = oracle.lame(cases.STEEL["E"], cases.STEEL["nu"])
+    f = dict(mu=np.full(nC, mu)*rng.uniform(0.9, 1.1, nC), lam=np.full(nC, lam)*rng.uniform(0.9, 1.1, nC),
+             rho=np.full(nC, cases.STEEL["rho"]), g=np.array([0.0, 0.0, -9.81]),
+             D=scale*rng.standard_normal((nC, 3)), gradD=scale*rng.standard_normal((nC, 9)),
+             gradDf=scale*rng.standard_normal((nF, 9)), traction=np.zeros((nBF, 3)), pressure=rng.uniform(0, 1e3, nBF),
+             fixedValue=scale*rng.standard_normal((nBF, 3)))
+    p = mesh.patch("loaded")
+    f["traction"][p["start"] - mesh.nInternalFaces:p["start"] - mesh.nInternalFaces + p["size"]] = [0.0, 0.0, -1e4]
+    return f
+
+
+def test_geometry_of_uniform_hex():
+    m = meshes.hex_box(6, 4, 5)
+    g = geometry.compute(m)
+    hx, hy, hz = 2.0/6, 0.5/4, 1.0/5
+    assert np.allclose(g.V, hx*hy*hz, rtol=1e-13)
+    assert np.allclose(g.weights, 0.5, rtol=1e-13)
+    l, u = m.lower_upper()
+    d = u.astype(np.int64) - l
+    assert np.allclose(g.deltaCoeffs[:m.nInternalFaces][d == 1], 1/hx, rtol=1e-12)
+    assert np.allclose(g.magSf[:m.nInternalFaces][d == 1], hy*hz, rtol=1e-12)
+    p = m.patch("fixed")
+    assert np.allclose(g.deltaCoeffs[p["start"]:p["start"] + p["size"]], 2/hx, rtol=1e-12)
+    assert np.allclose(g.Sf[p["start"]:p["start"] + p["size"]], [-hy*hz, 0, 0], atol=1e-15)
+
+
+def test_oracle_assembly_reduces_to_closed_form_on_orthogonal_hex():
+    """With uniform steel, D = 0 and gradDf = 0 the assembled z-component system is cases.cantilever_system()."""
+    nx, ny, nz = 6, 4, 5
+    m = meshes.hex_box(nx, ny, nz)
+    g = geometry.compute(m)
+    f = fields(m, 1)
+    mu, lam = oracle.lame(cases.STEEL["E"], cases.STEEL["nu"])
+    f["mu"][:] = mu; f["lam"][:] = lam
+    for k in ("D", "gradD", "gradDf", "fixedValue", "pressure"):
+        f[k][...] = 0.0
+    f["g"][:] = 0.0
+    a = oracle.assemble_D(m, g, PATCHES, f["mu"], f["lam"], f["rho"], f["g"], f["D"], f["gradD"], f["gradDf"],
+                          f["traction"], f["pressure"], f["fixedValue"], 1.0)
+    s = cases.cantilever_system(nx, ny, nz)
+    assert np.allclose(a["upper"], s["upper"], rtol=1e-12)
+    diag = a["diag"].copy()
+    src = a["source"][:, 2].copy()
+    nIF = m.nInternalFaces
+    np.add.at(diag, m.owner[nIF:], a["internalCoeffs"][:, 2])
+    np.add.at(src, m.owner[nIF:], a["boundaryCoeffs"][:, 2])
+    assert np.allclose(diag, s["diag"], rtol=1e-12)
+    assert np.allclose(src, s["b"], rtol=1e-12, atol=1e-9)
+    assert np.all(a["source"] == 0.0)
+    # orthogonal mesh: the skew correction vanishes identically, so random D / gradD must not change the source
+    f2 = fields(m, 2)
+    a2 = oracle.assemble_D(m, g, PATCHES, f["mu"], f["lam"], f["rho"], f["g"], f2["D"], f2["gradD"], f["gradDf"],
+                           f["traction"], f["pressure"], f["fixedValue"], 1.0)
+    assert np.max(np.abs(a2["source"])) <= 1e-6*np.max(np.abs(a2["upper"]))*1e-4
+
+
+def test_oracle_sigma_and_lame():
+    mu, lam = oracle.lame(2e11, 0.3)
+    assert mu == 2e11/(2.0*(1.0 + 0.3)) and lam == 0.3*2e11/((1.0 + 0.3)*(1.0 - 2.0*0.3))
+    assert oracle.lame(2e11, 0.3, True)[1] == 0.3*2e11/((1.0 + 0.3)*(1.0 - 0.3))
+    G = np.arange(9.0)[None, :]
+    eps, sig = oracle.sigma(np.array([2.0]), np.array([3.0]), G)
+    assert np.array_equal(eps[0], [0, 2, 4, 4, 6, 8])
+    assert np.array_equal(sig[0], [0 + 36, 8, 16, 16 + 36, 24, 32 + 36])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["hex", "tet"])
+def test_gpu_assembly_bit_exact(kind):
+    m = meshes.hex_box(12, 6, 8) if kind == "hex" else meshes.tet_box(6, 4, 5, jitter=0.15)
+    g = geometry.compute(m)
+    f = fields(m, 5)
+    gm = pkg.GpuMesh(m, g, PATCHES)
+    for limitCoeff in (1.0, 0.5):
+        a = gm.assemble_D(f["mu"], f["lam"], f["rho"], f["g"], f["D"], f["gradD"], f["gradDf"], f["traction"],
+                          f["pressure"], f["fixedValue"], limitCoeff)
+        r = oracle.assemble_D(m, g, PATCHES, f["mu"], f["lam"], f["rho"], f["g"], f["D"], f["gradD"], f["gradDf"],
+                              f["traction"], f["pressure"], f["fixedValue"], limitCoeff)
+        for k in ("upper", "diag", "source", "internalCoeffs", "boundaryCoeffs"):
+            assert np.array_equal(a[k], r[k]), k
+    if kind == "tet":
+        assert np.max(np.abs(r["source"])) > 0          # the skew correction is live on the jittered mesh
+    eps, sig = gm.sigma(f["mu"], f["lam"], f["gradD"])
+    e2, s2 = oracle.sigma(f["mu"], f["lam"], f["gradD"])
+    assert np.array_equal(eps, e2) and np.array_equal(sig, s2)
+    gm.close()
+
+
+@pytest.mark.gpu
+def test_assembled_system_solves_through_gpupcg():
+    """Assembly -> addBoundaryDiag/addBoundarySource -> gpuPCG, against the same chain on the oracle."""
+    m = meshes.hex_box(16, 6, 8)
+    g = geometry.compute(m)
+    f = fields(m, 9, scale=1e-6)
+    gm = pkg.GpuMesh(m, g, PATCHES)
+    a = gm.assemble_D(f["mu"], f["lam"], f["rho"], f["g"], f["D"], f["gradD"], f["gradDf"], f["traction"], f["pressure"],
+                      f["fixedValue"], 1.0)
+    l, u = m.lower_upper()
+    nIF = m.nInternalFaces
+    solver = pkg.GpuPCG(l, u, m.nCells)
+    for c in range(3):
+        diag = a["diag"].copy(); src = a["source"][:, c].copy()
+        np.add.at(diag, m.owner[nIF:], a["internalCoeffs"][:, c])
+        np.add.at(src, m.owner[nIF:], a["boundaryCoeffs"][:, c])
+        solver.set_matrix(diag, a["upper"] if c == 0 else None)
+        xg = np.zeros(m.nCells); xc = np.zeros(m.nCells)
+        pg, hg = solver.solve(xg, src, 1e-9, 0.01)
+        pc, hc = oracle.pcg_solve(l, u, diag, a["upper"], xc, src, 1e-9, 0.01)
+        assert pg["nIterations"] == pc["nIterations"] and pg["nIterations"] > 3
+        assert np.max(np.abs(xg - xc)) <= 1e-9*np.max(np.abs(xc))
+    solver.close(); gm.close()
