@@ -83,6 +83,8 @@ SYMBOLS = {
     "gpupcg_mesh_last_error": (C.c_char_p, [C.c_void_p]),
     "gpupcg_assemble_D": (C.c_int, [C.c_void_p] + [c_double_p]*10 + [C.c_double, C.c_int] + [c_double_p]*6),
     "gpupcg_sigma": (C.c_int, [C.c_void_p] + [c_double_p]*5),
+    "gpupcg_mesh_set_points": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_int_p, c_int_p]),
+    "gpupcg_gradients": (C.c_int, [C.c_void_p] + [c_double_p]*5 + [C.c_double, C.c_int] + [c_double_p]*4),
     "gpupcg_host_register": (C.c_int, [C.c_void_p, C.c_ulonglong]),
     "gpupcg_host_unregister": (C.c_int, [C.c_void_p]),
     "gpupcg_plan_export": (C.c_int, [C.c_int, C.c_int, c_int_p, c_int_p, C.c_int, C.c_int, C.POINTER(PlanInfo),
@@ -301,6 +303,18 @@ class GpuMesh(object):
         self._check(self.lib.gpupcg_assemble_D(self.h, *[_dp(v) for v in a], float(limitCoeff), int(reps), _dp(upper),
                                                _dp(diag), _dp(source), _dp(ic), _dp(bc), C.byref(ms)))
         return dict(upper=upper, diag=diag, source=source, internalCoeffs=ic, boundaryCoeffs=bc, kernel_ms=ms.value)
+
+    def gradients(self, D, pointD, gradDold, fixedValue, patchGradient, limitCoeff=1.0, reps=1):
+        if not getattr(self, "_points", None):
+            self._points = (_f64(self.mesh.points), _i32(self.mesh.faceStart), _i32(self.mesh.facePoints))
+            self._check(self.lib.gpupcg_mesh_set_points(self.h, self.mesh.nPoints, _dp(self._points[0]),
+                                                        _ip(self._points[1]), _ip(self._points[2])))
+        a = [_f64(v) for v in (D, pointD, gradDold, fixedValue, patchGradient)]
+        G = np.empty((self.nC, 9)); Gb = np.empty((self.nBF, 9)); Gf = np.empty((self.nF, 9))
+        ms = C.c_double(0.0)
+        self._check(self.lib.gpupcg_gradients(self.h, *[_dp(v) for v in a], float(limitCoeff), int(reps), _dp(G), _dp(Gb),
+                                              _dp(Gf), C.byref(ms)))
+        return G, Gb, Gf, ms.value
 
     def sigma(self, mu, lam, gradD):
         eps = np.empty((self.nC, 6)); sig = np.empty((self.nC, 6))

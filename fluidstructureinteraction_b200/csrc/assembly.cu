@@ -50,6 +50,9 @@ struct MeshDev
     const int *owner, *neighbour, *bfPatchType;      // bfPatchType[nFaces - nIF]
     const int *cellFaceStart, *cellFace;              // CSR; face id, bit 31 set = the cell is the face's neighbour
     const double *Sf, *magSf, *Cf, *C, *V, *weights, *deltaCoeffs;
+    int nPoints;
+    const int *faceStart, *facePoints;                // point loops of the faces (vertex-based gradients)
+    const double* points;
 };
 
 __global__ void __launch_bounds__(ATPB) k_asm_faces(MeshDev M, const double* __restrict__ mu, const double* __restrict__ lambda,
@@ -258,6 +261,243 @@ __global__ void __launch_bounds__(ATPB) k_sigma(int nCells, const double* __rest
     }
 }
 
+// ---- vertex-based gradients of the reference (numerics/fvc/fvcGradf.C) ---------------------------------------
+__device__ __forceinline__ void cross3(const double* a, const double* b, double* r)
+{
+    r[0] = sub(mul(a[1], b[2]), mul(a[2], b[1]));
+    r[1] = sub(mul(a[2], b[0]), mul(a[0], b[2]));
+    r[2] = sub(mul(a[0], b[1]), mul(a[1], b[0]));
+}
+
+// one face's triangle-fan contribution sign*(St*ttcf), sign*(St & Ct)   (fvcGradf.C:541-610, 623-684)
+__device__ void grad_face(const MeshDev& M, int f, const double* __restrict__ pf, bool minus, double* G, double& V)
+{
+    const int p0 = M.faceStart[f], n = M.faceStart[f + 1] - p0;
+    const int* fp = M.facePoints + p0;
+    const double* X = M.points;
+    if (n == 3)
+    {
+        const int i0 = fp[0], i1 = fp[1], i2 = fp[2];
+        double ab[3], ac[3], nrm[3], avg[3], ctr[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) { ab[d] = sub(X[3*i1 + d], X[3*i0 + d]); ac[d] = sub(X[3*i2 + d], X[3*i0 + d]); }
+        cross3(ab, ac, nrm);
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+        {
+            nrm[d] = mul(0.5, nrm[d]);
+            avg[d] = mul(1.0/3.0, add(add(pf[3*i0 + d], pf[3*i1 + d]), pf[3*i2 + d]));
+            ctr[d] = mul(1.0/3.0, add(add(X[3*i0 + d], X[3*i1 + d]), X[3*i2 + d]));
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+            {
+                const double t = mul(nrm[i], avg[j]);
+                G[3*i + j] = minus ? sub(G[3*i + j], t) : add(G[3*i + j], t);
+            }
+        const double sr = dot3(nrm, ctr);
+        V = minus ? sub(V, sr) : add(V, sr);
+        return;
+    }
+    double centre[3] = {0.0, 0.0, 0.0}, cf[3] = {0.0, 0.0, 0.0};
+    for (int p = 0; p < n; p++)
+    {
+        const int ip = fp[p];
+#pragma unroll
+        for (int d = 0; d < 3; d++) { centre[d] = add(centre[d], X[3*ip + d]); cf[d] = add(cf[d], pf[3*ip + d]); }
+    }
+    const double dn = (double)n;
+#pragma unroll
+    for (int d = 0; d < 3; d++) { centre[d] = dvd(centre[d], dn); cf[d] = dvd(cf[d], dn); }
+    for (int p = 0; p < n; p++)
+    {
+        const int ia = fp[p], ib = fp[(p + 1) % n];
+        double ttcf[3], a[3], b[3], St[3], Ct[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+        {
+            ttcf[d] = dvd(add(add(pf[3*ia + d], pf[3*ib + d]), cf[d]), 3.0);
+            a[d] = sub(X[3*ia + d], centre[d]);
+            b[d] = sub(X[3*ib + d], centre[d]);
+        }
+        cross3(a, b, St);
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+        {
+            St[d] = dvd(St[d], 2.0);
+            Ct[d] = dvd(add(add(centre[d], X[3*ia + d]), X[3*ib + d]), 3.0);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+            {
+                const double t = mul(St[i], ttcf[j]);
+                G[3*i + j] = minus ? sub(G[3*i + j], t) : add(G[3*i + j], t);
+            }
+        const double sc = dot3(St, Ct);
+        V = minus ? sub(V, sc) : add(V, sc);
+    }
+}
+
+// tangential face gradient from point values: sum_edges Le*fe / mag   (fvcGradf.C:97-142, 144-198, 410-482)
+__device__ void face_tangential_grad(const MeshDev& M, int f, const double* __restrict__ pf, double* G)
+{
+    const int p0 = M.faceStart[f], n = M.faceStart[f + 1] - p0;
+    const int* fp = M.facePoints + p0;
+    const double* X = M.points;
+    const double magSf = M.magSf[f];
+    double nf[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) nf[d] = dvd(M.Sf[3*(size_t)f + d], magSf);
+#pragma unroll
+    for (int k = 0; k < 9; k++) G[k] = 0.0;
+    for (int p = 0; p < n; p++)
+    {
+        const int s = fp[p], e_ = fp[(p + 1) % n];
+        double e[3], Le[3], fe[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) e[d] = sub(X[3*e_ + d], X[3*s + d]);
+        const double ne = dot3(nf, e);
+#pragma unroll
+        for (int d = 0; d < 3; d++) e[d] = sub(e[d], mul(nf[d], ne));
+        cross3(e, nf, Le);
+#pragma unroll
+        for (int d = 0; d < 3; d++) fe[d] = mul(0.5, add(pf[3*s + d], pf[3*e_ + d]));
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) G[3*i + j] = add(G[3*i + j], mul(Le[i], fe[j]));
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) G[k] = dvd(G[k], magSf);
+}
+
+// boundary snGrad of D: fixedDisplacement::snGrad() (fixedDisplacementFvPatchVectorField.C:96-127) or fixedGradient's gradient()
+__device__ void patch_snGrad(const MeshDev& M, int f, const double* __restrict__ D, const double* __restrict__ gradD,
+                             const double* __restrict__ fixedValue, const double* __restrict__ patchGradient, double* sn)
+{
+    const int bf = f - M.nIF, c = M.owner[f];
+    if (M.bfPatchType[bf] == 1)
+    {
+        double n[3], delta[3], k[3], kg[3], G[9];
+        const double magSf = M.magSf[f];
+#pragma unroll
+        for (int d = 0; d < 3; d++) { n[d] = dvd(M.Sf[3*(size_t)f + d], magSf); delta[d] = sub(M.Cf[3*(size_t)f + d], M.C[3*(size_t)c + d]); }
+        const double nd = dot3(n, delta);
+#pragma unroll
+        for (int d = 0; d < 3; d++) k[d] = sub(delta[d], mul(n[d], nd));
+#pragma unroll
+        for (int q = 0; q < 9; q++) G[q] = gradD[9*(size_t)c + q];
+        vdotT(k, G, kg);
+#pragma unroll
+        for (int d = 0; d < 3; d++) sn[d] = mul(sub(fixedValue[3*(size_t)bf + d], add(D[3*(size_t)c + d], kg[d])), M.deltaCoeffs[f]);
+    }
+    else
+    {
+#pragma unroll
+        for (int d = 0; d < 3; d++) sn[d] = patchGradient[3*(size_t)bf + d];
+    }
+}
+
+// K6: fvc::grad(D, pointD) -- one thread per cell gathers its faces in the order the reference's face loop visits it
+__global__ void __launch_bounds__(ATPB) k_grad_cells(MeshDev M, const double* __restrict__ pointD, double* __restrict__ gradD)
+{
+    for (int c = blockIdx.x*ATPB + threadIdx.x; c < M.nCells; c += gridDim.x*ATPB)
+    {
+        double G[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, V = 0.0;
+        for (int k = M.cellFaceStart[c]; k < M.cellFaceStart[c + 1]; k++)
+        {
+            const int code = M.cellFace[k];
+            grad_face(M, code & 0x7fffffff, pointD, code < 0, G, V);
+        }
+        V = dvd(V, 3.0);
+#pragma unroll
+        for (int q = 0; q < 9; q++) gradD[9*(size_t)c + q] = dvd(G[q], V);
+    }
+}
+
+// boundary field of grad(D): patch fGrad + gaussGrad::correctBoundaryConditions (fvcGradf.C:696-714)
+__global__ void __launch_bounds__(ATPB) k_grad_patches(MeshDev M, const double* __restrict__ D, const double* __restrict__ pointD,
+                                                       const double* __restrict__ gradDold, const double* __restrict__ fixedValue,
+                                                       const double* __restrict__ patchGradient, double* __restrict__ gradDb)
+{
+    const int nBF = M.nFaces - M.nIF;
+    for (int bf = blockIdx.x*ATPB + threadIdx.x; bf < nBF; bf += gridDim.x*ATPB)
+    {
+        const int f = M.nIF + bf;
+        double G[9], n[3], sn[3], nG[3];
+        face_tangential_grad(M, f, pointD, G);
+        const double magSf = M.magSf[f];
+#pragma unroll
+        for (int d = 0; d < 3; d++) n[d] = dvd(M.Sf[3*(size_t)f + d], magSf);
+        patch_snGrad(M, f, D, gradDold, fixedValue, patchGradient, sn);
+        vdotT(n, G, nG);
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) gradDb[9*(size_t)bf + 3*a + b] = add(G[3*a + b], mul(n[a], sub(sn[b], nG[b])));
+    }
+}
+
+// K7: fvc::fGrad(D, pointD) -- one thread per face: tangential part + n*snGrad(D) (skewCorrected scheme / patch snGrad)
+__global__ void __launch_bounds__(ATPB) k_fgrad_faces(MeshDev M, const double* __restrict__ D, const double* __restrict__ pointD,
+                                                      const double* __restrict__ gradD, const double* __restrict__ fixedValue,
+                                                      const double* __restrict__ patchGradient, double limitCoeff,
+                                                      double* __restrict__ gradDf)
+{
+    for (int f = blockIdx.x*ATPB + threadIdx.x; f < M.nFaces; f += gridDim.x*ATPB)
+    {
+        double G[9], n[3], sn[3];
+        face_tangential_grad(M, f, pointD, G);
+        const double magSf = M.magSf[f];
+        const double Sf[3] = {M.Sf[3*(size_t)f], M.Sf[3*(size_t)f + 1], M.Sf[3*(size_t)f + 2]};
+#pragma unroll
+        for (int d = 0; d < 3; d++) n[d] = dvd(Sf[d], magSf);
+        if (f < M.nIF)
+        {
+            const int P = M.owner[f], N = M.neighbour[f];
+            const double dc = M.deltaCoeffs[f];
+            const double Cf[3] = {M.Cf[3*(size_t)f], M.Cf[3*(size_t)f + 1], M.Cf[3*(size_t)f + 2]};
+            const double magSqrSf = add(add(mul(Sf[0], Sf[0]), mul(Sf[1], Sf[1])), mul(Sf[2], Sf[2]));
+            double kP[3], kN[3], a3[3], b3[3], ssf[3], t[3], GP[9], GN[9];
+#pragma unroll
+            for (int d = 0; d < 3; d++) kP[d] = sub(Cf[d], M.C[3*(size_t)P + d]);
+            {
+                const double s = dot3(Sf, kP);
+#pragma unroll
+                for (int d = 0; d < 3; d++) kP[d] = sub(kP[d], dvd(mul(Sf[d], s), magSqrSf));
+            }
+#pragma unroll
+            for (int d = 0; d < 3; d++) kN[d] = sub(Cf[d], M.C[3*(size_t)N + d]);
+            {
+                const double s = dot3(Sf, kN);
+#pragma unroll
+                for (int d = 0; d < 3; d++) kN[d] = sub(kN[d], dvd(mul(Sf[d], s), magSqrSf));
+            }
+#pragma unroll
+            for (int q = 0; q < 9; q++) { GP[q] = gradD[9*(size_t)P + q]; GN[q] = gradD[9*(size_t)N + q]; }
+            vdotT(kN, GN, a3);
+            vdotT(kP, GP, b3);
+#pragma unroll
+            for (int d = 0; d < 3; d++) ssf[d] = mul(sub(a3[d], b3[d]), dc);
+#pragma unroll
+            for (int d = 0; d < 3; d++) t[d] = add(mul(dc, sub(D[3*(size_t)N + d], D[3*(size_t)P + d])), ssf[d]);
+            double lim = dvd(mul(limitCoeff, mag3(t)), add(mul(sub(1.0, limitCoeff), mag3(ssf)), A_SMALL));
+            if (lim > 1.0) lim = 1.0;
+#pragma unroll
+            for (int d = 0; d < 3; d++) sn[d] = add(mul(dc, sub(D[3*(size_t)N + d], D[3*(size_t)P + d])), mul(ssf[d], lim));
+        }
+        else patch_snGrad(M, f, D, gradD, fixedValue, patchGradient, sn);
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) gradDf[9*(size_t)f + 3*a + b] = add(G[3*a + b], mul(n[a], sn[b]));
+    }
+}
+
 } // namespace
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -274,6 +514,7 @@ struct gpupcg_mesh_s
     double *dTraction = nullptr, *dPressure = nullptr, *dFixed = nullptr;
     double *dUpper = nullptr, *dLup = nullptr, *dGms = nullptr, *dFluxE = nullptr, *dFluxC = nullptr;
     double *dDiag = nullptr, *dSource = nullptr, *dIC = nullptr, *dBC = nullptr, *dEps = nullptr, *dSig = nullptr;
+    double *dPointD = nullptr, *dGradOld = nullptr, *dPatchGrad = nullptr, *dGradDb = nullptr;
 };
 
 static thread_local std::string g_meshErr;
@@ -434,5 +675,55 @@ extern "C" int gpupcg_sigma(gpupcg_mesh m, const double* mu, const double* lambd
     MCK(cudaMemcpyAsync(epsilon, m->dEps, sizeof(double)*6*(size_t)nC, cudaMemcpyDeviceToHost, s));
     MCK(cudaMemcpyAsync(sigma, m->dSig, sizeof(double)*6*(size_t)nC, cudaMemcpyDeviceToHost, s));
     MCK(cudaStreamSynchronize(s));
+    return GPUPCG_OK;
+}
+
+
+extern "C" int gpupcg_mesh_set_points(gpupcg_mesh m, int nPoints, const double* points, const int* faceStart, const int* facePoints)
+{
+    if (!m || nPoints < 0 || !points || !faceStart || !facePoints) return GPUPCG_ERR_ARG;
+    MCK(cudaSetDevice(m->device));
+    MeshDev& M = m->M;
+    M.nPoints = nPoints;
+    MCK(up(m, M.points, points, 3*(size_t)nPoints));
+    MCK(up(m, M.faceStart, faceStart, (size_t)M.nFaces + 1));
+    MCK(up(m, M.facePoints, facePoints, (size_t)faceStart[M.nFaces]));
+    const int nBF = M.nFaces - M.nIF;
+    MCK(alloc(m, m->dPointD, 3*(size_t)nPoints)); MCK(alloc(m, m->dGradOld, 9*(size_t)M.nCells));
+    MCK(alloc(m, m->dPatchGrad, 3*(size_t)nBF)); MCK(alloc(m, m->dGradDb, 9*(size_t)nBF));
+    MCK(cudaStreamSynchronize(m->stream));
+    return GPUPCG_OK;
+}
+
+// fvc::grad(D, pointD) then fvc::fGrad(D, pointD) exactly as evolve() calls them (unsTotalLagrangianStress.C:925-926):
+// the face gradient's snGrad correction and fixedDisplacement::snGrad see the NEW cell gradient.
+extern "C" int gpupcg_gradients(gpupcg_mesh m, const double* D, const double* pointD, const double* gradDold,
+                                const double* fixedValue, const double* patchGradient, double limitCoeff, int reps,
+                                double* gradD, double* gradDb, double* gradDf, double* kernel_ms)
+{
+    if (!m || !D || !pointD || !gradDold || !gradD || !gradDf) return GPUPCG_ERR_ARG;
+    if (!m->M.points) { m->err = "gpupcg_gradients: gpupcg_mesh_set_points has not been called"; return GPUPCG_ERR_STATE; }
+    const MeshDev& M = m->M;
+    const int nC = M.nCells, nF = M.nFaces, nBF = nF - M.nIF;
+    MCK(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+    auto h2d = [&](double* d, const double* h, size_t n) { return n && h ? cudaMemcpyAsync(d, h, n*sizeof(double), cudaMemcpyHostToDevice, s) : cudaSuccess; };
+    MCK(h2d(m->dD, D, 3*(size_t)nC)); MCK(h2d(m->dPointD, pointD, 3*(size_t)M.nPoints)); MCK(h2d(m->dGradOld, gradDold, 9*(size_t)nC));
+    MCK(h2d(m->dFixed, fixedValue, 3*(size_t)nBF)); MCK(h2d(m->dPatchGrad, patchGradient, 3*(size_t)nBF));
+    if (reps < 1) reps = 1;
+    MCK(cudaEventRecord(m->ev0, s));
+    for (int r = 0; r < reps; r++)
+    {
+        k_grad_cells<<<agrid(m, nC), ATPB, 0, s>>>(M, m->dPointD, m->dGradD);
+        if (nBF > 0)
+            k_grad_patches<<<agrid(m, nBF), ATPB, 0, s>>>(M, m->dD, m->dPointD, m->dGradOld, m->dFixed, m->dPatchGrad, m->dGradDb);
+        k_fgrad_faces<<<agrid(m, nF), ATPB, 0, s>>>(M, m->dD, m->dPointD, m->dGradD, m->dFixed, m->dPatchGrad, limitCoeff, m->dGradDf);
+    }
+    MCK(cudaEventRecord(m->ev1, s));
+    MCK(cudaGetLastError());
+    auto d2h = [&](double* h, const double* d, size_t n) { return n && h ? cudaMemcpyAsync(h, d, n*sizeof(double), cudaMemcpyDeviceToHost, s) : cudaSuccess; };
+    MCK(d2h(gradD, m->dGradD, 9*(size_t)nC)); MCK(d2h(gradDb, m->dGradDb, 9*(size_t)nBF)); MCK(d2h(gradDf, m->dGradDf, 9*(size_t)nF));
+    MCK(cudaStreamSynchronize(s));
+    if (kernel_ms) { float ms = 0.f; cudaEventElapsedTime(&ms, m->ev0, m->ev1); *kernel_ms = ms/reps; }
     return GPUPCG_OK;
 }

@@ -194,6 +194,15 @@ int gpupcg_assemble_D(gpupcg_mesh m, const double* mu, const double* lambda, con
                       double* boundaryCoeffs, double* kernel_ms);
 int gpupcg_sigma(gpupcg_mesh m, const double* mu, const double* lambda, const double* gradD,
                  double* epsilon, double* sigma);
+/* Vertex-based gradients of the reference (numerics/fvc/fvcGradf.C): gradD = fvc::grad(D, pointD) (:485-717, boundary
+ * field in gradDb) followed by gradDf = fvc::fGrad(D, pointD) (:47-231) exactly as evolve() calls them
+ * (unsTotalLagrangianStress.C:925-926).  gpupcg_mesh_set_points uploads mesh.points() and the face point loops.
+ * gradDold = the registered grad(D) at call time; patchGradient[nBoundaryFaces*3] = fixedGradient values of the
+ * tractionDisplacement patches (what their last updateCoeffs set).                                              */
+int gpupcg_mesh_set_points(gpupcg_mesh m, int nPoints, const double* points, const int* faceStart, const int* facePoints);
+int gpupcg_gradients(gpupcg_mesh m, const double* D, const double* pointD, const double* gradDold,
+                     const double* fixedValue, const double* patchGradient, double limitCoeff, int reps,
+                     double* gradD, double* gradDb, double* gradDf, double* kernel_ms);
 
 /* ---- host memory helpers ----------------------------------------------------------------------
  * Page-lock caller-owned arrays (scalarField storage) so that the staging copies are DMA.       */

@@ -27,7 +27,8 @@ class Domain(C.Structure):
 class Mesh(C.Structure):
     _fields_ = [("nCells", C.c_int), ("nFaces", C.c_int), ("nInternalFaces", C.c_int), ("nPatches", C.c_int),
                 ("owner", ip), ("neighbour", ip), ("patchStart", ip), ("patchSize", ip), ("patchType", ip),
-                ("Sf", dp), ("magSf", dp), ("Cf", dp), ("C", dp), ("V", dp), ("weights", dp), ("deltaCoeffs", dp)]
+                ("Sf", dp), ("magSf", dp), ("Cf", dp), ("C", dp), ("V", dp), ("weights", dp), ("deltaCoeffs", dp),
+                ("nPoints", C.c_int), ("faceStart", ip), ("facePoints", ip), ("points", dp)]
 
 
 class Perf(C.Structure):
@@ -69,6 +70,10 @@ def load(build=True):
     lib.orc_lame.argtypes = [C.c_double, C.c_double, C.c_int, dp, dp]
     lib.orc_assemble_D.restype = None
     lib.orc_assemble_D.argtypes = [C.POINTER(Mesh)] + [dp]*10 + [C.c_double] + [dp]*5
+    lib.orc_grad.restype = None
+    lib.orc_grad.argtypes = [C.POINTER(Mesh)] + [dp]*7
+    lib.orc_fgrad.restype = None
+    lib.orc_fgrad.argtypes = [C.POINTER(Mesh)] + [dp]*5 + [C.c_double, dp]
     lib.orc_sigma.restype = None
     lib.orc_sigma.argtypes = [C.c_int, dp, dp, dp, dp, dp]
     lib.orc_num_threads.restype = C.c_int
@@ -208,13 +213,14 @@ def _mesh_struct(mesh, geom, patchTypes):
     keep = dict(owner=_i(mesh.owner), neighbour=_i(mesh.neighbour), ps=_i([p["start"] for p in mesh.patches]),
                 pz=_i([p["size"] for p in mesh.patches]), pt=_i([PATCH_TYPES[patchTypes[p["name"]]] for p in mesh.patches]),
                 Sf=_f(geom.Sf), magSf=_f(geom.magSf), Cf=_f(geom.Cf), C=_f(geom.C), V=_f(geom.V), w=_f(geom.weights),
-                dc=_f(geom.deltaCoeffs))
+                dc=_f(geom.deltaCoeffs), fs=_i(mesh.faceStart), fp=_i(mesh.facePoints), pts=_f(mesh.points))
     M = Mesh()
     M.nCells, M.nFaces, M.nInternalFaces, M.nPatches = mesh.nCells, mesh.nFaces, mesh.nInternalFaces, len(mesh.patches)
     M.owner, M.neighbour = _ip(keep["owner"]), _ip(keep["neighbour"])
     M.patchStart, M.patchSize, M.patchType = _ip(keep["ps"]), _ip(keep["pz"]), _ip(keep["pt"])
     M.Sf, M.magSf, M.Cf, M.C, M.V = _dp(keep["Sf"]), _dp(keep["magSf"]), _dp(keep["Cf"]), _dp(keep["C"]), _dp(keep["V"])
     M.weights, M.deltaCoeffs = _dp(keep["w"]), _dp(keep["dc"])
+    M.nPoints, M.faceStart, M.facePoints, M.points = mesh.nPoints, _ip(keep["fs"]), _ip(keep["fp"]), _dp(keep["pts"])
     return M, keep
 
 
@@ -235,3 +241,24 @@ def sigma(mu, lam, gradD):
     eps = np.empty((n, 6)); sig = np.empty((n, 6))
     lib.orc_sigma(n, _dp(mu), _dp(lam), _dp(gradD), _dp(eps), _dp(sig))
     return eps, sig
+
+
+def grad(mesh, geom, patchTypes, D, pointD, gradDold, fixedValue, patchGradient):
+    """fvc::grad(D, pointD): returns (gradD (nC,9), boundary gradient (nBF,9))."""
+    lib = load()
+    M, keep = _mesh_struct(mesh, geom, patchTypes)
+    a = [_f(v) for v in (D, pointD, gradDold, fixedValue, patchGradient)]
+    nBF = mesh.nFaces - mesh.nInternalFaces
+    G = np.empty((mesh.nCells, 9)); Gb = np.empty((nBF, 9))
+    lib.orc_grad(C.byref(M), *[_dp(v) for v in a], _dp(G), _dp(Gb))
+    return G, Gb
+
+
+def fgrad(mesh, geom, patchTypes, D, pointD, gradD, fixedValue, patchGradient, limitCoeff=1.0):
+    """fvc::fGrad(D, pointD): face gradient on every face (nF,9)."""
+    lib = load()
+    M, keep = _mesh_struct(mesh, geom, patchTypes)
+    a = [_f(v) for v in (D, pointD, gradD, fixedValue, patchGradient)]
+    Gf = np.empty((mesh.nFaces, 9))
+    lib.orc_fgrad(C.byref(M), *[_dp(v) for v in a], float(limitCoeff), _dp(Gf))
+    return Gf

@@ -40,6 +40,11 @@ typedef struct orc_mesh
     const double* V;            /* [nCells] */
     const double* weights;      /* [nInternalFaces] */
     const double* deltaCoeffs;  /* [nFaces] */
+    /* point connectivity, only needed by the vertex-based gradients */
+    int nPoints;
+    const int* faceStart;       /* [nFaces+1] */
+    const int* facePoints;
+    const double* points;       /* [nPoints*3] */
 } orc_mesh;
 
 /* constitutiveModel::mu, lambda (constitutiveModel.C:193-257) */
@@ -266,5 +271,199 @@ void orc_sigma(int nCells, const double* mu, const double* lambda, const double*
         for (int k = 0; k < 6; k++) epsilon[6*c + k] = e[k];
         sigma[6*c + 0] = tm*e[0] + sph; sigma[6*c + 1] = tm*e[1]; sigma[6*c + 2] = tm*e[2];
         sigma[6*c + 3] = tm*e[3] + sph; sigma[6*c + 4] = tm*e[4]; sigma[6*c + 5] = tm*e[5] + sph;
+    }
+}
+
+
+/* ======================================================================================================== */
+/*  Vertex-based gradients of the reference: fvc::grad(vf, pf) and fvc::fGrad(vf, pf)                        */
+/*  (src/fluidStructureInteraction/numerics/fvc/fvcGradf.C), followed line by line.                          */
+/* ======================================================================================================== */
+static inline void cross3(const double* a, const double* b, double* r)
+{
+    r[0] = a[1]*b[2] - a[2]*b[1];
+    r[1] = a[2]*b[0] - a[0]*b[2];
+    r[2] = a[0]*b[1] - a[1]*b[0];
+}
+
+/* accumulate one face's contribution  sign*(St*ttcf)  and  sign*(St & Ct)  (fvcGradf.C:541-610 / 623-684) */
+static void grad_face(const orc_mesh* M, int f, const double* pf, double sign, double* G, double* V)
+{
+    const int* fp = M->facePoints + M->faceStart[f];
+    const int n = M->faceStart[f + 1] - M->faceStart[f];
+    const double* X = M->points;
+    if (n == 3)
+    {
+        /* SF = curFace.normal(points)*curFace.average(points, pfI) ; SR = normal & centre   ([EXT] face.C, triangle) */
+        const double *a = X + 3*fp[0], *b = X + 3*fp[1], *c = X + 3*fp[2];
+        double ab[3], ac[3], nrm[3], avg[3], ctr[3];
+        for (int d = 0; d < 3; d++) { ab[d] = b[d] - a[d]; ac[d] = c[d] - a[d]; }
+        cross3(ab, ac, nrm);
+        for (int d = 0; d < 3; d++)
+        {
+            nrm[d] = 0.5*nrm[d];
+            avg[d] = (1.0/3.0)*(pf[3*fp[0] + d] + pf[3*fp[1] + d] + pf[3*fp[2] + d]);
+            ctr[d] = (1.0/3.0)*(a[d] + b[d] + c[d]);
+        }
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++)
+            {
+                const double t = nrm[i]*avg[j];
+                if (sign > 0) G[3*i + j] += t; else G[3*i + j] -= t;
+            }
+        const double sr = dot3(nrm, ctr);
+        if (sign > 0) *V += sr; else *V -= sr;
+        return;
+    }
+    double centre[3] = {0, 0, 0}, cf[3] = {0, 0, 0};
+    for (int p = 0; p < n; p++)
+        for (int d = 0; d < 3; d++) { centre[d] += X[3*fp[p] + d]; cf[d] += pf[3*fp[p] + d]; }
+    for (int d = 0; d < 3; d++) { centre[d] /= n; cf[d] /= n; }
+    for (int p = 0; p < n; p++)
+    {
+        const int p0 = fp[p], p1 = fp[(p + 1) % n];
+        double ttcf[3], a[3], b[3], St[3], Ct[3];
+        for (int d = 0; d < 3; d++)
+        {
+            ttcf[d] = (pf[3*p0 + d] + pf[3*p1 + d] + cf[d])/3.0;
+            a[d] = X[3*p0 + d] - centre[d];
+            b[d] = X[3*p1 + d] - centre[d];
+        }
+        cross3(a, b, St);
+        for (int d = 0; d < 3; d++)
+        {
+            St[d] /= 2.0;
+            Ct[d] = (centre[d] + X[3*p0 + d] + X[3*p1 + d])/3;
+        }
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++)
+            {
+                const double t = St[i]*ttcf[j];
+                if (sign > 0) G[3*i + j] += t; else G[3*i + j] -= t;
+            }
+        const double sc = dot3(St, Ct);
+        if (sign > 0) *V += sc; else *V -= sc;
+    }
+}
+
+/* tangential face gradient from point values: sum_edges Le*fe / mag   (fvcGradf.C:97-142, 144-198, 410-482) */
+static void face_tangential_grad(const orc_mesh* M, int f, const double* pf, double* G)
+{
+    const int* fp = M->facePoints + M->faceStart[f];
+    const int n = M->faceStart[f + 1] - M->faceStart[f];
+    const double* X = M->points;
+    double nf[3];
+    for (int d = 0; d < 3; d++) nf[d] = M->Sf[3*f + d]/M->magSf[f];
+    for (int k = 0; k < 9; k++) G[k] = 0.0;
+    for (int p = 0; p < n; p++)
+    {
+        const int s = fp[p], e_ = fp[(p + 1) % n];
+        double e[3], Le[3], fe[3];
+        for (int d = 0; d < 3; d++) e[d] = X[3*e_ + d] - X[3*s + d];
+        const double ne = dot3(nf, e);
+        for (int d = 0; d < 3; d++) e[d] -= nf[d]*ne;
+        cross3(e, nf, Le);
+        for (int d = 0; d < 3; d++) fe[d] = 0.5*(pf[3*s + d] + pf[3*e_ + d]);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) G[3*i + j] += Le[i]*fe[j];
+    }
+    for (int k = 0; k < 9; k++) G[k] /= M->magSf[f];
+}
+
+/* boundary snGrad of D as the patch field classes give it:
+ *   fixedDisplacement::snGrad()  (fixedDisplacementFvPatchVectorField.C:96-127)
+ *   fixedGradient::snGrad() = gradient()  (tractionDisplacement: the gradient set by the last updateCoeffs)   */
+static void patch_snGrad(const orc_mesh* M, int ptype, int f, const double* D, const double* gradD,
+                         const double* fixedValue, const double* patchGradient, double* sn)
+{
+    const int bf = f - M->nInternalFaces, c = M->owner[f];
+    if (ptype == 1)
+    {
+        double n[3], delta[3], k[3], kg[3];
+        for (int d = 0; d < 3; d++) { n[d] = M->Sf[3*f + d]/M->magSf[f]; delta[d] = M->Cf[3*f + d] - M->C[3*c + d]; }
+        const double nd = dot3(n, delta);
+        for (int d = 0; d < 3; d++) k[d] = delta[d] - n[d]*nd;
+        vdotT(k, gradD + 9*c, kg);
+        for (int d = 0; d < 3; d++) sn[d] = (fixedValue[3*bf + d] - (D[3*c + d] + kg[d]))*M->deltaCoeffs[f];
+    }
+    else
+    {
+        for (int d = 0; d < 3; d++) sn[d] = patchGradient[3*bf + d];
+    }
+}
+
+/* fvc::grad(D, pointD)  (fvcGradf.C:485-717).  gradDold = the registered grad(D) at call time (used by
+ * fixedDisplacement::snGrad inside gaussGrad::correctBoundaryConditions); patchGradient = fixedGradient values.
+ * Outputs: gradD[nCells*9], gradDb[nBoundaryFaces*9] (boundary field of the gradient).                        */
+void orc_grad(const orc_mesh* M, const double* D, const double* pointD, const double* gradDold,
+              const double* fixedValue, const double* patchGradient, double* gradD, double* gradDb)
+{
+    const int nC = M->nCells, nIF = M->nInternalFaces, nF = M->nFaces;
+    double* V = (double*)calloc(nC, sizeof(double));
+    memset(gradD, 0, sizeof(double)*9*(size_t)nC);
+    for (int f = 0; f < nIF; f++)
+    {
+        /* the reference adds to the owner and subtracts from the neighbour triangle by triangle */
+        grad_face(M, f, pointD, +1.0, gradD + 9*M->owner[f], V + M->owner[f]);
+        grad_face(M, f, pointD, -1.0, gradD + 9*M->neighbour[f], V + M->neighbour[f]);
+    }
+    for (int f = nIF; f < nF; f++) grad_face(M, f, pointD, +1.0, gradD + 9*M->owner[f], V + M->owner[f]);
+    for (int c = 0; c < nC; c++)
+    {
+        V[c] /= 3;
+        for (int k = 0; k < 9; k++) gradD[9*c + k] /= V[c];
+    }
+    /* boundary: tangential gradient from the patch points, then gaussGrad::correctBoundaryConditions:
+       patchGrad += n*(snGrad - (n & patchGrad))                                                             */
+    for (int p = 0; p < M->nPatches; p++)
+    {
+        for (int i = 0; i < M->patchSize[p]; i++)
+        {
+            const int f = M->patchStart[p] + i, bf = f - nIF;
+            double* G = gradDb + 9*bf;
+            double n[3], sn[3], nG[3];
+            face_tangential_grad(M, f, pointD, G);
+            for (int d = 0; d < 3; d++) n[d] = M->Sf[3*f + d]/M->magSf[f];
+            patch_snGrad(M, M->patchType[p], f, D, gradDold, fixedValue, patchGradient, sn);
+            vdotT(n, G, nG);
+            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < 3; b++) G[3*a + b] += n[a]*(sn[b] - nG[b]);
+        }
+    }
+    free(V);
+}
+
+/* fvc::fGrad(D, pointD)  (fvcGradf.C:47-231): tangential part from the points + n*snGrad(D), snGrad = the
+ * skewCorrected scheme (orthogonal part + limited correction from the registered grad(D)) on internal faces
+ * and the patch field's snGrad() on boundary faces.                                                           */
+void orc_fgrad(const orc_mesh* M, const double* D, const double* pointD, const double* gradD,
+               const double* fixedValue, const double* patchGradient, double limitCoeff, double* gradDf)
+{
+    const int nIF = M->nInternalFaces;
+    for (int f = 0; f < M->nFaces; f++) face_tangential_grad(M, f, pointD, gradDf + 9*(size_t)f);
+    for (int f = 0; f < nIF; f++)
+    {
+        double ssf[3], sn[3], n[3];
+        skew_correction(M, f, D, gradD, limitCoeff, ssf);
+        const int P = M->owner[f], N = M->neighbour[f];
+        for (int d = 0; d < 3; d++)
+        {
+            sn[d] = M->deltaCoeffs[f]*(D[3*N + d] - D[3*P + d]) + ssf[d];
+            n[d] = M->Sf[3*f + d]/M->magSf[f];
+        }
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) gradDf[9*(size_t)f + 3*a + b] += n[a]*sn[b];
+    }
+    for (int p = 0; p < M->nPatches; p++)
+    {
+        for (int i = 0; i < M->patchSize[p]; i++)
+        {
+            const int f = M->patchStart[p] + i;
+            double sn[3], n[3];
+            patch_snGrad(M, M->patchType[p], f, D, gradD, fixedValue, patchGradient, sn);
+            for (int d = 0; d < 3; d++) n[d] = M->Sf[3*f + d]/M->magSf[f];
+            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < 3; b++) gradDf[9*(size_t)f + 3*a + b] += n[a]*sn[b];
+        }
     }
 }

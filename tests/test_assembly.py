@@ -124,3 +124,47 @@ def test_assembled_system_solves_through_gpupcg():
         assert pg["nIterations"] == pc["nIterations"] and pg["nIterations"] > 3
         assert np.max(np.abs(xg - xc)) <= 1e-9*np.max(np.abs(xc))
     solver.close(); gm.close()
+
+
+def linear_field(m, g):
+    A = np.array([[1e-3, 2e-4, -3e-4], [5e-4, -2e-3, 1e-4], [7e-4, 3e-4, 4e-3]])      # D_j = sum_i x_i A_ij
+    nIF = m.nInternalFaces
+    return A, g.C@A, m.points@A, g.Cf[nIF:]@A, (g.Sf[nIF:]/g.magSf[nIF:, None])@A
+
+
+def test_oracle_gradients_exact_for_linear_displacement():
+    """fvc::grad(D,pointD) and fvc::fGrad(D,pointD) (fvcGradf.C) reproduce a linear field's gradient: everywhere on the
+    orthogonal hex mesh; in the cells (any mesh) and on internal faces of the jittered tet mesh."""
+    m = meshes.hex_box(5, 4, 3)
+    g = geometry.compute(m)
+    A, D, pD, fixed, pgrad = linear_field(m, g)
+    G, Gb = oracle.grad(m, g, PATCHES, D, pD, np.tile(A.ravel(), (m.nCells, 1)), fixed, pgrad)
+    Gf = oracle.fgrad(m, g, PATCHES, D, pD, G, fixed, pgrad, 1.0)
+    for X in (G, Gb, Gf):
+        assert np.max(np.abs(X - A.ravel())) < 1e-15
+    m = meshes.tet_box(4, 3, 3, jitter=0.15)
+    g = geometry.compute(m)
+    A, D, pD, fixed, pgrad = linear_field(m, g)
+    G, Gb = oracle.grad(m, g, PATCHES, D, pD, np.tile(A.ravel(), (m.nCells, 1)), fixed, pgrad)
+    Gf = oracle.fgrad(m, g, PATCHES, D, pD, G, fixed, pgrad, 1.0)
+    assert np.max(np.abs(G - A.ravel())) < 1e-15
+    assert np.max(np.abs(Gf[:m.nInternalFaces] - A.ravel())) < 1e-14
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["hex", "tet"])
+def test_gpu_gradients_bit_exact(kind):
+    m = meshes.hex_box(12, 6, 8) if kind == "hex" else meshes.tet_box(6, 4, 5, jitter=0.15)
+    g = geometry.compute(m)
+    rng = np.random.default_rng(17)
+    nBF = m.nFaces - m.nInternalFaces
+    D = 1e-4*rng.standard_normal((m.nCells, 3)); pD = 1e-4*rng.standard_normal((m.nPoints, 3))
+    Gold = 1e-4*rng.standard_normal((m.nCells, 9)); fixed = 1e-4*rng.standard_normal((nBF, 3))
+    pgrad = 1e-4*rng.standard_normal((nBF, 3))
+    gm = pkg.GpuMesh(m, g, PATCHES)
+    for limitCoeff in (1.0, 0.5):
+        G, Gb, Gf, ms = gm.gradients(D, pD, Gold, fixed, pgrad, limitCoeff)
+        G2, Gb2 = oracle.grad(m, g, PATCHES, D, pD, Gold, fixed, pgrad)
+        Gf2 = oracle.fgrad(m, g, PATCHES, D, pD, G2, fixed, pgrad, limitCoeff)
+        assert np.array_equal(G, G2) and np.array_equal(Gb, Gb2) and np.array_equal(Gf, Gf2)
+    gm.close()
