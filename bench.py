@@ -184,6 +184,37 @@ def cpu_baseline(s, n, maxiter):
             "ms_per_iteration": 1e3*dt/max(1, perf["nIterations"])}
 
 
+def measure_assembly(nx, ny, nz, peak):
+    """GPU assembly of the D equation and the vertex-based gradients on the same mesh (one outer iteration's worth of
+    evolve() around DEqn.solve()): device time of the kernels on resident data, algorithmic bytes per SURVEY.md 8d."""
+    import fluidstructureinteraction_b200 as pkg
+    from fluidstructureinteraction_b200 import geometry, meshes
+    m = meshes.hex_box(nx, ny, nz)
+    geom = geometry.compute(m)
+    patches = {"fixed": "fixedDisplacement", "loaded": "tractionDisplacement", "free": "tractionDisplacement"}
+    gm = pkg.GpuMesh(m, geom, patches)
+    rng = np.random.default_rng(0)
+    nC, nF, nBF = m.nCells, m.nFaces, m.nFaces - m.nInternalFaces
+    mu, lam = cases.lame(cases.STEEL["E"], cases.STEEL["nu"])
+    D = 1e-5*rng.standard_normal((nC, 3)); pD = 1e-5*rng.standard_normal((m.nPoints, 3))
+    G = 1e-5*rng.standard_normal((nC, 9)); Gf = 1e-5*rng.standard_normal((nF, 9))
+    trac = np.zeros((nBF, 3)); pres = np.zeros(nBF); fixed = np.zeros((nBF, 3)); pgrad = np.zeros((nBF, 3))
+    a = gm.assemble_D(np.full(nC, mu), np.full(nC, lam), np.full(nC, cases.STEEL["rho"]), np.zeros(3), D, G, Gf, trac,
+                      pres, fixed, 1.0, reps=10)
+    _, _, _, gms = gm.gradients(D, pD, G, fixed, pgrad, 1.0, reps=10)
+    gm.close()
+    b_asm = (104 + 392 + 360)*nC          # laplacian + explicit flux/div + skew correction (SURVEY.md 8d, hex)
+    b_grad = (200 + 384)*nC               # cell gradient + face gradient
+    return {"assemble_D": {"ms": a["kernel_ms"], "algorithmic_bytes": b_asm, "achieved_gbs": b_asm/a["kernel_ms"]/1e6,
+                           "frac": b_asm/a["kernel_ms"]/1e6/peak,
+                           "kernels": "k_asm_faces + k_asm_cells + k_asm_patches"},
+            "gradients": {"ms": gms, "algorithmic_bytes": b_grad, "achieved_gbs": b_grad/gms/1e6, "frac": b_grad/gms/1e6/peak,
+                          "kernels": "k_grad_cells + k_grad_patches + k_fgrad_faces"}}
+
+
+from fluidstructureinteraction_b200 import cases  # noqa: E402
+
+
 def run_ours(args, nx, ny, nz):
     import torch
     import torch.distributed as dist
@@ -341,6 +372,8 @@ def run_ours(args, nx, ny, nz):
             "roofline": roof(dom_k), "roofline_amul": roof("amul"), "kernels": kern,
             "plan": {k: info[k] for k in ("nRows", "nLevels", "maxLevelRows", "sweepGrid", "streamGrid")},
         }
+        if world == 1 and nGlobal <= 4000000:
+            line["assembly"] = measure_assembly(nx, ny, nz, peak)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(s, nGlobal, args.cpu_maxiter)
         elif world == 1:

@@ -44,6 +44,7 @@ struct gpupcg_handle_s
     unsigned long long* dTileTicket = nullptr;
     unsigned long long* dTileTrace = nullptr;
     size_t smemFwd = 0, smemBwd = 0, smemAmul = 0;
+    bool hasOvf = false;            // some row has more than four faces on one side (polyhedral cells)
     int partStride = MAXPART;
     TileArgs tiles;
 
@@ -228,9 +229,13 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
         int ns = env_int("GPUPCG_SPIN_NS", 0);
         CK(cudaMemcpyToSymbol(g_spinNs, &ns, sizeof(int)));
     }
-    CK(cudaFuncSetAttribute(k_dic_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwd));
-    CK(cudaFuncSetAttribute(k_dic_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwd));
-    CK(cudaFuncSetAttribute(k_dic_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBwd));
+    CK(cudaFuncSetAttribute(k_dic_tile<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwd));
+    CK(cudaFuncSetAttribute(k_dic_tile<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwd));
+    CK(cudaFuncSetAttribute(k_dic_tile<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBwd));
+    CK(cudaFuncSetAttribute(k_dic_tile<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwd));
+    CK(cudaFuncSetAttribute(k_dic_tile<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwd));
+    CK(cudaFuncSetAttribute(k_dic_tile<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBwd));
+    h->hasOvf = (P.maxRowL > 4 || P.maxRowU > 4);
     CK(cudaFuncSetAttribute(k_amul_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemAmul));
     CK(cudaFuncSetAttribute(k_amul_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemAmul));
     CK(cudaFuncSetAttribute(k_amul_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemAmul));
@@ -544,8 +549,12 @@ static int enqueue_factor(gpupcg_handle h, int gated)
 {
     if (h->plan.nTiles == 0) return GPUPCG_OK;
     fill_sent(h, h->dY);
-    LAUNCH_SWEEP(k_dic_tile<1>, h->smemFwd, h->tiles, h->dDiag, h->dUval, nullptr, nullptr,
-                 (unsigned long long*)h->dY, h->dRD, h->dTileTicket, nullptr, 0, h->dState, gated);
+    if (h->hasOvf)
+        LAUNCH_SWEEP((k_dic_tile<1, true>), h->smemFwd, h->tiles, h->dDiag, h->dUval, nullptr, nullptr,
+                     (unsigned long long*)h->dY, h->dRD, h->dTileTicket, nullptr, 0, h->dState, gated);
+    else
+        LAUNCH_SWEEP((k_dic_tile<1, false>), h->smemFwd, h->tiles, h->dDiag, h->dUval, nullptr, nullptr,
+                     (unsigned long long*)h->dY, h->dRD, h->dTileTicket, nullptr, 0, h->dState, gated);
     fill_sent(h, h->dY);
     CK(cudaGetLastError());
     return GPUPCG_OK;
@@ -555,11 +564,23 @@ static int enqueue_factor(gpupcg_handle h, int gated)
 static int enqueue_sweeps(gpupcg_handle h, const double* rA, double* z, bool reduce, int gated)
 {
     if (h->plan.nTiles == 0) return GPUPCG_OK;
-    LAUNCH_SWEEP(k_dic_tile<0>, h->smemFwd, h->tiles, h->dRD, h->dUval, rA, nullptr,
-                 (unsigned long long*)h->dY, nullptr, h->dTileTicket, nullptr, 0, h->dState, gated);
-    LAUNCH_SWEEP(k_dic_tile<2>, h->smemBwd, h->tiles, h->dRD, h->dUval, rA, (unsigned long long*)h->dY,
-                 (unsigned long long*)z, nullptr, h->dTileTicket, reduce ? h->dPartials : nullptr, h->partStride,
-                 h->dState, gated);
+    unsigned long long* yb = (unsigned long long*)h->dY;
+    unsigned long long* zb = (unsigned long long*)z;
+    double* part = reduce ? h->dPartials : nullptr;
+    if (h->hasOvf)
+    {
+        LAUNCH_SWEEP((k_dic_tile<0, true>), h->smemFwd, h->tiles, h->dRD, h->dUval, rA, nullptr, yb, nullptr,
+                     h->dTileTicket, nullptr, 0, h->dState, gated);
+        LAUNCH_SWEEP((k_dic_tile<2, true>), h->smemBwd, h->tiles, h->dRD, h->dUval, rA, yb, zb, nullptr,
+                     h->dTileTicket, part, h->partStride, h->dState, gated);
+    }
+    else
+    {
+        LAUNCH_SWEEP((k_dic_tile<0, false>), h->smemFwd, h->tiles, h->dRD, h->dUval, rA, nullptr, yb, nullptr,
+                     h->dTileTicket, nullptr, 0, h->dState, gated);
+        LAUNCH_SWEEP((k_dic_tile<2, false>), h->smemBwd, h->tiles, h->dRD, h->dUval, rA, yb, zb, nullptr,
+                     h->dTileTicket, part, h->partStride, h->dState, gated);
+    }
     CK(cudaGetLastError());
     return GPUPCG_OK;
 }

@@ -542,10 +542,10 @@ __host__ __device__ inline SweepLayout sweep_layout(int T, int X, int I, int E, 
     L.one = T + X;
     L.vals = 0;
     L.rowF = 8u*L.NV;
-    L.rowC = L.rowF + 32u*T;
-    L.items = L.rowC + 16u*T;
+    L.rowC = L.rowF + 32u*(T + 1);                  // +1: the dummy row idle lanes work on (coefficients 0)
+    L.items = L.rowC + 16u*(T + 1);
     L.ovf = L.items + 8u*(I + 2);
-    L.slot = L.ovf + T;
+    L.slot = L.ovf + ((T + 1 + 15) & ~15u);
     L.Ub = (L.slot + 16 + 15) & ~15u;
     L.dv = L.Ub + 8u*E;
     L.av = L.dv + 8u*T;
@@ -622,32 +622,32 @@ __device__ __forceinline__ bool is_sent(double v)
 }
 
 // Static data of one row, fetched into registers one work item ahead of its use so that the only loads left on
-// the round-to-round dependency chain are the four value loads.
+// the round-to-round dependency chain are the four value loads.  rowC holds BYTE offsets into the value array.
+// Lanes without a row in a pass work on the dummy row T (zero coefficients, constant-slot dependencies) and store
+// into the scratch slot one+1: no predication in the loop except the global publish.
 struct RowRegs
 {
-    int q;              // tile-local row, -1 = this lane idles in this pass
-    int4 c;             // value indices of the first four entries
+    unsigned q8;        // byte offset of the row's value slot (scratch slot for idle lanes)
+    int qg;             // tile-local row for the global publish, -1 = idle lane
+    int4 c;             // byte offsets of the four dependency values
     double f0, f1, f2, f3;
     double acc0;
     int ovf;
 };
 
+template <bool HAS_OVF>
 __device__ __forceinline__ RowRegs load_row(unsigned sb, const SweepLayout& L, int2 item, int lane)
 {
     RowRegs R;
     const bool active = lane < (item.y & 0xffff);
-    const int q = active ? item.x + lane : 0;
-    R.q = active ? q : -1;
+    const int q = active ? item.x + lane : L.T;
+    R.qg = active ? q : -1;
+    R.q8 = active ? 8u*q : 8u*(L.one + 1);
     R.c = lds_v4(sb + L.rowC + 16u*q);
     const double2 fa = lds_d2(sb + L.rowF + 32u*q);
     const double2 fb = lds_d2(sb + L.rowF + 32u*q + 16u);
-    R.acc0 = lds_f64_weak(sb + L.vals + 8u*q);
-    R.ovf = lds_u8(sb + L.ovf + q);
-    if (!active)        // idle lanes must not wait on anything: point them at the constant slot
-    {
-        R.c = make_int4(L.one, L.one, L.one, L.one);
-        R.ovf = 0;
-    }
+    R.acc0 = lds_f64_weak(sb + L.vals + R.q8);
+    R.ovf = HAS_OVF ? lds_u8(sb + L.ovf + q) : 0;
     R.f0 = fa.x; R.f1 = fa.y; R.f2 = fb.x; R.f3 = fb.y;
     return R;
 }
@@ -656,11 +656,11 @@ __device__ __forceinline__ RowRegs load_row(unsigned sb, const SweepLayout& L, i
 // Rows of the tile are final by construction of the rounds; cross-tile slots may still hold SENT.
 __device__ __forceinline__ void dep_values4(unsigned vb, const int4 c, double& v0, double& v1, double& v2, double& v3)
 {
-    v0 = lds_f64_weak(vb + 8u*c.x); v1 = lds_f64_weak(vb + 8u*c.y);
-    v2 = lds_f64_weak(vb + 8u*c.z); v3 = lds_f64_weak(vb + 8u*c.w);
+    v0 = lds_f64_weak(vb + c.x); v1 = lds_f64_weak(vb + c.y);
+    v2 = lds_f64_weak(vb + c.z); v3 = lds_f64_weak(vb + c.w);
     while (is_sent(v0) | is_sent(v1) | is_sent(v2) | is_sent(v3))
     {
-        v0 = lds_f64(vb + 8u*c.x); v1 = lds_f64(vb + 8u*c.y); v2 = lds_f64(vb + 8u*c.z); v3 = lds_f64(vb + 8u*c.w);
+        v0 = lds_f64(vb + c.x); v1 = lds_f64(vb + c.y); v2 = lds_f64(vb + c.z); v3 = lds_f64(vb + c.w);
     }
 }
 
@@ -687,7 +687,14 @@ __device__ __forceinline__ double dep_value(unsigned vb, int idx)
 // global dependency level present in the tile, cut into passes of 32 rows) with __syncwarp between rounds, while
 // warps 1-3 poll the cross-tile inputs from global memory, in consumption order, into the value array.
 // ------------------------------------------------------------------------------------------
-template <int MODE>
+// a NaN that reaches the value array must not look like SENT: inputs are canonicalised once at staging (arithmetic
+// on canonical NaNs yields canonical NaNs), so the loop publishes values as they are
+__device__ __forceinline__ double canon(double v)
+{
+    return (v != v) ? __longlong_as_double((long long)QNAN) : v;
+}
+
+template <int MODE, bool HAS_OVF>
 __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double* __restrict__ diagOrRD,
                                                         const double* __restrict__ Uval,
                                                         const double* __restrict__ rA, unsigned long long* y,
@@ -765,8 +772,8 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
         const int wid = BWD ? si.widthU : si.widthL;
         const int off = (BWD ? si.offU - eU0 : si.offL - eL0) + (q & 31);
         const double d = dv[q];
-        if (BWD) { vals[q] = av[q]; y[r0 + q] = SENT; }
-        else vals[q] = FACTOR ? d : __dmul_rn(d, av[q]);
+        if (BWD) { vals[q] = canon(av[q]); y[r0 + q] = SENT; }
+        else vals[q] = canon(FACTOR ? d : __dmul_rn(d, av[q]));
         int nOver = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++)
@@ -780,14 +787,20 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
                 if (code != 0xFFFFu)
                 {
                     const double c = BWD ? Ub[e] : ((code & 0x8000u) ? cX[code & 0x7FFFu] : Ub[idxS[e]]);
-                    cf = FACTOR ? __dmul_rn(c, c) : __dmul_rn(d, c);
+                    cf = canon(FACTOR ? __dmul_rn(c, c) : __dmul_rn(d, c));
                 }
             }
-            rowC[4*q + j] = value_index16(code, T, L.one);
+            rowC[4*q + j] = 8*value_index16(code, T, L.one);
             rowF[4*q + j] = cf;
         }
         for (int j = 4; j < wid; j++) nOver += (colS[off + j*32] != 0xFFFFu);
         ovf[q] = (unsigned char)nOver;
+    }
+    if (threadIdx.x < 4)        // the dummy row of idle lanes
+    {
+        rowC[4*T + threadIdx.x] = 8*L.one;
+        rowF[4*T + threadIdx.x] = 0.0;
+        if (threadIdx.x == 0) { ovf[T] = 0; vals[L.one + 1] = 0.0; }
     }
     __syncthreads();
     if (g_tileTimes && threadIdx.x == 0 && MODE == 0) { g_tileTimes[3*tile] = tBegin; g_tileTimes[3*tile + 1] = gtime(); }
@@ -800,21 +813,21 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
         const unsigned ib = sb + L.items;
         const int syncBit = BWD ? (1 << 16) : (1 << 17);       // end of a round in sweep order
         int2 d0 = lds_i2(ib), d1 = lds_i2(ib + 8u);
-        RowRegs cur = load_row(sb, L, d0, lane);
+        RowRegs cur = load_row<HAS_OVF>(sb, L, d0, lane);
         for (int i = 0; i < nItems; i++)
         {
             const int2 d2 = lds_i2(ib + 8u*(i + 2));
-            const RowRegs nxt = load_row(sb, L, d1, lane);
+            const RowRegs nxt = load_row<HAS_OVF>(sb, L, d1, lane);
             double v0, v1, v2, v3;
             dep_values4(vb, cur.c, v0, v1, v2, v3);
             double acc = cur.acc0;
             if (BWD)
             {
-                if (cur.ovf)        // more than four owner-side faces: the tail (descending) comes first
+                if (HAS_OVF && cur.ovf)        // more than four owner-side faces: the tail (descending) comes first
                 {
-                    const SliceInfo si = sl[cur.q >> 5];
-                    const int off = si.offU - eU0 + (cur.q & 31);
-                    const double d = dv[cur.q];
+                    const SliceInfo si = sl[cur.qg >> 5];
+                    const int off = si.offU - eU0 + (cur.qg & 31);
+                    const double d = dv[cur.qg];
                     for (int j = si.widthU - 1; j >= 4; j--)
                     {
                         const unsigned code = colS[off + j*32];
@@ -832,10 +845,10 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
                 if (FACTOR)
                 {
                     // unused slots (coefficient 0, value 1) are exact no-ops: skip their ~250-cycle IEEE divisions
-                    t0 = (cur.c.x != L.one) ? __ddiv_rn(cur.f0, v0) : 0.0;
-                    t1 = (cur.c.y != L.one) ? __ddiv_rn(cur.f1, v1) : 0.0;
-                    t2 = (cur.c.z != L.one) ? __ddiv_rn(cur.f2, v2) : 0.0;
-                    t3 = (cur.c.w != L.one) ? __ddiv_rn(cur.f3, v3) : 0.0;
+                    t0 = (cur.c.x != 8*L.one) ? __ddiv_rn(cur.f0, v0) : 0.0;
+                    t1 = (cur.c.y != 8*L.one) ? __ddiv_rn(cur.f1, v1) : 0.0;
+                    t2 = (cur.c.z != 8*L.one) ? __ddiv_rn(cur.f2, v2) : 0.0;
+                    t3 = (cur.c.w != 8*L.one) ? __ddiv_rn(cur.f3, v3) : 0.0;
                 }
                 else
                 {
@@ -843,11 +856,11 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
                     t2 = __dmul_rn(cur.f2, v2); t3 = __dmul_rn(cur.f3, v3);
                 }
                 acc = __dsub_rn(__dsub_rn(__dsub_rn(__dsub_rn(acc, t0), t1), t2), t3);
-                if (cur.ovf)        // more than four neighbour-side faces: tail from the staged SELL block
+                if (HAS_OVF && cur.ovf)        // more than four neighbour-side faces: tail from the staged SELL block
                 {
-                    const SliceInfo si = sl[cur.q >> 5];
-                    const int off = si.offL - eL0 + (cur.q & 31);
-                    const double d = dv[cur.q];
+                    const SliceInfo si = sl[cur.qg >> 5];
+                    const int off = si.offL - eL0 + (cur.qg & 31);
+                    const double d = dv[cur.qg];
                     for (int j = 4; j < si.widthL; j++)
                     {
                         const unsigned code = colS[off + j*32];
@@ -859,11 +872,9 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
                     }
                 }
             }
-            if (cur.q >= 0)
-            {
-                sts_f64(vb + 8u*cur.q, acc);
-                publish(out + r0 + cur.q, acc);
-            }
+            sts_f64(vb + cur.q8, acc);
+            if (cur.qg >= 0)
+                asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" :: "l"(out + r0 + cur.qg), "d"(acc) : "memory");
             if (d0.y & syncBit) __syncwarp();
             cur = nxt; d0 = d1; d1 = d2;
         }

@@ -306,6 +306,7 @@ int build_plan(int nCells, int nFaces, const int* l, const int* u,
         }
         a++; b++;
     }
+    for (int r = 0; r < P.nRows; r++) { P.maxRowU = std::max<int>(P.maxRowU, nU[r]); P.maxRowL = std::max<int>(P.maxRowL, nL[r]); }
     P.slices.resize(P.nSlices);
     long long totU = 0, totL = 0;
     for (int s = 0; s < P.nSlices; s++)

@@ -59,6 +59,7 @@ struct HostPlan
     int maxRounds = 0;
     int maxTileEntriesL = 0, maxTileEntriesU = 0;       // SELL entries (incl. padding) of the largest tile
     int maxTileExtF = 0, maxTileExtB = 0;
+    int maxRowL = 0, maxRowU = 0;                       // most faces of one row on the neighbour / owner side
     std::vector<int> tileStart;         // [nTiles+1] first row of each tile (multiple of 32)
     std::vector<int> tileRoundPtr;      // [nTiles+1] into roundStart (tile t owns K_t+1 entries)
     std::vector<int> roundStart;        // tile-relative first row of each round, last = tile rows

@@ -202,3 +202,29 @@ def test_two_gpu_parity_against_oracle_on_same_partition():
                         "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "multigpu_parity.py")],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0 and "MULTIGPU-PARITY-OK" in r.stdout, r.stdout[-3000:]
+
+
+def random_ldu(n, extra, seed):
+    """A connected random graph in upper-triangular face order with some rows of high degree on both sides
+    (exercises the > 4 faces-per-side tail of the tile kernels and non-mesh-like schedules)."""
+    rng = np.random.default_rng(seed)
+    pairs = {(i, i + 1) for i in range(n - 1)}
+    a = rng.integers(0, n, size=extra); b = rng.integers(0, n, size=extra)
+    for i, j in zip(a, b):
+        if i != j:
+            pairs.add((min(i, j), max(i, j)))
+    hub = n//2
+    for j in rng.integers(0, n, size=12):           # one hub row with many faces on both sides
+        if j != hub:
+            pairs.add((min(hub, j), max(hub, j)))
+    arr = np.array(sorted(pairs), dtype=np.int32)
+    return arr[:, 0].copy(), arr[:, 1].copy()
+
+
+@pytest.mark.parametrize("n,extra", [(300, 900), (5000, 12000)])
+def test_random_graph_with_high_degree_rows(n, extra):
+    l, u = random_ldu(n, extra, 4)
+    diag, upper, b, x0 = synthetic_matrix(l, u, n, 31)
+    g = check_kernels(l, u, n, diag, upper, b)
+    check_solve(g, l, u, diag, upper, b, x0, 1e-9, 0.0)
+    g.close()
