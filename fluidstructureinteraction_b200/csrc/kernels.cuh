@@ -392,7 +392,7 @@ __device__ __forceinline__ int take_tile(unsigned long long* tileTicket, int nTi
 // Per-row operand order = reference face order: diag*x, neighbour-side faces ascending, owner-side ascending.
 // ifMask (may be null): rows that own coupled faces are left out of the MODE-1 dot here (k_iface_update adds them).
 // ------------------------------------------------------------------------------------------
-static constexpr int AMUL_TPB = 256;
+static constexpr int AMUL_TPB = 128;
 
 struct AmulLayout
 {
@@ -887,6 +887,9 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
         // held back until the latest of its 32 warp-mates had arrived: 1.7 us per tile hop instead of ~1.)
         int i = threadIdx.x - 32;
         const unsigned long long* p = (i < nExt) ? out + extCol[xBase + i] : nullptr;
+        // the address of the lane's NEXT entry is fetched while it waits for the current one: advancing must not put
+        // a global-load latency into the poll loop of the whole warp
+        int colNext = (i + FETCHERS < nExt) ? extCol[xBase + i + FETCHERS] : 0;
         const int ns = g_spinNs;
         while (i < nExt)
         {
@@ -895,7 +898,8 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
             {
                 sts_u64(vb + 8u*(T + i), v);
                 i += FETCHERS;
-                if (i < nExt) p = out + extCol[xBase + i];
+                p = out + colNext;
+                if (i + FETCHERS < nExt) colNext = extCol[xBase + i + FETCHERS];
             }
             else if (ns > 0) __nanosleep(ns);
         }
