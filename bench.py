@@ -35,6 +35,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's version banner / debug output goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 TOL, RELTOL = 1e-9, 0.01
 TRACTION = (0.5e4, 0.25e4, -1.0e4)          # all three components get a non-zero source
