@@ -44,6 +44,7 @@ struct gpupcg_handle_s
     unsigned long long* dTileTicket = nullptr;
     unsigned long long* dTileTrace = nullptr;
     size_t smemFwd = 0, smemBwd = 0, smemAmul = 0;
+    int amulGrid = 1;               // persistent CTAs of the Amul kernel
     bool hasOvf = false;            // some row has more than four faces on one side (polyhedral cells)
     int partStride = MAXPART;
     TileArgs tiles;
@@ -209,7 +210,7 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
         const HostPlan& Q = h->plan;
         h->smemFwd = sweep_layout(Q.tileRowsMax, Q.maxTileExtF, Q.maxItems, std::max(Q.maxTileEntriesU, Q.maxTileEntriesL), Q.maxTileEntriesL).bytes;
         h->smemBwd = sweep_layout(Q.tileRowsMax, Q.maxTileExtB, Q.maxItems, Q.maxTileEntriesU, Q.maxTileEntriesL).bytes;
-        h->smemAmul = amul_layout(Q.tileRowsMax, Q.maxTileEntriesU, Q.maxTileEntriesL, Q.maxTileExtF, Q.maxTileExtB).bytes;
+        h->smemAmul = 2*(size_t)((amul_layout(Q.tileRowsMax, Q.maxTileEntriesU, Q.maxTileEntriesL, Q.maxTileExtF, Q.maxTileExtB).bytes + 127u) & ~127u);
         const size_t need = std::max(h->smemAmul, std::max(h->smemFwd, h->smemBwd));
         if (rc == GPUPCG_OK && need <= smemCap) break;
         if (tileRows <= 32) break;
@@ -236,6 +237,12 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     CK(cudaFuncSetAttribute(k_dic_tile<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwd));
     CK(cudaFuncSetAttribute(k_dic_tile<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBwd));
     h->hasOvf = (P.maxRowL > 4 || P.maxRowU > 4);
+    {
+        int occ = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_amul_tile<1>, AMUL_TPB, h->smemAmul));
+        occ = std::max(1, std::min(occ, env_int("GPUPCG_AMUL_BPS", 16)));
+        h->amulGrid = std::max(1, std::min(P.nTiles, std::min(h->numSMs*occ, h->partStride)));
+    }
     CK(cudaFuncSetAttribute(k_amul_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemAmul));
     CK(cudaFuncSetAttribute(k_amul_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemAmul));
     CK(cudaFuncSetAttribute(k_amul_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemAmul));
@@ -524,11 +531,11 @@ static int enqueue_amul(gpupcg_handle h, int mode, const double* x, double* Ax, 
     {
         h->launches++;
         if (mode == 0)
-            k_amul_tile<0><<<P.nTiles, AMUL_TPB, h->smemAmul, s>>>(h->tiles, h->dDiag, h->dUval, h->dRowOld, mask, x, Ax, h->dPartials, h->partStride, h->dState);
+            k_amul_tile<0><<<h->amulGrid, AMUL_TPB, h->smemAmul, s>>>(h->tiles, h->dDiag, h->dUval, h->dRowOld, mask, x, Ax, h->dPartials, h->partStride, h->dState);
         else if (mode == 1)
-            k_amul_tile<1><<<P.nTiles, AMUL_TPB, h->smemAmul, s>>>(h->tiles, h->dDiag, h->dUval, h->dRowOld, mask, x, Ax, h->dPartials, h->partStride, h->dState);
+            k_amul_tile<1><<<h->amulGrid, AMUL_TPB, h->smemAmul, s>>>(h->tiles, h->dDiag, h->dUval, h->dRowOld, mask, x, Ax, h->dPartials, h->partStride, h->dState);
         else
-            k_amul_tile<2><<<P.nTiles, AMUL_TPB, h->smemAmul, s>>>(h->tiles, h->dDiag, h->dUval, h->dRowOld, mask, x, Ax, h->dPartials, h->partStride, h->dState);
+            k_amul_tile<2><<<h->amulGrid, AMUL_TPB, h->smemAmul, s>>>(h->tiles, h->dDiag, h->dUval, h->dRowOld, mask, x, Ax, h->dPartials, h->partStride, h->dState);
     }
     if (ifaces)
     {

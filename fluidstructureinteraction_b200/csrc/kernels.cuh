@@ -418,6 +418,19 @@ __host__ __device__ inline AmulLayout amul_layout(int T, int EU, int EL, int XF,
     return L;
 }
 
+// Persistent, double-buffered: a CTA walks tiles blockIdx.x, +gridDim.x, ...; while tile k is computed out of
+// buffer k&1 the bulk copies of tile k+1 are in flight into the other buffer, and its cross-tile gathers travel
+// through registers in a three-deep software pipeline (indices of tile k+2, values of tile k+1), so no global-load
+// latency is exposed between tiles.  Rows beyond EXT_R*AMUL_TPB cross-tile entries per list fall back to blocking
+// loads (never the case for the brick tiles of the structured cases).
+static constexpr int EXT_R = 2;
+
+struct ExtRegs
+{
+    int iF[EXT_R], cF[EXT_R], iB[EXT_R];        // indices (global row / U entry), -1 = none
+    double xF[EXT_R], vF[EXT_R], xB[EXT_R];     // gathered values
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(AMUL_TPB) k_amul_tile(TileArgs A, const double* __restrict__ diag,
                                                         const double* __restrict__ Uval, const int* __restrict__ rowOld,
@@ -428,19 +441,20 @@ __global__ void __launch_bounds__(AMUL_TPB) k_amul_tile(TileArgs A, const double
     if (MODE == 1 && st->done) return;
     extern __shared__ __align__(128) unsigned char smemRaw[];
     const AmulLayout L = amul_layout(A.tileRowsMax, A.maxEU, A.maxEL, A.maxExtF, A.maxExtB);
-    const unsigned sb = (unsigned)__cvta_generic_to_shared(smemRaw);
-    const int tile = blockIdx.x;
-    const int r0 = A.tileStart[tile], nr = A.tileStart[tile + 1] - r0;
-    const int s0 = r0 >> 5, nsl = nr >> 5;
-    const SliceInfo first = A.slices[s0], last = A.slices[s0 + nsl - 1];
-    const int eU0 = first.offU, nEU = last.offU + 32*last.widthU - eU0;
-    const int eL0 = first.offL, nEL = last.offL + 32*last.widthL - eL0;
-    const int fBase = A.extFPtr[tile], nXF = A.extFPtr[tile + 1] - fBase;
-    const int bBase = A.extBPtr[tile], nXB = A.extBPtr[tile + 1] - bBase;
+    const unsigned sb0 = (unsigned)__cvta_generic_to_shared(smemRaw);
+    const unsigned stageBytes = (L.bytes + 127u) & ~127u;
+    const double xc = (MODE == 2) ? st->xRef : 0.0;
+    const int tid = threadIdx.x;
 
-    if (threadIdx.x == 0)
+    // ---- helpers over a tile / a stage buffer
+    auto issue_bulk = [&](int tile, int stage)
     {
-        mbar_init(sb + L.bar, 1);
+        const unsigned sb = sb0 + stage*stageBytes;
+        const int r0 = A.tileStart[tile], nr = A.tileStart[tile + 1] - r0;
+        const int s0 = r0 >> 5, nsl = nr >> 5;
+        const SliceInfo first = A.slices[s0], last = A.slices[s0 + nsl - 1];
+        const int eU0 = first.offU, nEU = last.offU + 32*last.widthU - eU0;
+        const int eL0 = first.offL, nEL = last.offL + 32*last.widthL - eL0;
         const unsigned bytes = 8u*nEU + 2u*nEU + 4u*nEL + 8u*nr + (MODE == 2 ? 0u : 8u*nr) + 16u*nsl;
         mbar_expect_tx(sb + L.bar, bytes);
         bulk_g2s(sb + L.Ub, Uval + eU0, 8u*nEU, sb + L.bar);
@@ -450,68 +464,148 @@ __global__ void __launch_bounds__(AMUL_TPB) k_amul_tile(TileArgs A, const double
         bulk_g2s(sb + L.diag, diag + r0, 8u*nr, sb + L.bar);
         if (MODE != 2) bulk_g2s(sb + L.xs, x + r0, 8u*nr, sb + L.bar);
         bulk_g2s(sb + L.sl, A.slices + s0, 16u*nsl, sb + L.bar);
-    }
-    // meanwhile: cross-tile values (gathers, mostly L2 hits)
-    double* xF = (double*)(smemRaw + L.xF);
-    double* cF = (double*)(smemRaw + L.cF);
-    double* xB = (double*)(smemRaw + L.xB);
-    const double xc = (MODE == 2) ? st->xRef : 0.0;
-    for (int k = threadIdx.x; k < nXF; k += AMUL_TPB)
+    };
+    auto load_indices = [&](int tile, ExtRegs& E)
     {
-        xF[k] = (MODE == 2) ? xc : x[A.extFCol[fBase + k]];
-        cF[k] = Uval[A.extFIdx[fBase + k]];
-    }
-    for (int k = threadIdx.x; k < nXB; k += AMUL_TPB) xB[k] = (MODE == 2) ? xc : x[A.extBCol[bBase + k]];
-    double* xs = (double*)(smemRaw + L.xs);
-    if (MODE == 2)
+        const int fBase = A.extFPtr[tile], nXF = A.extFPtr[tile + 1] - fBase;
+        const int bBase = A.extBPtr[tile], nXB = A.extBPtr[tile + 1] - bBase;
+#pragma unroll
+        for (int k = 0; k < EXT_R; k++)
+        {
+            const int e = tid + k*AMUL_TPB;
+            E.iF[k] = (e < nXF) ? A.extFCol[fBase + e] : -1;
+            E.cF[k] = (e < nXF) ? A.extFIdx[fBase + e] : -1;
+            E.iB[k] = (e < nXB) ? A.extBCol[bBase + e] : -1;
+        }
+    };
+    auto load_values = [&](ExtRegs& E)
     {
-        for (int q = threadIdx.x; q < nr; q += AMUL_TPB) xs[q] = (rowOld[r0 + q] >= 0) ? xc : 0.0;
-    }
-    __syncthreads();                    // mbarrier init + gathers visible
-    mbar_wait(sb + L.bar, 0);
+#pragma unroll
+        for (int k = 0; k < EXT_R; k++)
+        {
+            E.xF[k] = (E.iF[k] >= 0) ? ((MODE == 2) ? xc : x[E.iF[k]]) : 0.0;
+            E.vF[k] = (E.cF[k] >= 0) ? Uval[E.cF[k]] : 0.0;
+            E.xB[k] = (E.iB[k] >= 0) ? ((MODE == 2) ? xc : x[E.iB[k]]) : 0.0;
+        }
+    };
+    auto store_values = [&](int tile, int stage, const ExtRegs& E)
+    {
+        unsigned char* base = smemRaw + stage*stageBytes;
+        double* xF = (double*)(base + L.xF);
+        double* cF = (double*)(base + L.cF);
+        double* xB = (double*)(base + L.xB);
+        const int fBase = A.extFPtr[tile], nXF = A.extFPtr[tile + 1] - fBase;
+        const int bBase = A.extBPtr[tile], nXB = A.extBPtr[tile + 1] - bBase;
+#pragma unroll
+        for (int k = 0; k < EXT_R; k++)
+        {
+            const int e = tid + k*AMUL_TPB;
+            if (e < nXF) { xF[e] = E.xF[k]; cF[e] = E.vF[k]; }
+            if (e < nXB) xB[e] = E.xB[k];
+        }
+        // more cross-tile entries than the register pipeline carries: blocking loads
+        for (int e = tid + EXT_R*AMUL_TPB; e < nXF; e += AMUL_TPB)
+        {
+            xF[e] = (MODE == 2) ? xc : x[A.extFCol[fBase + e]];
+            cF[e] = Uval[A.extFIdx[fBase + e]];
+        }
+        for (int e = tid + EXT_R*AMUL_TPB; e < nXB; e += AMUL_TPB) xB[e] = (MODE == 2) ? xc : x[A.extBCol[bBase + e]];
+        if (MODE == 2)
+        {
+            double* xs = (double*)(base + L.xs);
+            const int r0 = A.tileStart[tile], nr = A.tileStart[tile + 1] - r0;
+            for (int q = tid; q < nr; q += AMUL_TPB) xs[q] = (rowOld[r0 + q] >= 0) ? xc : 0.0;
+        }
+    };
 
-    const double* Ub = (const double*)(smemRaw + L.Ub);
-    const double* dg = (const double*)(smemRaw + L.diag);
-    const unsigned short* colU = (const unsigned short*)(smemRaw + L.colU);
-    const unsigned short* colL = (const unsigned short*)(smemRaw + L.colL);
-    const unsigned short* idxL = (const unsigned short*)(smemRaw + L.idxL);
-    const SliceInfo* sl = (const SliceInfo*)(smemRaw + L.sl);
-    double dot[1] = {0.0};
-    for (int q = threadIdx.x; q < nr; q += AMUL_TPB)
+    const int t0 = blockIdx.x, G = gridDim.x;
+    if (tid == 0)
     {
-        const SliceInfo si = sl[q >> 5];
-        const int ln = q & 31;
-        const double xr = xs[q];
-        double acc = __dmul_rn(dg[q], xr);
-        // neighbour-side faces (u == row), ascending f
-        for (int j = 0; j < si.widthL; j++)
+        mbar_init(sb0 + L.bar, 1);
+        mbar_init(sb0 + stageBytes + L.bar, 1);
+    }
+    __syncthreads();
+    ExtRegs Ecur, Enext;
+    if (t0 < A.nTiles)
+    {
+        if (tid == 0) issue_bulk(t0, 0);
+        load_indices(t0, Ecur);
+        load_values(Ecur);
+        store_values(t0, 0, Ecur);
+        if (t0 + G < A.nTiles) load_indices(t0 + G, Ecur);      // Ecur now carries the indices of the NEXT tile
+    }
+    double dot[1] = {0.0};
+    unsigned phase[2] = {0u, 0u};
+    int stage = 0;
+    for (int tile = t0; tile < A.nTiles; tile += G, stage ^= 1)
+    {
+        const int nextTile = tile + G;
+        const bool haveNext = nextTile < A.nTiles;
+        __syncthreads();                    // everyone is done reading buffer stage^1 (tile - G), and sees stage's gathers
+        if (haveNext)
         {
-            const int e = si.offL - eL0 + j*32 + ln;
-            const unsigned c = colL[e];
-            if (c == 0xFFFFu) break;
-            double cf, xv;
-            if (c & 0x8000u) { cf = cF[c & 0x7FFFu]; xv = xF[c & 0x7FFFu]; }
-            else { cf = Ub[idxL[e]]; xv = xs[c]; }
-            acc = __dadd_rn(acc, __dmul_rn(cf, xv));
+            if (tid == 0) issue_bulk(nextTile, stage ^ 1);
+            load_values(Ecur);                                   // values of tile+G (indices loaded one iteration ago)
+            if (nextTile + G < A.nTiles) load_indices(nextTile + G, Enext);
         }
-        // owner-side faces (l == row), ascending f
-        for (int j = 0; j < si.widthU; j++)
+        mbar_wait(sb0 + stage*stageBytes + L.bar, phase[stage]);
+        phase[stage] ^= 1u;
+
+        // ---- compute tile out of buffer `stage`
+        const unsigned char* base = smemRaw + stage*stageBytes;
+        const double* Ub = (const double*)(base + L.Ub);
+        const double* dg = (const double*)(base + L.diag);
+        const double* xs = (const double*)(base + L.xs);
+        const double* xF = (const double*)(base + L.xF);
+        const double* cF = (const double*)(base + L.cF);
+        const double* xB = (const double*)(base + L.xB);
+        const unsigned short* colU = (const unsigned short*)(base + L.colU);
+        const unsigned short* colL = (const unsigned short*)(base + L.colL);
+        const unsigned short* idxL = (const unsigned short*)(base + L.idxL);
+        const SliceInfo* sl = (const SliceInfo*)(base + L.sl);
+        const int r0 = A.tileStart[tile], nr = A.tileStart[tile + 1] - r0;
+        const int eU0 = sl[0].offU, eL0 = sl[0].offL;
+        for (int q = tid; q < nr; q += AMUL_TPB)
         {
-            const int e = si.offU - eU0 + j*32 + ln;
-            const unsigned c = colU[e];
-            if (c == 0xFFFFu) break;
-            const double xv = (c & 0x8000u) ? xB[c & 0x7FFFu] : xs[c];
-            acc = __dadd_rn(acc, __dmul_rn(Ub[e], xv));
+            const SliceInfo si = sl[q >> 5];
+            const int ln = q & 31;
+            const double xr = xs[q];
+            double acc = __dmul_rn(dg[q], xr);
+            // neighbour-side faces (u == row), ascending f
+            for (int j = 0; j < si.widthL; j++)
+            {
+                const int e = si.offL - eL0 + j*32 + ln;
+                const unsigned c = colL[e];
+                if (c == 0xFFFFu) break;
+                double cf, xv;
+                if (c & 0x8000u) { cf = cF[c & 0x7FFFu]; xv = xF[c & 0x7FFFu]; }
+                else { cf = Ub[idxL[e]]; xv = xs[c]; }
+                acc = __dadd_rn(acc, __dmul_rn(cf, xv));
+            }
+            // owner-side faces (l == row), ascending f
+            for (int j = 0; j < si.widthU; j++)
+            {
+                const int e = si.offU - eU0 + j*32 + ln;
+                const unsigned c = colU[e];
+                if (c == 0xFFFFu) break;
+                const double xv = (c & 0x8000u) ? xB[c & 0x7FFFu] : xs[c];
+                acc = __dadd_rn(acc, __dmul_rn(Ub[e], xv));
+            }
+            Ax[r0 + q] = acc;
+            if (MODE == 1)
+            {
+                const int r = r0 + q;
+                const bool masked = ifMask && ((ifMask[r >> 5] >> (r & 31)) & 1u);
+                if (!masked) dot[0] += acc*xr;
+            }
         }
-        Ax[r0 + q] = acc;
-        if (MODE == 1)
+        if (haveNext)
         {
-            const int r = r0 + q;
-            const bool masked = ifMask && ((ifMask[r >> 5] >> (r & 31)) & 1u);
-            if (!masked) dot[0] += acc*xr;
+            store_values(nextTile, stage ^ 1, Ecur);             // buffer stage^1 was released by the barrier above
+            Ecur = Enext;
         }
     }
-    if (MODE == 1) grid_reduce_finish<1, AMUL_TPB>(dot, partials, partStride, tile, A.nTiles, st, S_AMUL, nullptr);
+    if (MODE == 1) grid_reduce_finish<1, AMUL_TPB>(dot, partials, partStride, blockIdx.x, gridDim.x, st, S_AMUL, nullptr);
 }
 
 static constexpr int SWEEP_TPB = 128;       // warp 0 sweeps, warps 1-3 fetch cross-tile values
