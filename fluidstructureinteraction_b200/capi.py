@@ -256,7 +256,7 @@ class GpuPCG(object):
         self._check(self.lib.gpupcg_comm_init(self.h, rank, nRanks, buf))
 
 
-PATCH_TYPES = {"tractionDisplacement": 0, "fixedDisplacement": 1}
+PATCH_TYPES = {"tractionDisplacement": 0, "fixedDisplacement": 1, "symmetryDisplacement": 2}
 
 
 class GpuMesh(object):

@@ -55,6 +55,34 @@ struct MeshDev
     const double* points;
 };
 
+
+// symmetryDisplacementFvPatchVectorField::snGrad()  (symmetryDisplacementFvPatchVectorField.C:134-165)
+__device__ void symmetry_snGrad(const MeshDev& M, int f, const double* __restrict__ D, const double* __restrict__ gradD, double* sn)
+{
+    const int c = M.owner[f];
+    const double magSf = M.magSf[f];
+    double n[3], delta[3], k[3], kg[3], UP[3], G[9], S[6], T[6], tv[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) { n[d] = dvd(M.Sf[3*(size_t)f + d], magSf); delta[d] = sub(M.Cf[3*(size_t)f + d], M.C[3*(size_t)c + d]); }
+    const double nd = dot3(n, delta);
+#pragma unroll
+    for (int d = 0; d < 3; d++) k[d] = sub(delta[d], mul(n[d], nd));
+#pragma unroll
+    for (int q = 0; q < 9; q++) G[q] = gradD[9*(size_t)c + q];
+    vdotT(k, G, kg);
+#pragma unroll
+    for (int d = 0; d < 3; d++) UP[d] = add(D[3*(size_t)c + d], kg[d]);
+    S[0] = mul(n[0], n[0]); S[1] = mul(n[0], n[1]); S[2] = mul(n[0], n[2]); S[3] = mul(n[1], n[1]); S[4] = mul(n[1], n[2]); S[5] = mul(n[2], n[2]);
+    T[0] = sub(1.0, mul(2.0, S[0])); T[1] = -mul(2.0, S[1]); T[2] = -mul(2.0, S[2]);
+    T[3] = sub(1.0, mul(2.0, S[3])); T[4] = -mul(2.0, S[4]); T[5] = sub(1.0, mul(2.0, S[5]));
+    tv[0] = add(add(mul(T[0], UP[0]), mul(T[1], UP[1])), mul(T[2], UP[2]));
+    tv[1] = add(add(mul(T[1], UP[0]), mul(T[3], UP[1])), mul(T[4], UP[2]));
+    tv[2] = add(add(mul(T[2], UP[0]), mul(T[4], UP[1])), mul(T[5], UP[2]));
+    const double h = dvd(M.deltaCoeffs[f], 2.0);
+#pragma unroll
+    for (int d = 0; d < 3; d++) sn[d] = mul(sub(tv[d], UP[d]), h);
+}
+
 __global__ void __launch_bounds__(ATPB) k_asm_faces(MeshDev M, const double* __restrict__ mu, const double* __restrict__ lambda,
                                                     const double* __restrict__ D, const double* __restrict__ gradD,
                                                     const double* __restrict__ gradDf, double limitCoeff,
@@ -178,6 +206,7 @@ __global__ void __launch_bounds__(ATPB) k_asm_cells(MeshDev M, const double* __r
 }
 
 __global__ void __launch_bounds__(ATPB) k_asm_patches(MeshDev M, const double* __restrict__ mu, const double* __restrict__ lambda,
+                                                      const double* __restrict__ D,
                                                       const double* __restrict__ gradD, const double* __restrict__ gradDf,
                                                       const double* __restrict__ gms, const double* __restrict__ traction,
                                                       const double* __restrict__ pressure, const double* __restrict__ fixedValue,
@@ -208,6 +237,17 @@ __global__ void __launch_bounds__(ATPB) k_asm_patches(MeshDev M, const double* _
             {
                 gIC[d] = -dcf;
                 gBC[d] = mul(dcf, sub(fixedValue[3*(size_t)bf + d], kg[d]));
+            }
+        }
+        else if (M.bfPatchType[bf] == 2)
+        {
+            double sn[3];
+            symmetry_snGrad(M, f, D, gradD, sn);
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+            {
+                gIC[d] = mul(-dcf, fabs(n[d]));
+                gBC[d] = sub(sn[d], mul(gIC[d], D[3*(size_t)c + d]));
             }
         }
         else
@@ -395,6 +435,7 @@ __device__ void patch_snGrad(const MeshDev& M, int f, const double* __restrict__
 #pragma unroll
         for (int d = 0; d < 3; d++) sn[d] = mul(sub(fixedValue[3*(size_t)bf + d], add(D[3*(size_t)c + d], kg[d])), M.deltaCoeffs[f]);
     }
+    else if (M.bfPatchType[bf] == 2) symmetry_snGrad(M, f, D, gradD, sn);
     else
     {
 #pragma unroll
@@ -647,7 +688,7 @@ extern "C" int gpupcg_assemble_D(gpupcg_mesh m, const double* mu, const double* 
                                                   m->dUpper, m->dLup, m->dGms, m->dFluxE, m->dFluxC);
         k_asm_cells<<<agrid(m, nC), ATPB, 0, s>>>(M, m->dRho, g[0], g[1], g[2], m->dLup, m->dFluxE, m->dFluxC, m->dDiag, m->dSource);
         if (nBF > 0)
-            k_asm_patches<<<agrid(m, nBF), ATPB, 0, s>>>(M, m->dMu, m->dLambda, m->dGradD, m->dGradDf, m->dGms, m->dTraction,
+            k_asm_patches<<<agrid(m, nBF), ATPB, 0, s>>>(M, m->dMu, m->dLambda, m->dD, m->dGradD, m->dGradDf, m->dGms, m->dTraction,
                                                          m->dPressure, m->dFixed, m->dIC, m->dBC);
     }
     MCK(cudaEventRecord(m->ev1, s));

@@ -170,7 +170,8 @@ int gpupcg_comm_init(gpupcg_handle h, int rank, int nRanks, const void* ncclUniq
  * (unsTotalLagrangianStress.C:846-859, steadyState d2dt2, linear elasticity):
  *   fvm::laplacian(2*muf+lambdaf, D) with the reference's `skewCorrected` snGrad scheme
  *   (skewCorrectedVectorSnGrad.C:50-294), fvc::div(Sf & (...gradDf...)), rho*g, and the boundary
- *   coefficients of tractionDisplacement (patchType 0) / fixedDisplacement (patchType 1) patches.
+ *   coefficients of tractionDisplacement (patchType 0) / fixedDisplacement (1) / symmetryDisplacement (2) patches
+ *   (fvPatchFields/{tractionDisplacement,fixedDisplacement,symmetryDisplacement}/*.C).
  * gpupcg_mesh_create uploads what foam-extend's fvMesh provides once per mesh: owner/neighbour, the patch
  * table and mesh.Sf(), magSf(), Cf(), C(), V(), weights(), deltaCoeffs() (boundary faces included).
  * gpupcg_assemble_D: per-cell mu, lambda, rho, D[3], gradD[9]; per-face gradDf[9]; per boundary face

@@ -199,7 +199,7 @@ def set_sum_mode(mode):
     load().orc_set_sum_mode(int(mode))
 
 
-PATCH_TYPES = {"tractionDisplacement": 0, "fixedDisplacement": 1}
+PATCH_TYPES = {"tractionDisplacement": 0, "fixedDisplacement": 1, "symmetryDisplacement": 2}
 
 
 def lame(E, nu, planeStress=False):

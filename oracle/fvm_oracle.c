@@ -32,7 +32,7 @@ typedef struct orc_mesh
     const int* neighbour;       /* [nInternalFaces] */
     const int* patchStart;      /* [nPatches] first face */
     const int* patchSize;       /* [nPatches] */
-    const int* patchType;       /* 0 tractionDisplacement (fixedGradient), 1 fixedDisplacement (fixedValue) */
+    const int* patchType;       /* 0 tractionDisplacement (fixedGradient), 1 fixedDisplacement (fixedValue), 2 symmetryDisplacement */
     const double* Sf;           /* [nFaces*3] */
     const double* magSf;        /* [nFaces] */
     const double* Cf;           /* [nFaces*3] */
@@ -118,6 +118,28 @@ static void skew_correction(const orc_mesh* M, int f, const double* D, const dou
     double lim = limitCoeff*mag3(t)/((1 - limitCoeff)*mag3(ssf) + ORC_SMALL);
     if (lim > 1.0) lim = 1.0;
     for (int d = 0; d < 3; d++) ssf[d] *= lim;
+}
+
+
+/* symmetryDisplacementFvPatchVectorField::snGrad()   (symmetryDisplacementFvPatchVectorField.C:134-165):
+ *   UP = D_P + (k & gradD_P);  snGrad = (transform(I - 2.0*sqr(nHat), UP) - UP)*(deltaCoeffs/2.0)              */
+static void symmetry_snGrad(const orc_mesh* M, int f, const double* D, const double* gradD, double* sn)
+{
+    const int c = M->owner[f];
+    double n[3], delta[3], k[3], kg[3], UP[3], S[6], T[6], tv[3];
+    for (int d = 0; d < 3; d++) { n[d] = M->Sf[3*f + d]/M->magSf[f]; delta[d] = M->Cf[3*f + d] - M->C[3*c + d]; }
+    const double nd = dot3(n, delta);
+    for (int d = 0; d < 3; d++) k[d] = delta[d] - n[d]*nd;
+    vdotT(k, gradD + 9*c, kg);
+    for (int d = 0; d < 3; d++) UP[d] = D[3*c + d] + kg[d];
+    /* sqr(n) as symmTensor xx xy xz yy yz zz ; T = I - 2.0*sqr(n) */
+    S[0] = n[0]*n[0]; S[1] = n[0]*n[1]; S[2] = n[0]*n[2]; S[3] = n[1]*n[1]; S[4] = n[1]*n[2]; S[5] = n[2]*n[2];
+    T[0] = 1.0 - 2.0*S[0]; T[1] = -(2.0*S[1]); T[2] = -(2.0*S[2]); T[3] = 1.0 - 2.0*S[3]; T[4] = -(2.0*S[4]); T[5] = 1.0 - 2.0*S[5];
+    tv[0] = T[0]*UP[0] + T[1]*UP[1] + T[2]*UP[2];
+    tv[1] = T[1]*UP[0] + T[3]*UP[1] + T[4]*UP[2];
+    tv[2] = T[2]*UP[0] + T[4]*UP[1] + T[5]*UP[2];
+    const double h = M->deltaCoeffs[f]/2.0;
+    for (int d = 0; d < 3; d++) sn[d] = (tv[d] - UP[d])*h;
 }
 
 /*
@@ -220,6 +242,19 @@ void orc_assemble_D
                 {
                     gIC[d] = -dcf;
                     gBC[d] = dcf*(fixedValue[3*bf + d] - kg[d]);
+                }
+            }
+            else if (M->patchType[p] == 2)
+            {
+                /* symmetryDisplacement ([EXT] transformFvPatchField over symmetryFvPatchField):
+                   gradientInternalCoeffs = -deltaCoeffs*snGradTransformDiag(), snGradTransformDiag = (|nx|,|ny|,|nz|)
+                   gradientBoundaryCoeffs = snGrad() - cmptMultiply(gradientInternalCoeffs, patchInternalField)     */
+                double sn[3];
+                symmetry_snGrad(M, f, D, gradD, sn);
+                for (int d = 0; d < 3; d++)
+                {
+                    gIC[d] = -dcf*fabs(n[d]);
+                    gBC[d] = sn[d] - gIC[d]*D[3*c + d];
                 }
             }
             else
@@ -386,6 +421,7 @@ static void patch_snGrad(const orc_mesh* M, int ptype, int f, const double* D, c
         vdotT(k, gradD + 9*c, kg);
         for (int d = 0; d < 3; d++) sn[d] = (fixedValue[3*bf + d] - (D[3*c + d] + kg[d]))*M->deltaCoeffs[f];
     }
+    else if (ptype == 2) symmetry_snGrad(M, f, D, gradD, sn);
     else
     {
         for (int d = 0; d < 3; d++) sn[d] = patchGradient[3*bf + d];

@@ -79,12 +79,42 @@ def test_oracle_sigma_and_lame():
     assert np.array_equal(sig[0], [0 + 36, 8, 16, 16 + 36, 24, 32 + 36])
 
 
+PATCHES_SYM = {"fixed": "fixedDisplacement", "loaded": "tractionDisplacement", "free": "symmetryDisplacement"}
+
+
+def test_oracle_symmetry_plane_coefficients():
+    """symmetryDisplacement on an axis-aligned plane: the normal component is pinned (internalCoeffs = gamma|Sf|delta
+    on it, zero on the tangential ones) and a displacement field that is already symmetric gives no boundary source."""
+    m = meshes.hex_box(4, 3, 3)
+    g = geometry.compute(m)
+    f = fields(m, 2)
+    f["gradD"][...] = 0.0
+    a = oracle.assemble_D(m, g, PATCHES_SYM, f["mu"], f["lam"], f["rho"], f["g"], f["D"], f["gradD"], f["gradDf"],
+                          f["traction"], f["pressure"], f["fixedValue"], 1.0)
+    p = m.patch("free"); nIF = m.nInternalFaces
+    sl = slice(p["start"] - nIF, p["start"] - nIF + p["size"])
+    n = g.Sf[p["start"]:p["start"] + p["size"]]/g.magSf[p["start"]:p["start"] + p["size"], None]
+    ic = a["internalCoeffs"][sl]
+    assert np.all(ic[np.abs(n) < 0.5] == 0.0) and np.all(ic[np.abs(n) > 0.5] > 0.0)
+    # boundaryCoeffs = gamma|Sf|*(snGrad - gIC*D_P): with gradD = 0, snGrad = -delta*n(n.D_P) and gIC*D_P = -delta*|n|*D_P
+    # cancel on the normal component
+    assert np.max(np.abs(a["boundaryCoeffs"][sl])) <= 1e-9*np.max(np.abs(ic))*np.max(np.abs(f["D"]))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind", ["hex", "tet"])
 def test_gpu_assembly_bit_exact(kind):
     m = meshes.hex_box(12, 6, 8) if kind == "hex" else meshes.tet_box(6, 4, 5, jitter=0.15)
     g = geometry.compute(m)
     f = fields(m, 5)
+    gms = pkg.GpuMesh(m, g, PATCHES_SYM)
+    a = gms.assemble_D(f["mu"], f["lam"], f["rho"], f["g"], f["D"], f["gradD"], f["gradDf"], f["traction"],
+                       f["pressure"], f["fixedValue"], 1.0)
+    r = oracle.assemble_D(m, g, PATCHES_SYM, f["mu"], f["lam"], f["rho"], f["g"], f["D"], f["gradD"], f["gradDf"],
+                          f["traction"], f["pressure"], f["fixedValue"], 1.0)
+    for k in ("upper", "diag", "source", "internalCoeffs", "boundaryCoeffs"):
+        assert np.array_equal(a[k], r[k]), "symmetry " + k
+    gms.close()
     gm = pkg.GpuMesh(m, g, PATCHES)
     for limitCoeff in (1.0, 0.5):
         a = gm.assemble_D(f["mu"], f["lam"], f["rho"], f["g"], f["D"], f["gradD"], f["gradDf"], f["traction"],
@@ -161,10 +191,11 @@ def test_gpu_gradients_bit_exact(kind):
     D = 1e-4*rng.standard_normal((m.nCells, 3)); pD = 1e-4*rng.standard_normal((m.nPoints, 3))
     Gold = 1e-4*rng.standard_normal((m.nCells, 9)); fixed = 1e-4*rng.standard_normal((nBF, 3))
     pgrad = 1e-4*rng.standard_normal((nBF, 3))
-    gm = pkg.GpuMesh(m, g, PATCHES)
-    for limitCoeff in (1.0, 0.5):
-        G, Gb, Gf, ms = gm.gradients(D, pD, Gold, fixed, pgrad, limitCoeff)
-        G2, Gb2 = oracle.grad(m, g, PATCHES, D, pD, Gold, fixed, pgrad)
-        Gf2 = oracle.fgrad(m, g, PATCHES, D, pD, G2, fixed, pgrad, limitCoeff)
-        assert np.array_equal(G, G2) and np.array_equal(Gb, Gb2) and np.array_equal(Gf, Gf2)
-    gm.close()
+    for patches in (PATCHES, PATCHES_SYM):
+        gm = pkg.GpuMesh(m, g, patches)
+        for limitCoeff in (1.0, 0.5):
+            G, Gb, Gf, ms = gm.gradients(D, pD, Gold, fixed, pgrad, limitCoeff)
+            G2, Gb2 = oracle.grad(m, g, patches, D, pD, Gold, fixed, pgrad)
+            Gf2 = oracle.fgrad(m, g, patches, D, pD, G2, fixed, pgrad, limitCoeff)
+            assert np.array_equal(G, G2) and np.array_equal(Gb, Gb2) and np.array_equal(Gf, Gf2)
+        gm.close()
