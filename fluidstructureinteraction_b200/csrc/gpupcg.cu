@@ -41,6 +41,9 @@ struct gpupcg_handle_s
     int *dTileStart = nullptr, *dTileItemPtr = nullptr, *dItems = nullptr;
     unsigned short *dColL16 = nullptr, *dIdxL16 = nullptr, *dColU16 = nullptr;
     int *dExtFPtr = nullptr, *dExtFCol = nullptr, *dExtFIdx = nullptr, *dExtBPtr = nullptr, *dExtBCol = nullptr;
+    AmulTileMeta* dAmulMeta = nullptr; unsigned short* dAmulU16 = nullptr; unsigned int* dAmulL32 = nullptr;
+    int *dAmulExtX = nullptr, *dAmulExtC = nullptr;
+    int amulXStride = AMUL_TPB, amulCStride = AMUL_TPB;
     unsigned long long* dTileTicket = nullptr;
     unsigned long long* dTileTrace = nullptr;
     size_t smemFwd = 0, smemBwd = 0, smemAmul = 0;
@@ -160,13 +163,66 @@ extern "C" int gpupcg_destroy(gpupcg_handle h)
                     h->dX, h->dB, h->dRA, h->dWA, h->dPA, h->dY, h->dStageA, h->dStageB, h->dStageF,
                     h->dBou, h->dXNbr, h->dSend, h->dPartials, h->dHistory, h->dState, h->dFlush,
                     h->dTileStart, h->dTileItemPtr, h->dItems, h->dColL16, h->dIdxL16, h->dColU16,
-                    h->dExtFPtr, h->dExtFCol, h->dExtFIdx, h->dExtBPtr, h->dExtBCol, h->dTileTicket};
+                    h->dExtFPtr, h->dExtFCol, h->dExtFIdx, h->dExtBPtr, h->dExtBCol, h->dTileTicket,
+                    h->dAmulMeta, h->dAmulU16, h->dAmulL32, h->dAmulExtX, h->dAmulExtC};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->hState) cudaFreeHost(h->hState);
     if (h->hHistory) cudaFreeHost(h->hHistory);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->ownStream) cudaStreamDestroy(h->ownStream);
     delete h;
+    return GPUPCG_OK;
+}
+
+static int round_up(int v, int m) { return ((std::max(v, 1) + m - 1)/m)*m; }
+
+// The Amul kernel's view of the tiles: per-tile contiguous ranges, operand codes that index the kernel's shared
+// arrays directly (xv = [tile x | cross-tile x: neighbour side, then owner side], cv = [tile U block | cross-tile
+// neighbour-side coefficients]) and fixed-stride gather lists.  Derived from the plan's 16-bit tile codes.
+static int build_amul_view(gpupcg_handle h, cudaStream_t s)
+{
+    const HostPlan& P = h->plan;
+    const int T = P.tileRowsMax, EU = P.maxTileEntriesU;
+    const int XS = h->amulXStride, CS = h->amulCStride;
+    std::vector<AmulTileMeta> meta(std::max(1, P.nTiles));
+    std::vector<unsigned short> U16(P.colU16.size());
+    std::vector<unsigned int> L32(P.colL16.size());
+    std::vector<int> extX((size_t)std::max(1, P.nTiles)*XS, -1), extC((size_t)std::max(1, P.nTiles)*CS, -1);
+    for (int t = 0; t < P.nTiles; t++)
+    {
+        const int r0 = P.tileStart[t], r1 = P.tileStart[t + 1];
+        const int s0 = r0/32, s1 = r1/32;
+        const int eU0 = P.slices[s0].offU, eU1 = (s1 < P.nSlices) ? P.slices[s1].offU : (int)P.colU16.size();
+        const int eL0 = P.slices[s0].offL, eL1 = (s1 < P.nSlices) ? P.slices[s1].offL : (int)P.colL16.size();
+        const int nXF = P.extFPtr[t + 1] - P.extFPtr[t], nXB = P.extBPtr[t + 1] - P.extBPtr[t];
+        meta[t] = AmulTileMeta{r0, r1 - r0, eU0, eU1 - eU0, eL0, eL1 - eL0, nXF + nXB, nXF};
+        for (int k = 0; k < nXF; k++)
+        {
+            extX[(size_t)t*XS + k] = P.extFCol[P.extFPtr[t] + k];
+            extC[(size_t)t*CS + k] = P.extFIdx[P.extFPtr[t] + k];
+        }
+        for (int k = 0; k < nXB; k++) extX[(size_t)t*XS + nXF + k] = P.extBCol[P.extBPtr[t] + k];
+        for (int e = eL0; e < eL1; e++)
+        {
+            const unsigned c = P.colL16[e];
+            if (c == 0xFFFFu) L32[e] = 0x80000000u;
+            else if (c & 0x8000u) L32[e] = (unsigned)(T + (c & 0x7FFFu)) | ((unsigned)(EU + (c & 0x7FFFu)) << 16);
+            else L32[e] = c | ((unsigned)P.idxL16[e] << 16);
+        }
+        for (int e = eU0; e < eU1; e++)
+        {
+            const unsigned c = P.colU16[e];
+            if (c == 0xFFFFu) U16[e] = 0x8000u;
+            else if (c & 0x8000u) U16[e] = (unsigned short)(T + nXF + (c & 0x7FFFu));
+            else U16[e] = (unsigned short)c;
+        }
+    }
+    CK(upload(h->dAmulMeta, meta, s));
+    CK(upload(h->dAmulU16, U16, s));
+    CK(upload(h->dAmulL32, L32, s));
+    CK(upload(h->dAmulExtX, extX, s));
+    CK(upload(h->dAmulExtC, extC, s));
+    CK(cudaStreamSynchronize(s));
     return GPUPCG_OK;
 }
 
@@ -210,13 +266,21 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
         const HostPlan& Q = h->plan;
         h->smemFwd = sweep_layout(Q.tileRowsMax, Q.maxTileExtF, Q.maxItems, std::max(Q.maxTileEntriesU, Q.maxTileEntriesL), Q.maxTileEntriesL).bytes;
         h->smemBwd = sweep_layout(Q.tileRowsMax, Q.maxTileExtB, Q.maxItems, Q.maxTileEntriesU, Q.maxTileEntriesL).bytes;
-        h->smemAmul = 2*(size_t)((amul_layout(Q.tileRowsMax, Q.maxTileEntriesU, Q.maxTileEntriesL, Q.maxTileExtF, Q.maxTileExtB).bytes + 127u) & ~127u);
+        int maxX = 0;
+        for (int t = 0; rc == GPUPCG_OK && t < Q.nTiles; t++)
+            maxX = std::max(maxX, Q.extFPtr[t + 1] - Q.extFPtr[t] + Q.extBPtr[t + 1] - Q.extBPtr[t]);
+        h->amulXStride = round_up(maxX, AMUL_TPB);
+        h->amulCStride = round_up(Q.maxTileExtF, AMUL_TPB);
+        h->smemAmul = 2*(size_t)((amul_layout(Q.tileRowsMax, Q.maxTileEntriesU, Q.maxTileEntriesL, h->amulXStride, h->amulCStride).bytes + 127u) & ~127u);
         const size_t need = std::max(h->smemAmul, std::max(h->smemFwd, h->smemBwd));
-        if (rc == GPUPCG_OK && need <= smemCap) break;
+        // the Amul operand codes hold 15-bit indices into the kernel's shared arrays
+        const bool codesFit = Q.tileRowsMax + h->amulXStride < 0x8000 && Q.maxTileEntriesU + h->amulCStride < 0x8000;
+        if (rc == GPUPCG_OK && need <= smemCap && codesFit) break;
         if (tileRows <= 32) break;
         tileRows /= 2;
     }
-    if (rc != GPUPCG_OK || std::max(h->smemAmul, std::max(h->smemFwd, h->smemBwd)) > smemCap)
+    if (rc != GPUPCG_OK || std::max(h->smemAmul, std::max(h->smemFwd, h->smemBwd)) > smemCap ||
+        h->plan.tileRowsMax + h->amulXStride >= 0x8000 || h->plan.maxTileEntriesU + h->amulCStride >= 0x8000)
     {
         h->err = "gpupcg_create: a single 32-row tile does not fit in shared memory (rows with too many faces)";
         return GPUPCG_ERR_UNSUPPORTED;
@@ -269,6 +333,7 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     CK(upload(h->dExtFIdx, P.extFIdx, s));
     CK(upload(h->dExtBPtr, P.extBPtr, s));
     CK(upload(h->dExtBCol, P.extBCol, s));
+    { int rcv = build_amul_view(h, s); if (rcv) return rcv; }
     if (env_int("GPUPCG_TILE_TRACE", 0))
     {
         unsigned long long* d = nullptr;
@@ -312,6 +377,8 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     T.extBPtr = h->dExtBPtr; T.extBCol = h->dExtBCol;
     T.nTiles = P.nTiles; T.tileRowsMax = P.tileRowsMax; T.maxItems = P.maxItems;
     T.maxEU = P.maxTileEntriesU; T.maxEL = P.maxTileEntriesL; T.maxExtF = P.maxTileExtF; T.maxExtB = P.maxTileExtB;
+    T.amulMeta = h->dAmulMeta; T.amulU16 = h->dAmulU16; T.amulL32 = h->dAmulL32;
+    T.amulExtX = h->dAmulExtX; T.amulExtC = h->dAmulExtC; T.amulXStride = h->amulXStride; T.amulCStride = h->amulCStride;
     h->tiles = T;
 
     // the big host index arrays are no longer needed

@@ -323,6 +323,8 @@ __device__ __forceinline__ double wait_shared(const unsigned long long* p)
 // Everything a tile needs lives in CONTIGUOUS global ranges (rows are numbered tile-major, the SELL blocks of a
 // tile are adjacent), so a tile is staged into shared memory with a handful of 1-D bulk copies (cp.async.bulk,
 // SASS UBLKCP) completing on one mbarrier -- no per-thread dependent index->value load chains.
+struct AmulTileMeta { int r0, nr, eU0, nEU, eL0, nEL, nX, nC; };     // one tile's contiguous ranges (rows, U / L entries)
+
 struct TileArgs
 {
     const SliceInfo* slices;
@@ -339,6 +341,13 @@ struct TileArgs
     const int* extBCol;
     int nTiles;
     int tileRowsMax, maxEU, maxEL, maxExtF, maxExtB, maxItems;     // shared-memory carve-up
+    // ---- Amul view (built once per mesh in gpupcg.cu: build_amul_view)
+    const AmulTileMeta* amulMeta;   // [nTiles]
+    const unsigned short* amulU16;  // owner-side operand: index into xv, 0x8000 = pad
+    const unsigned int* amulL32;    // neighbour-side operand: xv index | cv index << 16, bit 31 = pad
+    const int* amulExtX;            // [nTiles][amulXStride] global rows of the cross-tile x values, -1 = none
+    const int* amulExtC;            // [nTiles][amulCStride] U-array indices of the cross-tile coefficients, -1 = none
+    int amulXStride, amulCStride;   // multiples of AMUL_TPB
 };
 
 // ---- mbarrier + 1-D bulk copy (TMA) primitives
@@ -393,44 +402,45 @@ __device__ __forceinline__ int take_tile(unsigned long long* tileTicket, int nTi
 // ifMask (may be null): rows that own coupled faces are left out of the MODE-1 dot here (k_iface_update adds them).
 // ------------------------------------------------------------------------------------------
 static constexpr int AMUL_TPB = 128;
+static constexpr int AMUL_RX = 4;       // cross-tile x gathers / coefficient gathers whose indices a thread carries in
+static constexpr int AMUL_RC = 2;       // registers one tile ahead (more than that: blocking index loads)
 
+// Shared-memory carve-up of one stage (byte offsets):
+//   cv [EU + XC] doubles: the tile's U block, then its cross-tile neighbour-side coefficients
+//   dg [T]       doubles
+//   xv [T + XX]  doubles: the tile's x, then its cross-tile x values (neighbour side first, then owner side)
+//   U16 [EU] u16, L32 [EL] u32: operand codes (see AmulCodes in gpupcg.cu), sl [T/32] SliceInfo, mbarrier
 struct AmulLayout
 {
-    unsigned Ub, diag, xs, xF, cF, xB, colU, colL, idxL, sl, bar, bytes;
+    unsigned cv, dg, xv, U16, L32, sl, bar, bytes;
 };
 
-__host__ __device__ inline AmulLayout amul_layout(int T, int EU, int EL, int XF, int XB)
+__host__ __device__ inline AmulLayout amul_layout(int T, int EU, int EL, int XX, int XC)
 {
     AmulLayout L;
-    const unsigned xf = (XF + 1) & ~1, xb = (XB + 1) & ~1;
-    L.Ub = 0;
-    L.diag = L.Ub + 8u*EU;
-    L.xs = L.diag + 8u*T;
-    L.xF = L.xs + 8u*T;
-    L.cF = L.xF + 8u*xf;
-    L.xB = L.cF + 8u*xf;
-    L.colU = L.xB + 8u*xb;
-    L.colL = L.colU + 2u*EU;
-    L.idxL = L.colL + 2u*EL;
-    L.sl = L.idxL + 2u*EL;
+    L.cv = 0;
+    L.dg = L.cv + 8u*(EU + XC);
+    L.xv = L.dg + 8u*T;
+    L.L32 = L.xv + 8u*(T + XX);
+    L.U16 = L.L32 + 4u*EL;
+    L.sl = (L.U16 + 2u*EU + 15u) & ~15u;
     L.bar = L.sl + 16u*(T/32 + 1);
     L.bytes = L.bar + 16;
     return L;
 }
 
-// Persistent, double-buffered: a CTA walks tiles blockIdx.x, +gridDim.x, ...; while tile k is computed out of
-// buffer k&1 the bulk copies of tile k+1 are in flight into the other buffer, and its cross-tile gathers travel
-// through registers in a three-deep software pipeline (indices of tile k+2, values of tile k+1), so no global-load
-// latency is exposed between tiles.  Rows beyond EXT_R*AMUL_TPB cross-tile entries per list fall back to blocking
-// loads (never the case for the brick tiles of the structured cases).
-static constexpr int EXT_R = 2;
-
-struct ExtRegs
+__device__ __forceinline__ void cp_async8(unsigned dst, const void* src)
 {
-    int iF[EXT_R], cF[EXT_R], iB[EXT_R];        // indices (global row / U entry), -1 = none
-    double xF[EXT_R], vF[EXT_R], xB[EXT_R];     // gathered values
-};
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// Persistent, double-buffered: a CTA walks tiles blockIdx.x, +gridDim.x, ...; while tile k is computed out of
+// buffer k&1 the bulk copies of tile k+1 and its cross-tile gathers (8-byte cp.async, indices prefetched into
+// registers while tile k-1 was computed) are in flight into the other buffer.  One __syncthreads per tile.
+// Operand codes are direct indices into xv / cv (built once per mesh), so the row loop is branch-free:
+// all codes of a row are loaded first, then all operands, then the products are added in reference order.
 template <int MODE>
 __global__ void __launch_bounds__(AMUL_TPB) k_amul_tile(TileArgs A, const double* __restrict__ diag,
                                                         const double* __restrict__ Uval, const int* __restrict__ rowOld,
@@ -440,82 +450,60 @@ __global__ void __launch_bounds__(AMUL_TPB) k_amul_tile(TileArgs A, const double
 {
     if (MODE == 1 && st->done) return;
     extern __shared__ __align__(128) unsigned char smemRaw[];
-    const AmulLayout L = amul_layout(A.tileRowsMax, A.maxEU, A.maxEL, A.maxExtF, A.maxExtB);
+    const AmulLayout L = amul_layout(A.tileRowsMax, A.maxEU, A.maxEL, A.amulXStride, A.amulCStride);
     const unsigned sb0 = (unsigned)__cvta_generic_to_shared(smemRaw);
     const unsigned stageBytes = (L.bytes + 127u) & ~127u;
     const double xc = (MODE == 2) ? st->xRef : 0.0;
     const int tid = threadIdx.x;
+    const int T = A.tileRowsMax, EU = A.maxEU;
+    const int nkX = A.amulXStride/AMUL_TPB, nkC = A.amulCStride/AMUL_TPB;
 
-    // ---- helpers over a tile / a stage buffer
-    auto issue_bulk = [&](int tile, int stage)
+    auto issue_bulk = [&](const AmulTileMeta& M, int stage)
+    {
+        const unsigned sb = sb0 + stage*stageBytes, bar = sb + L.bar;
+        const unsigned bytes = 8u*M.nEU + 2u*M.nEU + 4u*M.nEL + 8u*M.nr + (MODE == 2 ? 0u : 8u*M.nr) + 16u*(M.nr >> 5);
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(sb + L.cv, Uval + M.eU0, 8u*M.nEU, bar);
+        bulk_g2s(sb + L.L32, A.amulL32 + M.eL0, 4u*M.nEL, bar);
+        bulk_g2s(sb + L.U16, A.amulU16 + M.eU0, 2u*M.nEU, bar);
+        bulk_g2s(sb + L.dg, diag + M.r0, 8u*M.nr, bar);
+        if (MODE != 2) bulk_g2s(sb + L.xv, x + M.r0, 8u*M.nr, bar);
+        bulk_g2s(sb + L.sl, A.slices + (M.r0 >> 5), 16u*(M.nr >> 5), bar);
+    };
+    int iX[AMUL_RX], iC[AMUL_RC];
+    auto load_indices = [&](int tile)
+    {
+        const int* lx = A.amulExtX + (size_t)tile*A.amulXStride + tid;
+        const int* lc = A.amulExtC + (size_t)tile*A.amulCStride + tid;
+#pragma unroll
+        for (int k = 0; k < AMUL_RX; k++) iX[k] = (k < nkX) ? lx[k*AMUL_TPB] : -1;
+#pragma unroll
+        for (int k = 0; k < AMUL_RC; k++) iC[k] = (k < nkC) ? lc[k*AMUL_TPB] : -1;
+    };
+    auto issue_gathers = [&](int tile, int stage)
     {
         const unsigned sb = sb0 + stage*stageBytes;
-        const int r0 = A.tileStart[tile], nr = A.tileStart[tile + 1] - r0;
-        const int s0 = r0 >> 5, nsl = nr >> 5;
-        const SliceInfo first = A.slices[s0], last = A.slices[s0 + nsl - 1];
-        const int eU0 = first.offU, nEU = last.offU + 32*last.widthU - eU0;
-        const int eL0 = first.offL, nEL = last.offL + 32*last.widthL - eL0;
-        const unsigned bytes = 8u*nEU + 2u*nEU + 4u*nEL + 8u*nr + (MODE == 2 ? 0u : 8u*nr) + 16u*nsl;
-        mbar_expect_tx(sb + L.bar, bytes);
-        bulk_g2s(sb + L.Ub, Uval + eU0, 8u*nEU, sb + L.bar);
-        bulk_g2s(sb + L.colU, A.colU16 + eU0, 2u*nEU, sb + L.bar);
-        bulk_g2s(sb + L.colL, A.colL16 + eL0, 2u*nEL, sb + L.bar);
-        bulk_g2s(sb + L.idxL, A.idxL16 + eL0, 2u*nEL, sb + L.bar);
-        bulk_g2s(sb + L.diag, diag + r0, 8u*nr, sb + L.bar);
-        if (MODE != 2) bulk_g2s(sb + L.xs, x + r0, 8u*nr, sb + L.bar);
-        bulk_g2s(sb + L.sl, A.slices + s0, 16u*nsl, sb + L.bar);
-    };
-    auto load_indices = [&](int tile, ExtRegs& E)
-    {
-        const int fBase = A.extFPtr[tile], nXF = A.extFPtr[tile + 1] - fBase;
-        const int bBase = A.extBPtr[tile], nXB = A.extBPtr[tile + 1] - bBase;
+        const unsigned dx = sb + L.xv + 8u*(T + tid), dc = sb + L.cv + 8u*(EU + tid);
+        if (MODE != 2)
+        {
 #pragma unroll
-        for (int k = 0; k < EXT_R; k++)
-        {
-            const int e = tid + k*AMUL_TPB;
-            E.iF[k] = (e < nXF) ? A.extFCol[fBase + e] : -1;
-            E.cF[k] = (e < nXF) ? A.extFIdx[fBase + e] : -1;
-            E.iB[k] = (e < nXB) ? A.extBCol[bBase + e] : -1;
+            for (int k = 0; k < AMUL_RX; k++)
+                if (iX[k] >= 0) cp_async8(dx + 8u*k*AMUL_TPB, x + iX[k]);
+            for (int k = AMUL_RX; k < nkX; k++)
+            {
+                const int i = A.amulExtX[(size_t)tile*A.amulXStride + tid + k*AMUL_TPB];
+                if (i >= 0) cp_async8(dx + 8u*k*AMUL_TPB, x + i);
+            }
         }
-    };
-    auto load_values = [&](ExtRegs& E)
-    {
 #pragma unroll
-        for (int k = 0; k < EXT_R; k++)
+        for (int k = 0; k < AMUL_RC; k++)
+            if (iC[k] >= 0) cp_async8(dc + 8u*k*AMUL_TPB, Uval + iC[k]);
+        for (int k = AMUL_RC; k < nkC; k++)
         {
-            E.xF[k] = (E.iF[k] >= 0) ? ((MODE == 2) ? xc : x[E.iF[k]]) : 0.0;
-            E.vF[k] = (E.cF[k] >= 0) ? Uval[E.cF[k]] : 0.0;
-            E.xB[k] = (E.iB[k] >= 0) ? ((MODE == 2) ? xc : x[E.iB[k]]) : 0.0;
+            const int i = A.amulExtC[(size_t)tile*A.amulCStride + tid + k*AMUL_TPB];
+            if (i >= 0) cp_async8(dc + 8u*k*AMUL_TPB, Uval + i);
         }
-    };
-    auto store_values = [&](int tile, int stage, const ExtRegs& E)
-    {
-        unsigned char* base = smemRaw + stage*stageBytes;
-        double* xF = (double*)(base + L.xF);
-        double* cF = (double*)(base + L.cF);
-        double* xB = (double*)(base + L.xB);
-        const int fBase = A.extFPtr[tile], nXF = A.extFPtr[tile + 1] - fBase;
-        const int bBase = A.extBPtr[tile], nXB = A.extBPtr[tile + 1] - bBase;
-#pragma unroll
-        for (int k = 0; k < EXT_R; k++)
-        {
-            const int e = tid + k*AMUL_TPB;
-            if (e < nXF) { xF[e] = E.xF[k]; cF[e] = E.vF[k]; }
-            if (e < nXB) xB[e] = E.xB[k];
-        }
-        // more cross-tile entries than the register pipeline carries: blocking loads
-        for (int e = tid + EXT_R*AMUL_TPB; e < nXF; e += AMUL_TPB)
-        {
-            xF[e] = (MODE == 2) ? xc : x[A.extFCol[fBase + e]];
-            cF[e] = Uval[A.extFIdx[fBase + e]];
-        }
-        for (int e = tid + EXT_R*AMUL_TPB; e < nXB; e += AMUL_TPB) xB[e] = (MODE == 2) ? xc : x[A.extBCol[bBase + e]];
-        if (MODE == 2)
-        {
-            double* xs = (double*)(base + L.xs);
-            const int r0 = A.tileStart[tile], nr = A.tileStart[tile + 1] - r0;
-            for (int q = tid; q < nr; q += AMUL_TPB) xs[q] = (rowOld[r0 + q] >= 0) ? xc : 0.0;
-        }
+        cp_async_commit();
     };
 
     const int t0 = blockIdx.x, G = gridDim.x;
@@ -525,14 +513,18 @@ __global__ void __launch_bounds__(AMUL_TPB) k_amul_tile(TileArgs A, const double
         mbar_init(sb0 + stageBytes + L.bar, 1);
     }
     __syncthreads();
-    ExtRegs Ecur, Enext;
+    AmulTileMeta Mcur = {0, 0, 0, 0, 0, 0, 0, 0}, Mnext = Mcur;
     if (t0 < A.nTiles)
     {
-        if (tid == 0) issue_bulk(t0, 0);
-        load_indices(t0, Ecur);
-        load_values(Ecur);
-        store_values(t0, 0, Ecur);
-        if (t0 + G < A.nTiles) load_indices(t0 + G, Ecur);      // Ecur now carries the indices of the NEXT tile
+        Mcur = A.amulMeta[t0];
+        if (tid == 0) issue_bulk(Mcur, 0);
+        load_indices(t0);
+        issue_gathers(t0, 0);
+        if (t0 + G < A.nTiles)
+        {
+            Mnext = A.amulMeta[t0 + G];
+            load_indices(t0 + G);
+        }
     }
     double dot[1] = {0.0};
     unsigned phase[2] = {0u, 0u};
@@ -541,55 +533,81 @@ __global__ void __launch_bounds__(AMUL_TPB) k_amul_tile(TileArgs A, const double
     {
         const int nextTile = tile + G;
         const bool haveNext = nextTile < A.nTiles;
-        __syncthreads();                    // everyone is done reading buffer stage^1 (tile - G), and sees stage's gathers
+        cp_async_wait_all();                // my gathers of this tile have landed
+        __syncthreads();                    // ... and everyone's; everyone is done reading buffer stage^1 (tile - G)
+        AmulTileMeta M2 = Mnext;
         if (haveNext)
         {
-            if (tid == 0) issue_bulk(nextTile, stage ^ 1);
-            load_values(Ecur);                                   // values of tile+G (indices loaded one iteration ago)
-            if (nextTile + G < A.nTiles) load_indices(nextTile + G, Enext);
+            if (tid == 0) issue_bulk(Mnext, stage ^ 1);
+            issue_gathers(nextTile, stage ^ 1);
+            if (nextTile + G < A.nTiles)
+            {
+                M2 = A.amulMeta[nextTile + G];
+                load_indices(nextTile + G);
+            }
         }
         mbar_wait(sb0 + stage*stageBytes + L.bar, phase[stage]);
         phase[stage] ^= 1u;
 
         // ---- compute tile out of buffer `stage`
-        const unsigned char* base = smemRaw + stage*stageBytes;
-        const double* Ub = (const double*)(base + L.Ub);
-        const double* dg = (const double*)(base + L.diag);
-        const double* xs = (const double*)(base + L.xs);
-        const double* xF = (const double*)(base + L.xF);
-        const double* cF = (const double*)(base + L.cF);
-        const double* xB = (const double*)(base + L.xB);
-        const unsigned short* colU = (const unsigned short*)(base + L.colU);
-        const unsigned short* colL = (const unsigned short*)(base + L.colL);
-        const unsigned short* idxL = (const unsigned short*)(base + L.idxL);
+        unsigned char* base = smemRaw + stage*stageBytes;
+        const double* cv = (const double*)(base + L.cv);
+        const double* dg = (const double*)(base + L.dg);
+        double* xv = (double*)(base + L.xv);
+        const unsigned short* U16 = (const unsigned short*)(base + L.U16);
+        const unsigned int* L32 = (const unsigned int*)(base + L.L32);
         const SliceInfo* sl = (const SliceInfo*)(base + L.sl);
-        const int r0 = A.tileStart[tile], nr = A.tileStart[tile + 1] - r0;
-        const int eU0 = sl[0].offU, eL0 = sl[0].offL;
+        const int r0 = Mcur.r0, nr = Mcur.nr;
+        if (MODE == 2)
+        {
+            for (int q = tid; q < nr; q += AMUL_TPB) xv[q] = (rowOld[r0 + q] >= 0) ? xc : 0.0;
+            for (int q = tid; q < A.amulXStride; q += AMUL_TPB) xv[T + q] = xc;
+            __syncthreads();
+        }
         for (int q = tid; q < nr; q += AMUL_TPB)
         {
             const SliceInfo si = sl[q >> 5];
             const int ln = q & 31;
-            const double xr = xs[q];
+            const unsigned int* pl = L32 + (si.offL - Mcur.eL0 + ln);
+            const unsigned short* pu = U16 + (si.offU - Mcur.eU0 + ln);
+            const double* cu = cv + (si.offU - Mcur.eU0 + ln);
+            unsigned cl[4], cuv[4];
+            double fL[4], xL[4], fU[4], xU[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) cl[j] = (j < si.widthL) ? pl[32*j] : 0x80000000u;
+#pragma unroll
+            for (int j = 0; j < 4; j++) cuv[j] = (j < si.widthU) ? (unsigned)pu[32*j] : 0x8000u;
+            const double xr = xv[q];
             double acc = __dmul_rn(dg[q], xr);
-            // neighbour-side faces (u == row), ascending f
-            for (int j = 0; j < si.widthL; j++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
             {
-                const int e = si.offL - eL0 + j*32 + ln;
-                const unsigned c = colL[e];
-                if (c == 0xFFFFu) break;
-                double cf, xv;
-                if (c & 0x8000u) { cf = cF[c & 0x7FFFu]; xv = xF[c & 0x7FFFu]; }
-                else { cf = Ub[idxL[e]]; xv = xs[c]; }
-                acc = __dadd_rn(acc, __dmul_rn(cf, xv));
+                fL[j] = cv[(cl[j] >> 16) & 0x7FFFu];
+                xL[j] = xv[cl[j] & 0xFFFFu];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+            {
+                fU[j] = (j < si.widthU) ? cu[32*j] : 0.0;
+                xU[j] = xv[cuv[j] & 0x7FFFu];
+            }
+            // neighbour-side faces (u == row), ascending f
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if ((int)cl[j] >= 0) acc = __dadd_rn(acc, __dmul_rn(fL[j], xL[j]));
+            for (int j = 4; j < si.widthL; j++)
+            {
+                const unsigned c = pl[32*j];
+                if ((int)c >= 0) acc = __dadd_rn(acc, __dmul_rn(cv[(c >> 16) & 0x7FFFu], xv[c & 0xFFFFu]));
             }
             // owner-side faces (l == row), ascending f
-            for (int j = 0; j < si.widthU; j++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (!(cuv[j] & 0x8000u)) acc = __dadd_rn(acc, __dmul_rn(fU[j], xU[j]));
+            for (int j = 4; j < si.widthU; j++)
             {
-                const int e = si.offU - eU0 + j*32 + ln;
-                const unsigned c = colU[e];
-                if (c == 0xFFFFu) break;
-                const double xv = (c & 0x8000u) ? xB[c & 0x7FFFu] : xs[c];
-                acc = __dadd_rn(acc, __dmul_rn(Ub[e], xv));
+                const unsigned c = pu[32*j];
+                if (!(c & 0x8000u)) acc = __dadd_rn(acc, __dmul_rn(cu[32*j], xv[c & 0x7FFFu]));
             }
             Ax[r0 + q] = acc;
             if (MODE == 1)
@@ -599,11 +617,8 @@ __global__ void __launch_bounds__(AMUL_TPB) k_amul_tile(TileArgs A, const double
                 if (!masked) dot[0] += acc*xr;
             }
         }
-        if (haveNext)
-        {
-            store_values(nextTile, stage ^ 1, Ecur);             // buffer stage^1 was released by the barrier above
-            Ecur = Enext;
-        }
+        Mcur = Mnext;
+        Mnext = M2;
     }
     if (MODE == 1) grid_reduce_finish<1, AMUL_TPB>(dot, partials, partStride, blockIdx.x, gridDim.x, st, S_AMUL, nullptr);
 }
