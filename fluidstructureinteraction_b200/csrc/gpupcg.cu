@@ -47,6 +47,7 @@ struct gpupcg_handle_s
     unsigned long long* dTileTicket = nullptr;
     unsigned long long* dTileTrace = nullptr;
     size_t smemFwd = 0, smemBwd = 0, smemAmul = 0;
+    long long traceLen = 0;
     int amulGrid = 1;               // persistent CTAs of the Amul kernel
     bool hasOvf = false;            // some row has more than four faces on one side (polyhedral cells)
     int partStride = MAXPART;
@@ -337,8 +338,9 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     if (env_int("GPUPCG_TILE_TRACE", 0))
     {
         unsigned long long* d = nullptr;
-        CK(dalloc(d, 3LL*std::max(1, P.nTiles)));
-        CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long)*3*std::max(1, P.nTiles), s));
+        h->traceLen = 3LL*std::max(1, P.nTiles) + P.nRows + (long long)P.extFCol.size();
+        CK(dalloc(d, h->traceLen));
+        CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long)*h->traceLen, s));
         CK(cudaMemcpyToSymbol(g_tileTimes, &d, sizeof(d)));
         h->dTileTrace = d;
     }
@@ -470,6 +472,17 @@ extern "C" int gpupcg_debug_tile_trace(gpupcg_handle h, unsigned long long* out3
     CK(cudaMemcpy(out3n, h->dTileTrace, sizeof(unsigned long long)*3*h->plan.nTiles, cudaMemcpyDeviceToHost));
     return GPUPCG_OK;
 }
+
+#ifdef GPUPCG_DEEPTRACE
+// trace build only (tools/): tile stamps, then the publish time of every row, then the delivery time of every
+// cross-tile entry of the last forward sweep
+extern "C" int gpupcg_debug_deep_trace(gpupcg_handle h, unsigned long long* out, long long cap)
+{
+    if (!h || !out || !h->dTileTrace || cap < h->traceLen) return GPUPCG_ERR_ARG;
+    CK(cudaMemcpy(out, h->dTileTrace, sizeof(unsigned long long)*h->traceLen, cudaMemcpyDeviceToHost));
+    return GPUPCG_OK;
+}
+#endif
 
 extern "C" int gpupcg_launch_count(gpupcg_handle h, long long* count)
 {

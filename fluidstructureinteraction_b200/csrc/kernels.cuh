@@ -623,7 +623,10 @@ __global__ void __launch_bounds__(AMUL_TPB) k_amul_tile(TileArgs A, const double
     if (MODE == 1) grid_reduce_finish<1, AMUL_TPB>(dot, partials, partStride, blockIdx.x, gridDim.x, st, S_AMUL, nullptr);
 }
 
-static constexpr int SWEEP_TPB = 128;       // warp 0 sweeps, warps 1-3 fetch cross-tile values
+#ifndef GPUPCG_SWEEP_TPB
+#define GPUPCG_SWEEP_TPB 128
+#endif
+static constexpr int SWEEP_TPB = GPUPCG_SWEEP_TPB;       // one warp sweeps, the others fetch cross-tile values
 static constexpr int FETCHERS = SWEEP_TPB - 32;
 
 // Shared-memory carve-up of one sweep CTA (byte offsets, all 16 B aligned).
@@ -914,6 +917,8 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
     __syncthreads();
     if (g_tileTimes && threadIdx.x == 0 && MODE == 0) { g_tileTimes[3*tile] = tBegin; g_tileTimes[3*tile + 1] = gtime(); }
 
+    // (tried, no effect on B200: rotating the sweep-warp role over the SM's schedulers, sleeping between shared
+    //  polls, gating / doubling / tripling the global polls of the fetch lanes -- profiles/r1c_dic_latency_study.md)
     if (warp == 0)
     {
         // Software pipeline over the work items: in iteration i the descriptor of item i+2 and the static row data
@@ -984,31 +989,38 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
             sts_f64(vb + cur.q8, acc);
             if (cur.qg >= 0)
                 asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" :: "l"(out + r0 + cur.qg), "d"(acc) : "memory");
+#ifdef GPUPCG_DEEPTRACE
+            if (MODE == 0 && g_tileTimes && cur.qg >= 0) g_tileTimes[3*A.nTiles + r0 + cur.qg] = gtime();
+#endif
             if (d0.y & syncBit) __syncwarp();
             cur = nxt; d0 = d1; d1 = d2;
         }
-        if (g_tileTimes && threadIdx.x == 0 && MODE == 0) g_tileTimes[3*tile + 2] = gtime();
+        if (g_tileTimes && lane == 0 && MODE == 0) g_tileTimes[3*tile + 2] = gtime();
     }
     else
     {
         // Fetch lanes are independent state machines: each polls ITS current entry and delivers it the moment it
         // arrives.  (A plain "wait, then store" loop reconverges the warp before the store, so an early entry was
         // held back until the latest of its 32 warp-mates had arrived: 1.7 us per tile hop instead of ~1.)
-        int i = threadIdx.x - 32;
+        constexpr int stride = FETCHERS;
+        int i = (warp - 1)*32 + lane;
+        const int ns = g_spinNs;
         const unsigned long long* p = (i < nExt) ? out + extCol[xBase + i] : nullptr;
         // the address of the lane's NEXT entry is fetched while it waits for the current one: advancing must not put
         // a global-load latency into the poll loop of the whole warp
-        int colNext = (i + FETCHERS < nExt) ? extCol[xBase + i + FETCHERS] : 0;
-        const int ns = g_spinNs;
+        int colNext = (i + stride < nExt) ? extCol[xBase + i + stride] : 0;
         while (i < nExt)
         {
             const unsigned long long v = peek64(p);
             if (v != SENT)
             {
                 sts_u64(vb + 8u*(T + i), v);
-                i += FETCHERS;
+#ifdef GPUPCG_DEEPTRACE
+                if (MODE == 0 && g_tileTimes) g_tileTimes[3*A.nTiles + A.tileStart[A.nTiles] + xBase + i] = gtime();
+#endif
+                i += stride;
                 p = out + colNext;
-                if (i + FETCHERS < nExt) colNext = extCol[xBase + i + FETCHERS];
+                if (i + stride < nExt) colNext = extCol[xBase + i + stride];
             }
             else if (ns > 0) __nanosleep(ns);
         }

@@ -135,6 +135,14 @@ int build_plan(int nCells, int nFaces, const int* l, const int* u,
                         if (bb[k] < n3[k] && (long long)(bb[k] + 1)*bb[(k + 1) % 3]*bb[(k + 2) % 3] <= tileRows) { bb[k]++; grew = true; }
                     }
                 }
+                if (const char* ev = getenv("GPUPCG_BRICK"))       // experiment hook: explicit brick edges "bx,by,bz"
+                {
+                    int e0, e1, e2;
+                    if (sscanf(ev, "%d,%d,%d", &e0, &e1, &e2) == 3 && e0 > 0 && e1 > 0 && e2 > 0)
+                    {
+                        bb[0] = (int)std::min<long long>(e0, nx); bb[1] = (int)std::min<long long>(e1, ny); bb[2] = (int)std::min<long long>(e2, nz);
+                    }
+                }
                 const int bx = bb[0], by = bb[1], bz = bb[2];
                 // bricks in WAVEFRONT order (a+b+c ascending, then lexicographic): still topological at tile level,
                 // and the CTAs resident at any time are consecutive brick hyperplanes -- the ones the sweep is working

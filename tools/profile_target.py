@@ -4,6 +4,9 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import fluidstructureinteraction_b200 as pkg
+if os.environ.get("GPUPCG_LIB"):
+    from fluidstructureinteraction_b200 import capi
+    capi.LIB_PATH = os.environ["GPUPCG_LIB"]
 nx, ny, nz = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "200,50,100").split(",")]
 s = pkg.cases.cantilever_system(nx, ny, nz)
 g = pkg.GpuPCG(s["l"], s["u"], s["nCells"])
