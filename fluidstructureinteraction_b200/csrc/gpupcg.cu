@@ -48,6 +48,8 @@ struct gpupcg_handle_s
     unsigned long long* dTileTrace = nullptr;
     size_t smemFwd = 0, smemBwd = 0, smemAmul = 0;
     long long traceLen = 0;
+    DevState* hStateRing = nullptr;     // pinned, two snapshots of the device state (pipelined host loop)
+    cudaEvent_t evCheck[2] = {nullptr, nullptr};
     int amulGrid = 1;               // persistent CTAs of the Amul kernel
     bool hasOvf = false;            // some row has more than four faces on one side (polyhedral cells)
     int partStride = MAXPART;
@@ -168,6 +170,8 @@ extern "C" int gpupcg_destroy(gpupcg_handle h)
                     h->dAmulMeta, h->dAmulU16, h->dAmulL32, h->dAmulExtX, h->dAmulExtC};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->hState) cudaFreeHost(h->hState);
+    if (h->hStateRing) cudaFreeHost(h->hStateRing);
+    for (auto& e : h->evCheck) if (e) cudaEventDestroy(e);
     if (h->hHistory) cudaFreeHost(h->hHistory);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->ownStream) cudaStreamDestroy(h->ownStream);
@@ -366,6 +370,8 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     CK(dalloc(h->dHistory, h->historyCap));
     CK(dalloc(h->dState, 1));
     CK(cudaMallocHost((void**)&h->hState, sizeof(DevState)));
+    CK(cudaMallocHost((void**)&h->hStateRing, 2*sizeof(DevState)));
+    for (auto& e : h->evCheck) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CK(cudaMallocHost((void**)&h->hHistory, sizeof(double)*h->historyCap));
     memset(h->hState, 0, sizeof(DevState));
     CK(cudaMemsetAsync(h->dState, 0, sizeof(DevState), s));
@@ -712,28 +718,53 @@ static int solve_core(gpupcg_handle h, double tol, double relTol, int minIter, i
     fill_sent(h, h->dWA);
     CK(cudaGetLastError());
 
+    // Host loop, one batch ahead of the device: batch k+1 is enqueued BEFORE the host waits for the state snapshot
+    // taken after batch k-1, so the stream never runs dry while the host looks at `done`.  Every kernel of the
+    // iteration is gated on st->done on the device, so a batch enqueued after convergence is a string of no-ops.
     const int batch = std::max(1, env_int("GPUPCG_CHECK_EVERY", 8));
-    int launched = 0;
+    auto enqueue_check = [&](int slot) -> cudaError_t
+    {
+        cudaError_t e = cudaMemcpyAsync(h->hStateRing + slot, h->dState, sizeof(DevState), cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) return e;
+        return cudaEventRecord(h->evCheck[slot], s);
+    };
+    int launched = 0, slot = 0;
+    CK(enqueue_check(slot));
     while (true)
     {
-        CK(cudaMemcpyAsync(h->hState, h->dState, sizeof(DevState), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        if (h->hState->done || launched >= maxIter) break;
-        const int n = std::min(batch, maxIter - launched);
-        for (int i = 0; i < n; i++)
+        const bool canLaunch = launched < maxIter;
+        if (canLaunch)
         {
-            rc = enqueue_sweeps(h, h->dRA, h->dWA, true, 1); if (rc) return rc;
-            rc = allreduce_step(h, S_SWEEP, 1); if (rc) return rc;
-            LAUNCH(k_p_update, gN, s, h->dWA, h->dPA, P.nRows, h->dState);
-            rc = enqueue_amul(h, 1, h->dPA, h->dWA, false); if (rc) return rc;
-            rc = allreduce_step(h, S_AMUL, 2); if (rc) return rc;
-            LAUNCH(k_xr_update, gN, s, h->dPA, (unsigned long long*)h->dWA, h->dX, h->dRA, P.nRows,
-                                           h->dPartials, h->dState, h->dHistory);
-            rc = allreduce_step(h, S_XR, 1); if (rc) return rc;
+            const int n = std::min(batch, maxIter - launched);
+            for (int i = 0; i < n; i++)
+            {
+                rc = enqueue_sweeps(h, h->dRA, h->dWA, true, 1); if (rc) return rc;
+                rc = allreduce_step(h, S_SWEEP, 1); if (rc) return rc;
+                LAUNCH(k_p_update, gN, s, h->dWA, h->dPA, P.nRows, h->dState);
+                rc = enqueue_amul(h, 1, h->dPA, h->dWA, false); if (rc) return rc;
+                rc = allreduce_step(h, S_AMUL, 2); if (rc) return rc;
+                LAUNCH(k_xr_update, gN, s, h->dPA, (unsigned long long*)h->dWA, h->dX, h->dRA, P.nRows,
+                                               h->dPartials, h->dState, h->dHistory);
+                rc = allreduce_step(h, S_XR, 1); if (rc) return rc;
+            }
+            CK(cudaGetLastError());
+            launched += n;
+            CK(enqueue_check(slot ^ 1));
         }
-        CK(cudaGetLastError());
-        launched += n;
+        CK(cudaEventSynchronize(h->evCheck[slot]));
+        if (h->hStateRing[slot].done)
+        {
+            if (canLaunch)      // the batch enqueued above ran as no-ops; its snapshot is the same, final state
+            {
+                slot ^= 1;
+                CK(cudaEventSynchronize(h->evCheck[slot]));
+            }
+            break;
+        }
+        if (!canLaunch) break;  // maxIter launched and the last snapshot has been read
+        slot ^= 1;
     }
+    *h->hState = h->hStateRing[slot];
     CK(cudaEventRecord(h->ev[1], s));
     const DevState& st = *h->hState;
     const int nHist = std::min(std::min(st.nIter, historyCap), h->historyCap);
