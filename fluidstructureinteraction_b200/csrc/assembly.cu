@@ -26,7 +26,14 @@ constexpr double A_SMALL = 1.0e-15;
 __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ double dvd(double a, double b) { return __ddiv_rn(a, b); }
+// a/b.  A zero numerator sends __ddiv_rn through its ~65-instruction special-operand routine, and axis-aligned meshes
+// are full of them (two of the three components of every face vector).  0/b for a normal b is the signed zero 0*b.
+__device__ __forceinline__ double dvd(double a, double b)
+{
+    const unsigned eb = (unsigned)__double2hiint(b) & 0x7ff00000u;
+    if (a == 0.0 && eb - 0x00100000u < 0x7fe00000u) return __dmul_rn(a, b);
+    return __ddiv_rn(a, b);
+}
 
 __device__ __forceinline__ double dot3(const double* a, const double* b)
 {
@@ -309,6 +316,64 @@ __device__ __forceinline__ void cross3(const double* a, const double* b, double*
     r[2] = sub(mul(a[0], b[1]), mul(a[1], b[0]));
 }
 
+// x/3.0, correctly rounded, without the IEEE division sequence: q0 = x*RN(1/3), exact residual by FMA, one
+// correction (Markstein: with y = RN(1/b) and q0 within an ulp of a/b, q0 + (a - b*q0)*y rounds to RN(a/b); b = 3 is not
+// one of the all-ones-significand exceptions).  Only inside 2^-900 <= |x| < 2^901, where neither the residual nor the
+// correction can lose bits to underflow; zeros, subnormals, huge values, Inf and NaN take the division.
+// tools/div3_check.c compares it with x/3.0 on 4.6e8 operands (0 mismatches).
+__device__ __forceinline__ double div3(double x)
+{
+    const unsigned e = (unsigned)__double2hiint(x) & 0x7ff00000u;
+    if (e - 0x07b00000u < 0x70900000u)
+    {
+        const double r = 0x1.5555555555555p-2;
+        const double q0 = __dmul_rn(x, r);
+        const double rem = __fma_rn(-3.0, q0, x);
+        return __fma_rn(rem, r, q0);
+    }
+    return __ddiv_rn(x, 3.0);
+}
+// x/n for a face's point count: 4 and 2 are exact scalings, 3 the sequence above
+__device__ __forceinline__ double div_n(double x, int n, double dn)
+{
+    if (n == 4) return mul(x, 0.25);
+    if (n == 3) return div3(x);
+    return dvd(x, dn);
+}
+
+// one triangle (centre, a, b) of a face's fan: sign*(St*ttcf) into G, sign*(St & Ct) into V   (fvcGradf.C:541-610)
+__device__ __forceinline__ void fan_triangle(const double* Xa, const double* Xb, const double* Pa, const double* Pb,
+                                             const double* centre, const double* cf, bool minus, double* G, double& V)
+{
+    double ttcf[3], a[3], b[3], St[3], Ct[3], sP[3], sX[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+    {
+        sP[d] = add(add(Pa[d], Pb[d]), cf[d]);
+        sX[d] = add(add(centre[d], Xa[d]), Xb[d]);
+        a[d] = sub(Xa[d], centre[d]);
+        b[d] = sub(Xb[d], centre[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++) { ttcf[d] = div3(sP[d]); Ct[d] = div3(sX[d]); }
+    cross3(a, b, St);
+    // G -= St*ttcf and V -= St & Ct for the neighbour side: x - y == x + (-y) and (-a)*b == -(a*b) exactly, and a sum of
+    // negated terms is the negated sum, so the sign goes onto St once instead of onto every accumulation
+    const double half = minus ? -0.5 : 0.5;
+#pragma unroll
+    for (int d = 0; d < 3; d++) St[d] = mul(St[d], half);               // == +-(St/2.0) exactly
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) G[3*i + j] = add(G[3*i + j], mul(St[i], ttcf[j]));
+    V = add(V, dot3(St, Ct));
+}
+
+__device__ __forceinline__ void load3(const double* __restrict__ a, int i, double* r)
+{
+    r[0] = a[3*(size_t)i]; r[1] = a[3*(size_t)i + 1]; r[2] = a[3*(size_t)i + 2];
+}
+
 // one face's triangle-fan contribution sign*(St*ttcf), sign*(St & Ct)   (fvcGradf.C:541-610, 623-684)
 __device__ void grad_face(const MeshDev& M, int f, const double* __restrict__ pf, bool minus, double* G, double& V)
 {
@@ -341,6 +406,21 @@ __device__ void grad_face(const MeshDev& M, int f, const double* __restrict__ pf
         V = minus ? sub(V, sr) : add(V, sr);
         return;
     }
+    if (n == 4)         // the hex case: the four points live in registers, the fan is unrolled
+    {
+        double Xq[4][3], Pq[4][3], centre[3], cf[3];
+#pragma unroll
+        for (int p = 0; p < 4; p++) { const int ip = fp[p]; load3(X, ip, Xq[p]); load3(pf, ip, Pq[p]); }
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+        {
+            centre[d] = mul(add(add(add(add(0.0, Xq[0][d]), Xq[1][d]), Xq[2][d]), Xq[3][d]), 0.25);
+            cf[d] = mul(add(add(add(add(0.0, Pq[0][d]), Pq[1][d]), Pq[2][d]), Pq[3][d]), 0.25);
+        }
+#pragma unroll
+        for (int p = 0; p < 4; p++) fan_triangle(Xq[p], Xq[(p + 1) & 3], Pq[p], Pq[(p + 1) & 3], centre, cf, minus, G, V);
+        return;
+    }
     double centre[3] = {0.0, 0.0, 0.0}, cf[3] = {0.0, 0.0, 0.0};
     for (int p = 0; p < n; p++)
     {
@@ -351,35 +431,35 @@ __device__ void grad_face(const MeshDev& M, int f, const double* __restrict__ pf
     const double dn = (double)n;
 #pragma unroll
     for (int d = 0; d < 3; d++) { centre[d] = dvd(centre[d], dn); cf[d] = dvd(cf[d], dn); }
+    double Xa[3], Pa[3], Xb[3], Pb[3];
+    load3(X, fp[0], Xa); load3(pf, fp[0], Pa);
     for (int p = 0; p < n; p++)
     {
-        const int ia = fp[p], ib = fp[(p + 1) % n];
-        double ttcf[3], a[3], b[3], St[3], Ct[3];
+        const int ib = fp[(p + 1 == n) ? 0 : p + 1];
+        load3(X, ib, Xb); load3(pf, ib, Pb);
+        fan_triangle(Xa, Xb, Pa, Pb, centre, cf, minus, G, V);
 #pragma unroll
-        for (int d = 0; d < 3; d++)
-        {
-            ttcf[d] = dvd(add(add(pf[3*ia + d], pf[3*ib + d]), cf[d]), 3.0);
-            a[d] = sub(X[3*ia + d], centre[d]);
-            b[d] = sub(X[3*ib + d], centre[d]);
-        }
-        cross3(a, b, St);
-#pragma unroll
-        for (int d = 0; d < 3; d++)
-        {
-            St[d] = dvd(St[d], 2.0);
-            Ct[d] = dvd(add(add(centre[d], X[3*ia + d]), X[3*ib + d]), 3.0);
-        }
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int j = 0; j < 3; j++)
-            {
-                const double t = mul(St[i], ttcf[j]);
-                G[3*i + j] = minus ? sub(G[3*i + j], t) : add(G[3*i + j], t);
-            }
-        const double sc = dot3(St, Ct);
-        V = minus ? sub(V, sc) : add(V, sc);
+        for (int d = 0; d < 3; d++) { Xa[d] = Xb[d]; Pa[d] = Pb[d]; }
     }
+}
+
+// one edge (s -> e) of a face: Le*fe into G   (fvcGradf.C:97-142)
+__device__ __forceinline__ void tangential_edge(const double* Xs, const double* Xe, const double* Ps, const double* Pe,
+                                                const double* nf, double* G)
+{
+    double e[3], Le[3], fe[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) e[d] = sub(Xe[d], Xs[d]);
+    const double ne = dot3(nf, e);
+#pragma unroll
+    for (int d = 0; d < 3; d++) e[d] = sub(e[d], mul(nf[d], ne));
+    cross3(e, nf, Le);
+#pragma unroll
+    for (int d = 0; d < 3; d++) fe[d] = mul(0.5, add(Ps[d], Pe[d]));
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) G[3*i + j] = add(G[3*i + j], mul(Le[i], fe[j]));
 }
 
 // tangential face gradient from point values: sum_edges Le*fe / mag   (fvcGradf.C:97-142, 144-198, 410-482)
@@ -394,22 +474,34 @@ __device__ void face_tangential_grad(const MeshDev& M, int f, const double* __re
     for (int d = 0; d < 3; d++) nf[d] = dvd(M.Sf[3*(size_t)f + d], magSf);
 #pragma unroll
     for (int k = 0; k < 9; k++) G[k] = 0.0;
-    for (int p = 0; p < n; p++)
+    if (n == 4)
     {
-        const int s = fp[p], e_ = fp[(p + 1) % n];
-        double e[3], Le[3], fe[3];
+        double Xq[4][3], Pq[4][3];
 #pragma unroll
-        for (int d = 0; d < 3; d++) e[d] = sub(X[3*e_ + d], X[3*s + d]);
-        const double ne = dot3(nf, e);
+        for (int p = 0; p < 4; p++) { const int ip = fp[p]; load3(X, ip, Xq[p]); load3(pf, ip, Pq[p]); }
 #pragma unroll
-        for (int d = 0; d < 3; d++) e[d] = sub(e[d], mul(nf[d], ne));
-        cross3(e, nf, Le);
+        for (int p = 0; p < 4; p++) tangential_edge(Xq[p], Xq[(p + 1) & 3], Pq[p], Pq[(p + 1) & 3], nf, G);
+    }
+    else if (n == 3)
+    {
+        double Xq[3][3], Pq[3][3];
 #pragma unroll
-        for (int d = 0; d < 3; d++) fe[d] = mul(0.5, add(pf[3*s + d], pf[3*e_ + d]));
+        for (int p = 0; p < 3; p++) { const int ip = fp[p]; load3(X, ip, Xq[p]); load3(pf, ip, Pq[p]); }
 #pragma unroll
-        for (int i = 0; i < 3; i++)
+        for (int p = 0; p < 3; p++) tangential_edge(Xq[p], Xq[(p + 1) % 3], Pq[p], Pq[(p + 1) % 3], nf, G);
+    }
+    else
+    {
+        double Xs[3], Ps[3], Xe[3], Pe[3];
+        load3(X, fp[0], Xs); load3(pf, fp[0], Ps);
+        for (int p = 0; p < n; p++)
+        {
+            const int ie = fp[(p + 1 == n) ? 0 : p + 1];
+            load3(X, ie, Xe); load3(pf, ie, Pe);
+            tangential_edge(Xs, Xe, Ps, Pe, nf, G);
 #pragma unroll
-            for (int j = 0; j < 3; j++) G[3*i + j] = add(G[3*i + j], mul(Le[i], fe[j]));
+            for (int d = 0; d < 3; d++) { Xs[d] = Xe[d]; Ps[d] = Pe[d]; }
+        }
     }
 #pragma unroll
     for (int k = 0; k < 9; k++) G[k] = dvd(G[k], magSf);
@@ -454,7 +546,7 @@ __global__ void __launch_bounds__(ATPB) k_grad_cells(MeshDev M, const double* __
             const int code = M.cellFace[k];
             grad_face(M, code & 0x7fffffff, pointD, code < 0, G, V);
         }
-        V = dvd(V, 3.0);
+        V = div3(V);
 #pragma unroll
         for (int q = 0; q < 9; q++) gradD[9*(size_t)c + q] = dvd(G[q], V);
     }
