@@ -13,7 +13,10 @@
 #include "../../include/gpupcg.h"
 
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdio>
+#include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -90,14 +93,21 @@ __device__ void symmetry_snGrad(const MeshDev& M, int f, const double* __restric
     for (int d = 0; d < 3; d++) sn[d] = mul(sub(tv[d], UP[d]), h);
 }
 
-__global__ void __launch_bounds__(ATPB) k_asm_faces(MeshDev M, const double* __restrict__ mu, const double* __restrict__ lambda,
+// One chunk of the assembly (see AsmChunk): slot s of the chunk's flux ring is internal face f0 + s for s < nOwn (the
+// faces the chunk's cells own), then the chunk's extra faces: internal faces owned by an EARLIER chunk whose neighbour
+// cell is in this chunk (recomputed here: 1-2 % of the faces), then the boundary faces of the chunk's cells.
+struct AsmChunk { int c0, c1, f0, nOwn, extraStart, nExtra; };
+
+__global__ void __launch_bounds__(ATPB) k_asm_faces(MeshDev M, AsmChunk K, const int* __restrict__ extraFace,
+                                                    const double* __restrict__ mu, const double* __restrict__ lambda,
                                                     const double* __restrict__ D, const double* __restrict__ gradD,
                                                     const double* __restrict__ gradDf, double limitCoeff,
                                                     double* __restrict__ upper, double* __restrict__ Lup, double* __restrict__ gms,
                                                     double* __restrict__ fluxE, double* __restrict__ fluxC)
 {
-    for (int f = blockIdx.x*ATPB + threadIdx.x; f < M.nFaces; f += gridDim.x*ATPB)
+    for (int sl = blockIdx.x*ATPB + threadIdx.x; sl < K.nOwn + K.nExtra; sl += gridDim.x*ATPB)
     {
+        const int f = (sl < K.nOwn) ? K.f0 + sl : extraFace[K.extraStart + sl - K.nOwn];
         const int P = M.owner[f];
         const bool internal = f < M.nIF;
         const int N = internal ? M.neighbour[f] : P;
@@ -110,7 +120,7 @@ __global__ void __launch_bounds__(ATPB) k_asm_faces(MeshDev M, const double* __r
         }
         else { muf = mu[P]; laf = lambda[P]; }
         const double g = mul(add(mul(2.0, muf), laf), M.magSf[f]);
-        gms[f] = g;
+        if (!internal) gms[f] = g;                  // k_asm_patches reads it
         double Sf[3] = {M.Sf[3*f], M.Sf[3*f + 1], M.Sf[3*f + 2]};
         // explicit stress flux: Sf & ( -(muf+lambdaf)*G + muf*G.T() + lambdaf*(I*tr(G)) )
         {
@@ -126,14 +136,14 @@ __global__ void __launch_bounds__(ATPB) k_asm_faces(MeshDev M, const double* __r
             T[6] = add(mul(a, G[6]), mul(muf, G[2])); T[7] = add(mul(a, G[7]), mul(muf, G[5])); T[8] = add(add(mul(a, G[8]), mul(muf, G[8])), sph);
             double fl[3];
             vdotT(Sf, T, fl);
-            fluxE[3*(size_t)f] = fl[0]; fluxE[3*(size_t)f + 1] = fl[1]; fluxE[3*(size_t)f + 2] = fl[2];
+            fluxE[3*(size_t)sl] = fl[0]; fluxE[3*(size_t)sl + 1] = fl[1]; fluxE[3*(size_t)sl + 2] = fl[2];
         }
         if (internal)
         {
             const double dc = M.deltaCoeffs[f];
             const double up = mul(dc, g);
-            Lup[f] = up;
-            upper[f] = sub(0.0, up);
+            Lup[sl] = up;
+            if (sl < K.nOwn) upper[f] = sub(0.0, up);
             // skewCorrectedSnGrad<vector>::correction
             const double Cf[3] = {M.Cf[3*f], M.Cf[3*f + 1], M.Cf[3*f + 2]};
             const double magSqrSf = add(add(mul(Sf[0], Sf[0]), mul(Sf[1], Sf[1])), mul(Sf[2], Sf[2]));
@@ -163,31 +173,34 @@ __global__ void __launch_bounds__(ATPB) k_asm_faces(MeshDev M, const double* __r
             double lim = dvd(mul(limitCoeff, mag3(t)), add(mul(sub(1.0, limitCoeff), mag3(ssf)), A_SMALL));
             if (lim > 1.0) lim = 1.0;
 #pragma unroll
-            for (int d = 0; d < 3; d++) fluxC[3*(size_t)f + d] = mul(g, mul(ssf[d], lim));
+            for (int d = 0; d < 3; d++) fluxC[3*(size_t)sl + d] = mul(g, mul(ssf[d], lim));
         }
     }
 }
 
-__global__ void __launch_bounds__(ATPB) k_asm_cells(MeshDev M, const double* __restrict__ rho, double g0, double g1, double g2,
+// cellSlot[k] (parallel to the cell -> face CSR): ring slot of the face | bit 31: the cell is the face's neighbour |
+// bit 30: boundary face
+__global__ void __launch_bounds__(ATPB) k_asm_cells(MeshDev M, AsmChunk K, const int* __restrict__ cellSlot,
+                                                    const double* __restrict__ rho, double g0, double g1, double g2,
                                                     const double* __restrict__ Lup, const double* __restrict__ fluxE,
                                                     const double* __restrict__ fluxC, double* __restrict__ diag,
                                                     double* __restrict__ source)
 {
-    for (int c = blockIdx.x*ATPB + threadIdx.x; c < M.nCells; c += gridDim.x*ATPB)
+    for (int c = K.c0 + blockIdx.x*ATPB + threadIdx.x; c < K.c1; c += gridDim.x*ATPB)
     {
         double Ld = 0.0, sE[3] = {0.0, 0.0, 0.0}, sC[3] = {0.0, 0.0, 0.0};
         for (int k = M.cellFaceStart[c]; k < M.cellFaceStart[c + 1]; k++)
         {
-            const int code = M.cellFace[k];
-            const int f = code & 0x7fffffff;
+            const int code = cellSlot[k];
+            const int sl = code & 0x3fffffff;
             const bool nbr = code < 0;
-            if (f < M.nIF)
+            if (!(code & 0x40000000))
             {
-                Ld = sub(Ld, Lup[f]);
+                Ld = sub(Ld, Lup[sl]);
 #pragma unroll
                 for (int d = 0; d < 3; d++)
                 {
-                    const double fc = fluxC[3*(size_t)f + d], fe = fluxE[3*(size_t)f + d];
+                    const double fc = fluxC[3*(size_t)sl + d], fe = fluxE[3*(size_t)sl + d];
                     sC[d] = nbr ? sub(sC[d], fc) : add(sC[d], fc);
                     sE[d] = nbr ? sub(sE[d], fe) : add(sE[d], fe);
                 }
@@ -195,7 +208,7 @@ __global__ void __launch_bounds__(ATPB) k_asm_cells(MeshDev M, const double* __r
             else
             {
 #pragma unroll
-                for (int d = 0; d < 3; d++) sE[d] = add(sE[d], fluxE[3*(size_t)f + d]);
+                for (int d = 0; d < 3; d++) sE[d] = add(sE[d], fluxE[3*(size_t)sl + d]);
             }
         }
         diag[c] = sub(0.0, Ld);
@@ -333,14 +346,6 @@ __device__ __forceinline__ double div3(double x)
     }
     return __ddiv_rn(x, 3.0);
 }
-// x/n for a face's point count: 4 and 2 are exact scalings, 3 the sequence above
-__device__ __forceinline__ double div_n(double x, int n, double dn)
-{
-    if (n == 4) return mul(x, 0.25);
-    if (n == 3) return div3(x);
-    return dvd(x, dn);
-}
-
 // one triangle (centre, a, b) of a face's fan: sign*(St*ttcf) into G, sign*(St & Ct) into V   (fvcGradf.C:541-610)
 __device__ __forceinline__ void fan_triangle(const double* Xa, const double* Xb, const double* Pa, const double* Pb,
                                              const double* centre, const double* cf, bool minus, double* G, double& V)
@@ -648,6 +653,10 @@ struct gpupcg_mesh_s
     double *dUpper = nullptr, *dLup = nullptr, *dGms = nullptr, *dFluxE = nullptr, *dFluxC = nullptr;
     double *dDiag = nullptr, *dSource = nullptr, *dIC = nullptr, *dBC = nullptr, *dEps = nullptr, *dSig = nullptr;
     double *dPointD = nullptr, *dGradOld = nullptr, *dPatchGrad = nullptr, *dGradDb = nullptr;
+    // chunked assembly: the per-face fluxes of one chunk live in a ring sized to stay in L2 between the face and the cell kernel
+    std::vector<AsmChunk> chunks;
+    const int *dExtraFace = nullptr, *dCellSlot = nullptr;
+    int ringSlots = 0;
 };
 
 static thread_local std::string g_meshErr;
@@ -732,6 +741,47 @@ extern "C" int gpupcg_mesh_create(gpupcg_mesh* out, int device, int nCells, int 
         cf[cur[neighbour[f]]++] = f | 0x80000000;
     }
     for (int f = nIF; f < nFaces; f++) cf[cur[owner[f]]++] = f;
+    // chunks of consecutive cells; ring slots of a chunk = owned internal faces, halo faces, boundary faces.
+    // Default: ONE chunk.  Chunks small enough for the flux ring to stay in L2 between the face and the cell kernel
+    // were measured (GPUPCG_ASM_CHUNK_CELLS, with and without a persisting-L2 access window on the ring) and lose to
+    // the extra launches and tails at 1 M and 8 M cells: profiles/r1c_assembly_gradients.md.
+    std::vector<int> extraFace, cellSlot(cf.size(), 0);
+    {
+        const char* ev = getenv("GPUPCG_ASM_CHUNK_CELLS");
+        const int chunkCells = std::max(32, ev && *ev ? atoi(ev) : 0x3fffffff);
+        std::vector<int> ownStart(nCells + 1, 0);                  // first internal face owned by cell c
+        for (int f = 0; f < nIF; f++) ownStart[owner[f] + 1]++;
+        for (int c = 0; c < nCells; c++) ownStart[c + 1] += ownStart[c];
+        const int nChunks = (nCells + chunkCells - 1)/chunkCells;
+        std::vector<std::vector<int> > halo(nChunks), bnd(nChunks);
+        for (int f = 0; f < nIF; f++)
+        {
+            const int ko = owner[f]/chunkCells, kn = neighbour[f]/chunkCells;
+            if (kn != ko) halo[kn].push_back(f);
+        }
+        for (int f = nIF; f < nFaces; f++) bnd[owner[f]/chunkCells].push_back(f);
+        std::vector<int> slotOf(nFaces, -1);                        // scratch: slot of face f inside the chunk being numbered
+        for (int k = 0; k < nChunks; k++)
+        {
+            AsmChunk K;
+            K.c0 = k*chunkCells; K.c1 = std::min(nCells, K.c0 + chunkCells);
+            K.f0 = ownStart[K.c0]; K.nOwn = ownStart[K.c1] - K.f0;
+            K.extraStart = (int)extraFace.size();
+            for (int f : halo[k]) { slotOf[f] = K.nOwn + (int)extraFace.size() - K.extraStart; extraFace.push_back(f); }
+            for (int f : bnd[k]) { slotOf[f] = K.nOwn + (int)extraFace.size() - K.extraStart; extraFace.push_back(f); }
+            K.nExtra = (int)extraFace.size() - K.extraStart;
+            m->ringSlots = std::max(m->ringSlots, K.nOwn + K.nExtra);
+            for (int c = K.c0; c < K.c1; c++)
+                for (int e = start[c]; e < start[c + 1]; e++)
+                {
+                    const int f = cf[e] & 0x7fffffff;
+                    const int sl = (f < nIF && f >= K.f0 && f < K.f0 + K.nOwn) ? f - K.f0 : slotOf[f];
+                    cellSlot[e] = sl | (cf[e] & 0x80000000) | (f >= nIF ? 0x40000000 : 0);
+                }
+            m->chunks.push_back(K);
+        }
+        if (m->ringSlots >= 0x40000000) { g_meshErr = "gpupcg_mesh_create: assembly chunk too large"; delete m; return GPUPCG_ERR_ARG; }
+    }
     std::vector<int> bft(nBF > 0 ? nBF : 1, 0);
     for (int p = 0; p < nPatches; p++)
         for (int i = 0; i < patchSize[p]; i++) bft[patchStart[p] + i - nIF] = patchType[p];
@@ -739,14 +789,20 @@ extern "C" int gpupcg_mesh_create(gpupcg_mesh* out, int device, int nCells, int 
     M.nCells = nCells; M.nFaces = nFaces; M.nIF = nIF; M.nPatches = nPatches;
     MCK(up(m, M.owner, owner, nFaces)); MCK(up(m, M.neighbour, neighbour, nIF)); MCK(up(m, M.bfPatchType, bft.data(), nBF));
     MCK(up(m, M.cellFaceStart, start.data(), nCells + 1)); MCK(up(m, M.cellFace, cf.data(), cf.size()));
+    MCK(up(m, m->dExtraFace, extraFace.data(), extraFace.size())); MCK(up(m, m->dCellSlot, cellSlot.data(), cellSlot.size()));
     MCK(up(m, M.Sf, Sf, 3*(size_t)nFaces)); MCK(up(m, M.magSf, magSf, nFaces)); MCK(up(m, M.Cf, Cf, 3*(size_t)nFaces));
     MCK(up(m, M.C, C, 3*(size_t)nCells)); MCK(up(m, M.V, V, nCells)); MCK(up(m, M.weights, weights, nIF));
     MCK(up(m, M.deltaCoeffs, deltaCoeffs, nFaces));
     MCK(alloc(m, m->dMu, nCells)); MCK(alloc(m, m->dLambda, nCells)); MCK(alloc(m, m->dRho, nCells));
     MCK(alloc(m, m->dD, 3*(size_t)nCells)); MCK(alloc(m, m->dGradD, 9*(size_t)nCells)); MCK(alloc(m, m->dGradDf, 9*(size_t)nFaces));
     MCK(alloc(m, m->dTraction, 3*(size_t)nBF)); MCK(alloc(m, m->dPressure, nBF)); MCK(alloc(m, m->dFixed, 3*(size_t)nBF));
-    MCK(alloc(m, m->dUpper, nIF)); MCK(alloc(m, m->dLup, nIF)); MCK(alloc(m, m->dGms, nFaces));
-    MCK(alloc(m, m->dFluxE, 3*(size_t)nFaces)); MCK(alloc(m, m->dFluxC, 3*(size_t)nIF));
+    MCK(alloc(m, m->dUpper, nIF)); MCK(alloc(m, m->dGms, nFaces));
+    {
+        // one allocation for the ring {fluxE, fluxC, Lup}: 56 B per slot
+        double* ring = nullptr;
+        MCK(alloc(m, ring, 7*(size_t)std::max(1, m->ringSlots)));
+        m->dFluxE = ring; m->dFluxC = ring + 3*(size_t)m->ringSlots; m->dLup = ring + 6*(size_t)m->ringSlots;
+    }
     MCK(alloc(m, m->dDiag, nCells)); MCK(alloc(m, m->dSource, 3*(size_t)nCells));
     MCK(alloc(m, m->dIC, 3*(size_t)nBF)); MCK(alloc(m, m->dBC, 3*(size_t)nBF));
     MCK(alloc(m, m->dEps, 6*(size_t)nCells)); MCK(alloc(m, m->dSig, 6*(size_t)nCells));
@@ -776,9 +832,13 @@ extern "C" int gpupcg_assemble_D(gpupcg_mesh m, const double* mu, const double* 
     MCK(cudaEventRecord(m->ev0, s));
     for (int r = 0; r < reps; r++)
     {
-        k_asm_faces<<<agrid(m, nF), ATPB, 0, s>>>(M, m->dMu, m->dLambda, m->dD, m->dGradD, m->dGradDf, limitCoeff,
-                                                  m->dUpper, m->dLup, m->dGms, m->dFluxE, m->dFluxC);
-        k_asm_cells<<<agrid(m, nC), ATPB, 0, s>>>(M, m->dRho, g[0], g[1], g[2], m->dLup, m->dFluxE, m->dFluxC, m->dDiag, m->dSource);
+        for (const AsmChunk& K : m->chunks)
+        {
+            k_asm_faces<<<agrid(m, K.nOwn + K.nExtra), ATPB, 0, s>>>(M, K, m->dExtraFace, m->dMu, m->dLambda, m->dD, m->dGradD, m->dGradDf,
+                                                                     limitCoeff, m->dUpper, m->dLup, m->dGms, m->dFluxE, m->dFluxC);
+            k_asm_cells<<<agrid(m, K.c1 - K.c0), ATPB, 0, s>>>(M, K, m->dCellSlot, m->dRho, g[0], g[1], g[2], m->dLup, m->dFluxE, m->dFluxC,
+                                                               m->dDiag, m->dSource);
+        }
         if (nBF > 0)
             k_asm_patches<<<agrid(m, nBF), ATPB, 0, s>>>(M, m->dMu, m->dLambda, m->dD, m->dGradD, m->dGradDf, m->dGms, m->dTraction,
                                                          m->dPressure, m->dFixed, m->dIC, m->dBC);
