@@ -50,6 +50,8 @@ struct gpupcg_handle_s
     long long traceLen = 0;
     DevState* hStateRing = nullptr;     // pinned, two snapshots of the device state (pipelined host loop)
     cudaEvent_t evCheck[2] = {nullptr, nullptr};
+    cudaStream_t commStream = nullptr;  // halo swaps, overlapped with the interior Amul (multi-rank only)
+    cudaEvent_t evX = nullptr, evHalo = nullptr;
     int amulGrid = 1;               // persistent CTAs of the Amul kernel
     bool hasOvf = false;            // some row has more than four faces on one side (polyhedral cells)
     int partStride = MAXPART;
@@ -172,6 +174,9 @@ extern "C" int gpupcg_destroy(gpupcg_handle h)
     if (h->hState) cudaFreeHost(h->hState);
     if (h->hStateRing) cudaFreeHost(h->hStateRing);
     for (auto& e : h->evCheck) if (e) cudaEventDestroy(e);
+    if (h->evX) cudaEventDestroy(h->evX);
+    if (h->evHalo) cudaEventDestroy(h->evHalo);
+    if (h->commStream) cudaStreamDestroy(h->commStream);
     if (h->hHistory) cudaFreeHost(h->hHistory);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->ownStream) cudaStreamDestroy(h->ownStream);
@@ -586,12 +591,25 @@ static inline void fill_sent(gpupcg_handle h, double* p)
 }
 
 // halo: gather x[faceCells] -> exchange -> dXNbr.  Single rank: nothing to do.
-static int halo_exchange(gpupcg_handle h, const double* x)
+// The swap runs on the side stream h->commStream (processorFvPatchField::initInterfaceMatrixUpdate posts the
+// sends before the interior Amul in the reference too): it starts when x is ready on the main stream (evX), the
+// interior rows' Amul runs meanwhile on the main stream, and k_iface_update waits for evHalo.
+static int halo_exchange(gpupcg_handle h, const double* x, bool* overlapped)
 {
     const HostPlan& P = h->plan;
+    *overlapped = false;
     if (!h->comm.active() || P.nIfaceFaces == 0) return GPUPCG_OK;
-    LAUNCH(k_iface_gather, grid_for(P.nIfaceFaces, h->streamGrid), h->stream, x, h->dIfFaceRow, h->dSend, P.nIfaceFaces);
-    if (h->comm.exchange(h->dSend, h->dXNbr, P.patchStart, P.patchNbrRank, h->stream, h->err) != 0) return GPUPCG_ERR_NCCL;
+    cudaStream_t cs = h->stream;
+    if (h->commStream)
+    {
+        cs = h->commStream;
+        CK(cudaEventRecord(h->evX, h->stream));
+        CK(cudaStreamWaitEvent(cs, h->evX, 0));
+        *overlapped = true;
+    }
+    LAUNCH(k_iface_gather, grid_for(P.nIfaceFaces, h->streamGrid), cs, x, h->dIfFaceRow, h->dSend, P.nIfaceFaces);
+    if (h->comm.exchange(h->dSend, h->dXNbr, P.patchStart, P.patchNbrRank, cs, h->err) != 0) return GPUPCG_ERR_NCCL;
+    if (*overlapped) { CK(cudaEventRecord(h->evHalo, cs)); }
     return GPUPCG_OK;
 }
 
@@ -611,7 +629,8 @@ static int enqueue_amul(gpupcg_handle h, int mode, const double* x, double* Ax, 
     cudaStream_t s = h->stream;
     const bool ifaces = P.nIfaceFaces > 0;
     int rc;
-    if (ifaces && mode != 2 && !xNbrReady) { rc = halo_exchange(h, x); if (rc) return rc; }
+    bool haloInFlight = false;
+    if (ifaces && mode != 2 && !xNbrReady) { rc = halo_exchange(h, x, &haloInFlight); if (rc) return rc; }
     const unsigned int* mask = (ifaces && mode == 1) ? h->dIfMask : nullptr;
     if (P.nTiles > 0)
     {
@@ -625,6 +644,7 @@ static int enqueue_amul(gpupcg_handle h, int mode, const double* x, double* Ax, 
     }
     if (ifaces)
     {
+        if (haloInFlight) { CK(cudaStreamWaitEvent(s, h->evHalo, 0)); }
         const int gi = grid_for(h->nIfRows, h->streamGrid);
         if (mode == 1)
             LAUNCH(k_iface_update<1>, gi, s, h->dIfRow, h->dIfRowStart, h->dIfEntry, h->nIfRows, h->dBou, h->dXNbr, 0, x, Ax, h->dPartials, h->dState, 1);
@@ -970,5 +990,11 @@ extern "C" int gpupcg_comm_init(gpupcg_handle h, int rank, int nRanks, const voi
     if (!h || !id128 || rank < 0 || rank >= nRanks) return GPUPCG_ERR_ARG;
     CK(cudaSetDevice(h->device));
     if (h->comm.init(rank, nRanks, id128, h->plan.nCells, h->stream, h->err) != 0) return GPUPCG_ERR_NCCL;
+    if (!h->commStream && env_int("GPUPCG_OVERLAP_HALO", 1))
+    {
+        CK(cudaStreamCreateWithFlags(&h->commStream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->evX, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->evHalo, cudaEventDisableTiming));
+    }
     return GPUPCG_OK;
 }
