@@ -83,6 +83,8 @@ SYMBOLS = {
     "gpupcg_mesh_last_error": (C.c_char_p, [C.c_void_p]),
     "gpupcg_assemble_D": (C.c_int, [C.c_void_p] + [c_double_p]*10 + [C.c_double, C.c_int] + [c_double_p]*6),
     "gpupcg_sigma": (C.c_int, [C.c_void_p] + [c_double_p]*5),
+    "gpupcg_patch_gradient": (C.c_int, [C.c_void_p, c_double_p]),
+    "gpupcg_relax_residual": (C.c_int, [C.c_void_p, C.c_double, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "gpupcg_mesh_set_points": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_int_p, c_int_p]),
     "gpupcg_gradients": (C.c_int, [C.c_void_p] + [c_double_p]*5 + [C.c_double, C.c_int] + [c_double_p]*4),
     "gpupcg_host_register": (C.c_int, [C.c_void_p, C.c_ulonglong]),
@@ -309,12 +311,26 @@ class GpuMesh(object):
             self._points = (_f64(self.mesh.points), _i32(self.mesh.faceStart), _i32(self.mesh.facePoints))
             self._check(self.lib.gpupcg_mesh_set_points(self.h, self.mesh.nPoints, _dp(self._points[0]),
                                                         _ip(self._points[1]), _ip(self._points[2])))
-        a = [_f64(v) for v in (D, pointD, gradDold, fixedValue, patchGradient)]
+        a = [_f64(v) if v is not None else None for v in (D, pointD, gradDold, fixedValue, patchGradient)]
         G = np.empty((self.nC, 9)); Gb = np.empty((self.nBF, 9)); Gf = np.empty((self.nF, 9))
         ms = C.c_double(0.0)
         self._check(self.lib.gpupcg_gradients(self.h, *[_dp(v) for v in a], float(limitCoeff), int(reps), _dp(G), _dp(Gb),
                                               _dp(Gf), C.byref(ms)))
         return G, Gb, Gf, ms.value
+
+    def patch_gradient(self):
+        """gradient() of the tractionDisplacement patches as the last assemble_D left it on the device."""
+        pg = np.empty((self.nBF, 3))
+        self._check(self.lib.gpupcg_patch_gradient(self.h, _dp(pg)))
+        return pg
+
+    def relax_residual(self, D, Dprev, Dold, alpha=None):
+        """D.relax(alpha) in place (skipped when alpha is None), then unsTotalLagrangianStress::residual()."""
+        assert D.dtype == np.float64 and D.flags.c_contiguous
+        res = C.c_double(0.0)
+        self._check(self.lib.gpupcg_relax_residual(self.h, float(alpha if alpha is not None else 1.0), 0 if alpha is None else 1,
+                                                   _dp(D), _dp(_f64(Dprev)), _dp(_f64(Dold)), C.byref(res)))
+        return res.value
 
     def sigma(self, mu, lam, gradD):
         eps = np.empty((self.nC, 6)); sig = np.empty((self.nC, 6))

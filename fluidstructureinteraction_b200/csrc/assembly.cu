@@ -230,7 +230,8 @@ __global__ void __launch_bounds__(ATPB) k_asm_patches(MeshDev M, const double* _
                                                       const double* __restrict__ gradD, const double* __restrict__ gradDf,
                                                       const double* __restrict__ gms, const double* __restrict__ traction,
                                                       const double* __restrict__ pressure, const double* __restrict__ fixedValue,
-                                                      double* __restrict__ internalCoeffs, double* __restrict__ boundaryCoeffs)
+                                                      double* __restrict__ internalCoeffs, double* __restrict__ boundaryCoeffs,
+                                                      double* __restrict__ patchGrad)
 {
     const int nBF = M.nFaces - M.nIF;
     for (int bf = blockIdx.x*ATPB + threadIdx.x; bf < nBF; bf += gridDim.x*ATPB)
@@ -289,6 +290,7 @@ __global__ void __launch_bounds__(ATPB) k_asm_patches(MeshDev M, const double* _
                 const double t = sub(traction[3*(size_t)bf + d], mul(pressure[bf], n[d]));
                 gIC[d] = 0.0;
                 gBC[d] = dvd(sub(sub(t, nT[d]), mul(mul(n[d], la), tr)), den);
+                patchGrad[3*(size_t)bf + d] = gBC[d];       // the patch's gradient(): fvc::fGrad reads it next
             }
         }
         const double g = gms[f];
@@ -636,6 +638,60 @@ __global__ void __launch_bounds__(ATPB) k_fgrad_faces(MeshDev M, const double* _
     }
 }
 
+// ---- outer-iteration algebra of evolve(): D.relax() and residual() --------------------------------------------------
+// D = prevIter + alpha*(D - prevIter)  [EXT GeometricField::relax]; per-block max of mag(D - Dold)   (max is exact)
+__global__ void __launch_bounds__(ATPB) k_relax_maxdd(int nCells, double alpha, int doRelax, double* __restrict__ D,
+                                                      const double* __restrict__ Dprev, const double* __restrict__ Dold,
+                                                      double* __restrict__ blockMax)
+{
+    __shared__ double sh[ATPB];
+    double mx = -1.0e300;
+    for (int c = blockIdx.x*ATPB + threadIdx.x; c < nCells; c += gridDim.x*ATPB)
+    {
+        double d[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+        {
+            double v = D[3*(size_t)c + k];
+            if (doRelax)
+            {
+                const double pv = Dprev[3*(size_t)c + k];
+                v = add(pv, mul(alpha, sub(v, pv)));
+                D[3*(size_t)c + k] = v;
+            }
+            d[k] = sub(v, Dold[3*(size_t)c + k]);
+        }
+        mx = fmax(mx, mag3(d));
+    }
+    sh[threadIdx.x] = mx;
+    __syncthreads();
+    for (int o = ATPB/2; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + o]); __syncthreads(); }
+    if (threadIdx.x == 0) blockMax[blockIdx.x] = sh[0];
+}
+
+// res = max_c mag(D - Dprev)/(maxDD + SMALL)   (unsTotalLagrangianStressSolve.C:647-672)
+__global__ void __launch_bounds__(ATPB) k_residual(int nCells, int nBlocksPrev, const double* __restrict__ D,
+                                                   const double* __restrict__ Dprev, const double* __restrict__ blockMaxDD,
+                                                   double* __restrict__ blockRes)
+{
+    __shared__ double sh[ATPB];
+    double maxDD = -1.0e300;
+    for (int i = 0; i < nBlocksPrev; i++) maxDD = fmax(maxDD, blockMaxDD[i]);
+    const double den = add(maxDD, A_SMALL);
+    double mx = -1.0e300;
+    for (int c = blockIdx.x*ATPB + threadIdx.x; c < nCells; c += gridDim.x*ATPB)
+    {
+        double d[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) d[k] = sub(D[3*(size_t)c + k], Dprev[3*(size_t)c + k]);
+        mx = fmax(mx, dvd(mag3(d), den));
+    }
+    sh[threadIdx.x] = mx;
+    __syncthreads();
+    for (int o = ATPB/2; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + o]); __syncthreads(); }
+    if (threadIdx.x == 0) blockRes[blockIdx.x] = sh[0];
+}
+
 } // namespace
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -653,6 +709,7 @@ struct gpupcg_mesh_s
     double *dUpper = nullptr, *dLup = nullptr, *dGms = nullptr, *dFluxE = nullptr, *dFluxC = nullptr;
     double *dDiag = nullptr, *dSource = nullptr, *dIC = nullptr, *dBC = nullptr, *dEps = nullptr, *dSig = nullptr;
     double *dPointD = nullptr, *dGradOld = nullptr, *dPatchGrad = nullptr, *dGradDb = nullptr;
+    double *dDprev = nullptr, *dDold = nullptr, *dRed = nullptr;
     // chunked assembly: the per-face fluxes of one chunk live in a ring sized to stay in L2 between the face and the cell kernel
     std::vector<AsmChunk> chunks;
     const int *dExtraFace = nullptr, *dCellSlot = nullptr;
@@ -805,6 +862,9 @@ extern "C" int gpupcg_mesh_create(gpupcg_mesh* out, int device, int nCells, int 
     }
     MCK(alloc(m, m->dDiag, nCells)); MCK(alloc(m, m->dSource, 3*(size_t)nCells));
     MCK(alloc(m, m->dIC, 3*(size_t)nBF)); MCK(alloc(m, m->dBC, 3*(size_t)nBF));
+    MCK(alloc(m, m->dPatchGrad, 3*(size_t)nBF));
+    MCK(cudaMemsetAsync(m->dPatchGrad, 0, sizeof(double)*3*(size_t)std::max(1, nBF), m->stream));
+    MCK(alloc(m, m->dDprev, 3*(size_t)nCells)); MCK(alloc(m, m->dDold, 3*(size_t)nCells)); MCK(alloc(m, m->dRed, 2*1024));
     MCK(alloc(m, m->dEps, 6*(size_t)nCells)); MCK(alloc(m, m->dSig, 6*(size_t)nCells));
     MCK(cudaStreamSynchronize(m->stream));
     *out = m;
@@ -841,7 +901,7 @@ extern "C" int gpupcg_assemble_D(gpupcg_mesh m, const double* mu, const double* 
         }
         if (nBF > 0)
             k_asm_patches<<<agrid(m, nBF), ATPB, 0, s>>>(M, m->dMu, m->dLambda, m->dD, m->dGradD, m->dGradDf, m->dGms, m->dTraction,
-                                                         m->dPressure, m->dFixed, m->dIC, m->dBC);
+                                                         m->dPressure, m->dFixed, m->dIC, m->dBC, m->dPatchGrad);
     }
     MCK(cudaEventRecord(m->ev1, s));
     MCK(cudaGetLastError());
@@ -872,6 +932,42 @@ extern "C" int gpupcg_sigma(gpupcg_mesh m, const double* mu, const double* lambd
 }
 
 
+// gradient() of the tractionDisplacement patches as the last gpupcg_assemble_D left it (0 on other patches)
+extern "C" int gpupcg_patch_gradient(gpupcg_mesh m, double* patchGradient)
+{
+    if (!m || !patchGradient) return GPUPCG_ERR_ARG;
+    const int nBF = m->M.nFaces - m->M.nIF;
+    MCK(cudaSetDevice(m->device));
+    MCK(cudaMemcpyAsync(patchGradient, m->dPatchGrad, sizeof(double)*3*(size_t)nBF, cudaMemcpyDeviceToHost, m->stream));
+    MCK(cudaStreamSynchronize(m->stream));
+    return GPUPCG_OK;
+}
+
+// D.relax(alpha) (relax != 0) followed by unsTotalLagrangianStress::residual()
+extern "C" int gpupcg_relax_residual(gpupcg_mesh m, double alpha, int relax, double* D, const double* Dprev, const double* Dold,
+                                     double* residual)
+{
+    if (!m || !D || !Dprev || !Dold || !residual) return GPUPCG_ERR_ARG;
+    const int nC = m->M.nCells;
+    MCK(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+    MCK(cudaMemcpyAsync(m->dD, D, sizeof(double)*3*(size_t)nC, cudaMemcpyHostToDevice, s));
+    MCK(cudaMemcpyAsync(m->dDprev, Dprev, sizeof(double)*3*(size_t)nC, cudaMemcpyHostToDevice, s));
+    MCK(cudaMemcpyAsync(m->dDold, Dold, sizeof(double)*3*(size_t)nC, cudaMemcpyHostToDevice, s));
+    const int nb = std::min(1024, agrid(m, nC));
+    k_relax_maxdd<<<nb, ATPB, 0, s>>>(nC, alpha, relax, m->dD, m->dDprev, m->dDold, m->dRed);
+    k_residual<<<nb, ATPB, 0, s>>>(nC, nb, m->dD, m->dDprev, m->dRed, m->dRed + 1024);
+    MCK(cudaGetLastError());
+    std::vector<double> part(nb);
+    if (relax) MCK(cudaMemcpyAsync(D, m->dD, sizeof(double)*3*(size_t)nC, cudaMemcpyDeviceToHost, s));
+    MCK(cudaMemcpyAsync(part.data(), m->dRed + 1024, sizeof(double)*nb, cudaMemcpyDeviceToHost, s));
+    MCK(cudaStreamSynchronize(s));
+    double r = -1.0e300;
+    for (int i = 0; i < nb; i++) r = std::max(r, part[i]);
+    *residual = r;
+    return GPUPCG_OK;
+}
+
 extern "C" int gpupcg_mesh_set_points(gpupcg_mesh m, int nPoints, const double* points, const int* faceStart, const int* facePoints)
 {
     if (!m || nPoints < 0 || !points || !faceStart || !facePoints) return GPUPCG_ERR_ARG;
@@ -883,7 +979,7 @@ extern "C" int gpupcg_mesh_set_points(gpupcg_mesh m, int nPoints, const double* 
     MCK(up(m, M.facePoints, facePoints, (size_t)faceStart[M.nFaces]));
     const int nBF = M.nFaces - M.nIF;
     MCK(alloc(m, m->dPointD, 3*(size_t)nPoints)); MCK(alloc(m, m->dGradOld, 9*(size_t)M.nCells));
-    MCK(alloc(m, m->dPatchGrad, 3*(size_t)nBF)); MCK(alloc(m, m->dGradDb, 9*(size_t)nBF));
+    MCK(alloc(m, m->dGradDb, 9*(size_t)nBF));
     MCK(cudaStreamSynchronize(m->stream));
     return GPUPCG_OK;
 }

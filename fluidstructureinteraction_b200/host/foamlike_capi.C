@@ -1,6 +1,7 @@
 // C entry points so that the Python tests can drive the C++ host side (stand-in API + adaptor + segregated solve)
 // exactly the way foam-extend would: dictionary text -> lduMatrix::solver::New -> solve.
 #include "segregatedSolve.H"
+#include "stressModelEvolve.H"
 #include "../foam/gpuPCG/gpuPCG.H"
 
 #include <cstring>
@@ -85,4 +86,54 @@ extern "C" int foamlike_dict_lookup(const char* text, const char* key, char* out
         return 0;
     }
     catch (const Foam::error& e) { g_lastError = e.what(); return -1; }
+}
+
+
+// One time step of the solid model (unsTotalLagrangianStress::evolve(), linear elastic, steadyState) on the GPU.
+// ints:  [nCells, nFaces, nInternalFaces, nPatches, nPoints, device];  meshInts: owner, neighbour, patchStart, patchSize,
+// patchType, faceStart, facePoints;  meshReals: Sf, magSf, Cf, C, V, weights, deltaCoeffs, points;
+// fields: mu, lambda, rho, g[3], traction, pressure, fixedValue;  D/Dold in-out start values (D.oldTime() = Dold).
+// out: D, pointD, gradD, gradDf, epsilon, sigma; result = {converged, nOuter, initialResidual, lastSolverInitialResidual,
+// maxRes, res, totalPcgIterations}; history[historyCap] = relative residual of every outer iteration.
+extern "C" int foamlike_evolve(const int* ints, const int* const* meshInts, const double* const* meshReals,
+                               const double* const* fields, double limitCoeff, const char* stressPropertiesText,
+                               const char* solverDictText, double relaxD, Foam::volToPointFn interpolate, void* ctx,
+                               double* D, const double* Dold, double* pointD, double* gradD, double* gradDf,
+                               double* epsilon, double* sigma, double* result, double* history, int historyCap)
+{
+    try
+    {
+        lduMatrix::debug = 0;
+        solidMeshData M;
+        M.nCells = ints[0]; M.nFaces = ints[1]; M.nInternalFaces = ints[2]; M.nPatches = ints[3]; M.nPoints = ints[4];
+        M.owner = meshInts[0]; M.neighbour = meshInts[1]; M.patchStart = meshInts[2]; M.patchSize = meshInts[3];
+        M.patchType = meshInts[4]; M.faceStart = meshInts[5]; M.facePoints = meshInts[6];
+        M.Sf = meshReals[0]; M.magSf = meshReals[1]; M.Cf = meshReals[2]; M.C = meshReals[3]; M.V = meshReals[4];
+        M.weights = meshReals[5]; M.deltaCoeffs = meshReals[6]; M.points = meshReals[7];
+        unsTotalLagrangianStressGpu model(M, ints[5], fields[0], fields[1], fields[2], fields[3], fields[4], fields[5],
+                                          fields[6], limitCoeff);
+        model.D.assign(D, D + 3*(size_t)M.nCells);
+        model.Dold.assign(Dold, Dold + 3*(size_t)M.nCells);
+        model.gradD.assign(gradD, gradD + 9*(size_t)M.nCells);
+        model.gradDf.assign(gradDf, gradDf + 9*(size_t)M.nFaces);
+        dictionary sp((std::string(stressPropertiesText))), sd((std::string(solverDictText)));
+        evolveResult R = model.evolve(sp, sd, relaxD, interpolate, ctx);
+        memcpy(D, model.D.data(), sizeof(double)*model.D.size());
+        memcpy(pointD, model.pointD.data(), sizeof(double)*model.pointD.size());
+        memcpy(gradD, model.gradD.data(), sizeof(double)*model.gradD.size());
+        memcpy(gradDf, model.gradDf.data(), sizeof(double)*model.gradDf.size());
+        memcpy(epsilon, model.epsilon.data(), sizeof(double)*model.epsilon.size());
+        memcpy(sigma, model.sigma.data(), sizeof(double)*model.sigma.size());
+        result[0] = R.converged; result[1] = R.nOuterIterations; result[2] = R.initialResidual;
+        result[3] = R.lastSolverInitialResidual; result[4] = R.maxRes; result[5] = R.res; result[6] = R.totalPcgIterations;
+        const int nh = std::min<int>(historyCap, (int)model.residualHistory.size());
+        for (int i = 0; i < nh; i++) history[i] = model.residualHistory[i];
+        return nh;
+    }
+    catch (const Foam::error& e)
+    {
+        g_lastError = e.what();
+        gpuPCG::clearCache();
+        return -1;
+    }
 }

@@ -1,0 +1,134 @@
+#include "stressModelEvolve.H"
+#include "../foam/gpuPCG/gpuPCG.H"
+
+#include <algorithm>
+
+#include <cstdlib>
+#include <sstream>
+
+namespace Foam
+{
+
+static void meshCheck(gpupcg_mesh m, int rc, const char* what)
+{
+    if (rc != 0)
+    {
+        std::ostringstream os;
+        os << what << " failed (" << rc << "): " << gpupcg_mesh_last_error(m);
+        FatalErrorIn("unsTotalLagrangianStressGpu") << os.str() << abort(FatalError);
+    }
+}
+
+unsTotalLagrangianStressGpu::unsTotalLagrangianStressGpu
+(
+    const solidMeshData& mesh, int device, const scalar* mu, const scalar* lambda, const scalar* rho, const scalar* g,
+    const scalar* traction, const scalar* pressure, const scalar* fixedValue, scalar limitCoeff
+)
+:
+    mesh_(mesh), gm_(0), mu_(mu, mu + mesh.nCells), lambda_(lambda, lambda + mesh.nCells), rho_(rho, rho + mesh.nCells),
+    limitCoeff_(limitCoeff)
+{
+    const int nBF = mesh.nFaces - mesh.nInternalFaces;
+    traction_.assign(traction, traction + 3*(size_t)nBF);
+    pressure_.assign(pressure, pressure + nBF);
+    fixedValue_.assign(fixedValue, fixedValue + 3*(size_t)nBF);
+    g_[0] = g[0]; g_[1] = g[1]; g_[2] = g[2];
+    int rc = gpupcg_mesh_create(&gm_, device, mesh.nCells, mesh.nFaces, mesh.nInternalFaces, mesh.owner, mesh.neighbour,
+                                mesh.nPatches, mesh.patchStart, mesh.patchSize, mesh.patchType, mesh.Sf, mesh.magSf, mesh.Cf,
+                                mesh.C, mesh.V, mesh.weights, mesh.deltaCoeffs);
+    meshCheck(gm_, rc, "gpupcg_mesh_create");
+    meshCheck(gm_, gpupcg_mesh_set_points(gm_, mesh.nPoints, mesh.points, mesh.faceStart, mesh.facePoints), "gpupcg_mesh_set_points");
+    D.assign(3*(size_t)mesh.nCells, 0.0);
+    Dold = D;
+    pointD.assign(3*(size_t)mesh.nPoints, 0.0);
+    gradD.assign(9*(size_t)mesh.nCells, 0.0);
+    gradDf.assign(9*(size_t)mesh.nFaces, 0.0);
+    epsilon.assign(6*(size_t)mesh.nCells, 0.0);
+    sigma = epsilon;
+}
+
+unsTotalLagrangianStressGpu::~unsTotalLagrangianStressGpu()
+{
+    if (gm_) gpupcg_mesh_destroy(gm_);
+}
+
+evolveResult unsTotalLagrangianStressGpu::evolve
+(
+    const dictionary& stressProperties, const dictionary& solverDict, scalar relaxD, volToPointFn interpolate, void* ctx
+)
+{
+    const int nCorr = atoi(std::string(stressProperties.lookup("nCorrectors")).c_str());
+    const scalar convergenceTolerance = atof(std::string(stressProperties.lookup("convergenceTolerance")).c_str());
+    scalar relConvergenceTolerance = 0;
+    if (stressProperties.found("relConvergenceTolerance"))
+        relConvergenceTolerance = atof(std::string(stressProperties.lookup("relConvergenceTolerance")).c_str());
+
+    const int nC = mesh_.nCells, nIF = mesh_.nInternalFaces, nBF = mesh_.nFaces - nIF;
+    labelList l(nIF), u(nIF);
+    for (int f = 0; f < nIF; f++) { l[f] = mesh_.owner[f]; u[f] = mesh_.neighbour[f]; }
+    lduAddressing addr(nC, l, u, std::vector<labelList>());
+    lduMatrix matrix(addr);
+    std::vector<scalar> upper(nIF), diag(nC), source(3*(size_t)nC), ic(3*(size_t)std::max(1, nBF)), bc(3*(size_t)std::max(1, nBF));
+    std::vector<scalar> Dprev(D.size()), gradDb(9*(size_t)std::max(1, nBF));
+
+    evolveResult R;
+    R.converged = 1; R.nOuterIterations = 0; R.initialResidual = 0; R.lastSolverInitialResidual = 0;
+    R.maxRes = 0; R.res = 1; R.totalPcgIterations = 0;
+    residualHistory.clear();
+
+    int iCorr = 0;
+    scalar res = 1, maxRes = 0, curConvergenceTolerance = convergenceTolerance;
+    do
+    {
+        Dprev = D;                                                      // D_.storePrevIter()
+
+        meshCheck(gm_, gpupcg_assemble_D(gm_, &mu_[0], &lambda_[0], &rho_[0], g_, &D[0], &gradD[0], &gradDf[0], &traction_[0],
+                                         &pressure_[0], &fixedValue_[0], limitCoeff_, 1, &upper[0], &diag[0], &source[0],
+                                         &ic[0], &bc[0], 0), "gpupcg_assemble_D");
+        for (int c = 0; c < nC; c++) matrix.diag()[c] = diag[c];
+        for (int f = 0; f < nIF; f++) matrix.upper()[f] = upper[f];
+        fvMatrixLike DEqn("D", 3, matrix);
+        DEqn.source = source;
+        for (int p = 0; p < mesh_.nPatches; p++)
+        {
+            fvPatchCoeffs pc;
+            const int n = mesh_.patchSize[p], b0 = mesh_.patchStart[p] - nIF;
+            pc.faceCells.setSize(n);
+            for (int i = 0; i < n; i++) pc.faceCells[i] = mesh_.owner[mesh_.patchStart[p] + i];
+            pc.internalCoeffs.assign(ic.begin() + 3*(size_t)b0, ic.begin() + 3*(size_t)(b0 + n));
+            pc.boundaryCoeffs.assign(bc.begin() + 3*(size_t)b0, bc.begin() + 3*(size_t)(b0 + n));
+            DEqn.patches.push_back(pc);
+        }
+        std::vector<lduMatrix::solverPerformance> per;
+        lduMatrix::solverPerformance solverPerf = DEqn.solve(D, solverDict, &per);      // DEqn.solve()
+        for (size_t k = 0; k < per.size(); k++) R.totalPcgIterations += per[k].nIterations();
+
+        if (iCorr == 0) R.initialResidual = solverPerf.initialResidual();
+        R.lastSolverInitialResidual = solverPerf.initialResidual();
+
+        // D_.relax();  ...  res = residual()   (the residual only reads D, prevIter and oldTime: evaluated with the relax)
+        meshCheck(gm_, gpupcg_relax_residual(gm_, relaxD, relaxD >= 0 ? 1 : 0, &D[0], &Dprev[0], &Dold[0], &res),
+                  "gpupcg_relax_residual");
+
+        interpolate(ctx, &D[0], &pointD[0]);                            // volToPoint_.interpolate(D_, pointD_)
+        {
+            std::vector<scalar> gradOld(gradD);
+            // patchGradient = NULL: the tractionDisplacement gradient() the assembly above left on the device
+            meshCheck(gm_, gpupcg_gradients(gm_, &D[0], &pointD[0], &gradOld[0], &fixedValue_[0], 0, limitCoeff_, 1,
+                                            &gradD[0], &gradDb[0], &gradDf[0], 0), "gpupcg_gradients");
+        }
+
+        if (res > maxRes) maxRes = res;
+        curConvergenceTolerance = maxRes*relConvergenceTolerance;
+        if (curConvergenceTolerance < convergenceTolerance) curConvergenceTolerance = convergenceTolerance;
+        residualHistory.push_back(res);
+    }
+    while (res > curConvergenceTolerance && ++iCorr < nCorr);
+
+    meshCheck(gm_, gpupcg_sigma(gm_, &mu_[0], &lambda_[0], &gradD[0], &epsilon[0], &sigma[0]), "gpupcg_sigma");
+    gpuPCG::clearCache();       // `addr` dies with this call
+    R.nOuterIterations = iCorr; R.maxRes = maxRes; R.res = res;
+    return R;
+}
+
+} // namespace Foam

@@ -45,6 +45,7 @@ def load():
                                        C.c_char_p, dp, C.POINTER(Perf), C.POINTER(Perf)]
         lib.foamlike_dict_lookup.restype = C.c_int
         lib.foamlike_dict_lookup.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+        lib.foamlike_evolve.restype = C.c_int
         _lib = lib
     return _lib
 
@@ -87,3 +88,50 @@ def solve(psiName, l, u, diag, upper, source, patches, solverDict, psi):
     if n < 0:
         raise FoamFatalError(lib.foamlike_last_error().decode())
     return worst.as_dict(), [per[k].as_dict() for k in range(n)]
+
+
+VOLTOPOINT = C.CFUNCTYPE(None, C.c_void_p, dp, dp)
+
+
+def evolve(mesh, geom, patchTypes, mu, lam, rho, g, traction, pressure, fixedValue, volToPoint, stressProperties, solverDict,
+           D=None, Dold=None, gradD=None, gradDf=None, limitCoeff=1.0, relaxD=None, device=0):
+    """One time step of the solid model: unsTotalLagrangianStress::evolve() (unsTotalLagrangianStress.C:769-1009) driven by
+    the C++ host side (host/stressModelEvolve.C) with assembly, PCG, relax/residual, gradients and stress on the GPU.
+    volToPoint(D (nC,3)) -> pointD (nP,3) stands in for leastSquaresVolPointInterpolation.
+    stressProperties / solverDict: dictionary text in foam syntax.  Returns a dict of fields and loop statistics."""
+    from .capi import PATCH_TYPES
+    lib = load()
+    nC, nF, nIF, nP = mesh.nCells, mesh.nFaces, mesh.nInternalFaces, mesh.nPoints
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    ps = i32([p["start"] for p in mesh.patches]); pz = i32([p["size"] for p in mesh.patches])
+    pt = i32([PATCH_TYPES[patchTypes[p["name"]]] for p in mesh.patches])
+    ints = i32([nC, nF, nIF, len(mesh.patches), nP, device])
+    mi = [i32(mesh.owner), i32(mesh.neighbour), ps, pz, pt, i32(mesh.faceStart), i32(mesh.facePoints)]
+    mr = [f64(geom.Sf), f64(geom.magSf), f64(geom.Cf), f64(geom.C), f64(geom.V), f64(geom.weights), f64(geom.deltaCoeffs),
+          f64(mesh.points)]
+    fl = [f64(mu), f64(lam), f64(rho), f64(g), f64(traction), f64(pressure), f64(fixedValue)]
+    MI = (ip*len(mi))(*[a.ctypes.data_as(ip) for a in mi])
+    MR = (dp*len(mr))(*[a.ctypes.data_as(dp) for a in mr])
+    FL = (dp*len(fl))(*[a.ctypes.data_as(dp) for a in fl])
+    Dv = f64(np.zeros((nC, 3)) if D is None else D).copy(); Do = f64(np.zeros((nC, 3)) if Dold is None else Dold)
+    pD = np.zeros((nP, 3)); G = f64(np.zeros((nC, 9)) if gradD is None else gradD).copy()
+    Gf = f64(np.zeros((nF, 9)) if gradDf is None else gradDf).copy()
+    eps = np.zeros((nC, 6)); sig = np.zeros((nC, 6)); res = np.zeros(8); hist = np.zeros(1024)
+
+    def cb(ctx, dptr, pptr):
+        Din = np.ctypeslib.as_array(dptr, shape=(nC, 3))
+        out = np.ctypeslib.as_array(pptr, shape=(nP, 3))
+        out[...] = volToPoint(Din)
+
+    cfn = VOLTOPOINT(cb)
+    n = lib.foamlike_evolve(ints.ctypes.data_as(ip), MI, MR, FL, C.c_double(limitCoeff), stressProperties.encode(),
+                            solverDict.encode(), C.c_double(-1.0 if relaxD is None else relaxD), cfn, None,
+                            Dv.ctypes.data_as(dp), Do.ctypes.data_as(dp), pD.ctypes.data_as(dp), G.ctypes.data_as(dp),
+                            Gf.ctypes.data_as(dp), eps.ctypes.data_as(dp), sig.ctypes.data_as(dp), res.ctypes.data_as(dp),
+                            hist.ctypes.data_as(dp), C.c_int(hist.shape[0]))
+    if n < 0:
+        raise FoamFatalError(lib.foamlike_last_error().decode())
+    return dict(D=Dv, pointD=pD, gradD=G, gradDf=Gf, epsilon=eps, sigma=sig, converged=bool(res[0]), nOuterIterations=int(res[1]),
+                initialResidual=res[2], lastSolverInitialResidual=res[3], maxRes=res[4], res=res[5],
+                totalPcgIterations=int(res[6]), residualHistory=hist[:n].copy())

@@ -171,7 +171,7 @@ int gpupcg_comm_init(gpupcg_handle h, int rank, int nRanks, const void* ncclUniq
  *   fvm::laplacian(2*muf+lambdaf, D) with the reference's `skewCorrected` snGrad scheme
  *   (skewCorrectedVectorSnGrad.C:50-294), fvc::div(Sf & (...gradDf...)), rho*g, and the boundary
  *   coefficients of tractionDisplacement (patchType 0) / fixedDisplacement (1) / symmetryDisplacement (2) patches
- *   (fvPatchFields/{tractionDisplacement,fixedDisplacement,symmetryDisplacement}/*.C).
+ *   (fvPatchFields/{tractionDisplacement,fixedDisplacement,symmetryDisplacement}/ *.C).
  * gpupcg_mesh_create uploads what foam-extend's fvMesh provides once per mesh: owner/neighbour, the patch
  * table and mesh.Sf(), magSf(), Cf(), C(), V(), weights(), deltaCoeffs() (boundary faces included).
  * gpupcg_assemble_D: per-cell mu, lambda, rho, D[3], gradD[9]; per-face gradDf[9]; per boundary face
@@ -200,6 +200,16 @@ int gpupcg_sigma(gpupcg_mesh m, const double* mu, const double* lambda, const do
  * (unsTotalLagrangianStress.C:925-926).  gpupcg_mesh_set_points uploads mesh.points() and the face point loops.
  * gradDold = the registered grad(D) at call time; patchGradient[nBoundaryFaces*3] = fixedGradient values of the
  * tractionDisplacement patches (what their last updateCoeffs set).                                              */
+/* gradient() of the tractionDisplacement patches as the last gpupcg_assemble_D left it on the device
+ * (tractionDisplacementFvPatchVectorField::updateCoeffs, :148-257); gpupcg_gradients uses it when its patchGradient
+ * argument is NULL -- the order of unsTotalLagrangianStress::evolve(): assemble, solve, then the gradients.         */
+int gpupcg_patch_gradient(gpupcg_mesh m, double* patchGradient);
+/* D.relax(alpha) (unsTotalLagrangianStress.C:910; skipped when relax == 0: no relaxationFactor for D in fvSolution)
+ * followed by unsTotalLagrangianStress::residual() (unsTotalLagrangianStressSolve.C:647-672):
+ *   maxDD = gMax(mag(D - D.oldTime()));  residual = gMax(mag(D - D.prevIter())/(maxDD + SMALL)).
+ * D[nCells*3] in/out (host), Dprev = D.prevIter(), Dold = D.oldTime().                                              */
+int gpupcg_relax_residual(gpupcg_mesh m, double alpha, int relax, double* D, const double* Dprev, const double* Dold,
+                          double* residual);
 int gpupcg_mesh_set_points(gpupcg_mesh m, int nPoints, const double* points, const int* faceStart, const int* facePoints);
 int gpupcg_gradients(gpupcg_mesh m, const double* D, const double* pointD, const double* gradDold,
                      const double* fixedValue, const double* patchGradient, double limitCoeff, int reps,

@@ -230,8 +230,19 @@ def assemble_D(mesh, geom, patchTypes, mu, lam, rho, g, D, gradD, gradDf, tracti
     a = [_f(v) for v in (mu, lam, rho, g, D, gradD, gradDf, traction, pressure, fixedValue)]
     nC, nIF, nBF = mesh.nCells, mesh.nInternalFaces, mesh.nFaces - mesh.nInternalFaces
     upper = np.empty(nIF); diag = np.empty(nC); source = np.empty((nC, 3)); ic = np.empty((nBF, 3)); bc = np.empty((nBF, 3))
-    lib.orc_assemble_D(C.byref(M), *[_dp(v) for v in a], float(limitCoeff), _dp(upper), _dp(diag), _dp(source), _dp(ic), _dp(bc))
-    return dict(upper=upper, diag=diag, source=source, internalCoeffs=ic, boundaryCoeffs=bc)
+    pg = np.zeros((nBF, 3))
+    lib.orc_assemble_D(C.byref(M), *[_dp(v) for v in a], float(limitCoeff), _dp(upper), _dp(diag), _dp(source), _dp(ic), _dp(bc), _dp(pg))
+    return dict(upper=upper, diag=diag, source=source, internalCoeffs=ic, boundaryCoeffs=bc, patchGradient=pg)
+
+
+def relax_residual(D, Dprev, Dold, alpha=None):
+    """D.relax(alpha) (skipped when alpha is None) then unsTotalLagrangianStress::residual(); D is updated in place."""
+    lib = load()
+    assert D.dtype == np.float64 and D.flags.c_contiguous
+    Dprev, Dold = _f(Dprev), _f(Dold)
+    lib.orc_relax_residual.restype = C.c_double
+    return float(lib.orc_relax_residual(C.c_int(D.shape[0]), C.c_double(alpha if alpha is not None else 1.0),
+                                        C.c_int(0 if alpha is None else 1), _dp(D), _dp(Dprev), _dp(Dold)))
 
 
 def sigma(mu, lam, gradD):

@@ -153,7 +153,8 @@ void orc_assemble_D
     const orc_mesh* M, const double* mu, const double* lambda, const double* rho, const double* g,
     const double* D, const double* gradD, const double* gradDf,
     const double* traction, const double* pressure, const double* fixedValue, double limitCoeff,
-    double* upper, double* diag, double* source, double* internalCoeffs, double* boundaryCoeffs
+    double* upper, double* diag, double* source, double* internalCoeffs, double* boundaryCoeffs,
+    double* patchGradient       /* optional [nBoundaryFaces*3]: gradient() of the tractionDisplacement patches after updateCoeffs */
 )
 {
     const int nC = M->nCells, nF = M->nFaces, nIF = M->nInternalFaces;
@@ -276,6 +277,7 @@ void orc_assemble_D
                     t[d] = traction[3*bf + d] - pressure[bf]*n[d];
                     gIC[d] = 0.0;
                     gBC[d] = ((t[d] - nT[d]) - n[d]*la*tr)/den;
+                    if (patchGradient) patchGradient[3*bf + d] = gBC[d];
                 }
             }
             for (int d = 0; d < 3; d++)
@@ -502,4 +504,33 @@ void orc_fgrad(const orc_mesh* M, const double* D, const double* pointD, const d
                 for (int b = 0; b < 3; b++) gradDf[9*(size_t)f + 3*a + b] += n[a]*sn[b];
         }
     }
+}
+
+
+/* GeometricField::relax(alpha) [EXT GeometricField.C]:  D = prevIter + alpha*(D - prevIter)   (unsTotalLagrangianStress.C:910)
+ * then unsTotalLagrangianStress::residual()  (unsTotalLagrangianStressSolve.C:647-672):
+ *   maxDD = gMax(mag(D - D.oldTime()));  res = gMax(mag(D - D.prevIter())/(maxDD + SMALL))                            */
+static double mag3o(const double* v) { return sqrt(v[0]*v[0] + v[1]*v[1] + v[2]*v[2]); }
+
+double orc_relax_residual(int nCells, double alpha, int doRelax, double* D, const double* Dprev, const double* Dold)
+{
+    if (doRelax)
+    {
+        for (int i = 0; i < 3*nCells; i++) D[i] = Dprev[i] + alpha*(D[i] - Dprev[i]);
+    }
+    double maxDD = -1.0e300;        /* gMax of an empty list is -VGREAT; never empty here */
+    for (int c = 0; c < nCells; c++)
+    {
+        const double d[3] = {D[3*c] - Dold[3*c], D[3*c + 1] - Dold[3*c + 1], D[3*c + 2] - Dold[3*c + 2]};
+        const double m = mag3o(d);
+        if (m > maxDD) maxDD = m;
+    }
+    double res = -1.0e300;
+    for (int c = 0; c < nCells; c++)
+    {
+        const double d[3] = {D[3*c] - Dprev[3*c], D[3*c + 1] - Dprev[3*c + 1], D[3*c + 2] - Dprev[3*c + 2]};
+        const double r = mag3o(d)/(maxDD + 1.0e-15);
+        if (r > res) res = r;
+    }
+    return res;
 }
