@@ -117,3 +117,47 @@ def cantilever_subdomain(nx, ny, nz, px, py, pz, rank, L=2.0, W=0.5, H=1.0, E=ST
     gid = (gi + nx*(gj + ny*gk))
     return dict(l=l, u=u, diag=diag, upper=upper, b=b, nCells=n, cells=gid, patchFaceCells=pfc, patchBouCoeffs=pbc,
                 patchNbrDomain=nbr, gamma=gamma)
+
+
+def scalar_laplacian_system(mesh, geom, gamma, fixedValue=None, refCell=None, refValue=0.0, rate=None):
+    """The OTHER symmetric systems that reach the same lduMatrix::solver boundary (SURVEY.md 8 a15), assembled the way
+    [EXT] gaussLaplacianScheme::fvmLaplacianUncorrected + fixedValue / zeroGradient patches + fvMatrix::setReference do:
+      * TEqn (src/solvers/thermalStressFoam/TEqn.H:9-15): fvm::ddt(rhoC, T) - fvm::laplacian(k, T) with fixedValue and
+        zeroGradient patches -> fixedValue = {patch: value}, rate = rhoC/deltaT per cell (None: steady);
+      * pEqn (flowModels/consistentIcoFlow/consistentIcoFlow.C:213-224): fvm::laplacian(1/A, p) == div(phi) with all-Neumann
+        patches and a reference cell -> refCell, refValue.
+    Returns dict(l, u, diag, upper, source, patches=[(faceCells, internalCoeffs, boundaryCoeffs)]) of laplacian(gamma, psi)
+    (negative definite, as foam assembles it); `rate` adds +rate*V on the diagonal of MINUS that matrix, i.e. the system
+    returned is  rate*V*psi - laplacian(gamma, psi) = source  when rate is given, else  laplacian(gamma, psi) = source."""
+    nIF, nC = mesh.nInternalFaces, mesh.nCells
+    l = np.ascontiguousarray(mesh.owner[:nIF], dtype=np.int32)
+    u = np.ascontiguousarray(mesh.neighbour, dtype=np.int32)
+    gam = gamma*np.ones(mesh.nFaces)
+    upper = geom.deltaCoeffs[:nIF]*gam[:nIF]*geom.magSf[:nIF]
+    diag = np.zeros(nC)
+    np.subtract.at(diag, l, upper)              # negSumDiag: Diag[l[f]] -= Lower[f]; Diag[u[f]] -= Upper[f]
+    np.subtract.at(diag, u, upper)
+    source = np.zeros(nC)
+    patches = []
+    for p in mesh.patches:
+        fs = slice(p["start"], p["start"] + p["size"])
+        fc = np.ascontiguousarray(mesh.owner[fs], dtype=np.int64)
+        if fixedValue and p["name"] in fixedValue:
+            # fixedValue: gradientInternalCoeffs = -deltaCoeffs, gradientBoundaryCoeffs = deltaCoeffs*value;
+            # [EXT gaussLaplacianScheme]: internalCoeffs = gammaMagSf*gradientInternalCoeffs,
+            #                             boundaryCoeffs = -gammaMagSf*gradientBoundaryCoeffs
+            gms = gam[fs]*geom.magSf[fs]
+            ic = gms*(-geom.deltaCoeffs[fs])
+            bc = -gms*(geom.deltaCoeffs[fs]*fixedValue[p["name"]])
+        else:                                   # zeroGradient
+            ic = np.zeros(p["size"]); bc = np.zeros(p["size"])
+        patches.append((fc, ic, bc))
+    sgn = 1.0
+    if rate is not None:                        # rate*V*psi - laplacian: flip the laplacian's sign, add the ddt diagonal
+        sgn = -1.0
+        upper = -upper; diag = -diag + rate*geom.V
+        patches = [(fc, -ic, -bc) for fc, ic, bc in patches]
+    if refCell is not None:                     # fvMatrix::setReference: source[celli] += diag[celli]*value; diag[celli] += diag[celli]
+        source[refCell] += diag[refCell]*refValue
+        diag[refCell] += diag[refCell]
+    return dict(l=l, u=u, diag=diag, upper=np.ascontiguousarray(upper), source=source, patches=patches, sign=sgn)

@@ -228,3 +228,35 @@ def test_random_graph_with_high_degree_rows(n, extra):
     g = check_kernels(l, u, n, diag, upper, b)
     check_solve(g, l, u, diag, upper, b, x0, 1e-9, 0.0)
     g.close()
+
+
+def _scalar_system(kind):
+    """the other symmetric systems entering the same solver boundary."""
+    from fluidstructureinteraction_b200 import cases, geometry
+    m = meshes.hex_box(16, 6, 10)
+    g = geometry.compute(m)
+    if kind == "TEqn":          # thermalStressFoam TEqn.H:9-15: ddt(rhoC T) - laplacian(k T), hot and cold walls, rest adiabatic
+        s = cases.scalar_laplacian_system(m, g, 45.0, fixedValue={"fixed": 300.0, "loaded": 500.0}, rate=7854.0*434.0/1000.0)
+        s["source"] = s["source"] + (7854.0*434.0/1000.0)*g.V*300.0           # ddt source: rate*V*T_old
+        x0 = np.full(m.nCells, 300.0)
+    else:                        # consistentIcoFlow.C:213-224: laplacian(1/A, p) == div(phi), all Neumann + setReference
+        s = cases.scalar_laplacian_system(m, g, 2.5e-3, refCell=0, refValue=0.0)
+        rng = np.random.default_rng(17)
+        dv = rng.standard_normal(m.nCells); dv -= dv.mean()                  # a divergence field that sums to zero
+        s["source"] = s["source"] + dv*g.V
+        x0 = np.zeros(m.nCells)
+    # fvScalarMatrix::solve: addBoundaryDiag / addBoundarySource of the non-coupled patches
+    diag = s["diag"].copy(); b = s["source"].copy()
+    for fc, ic, bc in s["patches"]:
+        np.add.at(diag, fc, ic); np.add.at(b, fc, bc)
+    return m, s, diag, b, x0
+
+
+@pytest.mark.parametrize("kind", ["TEqn", "pEqn"])
+def test_other_scalar_systems_through_the_same_solver(kind):
+    m, s, diag, b, x0 = _scalar_system(kind)
+    g = check_kernels(s["l"], s["u"], m.nCells, diag, s["upper"], b)
+    pg, pc = check_solve(g, s["l"], s["u"], diag, s["upper"], b, x0, 1e-9, 0.0)
+    assert pg["converged"] and pg["nIterations"] >= 3
+    check_solve(g, s["l"], s["u"], diag, s["upper"], b, x0, 1e-6, 0.05)      # the shipped fluid / thermal tolerances
+    g.close()

@@ -182,3 +182,26 @@ def test_decomposed_oracle_matches_global_solution():
     assert perf["converged"] == 1 and perfG["converged"] == 1
     assert np.max(np.abs(xd - xg)) < 1e-9*np.max(np.abs(xg))
     assert perf["initialResidual"] == pytest.approx(perfG["initialResidual"], rel=1e-12)
+
+
+def test_other_scalar_systems_converge_in_the_oracle():
+    """TEqn-like (positive definite) and pEqn-like (negative definite, reference cell) systems."""
+    from fluidstructureinteraction_b200 import cases, geometry, meshes
+    m = meshes.hex_box(8, 4, 6)
+    g = geometry.compute(m)
+    for kw, x0 in ((dict(fixedValue={"fixed": 300.0, "loaded": 500.0}, rate=1.0e5), 300.0), (dict(refCell=0), 0.0)):
+        s = cases.scalar_laplacian_system(m, g, 3.0, **kw)
+        diag = s["diag"].copy(); b = s["source"].copy()
+        for fc, ic, bc in s["patches"]:
+            np.add.at(diag, fc, ic); np.add.at(b, fc, bc)
+        if "refCell" in kw:
+            rng = np.random.default_rng(2); dv = rng.standard_normal(m.nCells); b = b + (dv - dv.mean())*g.V
+        else:
+            b = b + 1.0e5*g.V*300.0
+        x = np.full(m.nCells, x0)
+        perf, hist = oracle.pcg_solve(s["l"], s["u"], diag, s["upper"], x, b, 1e-10, 0.0)
+        assert perf["converged"] and not perf["singular"]
+        r = b - oracle.amul(s["l"], s["u"], diag, s["upper"], x)
+        assert np.sum(np.abs(r)) <= 1e-8*max(np.sum(np.abs(b)), 1e-300) + 1e-10*perf["normFactor"]
+        if "refCell" not in kw:
+            assert 300.0 - 1e-6 <= x.min() and x.max() <= 500.0 + 1e-6      # maximum principle of the heat equation
