@@ -203,9 +203,13 @@ def measure_assembly(nx, ny, nz, peak):
     D = 1e-5*rng.standard_normal((nC, 3)); pD = 1e-5*rng.standard_normal((m.nPoints, 3))
     G = 1e-5*rng.standard_normal((nC, 9)); Gf = 1e-5*rng.standard_normal((nF, 9))
     trac = np.zeros((nBF, 3)); pres = np.zeros(nBF); fixed = np.zeros((nBF, 3)); pgrad = np.zeros((nBF, 3))
-    a = gm.assemble_D(np.full(nC, mu), np.full(nC, lam), np.full(nC, cases.STEEL["rho"]), np.zeros(3), D, G, Gf, trac,
-                      pres, fixed, 1.0, reps=10)
-    _, _, _, gms = gm.gradients(D, pD, G, fixed, pgrad, 1.0, reps=10)
+    # one untimed pass (first-launch cost, clocks ramping up after the host-side mesh build), then the best of three
+    # timed batches of 10 back-to-back assemblies (CUDA events on the launching stream; the working set is >> L2)
+    args_a = (np.full(nC, mu), np.full(nC, lam), np.full(nC, cases.STEEL["rho"]), np.zeros(3), D, G, Gf, trac, pres, fixed, 1.0)
+    gm.assemble_D(*args_a, reps=3)
+    a = min((gm.assemble_D(*args_a, reps=10) for _ in range(3)), key=lambda r: r["kernel_ms"])
+    gm.gradients(D, pD, G, fixed, pgrad, 1.0, reps=2)
+    gms = min(gm.gradients(D, pD, G, fixed, pgrad, 1.0, reps=10)[3] for _ in range(3))
     gm.close()
     b_asm = (104 + 392 + 360)*nC          # laplacian + explicit flux/div + skew correction (hex)
     b_grad = (200 + 384)*nC               # cell gradient + face gradient
@@ -372,9 +376,14 @@ def run_ours(args, nx, ny, nz):
         names = {"amul": "k_amul (lduMatrix::Amul + wApA)", "dic": "k_dic_sweeps (DIC forward+backward + wArA)",
                  "p_update": "k_p_update", "xr_update": "k_xr_update (+ sum|rA|)"}
 
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
+        # workload (profiles/r1c_ncu_full_1M_pcg.md); only valid for the default 1 M-cell single-GPU case
+        ncu_traffic = {"dic": 68.0e6 + 67.1e6, "amul": 69.2e6, "p_update": 16.4e6, "xr_update": 32.8e6} \
+            if (world == 1 and (nx, ny, nz) == (200, 50, 100)) else {}
+
         def roof(k):
             return {"kernel": names[k], "bound": "hbm", "achieved": kern[k]["achieved_gbs"], "peak": peak,
-                    "unit": "GB/s", "frac": kern[k]["frac"], "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": kern[k]["frac"], "traffic": ncu_traffic.get(k), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": kern[k]["algorithmic_bytes"], "ms_per_launch": kern[k]["ms"],
                     "share_of_iteration": kern[k]["share_of_iteration"]}
 
