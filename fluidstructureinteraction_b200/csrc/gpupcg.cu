@@ -43,7 +43,7 @@ struct gpupcg_handle_s
     int *dExtFPtr = nullptr, *dExtFCol = nullptr, *dExtFIdx = nullptr, *dExtBPtr = nullptr, *dExtBCol = nullptr;
     AmulTileMeta* dAmulMeta = nullptr; unsigned short* dAmulU16 = nullptr; unsigned int* dAmulL32 = nullptr;
     int *dAmulExtX = nullptr, *dAmulExtC = nullptr;
-    int amulXStride = AMUL_TPB, amulCStride = AMUL_TPB;
+    int amulXStride = AMUL_TPB, amulCStride = AMUL_TPB, nAmulTiles = 0, amulT = 32, amulEU = 0, amulEL = 0;
     unsigned long long* dTileTicket = nullptr;
     unsigned long long* dTileTrace = nullptr;
     size_t smemFwd = 0, smemBwd = 0, smemAmul = 0;
@@ -186,45 +186,75 @@ extern "C" int gpupcg_destroy(gpupcg_handle h)
 
 static int round_up(int v, int m) { return ((std::max(v, 1) + m - 1)/m)*m; }
 
-// The Amul kernel's view of the tiles: per-tile contiguous ranges, operand codes that index the kernel's shared
-// arrays directly (xv = [tile x | cross-tile x: neighbour side, then owner side], cv = [tile U block | cross-tile
-// neighbour-side coefficients]) and fixed-stride gather lists.  Derived from the plan's 16-bit tile codes.
+// The Amul kernel's view of the matrix.  Its tiles are its own: every sweep tile cut into pieces of <= amulRows rows
+// (the sweeps want long tiles -- few hops -- while Amul wants many small ones in flight).  Per tile: contiguous
+// ranges, operand codes that index the kernel's shared arrays directly (xv = [tile x | cross-tile x: neighbour side,
+// then owner side], cv = [tile U block | cross-tile neighbour-side coefficients]) and fixed-stride gather lists.
 static int build_amul_view(gpupcg_handle h, cudaStream_t s)
 {
     const HostPlan& P = h->plan;
-    const int T = P.tileRowsMax, EU = P.maxTileEntriesU;
-    const int XS = h->amulXStride, CS = h->amulCStride;
-    std::vector<AmulTileMeta> meta(std::max(1, P.nTiles));
-    std::vector<unsigned short> U16(P.colU16.size());
-    std::vector<unsigned int> L32(P.colL16.size());
-    std::vector<int> extX((size_t)std::max(1, P.nTiles)*XS, -1), extC((size_t)std::max(1, P.nTiles)*CS, -1);
+    const int amulRows = std::max(32, (env_int("GPUPCG_AMUL_ROWS", 256)/32)*32);
+    std::vector<int> start;                         // first row of every Amul tile, + nRows
     for (int t = 0; t < P.nTiles; t++)
+        for (int r = P.tileStart[t]; r < P.tileStart[t + 1]; r += amulRows) start.push_back(r);
+    start.push_back(P.nTiles > 0 ? P.tileStart[P.nTiles] : 0);
+    const int nT = (int)start.size() - 1;
+    auto offU = [&](int sl) { return sl < P.nSlices ? P.slices[sl].offU : (int)P.Ucol.size(); };
+    auto offL = [&](int sl) { return sl < P.nSlices ? P.slices[sl].offL : (int)P.Lcol.size(); };
+    // pass 1: sizes
+    int T = 32, EU = 0, EL = 0, maxX = 0, maxC = 0;
+    std::vector<int> nXF(std::max(1, nT), 0), nXB(std::max(1, nT), 0);
+    for (int t = 0; t < nT; t++)
     {
-        const int r0 = P.tileStart[t], r1 = P.tileStart[t + 1];
-        const int s0 = r0/32, s1 = r1/32;
-        const int eU0 = P.slices[s0].offU, eU1 = (s1 < P.nSlices) ? P.slices[s1].offU : (int)P.colU16.size();
-        const int eL0 = P.slices[s0].offL, eL1 = (s1 < P.nSlices) ? P.slices[s1].offL : (int)P.colL16.size();
-        const int nXF = P.extFPtr[t + 1] - P.extFPtr[t], nXB = P.extBPtr[t + 1] - P.extBPtr[t];
-        meta[t] = AmulTileMeta{r0, r1 - r0, eU0, eU1 - eU0, eL0, eL1 - eL0, nXF + nXB, nXF};
-        for (int k = 0; k < nXF; k++)
-        {
-            extX[(size_t)t*XS + k] = P.extFCol[P.extFPtr[t] + k];
-            extC[(size_t)t*CS + k] = P.extFIdx[P.extFPtr[t] + k];
-        }
-        for (int k = 0; k < nXB; k++) extX[(size_t)t*XS + nXF + k] = P.extBCol[P.extBPtr[t] + k];
+        const int r0 = start[t], r1 = start[t + 1];
+        const int eU0 = offU(r0/32), eU1 = offU(r1/32), eL0 = offL(r0/32), eL1 = offL(r1/32);
+        for (int e = eL0; e < eL1; e++) { const int c = P.Lcol[e]; if (c >= 0 && (c < r0 || c >= r1)) nXF[t]++; }
+        for (int e = eU0; e < eU1; e++) { const int c = P.Ucol[e]; if (c >= 0 && (c < r0 || c >= r1)) nXB[t]++; }
+        T = std::max(T, r1 - r0); EU = std::max(EU, eU1 - eU0); EL = std::max(EL, eL1 - eL0);
+        maxX = std::max(maxX, nXF[t] + nXB[t]); maxC = std::max(maxC, nXF[t]);
+    }
+    const int XS = round_up(maxX, AMUL_TPB), CS = round_up(maxC, AMUL_TPB);
+    if (T + XS >= 0x8000 || EU + CS >= 0x8000)
+    {
+        h->err = "gpupcg_create: Amul tile too large for its 15-bit operand codes (rows with too many faces)";
+        return GPUPCG_ERR_UNSUPPORTED;
+    }
+    h->nAmulTiles = nT; h->amulT = T; h->amulEU = EU; h->amulEL = EL; h->amulXStride = XS; h->amulCStride = CS;
+    // pass 2: codes and gather lists
+    std::vector<AmulTileMeta> meta(std::max(1, nT));
+    std::vector<unsigned short> U16(P.Ucol.size());
+    std::vector<unsigned int> L32(P.Lcol.size());
+    std::vector<int> extX((size_t)std::max(1, nT)*XS, -1), extC((size_t)std::max(1, nT)*CS, -1);
+    for (int t = 0; t < nT; t++)
+    {
+        const int r0 = start[t], r1 = start[t + 1];
+        const int eU0 = offU(r0/32), eU1 = offU(r1/32), eL0 = offL(r0/32), eL1 = offL(r1/32);
+        meta[t] = AmulTileMeta{r0, r1 - r0, eU0, eU1 - eU0, eL0, eL1 - eL0, nXF[t] + nXB[t], nXF[t]};
+        int kF = 0, kB = 0;
         for (int e = eL0; e < eL1; e++)
         {
-            const unsigned c = P.colL16[e];
-            if (c == 0xFFFFu) L32[e] = 0x80000000u;
-            else if (c & 0x8000u) L32[e] = (unsigned)(T + (c & 0x7FFFu)) | ((unsigned)(EU + (c & 0x7FFFu)) << 16);
-            else L32[e] = c | ((unsigned)P.idxL16[e] << 16);
+            const int c = P.Lcol[e];
+            if (c < 0) L32[e] = 0x80000000u;
+            else if (c >= r0 && c < r1) L32[e] = (unsigned)(c - r0) | ((unsigned)(P.Lidx[e] - eU0) << 16);
+            else
+            {
+                extX[(size_t)t*XS + kF] = c;
+                extC[(size_t)t*CS + kF] = P.Lidx[e];
+                L32[e] = (unsigned)(T + kF) | ((unsigned)(EU + kF) << 16);
+                kF++;
+            }
         }
         for (int e = eU0; e < eU1; e++)
         {
-            const unsigned c = P.colU16[e];
-            if (c == 0xFFFFu) U16[e] = 0x8000u;
-            else if (c & 0x8000u) U16[e] = (unsigned short)(T + nXF + (c & 0x7FFFu));
-            else U16[e] = (unsigned short)c;
+            const int c = P.Ucol[e];
+            if (c < 0) U16[e] = 0x8000u;
+            else if (c >= r0 && c < r1) U16[e] = (unsigned short)(c - r0);
+            else
+            {
+                extX[(size_t)t*XS + nXF[t] + kB] = c;
+                U16[e] = (unsigned short)(T + nXF[t] + kB);
+                kB++;
+            }
         }
     }
     CK(upload(h->dAmulMeta, meta, s));
@@ -276,21 +306,13 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
         const HostPlan& Q = h->plan;
         h->smemFwd = sweep_layout(Q.tileRowsMax, Q.maxTileExtF, Q.maxItems, std::max(Q.maxTileEntriesU, Q.maxTileEntriesL), Q.maxTileEntriesL).bytes;
         h->smemBwd = sweep_layout(Q.tileRowsMax, Q.maxTileExtB, Q.maxItems, Q.maxTileEntriesU, Q.maxTileEntriesL).bytes;
-        int maxX = 0;
-        for (int t = 0; rc == GPUPCG_OK && t < Q.nTiles; t++)
-            maxX = std::max(maxX, Q.extFPtr[t + 1] - Q.extFPtr[t] + Q.extBPtr[t + 1] - Q.extBPtr[t]);
-        h->amulXStride = round_up(maxX, AMUL_TPB);
-        h->amulCStride = round_up(Q.maxTileExtF, AMUL_TPB);
-        h->smemAmul = 2*(size_t)((amul_layout(Q.tileRowsMax, Q.maxTileEntriesU, Q.maxTileEntriesL, h->amulXStride, h->amulCStride).bytes + 127u) & ~127u);
-        const size_t need = std::max(h->smemAmul, std::max(h->smemFwd, h->smemBwd));
-        // the Amul operand codes hold 15-bit indices into the kernel's shared arrays
-        const bool codesFit = Q.tileRowsMax + h->amulXStride < 0x8000 && Q.maxTileEntriesU + h->amulCStride < 0x8000;
+        const size_t need = std::max(h->smemFwd, h->smemBwd);
+        const bool codesFit = true;
         if (rc == GPUPCG_OK && need <= smemCap && codesFit) break;
         if (tileRows <= 32) break;
         tileRows /= 2;
     }
-    if (rc != GPUPCG_OK || std::max(h->smemAmul, std::max(h->smemFwd, h->smemBwd)) > smemCap ||
-        h->plan.tileRowsMax + h->amulXStride >= 0x8000 || h->plan.maxTileEntriesU + h->amulCStride >= 0x8000)
+    if (rc != GPUPCG_OK || std::max(h->smemFwd, h->smemBwd) > smemCap)
     {
         h->err = "gpupcg_create: a single 32-row tile does not fit in shared memory (rows with too many faces)";
         return GPUPCG_ERR_UNSUPPORTED;
@@ -311,15 +333,6 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     CK(cudaFuncSetAttribute(k_dic_tile<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwd));
     CK(cudaFuncSetAttribute(k_dic_tile<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBwd));
     h->hasOvf = (P.maxRowL > 4 || P.maxRowU > 4);
-    {
-        int occ = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_amul_tile<1>, AMUL_TPB, h->smemAmul));
-        occ = std::max(1, std::min(occ, env_int("GPUPCG_AMUL_BPS", 16)));
-        h->amulGrid = std::max(1, std::min(P.nTiles, std::min(h->numSMs*occ, h->partStride)));
-    }
-    CK(cudaFuncSetAttribute(k_amul_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemAmul));
-    CK(cudaFuncSetAttribute(k_amul_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemAmul));
-    CK(cudaFuncSetAttribute(k_amul_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemAmul));
     h->sweepGrid = std::max(1, P.nTiles);
     int sbps = std::max(1, env_int("GPUPCG_STREAM_BPS", 8));
     h->streamGrid = std::min(h->numSMs*sbps, MAXPART);
@@ -344,6 +357,21 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     CK(upload(h->dExtBPtr, P.extBPtr, s));
     CK(upload(h->dExtBCol, P.extBCol, s));
     { int rcv = build_amul_view(h, s); if (rcv) return rcv; }
+    {
+        h->smemAmul = 2*(size_t)((amul_layout(h->amulT, h->amulEU, h->amulEL, h->amulXStride, h->amulCStride).bytes + 127u) & ~127u);
+        if (h->smemAmul > smemCap)
+        {
+            h->err = "gpupcg_create: an Amul tile does not fit in shared memory (rows with too many faces); lower GPUPCG_AMUL_ROWS";
+            return GPUPCG_ERR_UNSUPPORTED;
+        }
+        CK(cudaFuncSetAttribute(k_amul_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemAmul));
+        CK(cudaFuncSetAttribute(k_amul_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemAmul));
+        CK(cudaFuncSetAttribute(k_amul_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemAmul));
+        int occ = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_amul_tile<1>, AMUL_TPB, h->smemAmul));
+        occ = std::max(1, std::min(occ, env_int("GPUPCG_AMUL_BPS", 16)));
+        h->amulGrid = std::max(1, std::min(h->nAmulTiles, std::min(h->numSMs*occ, MAXPART)));
+    }
     if (env_int("GPUPCG_TILE_TRACE", 0))
     {
         unsigned long long* d = nullptr;
@@ -392,6 +420,7 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     T.maxEU = P.maxTileEntriesU; T.maxEL = P.maxTileEntriesL; T.maxExtF = P.maxTileExtF; T.maxExtB = P.maxTileExtB;
     T.amulMeta = h->dAmulMeta; T.amulU16 = h->dAmulU16; T.amulL32 = h->dAmulL32;
     T.amulExtX = h->dAmulExtX; T.amulExtC = h->dAmulExtC; T.amulXStride = h->amulXStride; T.amulCStride = h->amulCStride;
+    T.nAmulTiles = h->nAmulTiles; T.amulT = h->amulT; T.amulEU = h->amulEU; T.amulEL = h->amulEL;
     h->tiles = T;
 
     // the big host index arrays are no longer needed
@@ -632,7 +661,7 @@ static int enqueue_amul(gpupcg_handle h, int mode, const double* x, double* Ax, 
     bool haloInFlight = false;
     if (ifaces && mode != 2 && !xNbrReady) { rc = halo_exchange(h, x, &haloInFlight); if (rc) return rc; }
     const unsigned int* mask = (ifaces && mode == 1) ? h->dIfMask : nullptr;
-    if (P.nTiles > 0)
+    if (h->nAmulTiles > 0)
     {
         h->launches++;
         if (mode == 0)

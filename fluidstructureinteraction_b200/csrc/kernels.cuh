@@ -348,6 +348,7 @@ struct TileArgs
     const int* amulExtX;            // [nTiles][amulXStride] global rows of the cross-tile x values, -1 = none
     const int* amulExtC;            // [nTiles][amulCStride] U-array indices of the cross-tile coefficients, -1 = none
     int amulXStride, amulCStride;   // multiples of AMUL_TPB
+    int nAmulTiles, amulT, amulEU, amulEL;  // Amul tiles (pieces of the sweep tiles) and their shared-memory maxima
 };
 
 // ---- mbarrier + 1-D bulk copy (TMA) primitives
@@ -450,12 +451,12 @@ __global__ void __launch_bounds__(AMUL_TPB) k_amul_tile(TileArgs A, const double
 {
     if (MODE == 1 && st->done) return;
     extern __shared__ __align__(128) unsigned char smemRaw[];
-    const AmulLayout L = amul_layout(A.tileRowsMax, A.maxEU, A.maxEL, A.amulXStride, A.amulCStride);
+    const AmulLayout L = amul_layout(A.amulT, A.amulEU, A.amulEL, A.amulXStride, A.amulCStride);
     const unsigned sb0 = (unsigned)__cvta_generic_to_shared(smemRaw);
     const unsigned stageBytes = (L.bytes + 127u) & ~127u;
     const double xc = (MODE == 2) ? st->xRef : 0.0;
     const int tid = threadIdx.x;
-    const int T = A.tileRowsMax, EU = A.maxEU;
+    const int T = A.amulT, EU = A.amulEU;
     const int nkX = A.amulXStride/AMUL_TPB, nkC = A.amulCStride/AMUL_TPB;
 
     auto issue_bulk = [&](const AmulTileMeta& M, int stage)
@@ -514,13 +515,13 @@ __global__ void __launch_bounds__(AMUL_TPB) k_amul_tile(TileArgs A, const double
     }
     __syncthreads();
     AmulTileMeta Mcur = {0, 0, 0, 0, 0, 0, 0, 0}, Mnext = Mcur;
-    if (t0 < A.nTiles)
+    if (t0 < A.nAmulTiles)
     {
         Mcur = A.amulMeta[t0];
         if (tid == 0) issue_bulk(Mcur, 0);
         load_indices(t0);
         issue_gathers(t0, 0);
-        if (t0 + G < A.nTiles)
+        if (t0 + G < A.nAmulTiles)
         {
             Mnext = A.amulMeta[t0 + G];
             load_indices(t0 + G);
@@ -529,10 +530,10 @@ __global__ void __launch_bounds__(AMUL_TPB) k_amul_tile(TileArgs A, const double
     double dot[1] = {0.0};
     unsigned phase[2] = {0u, 0u};
     int stage = 0;
-    for (int tile = t0; tile < A.nTiles; tile += G, stage ^= 1)
+    for (int tile = t0; tile < A.nAmulTiles; tile += G, stage ^= 1)
     {
         const int nextTile = tile + G;
-        const bool haveNext = nextTile < A.nTiles;
+        const bool haveNext = nextTile < A.nAmulTiles;
         cp_async_wait_all();                // my gathers of this tile have landed
         __syncthreads();                    // ... and everyone's; everyone is done reading buffer stage^1 (tile - G)
         AmulTileMeta M2 = Mnext;
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(AMUL_TPB) k_amul_tile(TileArgs A, const double
         {
             if (tid == 0) issue_bulk(Mnext, stage ^ 1);
             issue_gathers(nextTile, stage ^ 1);
-            if (nextTile + G < A.nTiles)
+            if (nextTile + G < A.nAmulTiles)
             {
                 M2 = A.amulMeta[nextTile + G];
                 load_indices(nextTile + G);
