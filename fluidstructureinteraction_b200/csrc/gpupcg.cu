@@ -44,6 +44,11 @@ struct gpupcg_handle_s
     AmulTileMeta* dAmulMeta = nullptr; unsigned short* dAmulU16 = nullptr; unsigned int* dAmulL32 = nullptr;
     int *dAmulExtX = nullptr, *dAmulExtC = nullptr;
     int amulXStride = AMUL_TPB, amulCStride = AMUL_TPB, nAmulTiles = 0, amulT = 32, amulEU = 0, amulEL = 0;
+    // table variant of the sweeps (<= 4 faces per row and side): static index tables + per-matrix coefficient tables
+    bool useTab = false;
+    int4 *dTabCF = nullptr, *dTabCB = nullptr, *dTabIF = nullptr, *dTabIB = nullptr;
+    double *dTabF = nullptr, *dTabB = nullptr;
+    size_t smemFwdTab = 0, smemBwdTab = 0;
     unsigned long long* dTileTicket = nullptr;
     unsigned long long* dTileTrace = nullptr;
     size_t smemFwd = 0, smemBwd = 0, smemAmul = 0;
@@ -169,7 +174,8 @@ extern "C" int gpupcg_destroy(gpupcg_handle h)
                     h->dBou, h->dXNbr, h->dSend, h->dPartials, h->dHistory, h->dState, h->dFlush,
                     h->dTileStart, h->dTileItemPtr, h->dItems, h->dColL16, h->dIdxL16, h->dColU16,
                     h->dExtFPtr, h->dExtFCol, h->dExtFIdx, h->dExtBPtr, h->dExtBCol, h->dTileTicket,
-                    h->dAmulMeta, h->dAmulU16, h->dAmulL32, h->dAmulExtX, h->dAmulExtC};
+                    h->dAmulMeta, h->dAmulU16, h->dAmulL32, h->dAmulExtX, h->dAmulExtC,
+                    h->dTabCF, h->dTabCB, h->dTabIF, h->dTabIB, h->dTabF, h->dTabB};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->hState) cudaFreeHost(h->hState);
     if (h->hStateRing) cudaFreeHost(h->hStateRing);
@@ -266,6 +272,52 @@ static int build_amul_view(gpupcg_handle h, cudaStream_t s)
     return GPUPCG_OK;
 }
 
+// Row tables of the table variant, from the plan's 16-bit tile codes: per row and sweep direction four value offsets
+// (bytes into the sweep CTA's value array: tile row, cross-tile slot, or the constant slot) and the four U-array
+// indices their coefficients come from (-1: unused slot).
+static int build_sweep_tables(gpupcg_handle h, cudaStream_t s)
+{
+    const HostPlan& P = h->plan;
+    const int T = P.tileRowsMax, oneF = T + P.maxTileExtF, oneB = T + P.maxTileExtB;
+    std::vector<int4> cF(P.nRows), cB(P.nRows), iF(P.nRows), iB(P.nRows);
+    for (int t = 0; t < P.nTiles; t++)
+    {
+        const int r0 = P.tileStart[t], r1 = P.tileStart[t + 1];
+        const int eU0 = P.slices[r0/32].offU;
+        for (int r = r0; r < r1; r++)
+        {
+            const SliceInfo& si = P.slices[r/32];
+            int c4[4], i4[4];
+            for (int j = 0; j < 4; j++)
+            {
+                c4[j] = 8*oneF; i4[j] = -1;
+                if (j >= si.widthL) continue;
+                const int e = si.offL + 32*j + (r & 31);
+                const unsigned code = P.colL16[e];
+                if (code == 0xFFFFu) continue;
+                if (code & 0x8000u) { c4[j] = 8*(T + (int)(code & 0x7FFFu)); i4[j] = P.extFIdx[P.extFPtr[t] + (code & 0x7FFFu)]; }
+                else { c4[j] = 8*(int)code; i4[j] = eU0 + P.idxL16[e]; }
+            }
+            cF[r] = make_int4(c4[0], c4[1], c4[2], c4[3]); iF[r] = make_int4(i4[0], i4[1], i4[2], i4[3]);
+            for (int j = 0; j < 4; j++)
+            {
+                c4[j] = 8*oneB; i4[j] = -1;
+                if (j >= si.widthU) continue;
+                const int e = si.offU + 32*j + (r & 31);
+                const unsigned code = P.colU16[e];
+                if (code == 0xFFFFu) continue;
+                c4[j] = (code & 0x8000u) ? 8*(T + (int)(code & 0x7FFFu)) : 8*(int)code;
+                i4[j] = e;
+            }
+            cB[r] = make_int4(c4[0], c4[1], c4[2], c4[3]); iB[r] = make_int4(i4[0], i4[1], i4[2], i4[3]);
+        }
+    }
+    CK(upload(h->dTabCF, cF, s)); CK(upload(h->dTabCB, cB, s)); CK(upload(h->dTabIF, iF, s)); CK(upload(h->dTabIB, iB, s));
+    CK(dalloc(h->dTabF, 4LL*std::max(1, P.nRows))); CK(dalloc(h->dTabB, 4LL*std::max(1, P.nRows)));
+    CK(cudaStreamSynchronize(s));
+    return GPUPCG_OK;
+}
+
 static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, const int* l, const int* u,
                        int nPatches, const int* patchSizes, const int* const* patchFaceCells,
                        const int* patchNbrRank)
@@ -295,7 +347,9 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     h->nPatches = nPatches;
 
     // tile size: as large as the shared-memory carve-up of one CTA allows (several CTAs per SM wanted)
-    int tileRows = env_int("GPUPCG_TILE_ROWS", 256);
+    // default tile: 512 rows for bricks of a structured block (16 x 4 x 8), 256 for the greedy tiles of general meshes
+    const bool tileRowsGiven = getenv("GPUPCG_TILE_ROWS") && *getenv("GPUPCG_TILE_ROWS");
+    int tileRows = env_int("GPUPCG_TILE_ROWS", 512);
     const size_t smemCap = (size_t)std::min<long long>(prop.sharedMemPerBlockOptin, 200*1024);
     int rc;
     while (true)
@@ -303,16 +357,20 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
         rc = build_plan(nCells, nFaces, l, u, nPatches, patchSizes, patchFaceCells, patchNbrRank, tileRows,
                         env_int("GPUPCG_TILE_MODE", 2), h->plan, h->err);
         if (rc != GPUPCG_OK && rc != -100) return rc;
+        if (rc == GPUPCG_OK && !h->plan.bricks && !tileRowsGiven && tileRows > 256) { tileRows = 256; continue; }
         const HostPlan& Q = h->plan;
         h->smemFwd = sweep_layout(Q.tileRowsMax, Q.maxTileExtF, Q.maxItems, std::max(Q.maxTileEntriesU, Q.maxTileEntriesL), Q.maxTileEntriesL).bytes;
         h->smemBwd = sweep_layout(Q.tileRowsMax, Q.maxTileExtB, Q.maxItems, Q.maxTileEntriesU, Q.maxTileEntriesL).bytes;
-        const size_t need = std::max(h->smemFwd, h->smemBwd);
+        h->useTab = (rc == GPUPCG_OK) && Q.maxRowL <= 4 && Q.maxRowU <= 4 && env_int("GPUPCG_SWEEP_TABLES", 1);
+        h->smemFwdTab = tab_layout(Q.tileRowsMax, Q.maxTileExtF, Q.maxItems).bytes;
+        h->smemBwdTab = tab_layout(Q.tileRowsMax, Q.maxTileExtB, Q.maxItems).bytes;
+        const size_t need = h->useTab ? std::max(h->smemFwdTab, h->smemBwdTab) : std::max(h->smemFwd, h->smemBwd);
         const bool codesFit = true;
         if (rc == GPUPCG_OK && need <= smemCap && codesFit) break;
         if (tileRows <= 32) break;
         tileRows /= 2;
     }
-    if (rc != GPUPCG_OK || std::max(h->smemFwd, h->smemBwd) > smemCap)
+    if (rc != GPUPCG_OK || (h->useTab ? std::max(h->smemFwdTab, h->smemBwdTab) : std::max(h->smemFwd, h->smemBwd)) > smemCap)
     {
         h->err = "gpupcg_create: a single 32-row tile does not fit in shared memory (rows with too many faces)";
         return GPUPCG_ERR_UNSUPPORTED;
@@ -333,6 +391,12 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     CK(cudaFuncSetAttribute(k_dic_tile<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwd));
     CK(cudaFuncSetAttribute(k_dic_tile<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBwd));
     h->hasOvf = (P.maxRowL > 4 || P.maxRowU > 4);
+    if (h->useTab)
+    {
+        CK(cudaFuncSetAttribute((k_dic_tile<0, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwdTab));
+        CK(cudaFuncSetAttribute((k_dic_tile<1, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwdTab));
+        CK(cudaFuncSetAttribute((k_dic_tile<2, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBwdTab));
+    }
     h->sweepGrid = std::max(1, P.nTiles);
     int sbps = std::max(1, env_int("GPUPCG_STREAM_BPS", 8));
     h->streamGrid = std::min(h->numSMs*sbps, MAXPART);
@@ -357,6 +421,7 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     CK(upload(h->dExtBPtr, P.extBPtr, s));
     CK(upload(h->dExtBCol, P.extBCol, s));
     { int rcv = build_amul_view(h, s); if (rcv) return rcv; }
+    if (h->useTab) { int rcv = build_sweep_tables(h, s); if (rcv) return rcv; }
     {
         h->smemAmul = 2*(size_t)((amul_layout(h->amulT, h->amulEU, h->amulEL, h->amulXStride, h->amulCStride).bytes + 127u) & ~127u);
         if (h->smemAmul > smemCap)
@@ -691,7 +756,16 @@ static int enqueue_factor(gpupcg_handle h, int gated)
 {
     if (h->plan.nTiles == 0) return GPUPCG_OK;
     fill_sent(h, h->dY);
-    if (h->hasOvf)
+    if (h->useTab)
+    {
+        const int gT = grid_for(h->plan.nRows, h->streamGrid);
+        LAUNCH((k_tab_coeffs<0>), gT, h->stream, h->plan.nRows, h->dTabIF, h->dUval, nullptr, h->dTabF, h->dState, gated);
+        LAUNCH_SWEEP((k_dic_tile<1, false, true>), h->smemFwdTab, h->tiles, h->dDiag, h->dUval, nullptr, nullptr,
+                     (unsigned long long*)h->dY, h->dRD, h->dTileTicket, nullptr, 0, h->dState, gated, h->dTabCF, h->dTabF);
+        LAUNCH((k_tab_coeffs<1>), gT, h->stream, h->plan.nRows, h->dTabIF, h->dUval, h->dRD, h->dTabF, h->dState, gated);
+        LAUNCH((k_tab_coeffs<1>), gT, h->stream, h->plan.nRows, h->dTabIB, h->dUval, h->dRD, h->dTabB, h->dState, gated);
+    }
+    else if (h->hasOvf)
         LAUNCH_SWEEP((k_dic_tile<1, true>), h->smemFwd, h->tiles, h->dDiag, h->dUval, nullptr, nullptr,
                      (unsigned long long*)h->dY, h->dRD, h->dTileTicket, nullptr, 0, h->dState, gated);
     else
@@ -709,7 +783,14 @@ static int enqueue_sweeps(gpupcg_handle h, const double* rA, double* z, bool red
     unsigned long long* yb = (unsigned long long*)h->dY;
     unsigned long long* zb = (unsigned long long*)z;
     double* part = reduce ? h->dPartials : nullptr;
-    if (h->hasOvf)
+    if (h->useTab)
+    {
+        LAUNCH_SWEEP((k_dic_tile<0, false, true>), h->smemFwdTab, h->tiles, h->dRD, h->dUval, rA, nullptr, yb, nullptr,
+                     h->dTileTicket, nullptr, 0, h->dState, gated, h->dTabCF, h->dTabF);
+        LAUNCH_SWEEP((k_dic_tile<2, false, true>), h->smemBwdTab, h->tiles, h->dRD, h->dUval, rA, yb, zb, nullptr,
+                     h->dTileTicket, part, h->partStride, h->dState, gated, h->dTabCB, h->dTabB);
+    }
+    else if (h->hasOvf)
     {
         LAUNCH_SWEEP((k_dic_tile<0, true>), h->smemFwd, h->tiles, h->dRD, h->dUval, rA, nullptr, yb, nullptr,
                      h->dTileTicket, nullptr, 0, h->dState, gated);

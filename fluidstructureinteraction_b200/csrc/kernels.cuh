@@ -671,6 +671,27 @@ __host__ __device__ inline SweepLayout sweep_layout(int T, int X, int I, int E, 
     return L;
 }
 
+// Table variant (meshes with <= 4 faces per row and side): the row tables {4 coefficients, 4 value offsets} are global
+// arrays (indices static per mesh, coefficients pre-multiplied once per matrix), so staging is bulk copies only.
+__host__ __device__ inline SweepLayout tab_layout(int T, int X, int I)
+{
+    SweepLayout L;
+    L.T = T; L.X = X;
+    L.NV = (T + X + 3) & ~1;
+    L.one = T + X;
+    L.vals = 0;
+    L.rowF = 8u*L.NV;
+    L.rowC = L.rowF + 32u*(T + 1);
+    L.dv = L.rowC + 16u*(T + 1);
+    L.av = L.dv + 8u*(T + 2);
+    L.items = L.av + 8u*(T + 2);
+    L.slot = L.items + 8u*(I + 2);
+    L.bar = (L.slot + 16 + 15) & ~15u;
+    L.bytes = L.bar + 16;
+    L.ovf = L.Ub = L.col = L.idx = L.cX = L.sl = 0;
+    return L;
+}
+
 // shared-memory accessors on 32-bit shared addresses.  All volatile asm: the sweep loop is hand-scheduled and the
 // compiler must keep the order (prefetches of the NEXT item first, then the dependency loads of the current one).
 __device__ __forceinline__ double lds_f64(unsigned a)
@@ -765,6 +786,27 @@ __device__ __forceinline__ RowRegs load_row(unsigned sb, const SweepLayout& L, i
     return R;
 }
 
+// table variant: the start value is formed here, one item ahead of its use (MODE 0: rD*rA, 1: diag, 2: y)
+template <int MODE>
+__device__ __forceinline__ RowRegs load_row_tab(unsigned sb, const SweepLayout& L, int2 item, int lane)
+{
+    RowRegs R;
+    const bool active = lane < (item.y & 0xffff);
+    const int q = active ? item.x + lane : L.T;
+    R.qg = active ? q : -1;
+    R.q8 = active ? 8u*q : 8u*(L.one + 1);
+    R.c = lds_v4(sb + L.rowC + 16u*q);
+    const double2 fa = lds_d2(sb + L.rowF + 32u*q);
+    const double2 fb = lds_d2(sb + L.rowF + 32u*q + 16u);
+    if (MODE == 0) R.acc0 = __dmul_rn(lds_f64_weak(sb + L.dv + 8u*q), lds_f64_weak(sb + L.av + 8u*q));
+    else if (MODE == 1) R.acc0 = lds_f64_weak(sb + L.dv + 8u*q);
+    else R.acc0 = lds_f64_weak(sb + L.av + 8u*q);
+    R.acc0 = (R.acc0 != R.acc0) ? __longlong_as_double((long long)QNAN) : R.acc0;
+    R.ovf = 0;
+    R.f0 = fa.x; R.f1 = fa.y; R.f2 = fb.x; R.f3 = fb.y;
+    return R;
+}
+
 // the four register-resident dependencies of a row: four loads issued together, one combined readiness test.
 // Rows of the tile are final by construction of the rounds; cross-tile slots may still hold SENT.
 __device__ __forceinline__ void dep_values4(unsigned vb, const int4 c, double& v0, double& v1, double& v2, double& v3)
@@ -807,19 +849,23 @@ __device__ __forceinline__ double canon(double v)
     return (v != v) ? __longlong_as_double((long long)QNAN) : v;
 }
 
-template <int MODE, bool HAS_OVF>
+// TAB: table variant (tabC / tabF = the row tables of this sweep direction; Uval unused)
+template <int MODE, bool HAS_OVF, bool TAB = false>
 __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double* __restrict__ diagOrRD,
                                                         const double* __restrict__ Uval,
                                                         const double* __restrict__ rA, unsigned long long* y,
                                                         unsigned long long* out, double* __restrict__ rDout,
                                                         unsigned long long* tileTicket, double* partials, int partStride,
-                                                        DevState* st, int gated)
+                                                        DevState* st, int gated,
+                                                        const int4* __restrict__ tabC = nullptr, const double* __restrict__ tabF = nullptr)
 {
     if (gated && st->done) return;
+    static_assert(!(TAB && HAS_OVF), "the table variant carries four faces per row and side");
     constexpr bool BWD = (MODE == 2), FACTOR = (MODE == 1);
     extern __shared__ __align__(128) unsigned char smemRaw[];
     const int X = BWD ? A.maxExtB : A.maxExtF;
-    const SweepLayout L = sweep_layout(A.tileRowsMax, X, A.maxItems, BWD ? A.maxEU : max(A.maxEU, A.maxEL), A.maxEL);
+    const SweepLayout L = TAB ? tab_layout(A.tileRowsMax, X, A.maxItems)
+                              : sweep_layout(A.tileRowsMax, X, A.maxItems, BWD ? A.maxEU : max(A.maxEU, A.maxEL), A.maxEL);
     const unsigned sb = (unsigned)__cvta_generic_to_shared(smemRaw);
     const unsigned vb = sb + L.vals;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -832,10 +878,55 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
     const int nExt = (BWD ? A.extBPtr[tile + 1] : A.extFPtr[tile + 1]) - xBase;
     const int* extCol = BWD ? A.extBCol : A.extFCol;
     const int T = L.T;
-    const SliceInfo first = A.slices[s0], last = A.slices[s0 + nsl - 1];
-    const int eU0 = first.offU, nEU = last.offU + 32*last.widthU - eU0;
-    const int eL0 = first.offL, nEL = last.offL + 32*last.widthL - eL0;
+    int eU0 = 0, nEU = 0, eL0 = 0, nEL = 0;
+    if (!TAB)
+    {
+        const SliceInfo first = A.slices[s0], last = A.slices[s0 + nsl - 1];
+        eU0 = first.offU; nEU = last.offU + 32*last.widthU - eU0;
+        eL0 = first.offL; nEL = last.offL + 32*last.widthL - eL0;
+    }
+    double* vals = (double*)(smemRaw + L.vals);
+    double* cX = (double*)(smemRaw + L.cX);
+    const double* Ub = (const double*)(smemRaw + L.Ub);
+    const double* dv = (const double*)(smemRaw + L.dv);
+    const unsigned short* colS = (const unsigned short*)(smemRaw + L.col);
+    const unsigned short* idxS = (const unsigned short*)(smemRaw + L.idx);
+    const SliceInfo* sl = (const SliceInfo*)(smemRaw + L.sl);
 
+    if (TAB)
+    {
+        // ---- staging, table variant: five bulk copies, nothing to build
+        if (threadIdx.x == 0)
+        {
+            mbar_init(sb + L.bar, 1);
+            const unsigned bytes = 32u*nr + 16u*nr + (BWD ? 0u : 8u*nr) + (FACTOR ? 0u : 8u*nr);
+            mbar_expect_tx(sb + L.bar, bytes);
+            bulk_g2s(sb + L.rowF, tabF + 4*(size_t)r0, 32u*nr, sb + L.bar);
+            bulk_g2s(sb + L.rowC, tabC + r0, 16u*nr, sb + L.bar);
+            if (!BWD) bulk_g2s(sb + L.dv, diagOrRD + r0, 8u*nr, sb + L.bar);
+            if (!FACTOR) bulk_g2s(sb + L.av, BWD ? (const void*)(y + r0) : (const void*)(rA + r0), 8u*nr, sb + L.bar);
+        }
+        int2* items = (int2*)(smemRaw + L.items);
+        for (int i = threadIdx.x; i < nItems + 2; i += SWEEP_TPB)
+            items[i] = (i < nItems) ? A.items[ip + (BWD ? nItems - 1 - i : i)] : make_int2(0, 0);
+        for (int i = threadIdx.x; i < nExt; i += SWEEP_TPB) ((unsigned long long*)vals)[T + i] = SENT;
+        if (threadIdx.x < 4)            // the dummy row of idle lanes (never touched by the bulk copies: nr <= T)
+        {
+            ((int*)(smemRaw + L.rowC))[4*T + threadIdx.x] = 8*L.one;
+            ((double*)(smemRaw + L.rowF))[4*T + threadIdx.x] = 0.0;
+            if (threadIdx.x == 0)
+            {
+                vals[L.one] = 1.0; vals[L.one + 1] = 0.0;
+                ((double*)(smemRaw + L.dv))[T] = 0.0; ((double*)(smemRaw + L.av))[T] = 0.0;
+            }
+        }
+        __syncthreads();
+        mbar_wait(sb + L.bar, 0);
+        if (BWD && warp != 0)           // y has been read: re-arm it for the next forward sweep
+            for (int q = threadIdx.x - 32; q < nr; q += FETCHERS) y[r0 + q] = SENT;
+    }
+    else
+    {
     // ---- staging: bulk copies (one mbarrier) + cross-tile coefficient gathers
     if (threadIdx.x == 0)
     {
@@ -853,8 +944,6 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
             bulk_g2s(sb + L.idx, A.idxL16 + eL0, 2u*nEL, sb + L.bar);
         }
     }
-    double* vals = (double*)(smemRaw + L.vals);
-    double* cX = (double*)(smemRaw + L.cX);
     if (!BWD)
     {
         for (int k = threadIdx.x; k < nExt; k += SWEEP_TPB) cX[k] = Uval[A.extFIdx[xBase + k]];
@@ -870,12 +959,7 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
     mbar_wait(sb + L.bar, 0);
 
     // ---- build the round loop's working set from the staged blocks
-    const double* Ub = (const double*)(smemRaw + L.Ub);
-    const double* dv = (const double*)(smemRaw + L.dv);
     const double* av = (const double*)(smemRaw + L.av);
-    const unsigned short* colS = (const unsigned short*)(smemRaw + L.col);
-    const unsigned short* idxS = (const unsigned short*)(smemRaw + L.idx);
-    const SliceInfo* sl = (const SliceInfo*)(smemRaw + L.sl);
     double* rowF = (double*)(smemRaw + L.rowF);
     int* rowC = (int*)(smemRaw + L.rowC);
     unsigned char* ovf = smemRaw + L.ovf;
@@ -916,6 +1000,7 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
         if (threadIdx.x == 0) { ovf[T] = 0; vals[L.one + 1] = 0.0; }
     }
     __syncthreads();
+    }
     if (g_tileTimes && threadIdx.x == 0 && MODE == 0) { g_tileTimes[3*tile] = tBegin; g_tileTimes[3*tile + 1] = gtime(); }
 
     // (tried, no effect on B200: rotating the sweep-warp role over the SM's schedulers, sleeping between shared
@@ -928,11 +1013,11 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
         const unsigned ib = sb + L.items;
         const int syncBit = BWD ? (1 << 16) : (1 << 17);       // end of a round in sweep order
         int2 d0 = lds_i2(ib), d1 = lds_i2(ib + 8u);
-        RowRegs cur = load_row<HAS_OVF>(sb, L, d0, lane);
+        RowRegs cur = TAB ? load_row_tab<MODE>(sb, L, d0, lane) : load_row<HAS_OVF>(sb, L, d0, lane);
         for (int i = 0; i < nItems; i++)
         {
             const int2 d2 = lds_i2(ib + 8u*(i + 2));
-            const RowRegs nxt = load_row<HAS_OVF>(sb, L, d1, lane);
+            const RowRegs nxt = TAB ? load_row_tab<MODE>(sb, L, d1, lane) : load_row<HAS_OVF>(sb, L, d1, lane);
             double v0, v1, v2, v3;
             dep_values4(vb, cur.c, v0, v1, v2, v3);
             double acc = cur.acc0;
@@ -1038,6 +1123,36 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
         for (int q = threadIdx.x; q < nr; q += SWEEP_TPB) dot += vals[q]*rA[r0 + q];
         double v[1] = {dot};
         grid_reduce_finish<1, SWEEP_TPB>(v, partials, partStride, tile, A.nTiles, st, S_SWEEP, nullptr);
+    }
+}
+
+// Row-table coefficients of the table variant.  WHICH 0 (before the factor): c*c per neighbour-side face;
+// WHICH 1 (after it): rD[row]*c -- the products the reference forms first in  rD[u]*upper[f]*wA[l]  (left to right).
+template <int WHICH>
+__global__ void __launch_bounds__(TPB) k_tab_coeffs(int nRows, const int4* __restrict__ idx, const double* __restrict__ Uval,
+                                                    const double* __restrict__ rD, double* __restrict__ F,
+                                                    const DevState* __restrict__ st, int gated)
+{
+    if (gated && st->done) return;
+    for (int r = blockIdx.x*TPB + threadIdx.x; r < nRows; r += gridDim.x*TPB)
+    {
+        const int4 i4 = idx[r];
+        const int ii[4] = {i4.x, i4.y, i4.z, i4.w};
+        const double d = (WHICH == 1) ? rD[r] : 0.0;
+        double f[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+            f[j] = 0.0;
+            if (ii[j] >= 0)
+            {
+                const double c = Uval[ii[j]];
+                f[j] = canon((WHICH == 0) ? __dmul_rn(c, c) : __dmul_rn(d, c));
+            }
+        }
+        double2* o = (double2*)(F + 4*(size_t)r);
+        o[0] = make_double2(f[0], f[1]);
+        o[1] = make_double2(f[2], f[3]);
     }
 }
 

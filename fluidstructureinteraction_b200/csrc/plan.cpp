@@ -121,20 +121,18 @@ int build_plan(int nCells, int nFaces, const int* l, const int* u,
             }
             if (ok)
             {
-                // brick edges ~ sqrt(n_d) (minimises sum n_d/b_d at fixed volume), volume <= tileRows
-                double w[3] = {std::sqrt((double)nx), std::sqrt((double)ny), std::sqrt((double)nz)};
-                double scale = std::cbrt((double)tileRows/(w[0]*w[1]*w[2]));
+                // Brick shape.  One warp sweeps a brick level by level, so a level must not be wider than a warp: the
+                // cross-section (the two shorter edges) holds <= 32 rows, 4 x 8 with the 8 along the longer of the two
+                // axes, and the brick is long (tileRows/32) along the longest axis: few hops per dependency path AND one
+                // pass per round.  (Near-cubic bricks of the same volume have levels of ~40 rows = two passes per round:
+                // 0.254 vs 0.205 ms per precondition at 1 M cells, profiles/r1c_dic_latency_study.md.)
                 long long n3[3] = {nx, ny, nz};
+                int ax[3] = {0, 1, 2};
+                std::sort(ax, ax + 3, [&](int a, int b) { return n3[a] != n3[b] ? n3[a] > n3[b] : a < b; });
                 int bb[3];
-                for (int k = 0; k < 3; k++) bb[k] = (int)std::max(1.0, std::min((double)n3[k], std::floor(w[k]*scale)));
-                for (bool grew = true; grew;)          // use up the slack left by flooring / clamping
-                {
-                    grew = false;
-                    for (int k = 0; k < 3; k++)
-                    {
-                        if (bb[k] < n3[k] && (long long)(bb[k] + 1)*bb[(k + 1) % 3]*bb[(k + 2) % 3] <= tileRows) { bb[k]++; grew = true; }
-                    }
-                }
+                bb[ax[2]] = (int)std::min<long long>(n3[ax[2]], 4);
+                bb[ax[1]] = (int)std::min<long long>(n3[ax[1]], 32/bb[ax[2]]);
+                bb[ax[0]] = (int)std::max<long long>(1, std::min<long long>(n3[ax[0]], tileRows/(bb[ax[1]]*bb[ax[2]])));
                 if (const char* ev = getenv("GPUPCG_BRICK"))       // experiment hook: explicit brick edges "bx,by,bz"
                 {
                     int e0, e1, e2;
@@ -166,6 +164,7 @@ int build_plan(int nCells, int nFaces, const int* l, const int* u,
                 }
                 cuts.push_back(p);
                 bricks = true;
+                P.bricks = true;
             }
         }
     }

@@ -40,6 +40,7 @@ struct HostPlan
     int nRows = 0;              // padded (every tile is a whole number of slices)
     int nSlices = 0;
     int nLevels = 0;            // global dependency depth (information only)
+    bool bricks = false;        // tiles are bricks of a structured block (tile mode 2 detected one)
     int maxLevelRows = 0;
     long long entriesU = 0;
     long long entriesL = 0;
