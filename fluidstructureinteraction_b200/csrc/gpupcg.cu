@@ -777,7 +777,9 @@ static int enqueue_factor(gpupcg_handle h, int gated)
 }
 
 // y (h->dY) and z must hold SENT on entry; y is re-armed by the backward kernel.
-static int enqueue_sweeps(gpupcg_handle h, const double* rA, double* z, bool reduce, int gated)
+static int allreduce_step(gpupcg_handle h, int step, int count);
+
+static int enqueue_sweeps(gpupcg_handle h, const double* rA, double* z, bool reduce, int gated, bool fuseXR = false)
 {
     if (h->plan.nTiles == 0) return GPUPCG_OK;
     unsigned long long* yb = (unsigned long long*)h->dY;
@@ -785,6 +787,16 @@ static int enqueue_sweeps(gpupcg_handle h, const double* rA, double* z, bool red
     double* part = reduce ? h->dPartials : nullptr;
     if (h->useTab)
     {
+        if (fuseXR)
+        {
+            // the pending x/r update of the previous iteration rides in this sweep's staging; its sum|rA| goes through
+            // the same S_XR step (all-reduced first on several ranks)
+            FuseXR fx{h->dX, h->dPA, zb, h->dRA, h->dHistory};
+            LAUNCH_SWEEP((k_dic_tile<0, false, true>), h->smemFwdTab, h->tiles, h->dRD, h->dUval, rA, nullptr, yb, nullptr,
+                         h->dTileTicket, h->dPartials, h->partStride, h->dState, gated, h->dTabCF, h->dTabF, fx);
+            int rcx = allreduce_step(h, S_XR, 1); if (rcx) return rcx;
+        }
+        else
         LAUNCH_SWEEP((k_dic_tile<0, false, true>), h->smemFwdTab, h->tiles, h->dRD, h->dUval, rA, nullptr, yb, nullptr,
                      h->dTileTicket, nullptr, 0, h->dState, gated, h->dTabCF, h->dTabF);
         LAUNCH_SWEEP((k_dic_tile<2, false, true>), h->smemBwdTab, h->tiles, h->dRD, h->dUval, rA, yb, zb, nullptr,
@@ -852,6 +864,7 @@ static int solve_core(gpupcg_handle h, double tol, double relTol, int minIter, i
     // taken after batch k-1, so the stream never runs dry while the host looks at `done`.  Every kernel of the
     // iteration is gated on st->done on the device, so a batch enqueued after convergence is a string of no-ops.
     const int batch = std::max(1, env_int("GPUPCG_CHECK_EVERY", 8));
+    const bool fuseXR = h->useTab && env_int("GPUPCG_FUSE_XR", 1);
     auto enqueue_check = [&](int slot) -> cudaError_t
     {
         cudaError_t e = cudaMemcpyAsync(h->hStateRing + slot, h->dState, sizeof(DevState), cudaMemcpyDeviceToHost, s);
@@ -868,14 +881,17 @@ static int solve_core(gpupcg_handle h, double tol, double relTol, int minIter, i
             const int n = std::min(batch, maxIter - launched);
             for (int i = 0; i < n; i++)
             {
-                rc = enqueue_sweeps(h, h->dRA, h->dWA, true, 1); if (rc) return rc;
+                rc = enqueue_sweeps(h, h->dRA, h->dWA, true, 1, fuseXR); if (rc) return rc;
                 rc = allreduce_step(h, S_SWEEP, 1); if (rc) return rc;
                 LAUNCH(k_p_update, gN, s, h->dWA, h->dPA, P.nRows, h->dState);
                 rc = enqueue_amul(h, 1, h->dPA, h->dWA, false); if (rc) return rc;
                 rc = allreduce_step(h, S_AMUL, 2); if (rc) return rc;
-                LAUNCH(k_xr_update, gN, s, h->dPA, (unsigned long long*)h->dWA, h->dX, h->dRA, P.nRows,
-                                               h->dPartials, h->dState, h->dHistory);
-                rc = allreduce_step(h, S_XR, 1); if (rc) return rc;
+                if (!fuseXR)
+                {
+                    LAUNCH(k_xr_update, gN, s, h->dPA, (unsigned long long*)h->dWA, h->dX, h->dRA, P.nRows,
+                                                   h->dPartials, h->dState, h->dHistory);
+                    rc = allreduce_step(h, S_XR, 1); if (rc) return rc;
+                }
             }
             CK(cudaGetLastError());
             launched += n;
@@ -895,6 +911,15 @@ static int solve_core(gpupcg_handle h, double tol, double relTol, int minIter, i
         slot ^= 1;
     }
     *h->hState = h->hStateRing[slot];
+    if (fuseXR)
+    {
+        // the update of the last iteration launched has not been applied if the loop ran out of iterations
+        LAUNCH(k_xr_update, gN, s, h->dPA, (unsigned long long*)h->dWA, h->dX, h->dRA, P.nRows,
+                                       h->dPartials, h->dState, h->dHistory);
+        rc = allreduce_step(h, S_XR, 1); if (rc) return rc;
+        CK(cudaMemcpyAsync(h->hState, h->dState, sizeof(DevState), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
     CK(cudaEventRecord(h->ev[1], s));
     const DevState& st = *h->hState;
     const int nHist = std::min(std::min(st.nIter, historyCap), h->historyCap);
@@ -1046,6 +1071,7 @@ extern "C" int gpupcg_time_kernel(gpupcg_handle h, int which, int reps, int flus
     memset(&init, 0, sizeof(init));
     init.maxIter = 1 << 30; init.nGlobalCells = P.nCells; init.normFactor = 1.0; init.tol = 0.0;
     init.wArA = 1.0; init.wArAold = 1.0; init.wApA = 1.0e30; init.nIter = 1; init.initialResidual = 1.0;
+    init.pending = (which == 3) ? 1 : 0;
     *h->hState = init;
     CK(cudaMemcpyAsync(h->dState, h->hState, sizeof(DevState), cudaMemcpyHostToDevice, s));
     int rc = enqueue_factor(h, 0); if (rc) return rc;

@@ -49,7 +49,7 @@ struct DevState
     int nIter, done, converged, singular;
     int historyCap, multiRank;
     unsigned int ticket;
-    unsigned int pad_;
+    int pending;                // an x/r update (alpha known, wA = A pA) has not been applied yet
 };
 
 enum ScalarStep { S_INIT = 0, S_NORM = 1, S_SWEEP = 2, S_AMUL = 3, S_XR = 4 };
@@ -97,9 +97,12 @@ __device__ __forceinline__ void dev_scalar_step(DevState* st, int step, const do
             else
             {
                 st->singular = 0;
+                st->pending = 1;
             }
             break;
         case S_XR:      // finalResidual = gSumMag(rA)/normFactor; nIterations++; stop()
+            if (!st->pending) break;
+            st->pending = 0;
             st->finalResidual = __ddiv_rn(v[0], st->normFactor);
             if (history && st->nIter < st->historyCap) history[st->nIter] = st->finalResidual;
             st->nIter++;
@@ -684,11 +687,12 @@ __host__ __device__ inline SweepLayout tab_layout(int T, int X, int I)
     L.rowC = L.rowF + 32u*(T + 1);
     L.dv = L.rowC + 16u*(T + 1);
     L.av = L.dv + 8u*(T + 2);
-    L.items = L.av + 8u*(T + 2);
+    L.cX = L.av + 8u*(T + 2);               // forward sweep with the fused x/r update: the tile of wA = A pA
+    L.items = L.cX + 8u*(T + 2);
     L.slot = L.items + 8u*(I + 2);
     L.bar = (L.slot + 16 + 15) & ~15u;
     L.bytes = L.bar + 16;
-    L.ovf = L.Ub = L.col = L.idx = L.cX = L.sl = 0;
+    L.ovf = L.Ub = L.col = L.idx = L.sl = 0;
     return L;
 }
 
@@ -849,6 +853,18 @@ __device__ __forceinline__ double canon(double v)
     return (v != v) ? __longlong_as_double((long long)QNAN) : v;
 }
 
+// The x/r update of PCG::solve folded into the staging of the NEXT forward sweep (table variant only): the sweep is
+// latency-bound, its CTAs have bandwidth to spare, and the update's five streams ride along for free.
+//   x += alpha*pA;  rA -= alpha*wA;  sum|rA| -> S_XR (residual, stop test, history);  wA re-armed with SENT
+struct FuseXR
+{
+    double* x;                  // null: plain sweep
+    const double* pA;
+    unsigned long long* wA;
+    double* rA;
+    double* history;
+};
+
 // TAB: table variant (tabC / tabF = the row tables of this sweep direction; Uval unused)
 template <int MODE, bool HAS_OVF, bool TAB = false>
 __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double* __restrict__ diagOrRD,
@@ -857,9 +873,14 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
                                                         unsigned long long* out, double* __restrict__ rDout,
                                                         unsigned long long* tileTicket, double* partials, int partStride,
                                                         DevState* st, int gated,
-                                                        const int4* __restrict__ tabC = nullptr, const double* __restrict__ tabF = nullptr)
+                                                        const int4* __restrict__ tabC = nullptr, const double* __restrict__ tabF = nullptr,
+                                                        FuseXR fuse = FuseXR{nullptr, nullptr, nullptr, nullptr, nullptr})
 {
     if (gated && st->done) return;
+    const bool fused = TAB && MODE == 0 && fuse.x != nullptr;
+    const bool doXR = fused && st->pending;             // uniform over the grid: S_XR clears it after the last CTA
+    const double alphaXR = doXR ? __ddiv_rn(st->wArA, st->wApA) : 0.0;
+    double sumXR[1] = {0.0};
     static_assert(!(TAB && HAS_OVF), "the table variant carries four faces per row and side");
     constexpr bool BWD = (MODE == 2), FACTOR = (MODE == 1);
     extern __shared__ __align__(128) unsigned char smemRaw[];
@@ -899,12 +920,13 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
         if (threadIdx.x == 0)
         {
             mbar_init(sb + L.bar, 1);
-            const unsigned bytes = 32u*nr + 16u*nr + (BWD ? 0u : 8u*nr) + (FACTOR ? 0u : 8u*nr);
+            const unsigned bytes = 32u*nr + 16u*nr + (BWD ? 0u : 8u*nr) + (FACTOR ? 0u : 8u*nr) + (doXR ? 8u*nr : 0u);
             mbar_expect_tx(sb + L.bar, bytes);
             bulk_g2s(sb + L.rowF, tabF + 4*(size_t)r0, 32u*nr, sb + L.bar);
             bulk_g2s(sb + L.rowC, tabC + r0, 16u*nr, sb + L.bar);
             if (!BWD) bulk_g2s(sb + L.dv, diagOrRD + r0, 8u*nr, sb + L.bar);
             if (!FACTOR) bulk_g2s(sb + L.av, BWD ? (const void*)(y + r0) : (const void*)(rA + r0), 8u*nr, sb + L.bar);
+            if (doXR) bulk_g2s(sb + L.cX, fuse.wA + r0, 8u*nr, sb + L.bar);
         }
         int2* items = (int2*)(smemRaw + L.items);
         for (int i = threadIdx.x; i < nItems + 2; i += SWEEP_TPB)
@@ -924,6 +946,22 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
         mbar_wait(sb + L.bar, 0);
         if (BWD && warp != 0)           // y has been read: re-arm it for the next forward sweep
             for (int q = threadIdx.x - 32; q < nr; q += FETCHERS) y[r0 + q] = SENT;
+        if (doXR)
+        {
+            double* avw = (double*)(smemRaw + L.av);
+            const double* bv = (const double*)(smemRaw + L.cX);
+            for (int q = threadIdx.x; q < nr; q += SWEEP_TPB)
+            {
+                const int r = r0 + q;
+                fuse.x[r] = __dadd_rn(fuse.x[r], __dmul_rn(alphaXR, fuse.pA[r]));
+                const double rr = __dsub_rn(avw[q], __dmul_rn(alphaXR, bv[q]));
+                avw[q] = rr;
+                fuse.rA[r] = rr;
+                sumXR[0] += fabs(rr);
+                fuse.wA[r] = SENT;
+            }
+            __syncthreads();            // the sweep warp forms its start values from the updated residual
+        }
     }
     else
     {
@@ -1111,6 +1149,8 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
             else if (ns > 0) __nanosleep(ns);
         }
     }
+    if (fused)      // every CTA of a fused launch takes part (S_XR is a no-op when nothing was pending)
+        grid_reduce_finish<1, SWEEP_TPB>(sumXR, partials, partStride, tile, A.nTiles, st, S_XR, fuse.history);
     if (FACTOR)
     {
         __syncthreads();
@@ -1207,7 +1247,7 @@ __global__ void __launch_bounds__(TPB) k_xr_update(const double* __restrict__ pA
                                                    double* __restrict__ x, double* __restrict__ rA,
                                                    int nRows, double* partials, DevState* st, double* history)
 {
-    if (st->done) return;
+    if (!st->pending) return;       // nothing to apply: converged / singular before this update, or already applied (fused)
     const double alpha = __ddiv_rn(st->wArA, st->wApA);
     double v[1] = {0.0};
     for (int r = blockIdx.x*TPB + threadIdx.x; r < nRows; r += gridDim.x*TPB)
