@@ -564,7 +564,7 @@ extern "C" int gpupcg_get_plan_info(gpupcg_handle h, gpupcg_plan_info* info)
     info->nInterfaceFaces = P.nIfaceFaces; info->nInterfaces = h->nPatches;
     info->sweepGrid = h->sweepGrid; info->streamGrid = h->streamGrid; info->numSMs = h->numSMs;
     info->nTiles = P.nTiles; info->tileRowsMax = P.tileRowsMax; info->maxRounds = P.maxRounds;
-    info->sweepSmemBytes = (int)std::max(h->smemFwd, h->smemBwd);
+    info->sweepSmemBytes = (int)(h->useTab ? std::max(h->smemFwdTab, h->smemBwdTab) : std::max(h->smemFwd, h->smemBwd));
     info->extForward = h->plan.extFPtr.empty() ? 0 : h->plan.extFPtr.back();
     info->extBackward = h->plan.extBPtr.empty() ? 0 : h->plan.extBPtr.back();
     return GPUPCG_OK;
