@@ -63,6 +63,9 @@ struct MeshDev
     int nPoints;
     const int *faceStart, *facePoints;                // point loops of the faces (vertex-based gradients)
     const double* points;
+    // geometry of the faces' triangle fans, pre-computed by gpupcg_mesh_set_points (k_fan_geometry): per (face, fan
+    // triangle) the area vector St = ((a - centre) x (b - centre))/2 and St & Ct; per cell V = (sum +-St & Ct)/3
+    const double *fanS, *fanV, *gradV;
 };
 
 
@@ -372,105 +375,164 @@ __device__ __forceinline__ double div3(double x)
     }
     return __ddiv_rn(x, 3.0);
 }
-// one triangle (centre, a, b) of a face's fan: sign*(St*ttcf) into G, sign*(St & Ct) into V   (fvcGradf.C:541-610)
-__device__ __forceinline__ void fan_triangle(const double* Xa, const double* Xb, const double* Pa, const double* Pb,
-                                             const double* centre, const double* cf, bool minus, double* G, double& V)
-{
-    double ttcf[3], a[3], b[3], St[3], Ct[3], sP[3], sX[3];
-#pragma unroll
-    for (int d = 0; d < 3; d++)
-    {
-        sP[d] = add(add(Pa[d], Pb[d]), cf[d]);
-        sX[d] = add(add(centre[d], Xa[d]), Xb[d]);
-        a[d] = sub(Xa[d], centre[d]);
-        b[d] = sub(Xb[d], centre[d]);
-    }
-#pragma unroll
-    for (int d = 0; d < 3; d++) { ttcf[d] = div3(sP[d]); Ct[d] = div3(sX[d]); }
-    cross3(a, b, St);
-    // G -= St*ttcf and V -= St & Ct for the neighbour side: x - y == x + (-y) and (-a)*b == -(a*b) exactly, and a sum of
-    // negated terms is the negated sum, so the sign goes onto St once instead of onto every accumulation
-    const double half = minus ? -0.5 : 0.5;
-#pragma unroll
-    for (int d = 0; d < 3; d++) St[d] = mul(St[d], half);               // == +-(St/2.0) exactly
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) G[3*i + j] = add(G[3*i + j], mul(St[i], ttcf[j]));
-    V = add(V, dot3(St, Ct));
-}
-
 __device__ __forceinline__ void load3(const double* __restrict__ a, int i, double* r)
 {
     r[0] = a[3*(size_t)i]; r[1] = a[3*(size_t)i + 1]; r[2] = a[3*(size_t)i + 2];
 }
 
-// one face's triangle-fan contribution sign*(St*ttcf), sign*(St & Ct)   (fvcGradf.C:541-610, 623-684)
-__device__ void grad_face(const MeshDev& M, int f, const double* __restrict__ pf, bool minus, double* G, double& V)
+// ---- pre-computed fan geometry --------------------------------------------------------------------------------------
+// The geometric half of grad_face (area vectors and volume terms of the fan triangles) depends on the mesh only; it is
+// evaluated once per gpupcg_mesh_set_points with the same operations in the same order, so k_grad_cells below gives
+// the same bits as the all-in-one evaluation (and the oracle) while doing a third of the arithmetic per call.
+__global__ void __launch_bounds__(ATPB) k_fan_geometry(MeshDev M, double* __restrict__ fanS, double* __restrict__ fanV)
+{
+    const double* X = M.points;
+    for (int f = blockIdx.x*ATPB + threadIdx.x; f < M.nFaces; f += gridDim.x*ATPB)
+    {
+        const int p0 = M.faceStart[f], n = M.faceStart[f + 1] - p0;
+        const int* fp = M.facePoints + p0;
+        if (n == 3)
+        {
+            const int i0 = fp[0], i1 = fp[1], i2 = fp[2];
+            double ab[3], ac[3], nrm[3], ctr[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) { ab[d] = sub(X[3*i1 + d], X[3*i0 + d]); ac[d] = sub(X[3*i2 + d], X[3*i0 + d]); }
+            cross3(ab, ac, nrm);
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+            {
+                nrm[d] = mul(0.5, nrm[d]);
+                ctr[d] = mul(1.0/3.0, add(add(X[3*i0 + d], X[3*i1 + d]), X[3*i2 + d]));
+                fanS[3*(size_t)p0 + d] = nrm[d];
+            }
+            fanV[p0] = dot3(nrm, ctr);
+            for (int p = 1; p < 3; p++) { fanV[p0 + p] = 0.0; fanS[3*(size_t)(p0 + p)] = fanS[3*(size_t)(p0 + p) + 1] = fanS[3*(size_t)(p0 + p) + 2] = 0.0; }
+            continue;
+        }
+        double centre[3] = {0.0, 0.0, 0.0};
+        for (int p = 0; p < n; p++)
+        {
+            const int ip = fp[p];
+#pragma unroll
+            for (int d = 0; d < 3; d++) centre[d] = add(centre[d], X[3*ip + d]);
+        }
+        const double dn = (double)n;
+#pragma unroll
+        for (int d = 0; d < 3; d++) centre[d] = (n == 4) ? mul(centre[d], 0.25) : dvd(centre[d], dn);
+        double Xa[3], Xb[3];
+        load3(X, fp[0], Xa);
+        for (int p = 0; p < n; p++)
+        {
+            load3(X, fp[(p + 1 == n) ? 0 : p + 1], Xb);
+            double a[3], b[3], St[3], Ct[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) { a[d] = sub(Xa[d], centre[d]); b[d] = sub(Xb[d], centre[d]); }
+            cross3(a, b, St);
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+            {
+                St[d] = mul(St[d], 0.5);
+                Ct[d] = div3(add(add(centre[d], Xa[d]), Xb[d]));
+                fanS[3*(size_t)(p0 + p) + d] = St[d];
+            }
+            fanV[p0 + p] = dot3(St, Ct);
+#pragma unroll
+            for (int d = 0; d < 3; d++) Xa[d] = Xb[d];
+        }
+    }
+}
+
+// V_c = (sum over the cell's faces, fan triangle by fan triangle, of +-St & Ct)/3   (fvcGradf.C:537,554-555,607-608,688-690)
+__global__ void __launch_bounds__(ATPB) k_cell_fan_volume(MeshDev M, const double* __restrict__ fanV, double* __restrict__ gradV)
+{
+    for (int c = blockIdx.x*ATPB + threadIdx.x; c < M.nCells; c += gridDim.x*ATPB)
+    {
+        double V = 0.0;
+        for (int k = M.cellFaceStart[c]; k < M.cellFaceStart[c + 1]; k++)
+        {
+            const int code = M.cellFace[k], f = code & 0x7fffffff;
+            const bool minus = code < 0;
+            const int p0 = M.faceStart[f], n = M.faceStart[f + 1] - p0;
+            const int nt = (n == 3) ? 1 : n;
+            for (int p = 0; p < nt; p++) V = minus ? sub(V, fanV[p0 + p]) : add(V, fanV[p0 + p]);
+        }
+        gradV[c] = div3(V);
+    }
+}
+
+// one face's contribution sign*(St*ttcf) with the pre-computed area vectors
+__device__ __forceinline__ void grad_face_pre(const MeshDev& M, int f, const double* __restrict__ pf, bool minus, double* G)
 {
     const int p0 = M.faceStart[f], n = M.faceStart[f + 1] - p0;
     const int* fp = M.facePoints + p0;
-    const double* X = M.points;
+    const double* S = M.fanS + 3*(size_t)p0;
     if (n == 3)
     {
         const int i0 = fp[0], i1 = fp[1], i2 = fp[2];
-        double ab[3], ac[3], nrm[3], avg[3], ctr[3];
-#pragma unroll
-        for (int d = 0; d < 3; d++) { ab[d] = sub(X[3*i1 + d], X[3*i0 + d]); ac[d] = sub(X[3*i2 + d], X[3*i0 + d]); }
-        cross3(ab, ac, nrm);
+        double avg[3], nrm[3];
 #pragma unroll
         for (int d = 0; d < 3; d++)
         {
-            nrm[d] = mul(0.5, nrm[d]);
             avg[d] = mul(1.0/3.0, add(add(pf[3*i0 + d], pf[3*i1 + d]), pf[3*i2 + d]));
-            ctr[d] = mul(1.0/3.0, add(add(X[3*i0 + d], X[3*i1 + d]), X[3*i2 + d]));
+            nrm[d] = minus ? -S[d] : S[d];
         }
 #pragma unroll
         for (int i = 0; i < 3; i++)
 #pragma unroll
-            for (int j = 0; j < 3; j++)
-            {
-                const double t = mul(nrm[i], avg[j]);
-                G[3*i + j] = minus ? sub(G[3*i + j], t) : add(G[3*i + j], t);
-            }
-        const double sr = dot3(nrm, ctr);
-        V = minus ? sub(V, sr) : add(V, sr);
+            for (int j = 0; j < 3; j++) G[3*i + j] = add(G[3*i + j], mul(nrm[i], avg[j]));
         return;
     }
-    if (n == 4)         // the hex case: the four points live in registers, the fan is unrolled
+    if (n == 4)
     {
-        double Xq[4][3], Pq[4][3], centre[3], cf[3];
+        double Pq[4][3], cf[3];
 #pragma unroll
-        for (int p = 0; p < 4; p++) { const int ip = fp[p]; load3(X, ip, Xq[p]); load3(pf, ip, Pq[p]); }
+        for (int p = 0; p < 4; p++) load3(pf, fp[p], Pq[p]);
 #pragma unroll
-        for (int d = 0; d < 3; d++)
+        for (int d = 0; d < 3; d++) cf[d] = mul(add(add(add(add(0.0, Pq[0][d]), Pq[1][d]), Pq[2][d]), Pq[3][d]), 0.25);
+#pragma unroll
+        for (int p = 0; p < 4; p++)
         {
-            centre[d] = mul(add(add(add(add(0.0, Xq[0][d]), Xq[1][d]), Xq[2][d]), Xq[3][d]), 0.25);
-            cf[d] = mul(add(add(add(add(0.0, Pq[0][d]), Pq[1][d]), Pq[2][d]), Pq[3][d]), 0.25);
-        }
+            double St[3], ttcf[3];
 #pragma unroll
-        for (int p = 0; p < 4; p++) fan_triangle(Xq[p], Xq[(p + 1) & 3], Pq[p], Pq[(p + 1) & 3], centre, cf, minus, G, V);
+            for (int d = 0; d < 3; d++)
+            {
+                St[d] = minus ? -S[3*p + d] : S[3*p + d];
+                ttcf[d] = div3(add(add(Pq[p][d], Pq[(p + 1) & 3][d]), cf[d]));
+            }
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) G[3*i + j] = add(G[3*i + j], mul(St[i], ttcf[j]));
+        }
         return;
     }
-    double centre[3] = {0.0, 0.0, 0.0}, cf[3] = {0.0, 0.0, 0.0};
+    double cf[3] = {0.0, 0.0, 0.0};
     for (int p = 0; p < n; p++)
     {
         const int ip = fp[p];
 #pragma unroll
-        for (int d = 0; d < 3; d++) { centre[d] = add(centre[d], X[3*ip + d]); cf[d] = add(cf[d], pf[3*ip + d]); }
+        for (int d = 0; d < 3; d++) cf[d] = add(cf[d], pf[3*ip + d]);
     }
     const double dn = (double)n;
 #pragma unroll
-    for (int d = 0; d < 3; d++) { centre[d] = dvd(centre[d], dn); cf[d] = dvd(cf[d], dn); }
-    double Xa[3], Pa[3], Xb[3], Pb[3];
-    load3(X, fp[0], Xa); load3(pf, fp[0], Pa);
+    for (int d = 0; d < 3; d++) cf[d] = dvd(cf[d], dn);
+    double Pa[3], Pb[3];
+    load3(pf, fp[0], Pa);
     for (int p = 0; p < n; p++)
     {
-        const int ib = fp[(p + 1 == n) ? 0 : p + 1];
-        load3(X, ib, Xb); load3(pf, ib, Pb);
-        fan_triangle(Xa, Xb, Pa, Pb, centre, cf, minus, G, V);
+        load3(pf, fp[(p + 1 == n) ? 0 : p + 1], Pb);
+        double St[3], ttcf[3];
 #pragma unroll
-        for (int d = 0; d < 3; d++) { Xa[d] = Xb[d]; Pa[d] = Pb[d]; }
+        for (int d = 0; d < 3; d++)
+        {
+            St[d] = minus ? -S[3*p + d] : S[3*p + d];
+            ttcf[d] = div3(add(add(Pa[d], Pb[d]), cf[d]));
+            Pa[d] = Pb[d];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) G[3*i + j] = add(G[3*i + j], mul(St[i], ttcf[j]));
     }
 }
 
@@ -567,17 +629,20 @@ __device__ void patch_snGrad(const MeshDev& M, int f, const double* __restrict__
 }
 
 // K6: fvc::grad(D, pointD) -- one thread per cell gathers its faces in the order the reference's face loop visits it
-__global__ void __launch_bounds__(ATPB) k_grad_cells(MeshDev M, const double* __restrict__ pointD, double* __restrict__ gradD)
+// gather-latency bound (cell -> faces -> points -> values): small blocks, as many as fit
+constexpr int GTPB = 128;
+__global__ void __launch_bounds__(GTPB, 5) k_grad_cells(MeshDev M, const double* __restrict__ pointD, double* __restrict__ gradD)
 {
-    for (int c = blockIdx.x*ATPB + threadIdx.x; c < M.nCells; c += gridDim.x*ATPB)
+    for (int c = blockIdx.x*GTPB + threadIdx.x; c < M.nCells; c += gridDim.x*GTPB)
     {
-        double G[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, V = 0.0;
-        for (int k = M.cellFaceStart[c]; k < M.cellFaceStart[c + 1]; k++)
+        double G[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        const int k1 = M.cellFaceStart[c + 1];
+        for (int k = M.cellFaceStart[c]; k < k1; k++)
         {
             const int code = M.cellFace[k];
-            grad_face(M, code & 0x7fffffff, pointD, code < 0, G, V);
+            grad_face_pre(M, code & 0x7fffffff, pointD, code < 0, G);
         }
-        V = div3(V);
+        const double V = M.gradV[c];
 #pragma unroll
         for (int q = 0; q < 9; q++) gradD[9*(size_t)c + q] = dvd(G[q], V);
     }
@@ -1006,6 +1071,15 @@ extern "C" int gpupcg_mesh_set_points(gpupcg_mesh m, int nPoints, const double* 
     const int nBF = M.nFaces - M.nIF;
     MCK(alloc(m, m->dPointD, 3*(size_t)nPoints)); MCK(alloc(m, m->dGradOld, 9*(size_t)M.nCells));
     MCK(alloc(m, m->dGradDb, 9*(size_t)nBF));
+    {
+        double *fanS = nullptr, *fanV = nullptr, *gradV = nullptr;
+        const size_t nSlots = (size_t)faceStart[M.nFaces];
+        MCK(alloc(m, fanS, 3*nSlots)); MCK(alloc(m, fanV, nSlots)); MCK(alloc(m, gradV, (size_t)M.nCells));
+        M.fanS = fanS; M.fanV = fanV; M.gradV = gradV;
+        k_fan_geometry<<<agrid(m, M.nFaces), ATPB, 0, m->stream>>>(M, fanS, fanV);
+        k_cell_fan_volume<<<agrid(m, M.nCells), ATPB, 0, m->stream>>>(M, fanV, gradV);
+        MCK(cudaGetLastError());
+    }
     MCK(cudaStreamSynchronize(m->stream));
     return GPUPCG_OK;
 }
@@ -1029,7 +1103,7 @@ extern "C" int gpupcg_gradients(gpupcg_mesh m, const double* D, const double* po
     MCK(cudaEventRecord(m->ev0, s));
     for (int r = 0; r < reps; r++)
     {
-        k_grad_cells<<<agrid(m, nC), ATPB, 0, s>>>(M, m->dPointD, m->dGradD);
+        k_grad_cells<<<std::max(1, std::min((nC + GTPB - 1)/GTPB, m->numSMs*32)), GTPB, 0, s>>>(M, m->dPointD, m->dGradD);
         if (nBF > 0)
             k_grad_patches<<<agrid(m, nBF), ATPB, 0, s>>>(M, m->dD, m->dPointD, m->dGradOld, m->dFixed, m->dPatchGrad, m->dGradDb);
         k_fgrad_faces<<<agrid(m, nF), ATPB, 0, s>>>(M, m->dD, m->dPointD, m->dGradD, m->dFixed, m->dPatchGrad, limitCoeff, m->dGradDf);
