@@ -14,7 +14,7 @@ namespace
 typedef struct { char internal[128]; } ncclUniqueId_t;
 typedef void* ncclComm_p;
 enum { NCCL_SUCCESS = 0 };
-enum { NCCL_INT64 = 4, NCCL_FLOAT64 = 8 };    // ncclDataType_t values
+enum { NCCL_INT8 = 0, NCCL_INT64 = 4, NCCL_FLOAT64 = 8 };    // ncclDataType_t values
 enum { NCCL_SUM = 0 };                         // ncclRedOp_t
 
 struct Api
@@ -24,6 +24,7 @@ struct Api
     int (*CommInitRank)(ncclComm_p*, int, ncclUniqueId_t, int) = nullptr;
     int (*CommDestroy)(ncclComm_p) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_p, cudaStream_t) = nullptr;
     int (*Send)(const void*, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
@@ -48,6 +49,7 @@ Api& api()
     BIND(CommInitRank, "ncclCommInitRank");
     BIND(CommDestroy, "ncclCommDestroy");
     BIND(AllReduce, "ncclAllReduce");
+    BIND(AllGather, "ncclAllGather");
     BIND(Send, "ncclSend");
     BIND(Recv, "ncclRecv");
     BIND(GroupStart, "ncclGroupStart");
@@ -106,8 +108,71 @@ int Comm::init(int rank, int nRanks, const void* id128, int nCellsLocal, cudaStr
     return 0;
 }
 
+P2PDev* Comm::setup_p2p(cudaStream_t s, std::string& note)
+{
+    Api& a = api();
+    if (!comm_ || !a.AllGather || nRanks_ > P2P_MAX_RANKS) { note = "p2p reduce: not available (no ncclAllGather / too many ranks)"; return nullptr; }
+    if (p2pDev_) return p2pDev_;
+    if (cudaMalloc((void**)&mbox_, sizeof(P2PMailbox)) != cudaSuccess) { note = "p2p reduce: cudaMalloc failed"; cudaGetLastError(); return nullptr; }
+    cudaMemsetAsync(mbox_, 0, sizeof(P2PMailbox), s);
+    cudaIpcMemHandle_t mine;
+    bool ok = cudaIpcGetMemHandle(&mine, mbox_) == cudaSuccess;
+    // every rank must take part in the gather even if its own handle failed: a zeroed handle marks the failure
+    unsigned char* d = nullptr;
+    const size_t hb = sizeof(cudaIpcMemHandle_t) + 8;       // handle + "valid" byte (padded)
+    std::vector<unsigned char> sendb(hb, 0), all(hb*nRanks_, 0);
+    if (ok) { memcpy(sendb.data(), &mine, sizeof(mine)); sendb[sizeof(mine)] = 1; } else cudaGetLastError();
+    if (cudaMalloc((void**)&d, hb*(nRanks_ + 1)) != cudaSuccess) { note = "p2p reduce: cudaMalloc failed"; cudaGetLastError(); return nullptr; }
+    cudaMemcpyAsync(d, sendb.data(), hb, cudaMemcpyHostToDevice, s);
+    int rc = a.AllGather(d, d + hb, hb, NCCL_INT8, (ncclComm_p)comm_, s);
+    if (rc == NCCL_SUCCESS) cudaMemcpyAsync(all.data(), d + hb, hb*nRanks_, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    cudaFree(d);
+    if (rc != NCCL_SUCCESS) { note = "p2p reduce: ncclAllGather of the IPC handles failed"; return nullptr; }
+    P2PDev h;
+    memset(&h, 0, sizeof(h));
+    h.rank = rank_; h.nRanks = nRanks_; h.seq = 0;
+    bool allOk = true;
+    for (int r = 0; r < nRanks_; r++) allOk = allOk && all[hb*r + sizeof(cudaIpcMemHandle_t)] == 1;
+    for (int r = 0; allOk && r < nRanks_; r++)
+    {
+        if (r == rank_) { h.peer[r] = mbox_; continue; }
+        cudaIpcMemHandle_t hr;
+        memcpy(&hr, &all[hb*r], sizeof(hr));
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, hr, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); allOk = false; break; }
+        opened_.push_back(ptr);
+        h.peer[r] = (P2PMailbox*)ptr;
+    }
+    // all ranks must agree: one more tiny all-reduce of the success flag
+    long long* flag = nullptr;
+    long long v = allOk ? 1 : 0;
+    if (cudaMalloc((void**)&flag, sizeof(long long)) == cudaSuccess)
+    {
+        cudaMemcpyAsync(flag, &v, sizeof(v), cudaMemcpyHostToDevice, s);
+        rc = a.AllReduce(flag, flag, 1, NCCL_INT64, NCCL_SUM, (ncclComm_p)comm_, s);
+        cudaMemcpyAsync(&v, flag, sizeof(v), cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+        cudaFree(flag);
+    }
+    else { cudaGetLastError(); v = 0; }
+    if (rc != NCCL_SUCCESS || v != nRanks_)
+    {
+        note = "p2p reduce: peer mapping (cudaIpcOpenMemHandle) not available on every rank; using ncclAllReduce";
+        return nullptr;
+    }
+    if (cudaMalloc((void**)&p2pDev_, sizeof(P2PDev)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    cudaMemcpyAsync(p2pDev_, &h, sizeof(h), cudaMemcpyHostToDevice, s);
+    cudaStreamSynchronize(s);
+    return p2pDev_;
+}
+
 void Comm::destroy()
 {
+    for (void* p : opened_) cudaIpcCloseMemHandle(p);
+    opened_.clear();
+    if (p2pDev_) { cudaFree(p2pDev_); p2pDev_ = nullptr; }
+    if (mbox_) { cudaFree(mbox_); mbox_ = nullptr; }
     if (comm_)
     {
         api().CommDestroy((ncclComm_p)comm_);

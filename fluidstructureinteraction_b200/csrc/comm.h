@@ -11,6 +11,25 @@
 namespace gpupcg
 {
 
+// One-shot scalar all-reduce over NVLink peer memory (the three gSumProd/gSumMag of a PCG iteration are 8-16 byte
+// all-reduces: pure latency).  Every rank owns a mailbox; the thread that finishes a grid reduction writes its partial
+// sums straight into every peer's mailbox (P2P stores through NVSwitch, then a release flag = sequence number), waits
+// for the peers' flags in its OWN mailbox, and sums the values in rank order -- the same bits on every rank, no
+// kernel launch, no NCCL call on the critical path.  Two buffers by sequence parity: a rank can run at most one
+// reduction ahead of the slowest one.
+static constexpr int P2P_MAX_RANKS = 16;
+struct P2PMailbox
+{
+    double val[2][P2P_MAX_RANKS][4];
+    unsigned long long flag[2][P2P_MAX_RANKS];
+};
+struct P2PDev
+{
+    int rank, nRanks;
+    unsigned long long seq;
+    P2PMailbox* peer[P2P_MAX_RANKS];        // peer[r]: rank r's mailbox mapped into this process (peer[rank]: own)
+};
+
 class Comm
 {
 public:
@@ -28,10 +47,17 @@ public:
                  const std::vector<int>& nbr, cudaStream_t s, std::string& err);
     int allreduce_sum(double* buf, int count, cudaStream_t s, std::string& err);
 
+    // peer-memory mailboxes (cudaIpc handles swapped with one ncclAllGather); returns the device-side descriptor or
+    // nullptr when peer mapping is not available (the NCCL all-reduce path stays in use then)
+    P2PDev* setup_p2p(cudaStream_t s, std::string& note);
+
 private:
     void* comm_ = nullptr;
     int rank_ = 0, nRanks_ = 1;
     long long globalCells_ = 0;
+    P2PMailbox* mbox_ = nullptr;
+    P2PDev* p2pDev_ = nullptr;
+    std::vector<void*> opened_;
 };
 
 } // namespace gpupcg

@@ -57,6 +57,8 @@ struct gpupcg_handle_s
     cudaEvent_t evCheck[2] = {nullptr, nullptr};
     cudaStream_t commStream = nullptr;  // halo swaps, overlapped with the interior Amul (multi-rank only)
     cudaEvent_t evX = nullptr, evHalo = nullptr;
+    P2PDev* dP2P = nullptr;            // scalar all-reduces through peer-memory mailboxes (owned by comm)
+    std::string p2pNote;
     int amulGrid = 1;               // persistent CTAs of the Amul kernel
     bool hasOvf = false;            // some row has more than four faces on one side (polyhedral cells)
     int partStride = MAXPART;
@@ -710,6 +712,7 @@ static int halo_exchange(gpupcg_handle h, const double* x, bool* overlapped)
 static int allreduce_step(gpupcg_handle h, int step, int count)
 {
     if (!h->comm.active()) return GPUPCG_OK;
+    if (h->dP2P) return GPUPCG_OK;      // summed across ranks inside the kernel that finished the reduction
     if (h->comm.allreduce_sum((double*)((char*)h->dState + offsetof(DevState, red)), count, h->stream, h->err) != 0)
         return GPUPCG_ERR_NCCL;
     h->launches++; k_scalar_step<<<1, 32, 0, h->stream>>>(h->dState, step, h->dHistory);
@@ -842,6 +845,7 @@ static int solve_core(gpupcg_handle h, double tol, double relTol, int minIter, i
     init.nGlobalCells = h->comm.active() ? h->comm.globalCells(P.nCells) : P.nCells;
     init.historyCap = std::min(h->historyCap, std::max(0, maxIter));
     init.multiRank = h->comm.active() ? 1 : 0;
+    init.p2p = h->comm.active() ? h->dP2P : nullptr;
     init.wArA = K_MGREAT; init.wArAold = K_MGREAT;
     *h->hState = init;
     CK(cudaMemcpyAsync(h->dState, h->hState, sizeof(DevState), cudaMemcpyHostToDevice, s));
@@ -1126,6 +1130,12 @@ extern "C" int gpupcg_comm_init(gpupcg_handle h, int rank, int nRanks, const voi
     if (!h || !id128 || rank < 0 || rank >= nRanks) return GPUPCG_ERR_ARG;
     CK(cudaSetDevice(h->device));
     if (h->comm.init(rank, nRanks, id128, h->plan.nCells, h->stream, h->err) != 0) return GPUPCG_ERR_NCCL;
+    h->dP2P = env_int("GPUPCG_P2P_REDUCE", 1) ? h->comm.setup_p2p(h->stream, h->p2pNote) : nullptr;
+    if (!h->dP2P && env_int("GPUPCG_P2P_REDUCE", 1) == 2)    // 2: insist
+    {
+        h->err = "gpupcg_comm_init: " + h->p2pNote;
+        return GPUPCG_ERR_NCCL;
+    }
     if (!h->commStream && env_int("GPUPCG_OVERLAP_HALO", 1))
     {
         CK(cudaStreamCreateWithFlags(&h->commStream, cudaStreamNonBlocking));

@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "plan.h"
+#include "comm.h"
 
 namespace gpupcg
 {
@@ -50,6 +51,7 @@ struct DevState
     int historyCap, multiRank;
     unsigned int ticket;
     int pending;                // an x/r update (alpha known, wA = A pA) has not been applied yet
+    P2PDev* p2p;                // multi-rank: peer-memory mailboxes for the scalar all-reduces (null: ncclAllReduce + k_scalar_step)
 };
 
 enum ScalarStep { S_INIT = 0, S_NORM = 1, S_SWEEP = 2, S_AMUL = 3, S_XR = 4 };
@@ -111,6 +113,36 @@ __device__ __forceinline__ void dev_scalar_step(DevState* st, int step, const do
     }
 }
 
+// One-shot all-reduce of st->red[0..count) through the peers' mailboxes (comm.h), by ONE thread: write my values and
+// then my flag (= sequence number, release at system scope) into every rank's mailbox, wait for every rank's flag in my
+// own mailbox, sum in rank order.  Every rank gets the same bits.
+__device__ __forceinline__ void p2p_allreduce(P2PDev* c, const double* mine, int count, double* out)
+{
+    const unsigned long long seq = ++c->seq;
+    const int par = (int)(seq & 1ULL), me = c->rank;
+    for (int r = 0; r < c->nRanks; r++)
+    {
+        P2PMailbox* m = c->peer[r];
+        for (int k = 0; k < count; k++)
+            asm volatile("st.relaxed.sys.global.f64 [%0], %1;" :: "l"(&m->val[par][me][k]), "d"(mine[k]) : "memory");
+    }
+    for (int r = 0; r < c->nRanks; r++)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(&c->peer[r]->flag[par][me]), "l"(seq) : "memory");
+    P2PMailbox* own = c->peer[me];
+    for (int k = 0; k < count; k++) out[k] = 0.0;
+    for (int r = 0; r < c->nRanks; r++)
+    {
+        unsigned long long f;
+        do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&own->flag[par][r]) : "memory"); } while (f != seq);
+        for (int k = 0; k < count; k++)
+        {
+            double v;
+            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(&own->val[par][r][k]) : "memory");
+            out[k] += v;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // deterministic grid reduction: block tree -> partials[block] -> the last block to finish sums the
 // partials in a fixed order and either advances the scalar recurrence (single rank) or parks the
@@ -118,7 +150,8 @@ __device__ __forceinline__ void dev_scalar_step(DevState* st, int step, const do
 // ------------------------------------------------------------------------------------------
 template <int NV, int NT>
 __device__ __forceinline__ void grid_reduce_finish(double (&v)[NV], double* partials, int stride, int slot, int nSlots,
-                                                   DevState* st, int step, double* history, int redSlot = 0)
+                                                   DevState* st, int step, double* history, int redSlot = 0,
+                                                   bool lastOfStep = true)
 {
     constexpr int NW = NT/32;
     __shared__ double sm[NV][NW];
@@ -180,6 +213,15 @@ __device__ __forceinline__ void grid_reduce_finish(double (&v)[NV], double* part
 #pragma unroll
             for (int k = 0; k < NV; k++) st->red[redSlot + k] = f[k];
             if (step == S_AMUL && redSlot == 0) st->red[1] = 0.0;
+            if (st->p2p && lastOfStep)
+            {
+                // the cross-rank sum and the scalar step happen right here (no ncclAllReduce, no k_scalar_step launch)
+                const int count = (step == S_AMUL || step == S_NORM) ? 2 : 1;
+                double loc[2] = {st->red[0], st->red[1]}, g[4] = {0.0, 0.0, 0.0, 0.0};
+                p2p_allreduce(st->p2p, loc, count, g);
+                if (step == S_AMUL) g[0] = g[0] + g[1];
+                if (!(st->done && step >= S_SWEEP)) dev_scalar_step(st, step, g, history);
+            }
         }
         else
         {
@@ -624,7 +666,8 @@ __global__ void __launch_bounds__(AMUL_TPB) k_amul_tile(TileArgs A, const double
         Mcur = Mnext;
         Mnext = M2;
     }
-    if (MODE == 1) grid_reduce_finish<1, AMUL_TPB>(dot, partials, partStride, blockIdx.x, gridDim.x, st, S_AMUL, nullptr);
+    // with coupled faces k_iface_update<1> adds their rows' part of the dot and closes the step
+    if (MODE == 1) grid_reduce_finish<1, AMUL_TPB>(dot, partials, partStride, blockIdx.x, gridDim.x, st, S_AMUL, nullptr, 0, ifMask == nullptr);
 }
 
 #ifndef GPUPCG_SWEEP_TPB
