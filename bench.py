@@ -38,6 +38,17 @@ if ROOT not in sys.path:
 # stdout carries exactly one JSON line: NCCL's version banner / debug output goes to stderr
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
+# The contract is ONE JSON line on stdout.  Libraries write banners there on their own (NCCL prints its version line
+# to fd 1 at communicator creation whatever NCCL_DEBUG_FILE says), so fd 1 is pointed at stderr for the whole run and
+# the JSON line is written to the saved, real stdout at the end.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 TOL, RELTOL = 1e-9, 0.01
 TRACTION = (0.5e4, 0.25e4, -1.0e4)          # all three components get a non-zero source
 METRIC = "D-eqn PCG cell-updates/s (cells x PCG iterations / s; 3 component solves per step)"
@@ -165,7 +176,7 @@ def run_reference(args, nx, ny, nz):
         "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "iterations_per_step": float(np.mean(iters)), "host_cores": cores,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_name(nx, ny, nz, gpus):
@@ -422,7 +433,7 @@ def run_ours(args, nx, ny, nz):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
 
 
 def main():
