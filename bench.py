@@ -13,9 +13,12 @@ steel, fixedDisplacement at x=0, traction on x=L.  N>1: configs[2], the 64 M-cel
 decomposed into one sub-domain per GPU with processor-patch halos and global reductions over NCCL.
 
 metric  : PCG cell-updates/s = cells x PCG iterations / time  (whole job, all ranks); solves/s beside it.
-value   : matrix, x0, b resident in HBM (gpupcg_set_matrix once, gpupcg_solve_device per component).
-e2e     : the same step through the reference-facing C-ABI calls with HOST buffers: gpupcg_set_matrix(diag,
-          upper) + gpupcg_solve(x, b) per component, pinned host memory, H2D/D2H inside the timed region.
+The three component solves of a step go through the component-batched entry points (gpupcg_set_matrix_vector /
+gpupcg_solve_vector: fvMatrix<vector>::solve's component loop in one launch sequence, every kernel advances the three
+systems together); --scalar-solves runs them one after the other through gpupcg_set_matrix / gpupcg_solve instead.
+value   : matrix, x0, b resident in HBM (gpupcg_set_matrix_vector once, gpupcg_solve_vector_device per step).
+e2e     : the same step through the reference-facing C-ABI calls with HOST buffers: gpupcg_set_matrix_vector(diag per
+          component, upper) + gpupcg_solve_vector(x, b), pinned host memory, H2D/D2H inside the timed region.
 roofline: dominant kernel of the step by measured time, algorithmic bytes / CUDA-event time,
           against MEASURED_PEAKS.json hbm_gbs; the Amul figure BASELINE.json names is in roofline_amul.
 cpu_baseline: the CPU oracle (port of the reference's foam-extend PCG/DIC loops, oracle/ldu_oracle.c) on a
@@ -49,6 +52,9 @@ def emit(line):
     sys.stdout.flush()
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
+# DRAM bytes per launch of the batched kernels (ncu --set full, profiles/r1d_ncu_full_1M_vector.md); None until captured
+NCU_TRAFFIC_1M_VECTOR = {}
+
 TOL, RELTOL = 1e-9, 0.01
 TRACTION = (0.5e4, 0.25e4, -1.0e4)          # all three components get a non-zero source
 METRIC = "D-eqn PCG cell-updates/s (cells x PCG iterations / s; 3 component solves per step)"
@@ -64,6 +70,8 @@ def parse_args():
     ap.add_argument("--cpu-maxiter", type=int, default=0,
                     help="iteration cap of the bounded CPU sample (default: ~4e8 cell-updates per solve, 4..40)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scalar-solves", action="store_true",
+                    help="three sequential scalar component solves per step (gpupcg_solve) instead of the batched vector solve")
     ap.add_argument("--no-8m", action="store_true",
                     help="skip the extra 8.1 M-cell kernel measurements (Amul / DIC / assembly roofline fractions the north star quotes)")
     return ap.parse_args()
@@ -249,6 +257,15 @@ def measure_8m(peak):
     for k, nbytes in (("amul", cases.amul_bytes(n, nF)), ("dic", cases.dic_bytes(n, nF)), ("p_update", 24*n), ("xr_update", 48*n)):
         t = g.time_kernel(k, reps=10, flushL2=True)
         out[k] = {"ms": t, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes/t/1e6, "frac": nbytes/t/1e6/peak}
+    # the batched kernels (what a D-equation solve runs): one launch advances the three component systems
+    g.set_matrix_vector(np.ascontiguousarray(np.stack([s["diag"]]*3, axis=1)), s["upper"])
+    if g.vector_mode(3) == 1:
+        xv = np.zeros((n, 3))
+        g.solve_vector(xv, np.ascontiguousarray(np.stack([s["b"]*t for t in TRACTION], axis=1)), 1e-9, 0.01, 0, 4, history=False)
+        for k, nbytes in (("amul", cases.amul_bytes(n, nF)), ("dic", cases.dic_bytes(n, nF)), ("p_update", 24*n), ("xr_update", 48*n)):
+            t = g.time_kernel_vector(3, k, reps=10, flushL2=True)
+            out[k + "_batched3"] = {"ms": t, "systems_per_launch": 3, "algorithmic_bytes": 3*nbytes,
+                                    "achieved_gbs": 3*nbytes/t/1e6, "frac": 3*nbytes/t/1e6/peak}
     g.close()
     del s
     out.update(measure_assembly(nx, ny, nz, peak))
@@ -299,11 +316,26 @@ def run_ours(args, nx, ny, nz):
         torch.cuda.synchronize()
 
     # ---- device-resident arm -------------------------------------------------------------------------------------
-    g.set_matrix(diag, upper, patchBouCoeffs=bou)
-    d_b = [torch.from_numpy(bunit*t).cuda() for t in TRACTION]
-    d_x = [torch.zeros(n, dtype=torch.float64, device="cuda") for _ in TRACTION]
+    vector = not args.scalar_solves
+    diagC = np.ascontiguousarray(np.stack([diag]*3, axis=1))                # addBoundaryDiag per component: equal here
+    bC = np.ascontiguousarray(np.stack([bunit*t for t in TRACTION], axis=1))
+    bouC = [np.ascontiguousarray(np.stack([bb]*3, axis=1)) for bb in bou]
+    if vector:
+        g.set_matrix_vector(diagC, upper, patchBouCoeffsCmpt=bouC)
+        vmode = g.vector_mode(3)
+        d_bv = torch.from_numpy(bC).cuda()
+        d_xv = torch.zeros((n, 3), dtype=torch.float64, device="cuda")
+    else:
+        g.set_matrix(diag, upper, patchBouCoeffs=bou)
+        vmode = None
+        d_b = [torch.from_numpy(bunit*t).cuda() for t in TRACTION]
+        d_x = [torch.zeros(n, dtype=torch.float64, device="cuda") for _ in TRACTION]
 
     def step_device():
+        if vector:
+            d_xv.zero_()
+            perfs, _ = g.solve_vector_device(3, d_xv.data_ptr(), d_bv.data_ptr(), TOL, RELTOL, 0, 1000)
+            return sum(p["nIterations"] for p in perfs)
         its = 0
         for c in range(3):
             d_x[c].zero_()
@@ -340,12 +372,20 @@ def run_ours(args, nx, ny, nz):
     keep = []
     _, h_diag = pinned(diag); keep.append(_)
     _, h_upper = pinned(upper); keep.append(_)
+    _, h_diagC = pinned(diagC); keep.append(_)
+    _, h_bC = pinned(bC); keep.append(_)
+    _, h_xC = pinned(np.zeros((n, 3))); keep.append(_)
     h_b, h_x = [], []
     for t in TRACTION:
         tb, nb = pinned(bunit*t); keep.append(tb); h_b.append(nb)
         tx, nxx = pinned(np.zeros(n)); keep.append(tx); h_x.append(nxx)
 
     def step_e2e():
+        if vector:
+            g.set_matrix_vector(h_diagC, h_upper, patchBouCoeffsCmpt=bouC)
+            h_xC[:] = 0.0
+            perfs, _ = g.solve_vector(h_xC, h_bC, TOL, RELTOL, 0, 1000, history=False)
+            return sum(p["nIterations"] for p in perfs)
         its = 0
         for c in range(3):
             g.set_matrix(h_diag, h_upper if c == 0 else None, patchBouCoeffs=bou)
@@ -367,7 +407,7 @@ def run_ours(args, nx, ny, nz):
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     ms_e2e = float(ms2.item())
-    h2d = 3*8*n + 8*nF + 3*16*n
+    h2d = 3*8*n + 8*nF + 3*16*n          # diag per component + upper + x0 and b per component (either path)
     d2h = 3*8*n
 
     # ---- per-kernel roofline (rank 0, live CUDA-event timing on the launching stream, L2 flushed) --------------
@@ -376,30 +416,40 @@ def run_ours(args, nx, ny, nz):
         peak, peak_src = peaks()
         reps = 20
         kb = {"amul": cases.amul_bytes(n, nF), "dic": cases.dic_bytes(n, nF), "p_update": 24*n, "xr_update": 48*n}
+        batched = bool(vector and vmode == 1)
+        nsys = 3 if batched else 1          # systems one launch advances
+        if not vector:
+            pass
+        elif not batched:
+            g.set_matrix(diag, upper, patchBouCoeffs=bou)
         kern = {}
         for k, nbytes in kb.items():
-            t = g.time_kernel(k, reps=reps, flushL2=True)
-            kern[k] = {"ms": t, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes/t/1e6, "frac": nbytes/t/1e6/peak}
+            t = g.time_kernel_vector(3, k, reps=reps, flushL2=True) if batched else g.time_kernel(k, reps=reps, flushL2=True)
+            kern[k] = {"ms": t, "systems_per_launch": nsys, "algorithmic_bytes": nsys*nbytes,
+                       "achieved_gbs": nsys*nbytes/t/1e6, "frac": nsys*nbytes/t/1e6/peak}
         # inside a solve the x/r update rides in the staging of the next forward sweep (no launch of its own): the
         # iteration is amul + dic + p_update; k_xr_update is timed standalone for reference only
-        fused_xr = bool(info.get("sweepTables", 1)) and os.environ.get("GPUPCG_FUSE_XR", "1") != "0"
+        fused_xr = bool(info.get("sweepTables", 1)) and os.environ.get("GPUPCG_FUSE_XR", "1") != "0" and n <= 3000000
         tot = sum(v["ms"] for k, v in kern.items() if not (fused_xr and k == "xr_update"))
         for k, v in kern.items():
             v["share_of_iteration"] = None if (fused_xr and k == "xr_update") else v["ms"]/tot
         dom_k = max(kern, key=lambda k: kern[k]["ms"])
-        names = {"amul": "k_amul (lduMatrix::Amul + wApA)", "dic": "k_dic_sweeps (DIC forward+backward + wArA)",
-                 "p_update": "k_p_update", "xr_update": "k_xr_update (+ sum|rA|)"}
+        sfx = "_v<3>" if batched else ""
+        names = {"amul": "k_amul_tile%s (lduMatrix::Amul + wApA)" % sfx,
+                 "dic": "k_dic_tile%s forward + backward (DIC precondition + wArA)" % sfx,
+                 "p_update": "k_p_update%s" % sfx, "xr_update": "k_xr_update%s (+ sum|rA|)" % sfx}
 
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
-        # workload (profiles/r1c_ncu_full_1M_pcg.md); only valid for the default 1 M-cell single-GPU case
-        ncu_traffic = {"dic": 75.4e6 + 75.1e6, "amul": 71.4e6, "p_update": 16.0e6, "xr_update": 32.8e6} \
-            if (world == 1 and (nx, ny, nz) == (200, 50, 100)) else {}
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this
+        # workload (profiles/); only valid for the default 1 M-cell single-GPU case
+        ncu_traffic = {}
+        if world == 1 and (nx, ny, nz) == (200, 50, 100):
+            ncu_traffic = NCU_TRAFFIC_1M_VECTOR if batched else {"dic": 75.4e6 + 75.1e6, "amul": 71.4e6, "p_update": 16.0e6, "xr_update": 32.8e6}
 
         def roof(k):
             return {"kernel": names[k], "bound": "hbm", "achieved": kern[k]["achieved_gbs"], "peak": peak,
                     "unit": "GB/s", "frac": kern[k]["frac"], "traffic": ncu_traffic.get(k), "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": kern[k]["algorithmic_bytes"], "ms_per_launch": kern[k]["ms"],
-                    "share_of_iteration": kern[k]["share_of_iteration"]}
+                    "algorithmic_bytes_per_launch": kern[k]["algorithmic_bytes"], "systems_per_launch": nsys,
+                    "ms_per_launch": kern[k]["ms"], "share_of_iteration": kern[k]["share_of_iteration"]}
 
         value = nGlobal*iters/(ms_dev*1e-3)
         line = {
@@ -408,6 +458,8 @@ def run_ours(args, nx, ny, nz):
             "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(nx, ny, nz, world), "cells": nGlobal, "internal_faces": int(nFglobal),
                        "tolerance": TOL, "relTol": RELTOL, "solver": "gpuPCG", "preconditioner": "DIC",
+                       "component_solves": ("batched: gpupcg_solve_vector, 3 systems per launch" if batched else
+                                            "sequential: 3 x gpupcg_solve"),
                        "parallelism": "1 sub-domain/GPU x %d" % world,
                        "l2": "working set (%.0f MB) vs 126 MB L2: inputs larger than L2 at >= 1M cells; kernel timings flush L2" %
                              (cases.pcg_iteration_bytes(n, nF)/1e6)},

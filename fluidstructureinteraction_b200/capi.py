@@ -75,6 +75,14 @@ SYMBOLS = {
     "gpupcg_dic_factor": (C.c_int, [C.c_void_p, c_double_p]),
     "gpupcg_precondition": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
     "gpupcg_time_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]),
+    "gpupcg_vector_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "gpupcg_set_matrix_vector": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, C.POINTER(c_double_p)]),
+    "gpupcg_set_matrix_vector_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gpupcg_solve_vector": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, C.c_double, C.c_double, C.c_int, C.c_int,
+                                      C.POINTER(Perf), c_double_p, C.c_int]),
+    "gpupcg_solve_vector_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int,
+                                             C.c_int, C.POINTER(Perf), c_double_p, C.c_int]),
+    "gpupcg_time_kernel_vector": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p]),
     "gpupcg_comm_unique_id": (C.c_int, [C.c_void_p]),
     "gpupcg_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "gpupcg_mesh_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, C.c_int,
@@ -251,6 +259,58 @@ class GpuPCG(object):
     def time_kernel(self, which, reps=10, flushL2=True):
         ms = C.c_double(0.0)
         self._check(self.lib.gpupcg_time_kernel(self.h, self.KERNELS[which], reps, 1 if flushL2 else 0, C.byref(ms)))
+        return ms.value
+
+    # ---- component-batched solve (fvMatrix<vector>::solve's component loop in one launch sequence)
+    def vector_mode(self, nCmpt=3):
+        """1: the batched kernels run; 0: the components are solved one after the other on the scalar kernels."""
+        rc = self.lib.gpupcg_vector_mode(self.h, nCmpt)
+        if rc < 0:
+            self._check(rc)
+        return rc
+
+    def set_matrix_vector(self, diagCmpt, upper=None, patchBouCoeffsCmpt=()):
+        """diagCmpt: (nCells, nCmpt) = diag + internalCoeffs per component; upper shared (None keeps the previous)."""
+        diagCmpt = _f64(diagCmpt)
+        assert diagCmpt.ndim == 2 and diagCmpt.shape[0] == self.nCells
+        upper = _f64(upper) if upper is not None else None
+        bc = [_f64(b) for b in patchBouCoeffsCmpt]
+        ptrs = (c_double_p * max(len(bc), 1))(*[_dp(b) for b in bc]) if bc else None
+        self._check(self.lib.gpupcg_set_matrix_vector(self.h, diagCmpt.shape[1], _dp(diagCmpt), _dp(upper), ptrs))
+
+    def set_matrix_vector_device(self, nCmpt, d_diagCmpt, d_upper=None, d_bou=None):
+        self._check(self.lib.gpupcg_set_matrix_vector_device(self.h, nCmpt, C.c_void_p(d_diagCmpt),
+                                                             C.c_void_p(d_upper) if d_upper else None,
+                                                             C.c_void_p(d_bou) if d_bou else None))
+
+    def _vec_result(self, perf, hist, nCmpt, history):
+        ds = [perf[k].as_dict() for k in range(nCmpt)]
+        hs = [hist[k, :min(ds[k]["nIterations"], hist.shape[1])].copy() for k in range(nCmpt)] if history else None
+        return ds, hs
+
+    def solve_vector(self, x, b, tolerance=1e-6, relTol=0.0, minIter=0, maxIter=1000, history=True):
+        """x: (nCells, nCmpt) float64 C-contiguous, in/out.  Returns ([perf dict per component], [history per component])."""
+        if not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.c_contiguous and x.ndim == 2):
+            raise TypeError("x must be a C-contiguous float64 (nCells, nCmpt) ndarray (psi.internalField(), in/out)")
+        nCmpt = x.shape[1]
+        b = _f64(b)
+        assert b.shape == x.shape
+        perf = (Perf*nCmpt)()
+        hist = np.zeros((nCmpt, max(maxIter, 1)), dtype=np.float64) if history else None
+        self._check(self.lib.gpupcg_solve_vector(self.h, nCmpt, _dp(x), _dp(b), tolerance, relTol, minIter, maxIter, perf,
+                                                 _dp(hist), hist.shape[1] if history else 0))
+        return self._vec_result(perf, hist, nCmpt, history)
+
+    def solve_vector_device(self, nCmpt, d_x, d_b, tolerance=1e-6, relTol=0.0, minIter=0, maxIter=1000, history=False):
+        perf = (Perf*nCmpt)()
+        hist = np.zeros((nCmpt, max(maxIter, 1)), dtype=np.float64) if history else None
+        self._check(self.lib.gpupcg_solve_vector_device(self.h, nCmpt, C.c_void_p(d_x), C.c_void_p(d_b), tolerance, relTol,
+                                                        minIter, maxIter, perf, _dp(hist), hist.shape[1] if history else 0))
+        return self._vec_result(perf, hist, nCmpt, history)
+
+    def time_kernel_vector(self, nCmpt, which, reps=10, flushL2=True):
+        ms = C.c_double(0.0)
+        self._check(self.lib.gpupcg_time_kernel_vector(self.h, nCmpt, self.KERNELS[which], reps, 1 if flushL2 else 0, C.byref(ms)))
         return ms.value
 
     def comm_init(self, rank, nRanks, unique_id_bytes):

@@ -181,18 +181,19 @@ void Comm::destroy()
 }
 
 int Comm::exchange(const double* send, double* recv, const std::vector<int>& patchStart,
-                   const std::vector<int>& nbr, cudaStream_t s, std::string& err)
+                   const std::vector<int>& nbr, cudaStream_t s, std::string& err, int nb)
 {
     Api& a = api();
     int rc = a.GroupStart();
     if (rc != NCCL_SUCCESS) return fail(err, "ncclGroupStart", rc);
     for (size_t p = 0; p + 1 < patchStart.size(); p++)
     {
-        const size_t n = (size_t)(patchStart[p + 1] - patchStart[p]);
+        const size_t n = (size_t)nb*(size_t)(patchStart[p + 1] - patchStart[p]);
         if (n == 0 || nbr[p] < 0) continue;
-        rc = a.Send(send + patchStart[p], n, NCCL_FLOAT64, nbr[p], (ncclComm_p)comm_, s);
+        const size_t off = (size_t)nb*(size_t)patchStart[p];
+        rc = a.Send(send + off, n, NCCL_FLOAT64, nbr[p], (ncclComm_p)comm_, s);
         if (rc != NCCL_SUCCESS) return fail(err, "ncclSend", rc);
-        rc = a.Recv(recv + patchStart[p], n, NCCL_FLOAT64, nbr[p], (ncclComm_p)comm_, s);
+        rc = a.Recv(recv + off, n, NCCL_FLOAT64, nbr[p], (ncclComm_p)comm_, s);
         if (rc != NCCL_SUCCESS) return fail(err, "ncclRecv", rc);
     }
     rc = a.GroupEnd();

@@ -20,7 +20,7 @@ namespace gpupcg
 static constexpr int P2P_MAX_RANKS = 16;
 struct P2PMailbox
 {
-    double val[2][P2P_MAX_RANKS][4];
+    double val[2][P2P_MAX_RANKS][8];       // up to 2 sums x 3 components per step (vector solve)
     unsigned long long flag[2][P2P_MAX_RANKS];
 };
 struct P2PDev
@@ -42,9 +42,9 @@ public:
     int init(int rank, int nRanks, const void* id128, int nCellsLocal, cudaStream_t s, std::string& err);
     void destroy();
 
-    // send[patchStart[p]..) -> rank nbr[p];  recv[patchStart[p]..) <- rank nbr[p]
+    // send[patchStart[p]..) -> rank nbr[p];  recv[patchStart[p]..) <- rank nbr[p]   (nb values per face, interleaved)
     int exchange(const double* send, double* recv, const std::vector<int>& patchStart,
-                 const std::vector<int>& nbr, cudaStream_t s, std::string& err);
+                 const std::vector<int>& nbr, cudaStream_t s, std::string& err, int nb = 1);
     int allreduce_sum(double* buf, int count, cudaStream_t s, std::string& err);
 
     // peer-memory mailboxes (cudaIpc handles swapped with one ncclAllGather); returns the device-side descriptor or

@@ -3,6 +3,7 @@
 // fallback -- without a CUDA device every entry point fails with GPUPCG_ERR_NODEVICE.
 #include "../../include/gpupcg.h"
 #include "kernels.cuh"
+#include "kernels_vec.cuh"
 #include "plan.h"
 #include "comm.h"
 
@@ -79,6 +80,23 @@ struct gpupcg_handle_s
     long long flushN = 0;
 
     Comm comm;
+
+    // ---- component-batched ("vector") solve: fvMatrix<vector>::solve's NB systems advanced together (gpupcg_vec.cuh)
+    long long uvalVersion = 0, vTabVersion = -1;    // dUval writes / the version the vector path's row tables were built from
+    int vNB = 0;                    // components the buffers below are sized for (0: none yet)
+    bool vBatched = false;          // batched kernels usable (table variant, shared memory fits); else sequential scalar solves
+    bool vHaveMatrix = false;
+    size_t smemCap = 0;
+    double *vDiag = nullptr, *vRD = nullptr, *vX = nullptr, *vB = nullptr, *vRA = nullptr, *vWA = nullptr, *vPA = nullptr, *vY = nullptr;
+    double *vStageX = nullptr, *vStageB = nullptr, *vStageD = nullptr;     // [nCells*NB] caller's order
+    double *vTmpX = nullptr, *vTmpB = nullptr;                              // [nCells] sequential fall-back
+    double *vBou = nullptr, *vXNbr = nullptr, *vSend = nullptr;            // [nIfaceFaces*NB]
+    double *vPartials = nullptr, *vHistory = nullptr;
+    double *dTabSq = nullptr, *dTabUF = nullptr, *dTabUB = nullptr;        // [nRows*4] upper^2 / upper per row and side
+    DevState* vState = nullptr;
+    DevState* hvRing = nullptr;     // pinned: 3 x NB states
+    size_t smemFwdV = 0, smemBwdV = 0, smemFacV = 0, smemAmulV = 0;
+    int amulGridV = 1;
 };
 
 #define CK(call)                                                                                   \
@@ -177,8 +195,12 @@ extern "C" int gpupcg_destroy(gpupcg_handle h)
                     h->dTileStart, h->dTileItemPtr, h->dItems, h->dColL16, h->dIdxL16, h->dColU16,
                     h->dExtFPtr, h->dExtFCol, h->dExtFIdx, h->dExtBPtr, h->dExtBCol, h->dTileTicket,
                     h->dAmulMeta, h->dAmulU16, h->dAmulL32, h->dAmulExtX, h->dAmulExtC,
-                    h->dTabCF, h->dTabCB, h->dTabIF, h->dTabIB, h->dTabF, h->dTabB};
+                    h->dTabCF, h->dTabCB, h->dTabIF, h->dTabIB, h->dTabF, h->dTabB,
+                    h->vDiag, h->vRD, h->vX, h->vB, h->vRA, h->vWA, h->vPA, h->vY, h->vStageX, h->vStageB, h->vStageD,
+                    h->vTmpX, h->vTmpB, h->vBou, h->vXNbr, h->vSend, h->vPartials, h->vHistory, h->dTabSq, h->dTabUF,
+                    h->dTabUB, h->vState};
     for (void* p : ptrs) if (p) cudaFree(p);
+    if (h->hvRing) cudaFreeHost(h->hvRing);
     if (h->hState) cudaFreeHost(h->hState);
     if (h->hStateRing) cudaFreeHost(h->hStateRing);
     for (auto& e : h->evCheck) if (e) cudaEventDestroy(e);
@@ -351,8 +373,11 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     // tile size: as large as the shared-memory carve-up of one CTA allows (several CTAs per SM wanted)
     // default tile: 512 rows for bricks of a structured block (16 x 4 x 8), 256 for the greedy tiles of general meshes
     const bool tileRowsGiven = getenv("GPUPCG_TILE_ROWS") && *getenv("GPUPCG_TILE_ROWS");
-    int tileRows = env_int("GPUPCG_TILE_ROWS", 512);
+    // 256 rows (bricks 8 x 4 x 8): what the component-batched sweeps want (their CTAs carry three systems' tiles in
+    // shared memory); the scalar sweeps alone are ~8 % faster at 1 M cells with 512 (16 x 4 x 8)
+    int tileRows = env_int("GPUPCG_TILE_ROWS", 256);
     const size_t smemCap = (size_t)std::min<long long>(prop.sharedMemPerBlockOptin, 200*1024);
+    h->smemCap = smemCap;
     int rc;
     while (true)
     {
@@ -618,6 +643,7 @@ static int matrix_from_staging(gpupcg_handle h, bool haveUpper)
     if (haveUpper)
     {
         LAUNCH(k_coeffs_in, grid_for(P.entriesU, h->streamGrid), s, h->dStageF, h->dUval, h->dUfaceOld, P.entriesU);
+        h->uvalVersion++;
     }
     CK(cudaGetLastError());
     h->haveMatrix = true;
@@ -669,7 +695,10 @@ extern "C" int gpupcg_set_matrix_device(gpupcg_handle h, const double* d_diag, c
     cudaStream_t s = h->stream;
     LAUNCH(k_rows_in, grid_for(P.nRows, h->streamGrid), s, d_diag, h->dDiag, h->dRowOld, P.nRows, 1.0);
     if (d_upper)
+    {
         LAUNCH(k_coeffs_in, grid_for(P.entriesU, h->streamGrid), s, d_upper, h->dUval, h->dUfaceOld, P.entriesU);
+        h->uvalVersion++;
+    }
     else if (!h->haveMatrix && P.nFaces > 0) { h->err = "gpupcg_set_matrix_device: no coefficients yet"; return GPUPCG_ERR_STATE; }
     if (d_bou && P.nIfaceFaces > 0)
         CK(cudaMemcpyAsync(h->dBou, d_bou, sizeof(double)*P.nIfaceFaces, cudaMemcpyDeviceToDevice, s));
@@ -1144,3 +1173,5 @@ extern "C" int gpupcg_comm_init(gpupcg_handle h, int rank, int nRanks, const voi
     }
     return GPUPCG_OK;
 }
+
+#include "gpupcg_vec.cuh"

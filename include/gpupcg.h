@@ -156,6 +156,36 @@ int gpupcg_precondition(gpupcg_handle h, const double* rA, double* wA);
  * 2 pA update, 3 x/r update + residual norm, 4 DIC factor.  Returns mean ms per launch.        */
 int gpupcg_time_kernel(gpupcg_handle h, int which, int reps, int flushL2, double* ms_per_launch);
 
+/* ---- component-batched solve ------------------------------------------------------------------
+ * fvMatrix<vector>::solve [EXT fvMatrixSolve.C], as DEqn.solve() reaches it (unsTotalLagrangianStress.C:908;
+ * unsTotalLagrangianStressSolve.C:378,560), loops over the valid components: diag + internalCoeffs.component(cmpt),
+ * source.component(cmpt), one lduMatrix::solver::New(...)->solve(psiCmpt, sourceCmpt, cmpt) each.  The nCmpt (2 or 3)
+ * systems share upper() and lduAddr(), differ in diag and source, and are independent -- and the DIC sweeps of ONE
+ * system are bound by the latency of their dependency chain.  These entry points take the whole loop: every kernel
+ * advances all components in the same launch (kernels_vec.cuh), each component runs the reference's PCG recurrence
+ * with its own scalars and stops on its own (results per component = those of gpupcg_solve on that component).
+ *   diagCmpt            : [nCells*nCmpt], foam's Field<vector> layout (component-minor): matrix.diag() after
+ *                         addBoundaryDiag(diag, cmpt) for every cmpt
+ *   upper               : matrix.upper() (NULL keeps the previous coefficients)
+ *   patchBouCoeffsCmpt  : per coupled patch [size*nCmpt] = coupleBouCoeffs (boundaryCoeffs.component(cmpt))
+ *   x, b                : [nCells*nCmpt] = psi.internalField() (in/out) and the total source, same layout
+ *   perfCmpt            : [nCmpt];  history: [nCmpt*historyCap] (component-major) or NULL
+ * Meshes with more than four faces per row and side (polyhedra) and multi-rank runs without peer-memory mailboxes
+ * run the components one after the other on the scalar kernels (gpupcg_vector_mode returns 0 then, 1 when batched). */
+int gpupcg_vector_mode(gpupcg_handle h, int nCmpt);
+int gpupcg_set_matrix_vector(gpupcg_handle h, int nCmpt, const double* diagCmpt, const double* upper,
+                             const double* const* patchBouCoeffsCmpt);
+int gpupcg_set_matrix_vector_device(gpupcg_handle h, int nCmpt, const double* d_diagCmpt, const double* d_upper,
+                                    const double* d_patchBouCoeffsCmptConcat);
+int gpupcg_solve_vector(gpupcg_handle h, int nCmpt, double* x, const double* b,
+                        double tolerance, double relTol, int minIter, int maxIter,
+                        gpupcg_perf* perfCmpt, double* history_or_null, int historyCap);
+int gpupcg_solve_vector_device(gpupcg_handle h, int nCmpt, double* d_x, const double* d_b,
+                               double tolerance, double relTol, int minIter, int maxIter,
+                               gpupcg_perf* perfCmpt, double* history_or_null, int historyCap);
+/* gpupcg_time_kernel for the batched kernels (same `which` codes; one launch advances nCmpt systems). */
+int gpupcg_time_kernel_vector(gpupcg_handle h, int nCmpt, int which, int reps, int flushL2, double* ms_per_launch);
+
 /* ---- multi-GPU -------------------------------------------------------------------------------
  * One handle per rank/GPU (decomposePar sub-domain).  ncclUniqueId is the 128-byte
  * ncclUniqueId obtained on rank 0 (gpupcg_comm_unique_id) and broadcast by the host side

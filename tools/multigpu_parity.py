@@ -23,6 +23,51 @@ uid = [pkg.comm_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(uid, src=0)
 g.comm_init(rank, world, uid[0])
 g.set_matrix(s["diag"], s["upper"], patchBouCoeffs=s["patchBouCoeffs"])
+subs = [cases.cantilever_subdomain(nx, ny, nz, px, py, pz, r) for r in range(world)] if rank == 0 else None
+
+
+def compare(tag, pg, hg, xs, tol, rel, dscale=1.0, bscale=1.0):
+    """rank 0: the GPU result (perf, history, per-rank fields) against the oracle on the same partition."""
+    doms = []
+    for r, q in enumerate(subs):
+        back = [subs[t]["patchNbrDomain"].index(r) for t in q["patchNbrDomain"]]
+        doms.append(dict(l=q["l"], u=q["u"], diag=q["diag"]*dscale, upper=q["upper"], b=q["b"]*bscale, x=np.zeros(q["nCells"]),
+                         patchFaceCells=q["patchFaceCells"], patchBouCoeffs=q["patchBouCoeffs"],
+                         patchNbrDomain=q["patchNbrDomain"], patchNbrPatch=back))
+    # sensitivity envelope: the oracle against ITSELF with nothing changed but the association of its reductions
+    # (pairwise instead of sequential sums).  The GPU necessarily re-associates them too; it has to stay within
+    # 1e-10 relative, or -- where CG amplifies re-association beyond that -- within 16x that envelope (the growth is
+    # chaotic: one pairwise sample under-estimates the spread between two arbitrary associations by a small factor;
+    # measured on 2 B200: GPU 4.3e-10 where pairwise-vs-sequential is 6.0e-11 at iteration 31 of 33, both ~1e-14
+    # for the first 24 iterations).
+    oracle.set_sum_mode(1)
+    pp, hp = oracle.pcg_solve_multi([dict(d, x=np.zeros_like(d["x"])) for d in doms], tol, rel)
+    oracle.set_sum_mode(0)
+    pc, hc = oracle.pcg_solve_multi(doms, tol, rel)
+    m = min(len(hp), len(hc))
+    env = np.zeros(len(hc))
+    env[:m] = np.maximum.accumulate(np.abs(hp[:m] - hc[:m]))
+    if m < len(hc):
+        env[m:] = env[m - 1] if m else 0.0
+    scale = max(float(np.max(np.abs(hc))), pc["initialResidual"])
+    xscale = max(max(np.max(np.abs(d["x"])) for d in doms), 1e-300)
+    xenv = 4*float(np.max(np.abs(hp[m - 1] - hc[m - 1])/abs(hc[m - 1]))) if m else 0.0
+    good = (pg["nIterations"] == pc["nIterations"]
+            and np.all(np.abs(hg - hc) <= 1e-10*np.abs(hc) + 1e-13*scale + 16*env)
+            and all(np.max(np.abs(xs[r] - doms[r]["x"])) <= max(1e-9, xenv)*xscale for r in range(world)))
+    print(tag, "relTol", rel, "gpu iters", pg["nIterations"], "oracle iters", pc["nIterations"],
+          "max hist rel diff gpu-vs-oracle %.2e, oracle pairwise-vs-sequential %.2e" %
+          (float(np.max(np.abs(hg - hc)/np.abs(hc))), float(np.max(np.abs(hp[:m] - hc[:m])/np.abs(hc[:m])))),
+          "max field rel diff %.2e" % max(float(np.max(np.abs(xs[r] - doms[r]["x"]))/xscale) for r in range(world)),
+          "OK" if good else "MISMATCH", flush=True)
+    if not good:
+        rg = np.abs(hg - hc)/np.abs(hc); rp = np.zeros_like(rg); rp[:m] = np.abs(hp[:m] - hc[:m])/np.abs(hc[:m])
+        for i in range(len(hc)):
+            print("   it %3d  res %.6e  gpu-vs-oracle %.2e  pairwise-vs-seq %.2e  bound %.2e" % (
+                i, hc[i], rg[i], rp[i], (1e-10*abs(hc[i]) + 1e-13*scale + 16*env[i])/abs(hc[i])), flush=True)
+    return good
+
+
 ok = True
 for tol, rel in ((1e-9, 0.01), (1e-9, 0.0)):
     x = np.zeros(s["nCells"])
@@ -30,49 +75,26 @@ for tol, rel in ((1e-9, 0.01), (1e-9, 0.0)):
     xs = [None]*world
     dist.all_gather_object(xs, x)
     if rank == 0:
-        subs = [cases.cantilever_subdomain(nx, ny, nz, px, py, pz, r) for r in range(world)]
-        doms = []
-        for r, q in enumerate(subs):
-            back = [subs[t]["patchNbrDomain"].index(r) for t in q["patchNbrDomain"]]
-            doms.append(dict(l=q["l"], u=q["u"], diag=q["diag"], upper=q["upper"], b=q["b"], x=np.zeros(q["nCells"]),
-                             patchFaceCells=q["patchFaceCells"], patchBouCoeffs=q["patchBouCoeffs"],
-                             patchNbrDomain=q["patchNbrDomain"], patchNbrPatch=back))
-        pc, hc = oracle.pcg_solve_multi(doms, tol, rel)
-        # sensitivity envelope: the oracle against ITSELF with nothing changed but the association of its reductions
-        # (pairwise instead of sequential sums).  The GPU necessarily re-associates them too; it has to stay within
-        # 1e-10 relative, or -- where CG amplifies re-association beyond that -- within 16x that envelope (the growth is
-        # chaotic: one pairwise sample under-estimates the spread between two arbitrary associations by a small factor;
-        # measured on 2 B200: GPU 4.3e-10 where pairwise-vs-sequential is 6.0e-11 at iteration 31 of 33, both ~1e-14
-        # for the first 24 iterations).
-        for d in doms:
-            d["x"][:] = 0.0
-        xs_seq = None
-        oracle.set_sum_mode(1)
-        pp, hp = oracle.pcg_solve_multi([dict(d, x=np.zeros_like(d["x"])) for d in doms], tol, rel)
-        oracle.set_sum_mode(0)
-        pc, hc = oracle.pcg_solve_multi(doms, tol, rel)
-        m = min(len(hp), len(hc))
-        env = np.zeros(len(hc))
-        env[:m] = np.maximum.accumulate(np.abs(hp[:m] - hc[:m]))
-        if m < len(hc):
-            env[m:] = env[m - 1] if m else 0.0
-        scale = max(float(np.max(np.abs(hc))), pc["initialResidual"])
-        xscale = max(max(np.max(np.abs(d["x"])) for d in doms), 1e-300)
-        xenv = 4*float(np.max(np.abs(hp[m - 1] - hc[m - 1])/abs(hc[m - 1]))) if m else 0.0
-        good = (pg["nIterations"] == pc["nIterations"]
-                and np.all(np.abs(hg - hc) <= 1e-10*np.abs(hc) + 1e-13*scale + 16*env)
-                and all(np.max(np.abs(xs[r] - doms[r]["x"])) <= max(1e-9, xenv)*xscale for r in range(world)))
-        print("relTol", rel, "gpu iters", pg["nIterations"], "oracle iters", pc["nIterations"],
-              "max hist rel diff gpu-vs-oracle %.2e, oracle pairwise-vs-sequential %.2e" %
-              (float(np.max(np.abs(hg - hc)/np.abs(hc))), float(np.max(np.abs(hp[:m] - hc[:m])/np.abs(hc[:m])))),
-              "max field rel diff %.2e" % max(float(np.max(np.abs(xs[r] - doms[r]["x"]))/xscale) for r in range(world)),
-              "OK" if good else "MISMATCH", flush=True)
-        if not good:
-            rg = np.abs(hg - hc)/np.abs(hc); rp = np.zeros_like(rg); rp[:m] = np.abs(hp[:m] - hc[:m])/np.abs(hc[:m])
-            for i in range(len(hc)):
-                print("   it %3d  res %.6e  gpu-vs-oracle %.2e  pairwise-vs-seq %.2e  bound %.2e" % (
-                    i, hc[i], rg[i], rp[i], (1e-10*abs(hc[i]) + 1e-13*scale + 16*env[i])/abs(hc[i])), flush=True)
-        ok = ok and good
+        ok = compare("scalar", pg, hg, xs, tol, rel) and ok
+
+# the component-batched solve over the same communicator: three systems (diag and source scaled per component, so they
+# stop at different iterations), halos of three values per face, the scalar all-reduces of all components in one
+# peer-memory exchange
+DS, BS = (1.0, 1.25, 1.0), (1.0, 0.5, -2.0)
+dC = np.ascontiguousarray(np.stack([s["diag"]*d for d in DS], axis=1))
+bC = np.ascontiguousarray(np.stack([s["b"]*b for b in BS], axis=1))
+bouC = [np.ascontiguousarray(np.stack([bb]*3, axis=1)) for bb in s["patchBouCoeffs"]]
+g.set_matrix_vector(dC, s["upper"], patchBouCoeffsCmpt=bouC)
+mode = g.vector_mode(3)
+for tol, rel in ((1e-9, 0.01), (1e-9, 0.0)):
+    xv = np.zeros((s["nCells"], 3))
+    pv, hv = g.solve_vector(xv, bC, tol, rel)
+    xs = [None]*world
+    dist.all_gather_object(xs, xv)
+    if rank == 0:
+        for k in range(3):
+            ok = compare("vector[%d] mode %d" % (k, mode), pv[k], hv[k], [np.ascontiguousarray(a[:, k]) for a in xs], tol, rel,
+                         DS[k], BS[k]) and ok
 g.close()
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, 0)
