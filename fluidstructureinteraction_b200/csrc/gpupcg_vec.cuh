@@ -186,7 +186,7 @@ int vec_sweeps(gpupcg_handle h, double* rA, double* z, bool reduce, int gated, b
     const FuseXR none{nullptr, nullptr, nullptr, nullptr, nullptr};
     const FuseXR fx = fuseXR ? FuseXR{h->vX, h->vPA, zb, h->vRA, h->vHistory} : none;
     h->launches += 2;
-    k_dic_tile_v<NB, 0><<<h->sweepGrid, SWEEP_TPB, h->smemFwdV, h->stream>>>(h->tiles, h->vRD, rA, nullptr, yb, nullptr,
+    k_dic_tile_v<NB, 0><<<h->sweepGrid, SWEEP_TPB, fuseXR ? h->smemFwdV : h->smemFacV, h->stream>>>(h->tiles, h->vRD, rA, nullptr, yb, nullptr,
         h->dTileTicket, h->vPartials, h->partStride, h->vState, gated, h->dTabCF, h->dTabUF, fx, h->historyCap);
     k_dic_tile_v<NB, 2><<<h->sweepGrid, SWEEP_TPB, h->smemBwdV, h->stream>>>(h->tiles, h->vRD, rA, yb, zb, nullptr,
         h->dTileTicket, reduce ? h->vPartials : nullptr, h->partStride, h->vState, gated, h->dTabCB, h->dTabUB, none, 0);

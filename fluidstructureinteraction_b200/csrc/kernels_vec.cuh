@@ -650,13 +650,14 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile_v(TileArgs A, const doub
     }
     extern __shared__ __align__(128) unsigned char smemRaw[];
     const int X = BWD ? A.maxExtB : A.maxExtF;
-    const SweepLayout L = tabv_layout<NB>(A.tileRowsMax, X, A.maxItems, MODE == 0);
+    const SweepLayout L = tabv_layout<NB>(A.tileRowsMax, X, A.maxItems, fused);
     // the shared window base goes through an opaque move: ptxas otherwise rematerialises it INSIDE the round loop
     // (S2R SR_CgaCtaId + LEA, ~25 cycles in front of the dependency loads of every round)
     unsigned sb;
     asm volatile("mov.u32 %0, %1;" : "=r"(sb) : "r"((unsigned)__cvta_generic_to_shared(smemRaw)));
     const unsigned vb = sb + L.vals;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long tBegin = (g_tileTimes && threadIdx.x == 0) ? gtime() : 0ULL;
     const int tile = take_tile(tileTicket, A.nTiles, (int*)(smemRaw + L.slot), BWD);
     const int r0 = A.tileStart[tile], nr = A.tileStart[tile + 1] - r0;
     const int ip = A.tileItemPtr[tile], nItems = A.tileItemPtr[tile + 1] - ip;
@@ -729,6 +730,7 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile_v(TileArgs A, const doub
         __syncthreads();                // the sweep warp forms its start values from the updated residual
     }
 
+    if (g_tileTimes && threadIdx.x == 0 && MODE == 0) { g_tileTimes[3*tile] = tBegin; g_tileTimes[3*tile + 1] = gtime(); }
     if (warp == 0)
     {
         const unsigned ib = sb + L.items;
@@ -797,6 +799,7 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile_v(TileArgs A, const doub
             if (d0.y & syncBit) __syncwarp();
             cur = nxt; d0 = d1; d1 = d2;
         }
+        if (g_tileTimes && lane == 0 && MODE == 0) g_tileTimes[3*tile + 2] = gtime();
     }
     else
     {
@@ -913,6 +916,24 @@ __global__ void __launch_bounds__(TPB) k_norm_v(const double* __restrict__ wA, c
     grid_reduce_finish_v<2, NB, TPB>(v, partials, MAXPART, blockIdx.x, gridDim.x, st, S_NORM, nullptr, 0);
 }
 
+// one row (NS doubles, 16- or 32-byte aligned) per access: 256-bit loads/stores for NB = 3
+template <int NB>
+__device__ __forceinline__ void grow_load(const double* p, double (&v)[VecStride<NB>::v])
+{
+    if (NB == 3)
+        asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[VecStride<NB>::v - 1]) : "l"(p));
+    else
+        asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+}
+template <int NB>
+__device__ __forceinline__ void grow_store(double* p, const double (&v)[VecStride<NB>::v])
+{
+    if (NB == 3)
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[VecStride<NB>::v - 1]) : "memory");
+    else
+        asm volatile("st.global.v2.f64 [%0], {%1, %2};" :: "l"(p), "d"(v[0]), "d"(v[1]) : "memory");
+}
+
 template <int NB>
 __global__ void __launch_bounds__(TPB) k_p_update_v(const double* __restrict__ wA, double* __restrict__ pA,
                                                     long long nFlat, const DevState* __restrict__ st)
@@ -928,16 +949,17 @@ __global__ void __launch_bounds__(TPB) k_p_update_v(const double* __restrict__ w
         first[k] = (st[k].nIter == 0);
         beta[k] = first[k] ? 0.0 : __ddiv_rn(st[k].wArA, st[k].wArAold);
     }
-    for (long long i = (long long)blockIdx.x*TPB + threadIdx.x; i < nFlat; i += (long long)gridDim.x*TPB)
+    const long long nRows = nFlat/NS;
+    for (long long r = (long long)blockIdx.x*TPB + threadIdx.x; r < nRows; r += (long long)gridDim.x*TPB)
     {
-        const int k = (int)(i % NS);
-        bool fi = first[0], sk = skip[0]; double be = beta[0];
+        double w[NS], p[NS];
+        grow_load<NB>(wA + r*NS, w);
+        grow_load<NB>(pA + r*NS, p);
 #pragma unroll
-        for (int c = 1; c < NB; c++) { if (k == c) { fi = first[c]; sk = skip[c]; be = beta[c]; } }
-        if (k >= NB) { pA[i] = 0.0; continue; }
-        if (sk) continue;
-        const double w = wA[i];
-        pA[i] = fi ? w : __dadd_rn(w, __dmul_rn(be, pA[i]));
+        for (int k = 0; k < NB; k++)
+            if (!skip[k]) p[k] = first[k] ? w[k] : __dadd_rn(w[k], __dmul_rn(beta[k], p[k]));
+        if (NS > NB) p[NS - 1] = 0.0;
+        grow_store<NB>(pA + r*NS, p);
     }
 }
 
@@ -959,24 +981,30 @@ __global__ void __launch_bounds__(TPB) k_xr_update_v(const double* __restrict__ 
         v[k] = 0.0;
     }
     if (!any) return;
-    for (long long i = (long long)blockIdx.x*TPB + threadIdx.x; i < nFlat; i += (long long)gridDim.x*TPB)
+    const long long nRows = nFlat/NS;
+    double sent[NS];
+#pragma unroll
+    for (int k = 0; k < NS; k++) sent[k] = __longlong_as_double((long long)SENT);
+    for (long long r = (long long)blockIdx.x*TPB + threadIdx.x; r < nRows; r += (long long)gridDim.x*TPB)
     {
-        const int k = (int)(i % NS);
-        bool pe = pend[0]; double al = alpha[0];
+        double w[NS], p[NS], xx[NS], rr[NS];
+        grow_load<NB>((const double*)wAbits + r*NS, w);
+        grow_load<NB>(pA + r*NS, p);
+        grow_load<NB>(x + r*NS, xx);
+        grow_load<NB>(rA + r*NS, rr);
 #pragma unroll
-        for (int c = 1; c < NB; c++) { if (k == c) { pe = pend[c]; al = alpha[c]; } }
-        if (k >= NB) pe = false;
-        if (pe)
+        for (int k = 0; k < NB; k++)
         {
-            const double w = __longlong_as_double((long long)wAbits[i]);
-            x[i] = __dadd_rn(x[i], __dmul_rn(al, pA[i]));
-            const double rr = __dsub_rn(rA[i], __dmul_rn(al, w));
-            rA[i] = rr;
-            const double m = fabs(rr);
-#pragma unroll
-            for (int c = 0; c < NB; c++) v[c] += (k == c) ? m : 0.0;
+            if (pend[k])
+            {
+                xx[k] = __dadd_rn(xx[k], __dmul_rn(alpha[k], p[k]));
+                rr[k] = __dsub_rn(rr[k], __dmul_rn(alpha[k], w[k]));
+                v[k] += fabs(rr[k]);
+            }
         }
-        wAbits[i] = SENT;
+        grow_store<NB>(x + r*NS, xx);
+        grow_store<NB>(rA + r*NS, rr);
+        grow_store<NB>((double*)wAbits + r*NS, sent);
     }
     grid_reduce_finish_v<1, NB, TPB>(v, partials, MAXPART, blockIdx.x, gridDim.x, st, S_XR, history, histStride);
 }

@@ -124,20 +124,34 @@ void Foam::gpuPCG::clearCache()
 }
 
 
-Foam::lduMatrix::solverPerformance Foam::gpuPCG::solve
+namespace Foam
+{
+
+// Coupled (processor) interfaces of a sub-domain, in interface order
+struct gpuPCGPatches
+{
+    std::vector<int> ids, sizes, nbr;
+    std::vector<const int*> faceCells;
+};
+
+// Device handle for an lduAddressing (created once per mesh) + its communicator in a parallel run
+static gpuPCGCacheEntry& gpuPCGAcquire
 (
-    scalarField& x,
-    const scalarField& b,
-    const direction cmpt
-) const
+    const lduMatrix& matrix_,
+    const lduInterfaceFieldPtrsList& interfaces_,
+    const label device_,
+    const label nCells,
+    gpuPCGPatches& P
+)
 {
     const lduAddressing& addr = matrix_.lduAddr();
-    const label nCells = x.size();
     const label nFaces = addr.lowerAddr().size();
+    std::vector<int>& patchIds = P.ids;
+    std::vector<int>& patchSizes = P.sizes;
+    std::vector<int>& patchNbr = P.nbr;
+    std::vector<const int*>& patchFaceCells = P.faceCells;
 
     // --- Coupled (processor) interfaces of this sub-domain, in interface order
-    std::vector<int> patchIds, patchSizes, patchNbr;
-    std::vector<const int*> patchFaceCells;
     forAll(interfaces_, patchI)
     {
         if (interfaces_.set(patchI))
@@ -219,6 +233,25 @@ Foam::lduMatrix::solverPerformance Foam::gpuPCG::solve
     }
 #endif
 
+    return entry;
+}
+
+} // End namespace Foam
+
+
+Foam::lduMatrix::solverPerformance Foam::gpuPCG::solve
+(
+    scalarField& x,
+    const scalarField& b,
+    const direction cmpt
+) const
+{
+    const label nCells = x.size();
+    gpuPCGPatches P;
+    gpuPCGCacheEntry& entry = gpuPCGAcquire(matrix_, interfaces_, device_, nCells, P);
+    const std::vector<int>& patchIds = P.ids;
+    const int nPatches = patchIds.size();
+
     // --- Matrix: diag always (addBoundaryDiag changes it per component), upper only when it changed
     const scalarField& upper = matrix_.upper();
     const scalar check = upperFingerprint(upper);
@@ -276,6 +309,82 @@ Foam::lduMatrix::solverPerformance Foam::gpuPCG::solve
     );
 
     return solverPerf;
+}
+
+
+void Foam::gpuPCG::solveVector
+(
+    const label nCmpt,
+    scalar* x,
+    const scalar* b,
+    const scalar* diagCmpt,
+    const std::vector<const scalar*>& coupleBouCoeffsCmpt,
+    std::vector<lduMatrix::solverPerformance>& perfCmpt
+) const
+{
+    static const char* cmptNames[3] = {"x", "y", "z"};
+    const label nCells = matrix_.lduAddr().size();
+    gpuPCGPatches P;
+    gpuPCGCacheEntry& entry = gpuPCGAcquire(matrix_, interfaces_, device_, nCells, P);
+    const int nPatches = P.ids.size();
+
+    const scalarField& upper = matrix_.upper();
+    const scalar check = upperFingerprint(upper);
+    const bool sameUpper =
+        reuseUpper_ && entry.upperPtr == upper.begin() && entry.upperCheck == check;
+
+    std::vector<const scalar*> bouPtrs(nPatches);
+    for (int p = 0; p < nPatches; p++)
+    {
+        bouPtrs[p] = coupleBouCoeffsCmpt[P.ids[p]];
+    }
+
+    int rc = gpupcg_set_matrix_vector
+    (
+        entry.handle, nCmpt, diagCmpt,
+        sameUpper ? NULL : upper.begin(),
+        nPatches ? &bouPtrs[0] : NULL
+    );
+    if (rc != GPUPCG_OK)
+    {
+        FatalErrorIn("gpuPCG::solveVector(...)")
+            << "gpupcg_set_matrix_vector failed (" << rc << "): " << gpupcg_last_error(entry.handle)
+            << abort(FatalError);
+    }
+    entry.upperPtr = upper.begin();
+    entry.upperCheck = check;
+
+    gpupcg_perf perf[3];
+    rc = gpupcg_solve_vector
+    (
+        entry.handle, nCmpt, x, b,
+        tolerance_, relTolerance_, minIter_, maxIter_,
+        perf, NULL, 0
+    );
+    if (rc != GPUPCG_OK)
+    {
+        FatalErrorIn("gpuPCG::solveVector(...)")
+            << "gpupcg_solve_vector failed (" << rc << "): " << gpupcg_last_error(entry.handle)
+            << abort(FatalError);
+    }
+
+    perfCmpt.clear();
+    for (label c = 0; c < nCmpt; c++)
+    {
+        perfCmpt.push_back
+        (
+            lduMatrix::solverPerformance
+            (
+                preconName_ + typeName,
+                fieldName_ + cmptNames[c],
+                perf[c].initialResidual,
+                perf[c].finalResidual,
+                perf[c].nIterations,
+                perf[c].converged != 0,
+                perf[c].singular != 0
+            )
+        );
+    }
 }
 
 

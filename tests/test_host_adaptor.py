@@ -82,10 +82,14 @@ def test_adaptor_fails_loudly_without_gpu():
 
 
 @pytest.mark.gpu
-def test_segregated_vector_solve_matches_reference_flow():
+@pytest.mark.parametrize("batch", ["yes", "no"])
+def test_segregated_vector_solve_matches_reference_flow(batch):
+    """DEqn.solve() through the C++ host side: `batchComponents yes` (default) hands the three components to
+    gpuPCG::solveVector (one device launch sequence), `no` runs fvMatrix<vector>::solve's component loop over
+    gpuPCG::solve -- both must reproduce the reference flow component by component."""
     l, u, diag, upper, source, patches = vector_system(30, 8, 12)
     psi = np.zeros_like(source)
-    worst, per = hostapi.solve("D", l, u, diag, upper, source, patches, FVSOLUTION_D, psi)
+    worst, per = hostapi.solve("D", l, u, diag, upper, source, patches, FVSOLUTION_D + "    batchComponents %s;\n" % batch, psi)
     ref, perfs = reference_segregated(l, u, diag, upper, source, patches, 1e-9, 0.01)
     assert [p["fieldName"] for p in per] == ["Dx", "Dy", "Dz"]
     assert all(p["solverName"] == "DICgpuPCG" for p in per)
