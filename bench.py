@@ -52,8 +52,9 @@ def emit(line):
     sys.stdout.flush()
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
-# DRAM bytes per launch of the batched kernels (ncu --set full, profiles/r1d_ncu_full_1M_vector.md); None until captured
-NCU_TRAFFIC_1M_VECTOR = {}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the batched kernels (three systems per launch) from the
+# committed `ncu --set full` capture of this workload (profiles/r1d_vector_solve.md)
+NCU_TRAFFIC_1M_VECTOR = {"amul": 113.2e6 + 12.9e6, "dic": (140.6e6 + 15.5e6) + (173.3e6 + 38.2e6), "p_update": 64.0e6 + 0.5e6}
 
 TOL, RELTOL = 1e-9, 0.01
 TRACTION = (0.5e4, 0.25e4, -1.0e4)          # all three components get a non-zero source
