@@ -32,9 +32,14 @@ int vec_prepare(gpupcg_handle h)
                && std::max(h->smemFwdV, h->smemBwdV) <= h->smemCap && h->smemAmulV <= h->smemCap;
     if (h->vBatched)
     {
-        CK(cudaFuncSetAttribute((k_dic_tile_v<NB, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwdV));
-        CK(cudaFuncSetAttribute((k_dic_tile_v<NB, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFacV));
-        CK(cudaFuncSetAttribute((k_dic_tile_v<NB, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBwdV));
+        CK(cudaFuncSetAttribute((k_dic_tile_v<NB, 0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwdV));
+        CK(cudaFuncSetAttribute((k_dic_tile_v<NB, 1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFacV));
+        CK(cudaFuncSetAttribute((k_dic_tile_v<NB, 2, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBwdV));
+        CK(cudaFuncSetAttribute((k_dic_tile_v<NB, 0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwdV));
+        CK(cudaFuncSetAttribute((k_dic_tile_v<NB, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBwdV));
+        // latency-bound sweeps (small sub-domains) take the bank-swizzled variant, throughput-bound ones the leaner one
+        const int swEnv = env_int("GPUPCG_SWEEP_SWIZZLE", -1);
+        h->vSwizzle = (swEnv >= 0) ? (swEnv != 0) : (P.nRows <= env_int("GPUPCG_FUSE_XR_MAXROWS", 3000000));
         CK(cudaFuncSetAttribute((k_amul_tile_v<NB, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemAmulV));
         CK(cudaFuncSetAttribute((k_amul_tile_v<NB, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemAmulV));
         CK(cudaFuncSetAttribute((k_amul_tile_v<NB, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemAmulV));
@@ -169,7 +174,7 @@ int vec_factor(gpupcg_handle h, int gated)
     vec_fill_sent<NB>(h, h->vY);
     const FuseXR none{nullptr, nullptr, nullptr, nullptr, nullptr};
     h->launches++;
-    k_dic_tile_v<NB, 1><<<h->sweepGrid, SWEEP_TPB, h->smemFacV, h->stream>>>(h->tiles, h->vDiag, nullptr, nullptr,
+    k_dic_tile_v<NB, 1, false><<<h->sweepGrid, SWEEP_TPB, h->smemFacV, h->stream>>>(h->tiles, h->vDiag, nullptr, nullptr,
         (unsigned long long*)h->vY, h->vRD, h->dTileTicket, nullptr, 0, h->vState, gated, h->dTabCF, h->dTabSq, none, 0);
     vec_fill_sent<NB>(h, h->vY);
     CK(cudaGetLastError());
@@ -186,10 +191,22 @@ int vec_sweeps(gpupcg_handle h, double* rA, double* z, bool reduce, int gated, b
     const FuseXR none{nullptr, nullptr, nullptr, nullptr, nullptr};
     const FuseXR fx = fuseXR ? FuseXR{h->vX, h->vPA, zb, h->vRA, h->vHistory} : none;
     h->launches += 2;
-    k_dic_tile_v<NB, 0><<<h->sweepGrid, SWEEP_TPB, fuseXR ? h->smemFwdV : h->smemFacV, h->stream>>>(h->tiles, h->vRD, rA, nullptr, yb, nullptr,
-        h->dTileTicket, h->vPartials, h->partStride, h->vState, gated, h->dTabCF, h->dTabUF, fx, h->historyCap);
-    k_dic_tile_v<NB, 2><<<h->sweepGrid, SWEEP_TPB, h->smemBwdV, h->stream>>>(h->tiles, h->vRD, rA, yb, zb, nullptr,
-        h->dTileTicket, reduce ? h->vPartials : nullptr, h->partStride, h->vState, gated, h->dTabCB, h->dTabUB, none, 0);
+    const size_t smF = fuseXR ? h->smemFwdV : h->smemFacV;
+    double* part = reduce ? h->vPartials : nullptr;
+    if (h->vSwizzle)
+    {
+        k_dic_tile_v<NB, 0, true><<<h->sweepGrid, SWEEP_TPB, smF, h->stream>>>(h->tiles, h->vRD, rA, nullptr, yb, nullptr,
+            h->dTileTicket, h->vPartials, h->partStride, h->vState, gated, h->dTabCF, h->dTabUF, fx, h->historyCap);
+        k_dic_tile_v<NB, 2, true><<<h->sweepGrid, SWEEP_TPB, h->smemBwdV, h->stream>>>(h->tiles, h->vRD, rA, yb, zb, nullptr,
+            h->dTileTicket, part, h->partStride, h->vState, gated, h->dTabCB, h->dTabUB, none, 0);
+    }
+    else
+    {
+        k_dic_tile_v<NB, 0, false><<<h->sweepGrid, SWEEP_TPB, smF, h->stream>>>(h->tiles, h->vRD, rA, nullptr, yb, nullptr,
+            h->dTileTicket, h->vPartials, h->partStride, h->vState, gated, h->dTabCF, h->dTabUF, fx, h->historyCap);
+        k_dic_tile_v<NB, 2, false><<<h->sweepGrid, SWEEP_TPB, h->smemBwdV, h->stream>>>(h->tiles, h->vRD, rA, yb, zb, nullptr,
+            h->dTileTicket, part, h->partStride, h->vState, gated, h->dTabCB, h->dTabUB, none, 0);
+    }
     CK(cudaGetLastError());
     return GPUPCG_OK;
 }

@@ -33,6 +33,24 @@ __device__ __forceinline__ void row_load(const double* p, double (&v)[NB])
     v[0] = a.x; v[1] = a.y;
     if (NB == 3) v[2] = p[2];
 }
+// The same out of SHARED memory for lanes that read consecutive rows (32-byte stride): half the lanes fetch the upper
+// 16 bytes first, so that the eight lanes of a quarter-warp cover all 32 banks in each of the two accesses (two 2-way
+// conflicts otherwise: every access touches only half of each row).
+template <int NB>
+__device__ __forceinline__ void row_load_sw(const double* p, double (&v)[NB], bool hiFirst)
+{
+    if (NB == 3)
+    {
+        const double2 a = *reinterpret_cast<const double2*>(p + (hiFirst ? 2 : 0));
+        const double2 b = *reinterpret_cast<const double2*>(p + (hiFirst ? 0 : 2));
+        v[0] = hiFirst ? b.x : a.x; v[1] = hiFirst ? b.y : a.y; v[2] = hiFirst ? a.x : b.x;
+    }
+    else
+    {
+        const double2 a = *reinterpret_cast<const double2*>(p);
+        v[0] = a.x; v[1] = a.y;
+    }
+}
 template <int NB>
 __device__ __forceinline__ void row_store(double* p, const double (&v)[NB])
 {
@@ -432,13 +450,14 @@ __global__ void __launch_bounds__(AMUL_TPB) k_amul_tile_v(TileArgs A, const doub
                 fU[j] = (j < si.widthU) ? cu[32*j] : 0.0;
             }
             double xr[NB], dr[NB], acc[NB], xL[4][NB], xU[4][NB];
-            row_load<NB>(xv + (size_t)q*NS, xr);
-            row_load<NB>(dg + (size_t)q*NS, dr);
+            const bool hiFirst = (tid & 4) != 0;
+            row_load_sw<NB>(xv + (size_t)q*NS, xr, hiFirst);
+            row_load_sw<NB>(dg + (size_t)q*NS, dr, hiFirst);
 #pragma unroll
             for (int j = 0; j < 4; j++)
             {
-                row_load<NB>(xv + (size_t)(cl[j] & 0xFFFFu)*NS, xL[j]);
-                row_load<NB>(xv + (size_t)(cuv[j] & 0x7FFFu)*NS, xU[j]);
+                row_load_sw<NB>(xv + (size_t)(cl[j] & 0xFFFFu)*NS, xL[j], hiFirst);
+                row_load_sw<NB>(xv + (size_t)(cuv[j] & 0x7FFFu)*NS, xU[j], hiFirst);
             }
 #pragma unroll
             for (int k = 0; k < NB; k++) acc[k] = __dmul_rn(dr[k], xr[k]);
@@ -542,23 +561,45 @@ __device__ __forceinline__ double mul_here(double a, double b)
     return r;
 }
 
-// NB values of one row's slot in shared memory (16-byte aligned): weak / volatile (the polled form) / store
+// NB values of one row's slot in shared memory (16-byte aligned): weak / volatile (the polled form) / store.
+// NB = 3: two 16-byte accesses per row; lanes with (lane & 4) take the upper half first, so that the eight lanes of a
+// quarter-warp working on consecutive rows (32-byte stride) cover all 32 banks in each access.
 template <int NB, bool VOL>
-__device__ __forceinline__ void lds_row(unsigned a, double (&v)[NB])
+__device__ __forceinline__ void lds_row(unsigned a, double (&v)[NB], bool hiFirst)
 {
-    if (VOL) asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(a) : "memory");
-    else     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(a));
     if (NB == 3)
     {
-        if (VOL) asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v[NB - 1]) : "r"(a + 16u) : "memory");
-        else     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v[NB - 1]) : "r"(a + 16u));
+        double p0, p1, q0, q1;
+        const unsigned a0 = a + (hiFirst ? 16u : 0u), a1 = a + (hiFirst ? 0u : 16u);
+        if (VOL)
+        {
+            asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(p0), "=d"(p1) : "r"(a0) : "memory");
+            asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(q0), "=d"(q1) : "r"(a1) : "memory");
+        }
+        else
+        {
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(p0), "=d"(p1) : "r"(a0));
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(q0), "=d"(q1) : "r"(a1));
+        }
+        v[0] = hiFirst ? q0 : p0; v[1] = hiFirst ? q1 : p1; v[NB - 1] = hiFirst ? p0 : q0;
+    }
+    else
+    {
+        if (VOL) asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(a) : "memory");
+        else     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(a));
     }
 }
 template <int NB>
-__device__ __forceinline__ void sts_row(unsigned a, const double (&v)[NB])
+__device__ __forceinline__ void sts_row(unsigned a, const double (&v)[NB], bool hiFirst)
 {
-    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(a), "d"(v[0]), "d"(v[1]));
-    if (NB == 3) asm volatile("st.shared.f64 [%0], %1;" :: "r"(a + 16u), "d"(v[NB - 1]));
+    if (NB == 3)
+    {
+        const double z = 0.0;
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(a + (hiFirst ? 16u : 0u)), "d"(hiFirst ? v[NB - 1] : v[0]), "d"(hiFirst ? z : v[1]));
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(a + (hiFirst ? 0u : 16u)), "d"(hiFirst ? v[0] : v[NB - 1]), "d"(hiFirst ? v[1] : z));
+    }
+    else
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(a), "d"(v[0]), "d"(v[1]));
 }
 // one row = ONE global transaction (256 bits for NB = 3, 128 for NB = 2), at gpu scope: the hand-off between tiles
 template <int NB>
@@ -599,7 +640,7 @@ struct RowRegsV
 // static data of one row, LOADS ONLY, one work item ahead of its use.  The products the reference forms first
 // (MODE 0: rD*rA and rD*upper; MODE 2: rD*upper) are formed from these registers in the NEXT iteration, right after
 // that iteration's dependency loads have been issued: they fill the LDS latency instead of delaying the loads.
-template <int NB, int MODE>
+template <int NB, int MODE, bool SW>
 __device__ __forceinline__ RowRegsV<NB> load_row_v(unsigned sb, const SweepLayout& L, int2 item, int lane)
 {
     constexpr int NS = VecStride<NB>::v;
@@ -614,8 +655,9 @@ __device__ __forceinline__ RowRegsV<NB> load_row_v(unsigned sb, const SweepLayou
     const double2 fa = lds_d2(sb + L.rowF + 32u*q);
     const double2 fb = lds_d2(sb + L.rowF + 32u*q + 16u);
     R.f[0] = fa.x; R.f[1] = fa.y; R.f[2] = fb.x; R.f[3] = fb.y;
-    lds_row<NB, false>(sb + L.vals + R.q8, R.a);
-    if (MODE != 1) lds_row<NB, false>(sb + L.dv + 8u*NS*q, R.d);
+    const bool hiFirst = SW && (lane & 4) != 0;
+    lds_row<NB, false>(sb + L.vals + R.q8, R.a, hiFirst);
+    if (MODE != 1) lds_row<NB, false>(sb + L.dv + 8u*NS*q, R.d, hiFirst);
     else
     {
 #pragma unroll
@@ -624,7 +666,10 @@ __device__ __forceinline__ RowRegsV<NB> load_row_v(unsigned sb, const SweepLayou
     return R;
 }
 
-template <int NB, int MODE>
+// SW: bank-swizzled access order of the row slots (see lds_row).  Faster where the sweeps are latency-bound (0.322 ->
+// 0.298 ms per precondition at 1 M cells) but 30 registers dearer (120: four CTAs per SM instead of five), which costs
+// more than it gives where they are throughput-bound (1.01 -> 1.14 ms at 8 M cells): chosen by size on the host.
+template <int NB, int MODE, bool SW>
 __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile_v(TileArgs A, const double* __restrict__ diagOrRD,
                                                           double* rA, unsigned long long* y,
                                                           unsigned long long* out, double* __restrict__ rDout,
@@ -736,18 +781,19 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile_v(TileArgs A, const doub
         const unsigned ib = sb + L.items;
         const int syncBit = BWD ? (1 << 16) : (1 << 17);       // end of a round in sweep order
         const int one8 = (int)vb + NS*8*L.one;                 // address of the constant slot: an unused dependency
+        const bool hiF = SW && (lane & 4) != 0;
         int2 d0 = lds_i2(ib), d1 = lds_i2(ib + 8u);
-        RowRegsV<NB> cur = load_row_v<NB, MODE>(sb, L, d0, lane);
+        RowRegsV<NB> cur = load_row_v<NB, MODE, SW>(sb, L, d0, lane);
         for (int i = 0; i < nItems; i++)
         {
             const int2 d2 = lds_i2(ib + 8u*(i + 2));
             // 1. the dependency loads of this item: the only loads on the round-to-round chain go first
             const unsigned a0 = (unsigned)cur.c.x, a1 = (unsigned)cur.c.y, a2 = (unsigned)cur.c.z, a3 = (unsigned)cur.c.w;
             double v[4][NB];
-            lds_row<NB, false>(a0, v[0]); lds_row<NB, false>(a1, v[1]);
-            lds_row<NB, false>(a2, v[2]); lds_row<NB, false>(a3, v[3]);
+            lds_row<NB, false>(a0, v[0], hiF); lds_row<NB, false>(a1, v[1], hiF);
+            lds_row<NB, false>(a2, v[2], hiF); lds_row<NB, false>(a3, v[3], hiF);
             // 2. static data of the next item (loads only) ...
-            const RowRegsV<NB> nxt = load_row_v<NB, MODE>(sb, L, d1, lane);
+            const RowRegsV<NB> nxt = load_row_v<NB, MODE, SW>(sb, L, d1, lane);
             // 3. ... and this item's coefficient products, from registers, while the dependency loads are in flight
             double F[4][NB], acc0[NB];
 #pragma unroll
@@ -764,8 +810,8 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile_v(TileArgs A, const doub
                 for (int k = 0; k < NB; k++)
                     notYet = notYet | hi_is_sent(v[0][k]) | hi_is_sent(v[1][k]) | hi_is_sent(v[2][k]) | hi_is_sent(v[3][k]);
                 if (!notYet) break;
-                lds_row<NB, true>(a0, v[0]); lds_row<NB, true>(a1, v[1]);
-                lds_row<NB, true>(a2, v[2]); lds_row<NB, true>(a3, v[3]);
+                lds_row<NB, true>(a0, v[0], hiF); lds_row<NB, true>(a1, v[1], hiF);
+                lds_row<NB, true>(a2, v[2], hiF); lds_row<NB, true>(a3, v[3], hiF);
             }
             double acc[NB];
 #pragma unroll
@@ -794,7 +840,7 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile_v(TileArgs A, const doub
                 }
                 acc[k] = a;
             }
-            sts_row<NB>(vb + cur.q8, acc);
+            sts_row<NB>(vb + cur.q8, acc, hiF);
             if (cur.qg >= 0) publish_row<NB>(out + g0 + (size_t)NS*cur.qg, acc);
             if (d0.y & syncBit) __syncwarp();
             cur = nxt; d0 = d1; d1 = d2;
