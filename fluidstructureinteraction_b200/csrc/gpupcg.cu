@@ -86,6 +86,7 @@ struct gpupcg_handle_s
     int vNB = 0;                    // components the buffers below are sized for (0: none yet)
     bool vBatched = false;          // batched kernels usable (table variant, shared memory fits); else sequential scalar solves
     bool vHaveMatrix = false;
+    int vAgreed = -1;               // multi-rank: 1 every rank runs the batched kernels, 0 none does, -1 not asked yet
     bool vSwizzle = false;          // bank-swizzled sweep variant (small, latency-bound sub-domains)
     size_t smemCap = 0;
     double *vDiag = nullptr, *vRD = nullptr, *vX = nullptr, *vB = nullptr, *vRA = nullptr, *vWA = nullptr, *vPA = nullptr, *vY = nullptr;

@@ -64,10 +64,27 @@ int vec_prepare(gpupcg_handle h)
     return GPUPCG_OK;
 }
 
-// multi-rank runs need the peer-memory mailboxes (the batched kernels have no ncclAllReduce path)
+// Multi-rank runs need the peer-memory mailboxes (the batched kernels have no ncclAllReduce path), and every rank must
+// take the same path (the batched and the sequential solves issue different collectives): the ranks agree once, with
+// one all-reduce, on "batched everywhere" -- a rank whose sub-domain has polyhedral rows, or no rows at all, sends
+// everybody to the sequential component solves.
 inline bool vec_batched_now(gpupcg_handle h)
 {
-    return h->vBatched && (!h->comm.active() || h->dP2P != nullptr);
+    if (!h->comm.active()) return h->vBatched;
+    if (h->vAgreed < 0)
+    {
+        const double mine = (h->vBatched && h->dP2P != nullptr) ? 1.0 : 0.0;
+        double sum = 0.0;
+        double* d = nullptr;
+        bool ok = cudaMalloc((void**)&d, sizeof(double)) == cudaSuccess
+               && cudaMemcpyAsync(d, &mine, sizeof(double), cudaMemcpyHostToDevice, h->stream) == cudaSuccess
+               && h->comm.allreduce_sum(d, 1, h->stream, h->err) == 0
+               && cudaMemcpyAsync(&sum, d, sizeof(double), cudaMemcpyDeviceToHost, h->stream) == cudaSuccess
+               && cudaStreamSynchronize(h->stream) == cudaSuccess;
+        if (d) cudaFree(d);
+        h->vAgreed = (ok && sum == (double)h->comm.nRanks()) ? 1 : 0;
+    }
+    return h->vAgreed == 1;
 }
 
 template <int NB>

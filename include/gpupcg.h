@@ -171,7 +171,9 @@ int gpupcg_time_kernel(gpupcg_handle h, int which, int reps, int flushL2, double
  *   x, b                : [nCells*nCmpt] = psi.internalField() (in/out) and the total source, same layout
  *   perfCmpt            : [nCmpt];  history: [nCmpt*historyCap] (component-major) or NULL
  * Meshes with more than four faces per row and side (polyhedra) and multi-rank runs without peer-memory mailboxes
- * run the components one after the other on the scalar kernels (gpupcg_vector_mode returns 0 then, 1 when batched). */
+ * run the components one after the other on the scalar kernels (gpupcg_vector_mode returns 0 then, 1 when batched).
+ * Multi-rank: the ranks agree on the path with one all-reduce the first time it is needed, so gpupcg_vector_mode and
+ * the first gpupcg_solve_vector after gpupcg_comm_init are collective calls.                                        */
 int gpupcg_vector_mode(gpupcg_handle h, int nCmpt);
 int gpupcg_set_matrix_vector(gpupcg_handle h, int nCmpt, const double* diagCmpt, const double* upper,
                              const double* const* patchBouCoeffsCmpt);
