@@ -960,7 +960,14 @@ extern "C" int gpupcg_mesh_create(gpupcg_mesh* out, int device, int nCells, int 
     return GPUPCG_OK;
 }
 
-static int agrid(gpupcg_mesh m, long long n) { long long g = (n + ATPB - 1)/ATPB; return (int)std::max<long long>(1, std::min<long long>(g, m->numSMs*16)); }
+static int agrid(gpupcg_mesh m, long long n)
+{
+    const char* v = getenv("GPUPCG_ASM_GRID_MULT");         // CTAs per SM of the grid-stride kernels (0: one element per thread)
+    const int mult = (v && *v) ? atoi(v) : 24;      // 24: 1.778 ms per assembly at 8 M cells against 1.796 with 16 (tools/assembly_grid.py)
+    long long g = (n + ATPB - 1)/ATPB;
+    if (mult > 0) g = std::min<long long>(g, (long long)m->numSMs*mult);
+    return (int)std::max<long long>(1, g);
+}
 
 extern "C" int gpupcg_assemble_D(gpupcg_mesh m, const double* mu, const double* lambda, const double* rho, const double* g,
                                  const double* D, const double* gradD, const double* gradDf, const double* traction,
