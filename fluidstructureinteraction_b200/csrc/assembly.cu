@@ -803,6 +803,11 @@ struct gpupcg_mesh_s
     std::vector<AsmChunk> chunks;
     const int *dExtraFace = nullptr, *dCellSlot = nullptr;
     int ringSlots = 0;
+    // two chunks in flight: the (latency-bound) cell kernel of chunk i overlaps the (bandwidth-bound) face kernel of
+    // chunk i+1 on a second stream, each parity with its own flux ring
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr, evFaces[2] = {nullptr, nullptr};
+    double* ring2 = nullptr;
 };
 
 static thread_local std::string g_meshErr;
@@ -841,6 +846,10 @@ extern "C" int gpupcg_mesh_destroy(gpupcg_mesh m)
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     for (void* p : m->owned) cudaFree(p);
+    if (m->evFork) cudaEventDestroy(m->evFork);
+    if (m->evJoin) cudaEventDestroy(m->evJoin);
+    for (auto& e : m->evFaces) if (e) cudaEventDestroy(e);
+    if (m->stream2) cudaStreamDestroy(m->stream2);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -948,6 +957,14 @@ extern "C" int gpupcg_mesh_create(gpupcg_mesh* out, int device, int nCells, int 
         double* ring = nullptr;
         MCK(alloc(m, ring, 7*(size_t)std::max(1, m->ringSlots)));
         m->dFluxE = ring; m->dFluxC = ring + 3*(size_t)m->ringSlots; m->dLup = ring + 6*(size_t)m->ringSlots;
+        if (m->chunks.size() > 1)
+        {
+            MCK(alloc(m, m->ring2, 7*(size_t)std::max(1, m->ringSlots)));
+            MCK(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
+            MCK(cudaEventCreateWithFlags(&m->evFork, cudaEventDisableTiming));
+            MCK(cudaEventCreateWithFlags(&m->evJoin, cudaEventDisableTiming));
+            for (auto& e : m->evFaces) MCK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
     }
     MCK(alloc(m, m->dDiag, nCells)); MCK(alloc(m, m->dSource, 3*(size_t)nCells));
     MCK(alloc(m, m->dIC, 3*(size_t)nBF)); MCK(alloc(m, m->dBC, 3*(size_t)nBF));
@@ -988,15 +1005,28 @@ extern "C" int gpupcg_assemble_D(gpupcg_mesh m, const double* mu, const double* 
     MCK(cudaEventRecord(m->ev0, s));
     for (int r = 0; r < reps; r++)
     {
+        const char* ov = getenv("GPUPCG_ASM_OVERLAP");
+        const bool overlap = m->stream2 && !(ov && *ov == '0');
+        if (overlap) { MCK(cudaEventRecord(m->evFork, s)); MCK(cudaStreamWaitEvent(m->stream2, m->evFork, 0)); }
+        int ci = 0;
         for (const AsmChunk& K : m->chunks)
         {
             // (reading -upper instead of a separate Lup array in the cell kernel was measured: 3 % slower at 8 M cells)
-            double* lup = m->dLup;
-            k_asm_faces<<<agrid(m, K.nOwn + K.nExtra), ATPB, 0, s>>>(M, K, m->dExtraFace, m->dMu, m->dLambda, m->dD, m->dGradD, m->dGradDf,
-                                                                     limitCoeff, m->dUpper, lup, m->dGms, m->dFluxE, m->dFluxC);
-            k_asm_cells<<<agrid(m, K.c1 - K.c0), ATPB, 0, s>>>(M, K, m->dCellSlot, m->dRho, g[0], g[1], g[2], lup, m->dUpper, m->dFluxE,
-                                                               m->dFluxC, m->dDiag, m->dSource);
+            const bool odd = overlap && (ci & 1);
+            cudaStream_t cs = odd ? m->stream2 : s;
+            double* ring = odd ? m->ring2 : m->dFluxE;
+            double *fluxE = ring, *fluxC = ring + 3*(size_t)m->ringSlots, *lup = ring + 6*(size_t)m->ringSlots;
+            // the face kernels run one after the other (they are bandwidth-bound); what overlaps is the cell kernel of
+            // chunk i with the face kernel of chunk i+1
+            if (overlap && ci > 0) { MCK(cudaStreamWaitEvent(cs, m->evFaces[(ci - 1) & 1], 0)); }
+            k_asm_faces<<<agrid(m, K.nOwn + K.nExtra), ATPB, 0, cs>>>(M, K, m->dExtraFace, m->dMu, m->dLambda, m->dD, m->dGradD, m->dGradDf,
+                                                                      limitCoeff, m->dUpper, lup, m->dGms, fluxE, fluxC);
+            if (overlap) { MCK(cudaEventRecord(m->evFaces[ci & 1], cs)); }
+            k_asm_cells<<<agrid(m, K.c1 - K.c0), ATPB, 0, cs>>>(M, K, m->dCellSlot, m->dRho, g[0], g[1], g[2], lup, m->dUpper, fluxE,
+                                                                fluxC, m->dDiag, m->dSource);
+            ci++;
         }
+        if (overlap) { MCK(cudaEventRecord(m->evJoin, m->stream2)); MCK(cudaStreamWaitEvent(s, m->evJoin, 0)); }
         if (nBF > 0)
             k_asm_patches<<<agrid(m, nBF), ATPB, 0, s>>>(M, m->dMu, m->dLambda, m->dD, m->dGradD, m->dGradDf, m->dGms, m->dTraction,
                                                          m->dPressure, m->dFixed, m->dIC, m->dBC, m->dPatchGrad);
