@@ -94,6 +94,7 @@ SYMBOLS = {
     "gpupcg_patch_gradient": (C.c_int, [C.c_void_p, c_double_p]),
     "gpupcg_relax_residual": (C.c_int, [C.c_void_p, C.c_double, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "gpupcg_mesh_set_points": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_int_p, c_int_p]),
+    "gpupcg_mesh_fetch": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "gpupcg_gradients": (C.c_int, [C.c_void_p] + [c_double_p]*5 + [C.c_double, C.c_int] + [c_double_p]*4),
     "gpupcg_host_register": (C.c_int, [C.c_void_p, C.c_ulonglong]),
     "gpupcg_host_unregister": (C.c_int, [C.c_void_p]),
@@ -357,8 +358,18 @@ class GpuMesh(object):
         except Exception:
             pass
 
+    FIELDS = {"D": 0, "gradD": 1, "gradDf": 2, "gradDb": 3}
+
+    def fetch(self, which):
+        """A device-resident field on demand (gpupcg_mesh_fetch)."""
+        shape = {"D": (self.nC, 3), "gradD": (self.nC, 9), "gradDf": (self.nF, 9), "gradDb": (self.nBF, 9)}[which]
+        out = np.empty(shape)
+        self._check(self.lib.gpupcg_mesh_fetch(self.h, self.FIELDS[which], _dp(out)))
+        return out
+
     def assemble_D(self, mu, lam, rho, g, D, gradD, gradDf, traction, pressure, fixedValue, limitCoeff=1.0, reps=1):
-        a = [_f64(v) for v in (mu, lam, rho, g, D, gradD, gradDf, traction, pressure, fixedValue)]
+        """gradD / gradDf = None: the gradients the device holds (left there by gradients())."""
+        a = [_f64(v) if v is not None else None for v in (mu, lam, rho, g, D, gradD, gradDf, traction, pressure, fixedValue)]
         upper = np.empty(self.nIF); diag = np.empty(self.nC); source = np.empty((self.nC, 3))
         ic = np.empty((self.nBF, 3)); bc = np.empty((self.nBF, 3))
         ms = C.c_double(0.0)
@@ -366,11 +377,21 @@ class GpuMesh(object):
                                                _dp(diag), _dp(source), _dp(ic), _dp(bc), C.byref(ms)))
         return dict(upper=upper, diag=diag, source=source, internalCoeffs=ic, boundaryCoeffs=bc, kernel_ms=ms.value)
 
-    def gradients(self, D, pointD, gradDold, fixedValue, patchGradient, limitCoeff=1.0, reps=1):
+    def gradients_resident(self, D, pointD, fixedValue, patchGradient=None, limitCoeff=1.0):
+        """fvc::grad + fvc::fGrad with the device's current grad(D) as the registered gradient; results stay on the
+        device (fetch() them when needed)."""
+        self._ensure_points()
+        a = [_f64(v) if v is not None else None for v in (D, pointD, None, fixedValue, patchGradient)]
+        self._check(self.lib.gpupcg_gradients(self.h, *[_dp(v) for v in a], float(limitCoeff), 1, None, None, None, None))
+
+    def _ensure_points(self):
         if not getattr(self, "_points", None):
             self._points = (_f64(self.mesh.points), _i32(self.mesh.faceStart), _i32(self.mesh.facePoints))
             self._check(self.lib.gpupcg_mesh_set_points(self.h, self.mesh.nPoints, _dp(self._points[0]),
                                                         _ip(self._points[1]), _ip(self._points[2])))
+
+    def gradients(self, D, pointD, gradDold, fixedValue, patchGradient, limitCoeff=1.0, reps=1):
+        self._ensure_points()
         a = [_f64(v) if v is not None else None for v in (D, pointD, gradDold, fixedValue, patchGradient)]
         G = np.empty((self.nC, 9)); Gb = np.empty((self.nBF, 9)); Gf = np.empty((self.nF, 9))
         ms = C.c_double(0.0)
@@ -393,8 +414,10 @@ class GpuMesh(object):
         return res.value
 
     def sigma(self, mu, lam, gradD):
+        """gradD = None: the device's grad(D)."""
         eps = np.empty((self.nC, 6)); sig = np.empty((self.nC, 6))
-        self._check(self.lib.gpupcg_sigma(self.h, _dp(_f64(mu)), _dp(_f64(lam)), _dp(_f64(gradD)), _dp(eps), _dp(sig)))
+        self._check(self.lib.gpupcg_sigma(self.h, _dp(_f64(mu)), _dp(_f64(lam)), _dp(_f64(gradD)) if gradD is not None else None,
+                                          _dp(eps), _dp(sig)))
         return eps, sig
 
 

@@ -805,6 +805,7 @@ struct gpupcg_mesh_s
     int ringSlots = 0;
     // two chunks in flight: the (latency-bound) cell kernel of chunk i overlaps the (bandwidth-bound) face kernel of
     // chunk i+1 on a second stream, each parity with its own flux ring
+    bool haveGradD = false, haveGradDf = false;     // the device holds grad(D) / the face gradient (residency across calls)
     cudaStream_t stream2 = nullptr;
     cudaEvent_t evFork = nullptr, evJoin = nullptr, evFaces[2] = {nullptr, nullptr};
     double* ring2 = nullptr;
@@ -992,10 +993,17 @@ extern "C" int gpupcg_assemble_D(gpupcg_mesh m, const double* mu, const double* 
                                  double* upper, double* diag, double* source, double* internalCoeffs,
                                  double* boundaryCoeffs, double* kernel_ms)
 {
-    if (!m || !mu || !lambda || !rho || !g || !D || !gradD || !gradDf) return GPUPCG_ERR_ARG;
+    if (!m || !mu || !lambda || !rho || !g || !D) return GPUPCG_ERR_ARG;
+    if ((!gradD && !m->haveGradD) || (!gradDf && !m->haveGradDf))
+    {
+        m->err = "gpupcg_assemble_D: gradD / gradDf == NULL but the device holds no gradients yet (gpupcg_gradients first)";
+        return GPUPCG_ERR_STATE;
+    }
     const MeshDev& M = m->M;
     const int nC = M.nCells, nF = M.nFaces, nIF = M.nIF, nBF = nF - nIF;
     MCK(cudaSetDevice(m->device));
+    if (gradD) m->haveGradD = true;
+    if (gradDf) m->haveGradDf = true;
     cudaStream_t s = m->stream;
     auto h2d = [&](double* d, const double* h, size_t n) { return n && h ? cudaMemcpyAsync(d, h, n*sizeof(double), cudaMemcpyHostToDevice, s) : cudaSuccess; };
     MCK(h2d(m->dMu, mu, nC)); MCK(h2d(m->dLambda, lambda, nC)); MCK(h2d(m->dRho, rho, nC));
@@ -1044,13 +1052,14 @@ extern "C" int gpupcg_assemble_D(gpupcg_mesh m, const double* mu, const double* 
 extern "C" int gpupcg_sigma(gpupcg_mesh m, const double* mu, const double* lambda, const double* gradD,
                             double* epsilon, double* sigma)
 {
-    if (!m || !mu || !lambda || !gradD || !epsilon || !sigma) return GPUPCG_ERR_ARG;
+    if (!m || !mu || !lambda || !epsilon || !sigma) return GPUPCG_ERR_ARG;
+    if (!gradD && !m->haveGradD) { m->err = "gpupcg_sigma: gradD == NULL but the device holds no grad(D) yet"; return GPUPCG_ERR_STATE; }
     const int nC = m->M.nCells;
     MCK(cudaSetDevice(m->device));
     cudaStream_t s = m->stream;
     MCK(cudaMemcpyAsync(m->dMu, mu, sizeof(double)*nC, cudaMemcpyHostToDevice, s));
     MCK(cudaMemcpyAsync(m->dLambda, lambda, sizeof(double)*nC, cudaMemcpyHostToDevice, s));
-    MCK(cudaMemcpyAsync(m->dGradD, gradD, sizeof(double)*9*(size_t)nC, cudaMemcpyHostToDevice, s));
+    if (gradD) { MCK(cudaMemcpyAsync(m->dGradD, gradD, sizeof(double)*9*(size_t)nC, cudaMemcpyHostToDevice, s)); m->haveGradD = true; }
     k_sigma<<<agrid(m, nC), ATPB, 0, s>>>(nC, m->dMu, m->dLambda, m->dGradD, m->dEps, m->dSig);
     MCK(cudaGetLastError());
     MCK(cudaMemcpyAsync(epsilon, m->dEps, sizeof(double)*6*(size_t)nC, cudaMemcpyDeviceToHost, s));
@@ -1127,14 +1136,21 @@ extern "C" int gpupcg_gradients(gpupcg_mesh m, const double* D, const double* po
                                 const double* fixedValue, const double* patchGradient, double limitCoeff, int reps,
                                 double* gradD, double* gradDb, double* gradDf, double* kernel_ms)
 {
-    if (!m || !D || !pointD || !gradDold || !gradD || !gradDf) return GPUPCG_ERR_ARG;
+    if (!m || !D || !pointD) return GPUPCG_ERR_ARG;
     if (!m->M.points) { m->err = "gpupcg_gradients: gpupcg_mesh_set_points has not been called"; return GPUPCG_ERR_STATE; }
+    if (!gradDold && !m->haveGradD)
+    {
+        m->err = "gpupcg_gradients: gradDold == NULL but the device holds no grad(D) yet";
+        return GPUPCG_ERR_STATE;
+    }
     const MeshDev& M = m->M;
     const int nC = M.nCells, nF = M.nFaces, nBF = nF - M.nIF;
     MCK(cudaSetDevice(m->device));
     cudaStream_t s = m->stream;
     auto h2d = [&](double* d, const double* h, size_t n) { return n && h ? cudaMemcpyAsync(d, h, n*sizeof(double), cudaMemcpyHostToDevice, s) : cudaSuccess; };
-    MCK(h2d(m->dD, D, 3*(size_t)nC)); MCK(h2d(m->dPointD, pointD, 3*(size_t)M.nPoints)); MCK(h2d(m->dGradOld, gradDold, 9*(size_t)nC));
+    MCK(h2d(m->dD, D, 3*(size_t)nC)); MCK(h2d(m->dPointD, pointD, 3*(size_t)M.nPoints));
+    if (gradDold) { MCK(h2d(m->dGradOld, gradDold, 9*(size_t)nC)); }
+    else { MCK(cudaMemcpyAsync(m->dGradOld, m->dGradD, sizeof(double)*9*(size_t)nC, cudaMemcpyDeviceToDevice, s)); }   // the registered grad(D) at call time
     MCK(h2d(m->dFixed, fixedValue, 3*(size_t)nBF)); MCK(h2d(m->dPatchGrad, patchGradient, 3*(size_t)nBF));
     if (reps < 1) reps = 1;
     MCK(cudaEventRecord(m->ev0, s));
@@ -1150,6 +1166,32 @@ extern "C" int gpupcg_gradients(gpupcg_mesh m, const double* D, const double* po
     auto d2h = [&](double* h, const double* d, size_t n) { return n && h ? cudaMemcpyAsync(h, d, n*sizeof(double), cudaMemcpyDeviceToHost, s) : cudaSuccess; };
     MCK(d2h(gradD, m->dGradD, 9*(size_t)nC)); MCK(d2h(gradDb, m->dGradDb, 9*(size_t)nBF)); MCK(d2h(gradDf, m->dGradDf, 9*(size_t)nF));
     MCK(cudaStreamSynchronize(s));
+    m->haveGradD = m->haveGradDf = true;
     if (kernel_ms) { float ms = 0.f; cudaEventElapsedTime(&ms, m->ev0, m->ev1); *kernel_ms = ms/reps; }
+    return GPUPCG_OK;
+}
+
+// a device-resident field on demand: which 0 D [nCells*3], 1 gradD [nCells*9], 2 gradDf [nFaces*9], 3 gradDb [nBoundaryFaces*9]
+extern "C" int gpupcg_mesh_fetch(gpupcg_mesh m, int which, double* out)
+{
+    if (!m || !out) return GPUPCG_ERR_ARG;
+    const MeshDev& M = m->M;
+    const double* src = nullptr; size_t n = 0;
+    switch (which)
+    {
+        case 0: src = m->dD; n = 3*(size_t)M.nCells; break;
+        case 1: src = m->dGradD; n = 9*(size_t)M.nCells; break;
+        case 2: src = m->dGradDf; n = 9*(size_t)M.nFaces; break;
+        case 3: src = m->dGradDb; n = 9*(size_t)(M.nFaces - M.nIF); break;
+        default: m->err = "gpupcg_mesh_fetch: unknown field id"; return GPUPCG_ERR_ARG;
+    }
+    if ((which == 1 && !m->haveGradD) || (which >= 2 && !m->haveGradDf) || !src)
+    {
+        m->err = "gpupcg_mesh_fetch: the device does not hold that field yet";
+        return GPUPCG_ERR_STATE;
+    }
+    MCK(cudaSetDevice(m->device));
+    if (n) MCK(cudaMemcpyAsync(out, src, n*sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    MCK(cudaStreamSynchronize(m->stream));
     return GPUPCG_OK;
 }

@@ -69,7 +69,7 @@ evolveResult unsTotalLagrangianStressGpu::evolve
     lduAddressing addr(nC, l, u, std::vector<labelList>());
     lduMatrix matrix(addr);
     std::vector<scalar> upper(nIF), diag(nC), source(3*(size_t)nC), ic(3*(size_t)std::max(1, nBF)), bc(3*(size_t)std::max(1, nBF));
-    std::vector<scalar> Dprev(D.size()), gradDb(9*(size_t)std::max(1, nBF));
+    std::vector<scalar> Dprev(D.size());
 
     evolveResult R;
     R.converged = 1; R.nOuterIterations = 0; R.initialResidual = 0; R.lastSolverInitialResidual = 0;
@@ -82,7 +82,11 @@ evolveResult unsTotalLagrangianStressGpu::evolve
     {
         Dprev = D;                                                      // D_.storePrevIter()
 
-        meshCheck(gm_, gpupcg_assemble_D(gm_, &mu_[0], &lambda_[0], &rho_[0], g_, &D[0], &gradD[0], &gradDf[0], &traction_[0],
+        // the gradients cross PCIe once per time step: uploaded with the first assembly, then resident on the device
+        // (gpupcg_gradients leaves them there), fetched once after the loop
+        const scalar* gD = (iCorr == 0) ? &gradD[0] : 0;
+        const scalar* gDf = (iCorr == 0) ? &gradDf[0] : 0;
+        meshCheck(gm_, gpupcg_assemble_D(gm_, &mu_[0], &lambda_[0], &rho_[0], g_, &D[0], gD, gDf, &traction_[0],
                                          &pressure_[0], &fixedValue_[0], limitCoeff_, 1, &upper[0], &diag[0], &source[0],
                                          &ic[0], &bc[0], 0), "gpupcg_assemble_D");
         for (int c = 0; c < nC; c++) matrix.diag()[c] = diag[c];
@@ -111,12 +115,9 @@ evolveResult unsTotalLagrangianStressGpu::evolve
                   "gpupcg_relax_residual");
 
         interpolate(ctx, &D[0], &pointD[0]);                            // volToPoint_.interpolate(D_, pointD_)
-        {
-            std::vector<scalar> gradOld(gradD);
-            // patchGradient = NULL: the tractionDisplacement gradient() the assembly above left on the device
-            meshCheck(gm_, gpupcg_gradients(gm_, &D[0], &pointD[0], &gradOld[0], &fixedValue_[0], 0, limitCoeff_, 1,
-                                            &gradD[0], &gradDb[0], &gradDf[0], 0), "gpupcg_gradients");
-        }
+        // gradDold = NULL: the device's current grad(D) is the registered gradient; patchGradient = NULL: the
+        // tractionDisplacement gradient() the assembly above left on the device; outputs stay on the device
+        meshCheck(gm_, gpupcg_gradients(gm_, &D[0], &pointD[0], 0, &fixedValue_[0], 0, limitCoeff_, 1, 0, 0, 0, 0), "gpupcg_gradients");
 
         if (res > maxRes) maxRes = res;
         curConvergenceTolerance = maxRes*relConvergenceTolerance;
@@ -125,7 +126,9 @@ evolveResult unsTotalLagrangianStressGpu::evolve
     }
     while (res > curConvergenceTolerance && ++iCorr < nCorr);
 
-    meshCheck(gm_, gpupcg_sigma(gm_, &mu_[0], &lambda_[0], &gradD[0], &epsilon[0], &sigma[0]), "gpupcg_sigma");
+    meshCheck(gm_, gpupcg_sigma(gm_, &mu_[0], &lambda_[0], 0, &epsilon[0], &sigma[0]), "gpupcg_sigma");
+    meshCheck(gm_, gpupcg_mesh_fetch(gm_, 1, &gradD[0]), "gpupcg_mesh_fetch(gradD)");
+    meshCheck(gm_, gpupcg_mesh_fetch(gm_, 2, &gradDf[0]), "gpupcg_mesh_fetch(gradDf)");
     gpuPCG::clearCache();       // `addr` dies with this call
     R.nOuterIterations = iCorr; R.maxRes = maxRes; R.res = res;
     return R;

@@ -243,6 +243,17 @@ int gpupcg_patch_gradient(gpupcg_mesh m, double* patchGradient);
 int gpupcg_relax_residual(gpupcg_mesh m, double alpha, int relax, double* D, const double* Dprev, const double* Dold,
                           double* residual);
 int gpupcg_mesh_set_points(gpupcg_mesh m, int nPoints, const double* points, const int* faceStart, const int* facePoints);
+/* Residency across the outer iterations of evolve(): grad(D) and the face gradient (72 B per cell / per face) stay on the
+ * device between gpupcg_gradients (:925-926) and the next gpupcg_assemble_D (:846-859) instead of crossing PCIe twice.
+ *   gpupcg_assemble_D : gradD == NULL / gradDf == NULL -> what the device holds (from gpupcg_gradients, or the last
+ *                       upload);
+ *   gpupcg_gradients  : gradDold == NULL -> the device's current grad(D) is copied aside as the registered gradient;
+ *                       gradD / gradDb / gradDf == NULL -> not copied back;
+ *   gpupcg_sigma      : gradD == NULL -> the device's grad(D);
+ *   gpupcg_mesh_fetch : copies a device-resident field out on demand: which = 0 D [nCells*3], 1 gradD [nCells*9],
+ *                       2 gradDf [nFaces*9], 3 gradDb [nBoundaryFaces*9].
+ * GPUPCG_ERR_STATE if the device holds nothing yet.                                                                    */
+int gpupcg_mesh_fetch(gpupcg_mesh m, int which, double* out);
 int gpupcg_gradients(gpupcg_mesh m, const double* D, const double* pointD, const double* gradDold,
                      const double* fixedValue, const double* patchGradient, double limitCoeff, int reps,
                      double* gradD, double* gradDb, double* gradDf, double* kernel_ms);

@@ -218,3 +218,46 @@ def test_gpu_gradients_bit_exact(kind):
             Gf2 = oracle.fgrad(m, g, patches, D, pD, G2, fixed, pgrad, limitCoeff)
             assert np.array_equal(G, G2) and np.array_equal(Gb, Gb2) and np.array_equal(Gf, Gf2)
         gm.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["hex", "tet"])
+def test_gpu_gradients_stay_resident_between_outer_iterations(kind):
+    """Residency of evolve()'s outer loop (unsTotalLagrangianStress.C:846-926): gradients with NULL outputs leave
+    grad(D) / the face gradient on the device, the next assembly (gradD = gradDf = NULL), the next gradients
+    (gradDold = NULL: the device's grad(D) is the registered one) and sigma (gradD = NULL) read them there -- the same bits
+    as the path through host arrays, and as the oracle."""
+    m = meshes.hex_box(12, 6, 8) if kind == "hex" else meshes.tet_box(6, 4, 5, jitter=0.15)
+    g = geometry.compute(m)
+    f = fields(m, 7)
+    rng = np.random.default_rng(23)
+    pD1 = 1e-4*rng.standard_normal((m.nPoints, 3)); pD2 = 1e-4*rng.standard_normal((m.nPoints, 3))
+    D1 = 1e-4*rng.standard_normal((m.nCells, 3)); D2 = 1e-4*rng.standard_normal((m.nCells, 3))
+    gm = pkg.GpuMesh(m, g, PATCHES)
+    with pytest.raises(pkg.GpuPcgError) as e:
+        gm.assemble_D(f["mu"], f["lam"], f["rho"], f["g"], f["D"], None, None, f["traction"], f["pressure"], f["fixedValue"], 1.0)
+    assert e.value.code == -5                       # nothing resident yet
+    with pytest.raises(pkg.GpuPcgError):
+        gm.fetch("gradD")
+    # host path: assembly -> gradients -> assembly -> gradients, everything through host arrays
+    a0 = gm.assemble_D(f["mu"], f["lam"], f["rho"], f["g"], f["D"], f["gradD"], f["gradDf"], f["traction"], f["pressure"], f["fixedValue"], 1.0)
+    G1, Gb1, Gf1, _ = gm.gradients(D1, pD1, f["gradD"], f["fixedValue"], None, 1.0)
+    a1 = gm.assemble_D(f["mu"], f["lam"], f["rho"], f["g"], D1, G1, Gf1, f["traction"], f["pressure"], f["fixedValue"], 1.0)
+    G2, Gb2, Gf2, _ = gm.gradients(D2, pD2, G1, f["fixedValue"], None, 1.0)
+    eps2, sig2 = gm.sigma(f["mu"], f["lam"], G2)
+    gm.close()
+    # resident path
+    gm = pkg.GpuMesh(m, g, PATCHES)
+    b0 = gm.assemble_D(f["mu"], f["lam"], f["rho"], f["g"], f["D"], f["gradD"], f["gradDf"], f["traction"], f["pressure"], f["fixedValue"], 1.0)
+    gm.gradients_resident(D1, pD1, f["fixedValue"])
+    b1 = gm.assemble_D(f["mu"], f["lam"], f["rho"], f["g"], D1, None, None, f["traction"], f["pressure"], f["fixedValue"], 1.0)
+    gm.gradients_resident(D2, pD2, f["fixedValue"])
+    eps3, sig3 = gm.sigma(f["mu"], f["lam"], None)
+    for k in ("upper", "diag", "source", "internalCoeffs", "boundaryCoeffs"):
+        assert np.array_equal(a0[k], b0[k]) and np.array_equal(a1[k], b1[k]), k
+    assert np.array_equal(gm.fetch("gradD"), G2) and np.array_equal(gm.fetch("gradDf"), Gf2) and np.array_equal(gm.fetch("gradDb"), Gb2)
+    assert np.array_equal(eps3, eps2) and np.array_equal(sig3, sig2)
+    # and against the oracle
+    r1 = oracle.assemble_D(m, g, PATCHES, f["mu"], f["lam"], f["rho"], f["g"], D1, G1, Gf1, f["traction"], f["pressure"], f["fixedValue"], 1.0)
+    assert np.array_equal(b1["source"], r1["source"])
+    gm.close()
