@@ -95,6 +95,8 @@ SYMBOLS = {
     "gpupcg_relax_residual": (C.c_int, [C.c_void_p, C.c_double, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "gpupcg_mesh_set_points": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_int_p, c_int_p]),
     "gpupcg_mesh_fetch": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
+    "gpupcg_solve_assembled_D": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_double, C.c_double, C.c_int, C.c_int,
+                                           C.POINTER(Perf)]),
     "gpupcg_gradients": (C.c_int, [C.c_void_p] + [c_double_p]*5 + [C.c_double, C.c_int] + [c_double_p]*4),
     "gpupcg_host_register": (C.c_int, [C.c_void_p, C.c_ulonglong]),
     "gpupcg_host_unregister": (C.c_int, [C.c_void_p]),
@@ -309,6 +311,14 @@ class GpuPCG(object):
                                                         minIter, maxIter, perf, _dp(hist), hist.shape[1] if history else 0))
         return self._vec_result(perf, hist, nCmpt, history)
 
+    def solve_assembled_D(self, gpuMesh, D, tolerance=1e-6, relTol=0.0, minIter=0, maxIter=1000):
+        """DEqn.solve() on the D equation gpuMesh.assemble_D left on the device (the matrix never crosses PCIe).
+        D: (nCells, 3) float64 C-contiguous, in/out.  Returns [perf dict per component]."""
+        assert D.dtype == np.float64 and D.flags.c_contiguous and D.shape == (self.nCells, 3)
+        perf = (Perf*3)()
+        self._check(self.lib.gpupcg_solve_assembled_D(self.h, gpuMesh.h, _dp(D), tolerance, relTol, minIter, maxIter, perf))
+        return [perf[k].as_dict() for k in range(3)]
+
     def time_kernel_vector(self, nCmpt, which, reps=10, flushL2=True):
         ms = C.c_double(0.0)
         self._check(self.lib.gpupcg_time_kernel_vector(self.h, nCmpt, self.KERNELS[which], reps, 1 if flushL2 else 0, C.byref(ms)))
@@ -367,12 +377,16 @@ class GpuMesh(object):
         self._check(self.lib.gpupcg_mesh_fetch(self.h, self.FIELDS[which], _dp(out)))
         return out
 
-    def assemble_D(self, mu, lam, rho, g, D, gradD, gradDf, traction, pressure, fixedValue, limitCoeff=1.0, reps=1):
+    def assemble_D(self, mu, lam, rho, g, D, gradD, gradDf, traction, pressure, fixedValue, limitCoeff=1.0, reps=1, copy_back=True):
         """gradD / gradDf = None: the gradients the device holds (left there by gradients())."""
         a = [_f64(v) if v is not None else None for v in (mu, lam, rho, g, D, gradD, gradDf, traction, pressure, fixedValue)]
+        ms = C.c_double(0.0)
+        if not copy_back:       # the equation stays on the device (solve_assembled_D)
+            self._check(self.lib.gpupcg_assemble_D(self.h, *[_dp(v) for v in a], float(limitCoeff), int(reps), None, None, None,
+                                                   None, None, C.byref(ms)))
+            return dict(kernel_ms=ms.value)
         upper = np.empty(self.nIF); diag = np.empty(self.nC); source = np.empty((self.nC, 3))
         ic = np.empty((self.nBF, 3)); bc = np.empty((self.nBF, 3))
-        ms = C.c_double(0.0)
         self._check(self.lib.gpupcg_assemble_D(self.h, *[_dp(v) for v in a], float(limitCoeff), int(reps), _dp(upper),
                                                _dp(diag), _dp(source), _dp(ic), _dp(bc), C.byref(ms)))
         return dict(upper=upper, diag=diag, source=source, internalCoeffs=ic, boundaryCoeffs=bc, kernel_ms=ms.value)

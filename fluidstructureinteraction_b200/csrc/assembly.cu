@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include "mesh_view.h"
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -805,6 +806,8 @@ struct gpupcg_mesh_s
     int ringSlots = 0;
     // two chunks in flight: the (latency-bound) cell kernel of chunk i overlaps the (bandwidth-bound) face kernel of
     // chunk i+1 on a second stream, each parity with its own flux ring
+    const int *dCellBfStart = nullptr, *dCellBf = nullptr;   // cell -> its boundary faces (index - nIF), ascending = patch order
+    bool assembled = false;                                   // the device holds an assembled D equation
     bool haveGradD = false, haveGradDf = false;     // the device holds grad(D) / the face gradient (residency across calls)
     cudaStream_t stream2 = nullptr;
     cudaEvent_t evFork = nullptr, evJoin = nullptr, evFaces[2] = {nullptr, nullptr};
@@ -946,6 +949,16 @@ extern "C" int gpupcg_mesh_create(gpupcg_mesh* out, int device, int nCells, int 
     MCK(up(m, M.owner, owner, nFaces)); MCK(up(m, M.neighbour, neighbour, nIF)); MCK(up(m, M.bfPatchType, bft.data(), nBF));
     MCK(up(m, M.cellFaceStart, start.data(), nCells + 1)); MCK(up(m, M.cellFace, cf.data(), cf.size()));
     MCK(up(m, m->dExtraFace, extraFace.data(), extraFace.size())); MCK(up(m, m->dCellSlot, cellSlot.data(), cellSlot.size()));
+    {
+        // cell -> boundary faces, in the order fvMatrix::addBoundaryDiag / addBoundarySource reach a cell (patches in
+        // index order, faces in patch order = ascending face index)
+        std::vector<int> bs(nCells + 1, 0), bfs(std::max(1, nBF));
+        for (int f = nIF; f < nFaces; f++) bs[owner[f] + 1]++;
+        for (int c = 0; c < nCells; c++) bs[c + 1] += bs[c];
+        std::vector<int> bc(bs.begin(), bs.end() - 1);
+        for (int f = nIF; f < nFaces; f++) bfs[bc[owner[f]]++] = f - nIF;
+        MCK(up(m, m->dCellBfStart, bs.data(), bs.size())); MCK(up(m, m->dCellBf, bfs.data(), bfs.size()));
+    }
     MCK(up(m, M.Sf, Sf, 3*(size_t)nFaces)); MCK(up(m, M.magSf, magSf, nFaces)); MCK(up(m, M.Cf, Cf, 3*(size_t)nFaces));
     MCK(up(m, M.C, C, 3*(size_t)nCells)); MCK(up(m, M.V, V, nCells)); MCK(up(m, M.weights, weights, nIF));
     MCK(up(m, M.deltaCoeffs, deltaCoeffs, nFaces));
@@ -1041,6 +1054,7 @@ extern "C" int gpupcg_assemble_D(gpupcg_mesh m, const double* mu, const double* 
     }
     MCK(cudaEventRecord(m->ev1, s));
     MCK(cudaGetLastError());
+    m->assembled = true;
     auto d2h = [&](double* h, const double* d, size_t n) { return n && h ? cudaMemcpyAsync(h, d, n*sizeof(double), cudaMemcpyDeviceToHost, s) : cudaSuccess; };
     MCK(d2h(upper, m->dUpper, nIF)); MCK(d2h(diag, m->dDiag, nC)); MCK(d2h(source, m->dSource, 3*(size_t)nC));
     MCK(d2h(internalCoeffs, m->dIC, 3*(size_t)nBF)); MCK(d2h(boundaryCoeffs, m->dBC, 3*(size_t)nBF));
@@ -1168,6 +1182,19 @@ extern "C" int gpupcg_gradients(gpupcg_mesh m, const double* D, const double* po
     MCK(cudaStreamSynchronize(s));
     m->haveGradD = m->haveGradDf = true;
     if (kernel_ms) { float ms = 0.f; cudaEventElapsedTime(&ms, m->ev0, m->ev1); *kernel_ms = ms/reps; }
+    return GPUPCG_OK;
+}
+
+// internal (csrc/mesh_view.h): what the solver side needs of an assembled D equation; the mesh's stream is idle on return
+extern "C" int gpupcgi_mesh_view(gpupcg_mesh m, gpupcg_mesh_view* v)
+{
+    if (!m || !v) return GPUPCG_ERR_ARG;
+    if (!m->assembled) { m->err = "no assembled D equation on the device (gpupcg_assemble_D first)"; return GPUPCG_ERR_STATE; }
+    MCK(cudaSetDevice(m->device));
+    MCK(cudaStreamSynchronize(m->stream));
+    v->device = m->device; v->nCells = m->M.nCells; v->nIF = m->M.nIF; v->nBF = m->M.nFaces - m->M.nIF;
+    v->upper = m->dUpper; v->diag = m->dDiag; v->source = m->dSource; v->ic = m->dIC; v->bc = m->dBC;
+    v->cellBfStart = m->dCellBfStart; v->cellBf = m->dCellBf;
     return GPUPCG_OK;
 }
 

@@ -539,3 +539,44 @@ extern "C" int gpupcg_time_kernel_vector(gpupcg_handle h, int nCmpt, int which, 
     CK(cudaSetDevice(h->device));
     return VEC_DISPATCH(nCmpt, vec_time_kernel<2>(h, which, reps, flushL2, msOut), vec_time_kernel<3>(h, which, reps, flushL2, msOut));
 }
+
+// DEqn.solve() on the matrix the last gpupcg_assemble_D left on the device: the matrix never crosses PCIe.
+#include "mesh_view.h"
+
+extern "C" int gpupcg_solve_assembled_D(gpupcg_handle h, gpupcg_mesh m, double* D, double tol, double relTol, int minIter,
+                                        int maxIter, gpupcg_perf* perf)
+{
+    if (!h || !m || !D) return GPUPCG_ERR_ARG;
+    gpupcg_mesh_view v;
+    int rc = gpupcgi_mesh_view(m, &v);
+    if (rc) { h->err = std::string("gpupcg_solve_assembled_D: ") + gpupcg_mesh_last_error(m); return rc; }
+    const HostPlan& P = h->plan;
+    if (v.device != h->device || v.nCells != P.nCells || v.nIF != P.nFaces)
+    {
+        h->err = "gpupcg_solve_assembled_D: the solver handle was not created for this mesh (device / cells / internal faces differ)";
+        return GPUPCG_ERR_ARG;
+    }
+    if (h->nPatches > 0) { h->err = "gpupcg_solve_assembled_D: coupled (processor) patches are not assembled on the device yet"; return GPUPCG_ERR_UNSUPPORTED; }
+    CK(cudaSetDevice(h->device));
+    rc = vec_prepare<3>(h); if (rc) return rc;
+    cudaStream_t s = h->stream;
+    const size_t bytes = sizeof(double)*3*(size_t)P.nCells;
+    CK(cudaEventRecord(h->ev[2], s));
+    CK(cudaMemcpyAsync(h->vStageX, D, bytes, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(h->ev[3], s));
+    // addBoundaryDiag / addBoundarySource on the device, straight into the solver's staging buffers
+    LAUNCH(k_add_boundary3, grid_for(P.nCells, h->streamGrid), s, P.nCells, v.cellBfStart, v.cellBf, v.diag, v.source, v.ic, v.bc,
+           h->vStageD, h->vStageB);
+    CK(cudaGetLastError());
+    rc = vec_set_matrix_device<3>(h, h->vStageD, v.upper, nullptr); if (rc) return rc;
+    rc = vec_solve_device<3>(h, h->vStageX, h->vStageB, tol, relTol, minIter, maxIter, perf, nullptr, 0); if (rc) return rc;
+    float msIn = 0.f, msOut = 0.f;
+    cudaEventElapsedTime(&msIn, h->ev[2], h->ev[3]);
+    CK(cudaEventRecord(h->ev[2], s));
+    CK(cudaMemcpyAsync(D, h->vStageX, bytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(h->ev[3], s));
+    CK(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&msOut, h->ev[2], h->ev[3]);
+    if (perf) for (int k = 0; k < 3; k++) { perf[k].h2d_ms = msIn; perf[k].d2h_ms = msOut; }
+    return GPUPCG_OK;
+}

@@ -898,6 +898,29 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile_v(TileArgs A, const doub
     }
 }
 
+// fvMatrix::addBoundaryDiag / addBoundarySource [EXT fvMatrix.C] of the non-coupled patches for the three components of
+// the D equation, in fvMatrix's order (a cell's boundary faces ascending = patches in index order, faces in patch
+// order):  diagC[c][k] = diag[c] + sum internalCoeffs[bf][k],  bC[c][k] = source[c][k] + sum boundaryCoeffs[bf][k]
+__global__ void __launch_bounds__(TPB) k_add_boundary3(int nCells, const int* __restrict__ cellBfStart, const int* __restrict__ cellBf,
+                                                       const double* __restrict__ diag, const double* __restrict__ source,
+                                                       const double* __restrict__ ic, const double* __restrict__ bc,
+                                                       double* __restrict__ diagC, double* __restrict__ bC)
+{
+    for (int c = blockIdx.x*TPB + threadIdx.x; c < nCells; c += gridDim.x*TPB)
+    {
+        const double d0 = diag[c];
+        double d[3] = {d0, d0, d0}, b[3] = {source[3*(size_t)c], source[3*(size_t)c + 1], source[3*(size_t)c + 2]};
+        for (int q = cellBfStart[c]; q < cellBfStart[c + 1]; q++)
+        {
+            const size_t bf = (size_t)cellBf[q];
+#pragma unroll
+            for (int k = 0; k < 3; k++) { d[k] = __dadd_rn(d[k], ic[3*bf + k]); b[k] = __dadd_rn(b[k], bc[3*bf + k]); }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) { diagC[3*(size_t)c + k] = d[k]; bC[3*(size_t)c + k] = b[k]; }
+    }
+}
+
 // raw face coefficients per row (shared by the components)
 __global__ void __launch_bounds__(TPB) k_tab_raw(int nRows, const int4* __restrict__ idx, const double* __restrict__ Uval,
                                                  double* __restrict__ F)

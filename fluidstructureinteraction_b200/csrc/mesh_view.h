@@ -1,0 +1,14 @@
+// mesh_view.h -- internal hand-over between the assembly side (assembly.cu) and the solver side (gpupcg_vec.cuh) of the
+// library: device pointers of the D equation the last gpupcg_assemble_D left on the device.  Not part of the C ABI.
+#pragma once
+#include "../../include/gpupcg.h"
+
+struct gpupcg_mesh_view
+{
+    int device, nCells, nIF, nBF;
+    const double *upper, *diag, *source;        // [nIF], [nCells], [nCells*3]  (before addBoundaryDiag / addBoundarySource)
+    const double *ic, *bc;                      // internalCoeffs / boundaryCoeffs [nBF*3]
+    const int *cellBfStart, *cellBf;            // cell -> boundary faces (face index - nIF), ascending
+};
+
+extern "C" int gpupcgi_mesh_view(gpupcg_mesh m, gpupcg_mesh_view* v);

@@ -25,7 +25,7 @@ unsTotalLagrangianStressGpu::unsTotalLagrangianStressGpu
     const scalar* traction, const scalar* pressure, const scalar* fixedValue, scalar limitCoeff
 )
 :
-    mesh_(mesh), gm_(0), mu_(mu, mu + mesh.nCells), lambda_(lambda, lambda + mesh.nCells), rho_(rho, rho + mesh.nCells),
+    mesh_(mesh), gm_(0), solver_(0), device_(device), mu_(mu, mu + mesh.nCells), lambda_(lambda, lambda + mesh.nCells), rho_(rho, rho + mesh.nCells),
     limitCoeff_(limitCoeff)
 {
     const int nBF = mesh.nFaces - mesh.nInternalFaces;
@@ -49,6 +49,7 @@ unsTotalLagrangianStressGpu::unsTotalLagrangianStressGpu
 
 unsTotalLagrangianStressGpu::~unsTotalLagrangianStressGpu()
 {
+    if (solver_) gpupcg_destroy(solver_);
     if (gm_) gpupcg_mesh_destroy(gm_);
 }
 
@@ -71,6 +72,18 @@ evolveResult unsTotalLagrangianStressGpu::evolve
     std::vector<scalar> upper(nIF), diag(nC), source(3*(size_t)nC), ic(3*(size_t)std::max(1, nBF)), bc(3*(size_t)std::max(1, nBF));
     std::vector<scalar> Dprev(D.size());
 
+    // `solver gpuPCG` with batchComponents (default): DEqn.solve() runs on the matrix where the assembly left it, on the
+    // device (keyword residentMatrix no: the fvMatrix is rebuilt on the host and solved through lduMatrix::solver::New)
+    const bool residentSolve = word(solverDict.lookup("solver")) == gpuPCG::typeName
+                            && solverDict.lookupOrDefault<word>("batchComponents", "yes") != "no"
+                            && solverDict.lookupOrDefault<word>("residentMatrix", "yes") != "no";
+    if (residentSolve && solverDict.found("preconditioner") && word(solverDict.lookup("preconditioner")) != "DIC")
+        FatalErrorIn("unsTotalLagrangianStressGpu::evolve") << "gpuPCG implements the DIC preconditioner only" << abort(FatalError);
+    scalar tolerance = 1e-6, relTol = 0;
+    int minIter = 0, maxIter = 1000;                                    // lduMatrix::solver::readControls defaults
+    solverDict.readIfPresent("tolerance", tolerance); solverDict.readIfPresent("relTol", relTol);
+    solverDict.readIfPresent("minIter", minIter); solverDict.readIfPresent("maxIter", maxIter);
+
     evolveResult R;
     R.converged = 1; R.nOuterIterations = 0; R.initialResidual = 0; R.lastSolverInitialResidual = 0;
     R.maxRes = 0; R.res = 1; R.totalPcgIterations = 0;
@@ -86,6 +99,37 @@ evolveResult unsTotalLagrangianStressGpu::evolve
         // (gpupcg_gradients leaves them there), fetched once after the loop
         const scalar* gD = (iCorr == 0) ? &gradD[0] : 0;
         const scalar* gDf = (iCorr == 0) ? &gradDf[0] : 0;
+        lduMatrix::solverPerformance solverPerf;
+        if (residentSolve)
+        {
+            // the assembled equation stays on the device: addBoundaryDiag / addBoundarySource and the three component
+            // solves happen there (gpupcg_solve_assembled_D); only D travels
+            meshCheck(gm_, gpupcg_assemble_D(gm_, &mu_[0], &lambda_[0], &rho_[0], g_, &D[0], gD, gDf, &traction_[0], &pressure_[0],
+                                             &fixedValue_[0], limitCoeff_, 1, 0, 0, 0, 0, 0, 0), "gpupcg_assemble_D");
+            if (!solver_)
+            {
+                int rc = gpupcg_create(&solver_, device_, nC, nIF, mesh_.owner, mesh_.neighbour, 0, 0, 0, 0);
+                if (rc != 0)
+                    FatalErrorIn("unsTotalLagrangianStressGpu::evolve") << "gpupcg_create failed (" << rc << "): "
+                                                                       << gpupcg_last_error(0) << abort(FatalError);
+            }
+            gpupcg_perf perf[3];
+            int rc = gpupcg_solve_assembled_D(solver_, gm_, &D[0], tolerance, relTol, minIter, maxIter, perf);
+            if (rc != 0)
+                FatalErrorIn("unsTotalLagrangianStressGpu::evolve") << "gpupcg_solve_assembled_D failed (" << rc << "): "
+                                                                   << gpupcg_last_error(solver_) << abort(FatalError);
+            static const char* cmptNames[3] = {"x", "y", "z"};
+            for (int k = 0; k < 3; k++)
+            {
+                lduMatrix::solverPerformance p("DICgpuPCG", word("D") + cmptNames[k], perf[k].initialResidual, perf[k].finalResidual,
+                                               perf[k].nIterations, perf[k].converged != 0, perf[k].singular != 0);
+                p.print();
+                R.totalPcgIterations += p.nIterations();
+                if (k == 0 || (p.initialResidual() > solverPerf.initialResidual() && !p.singular())) solverPerf = p;
+            }
+        }
+        else
+        {
         meshCheck(gm_, gpupcg_assemble_D(gm_, &mu_[0], &lambda_[0], &rho_[0], g_, &D[0], gD, gDf, &traction_[0],
                                          &pressure_[0], &fixedValue_[0], limitCoeff_, 1, &upper[0], &diag[0], &source[0],
                                          &ic[0], &bc[0], 0), "gpupcg_assemble_D");
@@ -104,8 +148,9 @@ evolveResult unsTotalLagrangianStressGpu::evolve
             DEqn.patches.push_back(pc);
         }
         std::vector<lduMatrix::solverPerformance> per;
-        lduMatrix::solverPerformance solverPerf = DEqn.solve(D, solverDict, &per);      // DEqn.solve()
+        solverPerf = DEqn.solve(D, solverDict, &per);                                   // DEqn.solve()
         for (size_t k = 0; k < per.size(); k++) R.totalPcgIterations += per[k].nIterations();
+        }
 
         if (iCorr == 0) R.initialResidual = solverPerf.initialResidual();
         R.lastSolverInitialResidual = solverPerf.initialResidual();

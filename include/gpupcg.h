@@ -254,6 +254,14 @@ int gpupcg_mesh_set_points(gpupcg_mesh m, int nPoints, const double* points, con
  *                       2 gradDf [nFaces*9], 3 gradDb [nBoundaryFaces*9].
  * GPUPCG_ERR_STATE if the device holds nothing yet.                                                                    */
 int gpupcg_mesh_fetch(gpupcg_mesh m, int which, double* out);
+/* DEqn.solve() (unsTotalLagrangianStress.C:908) on the D equation the last gpupcg_assemble_D left on the device, without
+ * the matrix crossing PCIe: fvMatrix::addBoundaryDiag / addBoundarySource of the (non-coupled) patches [EXT fvMatrix.C]
+ * are applied on the device in fvMatrix's order, then the three components are solved by the batched PCG -- the same
+ * bits as gpupcg_assemble_D -> host -> gpupcg_set_matrix_vector + gpupcg_solve_vector.  h: a solver handle created
+ * with this mesh's owner/neighbour (internal faces) addressing on the same device; D [nCells*3] host, in/out;
+ * perfCmpt [3].  gpupcg_assemble_D may be called with NULL output pointers then (nothing is copied back).            */
+int gpupcg_solve_assembled_D(gpupcg_handle h, gpupcg_mesh m, double* D, double tolerance, double relTol, int minIter,
+                             int maxIter, gpupcg_perf* perfCmpt);
 int gpupcg_gradients(gpupcg_mesh m, const double* D, const double* pointD, const double* gradDold,
                      const double* fixedValue, const double* patchGradient, double limitCoeff, int reps,
                      double* gradD, double* gradDb, double* gradDf, double* kernel_ms);

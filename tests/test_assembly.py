@@ -261,3 +261,44 @@ def test_gpu_gradients_stay_resident_between_outer_iterations(kind):
     r1 = oracle.assemble_D(m, g, PATCHES, f["mu"], f["lam"], f["rho"], f["g"], D1, G1, Gf1, f["traction"], f["pressure"], f["fixedValue"], 1.0)
     assert np.array_equal(b1["source"], r1["source"])
     gm.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["hex", "tet"])
+def test_gpu_solve_on_the_resident_equation(kind):
+    """gpupcg_solve_assembled_D: DEqn.solve() on the equation the assembly left on the device (addBoundaryDiag /
+    addBoundarySource there, in fvMatrix's order; batched component solves) gives the same bits as assembly -> host ->
+    fvMatrix<vector>::solve's diag / source per component -> gpupcg_set_matrix_vector + gpupcg_solve_vector."""
+    m = meshes.hex_box(12, 6, 8) if kind == "hex" else meshes.tet_box(6, 4, 5, jitter=0.15)
+    g = geometry.compute(m)
+    f = fields(m, 9)
+    nIF = m.nInternalFaces
+    l, u = m.lower_upper()
+    args = (f["mu"], f["lam"], f["rho"], f["g"], f["D"], f["gradD"], f["gradDf"], f["traction"], f["pressure"], f["fixedValue"], 1.0)
+    gm = pkg.GpuMesh(m, g, PATCHES)
+    solver = pkg.GpuPCG(l, u, m.nCells)
+    with pytest.raises(pkg.GpuPcgError) as e:
+        solver.solve_assembled_D(gm, np.zeros((m.nCells, 3)))
+    assert e.value.code == -5                       # nothing assembled yet
+    a = gm.assemble_D(*args)
+    diagC = np.repeat(a["diag"][:, None], 3, axis=1)
+    bC = a["source"].copy()
+    own = np.asarray(m.owner[nIF:])
+    for k in range(3):                              # fvMatrix order: boundary faces ascending
+        np.add.at(diagC[:, k], own, a["internalCoeffs"][:, k])
+        np.add.at(bC[:, k], own, a["boundaryCoeffs"][:, k])
+    ref = pkg.GpuPCG(l, u, m.nCells)
+    ref.set_matrix_vector(np.ascontiguousarray(diagC), a["upper"])
+    D2 = np.ascontiguousarray(f["D"].copy())
+    p2, _ = ref.solve_vector(D2, np.ascontiguousarray(bC), 1e-12, 0.0)
+    gm.assemble_D(*args, copy_back=False)
+    D1 = np.ascontiguousarray(f["D"].copy())
+    p1 = solver.solve_assembled_D(gm, D1, 1e-12, 0.0)
+    assert [p["nIterations"] for p in p1] == [p["nIterations"] for p in p2] and max(p["nIterations"] for p in p1) > 3
+    assert np.array_equal(D1, D2)
+    wrong = pkg.GpuPCG(l[:-1], u[:-1], m.nCells)
+    with pytest.raises(pkg.GpuPcgError) as e:
+        wrong.solve_assembled_D(gm, D1)
+    assert e.value.code == -1                       # handle of another addressing
+    for x in (solver, ref, wrong, gm):
+        x.close()

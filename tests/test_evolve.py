@@ -81,8 +81,11 @@ def test_gpu_relax_residual_bit_exact(kind):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind,relax", [("hex", None), ("tet", 0.8)])
-def test_gpu_evolve_matches_oracle_loop(kind, relax):
+@pytest.mark.parametrize("kind,relax,resident", [("hex", None, "yes"), ("tet", 0.8, "yes"), ("hex", None, "no"), ("tet", 0.8, "no")])
+def test_gpu_evolve_matches_oracle_loop(kind, relax, resident):
+    """residentMatrix yes (default): the assembled D equation never leaves the device (gpupcg_solve_assembled_D) and the
+    gradients stay there between outer iterations; no: the fvMatrix is rebuilt on the host every outer iteration and
+    solved through lduMatrix::solver::New -- the same loop statistics and fields either way."""
     m, g, mu, lam, rho, grav, trac, pres, fixed = problem(kind)
     v2p = point_average(m)
     nCorr = 6
@@ -90,7 +93,7 @@ def test_gpu_evolve_matches_oracle_loop(kind, relax):
                          convergenceTolerance=1e-12, relConvergenceTolerance=1e-9, relaxD=relax)
     got = hostapi.evolve(m, g, PATCHES, mu, lam, rho, grav, trac, pres, fixed, v2p,
                          "nCorrectors %d; convergenceTolerance 1e-12; relConvergenceTolerance 1e-9;" % nCorr,
-                         "solver gpuPCG; preconditioner DIC; tolerance 1e-09; relTol 0.01;", relaxD=relax)
+                         "solver gpuPCG; preconditioner DIC; tolerance 1e-09; relTol 0.01; residentMatrix %s;" % resident, relaxD=relax)
     assert got["nOuterIterations"] == ref["nOuterIterations"]
     assert got["totalPcgIterations"] == ref["totalPcgIterations"]
     # the pieces are bit-exact except the PCG reductions (re-associated): the solutions agree to ~1e-12 of their size
