@@ -2,6 +2,8 @@
 #include "../foam/gpuPCG/gpuPCG.H"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 
 #include <cstdlib>
 #include <sstream>
@@ -89,6 +91,13 @@ evolveResult unsTotalLagrangianStressGpu::evolve
     R.maxRes = 0; R.res = 1; R.totalPcgIterations = 0;
     residualHistory.clear();
 
+    // GPUPCG_EVOLVE_TIMING=1: wall time per phase of the outer loop on stderr
+    const bool timing = getenv("GPUPCG_EVOLVE_TIMING") != 0;
+    typedef std::chrono::steady_clock clk;
+    double tAsm = 0, tSolve = 0, tRelax = 0, tInterp = 0, tGrad = 0;
+    clk::time_point t0 = clk::now();
+    auto lap = [&](double& acc) { clk::time_point t1 = clk::now(); acc += std::chrono::duration<double>(t1 - t0).count(); t0 = t1; };
+
     int iCorr = 0;
     scalar res = 1, maxRes = 0, curConvergenceTolerance = convergenceTolerance;
     do
@@ -106,6 +115,7 @@ evolveResult unsTotalLagrangianStressGpu::evolve
             // solves happen there (gpupcg_solve_assembled_D); only D travels
             meshCheck(gm_, gpupcg_assemble_D(gm_, &mu_[0], &lambda_[0], &rho_[0], g_, &D[0], gD, gDf, &traction_[0], &pressure_[0],
                                              &fixedValue_[0], limitCoeff_, 1, 0, 0, 0, 0, 0, 0), "gpupcg_assemble_D");
+            lap(tAsm);
             if (!solver_)
             {
                 int rc = gpupcg_create(&solver_, device_, nC, nIF, mesh_.owner, mesh_.neighbour, 0, 0, 0, 0);
@@ -133,6 +143,7 @@ evolveResult unsTotalLagrangianStressGpu::evolve
         meshCheck(gm_, gpupcg_assemble_D(gm_, &mu_[0], &lambda_[0], &rho_[0], g_, &D[0], gD, gDf, &traction_[0],
                                          &pressure_[0], &fixedValue_[0], limitCoeff_, 1, &upper[0], &diag[0], &source[0],
                                          &ic[0], &bc[0], 0), "gpupcg_assemble_D");
+        lap(tAsm);
         for (int c = 0; c < nC; c++) matrix.diag()[c] = diag[c];
         for (int f = 0; f < nIF; f++) matrix.upper()[f] = upper[f];
         fvMatrixLike DEqn("D", 3, matrix);
@@ -152,17 +163,21 @@ evolveResult unsTotalLagrangianStressGpu::evolve
         for (size_t k = 0; k < per.size(); k++) R.totalPcgIterations += per[k].nIterations();
         }
 
+        lap(tSolve);
         if (iCorr == 0) R.initialResidual = solverPerf.initialResidual();
         R.lastSolverInitialResidual = solverPerf.initialResidual();
 
         // D_.relax();  ...  res = residual()   (the residual only reads D, prevIter and oldTime: evaluated with the relax)
         meshCheck(gm_, gpupcg_relax_residual(gm_, relaxD, relaxD >= 0 ? 1 : 0, &D[0], &Dprev[0], &Dold[0], &res),
                   "gpupcg_relax_residual");
+        lap(tRelax);
 
         interpolate(ctx, &D[0], &pointD[0]);                            // volToPoint_.interpolate(D_, pointD_)
+        lap(tInterp);
         // gradDold = NULL: the device's current grad(D) is the registered gradient; patchGradient = NULL: the
         // tractionDisplacement gradient() the assembly above left on the device; outputs stay on the device
         meshCheck(gm_, gpupcg_gradients(gm_, &D[0], &pointD[0], 0, &fixedValue_[0], 0, limitCoeff_, 1, 0, 0, 0, 0), "gpupcg_gradients");
+        lap(tGrad);
 
         if (res > maxRes) maxRes = res;
         curConvergenceTolerance = maxRes*relConvergenceTolerance;
@@ -174,6 +189,10 @@ evolveResult unsTotalLagrangianStressGpu::evolve
     meshCheck(gm_, gpupcg_sigma(gm_, &mu_[0], &lambda_[0], 0, &epsilon[0], &sigma[0]), "gpupcg_sigma");
     meshCheck(gm_, gpupcg_mesh_fetch(gm_, 1, &gradD[0]), "gpupcg_mesh_fetch(gradD)");
     meshCheck(gm_, gpupcg_mesh_fetch(gm_, 2, &gradDf[0]), "gpupcg_mesh_fetch(gradDf)");
+    double tEnd = 0; lap(tEnd);
+    if (timing)
+        fprintf(stderr, "evolve timing [s]: assemble %.3f  solve %.3f  relax/residual %.3f  volToPoint %.3f  gradients %.3f  sigma+fetch %.3f  (%s)\n",
+                tAsm, tSolve, tRelax, tInterp, tGrad, tEnd, residentSolve ? "resident" : "host matrix");
     gpuPCG::clearCache();       // `addr` dies with this call
     R.nOuterIterations = iCorr; R.maxRes = maxRes; R.res = res;
     return R;
