@@ -25,17 +25,9 @@ namespace gpupcg
 // row stride of the interleaved vectors
 template <int NB> struct VecStride { static constexpr int v = (NB == 3) ? 4 : NB; };
 
-// NB values of one row out of shared / global memory (p 16-byte aligned: rows are 16 or 32 bytes)
-template <int NB>
-__device__ __forceinline__ void row_load(const double* p, double (&v)[NB])
-{
-    const double2 a = *reinterpret_cast<const double2*>(p);
-    v[0] = a.x; v[1] = a.y;
-    if (NB == 3) v[2] = p[2];
-}
-// The same out of SHARED memory for lanes that read consecutive rows (32-byte stride): half the lanes fetch the upper
-// 16 bytes first, so that the eight lanes of a quarter-warp cover all 32 banks in each of the two accesses (two 2-way
-// conflicts otherwise: every access touches only half of each row).
+// NB values of one row (p 16-byte aligned: rows are 16 or 32 bytes) out of SHARED memory, for lanes that read consecutive
+// rows (32-byte stride): half the lanes fetch the upper 16 bytes first, so that the eight lanes of a quarter-warp cover
+// all 32 banks in each of the two accesses (two 2-way conflicts otherwise: every access touches only half of each row).
 template <int NB>
 __device__ __forceinline__ void row_load_sw(const double* p, double (&v)[NB], bool hiFirst)
 {
