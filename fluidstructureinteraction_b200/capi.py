@@ -40,6 +40,40 @@ class Perf(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+class EqnControls(C.Structure):
+    """gpupcg_eqn_controls"""
+    _fields_ = [("d2dt2Scheme", C.c_int), ("ddtScheme", C.c_int), ("deltaT", C.c_double), ("deltaT0", C.c_double),
+                ("K", C.c_double), ("nonLinear", C.c_int), ("thermal", C.c_int), ("limitCoeff", C.c_double)]
+
+
+class EvolveControls(C.Structure):
+    """gpupcg_evolve_controls"""
+    _fields_ = [("nCorrectors", C.c_int), ("convergenceTolerance", C.c_double), ("relConvergenceTolerance", C.c_double),
+                ("tolerance", C.c_double), ("relTol", C.c_double), ("minIter", C.c_int), ("maxIter", C.c_int),
+                ("relaxD", C.c_double), ("doRelax", C.c_int), ("validCmpt", C.c_int*3), ("g", C.c_double*3),
+                ("eqn", EqnControls)]
+
+
+class EvolveResult(C.Structure):
+    """gpupcg_evolve_result"""
+    _fields_ = [("nOuterIterations", C.c_int), ("totalPcgIterations", C.c_int), ("enforceLinear", C.c_int),
+                ("converged", C.c_int), ("initialResidual", C.c_double), ("lastSolverInitialResidual", C.c_double),
+                ("maxRes", C.c_double), ("res", C.c_double), ("assemble_ms", C.c_double), ("solve_ms", C.c_double),
+                ("update_ms", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+SCHEMES = {"steadyState": 0, "Euler": 1}
+
+
+def eqn_controls(d2dt2="steadyState", ddt="steadyState", deltaT=1.0, deltaT0=None, K=0.0, nonLinear=False, thermal=False,
+                 limitCoeff=1.0):
+    return EqnControls(SCHEMES[d2dt2], SCHEMES[ddt], float(deltaT), float(deltaT if deltaT0 is None else deltaT0), float(K),
+                       int(bool(nonLinear)), int(bool(thermal)), float(limitCoeff))
+
+
 class PlanInfo(C.Structure):
     _fields_ = [
         ("nCells", C.c_int), ("nFaces", C.c_int), ("nRows", C.c_int), ("nSlices", C.c_int),
@@ -98,6 +132,17 @@ SYMBOLS = {
     "gpupcg_solve_assembled_D": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_double, C.c_double, C.c_int, C.c_int,
                                            C.POINTER(Perf)]),
     "gpupcg_gradients": (C.c_int, [C.c_void_p] + [c_double_p]*5 + [C.c_double, C.c_int] + [c_double_p]*4),
+    "gpupcg_mesh_field_size": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]),
+    "gpupcg_mesh_set_field": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
+    "gpupcg_mesh_get_field": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
+    "gpupcg_mesh_set_lsq": (C.c_int, [C.c_void_p, c_int_p, c_int_p, c_double_p, c_double_p, C.POINTER(C.c_ubyte)]),
+    "gpupcg_vol_to_point": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
+    "gpupcg_patch_evaluate": (C.c_int, [C.c_void_p]),
+    "gpupcg_assemble_D_resident": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p]),
+    "gpupcg_gradients_resident": (C.c_int, [C.c_void_p, C.c_double]),
+    "gpupcg_sigma_resident": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gpupcg_mesh_new_time_step": (C.c_int, [C.c_void_p]),
+    "gpupcg_evolve_D": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_double_p, c_int_p, C.c_int]),
     "gpupcg_host_register": (C.c_int, [C.c_void_p, C.c_ulonglong]),
     "gpupcg_host_unregister": (C.c_int, [C.c_void_p]),
     "gpupcg_plan_export": (C.c_int, [C.c_int, C.c_int, c_int_p, c_int_p, C.c_int, C.c_int, C.POINTER(PlanInfo),
@@ -319,6 +364,28 @@ class GpuPCG(object):
         self._check(self.lib.gpupcg_solve_assembled_D(self.h, gpuMesh.h, _dp(D), tolerance, relTol, minIter, maxIter, perf))
         return [perf[k].as_dict() for k in range(3)]
 
+    def evolve_D(self, gpuMesh, nCorrectors, convergenceTolerance, relConvergenceTolerance=0.0, tolerance=1e-9, relTol=0.01,
+                 minIter=0, maxIter=1000, relaxD=None, validCmpts=(1, 1, 1), g=(0.0, 0.0, 0.0), eqn=None, historyCap=None):
+        """unsTotalLagrangianStress::evolve() on the fields resident in gpuMesh (gpupcg_evolve_D)."""
+        ec = EvolveControls()
+        ec.nCorrectors = int(nCorrectors); ec.convergenceTolerance = convergenceTolerance
+        ec.relConvergenceTolerance = relConvergenceTolerance; ec.tolerance = tolerance; ec.relTol = relTol
+        ec.minIter = minIter; ec.maxIter = maxIter
+        ec.relaxD = 1.0 if relaxD is None else float(relaxD); ec.doRelax = 0 if relaxD is None else 1
+        for k in range(3):
+            ec.validCmpt[k] = int(validCmpts[k]); ec.g[k] = float(g[k])
+        ec.eqn = eqn if eqn is not None else eqn_controls()
+        cap = int(historyCap if historyCap is not None else nCorrectors)
+        hist = np.zeros(max(cap, 1)); its = np.zeros((max(cap, 1), 3), dtype=np.int32)
+        res = EvolveResult()
+        self._check(self.lib.gpupcg_evolve_D(self.h, gpuMesh.h, C.byref(ec), C.byref(res), _dp(hist), _ip(its), cap))
+        r = res.as_dict()
+        n = min(cap, r["nOuterIterations"] + 1)
+        r["residualHistory"] = hist[:n].copy()
+        nv = int(sum(1 for v in validCmpts if v))
+        r["pcgIterations"] = its[:n, :nv].copy()
+        return r
+
     def time_kernel_vector(self, nCmpt, which, reps=10, flushL2=True):
         ms = C.c_double(0.0)
         self._check(self.lib.gpupcg_time_kernel_vector(self.h, nCmpt, self.KERNELS[which], reps, 1 if flushL2 else 0, C.byref(ms)))
@@ -329,7 +396,14 @@ class GpuPCG(object):
         self._check(self.lib.gpupcg_comm_init(self.h, rank, nRanks, buf))
 
 
-PATCH_TYPES = {"tractionDisplacement": 0, "fixedDisplacement": 1, "symmetryDisplacement": 2}
+PATCH_TYPES = {"tractionDisplacement": 0, "fixedDisplacement": 1, "symmetryDisplacement": 2, "symmetryPlane": 3, "empty": 4}
+
+FIELD_IDS = dict(mu=0, lambda_=1, rho=2, D=3, Dold=4, Doldold=5, gradD=6, gradDf=7, traction=8, pressure=9, fixedValue=10,
+                 threeK=11, alpha=12, DT=13, DTb=14, pointD=15, Db=16, gradDb=17, U=18, epsilon=19, sigma=20, upper=21,
+                 diag=22, source=23, internalCoeffs=24, boundaryCoeffs=25, patchGradient=26, Dprev=27, DbPrev=28)
+_FIELD_COLS = dict(mu=1, lambda_=1, rho=1, D=3, Dold=3, Doldold=3, gradD=9, gradDf=9, traction=3, pressure=1, fixedValue=3,
+                   threeK=1, alpha=1, DT=1, DTb=1, pointD=3, Db=3, gradDb=9, U=3, epsilon=6, sigma=6, upper=1, diag=1,
+                   source=3, internalCoeffs=3, boundaryCoeffs=3, patchGradient=3, Dprev=3, DbPrev=3)
 
 
 class GpuMesh(object):
@@ -426,6 +500,55 @@ class GpuMesh(object):
         self._check(self.lib.gpupcg_relax_residual(self.h, float(alpha if alpha is not None else 1.0), 0 if alpha is None else 1,
                                                    _dp(D), _dp(_f64(Dprev)), _dp(_f64(Dold)), C.byref(res)))
         return res.value
+
+    # ---- resident fields (round 2) ----
+    def _field_shape(self, name):
+        n = C.c_longlong(0)
+        self._check(self.lib.gpupcg_mesh_field_size(self.h, FIELD_IDS[name], C.byref(n)))
+        k = _FIELD_COLS[name]
+        return (n.value // k, k) if k > 1 else (n.value,)
+
+    def set_field(self, name, a):
+        if name == "pointD":
+            self._ensure_points()
+        a = _f64(a)
+        shape = self._field_shape(name)
+        assert a.size == int(np.prod(shape)), (name, a.shape, shape)
+        self._check(self.lib.gpupcg_mesh_set_field(self.h, FIELD_IDS[name], _dp(a)))
+
+    def get_field(self, name):
+        out = np.empty(self._field_shape(name))
+        self._check(self.lib.gpupcg_mesh_get_field(self.h, FIELD_IDS[name], _dp(out)))
+        return out
+
+    def set_lsq(self, lsq):
+        """lsq: dict(start, entry, inv, origin, mirror) -- what leastSquaresVolPointInterpolation holds (lsq.build)."""
+        self._ensure_points()
+        st, en, iv, og, mi = _i32(lsq["start"]), _i32(lsq["entry"]), _f64(lsq["inv"]), _f64(lsq["origin"]), \
+            np.ascontiguousarray(lsq["mirror"], dtype=np.uint8)
+        self._check(self.lib.gpupcg_mesh_set_lsq(self.h, _ip(st), _ip(en), _dp(iv), _dp(og), mi.ctypes.data_as(C.POINTER(C.c_ubyte))))
+
+    def vol_to_point(self, reps=1):
+        ms = C.c_double(0.0)
+        self._check(self.lib.gpupcg_vol_to_point(self.h, int(reps), C.byref(ms)))
+        return ms.value
+
+    def patch_evaluate(self):
+        self._check(self.lib.gpupcg_patch_evaluate(self.h))
+
+    def assemble_resident(self, eqn, g=(0.0, 0.0, 0.0)):
+        gv = _f64(g)
+        self._check(self.lib.gpupcg_assemble_D_resident(self.h, C.byref(eqn) if eqn is not None else None, _dp(gv)))
+
+    def gradients_on_device(self, limitCoeff=1.0):
+        self._ensure_points()
+        self._check(self.lib.gpupcg_gradients_resident(self.h, float(limitCoeff)))
+
+    def sigma_resident(self, eqn=None):
+        self._check(self.lib.gpupcg_sigma_resident(self.h, C.byref(eqn) if eqn is not None else None))
+
+    def new_time_step(self):
+        self._check(self.lib.gpupcg_mesh_new_time_step(self.h))
 
     def sigma(self, mu, lam, gradD):
         """gradD = None: the device's grad(D)."""

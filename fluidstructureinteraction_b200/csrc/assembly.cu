@@ -97,6 +97,8 @@ __device__ void symmetry_snGrad(const MeshDev& M, int f, const double* __restric
     for (int d = 0; d < 3; d++) sn[d] = mul(sub(tv[d], UP[d]), h);
 }
 
+#include "assembly_ext.cuh"
+
 // One chunk of the assembly (see AsmChunk): slot s of the chunk's flux ring is internal face f0 + s for s < nOwn (the
 // faces the chunk's cells own), then the chunk's extra faces: internal faces owned by an EARLIER chunk whose neighbour
 // cell is in this chunk (recomputed here: 1-2 % of the faces), then the boundary faces of the chunk's cells.
@@ -114,6 +116,13 @@ __global__ void __launch_bounds__(ATPB) k_asm_faces(MeshDev M, AsmChunk K, const
         const int f = (sl < K.nOwn) ? K.f0 + sl : extraFace[K.extraStart + sl - K.nOwn];
         const int P = M.owner[f];
         const bool internal = f < M.nIF;
+        if (!internal && M.bfPatchType[f - M.nIF] == 4)
+        {
+            // empty patch (2-D cases): its fvsPatchFields have no faces -- no flux, no coefficients
+            gms[f] = 0.0;
+            fluxE[3*(size_t)sl] = 0.0; fluxE[3*(size_t)sl + 1] = 0.0; fluxE[3*(size_t)sl + 2] = 0.0;
+            continue;
+        }
         const int N = internal ? M.neighbour[f] : P;
         double muf, laf;
         if (internal)
@@ -184,7 +193,8 @@ __global__ void __launch_bounds__(ATPB) k_asm_faces(MeshDev M, AsmChunk K, const
 
 // cellSlot[k] (parallel to the cell -> face CSR): ring slot of the face | bit 31: the cell is the face's neighbour |
 // bit 30: boundary face
-__global__ void __launch_bounds__(ATPB) k_asm_cells(MeshDev M, AsmChunk K, const int* __restrict__ cellSlot,
+__global__ void __launch_bounds__(ATPB) k_asm_cells(MeshDev M, AsmChunk K, AsmCtl T, const double* __restrict__ Dold,
+                                                    const double* __restrict__ Doldold, const int* __restrict__ cellSlot,
                                                     const double* __restrict__ rho, double g0, double g1, double g2,
                                                     const double* __restrict__ Lup, const double* __restrict__ upperSingle,
                                                     const double* __restrict__ fluxE,
@@ -239,21 +249,57 @@ __global__ void __launch_bounds__(ATPB) k_asm_cells(MeshDev M, AsmChunk K, const
                 }
             }
         }
-        diag[c] = sub(0.0, Ld);
         const double V = M.V[c];
+        const double rh = rho[c];
+        // A = rho*fvm::d2dt2(D): steadyState contributes nothing; Euler [EXT EulerD2dt2Scheme, weights as in the
+        // reference's backwardD2dt2Scheme.C:306-331]: diag = (coefft*rDeltaT2)*V, source = rDeltaT2*V*((coefft+coefft00)*
+        // D.oldTime() - coefft00*D.oldTime().oldTime()), both then scaled by rho
+        double dA = 0.0, sA[3] = {0.0, 0.0, 0.0};
+        if (T.d2dt2 == 1)
+        {
+            dA = mul(mul(mul(T.coefft, T.rDeltaT2), V), rh);
+            const double t1 = mul(T.rDeltaT2, V), cc = add(T.coefft, T.coefft00);
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+                sA[d] = mul(mul(t1, sub(mul(cc, Dold[3*(size_t)c + d]), mul(T.coefft00, Doldold[3*(size_t)c + d]))), rh);
+        }
+        double dg = sub(dA, Ld);
         const double gv[3] = {g0, g1, g2};
+        double src[3];
 #pragma unroll
         for (int d = 0; d < 3; d++)
         {
             const double dcv = dvd(sC[d], V), de = dvd(sE[d], V);
-            const double rg = mul(rho[c], gv[d]);
+            const double rg = mul(rh, gv[d]);
             const double R = sub(sub(sub(0.0, mul(V, dcv)), mul(V, de)), mul(V, rg));
-            source[3*(size_t)c + d] = sub(0.0, R);
+            src[d] = sub(sA[d], R);
         }
+        if (T.damping)
+        {
+            // DEqn += K*rho_*fvm::ddt(D_)   (unsTotalLagrangianStress.C:861-865; [EXT] EulerDdtScheme::fvmDdt)
+            const double sf = mul(T.K, rh);
+            if (T.ddt == 1)
+            {
+                dg = add(dg, mul(mul(T.rDeltaT, V), sf));
+#pragma unroll
+                for (int d = 0; d < 3; d++) src[d] = add(src[d], mul(mul(mul(T.rDeltaT, Dold[3*(size_t)c + d]), V), sf));
+            }
+            else
+            {
+                dg = add(dg, 0.0);
+#pragma unroll
+                for (int d = 0; d < 3; d++) src[d] = add(src[d], 0.0);
+            }
+        }
+        diag[c] = dg;
+#pragma unroll
+        for (int d = 0; d < 3; d++) source[3*(size_t)c + d] = src[d];
     }
 }
 
-__global__ void __launch_bounds__(ATPB) k_asm_patches(MeshDev M, const double* __restrict__ mu, const double* __restrict__ lambda,
+__global__ void __launch_bounds__(ATPB) k_asm_patches(MeshDev M, AsmCtl T, const double* __restrict__ threeK, const double* __restrict__ alpha,
+                                                      const double* __restrict__ DTb,
+                                                      const double* __restrict__ mu, const double* __restrict__ lambda,
                                                       const double* __restrict__ D,
                                                       const double* __restrict__ gradD, const double* __restrict__ gradDf,
                                                       const double* __restrict__ gms, const double* __restrict__ traction,
@@ -268,9 +314,16 @@ __global__ void __launch_bounds__(ATPB) k_asm_patches(MeshDev M, const double* _
         const double Sf[3] = {M.Sf[3*f], M.Sf[3*f + 1], M.Sf[3*f + 2]};
         const double magSf = M.magSf[f], dcf = M.deltaCoeffs[f];
         double n[3], gIC[3], gBC[3];
+        const int ptype = M.bfPatchType[bf];
+        if (ptype == 4)
+        {
+#pragma unroll
+            for (int d = 0; d < 3; d++) { internalCoeffs[3*(size_t)bf + d] = 0.0; boundaryCoeffs[3*(size_t)bf + d] = 0.0; }
+            continue;
+        }
 #pragma unroll
         for (int d = 0; d < 3; d++) n[d] = dvd(Sf[d], magSf);
-        if (M.bfPatchType[bf] == 1)
+        if (ptype == 1)
         {
             double delta[3], k[3], kg[3], G[9];
 #pragma unroll
@@ -288,10 +341,10 @@ __global__ void __launch_bounds__(ATPB) k_asm_patches(MeshDev M, const double* _
                 gBC[d] = mul(dcf, sub(fixedValue[3*(size_t)bf + d], kg[d]));
             }
         }
-        else if (M.bfPatchType[bf] == 2)
+        else if (ptype == 2 || ptype == 3)
         {
             double sn[3];
-            symmetry_snGrad(M, f, D, gradD, sn);
+            if (ptype == 2) symmetry_snGrad(M, f, D, gradD, sn); else symmetryPlane_snGrad(M, f, D, sn);
 #pragma unroll
             for (int d = 0; d < 3; d++)
             {
@@ -302,22 +355,16 @@ __global__ void __launch_bounds__(ATPB) k_asm_patches(MeshDev M, const double* _
         else
         {
             const double m = mu[c], la = lambda[c];
-            double G[9], T[9], nT[3];
+            double G[9];
 #pragma unroll
             for (int q = 0; q < 9; q++) G[q] = gradDf[9*(size_t)f + q];
-            const double ml = add(m, la);
-            T[0] = sub(mul(m, G[0]), mul(ml, G[0])); T[1] = sub(mul(m, G[3]), mul(ml, G[1])); T[2] = sub(mul(m, G[6]), mul(ml, G[2]));
-            T[3] = sub(mul(m, G[1]), mul(ml, G[3])); T[4] = sub(mul(m, G[4]), mul(ml, G[4])); T[5] = sub(mul(m, G[7]), mul(ml, G[5]));
-            T[6] = sub(mul(m, G[2]), mul(ml, G[6])); T[7] = sub(mul(m, G[5]), mul(ml, G[7])); T[8] = sub(mul(m, G[8]), mul(ml, G[8]));
-            vdotT(n, T, nT);
-            const double tr = add(add(G[0], G[4]), G[8]);
-            const double den = add(mul(2.0, m), la);
+            const double tr3[3] = {traction[3*(size_t)bf], traction[3*(size_t)bf + 1], traction[3*(size_t)bf + 2]};
+            traction_gradient(M, T, f, m, la, G, tr3, pressure[bf], T.thermal ? threeK[c] : 0.0, T.thermal ? alpha[c] : 0.0,
+                              T.thermal ? DTb[bf] : 0.0, gBC);
 #pragma unroll
             for (int d = 0; d < 3; d++)
             {
-                const double t = sub(traction[3*(size_t)bf + d], mul(pressure[bf], n[d]));
                 gIC[d] = 0.0;
-                gBC[d] = dvd(sub(sub(t, nT[d]), mul(mul(n[d], la), tr)), den);
                 patchGrad[3*(size_t)bf + d] = gBC[d];       // the patch's gradient(): fvc::fGrad reads it next
             }
         }
@@ -622,6 +669,7 @@ __device__ void patch_snGrad(const MeshDev& M, int f, const double* __restrict__
         for (int d = 0; d < 3; d++) sn[d] = mul(sub(fixedValue[3*(size_t)bf + d], add(D[3*(size_t)c + d], kg[d])), M.deltaCoeffs[f]);
     }
     else if (M.bfPatchType[bf] == 2) symmetry_snGrad(M, f, D, gradD, sn);
+    else if (M.bfPatchType[bf] == 3) symmetryPlane_snGrad(M, f, D, sn);
     else
     {
 #pragma unroll
@@ -658,6 +706,7 @@ __global__ void __launch_bounds__(ATPB) k_grad_patches(MeshDev M, const double* 
     for (int bf = blockIdx.x*ATPB + threadIdx.x; bf < nBF; bf += gridDim.x*ATPB)
     {
         const int f = M.nIF + bf;
+        if (M.bfPatchType[bf] == 4) continue;           // empty: the fvPatch has no faces
         double G[9], n[3], sn[3], nG[3];
         face_tangential_grad(M, f, pointD, G);
         const double magSf = M.magSf[f];
@@ -680,6 +729,7 @@ __global__ void __launch_bounds__(ATPB) k_fgrad_faces(MeshDev M, const double* _
 {
     for (int f = blockIdx.x*ATPB + threadIdx.x; f < M.nFaces; f += gridDim.x*ATPB)
     {
+        if (f >= M.nIF && M.bfPatchType[f - M.nIF] == 4) continue;
         double G[9], n[3], sn[3];
         face_tangential_grad(M, f, pointD, G);
         const double magSf = M.magSf[f];
@@ -800,6 +850,13 @@ struct gpupcg_mesh_s
     double *dDiag = nullptr, *dSource = nullptr, *dIC = nullptr, *dBC = nullptr, *dEps = nullptr, *dSig = nullptr;
     double *dPointD = nullptr, *dGradOld = nullptr, *dPatchGrad = nullptr, *dGradDb = nullptr;
     double *dDprev = nullptr, *dDold = nullptr, *dRed = nullptr;
+    // round 2: the remaining state of evolve() (allocated on first use)
+    double *dDoldold = nullptr, *dThreeK = nullptr, *dAlpha = nullptr, *dDT = nullptr, *dDTb = nullptr;
+    double *dDb = nullptr, *dDbPrev = nullptr, *dU = nullptr;
+    double *dFluxX = nullptr, *dFluxY = nullptr, *dFluxT = nullptr;
+    bool haveDold = false, haveDoldold = false, haveThermal = false, haveDb = false;
+    LsqDev lsq{};                                  // leastSquaresVolPointInterpolation data (gpupcg_mesh_set_lsq)
+    double* hScal = nullptr;                       // pinned: {residual, maxDD, minDet, maxDet}
     // chunked assembly: the per-face fluxes of one chunk live in a ring sized to stay in L2 between the face and the cell kernel
     std::vector<AsmChunk> chunks;
     const int *dExtraFace = nullptr, *dCellSlot = nullptr;
@@ -869,6 +926,33 @@ extern "C" int gpupcg_mesh_create(gpupcg_mesh* out, int device, int nCells, int 
 {
     if (!out || nCells < 0 || nFaces < nInternalFaces || !owner || (nInternalFaces > 0 && !neighbour)) return GPUPCG_ERR_ARG;
     *out = nullptr;
+    if (!Sf || !magSf || !Cf || !C || !V || !deltaCoeffs || (nInternalFaces > 0 && !weights) || nPatches < 0 ||
+        (nPatches > 0 && (!patchStart || !patchSize || !patchType)))
+    {
+        g_meshErr = "gpupcg_mesh_create: NULL geometry / patch table";
+        return GPUPCG_ERR_ARG;
+    }
+    for (int p = 0; p < nPatches; p++)
+    {
+        if (patchSize[p] < 0 || patchStart[p] < nInternalFaces || (long long)patchStart[p] + patchSize[p] > nFaces)
+        {
+            g_meshErr = "gpupcg_mesh_create: patch " + std::to_string(p) + " lies outside the boundary faces [nInternalFaces, nFaces)";
+            return GPUPCG_ERR_ARG;
+        }
+        if (patchType[p] < 0 || patchType[p] > 4)
+        {
+            // anything else (processor, cyclic, solidTraction, ...) would silently get tractionDisplacement coefficients
+            g_meshErr = "gpupcg_mesh_create: patch " + std::to_string(p) + " has patchType " + std::to_string(patchType[p]) +
+                        " (supported: 0 tractionDisplacement, 1 fixedDisplacement, 2 symmetryDisplacement, 3 symmetryPlane, 4 empty)";
+            return GPUPCG_ERR_UNSUPPORTED;
+        }
+    }
+    for (int f = 0; f < nFaces; f++)
+        if (owner[f] < 0 || owner[f] >= nCells || (f < nInternalFaces && (neighbour[f] < 0 || neighbour[f] >= nCells)))
+        {
+            g_meshErr = "gpupcg_mesh_create: owner/neighbour label out of range at face " + std::to_string(f);
+            return GPUPCG_ERR_ARG;
+        }
     int nDev = 0;
     if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0 || device >= nDev)
     {
@@ -1043,14 +1127,15 @@ extern "C" int gpupcg_assemble_D(gpupcg_mesh m, const double* mu, const double* 
             k_asm_faces<<<agrid(m, K.nOwn + K.nExtra), ATPB, 0, cs>>>(M, K, m->dExtraFace, m->dMu, m->dLambda, m->dD, m->dGradD, m->dGradDf,
                                                                       limitCoeff, m->dUpper, lup, m->dGms, fluxE, fluxC);
             if (overlap) { MCK(cudaEventRecord(m->evFaces[ci & 1], cs)); }
-            k_asm_cells<<<agrid(m, K.c1 - K.c0), ATPB, 0, cs>>>(M, K, m->dCellSlot, m->dRho, g[0], g[1], g[2], lup, m->dUpper, fluxE,
-                                                                fluxC, m->dDiag, m->dSource);
+            k_asm_cells<<<agrid(m, K.c1 - K.c0), ATPB, 0, cs>>>(M, K, AsmCtl{}, nullptr, nullptr, m->dCellSlot, m->dRho, g[0], g[1], g[2],
+                                                                lup, m->dUpper, fluxE, fluxC, m->dDiag, m->dSource);
             ci++;
         }
         if (overlap) { MCK(cudaEventRecord(m->evJoin, m->stream2)); MCK(cudaStreamWaitEvent(s, m->evJoin, 0)); }
         if (nBF > 0)
-            k_asm_patches<<<agrid(m, nBF), ATPB, 0, s>>>(M, m->dMu, m->dLambda, m->dD, m->dGradD, m->dGradDf, m->dGms, m->dTraction,
-                                                         m->dPressure, m->dFixed, m->dIC, m->dBC, m->dPatchGrad);
+            k_asm_patches<<<agrid(m, nBF), ATPB, 0, s>>>(M, AsmCtl{}, nullptr, nullptr, nullptr, m->dMu, m->dLambda, m->dD, m->dGradD,
+                                                         m->dGradDf, m->dGms, m->dTraction, m->dPressure, m->dFixed, m->dIC, m->dBC,
+                                                         m->dPatchGrad);
     }
     MCK(cudaEventRecord(m->ev1, s));
     MCK(cudaGetLastError());
@@ -1222,3 +1307,356 @@ extern "C" int gpupcg_mesh_fetch(gpupcg_mesh m, int which, double* out)
     MCK(cudaStreamSynchronize(m->stream));
     return GPUPCG_OK;
 }
+
+// ====================================================================================================================
+// Round 2: the whole outer loop of evolve() on resident fields (no per-iteration PCIe traffic)
+// ====================================================================================================================
+namespace
+{
+struct FieldRef { double** p; size_t n; bool* have; };
+
+FieldRef field_ref(gpupcg_mesh m, int id)
+{
+    const MeshDev& M = m->M;
+    const size_t nC = (size_t)M.nCells, nF = (size_t)M.nFaces, nIF = (size_t)M.nIF, nBF = nF - nIF, nP = (size_t)M.nPoints;
+    switch (id)
+    {
+        case GPUPCG_F_MU: return {&m->dMu, nC, nullptr};
+        case GPUPCG_F_LAMBDA: return {&m->dLambda, nC, nullptr};
+        case GPUPCG_F_RHO: return {&m->dRho, nC, nullptr};
+        case GPUPCG_F_D: return {&m->dD, 3*nC, nullptr};
+        case GPUPCG_F_DOLD: return {&m->dDold, 3*nC, &m->haveDold};
+        case GPUPCG_F_DOLDOLD: return {&m->dDoldold, 3*nC, &m->haveDoldold};
+        case GPUPCG_F_GRADD: return {&m->dGradD, 9*nC, &m->haveGradD};
+        case GPUPCG_F_GRADDF: return {&m->dGradDf, 9*nF, &m->haveGradDf};
+        case GPUPCG_F_TRACTION: return {&m->dTraction, 3*nBF, nullptr};
+        case GPUPCG_F_PRESSURE: return {&m->dPressure, nBF, nullptr};
+        case GPUPCG_F_FIXEDVALUE: return {&m->dFixed, 3*nBF, nullptr};
+        case GPUPCG_F_THREEK: return {&m->dThreeK, nC, &m->haveThermal};
+        case GPUPCG_F_ALPHA: return {&m->dAlpha, nC, nullptr};
+        case GPUPCG_F_DT: return {&m->dDT, nC, nullptr};
+        case GPUPCG_F_DTB: return {&m->dDTb, nBF, nullptr};
+        case GPUPCG_F_POINTD: return {&m->dPointD, 3*nP, nullptr};
+        case GPUPCG_F_DB: return {&m->dDb, 3*nBF, &m->haveDb};
+        case GPUPCG_F_GRADDB: return {&m->dGradDb, 9*nBF, nullptr};
+        case GPUPCG_F_U: return {&m->dU, 3*nC, nullptr};
+        case GPUPCG_F_EPSILON: return {&m->dEps, 6*nC, nullptr};
+        case GPUPCG_F_SIGMA: return {&m->dSig, 6*nC, nullptr};
+        case GPUPCG_F_UPPER: return {&m->dUpper, nIF, nullptr};
+        case GPUPCG_F_DIAG: return {&m->dDiag, nC, nullptr};
+        case GPUPCG_F_SOURCE: return {&m->dSource, 3*nC, nullptr};
+        case GPUPCG_F_INTERNALCOEFFS: return {&m->dIC, 3*nBF, nullptr};
+        case GPUPCG_F_BOUNDARYCOEFFS: return {&m->dBC, 3*nBF, nullptr};
+        case GPUPCG_F_PATCHGRADIENT: return {&m->dPatchGrad, 3*nBF, nullptr};
+        case GPUPCG_F_DPREV: return {&m->dDprev, 3*nC, nullptr};
+        case GPUPCG_F_DBPREV: return {&m->dDbPrev, 3*nBF, nullptr};
+        default: return {nullptr, 0, nullptr};
+    }
+}
+
+// a field that is allocated on first use (zero-filled)
+int ensure(gpupcg_mesh m, double*& p, size_t n)
+{
+    if (p) return GPUPCG_OK;
+    MCK(alloc(m, p, n));
+    MCK(cudaMemsetAsync(p, 0, sizeof(double)*std::max<size_t>(n, 1), m->stream));
+    return GPUPCG_OK;
+}
+
+AsmCtl make_ctl(const gpupcg_eqn_controls* c)
+{
+    AsmCtl T{};
+    if (!c) return T;
+    T.d2dt2 = c->d2dt2Scheme; T.ddt = c->ddtScheme; T.K = c->K; T.damping = c->K > A_SMALL;
+    T.nonLinear = c->nonLinear != 0; T.thermal = c->thermal != 0;
+    if (T.d2dt2 == 1)
+    {
+        // host-side scalars of [EXT] EulerD2dt2Scheme::fvmD2dt2, IEEE double, in its order
+        T.coefft = (c->deltaT + c->deltaT0)/(2*c->deltaT);
+        T.coefft00 = (c->deltaT + c->deltaT0)/(2*c->deltaT0);
+        const double s = c->deltaT + c->deltaT0;
+        T.rDeltaT2 = 4.0/(s*s);
+    }
+    if (T.ddt == 1) T.rDeltaT = 1.0/c->deltaT;
+    return T;
+}
+} // namespace
+
+extern "C" int gpupcg_mesh_field_size(gpupcg_mesh m, int id, long long* n)
+{
+    if (!m || !n) return GPUPCG_ERR_ARG;
+    FieldRef r = field_ref(m, id);
+    if (!r.p) { m->err = "gpupcg_mesh_field_size: unknown field id"; return GPUPCG_ERR_ARG; }
+    *n = (long long)r.n;
+    return GPUPCG_OK;
+}
+
+extern "C" int gpupcg_mesh_set_field(gpupcg_mesh m, int id, const double* host)
+{
+    if (!m || !host) return GPUPCG_ERR_ARG;
+    FieldRef r = field_ref(m, id);
+    if (!r.p) { m->err = "gpupcg_mesh_set_field: unknown field id"; return GPUPCG_ERR_ARG; }
+    if (id == GPUPCG_F_POINTD && !m->M.points) { m->err = "gpupcg_mesh_set_field: gpupcg_mesh_set_points first"; return GPUPCG_ERR_STATE; }
+    MCK(cudaSetDevice(m->device));
+    int rc = ensure(m, *r.p, r.n); if (rc) return rc;
+    if (r.n) MCK(cudaMemcpyAsync(*r.p, host, sizeof(double)*r.n, cudaMemcpyHostToDevice, m->stream));
+    MCK(cudaStreamSynchronize(m->stream));
+    if (r.have) *r.have = true;
+    return GPUPCG_OK;
+}
+
+extern "C" int gpupcg_mesh_get_field(gpupcg_mesh m, int id, double* host)
+{
+    if (!m || !host) return GPUPCG_ERR_ARG;
+    FieldRef r = field_ref(m, id);
+    if (!r.p) { m->err = "gpupcg_mesh_get_field: unknown field id"; return GPUPCG_ERR_ARG; }
+    if (!*r.p) { m->err = "gpupcg_mesh_get_field: the device does not hold that field yet"; return GPUPCG_ERR_STATE; }
+    MCK(cudaSetDevice(m->device));
+    if (r.n) MCK(cudaMemcpyAsync(host, *r.p, sizeof(double)*r.n, cudaMemcpyDeviceToHost, m->stream));
+    MCK(cudaStreamSynchronize(m->stream));
+    return GPUPCG_OK;
+}
+
+// leastSquaresVolPointInterpolation data of the mesh: what the reference's volToPoint_ object holds
+// (pointCells / pointBndFaces stencils, origins(), invLsMatrices(), mirror planes), flattened.
+extern "C" int gpupcg_mesh_set_lsq(gpupcg_mesh m, const int* pointStart, const int* entry, const double* invLs,
+                                   const double* origin, const unsigned char* mirror)
+{
+    if (!m || !pointStart || !entry || !invLs || !origin || !mirror) return GPUPCG_ERR_ARG;
+    if (!m->M.points) { m->err = "gpupcg_mesh_set_lsq: gpupcg_mesh_set_points has not been called"; return GPUPCG_ERR_STATE; }
+    const int nP = m->M.nPoints, nC = m->M.nCells, nBF = m->M.nFaces - m->M.nIF;
+    const int rows = pointStart[nP];
+    for (int p = 0; p < nP; p++)
+        if (pointStart[p + 1] < pointStart[p] || (mirror[p] && ((pointStart[p + 1] - pointStart[p]) & 1)))
+        { m->err = "gpupcg_mesh_set_lsq: pointStart not ascending / odd row count at a mirrored point"; return GPUPCG_ERR_ARG; }
+    for (int r = 0; r < rows; r++)
+        if (entry[r] >= nC || -1 - entry[r] >= nBF) { m->err = "gpupcg_mesh_set_lsq: stencil entry out of range"; return GPUPCG_ERR_ARG; }
+    MCK(cudaSetDevice(m->device));
+    LsqDev& L = m->lsq;
+    L.nPoints = nP;
+    MCK(up(m, L.start, pointStart, (size_t)nP + 1)); MCK(up(m, L.entry, entry, (size_t)rows));
+    MCK(up(m, L.inv, invLs, 3*(size_t)rows)); MCK(up(m, L.origin, origin, 3*(size_t)nP));
+    MCK(up(m, L.mirror, mirror, (size_t)nP));
+    MCK(cudaStreamSynchronize(m->stream));
+    return GPUPCG_OK;
+}
+
+// runTime++ : D.storeOldTimes()  ->  D.oldTime().oldTime() = D.oldTime(); D.oldTime() = D
+extern "C" int gpupcg_mesh_new_time_step(gpupcg_mesh m)
+{
+    if (!m) return GPUPCG_ERR_ARG;
+    MCK(cudaSetDevice(m->device));
+    const size_t n = 3*(size_t)m->M.nCells;
+    int rc = ensure(m, m->dDoldold, n); if (rc) return rc;
+    MCK(cudaMemcpyAsync(m->dDoldold, m->dDold, sizeof(double)*n, cudaMemcpyDeviceToDevice, m->stream));
+    MCK(cudaMemcpyAsync(m->dDold, m->dD, sizeof(double)*n, cudaMemcpyDeviceToDevice, m->stream));
+    m->haveDold = m->haveDoldold = true;
+    MCK(cudaStreamSynchronize(m->stream));
+    return GPUPCG_OK;
+}
+
+static int check_ctl(gpupcg_mesh m, const gpupcg_eqn_controls* c)
+{
+    if (!c) return GPUPCG_OK;
+    if (c->d2dt2Scheme < 0 || c->d2dt2Scheme > 1 || c->ddtScheme < 0 || c->ddtScheme > 1)
+    { m->err = "unsupported d2dt2 / ddt scheme (0 steadyState, 1 Euler)"; return GPUPCG_ERR_UNSUPPORTED; }
+    if ((c->d2dt2Scheme == 1 || c->ddtScheme == 1) && !(c->deltaT > 0.0 && c->deltaT0 > 0.0))
+    { m->err = "Euler time scheme needs deltaT > 0 and deltaT0 > 0"; return GPUPCG_ERR_ARG; }
+    if (c->thermal && !m->haveThermal)
+    { m->err = "thermal stress requested but threeK / alpha / DT / DTb have not been set (gpupcg_mesh_set_field)"; return GPUPCG_ERR_STATE; }
+    return GPUPCG_OK;
+}
+
+// the D equation from the RESIDENT fields, every branch of unsTotalLagrangianStress.C:846-890; stream = m->stream
+static int assemble_resident(gpupcg_mesh m, const gpupcg_eqn_controls* c, const double* g)
+{
+    const MeshDev& M = m->M;
+    const int nC = M.nCells, nF = M.nFaces, nBF = nF - M.nIF;
+    int rc = check_ctl(m, c); if (rc) return rc;
+    if (!m->haveGradD || !m->haveGradDf) { m->err = "no grad(D) / gradDf on the device yet"; return GPUPCG_ERR_STATE; }
+    const AsmCtl T = make_ctl(c);
+    cudaStream_t s = m->stream;
+    if (T.d2dt2 == 1 || (T.damping && T.ddt == 1))
+    {
+        rc = ensure(m, m->dDoldold, 3*(size_t)nC); if (rc) return rc;
+    }
+    if (T.thermal) { rc = ensure(m, m->dAlpha, nC); if (rc) return rc; rc = ensure(m, m->dDT, nC); if (rc) return rc; rc = ensure(m, m->dDTb, nBF); if (rc) return rc; }
+    const double limitCoeff = c ? c->limitCoeff : 1.0;
+    if (m->chunks.size() != 1) { m->err = "resident assembly needs the one-chunk layout (unset GPUPCG_ASM_CHUNK_CELLS)"; return GPUPCG_ERR_UNSUPPORTED; }
+    const AsmChunk& K = m->chunks[0];
+    double *fluxE = m->dFluxE, *fluxC = m->dFluxE + 3*(size_t)m->ringSlots, *lup = m->dFluxE + 6*(size_t)m->ringSlots;
+    k_asm_faces<<<agrid(m, K.nOwn + K.nExtra), ATPB, 0, s>>>(M, K, m->dExtraFace, m->dMu, m->dLambda, m->dD, m->dGradD, m->dGradDf,
+                                                             limitCoeff, m->dUpper, lup, m->dGms, fluxE, fluxC);
+    k_asm_cells<<<agrid(m, nC), ATPB, 0, s>>>(M, K, T, m->dDold, m->dDoldold, m->dCellSlot, m->dRho, g[0], g[1], g[2], lup, m->dUpper,
+                                              fluxE, fluxC, m->dDiag, m->dSource);
+    if (T.nonLinear || T.thermal)
+    {
+        if (T.nonLinear) { rc = ensure(m, m->dFluxX, 3*(size_t)nF); if (rc) return rc; rc = ensure(m, m->dFluxY, 3*(size_t)nF); if (rc) return rc; }
+        if (T.thermal) { rc = ensure(m, m->dFluxT, 3*(size_t)nF); if (rc) return rc; }
+        k_asm_faces_extra<<<agrid(m, nF), ATPB, 0, s>>>(M, T, m->dMu, m->dLambda, m->dGradDf, m->dThreeK, m->dAlpha, m->dDT, m->dDTb,
+                                                        m->dFluxX, m->dFluxY, m->dFluxT);
+        k_asm_cells_extra<<<agrid(m, nC), ATPB, 0, s>>>(M, T, m->dFluxX, m->dFluxY, m->dFluxT, m->dSource);
+    }
+    if (nBF > 0)
+        k_asm_patches<<<agrid(m, nBF), ATPB, 0, s>>>(M, T, m->dThreeK, m->dAlpha, m->dDTb, m->dMu, m->dLambda, m->dD, m->dGradD, m->dGradDf,
+                                                     m->dGms, m->dTraction, m->dPressure, m->dFixed, m->dIC, m->dBC, m->dPatchGrad);
+    MCK(cudaGetLastError());
+    m->assembled = true;
+    return GPUPCG_OK;
+}
+
+extern "C" int gpupcg_assemble_D_resident(gpupcg_mesh m, const gpupcg_eqn_controls* ctl, const double* g)
+{
+    if (!m || !g) return GPUPCG_ERR_ARG;
+    MCK(cudaSetDevice(m->device));
+    int rc = assemble_resident(m, ctl, g); if (rc) return rc;
+    MCK(cudaStreamSynchronize(m->stream));
+    return GPUPCG_OK;
+}
+
+// D.correctBoundaryConditions() on the resident D: boundary values -> Db (slots of empty faces untouched)
+static int evaluate_resident(gpupcg_mesh m)
+{
+    const MeshDev& M = m->M;
+    const int nBF = M.nFaces - M.nIF;
+    int rc = ensure(m, m->dDb, 3*(size_t)nBF); if (rc) return rc;
+    if (nBF > 0) k_patch_evaluate<<<agrid(m, nBF), ATPB, 0, m->stream>>>(M, m->dD, m->dGradD, m->dFixed, m->dPatchGrad, m->dDb);
+    MCK(cudaGetLastError());
+    m->haveDb = true;
+    return GPUPCG_OK;
+}
+
+extern "C" int gpupcg_patch_evaluate(gpupcg_mesh m)
+{
+    if (!m) return GPUPCG_ERR_ARG;
+    MCK(cudaSetDevice(m->device));
+    int rc = ensure(m, m->dGradD, 9*(size_t)m->M.nCells); if (rc) return rc;
+    rc = evaluate_resident(m); if (rc) return rc;
+    MCK(cudaStreamSynchronize(m->stream));
+    return GPUPCG_OK;
+}
+
+// volToPoint_.interpolate(D_, pointD_) on the resident D and D.boundaryField()   (unsTotalLagrangianStress.C:924)
+static int vol_to_point_resident(gpupcg_mesh m)
+{
+    if (!m->lsq.start) { m->err = "gpupcg_mesh_set_lsq has not been called"; return GPUPCG_ERR_STATE; }
+    if (!m->haveDb) { m->err = "no boundary values of D on the device (gpupcg_patch_evaluate / set_field DB first)"; return GPUPCG_ERR_STATE; }
+    k_lsq_interpolate<<<agrid(m, m->M.nPoints), ATPB, 0, m->stream>>>(m->lsq, m->M.points, m->dD, m->dDb, m->dPointD);
+    MCK(cudaGetLastError());
+    return GPUPCG_OK;
+}
+
+extern "C" int gpupcg_vol_to_point(gpupcg_mesh m, int reps, double* kernel_ms)
+{
+    if (!m) return GPUPCG_ERR_ARG;
+    MCK(cudaSetDevice(m->device));
+    if (reps < 1) reps = 1;
+    MCK(cudaEventRecord(m->ev0, m->stream));
+    for (int r = 0; r < reps; r++) { int rc = vol_to_point_resident(m); if (rc) return rc; }
+    MCK(cudaEventRecord(m->ev1, m->stream));
+    MCK(cudaStreamSynchronize(m->stream));
+    if (kernel_ms) { float ms = 0.f; cudaEventElapsedTime(&ms, m->ev0, m->ev1); *kernel_ms = ms/reps; }
+    return GPUPCG_OK;
+}
+
+static int gradients_resident(gpupcg_mesh m, double limitCoeff)
+{
+    const MeshDev& M = m->M;
+    const int nC = M.nCells, nF = M.nFaces, nBF = nF - M.nIF;
+    cudaStream_t s = m->stream;
+    MCK(cudaMemcpyAsync(m->dGradOld, m->dGradD, sizeof(double)*9*(size_t)nC, cudaMemcpyDeviceToDevice, s));
+    k_grad_cells<<<std::max(1, std::min((nC + GTPB - 1)/GTPB, m->numSMs*32)), GTPB, 0, s>>>(M, m->dPointD, m->dGradD);
+    if (nBF > 0)
+        k_grad_patches<<<agrid(m, nBF), ATPB, 0, s>>>(M, m->dD, m->dPointD, m->dGradOld, m->dFixed, m->dPatchGrad, m->dGradDb);
+    k_fgrad_faces<<<agrid(m, nF), ATPB, 0, s>>>(M, m->dD, m->dPointD, m->dGradD, m->dFixed, m->dPatchGrad, limitCoeff, m->dGradDf);
+    MCK(cudaGetLastError());
+    m->haveGradD = m->haveGradDf = true;
+    return GPUPCG_OK;
+}
+
+extern "C" int gpupcg_gradients_resident(gpupcg_mesh m, double limitCoeff)
+{
+    if (!m) return GPUPCG_ERR_ARG;
+    if (!m->M.points) { m->err = "gpupcg_gradients_resident: gpupcg_mesh_set_points has not been called"; return GPUPCG_ERR_STATE; }
+    MCK(cudaSetDevice(m->device));
+    int rc = gradients_resident(m, limitCoeff); if (rc) return rc;
+    MCK(cudaStreamSynchronize(m->stream));
+    return GPUPCG_OK;
+}
+
+extern "C" int gpupcg_sigma_resident(gpupcg_mesh m, const gpupcg_eqn_controls* c)
+{
+    if (!m) return GPUPCG_ERR_ARG;
+    if (!m->haveGradD) { m->err = "gpupcg_sigma_resident: no grad(D) on the device"; return GPUPCG_ERR_STATE; }
+    MCK(cudaSetDevice(m->device));
+    int rc = check_ctl(m, c); if (rc) return rc;
+    const int nC = m->M.nCells;
+    const AsmCtl T = make_ctl(c);
+    cudaStream_t s = m->stream;
+    rc = ensure(m, m->dU, 3*(size_t)nC); if (rc) return rc;
+    // U_ = fvc::ddt(D_)   (:973)
+    k_ddt<<<agrid(m, 3*(long long)nC), ATPB, 0, s>>>(3*(long long)nC, T.ddt, T.rDeltaT, m->dD, m->dDold, m->dU);
+    // nonLinear here is the dictionary switch itself (:979), not `nonLinear && !enforceLinear`: the caller passes it in c->nonLinear
+    k_sigma_ex<<<agrid(m, nC), ATPB, 0, s>>>(nC, T.nonLinear, T.thermal, m->dMu, m->dLambda, m->dGradD, m->dThreeK, m->dAlpha, m->dDT,
+                                             m->dEps, m->dSig);
+    MCK(cudaGetLastError());
+    MCK(cudaStreamSynchronize(s));
+    return GPUPCG_OK;
+}
+
+// ---- internal: the stages of one outer iteration, driven by gpupcg_evolve_D (gpupcg_vec.cuh) -------------------------
+extern "C" int gpupcgi_mesh_bind_stream(gpupcg_mesh m, void* stream, void** previous)
+{
+    if (!m) return GPUPCG_ERR_ARG;
+    if (previous) *previous = (void*)m->stream;
+    m->stream = (cudaStream_t)stream;
+    return GPUPCG_OK;
+}
+
+// D_.storePrevIter() (:844) incl. the boundary field, then the assembly
+extern "C" int gpupcgi_mesh_outer_begin(gpupcg_mesh m, const gpupcg_eqn_controls* c, const double* g)
+{
+    const MeshDev& M = m->M;
+    const size_t n = 3*(size_t)M.nCells, nb = 3*(size_t)(M.nFaces - M.nIF);
+    int rc = ensure(m, m->dDb, nb); if (rc) return rc;
+    rc = ensure(m, m->dDbPrev, nb); if (rc) return rc;
+    if (!m->haveDb) { rc = evaluate_resident(m); if (rc) return rc; }
+    MCK(cudaMemcpyAsync(m->dDprev, m->dD, sizeof(double)*n, cudaMemcpyDeviceToDevice, m->stream));
+    if (nb) MCK(cudaMemcpyAsync(m->dDbPrev, m->dDb, sizeof(double)*nb, cudaMemcpyDeviceToDevice, m->stream));
+    return assemble_resident(m, c, g);
+}
+
+// after DEqn.solve(): correctBoundaryConditions, D.relax() (:910), volToPoint (:924), grad / fGrad (:925-926), det bounds
+// (:929-937), residual() (:949).  hostScal (pinned, 4 doubles) <- {residual, maxDD, minDet, maxDet}, asynchronously.
+extern "C" int gpupcgi_mesh_outer_end(gpupcg_mesh m, const gpupcg_eqn_controls* c, double alpha, int doRelax, int detBounds,
+                                      double* hostScal)
+{
+    const MeshDev& M = m->M;
+    const int nC = M.nCells;
+    const long long nb3 = 3*(long long)(M.nFaces - M.nIF);
+    cudaStream_t s = m->stream;
+    int rc = evaluate_resident(m); if (rc) return rc;
+    if (doRelax && nb3 > 0) k_relax_boundary<<<agrid(m, nb3), ATPB, 0, s>>>(nb3, alpha, m->dDb, m->dDbPrev);
+    const int nb = std::min(1024, agrid(m, nC));
+    k_relax_maxdd<<<nb, ATPB, 0, s>>>(nC, alpha, doRelax, m->dD, m->dDprev, m->dDold, m->dRed);
+    k_residual<<<nb, ATPB, 0, s>>>(nC, nb, m->dD, m->dDprev, m->dRed, m->dRed + 1024);
+    MCK(cudaGetLastError());
+    rc = vol_to_point_resident(m); if (rc) return rc;
+    rc = gradients_resident(m, c ? c->limitCoeff : 1.0); if (rc) return rc;
+    double* out = m->dRed + 2048 - 8;       // the tail of the 2 x 1024 partials buffer is never reached (nb <= 1024 - 8 checked below)
+    if (nb > 1016) { m->err = "internal: partials buffer too small"; return GPUPCG_ERR_STATE; }
+    k_final_minmax<<<1, ATPB, 0, s>>>(nb, m->dRed + 1024, nullptr, out);            // out[0] = residual
+    k_final_minmax<<<1, ATPB, 0, s>>>(nb, m->dRed, nullptr, out + 2);               // out[2] = maxDD
+    if (detBounds)
+    {
+        const int nbd = std::min(1016, agrid(m, M.nFaces));
+        k_det_minmax<<<nbd, ATPB, 0, s>>>(M, m->dGradDf, m->dRed, m->dRed + 1024);
+        k_final_minmax<<<1, ATPB, 0, s>>>(nbd, m->dRed + 1024, m->dRed, out + 4);   // out[4] = maxDet, out[5] = minDet
+    }
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpyAsync(hostScal, out, sizeof(double)*6, cudaMemcpyDeviceToHost, s));
+    return GPUPCG_OK;
+}
+
+extern "C" int gpupcgi_mesh_D(gpupcg_mesh m, double** D) { if (!m || !D) return GPUPCG_ERR_ARG; *D = m->dD; return GPUPCG_OK; }
+extern "C" void gpupcgi_mesh_set_error(gpupcg_mesh m, const char* msg) { if (m) m->err = msg; }

@@ -580,3 +580,120 @@ extern "C" int gpupcg_solve_assembled_D(gpupcg_handle h, gpupcg_mesh m, double* 
     if (perf) for (int k = 0; k < 3; k++) { perf[k].h2d_ms = msIn; perf[k].d2h_ms = msOut; }
     return GPUPCG_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// unsTotalLagrangianStress::evolve() (unsTotalLagrangianStress.C:769-1009) with every field resident on the device:
+// per outer iteration storePrevIter -> assembly (all branches) -> DEqn.solve() (addBoundaryDiag / addBoundarySource +
+// the batched PCG over the valid components) -> correctBoundaryConditions -> D.relax() -> least-squares vol->point ->
+// grad / fGrad -> det(I + gradDf) bounds -> residual().  The host sees 6 doubles per outer iteration (the convergence
+// logic of :949-971 needs them) and nothing else.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int NB>
+static int evolve_impl(gpupcg_handle h, gpupcg_mesh m, const gpupcg_evolve_controls* ec, gpupcg_evolve_result* res,
+                       double* residualHistory, int* pcgIterations, int historyCap)
+{
+    gpupcg_mesh_view v;
+    const HostPlan& P = h->plan;
+    int rc = vec_prepare<NB>(h); if (rc) return rc;
+    cudaStream_t s = h->stream;
+    double* hostScal = nullptr;
+    CK(cudaMallocHost((void**)&hostScal, 8*sizeof(double)));
+    void* prevStream = nullptr;
+    gpupcgi_mesh_bind_stream(m, (void*)s, &prevStream);
+    struct Restore { gpupcg_mesh m; void* st; double* hs; ~Restore() { gpupcgi_mesh_bind_stream(m, st, nullptr); cudaFreeHost(hs); } } restore{m, prevStream, hostScal};
+    double* dD = nullptr;
+    gpupcgi_mesh_D(m, &dD);
+    int cm[3] = {0, 1, 2}, nv = 0;
+    for (int k = 0; k < 3; k++) if (ec->validCmpt[k]) cm[nv++] = k;
+    gpupcg_eqn_controls eq = ec->eqn;
+    const bool nonLinear = ec->eqn.nonLinear != 0;
+    bool enforceLinear = false, haveView = false;
+    int iCorr = 0, totalIts = 0;
+    double r = 1.0, maxRes = 0.0, initialResidual = 0.0, lastInit = 0.0;
+    float msA = 0.f, msS = 0.f, msE = 0.f, t = 0.f;
+    cudaEvent_t e0 = h->ev[0], e1 = h->ev[1], e2 = h->ev[2], e3 = h->ev[3];
+    std::vector<gpupcg_perf> perf(NB);
+    while (true)
+    {
+        eq.nonLinear = (nonLinear && !enforceLinear) ? 1 : 0;
+        CK(cudaEventRecord(e0, s));
+        rc = gpupcgi_mesh_outer_begin(m, &eq, ec->g);
+        if (rc) { h->err = std::string("gpupcg_evolve_D: ") + gpupcg_mesh_last_error(m); return rc; }
+        if (!haveView)      // the device pointers of the assembled equation do not change between outer iterations
+        {
+            rc = gpupcgi_mesh_view(m, &v);
+            if (rc) { h->err = std::string("gpupcg_evolve_D: ") + gpupcg_mesh_last_error(m); return rc; }
+            if (v.device != h->device || v.nCells != P.nCells || v.nIF != P.nFaces)
+            {
+                h->err = "gpupcg_evolve_D: the solver handle was not created for this mesh (device / cells / internal faces differ)";
+                return GPUPCG_ERR_ARG;
+            }
+            haveView = true;
+        }
+        // fvMatrix<vector>::solve: addBoundaryDiag / addBoundarySource per valid component, psi.component(cmpt)
+        h->launches++;
+        k_add_boundary_v<NB><<<grid_for(P.nCells, h->streamGrid), TPB, 0, s>>>(P.nCells, v.cellBfStart, v.cellBf, v.diag, v.source, v.ic, v.bc,
+                                                                               dD, cm[0], cm[1], cm[2], h->vStageD, h->vStageB, h->vStageX);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e1, s));
+        rc = vec_set_matrix_device<NB>(h, h->vStageD, v.upper, nullptr); if (rc) return rc;
+        rc = vec_solve_device<NB>(h, h->vStageX, h->vStageB, ec->tolerance, ec->relTol, ec->minIter, ec->maxIter, perf.data(), nullptr, 0);
+        if (rc) return rc;
+        h->launches++;
+        k_unpack_cmpts<NB><<<grid_for(P.nCells, h->streamGrid), TPB, 0, s>>>(P.nCells, h->vStageX, cm[0], cm[1], cm[2], dD);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e2, s));
+        rc = gpupcgi_mesh_outer_end(m, &eq, ec->relaxD, ec->doRelax, eq.nonLinear, hostScal);
+        if (rc) { h->err = std::string("gpupcg_evolve_D: ") + gpupcg_mesh_last_error(m); return rc; }
+        CK(cudaEventRecord(e3, s));
+        CK(cudaStreamSynchronize(s));
+        cudaEventElapsedTime(&t, e0, e1); msA += t;
+        cudaEventElapsedTime(&t, e1, e2); msS += t;
+        cudaEventElapsedTime(&t, e2, e3); msE += t;
+        // keep the component with the largest initial residual, singular ones ignored (fvMatrixSolve.C)
+        const gpupcg_perf* worst = &perf[0];
+        for (int k = 1; k < NB; k++)
+            if (perf[k].initialResidual > worst->initialResidual && !perf[k].singular) worst = &perf[k];
+        for (int k = 0; k < NB; k++) totalIts += perf[k].nIterations;
+        if (iCorr == 0) initialResidual = worst->initialResidual;
+        lastInit = worst->initialResidual;
+        if (eq.nonLinear && (hostScal[5] < 0.01 || hostScal[4] > 100)) enforceLinear = true;       // :939-945
+        r = hostScal[0];
+        if (r > maxRes) maxRes = r;
+        double cur = maxRes*ec->relConvergenceTolerance;
+        if (cur < ec->convergenceTolerance) cur = ec->convergenceTolerance;
+        if (residualHistory && iCorr < historyCap) residualHistory[iCorr] = r;
+        if (pcgIterations && iCorr < historyCap) for (int k = 0; k < NB; k++) pcgIterations[3*iCorr + k] = perf[k].nIterations;
+        if (!(r > cur)) break;
+        if (!(++iCorr < ec->nCorrectors)) break;
+    }
+    if (res)
+    {
+        res->nOuterIterations = iCorr; res->totalPcgIterations = totalIts; res->enforceLinear = enforceLinear ? 1 : 0;
+        res->converged = (nonLinear && enforceLinear) ? 0 : 1;
+        res->initialResidual = initialResidual; res->lastSolverInitialResidual = lastInit; res->maxRes = maxRes; res->res = r;
+        res->assemble_ms = msA; res->solve_ms = msS; res->update_ms = msE;
+    }
+    return GPUPCG_OK;
+}
+
+extern "C" int gpupcg_evolve_D(gpupcg_handle h, gpupcg_mesh m, const gpupcg_evolve_controls* ec, gpupcg_evolve_result* res,
+                               double* residualHistory, int* pcgIterations, int historyCap)
+{
+    if (!h || !m || !ec) return GPUPCG_ERR_ARG;
+    gpupcg_mesh_view v;
+    double* dD = nullptr;
+    if (gpupcgi_mesh_D(m, &dD) || !dD) return GPUPCG_ERR_ARG;
+    const HostPlan& P = h->plan;
+    int nv = 0;
+    for (int k = 0; k < 3; k++) nv += ec->validCmpt[k] ? 1 : 0;
+    if (nv < 2) { h->err = "gpupcg_evolve_D: at least two solution directions are needed (validCmpt)"; return GPUPCG_ERR_UNSUPPORTED; }
+    if (h->nPatches > 0) { h->err = "gpupcg_evolve_D: coupled (processor) patches are not assembled on the device yet"; return GPUPCG_ERR_UNSUPPORTED; }
+    if (ec->nCorrectors < 1) { h->err = "gpupcg_evolve_D: nCorrectors < 1"; return GPUPCG_ERR_ARG; }
+    CK(cudaSetDevice(h->device));
+    // the mesh must be the one the solver handle was built for: checked against the view after the first assembly
+    (void)v; (void)P;
+    return VEC_DISPATCH(nv, evolve_impl<2>(h, m, ec, res, residualHistory, pcgIterations, historyCap),
+                            evolve_impl<3>(h, m, ec, res, residualHistory, pcgIterations, historyCap));
+}

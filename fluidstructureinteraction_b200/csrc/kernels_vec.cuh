@@ -913,6 +913,49 @@ __global__ void __launch_bounds__(TPB) k_add_boundary3(int nCells, const int* __
     }
 }
 
+// the same for the NB valid components of a 2-D (empty) or 3-D case: component k of the solve is direction cm[k] of D.
+// Also packs x[c][k] = D[c][cm[k]] (psi.component(cmpt), fvMatrixSolve.C)
+template <int NB>
+__global__ void __launch_bounds__(TPB) k_add_boundary_v(int nCells, const int* __restrict__ cellBfStart, const int* __restrict__ cellBf,
+                                                        const double* __restrict__ diag, const double* __restrict__ source,
+                                                        const double* __restrict__ ic, const double* __restrict__ bc,
+                                                        const double* __restrict__ D, int cm0, int cm1, int cm2,
+                                                        double* __restrict__ diagC, double* __restrict__ bC, double* __restrict__ xC)
+{
+    const int cm[3] = {cm0, cm1, cm2};
+    for (int c = blockIdx.x*TPB + threadIdx.x; c < nCells; c += gridDim.x*TPB)
+    {
+        const double d0 = diag[c];
+        double d[NB], b[NB];
+#pragma unroll
+        for (int k = 0; k < NB; k++) { d[k] = d0; b[k] = source[3*(size_t)c + cm[k]]; }
+        for (int q = cellBfStart[c]; q < cellBfStart[c + 1]; q++)
+        {
+            const size_t bf = (size_t)cellBf[q];
+#pragma unroll
+            for (int k = 0; k < NB; k++) { d[k] = __dadd_rn(d[k], ic[3*bf + cm[k]]); b[k] = __dadd_rn(b[k], bc[3*bf + cm[k]]); }
+        }
+#pragma unroll
+        for (int k = 0; k < NB; k++)
+        {
+            diagC[(size_t)NB*c + k] = d[k]; bC[(size_t)NB*c + k] = b[k];
+            if (xC) xC[(size_t)NB*c + k] = D[3*(size_t)c + cm[k]];
+        }
+    }
+}
+
+// psi.replace(cmpt, psiCmpt) for the solved components
+template <int NB>
+__global__ void __launch_bounds__(TPB) k_unpack_cmpts(int nCells, const double* __restrict__ xC, int cm0, int cm1, int cm2, double* __restrict__ D)
+{
+    const int cm[3] = {cm0, cm1, cm2};
+    for (int c = blockIdx.x*TPB + threadIdx.x; c < nCells; c += gridDim.x*TPB)
+    {
+#pragma unroll
+        for (int k = 0; k < NB; k++) D[3*(size_t)c + cm[k]] = xC[(size_t)NB*c + k];
+    }
+}
+
 // raw face coefficients per row (shared by the components)
 __global__ void __launch_bounds__(TPB) k_tab_raw(int nRows, const int4* __restrict__ idx, const double* __restrict__ Uval,
                                                  double* __restrict__ F)

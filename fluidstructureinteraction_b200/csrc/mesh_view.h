@@ -12,3 +12,11 @@ struct gpupcg_mesh_view
 };
 
 extern "C" int gpupcgi_mesh_view(gpupcg_mesh m, gpupcg_mesh_view* v);
+
+// ---- the stages of one outer iteration of evolve() on the mesh side (assembly.cu), driven by gpupcg_evolve_D ----------
+extern "C" int gpupcgi_mesh_bind_stream(gpupcg_mesh m, void* stream, void** previous);
+extern "C" int gpupcgi_mesh_outer_begin(gpupcg_mesh m, const gpupcg_eqn_controls* c, const double* g);
+extern "C" int gpupcgi_mesh_outer_end(gpupcg_mesh m, const gpupcg_eqn_controls* c, double alpha, int doRelax, int detBounds,
+                                      double* hostScal6);
+extern "C" int gpupcgi_mesh_D(gpupcg_mesh m, double** D);
+extern "C" void gpupcgi_mesh_set_error(gpupcg_mesh m, const char* msg);

@@ -111,8 +111,9 @@ def hex_ldu(nx, ny, nz):
     return l, u
 
 
-def hex_box(nx, ny, nz, L=2.0, W=0.5, H=1.0):
-    """Full polyMesh of the cantilever box.  Patches: fixed (x=0), loaded (x=L), free (the four sides)."""
+def hex_box(nx, ny, nz, L=2.0, W=0.5, H=1.0, split_free=False):
+    """Full polyMesh of the cantilever box.  Patches: fixed (x=0), loaded (x=L), free (the four sides); with split_free
+    the four sides become `sides` (y = 0, y = W) and `frontAndBack` (z = 0, z = H: the empty patch of a 2-D case, nz = 1)."""
     npx, npy = nx + 1, ny + 1
     xs = np.linspace(0.0, L, nx + 1)
     ys = np.linspace(0.0, W, ny + 1)
@@ -174,7 +175,11 @@ def hex_box(nx, ny, nz, L=2.0, W=0.5, H=1.0):
     fc.append(cells); fq.append(np.stack([P(i, j, o), P(i, j + 1, o), P(i + 1, j + 1, o), P(i + 1, j, o)], 1))
     cells = c[ck == nz - 1]; i, j = ci[cells], cj[cells]; o = z0(cells.shape[0], dtype=np.int64) + nz
     fc.append(cells); fq.append(np.stack([P(i, j, o), P(i + 1, j, o), P(i + 1, j + 1, o), P(i, j + 1, o)], 1))
-    add_patch("free", "patch", np.concatenate(fc), np.concatenate(fq))
+    if split_free:
+        add_patch("sides", "patch", np.concatenate(fc[:2]), np.concatenate(fq[:2]))
+        add_patch("frontAndBack", "empty", np.concatenate(fc[2:]), np.concatenate(fq[2:]))
+    else:
+        add_patch("free", "patch", np.concatenate(fc), np.concatenate(fq))
 
     owner = np.concatenate(owners)
     quads = np.concatenate(faces)

@@ -266,6 +266,113 @@ int gpupcg_gradients(gpupcg_mesh m, const double* D, const double* pointD, const
                      const double* fixedValue, const double* patchGradient, double limitCoeff, int reps,
                      double* gradD, double* gradDb, double* gradDf, double* kernel_ms);
 
+/* ---- the whole outer loop of evolve() on resident fields (round 2) ---------------------------------------------------
+ * unsTotalLagrangianStress::evolve() (unsTotalLagrangianStress.C:769-1009) with D, pointD, grad(D), gradDf, D.oldTime(),
+ * D.boundaryField() ... resident on the device across outer iterations AND time steps: nothing but six scalars per
+ * outer iteration crosses PCIe.  Patch types of gpupcg_mesh_create: 0 tractionDisplacement, 1 fixedDisplacement,
+ * 2 symmetryDisplacement (fvPatchFields/ of the reference), 3 symmetryPlane [EXT symmetryFvPatchField], 4 empty (2-D).
+ *
+ * gpupcg_eqn_controls: what evolve() reads from fvSchemes / stressProperties for the equation itself
+ *   d2dt2Scheme / ddtScheme  0 steadyState, 1 Euler  (d2dt2(D), ddt(D) of fvSchemes; deltaT0 = runTime.deltaT0())
+ *   K                        damping coefficient (stressProperties "K", :800-804), active when > SMALL (:862)
+ *   nonLinear                stressProperties "nonLinear" (:796); thermal: stressModel::thermalStress() (:815)
+ *   limitCoeff               snGrad scheme "skewCorrected <limitCoeff>" of fvSchemes                                      */
+typedef struct gpupcg_eqn_controls
+{
+    int    d2dt2Scheme, ddtScheme;
+    double deltaT, deltaT0;
+    double K;
+    int    nonLinear, thermal;
+    double limitCoeff;
+} gpupcg_eqn_controls;
+
+/* Field ids of gpupcg_mesh_set_field / gpupcg_mesh_get_field (host <-> resident device field, caller's numbering).
+ * Cell fields [nCells*k], face fields [nFaces*k], boundary fields [nBoundaryFaces*k] (face index - nInternalFaces).   */
+#define GPUPCG_F_MU              0   /* rheology mu()              [nCells]                    */
+#define GPUPCG_F_LAMBDA          1
+#define GPUPCG_F_RHO             2
+#define GPUPCG_F_D               3   /* D internal field           [nCells*3]                  */
+#define GPUPCG_F_DOLD            4   /* D.oldTime()                                            */
+#define GPUPCG_F_DOLDOLD         5   /* D.oldTime().oldTime()                                  */
+#define GPUPCG_F_GRADD           6   /* grad(D)                    [nCells*9]                  */
+#define GPUPCG_F_GRADDF          7   /* gradDf                     [nFaces*9]                  */
+#define GPUPCG_F_TRACTION        8   /* tractionDisplacement::traction()  [nBoundaryFaces*3]   */
+#define GPUPCG_F_PRESSURE        9   /*                       pressure()  [nBoundaryFaces]     */
+#define GPUPCG_F_FIXEDVALUE     10   /* fixedDisplacement values          [nBoundaryFaces*3]   */
+#define GPUPCG_F_THREEK         11   /* threeK() = rheology.threeK()*rho  [nCells]  (:1313)    */
+#define GPUPCG_F_ALPHA          12   /* thermal.alpha()                   [nCells]             */
+#define GPUPCG_F_DT             13   /* DT = T - T0 (TEqn.H:34)           [nCells]             */
+#define GPUPCG_F_DTB            14   /* boundary values of DT             [nBoundaryFaces]     */
+#define GPUPCG_F_POINTD         15   /* pointD                            [nPoints*3]          */
+#define GPUPCG_F_DB             16   /* D.boundaryField()                 [nBoundaryFaces*3]   */
+#define GPUPCG_F_GRADDB         17   /* boundary field of grad(D)         [nBoundaryFaces*9]   */
+#define GPUPCG_F_U              18   /* U = fvc::ddt(D)                   [nCells*3]           */
+#define GPUPCG_F_EPSILON        19   /* symmTensor xx xy xz yy yz zz      [nCells*6]           */
+#define GPUPCG_F_SIGMA          20
+#define GPUPCG_F_UPPER          21   /* the assembled equation: upper [nInternalFaces], diag [nCells], source [nCells*3], */
+#define GPUPCG_F_DIAG           22   /* internalCoeffs / boundaryCoeffs [nBoundaryFaces*3]                                */
+#define GPUPCG_F_SOURCE         23
+#define GPUPCG_F_INTERNALCOEFFS 24
+#define GPUPCG_F_BOUNDARYCOEFFS 25
+#define GPUPCG_F_PATCHGRADIENT  26   /* gradient() of the tractionDisplacement patches [nBoundaryFaces*3] */
+#define GPUPCG_F_DPREV          27   /* D.prevIter()                                           */
+#define GPUPCG_F_DBPREV         28
+int gpupcg_mesh_field_size(gpupcg_mesh m, int fieldId, long long* nDoubles);
+int gpupcg_mesh_set_field(gpupcg_mesh m, int fieldId, const double* host);
+int gpupcg_mesh_get_field(gpupcg_mesh m, int fieldId, double* host);
+
+/* leastSquaresVolPointInterpolation (numerics/leastSquaresVolPointInterpolation/): the data the reference's volToPoint_
+ * object holds, flattened.  Point p owns rows pointStart[p] .. pointStart[p+1]: its cells (mesh.pointCells()), then its
+ * boundary faces (pointBndFaces(), leastSquaresVolPointInterpolation.C:54-205) -- entry >= 0: cell, < 0: boundary face
+ * -1 - entry --; points on a mirror plane (empty patch, :1829-1940, mirror[p] != 0) carry the rows twice.  invLs[row][3]
+ * is column `row` of invLsMatrices()[p] (:1425-1826), origin = origins()[p] (:1138-1421); weights() are all 1 (:1116-1133).
+ * gpupcg_vol_to_point = interpolate(D, pointD) (leastSquaresVolPointInterpolate.C:43-304) on the resident D and
+ * D.boundaryField(); kernel_ms (optional) = mean device time over reps launches.                                          */
+int gpupcg_mesh_set_lsq(gpupcg_mesh m, const int* pointStart, const int* entry, const double* invLs, const double* origin,
+                        const unsigned char* mirror);
+int gpupcg_vol_to_point(gpupcg_mesh m, int reps, double* kernel_ms);
+/* D.correctBoundaryConditions(): evaluate() of every patch field on the resident D, grad(D), gradient() -> D.boundaryField()
+ * (tractionDisplacementFvPatchVectorField.C:259-300, symmetryDisplacementFvPatchVectorField.C:169-207).                   */
+int gpupcg_patch_evaluate(gpupcg_mesh m);
+/* gpupcg_assemble_D / gpupcg_gradients / gpupcg_sigma on the resident fields, every branch of :846-890, :973-990
+ * (gpupcg_sigma_resident: controls->nonLinear is the dictionary switch of :979, controls->ddtScheme gives U = fvc::ddt(D)). */
+int gpupcg_assemble_D_resident(gpupcg_mesh m, const gpupcg_eqn_controls* controls, const double* g);
+int gpupcg_gradients_resident(gpupcg_mesh m, double limitCoeff);
+int gpupcg_sigma_resident(gpupcg_mesh m, const gpupcg_eqn_controls* controls);
+/* runTime++: D.oldTime().oldTime() = D.oldTime(); D.oldTime() = D                                                          */
+int gpupcg_mesh_new_time_step(gpupcg_mesh m);
+
+typedef struct gpupcg_evolve_controls
+{
+    int    nCorrectors;                                     /* stressProperties (:773-788)                        */
+    double convergenceTolerance, relConvergenceTolerance;
+    double tolerance, relTol;                               /* fvSolution solvers { D { ... } }                   */
+    int    minIter, maxIter;
+    double relaxD;                                          /* fvSolution relaxationFactors D                     */
+    int    doRelax;                                         /* 0: no relaxation factor for D in fvSolution        */
+    int    validCmpt[3];                                    /* mesh.solutionD() != -1 per direction (2-D: one 0)  */
+    double g[3];                                            /* stressProperties "g" (:806-810)                    */
+    gpupcg_eqn_controls eqn;
+} gpupcg_evolve_controls;
+
+typedef struct gpupcg_evolve_result
+{
+    int    nOuterIterations;            /* iCorr at exit (:967-971)                                       */
+    int    totalPcgIterations;
+    int    enforceLinear;               /* set when det(I + gradDf) left [0.01, 100] (:939-945)           */
+    int    converged;                   /* evolve()'s return value (:1002-1008)                           */
+    double initialResidual;             /* solverPerf.initialResidual() of the first outer iteration      */
+    double lastSolverInitialResidual;   /* ... of the last one ("Final residual" of the summary, :994)    */
+    double maxRes, res;
+    double assemble_ms, solve_ms, update_ms;    /* device time: assembly | DEqn.solve() | evaluate+relax+interpolate+gradients+residual */
+} gpupcg_evolve_result;
+
+/* h: solver handle created with this mesh's internal-face addressing on the same device (no coupled patches yet).
+ * residualHistory [historyCap] (optional): res of every outer iteration; pcgIterations [historyCap*3] (optional):
+ * PCG iterations per valid component and outer iteration.  gpupcg_sigma_resident afterwards gives U, epsilon, sigma.   */
+int gpupcg_evolve_D(gpupcg_handle h, gpupcg_mesh m, const gpupcg_evolve_controls* controls, gpupcg_evolve_result* result,
+                    double* residualHistory, int* pcgIterations, int historyCap);
+
 /* ---- host memory helpers ----------------------------------------------------------------------
  * Page-lock caller-owned arrays (scalarField storage) so that the staging copies are DMA.       */
 int gpupcg_host_register(void* ptr, unsigned long long bytes);

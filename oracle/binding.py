@@ -199,7 +199,7 @@ def set_sum_mode(mode):
     load().orc_set_sum_mode(int(mode))
 
 
-PATCH_TYPES = {"tractionDisplacement": 0, "fixedDisplacement": 1, "symmetryDisplacement": 2}
+PATCH_TYPES = {"tractionDisplacement": 0, "fixedDisplacement": 1, "symmetryDisplacement": 2, "symmetryPlane": 3, "empty": 4}
 
 
 def lame(E, nu, planeStress=False):
@@ -273,3 +273,158 @@ def fgrad(mesh, geom, patchTypes, D, pointD, gradD, fixedValue, patchGradient, l
     Gf = np.empty((mesh.nFaces, 9))
     lib.orc_fgrad(C.byref(M), *[_dp(v) for v in a], float(limitCoeff), _dp(Gf))
     return Gf
+
+
+# ---- round 2: transient / damping / non-linear / thermal branches, boundary evaluate, least-squares vol->point -------
+class Controls(C.Structure):
+    _fields_ = [("d2dt2Scheme", C.c_int), ("ddtScheme", C.c_int), ("deltaT", C.c_double), ("deltaT0", C.c_double),
+                ("K", C.c_double), ("nonLinear", C.c_int), ("thermal", C.c_int), ("limitCoeff", C.c_double)]
+
+
+def controls(d2dt2="steadyState", ddt="steadyState", deltaT=1.0, deltaT0=None, K=0.0, nonLinear=False, thermal=False,
+             limitCoeff=1.0):
+    sch = {"steadyState": 0, "Euler": 1}
+    return Controls(sch[d2dt2], sch[ddt], float(deltaT), float(deltaT if deltaT0 is None else deltaT0), float(K),
+                    int(bool(nonLinear)), int(bool(thermal)), float(limitCoeff))
+
+
+def _opt(a):
+    return None if a is None else _f(a)
+
+
+def _odp(a):
+    return None if a is None else _dp(a)
+
+
+def assemble_D_ex(mesh, geom, patchTypes, ctl, mu, lam, rho, g, D, Dold, Doldold, gradD, gradDf, traction, pressure,
+                  fixedValue, threeK=None, alpha=None, DT=None, DTb=None):
+    lib = load()
+    M, keep = _mesh_struct(mesh, geom, patchTypes)
+    a = [_opt(v) for v in (mu, lam, rho, g, D, Dold, Doldold, gradD, gradDf, traction, pressure, fixedValue, threeK, alpha, DT, DTb)]
+    nC, nIF, nBF = mesh.nCells, mesh.nInternalFaces, mesh.nFaces - mesh.nInternalFaces
+    upper = np.empty(nIF); diag = np.empty(nC); source = np.empty((nC, 3)); ic = np.empty((nBF, 3)); bc = np.empty((nBF, 3))
+    pg = np.zeros((nBF, 3))
+    lib.orc_assemble_D_ex.restype = None
+    lib.orc_assemble_D_ex.argtypes = [C.POINTER(Mesh), C.POINTER(Controls)] + [dp]*22
+    lib.orc_assemble_D_ex(C.byref(M), C.byref(ctl), *[_odp(v) for v in a], _dp(upper), _dp(diag), _dp(source), _dp(ic),
+                          _dp(bc), _dp(pg))
+    return dict(upper=upper, diag=diag, source=source, internalCoeffs=ic, boundaryCoeffs=bc, patchGradient=pg)
+
+
+def patch_evaluate(mesh, geom, patchTypes, D, gradD, fixedValue, patchGradient, Db=None):
+    """D.correctBoundaryConditions(): boundary values (nBF,3); slots of empty faces keep what Db held (zeros if None)."""
+    lib = load()
+    M, keep = _mesh_struct(mesh, geom, patchTypes)
+    nBF = mesh.nFaces - mesh.nInternalFaces
+    out = np.zeros((nBF, 3)) if Db is None else np.array(Db, dtype=np.float64, copy=True)
+    a = [_f(v) for v in (D, gradD, fixedValue, patchGradient)]
+    lib.orc_patch_evaluate.restype = None
+    lib.orc_patch_evaluate.argtypes = [C.POINTER(Mesh)] + [dp]*5
+    lib.orc_patch_evaluate(C.byref(M), *[_dp(v) for v in a], _dp(out))
+    return out
+
+
+def grad_ex(mesh, geom, patchTypes, D, pointD, gradDold, fixedValue, patchGradient, gradDb=None):
+    lib = load()
+    M, keep = _mesh_struct(mesh, geom, patchTypes)
+    a = [_f(v) for v in (D, pointD, gradDold, fixedValue, patchGradient)]
+    nBF = mesh.nFaces - mesh.nInternalFaces
+    G = np.empty((mesh.nCells, 9)); Gb = np.zeros((nBF, 9)) if gradDb is None else np.array(gradDb, dtype=np.float64, copy=True)
+    lib.orc_grad_ex.restype = None
+    lib.orc_grad_ex.argtypes = [C.POINTER(Mesh)] + [dp]*7
+    lib.orc_grad_ex(C.byref(M), *[_dp(v) for v in a], _dp(G), _dp(Gb))
+    return G, Gb
+
+
+def fgrad_ex(mesh, geom, patchTypes, D, pointD, gradD, fixedValue, patchGradient, limitCoeff=1.0, gradDf=None):
+    lib = load()
+    M, keep = _mesh_struct(mesh, geom, patchTypes)
+    a = [_f(v) for v in (D, pointD, gradD, fixedValue, patchGradient)]
+    Gf = np.zeros((mesh.nFaces, 9)) if gradDf is None else np.array(gradDf, dtype=np.float64, copy=True)
+    lib.orc_fgrad_ex.restype = None
+    lib.orc_fgrad_ex.argtypes = [C.POINTER(Mesh)] + [dp]*5 + [C.c_double, dp]
+    lib.orc_fgrad_ex(C.byref(M), *[_dp(v) for v in a], float(limitCoeff), _dp(Gf))
+    return Gf
+
+
+def sigma_ex(mu, lam, gradD, nonLinear=False, thermal=False, threeK=None, alpha=None, DT=None):
+    lib = load()
+    mu, lam, gradD = _f(mu), _f(lam), _f(gradD)
+    n = mu.shape[0]
+    eps = np.empty((n, 6)); sig = np.empty((n, 6))
+    t = [_opt(v) for v in (threeK, alpha, DT)]
+    lib.orc_sigma_ex.restype = None
+    lib.orc_sigma_ex.argtypes = [C.c_int, C.c_int, C.c_int] + [dp]*8
+    lib.orc_sigma_ex(n, int(bool(nonLinear)), int(bool(thermal)), _dp(mu), _dp(lam), _dp(gradD), *[_odp(v) for v in t], _dp(eps), _dp(sig))
+    return eps, sig
+
+
+def det_minmax(mesh, geom, patchTypes, gradDf):
+    lib = load()
+    M, keep = _mesh_struct(mesh, geom, patchTypes)
+    g = _f(gradDf)
+    mn, mx = C.c_double(), C.c_double()
+    lib.orc_det_minmax.restype = None
+    lib.orc_det_minmax.argtypes = [C.POINTER(Mesh), dp, dp, dp]
+    lib.orc_det_minmax(C.byref(M), _dp(g), C.byref(mn), C.byref(mx))
+    return mn.value, mx.value
+
+
+def ddt(D, Dold, scheme, deltaT):
+    lib = load()
+    D, Dold = _f(D), _f(Dold)
+    U = np.empty_like(D)
+    lib.orc_ddt.restype = None
+    lib.orc_ddt.argtypes = [C.c_int, C.c_int, C.c_double, dp, dp, dp]
+    lib.orc_ddt(D.shape[0], {"steadyState": 0, "Euler": 1}[scheme], float(deltaT), _dp(D), _dp(Dold), _dp(U))
+    return U
+
+
+def relax_boundary(Db, DbPrev, alpha):
+    lib = load()
+    assert Db.dtype == np.float64 and Db.flags.c_contiguous
+    DbPrev = _f(DbPrev)
+    lib.orc_relax_boundary.restype = None
+    lib.orc_relax_boundary.argtypes = [C.c_int, C.c_double, dp, dp]
+    lib.orc_relax_boundary(Db.size, float(alpha), _dp(Db), _dp(DbPrev))
+
+
+class Lsq(object):
+    """leastSquaresVolPointInterpolation of one mesh (stencils, origins, inverse least-squares matrices)."""
+
+    def __init__(self, mesh, geom, patchTypes):
+        lib = load()
+        self._M, self._keep = _mesh_struct(mesh, geom, patchTypes)
+        lib.orc_lsq_build.restype = C.c_void_p
+        lib.orc_lsq_build.argtypes = [C.POINTER(Mesh)]
+        self._h = C.c_void_p(lib.orc_lsq_build(C.byref(self._M)))
+        self.nPoints = mesh.nPoints
+
+    def export(self):
+        lib = load()
+        lib.orc_lsq_rows.restype = C.c_int
+        lib.orc_lsq_rows.argtypes = [C.c_void_p]
+        rows = lib.orc_lsq_rows(self._h)
+        start = np.empty(self.nPoints + 1, dtype=np.int32); entry = np.empty(max(rows, 1), dtype=np.int32)
+        inv = np.empty((max(rows, 1), 3)); origin = np.empty((self.nPoints, 3)); mirror = np.empty(self.nPoints, dtype=np.uint8)
+        lib.orc_lsq_export.restype = None
+        lib.orc_lsq_export.argtypes = [C.c_void_p, ip, ip, dp, dp, C.POINTER(C.c_ubyte)]
+        lib.orc_lsq_export(self._h, _ip(start), _ip(entry), _dp(inv), _dp(origin), mirror.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        return dict(start=start, entry=entry[:rows], inv=inv[:rows], origin=origin, mirror=mirror)
+
+    def interpolate(self, D, Db):
+        lib = load()
+        D, Db = _f(D), _f(Db)
+        out = np.empty((self.nPoints, 3))
+        lib.orc_lsq_interpolate.restype = None
+        lib.orc_lsq_interpolate.argtypes = [C.c_void_p, C.POINTER(Mesh), dp, dp, dp]
+        lib.orc_lsq_interpolate(self._h, C.byref(self._M), _dp(D), _dp(Db), _dp(out))
+        return out
+
+    def __del__(self):
+        try:
+            lib = load()
+            lib.orc_lsq_free.argtypes = [C.c_void_p]
+            lib.orc_lsq_free(self._h)
+        except Exception:
+            pass

@@ -73,3 +73,126 @@ def evolve(mesh, geom, patchTypes, mu, lam, rho, g, traction, pressure, fixedVal
     return dict(D=D, pointD=pointD, gradD=gradD, gradDf=gradDf, epsilon=eps, sigma=sig, nOuterIterations=iCorr,
                 initialResidual=initialResidual, lastSolverInitialResidual=lastInit, maxRes=maxRes, res=res,
                 totalPcgIterations=totalIts, residualHistory=np.array(hist))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Round 2: the complete outer loop -- every branch of evolve() (:769-1009), D.boundaryField() tracked, the reference's
+# least-squares vol->point interpolation (:924) instead of a callback, 2-D (empty) cases, time stepping.
+# ---------------------------------------------------------------------------------------------------------------------
+def segregated_solve_ex(l, u, diag, upper, source, patches, D, tolerance, relTol, validCmpts=(1, 1, 1), maxIter=1000, minIter=0):
+    """[EXT] fvMatrix<vector>::solve: components with solutionD == -1 (the empty direction) are skipped."""
+    total = np.array(source, dtype=np.float64, copy=True)
+    for fc, ic, bc in patches:
+        for k in range(3):
+            np.add.at(total[:, k], fc, bc[:, k])
+    perfs, hists = {}, {}
+    for k in range(3):
+        if not validCmpts[k]:
+            continue
+        dk = np.array(diag, dtype=np.float64, copy=True)
+        for fc, ic, bc in patches:
+            np.add.at(dk, fc, ic[:, k])
+        x = np.ascontiguousarray(D[:, k])
+        perf, hist = orc.pcg_solve(l, u, dk, upper, x, np.ascontiguousarray(total[:, k]), tolerance, relTol, minIter, maxIter)
+        D[:, k] = x
+        perfs[k] = perf; hists[k] = hist
+    ks = sorted(perfs)
+    worst = perfs[ks[0]]
+    for k in ks[1:]:
+        if perfs[k]["initialResidual"] > worst["initialResidual"] and not perfs[k]["singular"]:
+            worst = perfs[k]
+    return worst, perfs, hists
+
+
+class SolidCase(object):
+    """State of one unsTotalLagrangianStress object: fields that persist across evolve() calls and time steps."""
+
+    def __init__(self, mesh, geom, patchTypes, mu, lam, rho, traction=None, pressure=None, fixedValue=None, g=(0.0, 0.0, 0.0),
+                 threeK=None, alpha=None, validCmpts=(1, 1, 1)):
+        nC, nF, nIF = mesh.nCells, mesh.nFaces, mesh.nInternalFaces
+        nBF = nF - nIF
+        self.mesh, self.geom, self.patchTypes = mesh, geom, patchTypes
+        self.mu = np.full(nC, mu) if np.isscalar(mu) else np.asarray(mu, dtype=np.float64)
+        self.lam = np.full(nC, lam) if np.isscalar(lam) else np.asarray(lam, dtype=np.float64)
+        self.rho = np.full(nC, rho) if np.isscalar(rho) else np.asarray(rho, dtype=np.float64)
+        self.g = np.asarray(g, dtype=np.float64)
+        self.traction = np.zeros((nBF, 3)) if traction is None else np.asarray(traction, dtype=np.float64)
+        self.pressure = np.zeros(nBF) if pressure is None else np.asarray(pressure, dtype=np.float64)
+        self.fixedValue = np.zeros((nBF, 3)) if fixedValue is None else np.asarray(fixedValue, dtype=np.float64)
+        self.threeK = None if threeK is None else (np.full(nC, threeK) if np.isscalar(threeK) else np.asarray(threeK, dtype=np.float64))
+        self.alpha = None if alpha is None else (np.full(nC, alpha) if np.isscalar(alpha) else np.asarray(alpha, dtype=np.float64))
+        self.DT = np.zeros(nC); self.DTb = np.zeros(nBF)
+        self.validCmpts = tuple(validCmpts)
+        self.D = np.zeros((nC, 3)); self.Dold = np.zeros((nC, 3)); self.Doldold = np.zeros((nC, 3))
+        self.gradD = np.zeros((nC, 9)); self.gradDb = np.zeros((nBF, 9)); self.gradDf = np.zeros((nF, 9))
+        self.pointD = np.zeros((mesh.nPoints, 3))
+        self.U = np.zeros((nC, 3))
+        self.lsq = orc.Lsq(mesh, geom, patchTypes)
+        self.patchGradient = np.zeros((nBF, 3))
+        self.Db = orc.patch_evaluate(mesh, geom, patchTypes, self.D, self.gradD, self.fixedValue, self.patchGradient)
+        self.enforceLinear = False
+        self.l = np.ascontiguousarray(mesh.owner[:nIF], dtype=np.int32)
+        self.u = np.ascontiguousarray(mesh.neighbour, dtype=np.int32)
+
+    def new_time_step(self):
+        """runTime++ : storeOldTimes of D."""
+        self.Doldold = self.Dold
+        self.Dold = self.D.copy()
+
+    def evolve(self, nCorrectors, convergenceTolerance, relConvergenceTolerance=0.0, tolerance=1e-9, relTol=0.01,
+               d2dt2="steadyState", ddt="steadyState", deltaT=1.0, deltaT0=None, K=0.0, nonLinear=False, thermal=False,
+               limitCoeff=1.0, relaxD=None, maxIter=1000):
+        mesh, geom, pt = self.mesh, self.geom, self.patchTypes
+        nIF = mesh.nInternalFaces
+        self.enforceLinear = False                      # evolve() resets it (:812-813)
+        iCorr, res, maxRes = 0, 1.0, 0.0
+        hist, initialResidual, lastInit, totalIts, pcgIts = [], 0.0, 0.0, 0, []
+        while True:
+            Dprev = self.D.copy(); DbPrev = self.Db.copy()
+            ctl = orc.controls(d2dt2, ddt, deltaT, deltaT0, K, nonLinear and not self.enforceLinear, thermal, limitCoeff)
+            a = orc.assemble_D_ex(mesh, geom, pt, ctl, self.mu, self.lam, self.rho, self.g, self.D, self.Dold, self.Doldold,
+                                  self.gradD, self.gradDf, self.traction, self.pressure, self.fixedValue, self.threeK,
+                                  self.alpha, self.DT, self.DTb)
+            self.lastAssembly = a
+            patches = []
+            for p in mesh.patches:
+                if pt[p["name"]] == "empty":
+                    continue
+                b0 = p["start"] - nIF
+                patches.append((np.ascontiguousarray(mesh.owner[p["start"]:p["start"] + p["size"]], dtype=np.int64),
+                                a["internalCoeffs"][b0:b0 + p["size"]], a["boundaryCoeffs"][b0:b0 + p["size"]]))
+            worst, perfs, hists = segregated_solve_ex(self.l, self.u, a["diag"], a["upper"], a["source"], patches, self.D,
+                                                      tolerance, relTol, self.validCmpts, maxIter)
+            totalIts += sum(p["nIterations"] for p in perfs.values())
+            pcgIts.append([perfs[k]["nIterations"] for k in sorted(perfs)])
+            if iCorr == 0:
+                initialResidual = worst["initialResidual"]
+            lastInit = worst["initialResidual"]
+            self.patchGradient = a["patchGradient"]
+            self.Db = orc.patch_evaluate(mesh, geom, pt, self.D, self.gradD, self.fixedValue, self.patchGradient, self.Db)
+            if relaxD is not None:
+                orc.relax_boundary(self.Db, DbPrev, relaxD)
+            res = orc.relax_residual(self.D, Dprev, self.Dold, relaxD)
+            self.pointD = self.lsq.interpolate(self.D, self.Db)
+            gradOld = self.gradD
+            self.gradD, self.gradDb = orc.grad_ex(mesh, geom, pt, self.D, self.pointD, gradOld, self.fixedValue,
+                                                  self.patchGradient, self.gradDb)
+            self.gradDf = orc.fgrad_ex(mesh, geom, pt, self.D, self.pointD, self.gradD, self.fixedValue, self.patchGradient,
+                                       limitCoeff, self.gradDf)
+            if nonLinear and not self.enforceLinear:
+                mn, mx = orc.det_minmax(mesh, geom, pt, self.gradDf)
+                if mn < 0.01 or mx > 100:
+                    self.enforceLinear = True
+            maxRes = max(maxRes, res)
+            cur = max(maxRes*relConvergenceTolerance, convergenceTolerance)
+            hist.append(res)
+            if not (res > cur):
+                break
+            iCorr += 1
+            if not (iCorr < nCorrectors):
+                break
+        self.U = orc.ddt(self.D, self.Dold, ddt, deltaT)
+        self.epsilon, self.sigma = orc.sigma_ex(self.mu, self.lam, self.gradD, nonLinear, thermal, self.threeK, self.alpha, self.DT)
+        return dict(nOuterIterations=iCorr, initialResidual=initialResidual, lastSolverInitialResidual=lastInit, maxRes=maxRes,
+                    res=res, totalPcgIterations=totalIts, pcgIterations=pcgIts, residualHistory=np.array(hist),
+                    enforceLinear=self.enforceLinear, converged=not (nonLinear and self.enforceLinear))
