@@ -4,6 +4,7 @@
 #include "../../include/gpupcg.h"
 #include "kernels.cuh"
 #include "kernels_vec.cuh"
+#include "kernels_pencil.cuh"
 #include "plan.h"
 #include "comm.h"
 
@@ -50,6 +51,13 @@ struct gpupcg_handle_s
     int4 *dTabCF = nullptr, *dTabCB = nullptr, *dTabIF = nullptr, *dTabIB = nullptr;
     double *dTabF = nullptr, *dTabB = nullptr;
     size_t smemFwdTab = 0, smemBwdTab = 0;
+    // streaming pencil sweeps (structured blocks, plan.h): per-pencil meta, coefficient index / value tables
+    bool pencil = false;
+    int* dPenMeta = nullptr; int *dPenIdxF = nullptr, *dPenIdxB = nullptr;
+    double *dPenCoefF = nullptr, *dPenCoefB = nullptr;
+    long long penCoefVersion = -1;
+    PencilArgs pen{};
+    unsigned int* dSmCounter = nullptr;
     unsigned long long* dTileTicket = nullptr;
     unsigned long long* dTileTrace = nullptr;
     size_t smemFwd = 0, smemBwd = 0, smemAmul = 0;
@@ -200,7 +208,7 @@ extern "C" int gpupcg_destroy(gpupcg_handle h)
                     h->dTabCF, h->dTabCB, h->dTabIF, h->dTabIB, h->dTabF, h->dTabB,
                     h->vDiag, h->vRD, h->vX, h->vB, h->vRA, h->vWA, h->vPA, h->vY, h->vStageX, h->vStageB, h->vStageD,
                     h->vTmpX, h->vTmpB, h->vBou, h->vXNbr, h->vSend, h->vPartials, h->vHistory, h->dTabSq, h->dTabUF,
-                    h->dTabUB, h->vState};
+                    h->dTabUB, h->vState, h->dPenMeta, h->dPenIdxF, h->dPenIdxB, h->dPenCoefF, h->dPenCoefB, h->dSmCounter};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->hvRing) cudaFreeHost(h->hvRing);
     if (h->hState) cudaFreeHost(h->hState);
@@ -346,6 +354,8 @@ static int build_sweep_tables(gpupcg_handle h, cudaStream_t s)
     return GPUPCG_OK;
 }
 
+template <int NB> static cudaError_t pencil_attrs(int pLong, size_t cap);      // defined with the pencil launch helpers below
+
 static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, const int* l, const int* u,
                        int nPatches, const int* patchSizes, const int* const* patchFaceCells,
                        const int* patchNbrRank)
@@ -386,8 +396,9 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     while (true)
     {
         rc = build_plan(nCells, nFaces, l, u, nPatches, patchSizes, patchFaceCells, patchNbrRank, tileRows,
-                        env_int("GPUPCG_TILE_MODE", 2), h->plan, h->err);
+                        env_int("GPUPCG_TILE_MODE", 3), h->plan, h->err);
         if (rc != GPUPCG_OK && rc != -100) return rc;
+        if (rc == GPUPCG_OK && h->plan.pencil) { h->pencil = true; h->useTab = false; break; }
         if (rc == GPUPCG_OK && !h->plan.bricks && !tileRowsGiven && tileRows > 256) { tileRows = 256; continue; }
         const HostPlan& Q = h->plan;
         h->smemFwd = sweep_layout(Q.tileRowsMax, Q.maxTileExtF, Q.maxItems, std::max(Q.maxTileEntriesU, Q.maxTileEntriesL), Q.maxTileEntriesL).bytes;
@@ -401,7 +412,7 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
         if (tileRows <= 32) break;
         tileRows /= 2;
     }
-    if (rc != GPUPCG_OK || (h->useTab ? std::max(h->smemFwdTab, h->smemBwdTab) : std::max(h->smemFwd, h->smemBwd)) > smemCap)
+    if (!h->pencil && (rc != GPUPCG_OK || (h->useTab ? std::max(h->smemFwdTab, h->smemBwdTab) : std::max(h->smemFwd, h->smemBwd)) > smemCap))
     {
         h->err = "gpupcg_create: a single 32-row tile does not fit in shared memory (rows with too many faces)";
         return GPUPCG_ERR_UNSUPPORTED;
@@ -415,6 +426,24 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
         int ns = env_int("GPUPCG_SPIN_NS", 0);
         CK(cudaMemcpyToSymbol(g_spinNs, &ns, sizeof(int)));
     }
+    if (h->pencil)
+    {
+        const HostPlan& Q = h->plan;
+        h->pen.nPencils = Q.nTiles; h->pen.w1 = Q.pW1; h->pen.w2 = Q.pW2; h->pen.n0 = Q.pN0; h->pen.steps = Q.pSteps;
+        CK(upload(h->dPenMeta, Q.pMeta, h->stream));
+        CK(upload(h->dPenIdxF, Q.pIdxF, h->stream));
+        CK(upload(h->dPenIdxB, Q.pIdxB, h->stream));
+        CK(dalloc(h->dPenCoefF, 3LL*std::max(1, Q.nRows))); CK(dalloc(h->dPenCoefB, 3LL*std::max(1, Q.nRows)));
+        h->pen.meta = h->dPenMeta; h->pen.coefF = h->dPenCoefF; h->pen.coefB = h->dPenCoefB;
+        CK(pencil_attrs<1>(Q.pLong, smemCap));
+        CK(dalloc(h->dSmCounter, 1024));
+        CK(cudaMemsetAsync(h->dSmCounter, 0, sizeof(unsigned int)*1024, h->stream));
+        h->pen.smCounter = env_int("GPUPCG_PENCIL_ROTATE", 1) ? h->dSmCounter : nullptr;
+        CK(cudaStreamSynchronize(h->stream));
+        std::vector<int>().swap(h->plan.pIdxF); std::vector<int>().swap(h->plan.pIdxB);
+    }
+    else
+    {
     CK(cudaFuncSetAttribute(k_dic_tile<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwd));
     CK(cudaFuncSetAttribute(k_dic_tile<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwd));
     CK(cudaFuncSetAttribute(k_dic_tile<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBwd));
@@ -428,6 +457,7 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
         CK(cudaFuncSetAttribute((k_dic_tile<1, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwdTab));
         CK(cudaFuncSetAttribute((k_dic_tile<2, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBwdTab));
     }
+    }   // !pencil
     h->sweepGrid = std::max(1, P.nTiles);
     int sbps = std::max(1, env_int("GPUPCG_STREAM_BPS", 8));
     h->streamGrid = std::min(h->numSMs*sbps, MAXPART);
@@ -785,6 +815,60 @@ static int enqueue_amul(gpupcg_handle h, int mode, const double* x, double* Ax, 
     return GPUPCG_OK;
 }
 
+// ---- streaming pencil sweeps (kernels_pencil.cuh): one CTA per pencil -------------------------------------------------
+template <int NB, int MODE, int LONG>
+static cudaError_t pencil_attr(size_t cap)
+{
+    return cudaFuncSetAttribute((k_dic_pencil<NB, MODE, LONG>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+}
+template <int NB>
+static cudaError_t pencil_attrs(int pLong, size_t cap)
+{
+    cudaError_t e = cudaSuccess;
+    if (pLong == 0) { e = pencil_attr<NB, 0, 0>(cap); if (!e) e = pencil_attr<NB, 1, 0>(cap); if (!e) e = pencil_attr<NB, 2, 0>(cap); }
+    else if (pLong == 1) { e = pencil_attr<NB, 0, 1>(cap); if (!e) e = pencil_attr<NB, 1, 1>(cap); if (!e) e = pencil_attr<NB, 2, 1>(cap); }
+    else { e = pencil_attr<NB, 0, 2>(cap); if (!e) e = pencil_attr<NB, 1, 2>(cap); if (!e) e = pencil_attr<NB, 2, 2>(cap); }
+    return e;
+}
+
+// coefficient tables of the pencil sweeps follow dUval
+static int pencil_coeffs(gpupcg_handle h)
+{
+    if (h->penCoefVersion == h->uvalVersion) return GPUPCG_OK;
+    const long long n3 = 3LL*h->plan.nRows;
+    LAUNCH(k_pencil_coeffs, grid_for(n3, h->streamGrid), h->stream, n3, h->dPenIdxF, h->dUval, h->dPenCoefF);
+    LAUNCH(k_pencil_coeffs, grid_for(n3, h->streamGrid), h->stream, n3, h->dPenIdxB, h->dUval, h->dPenCoefB);
+    CK(cudaGetLastError());
+    h->penCoefVersion = h->uvalVersion;
+    return GPUPCG_OK;
+}
+
+template <int NB, int MODE>
+static int launch_pencil(gpupcg_handle h, const double* diagOrRD, const double* rA, unsigned long long* y, unsigned long long* out,
+                         double* rDout, double* partials, DevState* st, int gated)
+{
+    const bool withDot = (MODE == 2) && partials != nullptr;
+    PencilArgs A = h->pen;
+    // ring stages: as many as fit the budget (default ~100 KB: two CTAs per SM), 2 ... 8
+    const size_t cap = std::min<size_t>(h->smemCap, (size_t)env_int("GPUPCG_PENCIL_SMEM_KB", 100)*1024);
+    int nst = std::max(2, std::min(8, env_int("GPUPCG_PENCIL_STAGES", 8)));
+    while (nst > 2 && pen_smem_bytes<NB, MODE>(nst, A.w1, A.w2, withDot) > cap) nst--;
+    A.nStages = nst;
+    A.fetchWindow = env_int("GPUPCG_PENCIL_FETCH_WINDOW", 1);     // 1: measured best (profiles/r2_pencil_sweeps.md); 0 = adaptive
+    A.fetchSleep = std::max(0, env_int("GPUPCG_PENCIL_FETCH_SLEEP", 100));
+    const size_t smem = pen_smem_bytes<NB, MODE>(nst, A.w1, A.w2, withDot);
+    if (smem > h->smemCap) { h->err = "pencil sweep: the ring does not fit in shared memory"; return GPUPCG_ERR_UNSUPPORTED; }
+    h->launches++;
+    const int grid = A.nPencils;
+    switch (h->plan.pLong)
+    {
+        case 0: k_dic_pencil<NB, MODE, 0><<<grid, PEN_TPB, smem, h->stream>>>(A, diagOrRD, rA, y, out, rDout, h->dTileTicket, partials, h->partStride, st, gated); break;
+        case 1: k_dic_pencil<NB, MODE, 1><<<grid, PEN_TPB, smem, h->stream>>>(A, diagOrRD, rA, y, out, rDout, h->dTileTicket, partials, h->partStride, st, gated); break;
+        default: k_dic_pencil<NB, MODE, 2><<<grid, PEN_TPB, smem, h->stream>>>(A, diagOrRD, rA, y, out, rDout, h->dTileTicket, partials, h->partStride, st, gated); break;
+    }
+    return GPUPCG_OK;
+}
+
 #define LAUNCH_SWEEP(kern, smem, ...)                                                              \
     do { h->launches++; kern<<<h->sweepGrid, SWEEP_TPB, (smem), h->stream>>>(__VA_ARGS__); } while (0)
 
@@ -792,7 +876,13 @@ static int enqueue_factor(gpupcg_handle h, int gated)
 {
     if (h->plan.nTiles == 0) return GPUPCG_OK;
     fill_sent(h, h->dY);
-    if (h->useTab)
+    if (h->pencil)
+    {
+        int rcp = pencil_coeffs(h); if (rcp) return rcp;
+        rcp = launch_pencil<1, 1>(h, h->dDiag, nullptr, nullptr, (unsigned long long*)h->dY, h->dRD, nullptr, h->dState, gated);
+        if (rcp) return rcp;
+    }
+    else if (h->useTab)
     {
         const int gT = grid_for(h->plan.nRows, h->streamGrid);
         LAUNCH((k_tab_coeffs<0>), gT, h->stream, h->plan.nRows, h->dTabIF, h->dUval, nullptr, h->dTabF, h->dState, gated);
@@ -821,7 +911,13 @@ static int enqueue_sweeps(gpupcg_handle h, const double* rA, double* z, bool red
     unsigned long long* yb = (unsigned long long*)h->dY;
     unsigned long long* zb = (unsigned long long*)z;
     double* part = reduce ? h->dPartials : nullptr;
-    if (h->useTab)
+    if (h->pencil)
+    {
+        int rcp = pencil_coeffs(h); if (rcp) return rcp;
+        rcp = launch_pencil<1, 0>(h, h->dRD, rA, nullptr, yb, nullptr, nullptr, h->dState, gated); if (rcp) return rcp;
+        rcp = launch_pencil<1, 2>(h, h->dRD, rA, yb, zb, nullptr, part, h->dState, gated); if (rcp) return rcp;
+    }
+    else if (h->useTab)
     {
         if (fuseXR)
         {

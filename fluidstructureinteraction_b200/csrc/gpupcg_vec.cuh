@@ -28,15 +28,19 @@ int vec_prepare(gpupcg_handle h)
     h->smemFacV = tabv_layout<NB>(P.tileRowsMax, P.maxTileExtF, P.maxItems, false).bytes;
     h->smemBwdV = tabv_layout<NB>(P.tileRowsMax, P.maxTileExtB, P.maxItems, false).bytes;
     h->smemAmulV = 2*(size_t)((amul_layout_v<NB>(h->amulT, h->amulEU, h->amulEL, h->amulXStride, h->amulCStride).bytes + 127u) & ~127u);
-    h->vBatched = h->useTab && P.nTiles > 0 && env_int("GPUPCG_VECTOR_BATCH", 1)
-               && std::max(h->smemFwdV, h->smemBwdV) <= h->smemCap && h->smemAmulV <= h->smemCap;
+    h->vBatched = (h->pencil || (h->useTab && std::max(h->smemFwdV, h->smemBwdV) <= h->smemCap)) && P.nTiles > 0
+               && env_int("GPUPCG_VECTOR_BATCH", 1) && h->smemAmulV <= h->smemCap;
     if (h->vBatched)
     {
+        if (h->pencil) { CK(pencil_attrs<NB>(P.pLong, h->smemCap)); }
+        else
+        {
         CK(cudaFuncSetAttribute((k_dic_tile_v<NB, 0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwdV));
         CK(cudaFuncSetAttribute((k_dic_tile_v<NB, 1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFacV));
         CK(cudaFuncSetAttribute((k_dic_tile_v<NB, 2, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBwdV));
         CK(cudaFuncSetAttribute((k_dic_tile_v<NB, 0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemFwdV));
         CK(cudaFuncSetAttribute((k_dic_tile_v<NB, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBwdV));
+        }
         // latency-bound sweeps (small sub-domains) take the bank-swizzled variant, throughput-bound ones the leaner one
         const int swEnv = env_int("GPUPCG_SWEEP_SWIZZLE", -1);
         h->vSwizzle = (swEnv >= 0) ? (swEnv != 0) : (P.nRows <= env_int("GPUPCG_FUSE_XR_MAXROWS", 3000000));
@@ -111,7 +115,8 @@ int vec_set_matrix_device(gpupcg_handle h, const double* d_diagC, const double* 
     {
         const long long nFlat = (long long)P.nRows*VecStride<NB>::v;
         LAUNCH((k_rows_in_v<NB>), grid_for(nFlat, h->streamGrid), s, h->vStageD, h->vDiag, h->dRowOld, nFlat, 1.0);
-        if (h->vTabVersion != h->uvalVersion)
+        if (h->pencil) { int rcp = pencil_coeffs(h); if (rcp) return rcp; }
+        else if (h->vTabVersion != h->uvalVersion)
         {
             h->vTabVersion = h->uvalVersion;
             const int gT = grid_for(P.nRows, h->streamGrid);
@@ -190,9 +195,18 @@ int vec_factor(gpupcg_handle h, int gated)
     if (h->plan.nTiles == 0) return GPUPCG_OK;
     vec_fill_sent<NB>(h, h->vY);
     const FuseXR none{nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (h->pencil)
+    {
+        int rcp = pencil_coeffs(h); if (rcp) return rcp;
+        rcp = launch_pencil<NB, 1>(h, h->vDiag, nullptr, nullptr, (unsigned long long*)h->vY, h->vRD, nullptr, h->vState, gated);
+        if (rcp) return rcp;
+    }
+    else
+    {
     h->launches++;
     k_dic_tile_v<NB, 1, false><<<h->sweepGrid, SWEEP_TPB, h->smemFacV, h->stream>>>(h->tiles, h->vDiag, nullptr, nullptr,
         (unsigned long long*)h->vY, h->vRD, h->dTileTicket, nullptr, 0, h->vState, gated, h->dTabCF, h->dTabSq, none, 0);
+    }
     vec_fill_sent<NB>(h, h->vY);
     CK(cudaGetLastError());
     return GPUPCG_OK;
@@ -206,6 +220,15 @@ int vec_sweeps(gpupcg_handle h, double* rA, double* z, bool reduce, int gated, b
     unsigned long long* yb = (unsigned long long*)h->vY;
     unsigned long long* zb = (unsigned long long*)z;
     const FuseXR none{nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (h->pencil)
+    {
+        if (fuseXR) { h->err = "internal: the pencil sweeps do not carry the x/r update"; return GPUPCG_ERR_STATE; }
+        int rcp = pencil_coeffs(h); if (rcp) return rcp;
+        rcp = launch_pencil<NB, 0>(h, h->vRD, rA, nullptr, yb, nullptr, nullptr, h->vState, gated); if (rcp) return rcp;
+        rcp = launch_pencil<NB, 2>(h, h->vRD, rA, yb, zb, nullptr, reduce ? h->vPartials : nullptr, h->vState, gated); if (rcp) return rcp;
+        CK(cudaGetLastError());
+        return GPUPCG_OK;
+    }
     const FuseXR fx = fuseXR ? FuseXR{h->vX, h->vPA, zb, h->vRA, h->vHistory} : none;
     h->launches += 2;
     const size_t smF = fuseXR ? h->smemFwdV : h->smemFacV;
@@ -265,7 +288,7 @@ int vec_solve_core(gpupcg_handle h, double tol, double relTol, int minIter, int 
     // The x/r update rides in the staging of the next forward sweep while the sweeps are latency-bound (their CTAs
     // have bandwidth to spare); on large sub-domains the sweeps are throughput-bound and a streaming kernel is cheaper.
     const int fuseEnv = env_int("GPUPCG_FUSE_XR", -1);
-    const bool fuseXR = (fuseEnv >= 0) ? (fuseEnv != 0) : (P.nRows <= env_int("GPUPCG_FUSE_XR_MAXROWS", 3000000));
+    const bool fuseXR = !h->pencil && ((fuseEnv >= 0) ? (fuseEnv != 0) : (P.nRows <= env_int("GPUPCG_FUSE_XR_MAXROWS", 3000000)));
     auto all_done_host = [&](const DevState* st) { bool d = true; for (int k = 0; k < NB; k++) d = d && st[k].done; return d; };
     auto enqueue_check = [&](int slot) -> cudaError_t
     {

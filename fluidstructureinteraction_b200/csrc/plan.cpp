@@ -87,6 +87,8 @@ int build_plan(int nCells, int nFaces, const int* l, const int* u,
     std::vector<int> order(nCells);
     std::vector<int> cuts;                          // first position (in `order`) of every tile, + nCells
     bool bricks = false;
+    const bool wantPencils = (tileMode == 3);
+    if (tileMode == 3) tileMode = 2;
     if (tileMode == 2 && nFaces > 0)
     {
         // detect: at most three distinct strides u-l, 1 | nx | nx*ny, box completely filled
@@ -129,6 +131,59 @@ int build_plan(int nCells, int nFaces, const int* l, const int* u,
                 long long n3[3] = {nx, ny, nz};
                 int ax[3] = {0, 1, 2};
                 std::sort(ax, ax + 3, [&](int a, int b) { return n3[a] != n3[b] ? n3[a] > n3[b] : a < b; });
+                if (wantPencils && n3[ax[0]] >= 16 && (long long)nCells >= 4096)
+                {
+                    // pencils: long axis = the longest (ties: x before y before z, so that the own-lane dependency comes
+                    // last in the reference's z, y, x chain); a1 < a2 are the other two axes in x < y < z order
+                    const int a0 = ax[0], a1 = (a0 == 0) ? 1 : 0, a2 = (a0 == 2) ? 1 : 2;
+                    const int w1 = (int)std::min<long long>(n3[a1], 4), w2 = (int)std::min<long long>(n3[a2], 32/w1);
+                    const int nP1 = (int)((n3[a1] + w1 - 1)/w1), nP2 = (int)((n3[a2] + w2 - 1)/w2);
+                    const int n0 = (int)n3[a0], steps = ((n0 + w1 + w2 - 2 + 3)/4)*4;      // whole ring stages (PEN_SS = 4)
+                    if ((long long)nP1*nP2*steps*32 < (long long)INT_MAX - 64)
+                    {
+                        P.pencil = true; P.pStride1 = (int)nx; P.pLong = a0; P.pW1 = w1; P.pW2 = w2; P.pN0 = n0; P.pSteps = steps;
+                        struct Pen { int s, b, a; };
+                        std::vector<Pen> pl;
+                        for (int b = 0; b < nP2; b++) for (int a = 0; a < nP1; a++) pl.push_back(Pen{a + b, b, a});
+                        std::sort(pl.begin(), pl.end(), [](const Pen& x, const Pen& y)
+                                  { return x.s != y.s ? x.s < y.s : (x.b != y.b ? x.b < y.b : x.a < y.a); });
+                        std::vector<int> tileOf((size_t)nP1*nP2);
+                        for (size_t t = 0; t < pl.size(); t++) tileOf[(size_t)pl[t].b*nP1 + pl[t].a] = (int)t;
+                        P.nTiles = (int)pl.size();
+                        P.tileStart.assign(P.nTiles + 1, 0);
+                        P.pos.assign(nCells, -1);
+                        P.pMeta.assign((size_t)8*P.nTiles, -1);
+                        const long long str[3] = {1, nx, nx*ny};
+                        for (int t = 0; t < P.nTiles; t++)
+                        {
+                            const int a = pl[t].a, b = pl[t].b;
+                            const int base = t*steps*32;
+                            const int w1a = (int)std::min<long long>(w1, n3[a1] - (long long)a*w1), w2a = (int)std::min<long long>(w2, n3[a2] - (long long)b*w2);
+                            P.tileStart[t] = base;
+                            int* M = &P.pMeta[(size_t)8*t];
+                            M[0] = base; M[1] = w1a; M[2] = w2a;
+                            M[3] = a > 0 ? tileOf[(size_t)b*nP1 + a - 1] : -1;
+                            M[4] = b > 0 ? tileOf[(size_t)(b - 1)*nP1 + a] : -1;
+                            M[5] = a + 1 < nP1 ? tileOf[(size_t)b*nP1 + a + 1] : -1;
+                            M[6] = b + 1 < nP2 ? tileOf[(size_t)(b + 1)*nP1 + a] : -1;
+                            M[7] = 0;
+                            for (int p2 = 0; p2 < w2a; p2++)
+                            for (int p1 = 0; p1 < w1a; p1++)
+                            for (int q = 0; q < n0; q++)
+                            {
+                                const long long c = q*str[a0] + ((long long)a*w1 + p1)*str[a1] + ((long long)b*w2 + p2)*str[a2];
+                                P.pos[(size_t)c] = base + 32*(q + p1 + p2) + (p1 + w1*p2);
+                            }
+                        }
+                        P.tileStart[P.nTiles] = P.nTiles*steps*32;
+                        P.nRows = P.tileStart[P.nTiles];
+                        P.nSlices = P.nRows/W;
+                        P.tileRowsMax = steps*32;
+                        bricks = true;          // skips the generic tile construction below
+                    }
+                }
+                if (!P.pencil)
+                {
                 int bb[3];
                 bb[ax[2]] = (int)std::min<long long>(n3[ax[2]], 4);
                 bb[ax[1]] = (int)std::min<long long>(n3[ax[1]], 32/bb[ax[2]]);
@@ -165,6 +220,7 @@ int build_plan(int nCells, int nFaces, const int* l, const int* u,
                 cuts.push_back(p);
                 bricks = true;
                 P.bricks = true;
+                }
             }
         }
     }
@@ -215,8 +271,19 @@ int build_plan(int nCells, int nFaces, const int* l, const int* u,
         for (int p = 0; p < nCells; p += tileRows) cuts.push_back(p);
         cuts.push_back(nCells);
     }
-    const int nTiles = (int)cuts.size() - 1;
+    const int nTiles = P.pencil ? P.nTiles : (int)cuts.size() - 1;
     P.nTiles = nTiles;
+    if (P.pencil)
+    {
+        // one dummy round per tile: the tile kernels are not used on pencils
+        std::vector<int>().swap(level);
+        std::vector<int>().swap(order);
+        P.tileRoundPtr.assign(nTiles + 1, 0);
+        P.tileItemPtr.assign(nTiles + 1, 0);
+        P.maxRounds = P.pSteps;
+    }
+    else
+    {
 
 
     // Round of a row = rank of its GLOBAL dependency level among the levels present in its tile.  Using the
@@ -297,6 +364,7 @@ int build_plan(int nCells, int nFaces, const int* l, const int* u,
         P.maxItems = std::max(P.maxItems, P.tileItemPtr[t + 1] - P.tileItemPtr[t]);
     }
     std::vector<int>().swap(lvl);
+    }   // !pencil
     P.rowOld.assign(P.nRows, -1);
     for (int c = 0; c < nCells; c++) P.rowOld[P.pos[c]] = c;
 
@@ -366,6 +434,37 @@ int build_plan(int nCells, int nFaces, const int* l, const int* u,
         }
     }
 
+    if (P.pencil)
+    {
+        // coefficient index tables of the pencil sweeps: per row the U index of the face to the lower (forward / factor)
+        // and upper (backward) neighbour along z, y, x -- the order the reference's face loops subtract them in
+        P.pIdxF.assign((size_t)3*P.nRows, -1);
+        P.pIdxB.assign((size_t)3*P.nRows, -1);
+        for (int r = 0; r < P.nRows; r++)
+        {
+            const int c = P.rowOld[r];
+            if (c < 0) continue;
+            const SliceInfo& si = P.slices[r/W];
+            for (int j = 0; j < nL[r]; j++)
+            {
+                const int e = si.offL + j*W + (r % W);
+                const long long d = (long long)c - P.rowOld[P.Lcol[e]];
+                const int slot = (d == 1) ? 2 : ((P.pStride1 == d) ? 1 : 0);
+                P.pIdxF[(size_t)3*r + slot] = P.Lidx[e];
+            }
+            for (int j = 0; j < nU[r]; j++)
+            {
+                const int e = si.offU + j*W + (r % W);
+                const long long d = (long long)P.rowOld[P.Ucol[e]] - c;
+                const int slot = (d == 1) ? 2 : ((P.pStride1 == d) ? 1 : 0);
+                P.pIdxB[(size_t)3*r + slot] = e;
+            }
+        }
+        P.extFPtr.assign(nTiles + 1, 0);
+        P.extBPtr.assign(nTiles + 1, 0);
+    }
+    else
+    {
     // ---- tile view of the columns + external (cross-tile) lists in consumption order
     P.LcolTile.assign(totL, -1);
     P.UcolTile.assign(totU, -1);
@@ -446,6 +545,7 @@ int build_plan(int nCells, int nFaces, const int* l, const int* u,
         err = "gpupcg_create: tile too large for the 16-bit tile codes";
         return GPUPCG_ERR_TILE;
     }
+    }   // !pencil
 
     // ---- coupled interfaces
     P.patchStart.assign(nPatches + 1, 0);

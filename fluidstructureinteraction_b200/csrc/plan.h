@@ -41,6 +41,18 @@ struct HostPlan
     int nSlices = 0;
     int nLevels = 0;            // global dependency depth (information only)
     bool bricks = false;        // tiles are bricks of a structured block (tile mode 2 detected one)
+    // ---- pencils (tile mode 3 on a structured block): one tile = one pencil, the full length n0 of the block's longest
+    // axis times a w1 x w2 (<= 32) cross-section.  Row of cell (q, p1, p2) of a pencil = base + 32*(q + p1 + p2) + (p1 +
+    // w1*p2): a warp that marches along the pencil one 32-row step at a time meets every dependency of step t in step
+    // t - 1 (forward) / t + 1 (backward) -- own lane (long axis), lane -+1 (axis a1), lane -+w1 (axis a2) -- so a sweep
+    // needs no shared-memory round trip inside the pencil: registers + shuffles (kernels_pencil.cuh).
+    bool pencil = false;
+    int pLong = 0;              // 0 / 1 / 2: the long axis is x / y / z (a1, a2 = the other two in x < y < z order)
+    int pStride1 = 0;           // nx: cell-index stride of a y neighbour (x: 1, z: anything else)
+    int pW1 = 0, pW2 = 0, pN0 = 0, pSteps = 0;     // cross-section, pencil length, steps = n0 + w1 + w2 - 2
+    std::vector<int> pMeta;     // 8 ints per pencil: base row, actual w1, actual w2, tile of the a1-, a2-, a1+, a2+ neighbour (-1), pad
+    std::vector<int> pIdxF, pIdxB;  // [nRows*3] U-array index of the coefficient of the row's lower / upper neighbour in
+                                    // the order the reference subtracts them (z, y, x), -1: no such neighbour
     int maxLevelRows = 0;
     long long entriesU = 0;
     long long entriesL = 0;

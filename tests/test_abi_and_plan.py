@@ -251,3 +251,37 @@ def test_mesh_generators_closed_cells():
                 vol[m.neighbour[f]] -= np.dot(Sf[f], fc)/3
         assert np.all(vol > 0)
         assert abs(vol.sum() - 1.0) < 1e-9           # 2 x 0.5 x 1 box
+
+
+def test_pencil_plan_puts_every_dependency_one_step_back():
+    """Tile mode 3 (structured block): rows are numbered base + 32*step + lane per pencil so that, inside a pencil, the
+    three lower neighbours of a cell sit exactly one step back -- own lane (long axis), lane - 1, lane - w1 -- which is
+    what lets the sweep warp of kernels_pencil.cuh run on registers and shuffles."""
+    nx, ny, nz = 40, 9, 13
+    l, u = meshes.hex_ldu(nx, ny, nz)
+    n = nx*ny*nz
+    from fluidstructureinteraction_b200 import plan_export
+    P = plan_export(l, u, n, tileRows=256, tileMode=3)
+    rowOld, ts = P["rowOld"], P["tileStart"]
+    pos = np.full(n, -1, dtype=np.int64)
+    real = np.flatnonzero(rowOld >= 0)
+    pos[rowOld[real]] = real
+    assert np.all(pos >= 0) and real.size == n                     # a permutation plus padding rows
+    assert np.all(ts % 32 == 0) and np.all(np.diff(ts) == ts[1] - ts[0])
+    tile = np.searchsorted(ts, pos, side="right") - 1
+    step = (pos - ts[tile])//32
+    lane = pos % 32
+    rl, ru = pos[l], pos[u]
+    same = tile[l] == tile[u]
+    assert np.all(step[u][same] == step[l][same] + 1)
+    d = (u - l)[same]
+    dl = (lane[u] - lane[l])[same]
+    assert np.all(dl[d == 1] == 0)                                  # long axis (x, the longest): own lane
+    assert np.all(dl[d == nx] == 1) and np.all(dl[d == nx*ny] == 4)  # a1 = y: lane + 1, a2 = z: lane + w1
+    # across pencils: the producer is an earlier tile (forward sweeps take tiles in ascending order)
+    assert np.all(tile[l][~same] < tile[u][~same])
+    # a general mesh keeps the tile schedule (no pencils)
+    m = meshes.tet_box(4, 3, 3)
+    lt, ut = m.lower_upper()
+    Pt = plan_export(lt, ut, m.nCells, tileRows=256, tileMode=3)
+    assert Pt["info"]["nRows"] >= m.nCells and Pt["info"]["maxRounds"] > 0
