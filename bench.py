@@ -73,6 +73,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scalar-solves", action="store_true",
                     help="three sequential scalar component solves per step (gpupcg_solve) instead of the batched vector solve")
+    ap.add_argument("--no-evolve", action="store_true", help="skip the device-resident evolve() outer-iteration measurement")
+    ap.add_argument("--no-64m", action="store_true",
+                    help="skip the single-GPU run of the 64 M-cell case (scale_base_64M, the N = 1 point of the strong-scaling curve)")
     ap.add_argument("--no-8m", action="store_true",
                     help="skip the extra 8.1 M-cell kernel measurements (Amul / DIC / assembly roofline fractions the north star quotes)")
     return ap.parse_args()
@@ -153,29 +156,31 @@ def run_reference(args, nx, ny, nz):
     import oracle
     from fluidstructureinteraction_b200 import decompose
     cores = os.cpu_count() or 1
-    threads = 1
-    for t in (8, 4, 2, 1):
-        if t <= cores:
-            threads = t
-            break
+    threads = cores                                 # every host core: one decomposePar sub-domain per thread
     s = build_system(nx, ny, nz)
     n = s["nCells"]
-    px, py, pz = decompose.proc_grid(threads)
+    px, py, pz = host_proc_grid(threads, nx, ny, nz)
     cellProc = decompose.simple_cell_proc(nx, ny, nz, px, py, pz)
     oracle.set_num_threads(threads)
-    b = s["b"]*TRACTION[2]
     times, iters = [], []
+    doms = decompose.decompose_ldu(s["l"], s["u"], s["diag"], s["upper"], s["b"], np.zeros(n), cellProc, threads)
+    bunit = [d["b"] for d in doms]
     for it in range(args.warmup + args.steps):
-        doms = decompose.decompose_ldu(s["l"], s["u"], s["diag"], s["upper"], b, np.zeros(n), cellProc, threads)
-        t0 = time.perf_counter()
-        perf, _ = oracle.pcg_solve_multi(doms, TOL, RELTOL, 0, args.cpu_maxiter)
-        dt = time.perf_counter() - t0
+        dt, its = 0.0, 0
+        for tr in TRACTION:                         # the three component solves of one DEqn.solve(), as in the GPU arm
+            for d, bu in zip(doms, bunit):
+                d["b"] = bu*tr; d["x"] = np.zeros(bu.shape[0])
+            t0 = time.perf_counter()
+            perf, _ = oracle.pcg_solve_multi(doms, TOL, RELTOL, 0, args.cpu_maxiter)
+            dt += time.perf_counter() - t0
+            its += perf["nIterations"]
         if it >= args.warmup:
-            times.append(dt); iters.append(perf["nIterations"])
+            times.append(dt); iters.append(its)
     tot = float(np.sum(times))
     value = n*float(np.sum(iters))/tot
-    sample = ("one Dz component solve of the same %dx%dx%d system per step, capped at %d PCG iterations, "
-              "decomposed simple(%d %d %d), one sub-domain per OpenMP thread" % (nx, ny, nz, args.cpu_maxiter, px, py, pz))
+    sample = ("the three component solves (Dx, Dy, Dz) of the same %dx%dx%d system per step, each capped at %d PCG iterations, "
+              "decomposed simple(%d %d %d) over all %d host cores, one sub-domain per OpenMP thread (stand-in for mpirun -np %d)"
+              % (nx, ny, nz, args.cpu_maxiter, px, py, pz, threads, threads))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3*tot/args.steps, "higher_is_better": True,
@@ -186,6 +191,21 @@ def run_reference(args, nx, ny, nz):
         "iterations_per_step": float(np.mean(iters)), "host_cores": cores,
     }
     emit(line)
+
+
+def host_proc_grid(threads, nx, ny, nz):
+    """`simple (px py pz)` with px*py*pz = threads: factors of two peeled off the longest remaining block edge."""
+    p = [1, 1, 1]
+    n = [float(nx), float(ny), float(nz)]
+    t = threads
+    f = 2
+    while t > 1:
+        while t % f:
+            f += 1
+        k = int(np.argmax([n[i]/p[i] for i in range(3)]))
+        p[k] *= f
+        t //= f
+    return tuple(p)
 
 
 def workload_name(nx, ny, nz, gpus):
@@ -206,6 +226,68 @@ def cpu_baseline(s, n, maxiter):
             "sample": "one Dz component solve of the same system, first %d PCG iterations (%.1f s), oracle/ldu_oracle.c serial"
                       % (perf["nIterations"], dt),
             "ms_per_iteration": 1e3*dt/max(1, perf["nIterations"])}
+
+
+def kernel_bytes(n, nF, nsys):
+    """Algorithmic bytes per launch (SURVEY.md 8d).  `systems`: the reference's bytes for nsys independent systems;
+    `shared`: the minimum when the nsys systems of one fvMatrix<vector>::solve share upper()/lduAddr() (what the batched
+    kernels can at best move) -- Amul nsys*24N + 16F, DIC nsys*24N + 32F, updates nsys*24N / nsys*48N."""
+    per = {"amul": (24*n, 16*nF), "dic": (24*n, 32*nF), "p_update": (24*n, 0), "xr_update": (48*n, 0)}
+    return {k: {"systems": nsys*(a + b), "shared": nsys*a + b} for k, (a, b) in per.items()}
+
+
+def kernel_entry(t, nsys, kb, peak):
+    e = {"ms": t, "systems_per_launch": nsys, "algorithmic_bytes": kb["shared"], "achieved_gbs": kb["shared"]/t/1e6,
+         "frac": kb["shared"]/t/1e6/peak}
+    if nsys > 1:
+        e["algorithmic_bytes_as_independent_systems"] = kb["systems"]
+        e["frac_as_independent_systems"] = kb["systems"]/t/1e6/peak
+    return e
+
+
+def ncu_traffic(nx, ny, nz, batched):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+    (profiles/r2_ncu_traffic.json: kernel -> bytes, with the capture's file and commit)."""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    if not os.path.exists(p):
+        return {}, None
+    with open(p) as f:
+        t = json.load(f)
+    key = "%dx%dx%d_%s" % (nx, ny, nz, "batched3" if batched else "scalar")
+    return t.get(key, {}), t.get("source")
+
+
+def measure_evolve(nx, ny, nz, nOuter=4):
+    """One evolve() call (unsTotalLagrangianStress.C:769-1009) resident on the device: ms per OUTER iteration, split
+    into assembly | DEqn.solve() | correctBoundaryConditions + relax + least-squares vol->point + grad/fGrad + residual."""
+    from fluidstructureinteraction_b200 import geometry, meshes, lsq
+    from fluidstructureinteraction_b200.solid import GpuSolidCase
+    t0 = time.perf_counter()
+    m = meshes.hex_box(nx, ny, nz)
+    geom = geometry.compute(m)
+    pt = {"fixed": "fixedDisplacement", "loaded": "tractionDisplacement", "free": "tractionDisplacement"}
+    L = lsq.build(m, geom, pt)
+    t_setup = time.perf_counter() - t0
+    mu, lam = cases.lame(cases.STEEL["E"], cases.STEEL["nu"])
+    nBF, nIF = m.nFaces - m.nInternalFaces, m.nInternalFaces
+    tr = np.zeros((nBF, 3)); p = m.patch("loaded")
+    tr[p["start"] - nIF:p["start"] - nIF + p["size"]] = TRACTION
+    c = GpuSolidCase(m, geom, pt, mu, lam, cases.STEEL["rho"], traction=tr, lsq=L)
+    c.evolve(1, 0.0, tolerance=TOL, relTol=RELTOL)                      # warm-up outer iteration
+    t1 = time.perf_counter()
+    r = c.evolve(nOuter, 0.0, tolerance=TOL, relTol=RELTOL)             # convergenceTolerance 0: exactly nOuter iterations
+    wall = time.perf_counter() - t1
+    tvp = c.gm.vol_to_point(reps=10)
+    c.close()
+    k = r["nOuterIterations"]
+    nP = m.nPoints
+    return {"workload": "hex cantilever %dx%dx%d, %d outer iterations of evolve() resident on the device" % (nx, ny, nz, k),
+            "outer_iterations": k, "pcg_iterations": int(r["totalPcgIterations"]),
+            "ms_per_outer_iteration": 1e3*wall/k, "assemble_ms": r["assemble_ms"]/k, "solve_ms": r["solve_ms"]/k,
+            "update_ms": r["update_ms"]/k, "host_bytes_per_outer_iteration": 48,
+            "vol_to_point": {"ms": tvp, "kernel": "k_lsq_interpolate", "points": nP,
+                             "algorithmic_bytes": int(L["entry"].shape[0]*28 + nP*(24 + 24 + 24 + 4 + 1) + 24*m.nCells + 24*nBF)},
+            "lsq_setup_s": t_setup}
 
 
 def measure_assembly(nx, ny, nz, peak):
@@ -255,18 +337,16 @@ def measure_8m(peak):
     x = np.zeros(n)
     g.solve(x, s["b"]*-1e4, 1e-9, 0.01, 0, 4)
     out = {"workload": "synthetic hex cantilever %dx%dx%d = %d cells" % (nx, ny, nz, n), "cells": n}
-    for k, nbytes in (("amul", cases.amul_bytes(n, nF)), ("dic", cases.dic_bytes(n, nF)), ("p_update", 24*n), ("xr_update", 48*n)):
-        t = g.time_kernel(k, reps=10, flushL2=True)
-        out[k] = {"ms": t, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes/t/1e6, "frac": nbytes/t/1e6/peak}
+    kb1, kb3 = kernel_bytes(n, nF, 1), kernel_bytes(n, nF, 3)
+    for k in ("amul", "dic", "p_update", "xr_update"):
+        out[k] = kernel_entry(g.time_kernel(k, reps=10, flushL2=True), 1, kb1[k], peak)
     # the batched kernels (what a D-equation solve runs): one launch advances the three component systems
     g.set_matrix_vector(np.ascontiguousarray(np.stack([s["diag"]]*3, axis=1)), s["upper"])
     if g.vector_mode(3) == 1:
         xv = np.zeros((n, 3))
         g.solve_vector(xv, np.ascontiguousarray(np.stack([s["b"]*t for t in TRACTION], axis=1)), 1e-9, 0.01, 0, 4, history=False)
-        for k, nbytes in (("amul", cases.amul_bytes(n, nF)), ("dic", cases.dic_bytes(n, nF)), ("p_update", 24*n), ("xr_update", 48*n)):
-            t = g.time_kernel_vector(3, k, reps=10, flushL2=True)
-            out[k + "_batched3"] = {"ms": t, "systems_per_launch": 3, "algorithmic_bytes": 3*nbytes,
-                                    "achieved_gbs": 3*nbytes/t/1e6, "frac": 3*nbytes/t/1e6/peak}
+        for k in ("amul", "dic", "p_update", "xr_update"):
+            out[k + "_batched3"] = kernel_entry(g.time_kernel_vector(3, k, reps=10, flushL2=True), 3, kb3[k], peak)
     g.close()
     del s
     out.update(measure_assembly(nx, ny, nz, peak))
@@ -411,46 +491,75 @@ def run_ours(args, nx, ny, nz):
     h2d = 3*8*n + 8*nF + 3*16*n          # diag per component + upper + x0 and b per component (either path)
     d2h = 3*8*n
 
+    # ---- the drop-in path an unmodified foam-extend reaches with `solver gpuPCG;` alone: fvMatrix<vector>::solve's own
+    #      component loop, i.e. 3 x (gpupcg_set_matrix + gpupcg_solve) with host buffers
+    dropin = None
+    if vector:
+        def step_scalar_e2e():
+            its = 0
+            for c in range(3):
+                g.set_matrix(h_diag, h_upper if c == 0 else None, patchBouCoeffs=bou)
+                h_x[c][:] = 0.0
+                perf, _ = g.solve(h_x[c], h_b[c], TOL, RELTOL, 0, 1000, history=False)
+                its += perf["nIterations"]
+            return its
+        step_scalar_e2e()
+        barrier()
+        e0.record()
+        its_s = 0
+        nS = max(1, min(args.steps, 3))
+        for _ in range(nS):
+            its_s += step_scalar_e2e()
+        e1.record()
+        barrier()
+        ms3 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
+        dropin = {"path": "3 x (gpupcg_set_matrix + gpupcg_solve), host buffers: what `solver gpuPCG;` in fvSolution gives without "
+                          "touching fvMatrix<Type>::solve", "value": nGlobal*its_s/(float(ms3.item())*1e-3), "unit": "cell-updates/s",
+                  "ms_per_step": float(ms3.item())/nS, "steps": nS, "iterations_per_step": its_s/nS}
+        g.set_matrix_vector(diagC, upper, patchBouCoeffsCmpt=bouC)      # back to the batched matrix for the kernel timings
+
     # ---- per-kernel roofline (rank 0, live CUDA-event timing on the launching stream, L2 flushed) --------------
     line = None
     if rank == 0:
         peak, peak_src = peaks()
         reps = 20
-        kb = {"amul": cases.amul_bytes(n, nF), "dic": cases.dic_bytes(n, nF), "p_update": 24*n, "xr_update": 48*n}
         batched = bool(vector and vmode == 1)
         nsys = 3 if batched else 1          # systems one launch advances
-        if not vector:
-            pass
-        elif not batched:
+        kb = kernel_bytes(n, nF, nsys)
+        if vector and not batched:
             g.set_matrix(diag, upper, patchBouCoeffs=bou)
         kern = {}
-        for k, nbytes in kb.items():
+        for k in ("amul", "dic", "p_update", "xr_update"):
             t = g.time_kernel_vector(3, k, reps=reps, flushL2=True) if batched else g.time_kernel(k, reps=reps, flushL2=True)
-            kern[k] = {"ms": t, "systems_per_launch": nsys, "algorithmic_bytes": nsys*nbytes,
-                       "achieved_gbs": nsys*nbytes/t/1e6, "frac": nsys*nbytes/t/1e6/peak}
-        # inside a solve the x/r update rides in the staging of the next forward sweep (no launch of its own): the
-        # iteration is amul + dic + p_update; k_xr_update is timed standalone for reference only
-        fused_xr = bool(info.get("sweepTables", 1)) and os.environ.get("GPUPCG_FUSE_XR", "1") != "0" and n <= 3000000
+            kern[k] = kernel_entry(t, nsys, kb[k], peak)
+        pencil = info["nTiles"] > 0 and info["tileRowsMax"] > 4096 and info["maxRounds"]*32 == info["tileRowsMax"]
+        # on the tile sweeps of small sub-domains the x/r update rides in the staging of the next forward sweep (no
+        # launch of its own); the pencil sweeps and large sub-domains run k_xr_update as a kernel of the iteration
+        fused_xr = (not pencil) and os.environ.get("GPUPCG_FUSE_XR", "1") != "0" and n <= 3000000
         tot = sum(v["ms"] for k, v in kern.items() if not (fused_xr and k == "xr_update"))
         for k, v in kern.items():
             v["share_of_iteration"] = None if (fused_xr and k == "xr_update") else v["ms"]/tot
         dom_k = max(kern, key=lambda k: kern[k]["ms"])
         sfx = "_v<3>" if batched else ""
+        sweep = ("k_dic_pencil<%d,0|2> forward + backward" % nsys) if pencil else ("k_dic_tile%s forward + backward" % sfx)
         names = {"amul": "k_amul_tile%s (lduMatrix::Amul + wApA)" % sfx,
-                 "dic": "k_dic_tile%s forward + backward (DIC precondition + wArA)" % sfx,
+                 "dic": sweep + " (DIC precondition + wArA)",
                  "p_update": "k_p_update%s" % sfx, "xr_update": "k_xr_update%s (+ sum|rA|)" % sfx}
-
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this
-        # workload (profiles/); only valid for the default 1 M-cell single-GPU case
-        ncu_traffic = {}
-        if world == 1 and (nx, ny, nz) == (200, 50, 100):
-            ncu_traffic = NCU_TRAFFIC_1M_VECTOR if batched else {"dic": 75.4e6 + 75.1e6, "amul": 71.4e6, "p_update": 16.0e6, "xr_update": 32.8e6}
+        traffic, traffic_src = ncu_traffic(nx, ny, nz, batched) if world == 1 else ({}, None)
 
         def roof(k):
-            return {"kernel": names[k], "bound": "hbm", "achieved": kern[k]["achieved_gbs"], "peak": peak,
-                    "unit": "GB/s", "frac": kern[k]["frac"], "traffic": ncu_traffic.get(k), "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": kern[k]["algorithmic_bytes"], "systems_per_launch": nsys,
-                    "ms_per_launch": kern[k]["ms"], "share_of_iteration": kern[k]["share_of_iteration"]}
+            r = {"kernel": names[k], "bound": "hbm", "achieved": kern[k]["achieved_gbs"], "peak": peak,
+                 "unit": "GB/s", "frac": kern[k]["frac"], "traffic": traffic.get(k),
+                 "traffic_source": traffic_src if traffic.get(k) is not None else None, "peak_source": peak_src,
+                 "algorithmic_bytes_per_launch": kern[k]["algorithmic_bytes"],
+                 "algorithmic_bytes_definition": ("%d systems sharing upper()/lduAddr(): SURVEY.md 8d per-system vector bytes x %d + the "
+                                                  "coefficient and label bytes once" % (nsys, nsys)) if nsys > 1 else "SURVEY.md 8d",
+                 "systems_per_launch": nsys, "ms_per_launch": kern[k]["ms"], "share_of_iteration": kern[k]["share_of_iteration"]}
+            if nsys > 1:
+                r["frac_as_independent_systems"] = kern[k]["frac_as_independent_systems"]
+            return r
 
         value = nGlobal*iters/(ms_dev*1e-3)
         line = {
@@ -461,32 +570,86 @@ def run_ours(args, nx, ny, nz):
                        "tolerance": TOL, "relTol": RELTOL, "solver": "gpuPCG", "preconditioner": "DIC",
                        "component_solves": ("batched: gpupcg_solve_vector, 3 systems per launch" if batched else
                                             "sequential: 3 x gpupcg_solve"),
+                       "sweeps": "streaming pencils (kernels_pencil.cuh)" if pencil else "tiles (kernels.cuh / kernels_vec.cuh)",
                        "parallelism": "1 sub-domain/GPU x %d" % world,
+                       "scaling_workload": ("N = 1 runs configs[1] (1 M cells, the config the metric is quoted on); N >= 2 run "
+                                            "configs[2] (64 M cells, strong scaling).  The 1 -> N curve of the 64 M-cell case "
+                                            "starts at scale_base_64M of the N = 1 line, not at its `value`."),
                        "l2": "working set (%.0f MB) vs 126 MB L2: inputs larger than L2 at >= 1M cells; kernel timings flush L2" %
                              (cases.pcg_iteration_bytes(n, nF)/1e6)},
             "solves_per_s": 3*args.steps/(ms_dev*1e-3), "iterations_per_step": iters/args.steps,
             "cells_per_gpu": n,
             "e2e": {"value": nGlobal*iters_e2e/(ms_e2e*1e-3), "unit": "cell-updates/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e/args.steps,
-                    "solves_per_s": 3*args.steps/(ms_e2e*1e-3)},
+                    "solves_per_s": 3*args.steps/(ms_e2e*1e-3),
+                    "path": "gpupcg_set_matrix_vector + gpupcg_solve_vector (pinned host buffers)" if vector else
+                            "3 x (gpupcg_set_matrix + gpupcg_solve)"},
+            "dropin_scalar_e2e": dropin,
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roof(dom_k), "roofline_amul": roof("amul"), "kernels": kern,
-            "plan": {k: info[k] for k in ("nRows", "nLevels", "maxLevelRows", "sweepGrid", "streamGrid")},
+            "plan": {k: info[k] for k in ("nRows", "nLevels", "maxLevelRows", "sweepGrid", "streamGrid", "nTiles")},
         }
         if world == 1 and nGlobal <= 4000000:
             line["assembly"] = measure_assembly(nx, ny, nz, peak)
-        if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(s, nGlobal, args.cpu_maxiter)
-        elif world == 1:
+        if not args.no_cpu_baseline:
+            if world == 1:
+                line["cpu_baseline"] = cpu_baseline(s, nGlobal, args.cpu_maxiter)
+            else:
+                # N > 1: the same serial port on the 1 M-cell cantilever (a rate; the 64 M-cell system does not fit a bounded sample)
+                s1 = build_system(200, 50, 100)
+                line["cpu_baseline"] = cpu_baseline(s1, s1["nCells"], 20)
+                line["cpu_baseline"]["sample"] += " -- 200x50x100 cantilever (rate comparison for the N > 1 lines)"
+        else:
             line["cpu_baseline"] = None
     g.close()
+    del g
     if world == 1 and rank == 0 and not args.no_8m and not args.cells:
         line["targets_8M"] = measure_8m(peak)
+    if world == 1 and rank == 0 and not args.no_evolve and nGlobal <= 4000000:
+        line["evolve"] = measure_evolve(nx, ny, nz)
+    if world == 1 and rank == 0 and not args.no_64m and not args.cells:
+        line["scale_base_64M"] = measure_64m(args)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
         emit(line)
+
+
+def measure_64m(args):
+    """configs[2] on ONE GPU: the 400^3 = 64 M-cell cantilever, batched three-component solve, device-resident --
+    the N = 1 point of the 64 M-cell strong-scaling curve (the N >= 2 lines run the same system decomposed)."""
+    import torch
+    import fluidstructureinteraction_b200 as pkg
+    nx, ny, nz = 400, 400, 400
+    s = build_system(nx, ny, nz)
+    n = s["nCells"]
+    g = pkg.GpuPCG(s["l"], s["u"], n)
+    g.set_stream(torch.cuda.current_stream().cuda_stream)
+    diagC = np.ascontiguousarray(np.stack([s["diag"]]*3, axis=1))
+    g.set_matrix_vector(diagC, s["upper"])
+    del diagC
+    d_b = torch.from_numpy(np.ascontiguousarray(np.stack([s["b"]*t for t in TRACTION], axis=1))).cuda()
+    d_x = torch.zeros((n, 3), dtype=torch.float64, device="cuda")
+    del s
+    steps = 3
+
+    def step():
+        d_x.zero_()
+        perfs, _ = g.solve_vector_device(3, d_x.data_ptr(), d_b.data_ptr(), TOL, RELTOL, 0, 1000)
+        return sum(p["nIterations"] for p in perfs)
+    step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    its = sum(step() for _ in range(steps))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    g.close()
+    return {"workload": workload_name(nx, ny, nz, 1).replace("configs[1]", "configs[2] on one GPU"), "cells": n, "n_gpus": 1,
+            "steps": steps, "warmup": 1, "value": n*its/(ms*1e-3), "unit": "cell-updates/s", "ms_per_step": ms/steps,
+            "iterations_per_step": its/steps}
 
 
 def main():

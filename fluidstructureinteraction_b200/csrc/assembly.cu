@@ -1637,7 +1637,7 @@ extern "C" int gpupcgi_mesh_outer_end(gpupcg_mesh m, const gpupcg_eqn_controls* 
     cudaStream_t s = m->stream;
     int rc = evaluate_resident(m); if (rc) return rc;
     if (doRelax && nb3 > 0) k_relax_boundary<<<agrid(m, nb3), ATPB, 0, s>>>(nb3, alpha, m->dDb, m->dDbPrev);
-    const int nb = std::min(1024, agrid(m, nC));
+    const int nb = std::min(1000, agrid(m, nC));        // partials: dRed[0, 1000) and dRed[1024, 2024); results at dRed[2040, 2048)
     k_relax_maxdd<<<nb, ATPB, 0, s>>>(nC, alpha, doRelax, m->dD, m->dDprev, m->dDold, m->dRed);
     k_residual<<<nb, ATPB, 0, s>>>(nC, nb, m->dD, m->dDprev, m->dRed, m->dRed + 1024);
     MCK(cudaGetLastError());
@@ -1649,7 +1649,7 @@ extern "C" int gpupcgi_mesh_outer_end(gpupcg_mesh m, const gpupcg_eqn_controls* 
     k_final_minmax<<<1, ATPB, 0, s>>>(nb, m->dRed, nullptr, out + 2);               // out[2] = maxDD
     if (detBounds)
     {
-        const int nbd = std::min(1016, agrid(m, M.nFaces));
+        const int nbd = std::min(1000, agrid(m, M.nFaces));
         k_det_minmax<<<nbd, ATPB, 0, s>>>(M, m->dGradDf, m->dRed, m->dRed + 1024);
         k_final_minmax<<<1, ATPB, 0, s>>>(nbd, m->dRed + 1024, m->dRed, out + 4);   // out[4] = maxDet, out[5] = minDet
     }

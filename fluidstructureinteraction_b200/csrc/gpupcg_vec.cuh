@@ -635,7 +635,10 @@ static int evolve_impl(gpupcg_handle h, gpupcg_mesh m, const gpupcg_evolve_contr
     int iCorr = 0, totalIts = 0;
     double r = 1.0, maxRes = 0.0, initialResidual = 0.0, lastInit = 0.0;
     float msA = 0.f, msS = 0.f, msE = 0.f, t = 0.f;
-    cudaEvent_t e0 = h->ev[0], e1 = h->ev[1], e2 = h->ev[2], e3 = h->ev[3];
+    // own events: the solve records h->ev[] itself
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2)); CK(cudaEventCreate(&e3));
+    struct EvGuard { cudaEvent_t a, b, c, d; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); cudaEventDestroy(c); cudaEventDestroy(d); } } evGuard{e0, e1, e2, e3};
     std::vector<gpupcg_perf> perf(NB);
     while (true)
     {
