@@ -136,6 +136,7 @@ SYMBOLS = {
     "gpupcg_mesh_set_field": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "gpupcg_mesh_get_field": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "gpupcg_mesh_set_lsq": (C.c_int, [C.c_void_p, c_int_p, c_int_p, c_double_p, c_double_p, C.POINTER(C.c_ubyte)]),
+    "gpupcg_mesh_set_point_constraints": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p, c_int_p, c_double_p]),
     "gpupcg_vol_to_point": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "gpupcg_patch_evaluate": (C.c_int, [C.c_void_p]),
     "gpupcg_assemble_D_resident": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p]),
@@ -396,7 +397,8 @@ class GpuPCG(object):
         self._check(self.lib.gpupcg_comm_init(self.h, rank, nRanks, buf))
 
 
-PATCH_TYPES = {"tractionDisplacement": 0, "fixedDisplacement": 1, "symmetryDisplacement": 2, "symmetryPlane": 3, "empty": 4}
+PATCH_TYPES = {"tractionDisplacement": 0, "fixedDisplacement": 1, "symmetryDisplacement": 2, "symmetryPlane": 3, "empty": 4,
+               "fixedValue": 5}
 
 FIELD_IDS = dict(mu=0, lambda_=1, rho=2, D=3, Dold=4, Doldold=5, gradD=6, gradDf=7, traction=8, pressure=9, fixedValue=10,
                  threeK=11, alpha=12, DT=13, DTb=14, pointD=15, Db=16, gradDb=17, U=18, epsilon=19, sigma=20, upper=21,
@@ -520,6 +522,11 @@ class GpuMesh(object):
         out = np.empty(self._field_shape(name))
         self._check(self.lib.gpupcg_mesh_get_field(self.h, FIELD_IDS[name], _dp(out)))
         return out
+
+    def set_point_constraints(self, pc):
+        """pc: dict(point, start, kind, vec) -- the point patch fields of pointD (lsq.point_constraints)."""
+        pt, st, kd, vc = _i32(pc["point"]), _i32(pc["start"]), _i32(pc["kind"]), _f64(pc["vec"])
+        self._check(self.lib.gpupcg_mesh_set_point_constraints(self.h, int(pt.shape[0]), _ip(pt), _ip(st), _ip(kd), _dp(vc)))
 
     def set_lsq(self, lsq):
         """lsq: dict(start, entry, inv, origin, mirror) -- what leastSquaresVolPointInterpolation holds (lsq.build)."""

@@ -161,3 +161,162 @@ def scalar_laplacian_system(mesh, geom, gamma, fixedValue=None, refCell=None, re
         source[refCell] += diag[refCell]*refValue
         diag[refCell] += diag[refCell]
     return dict(l=l, u=u, diag=diag, upper=np.ascontiguousarray(upper), source=source, patches=patches, sign=sgn)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# config 1: the shipped run/stressFoam/plateHole case and its analytical (Kirsch) solution
+# ---------------------------------------------------------------------------------------------------------------------
+PLATE_HOLE = dict(T=10000.0, a=0.5, E=2.0e11, nu=0.3, rho=7854.0, planeStress=True,
+                  # constant/stressProperties:19-26, system/fvSolution:18-27, system/fvSchemes:49-56
+                  nCorrectors=1000, convergenceTolerance=1e-8, tolerance=1e-9, relTol=0.01, limitCoeff=1.0,
+                  # 0/D:19-62 (the tractions are overwritten by setPlateHoleBC::setBC at start-up)
+                  patchTypes={"left": "symmetryDisplacement", "right": "tractionDisplacement", "down": "symmetryDisplacement",
+                              "up": "tractionDisplacement", "hole": "tractionDisplacement", "frontAndBack": "empty"},
+                  # 0/pointD:19-50
+                  pointPatchTypes={"left": "symmetryPlane", "right": "calculated", "down": "symmetryPlane", "up": "calculated",
+                                   "hole": "calculated", "frontAndBack": "empty"})
+
+
+def kirsch_stress(C, T=10000.0, a=0.5):
+    """setPlateHoleBC::plateHoleStress (run/stressFoam/plateHole/setPlateHoleBC/setPlateHoleBC.C:57-113): the stress of an
+    infinite plate with a circular hole of radius a under uniaxial tension T along x.  C (n,3) -> (n,6) symmTensor
+    (xx xy xz yy yz zz)."""
+    C = np.atleast_2d(np.asarray(C, dtype=np.float64))
+    r = np.sqrt(C[:, 0]**2 + C[:, 1]**2)
+    th = np.arctan2(C[:, 1], C[:, 0])
+    a2r2 = a**2/r**2
+    a4r4 = 3.0*a**4/(2.0*r**4)
+    s = np.zeros((C.shape[0], 6))
+    s[:, 0] = T*(1.0 - a2r2*(3.0*np.cos(2*th)/2.0 + np.cos(4*th)) + a4r4*np.cos(4*th))
+    s[:, 3] = T*(-a2r2*(np.cos(2*th)/2.0 - np.cos(4*th)) - a4r4*np.cos(4*th))
+    s[:, 1] = T*(-a2r2*(np.sin(2*th)/2.0 + np.sin(4*th)) + a4r4*np.sin(4*th))
+    return s
+
+
+def kirsch_displacement(C, T=10000.0, a=0.5, E=2.0e11, nu=0.3):
+    """setPlateHoleBC::plateHoleDisplacement (setPlateHoleBC.C:116-152), plane stress: kappa = (3 - nu)/(1 + nu)."""
+    C = np.atleast_2d(np.asarray(C, dtype=np.float64))
+    mu = E/(2.0*(1.0 + nu))
+    kappa = (3.0 - nu)/(1.0 + nu)
+    r = np.sqrt(C[:, 0]**2 + C[:, 1]**2)
+    th = np.arctan2(C[:, 1], C[:, 0])
+    d = np.zeros((C.shape[0], 3))
+    d[:, 0] = (a*T/(8.0*mu))*((r/a)*(kappa + 1.0)*np.cos(th) + (2.0*a/r)*((1.0 + kappa)*np.cos(th) + np.cos(3*th))
+                              - (2.0*a**3/r**3)*np.cos(3*th))
+    d[:, 1] = (a*T/(8.0*mu))*((r/a)*(kappa - 3.0)*np.sin(th) + (2.0*a/r)*((1.0 - kappa)*np.sin(th) + np.sin(3*th))
+                              - (2.0*a**3/r**3)*np.sin(3*th))
+    return d
+
+
+def plate_hole_tractions(mesh, geom, patchTypes):
+    """setPlateHoleBC::setBC (setPlateHoleBC.C:202-247): on every tractionDisplacement patch traction = nf & sigma(Cf) with
+    the z of Cf dropped; on `hole` the stress is evaluated at the face centre projected onto the circle r = 0.5."""
+    nIF = mesh.nInternalFaces
+    tr = np.zeros((mesh.nFaces - nIF, 3))
+    for p in mesh.patches:
+        if patchTypes[p["name"]] != "tractionDisplacement":
+            continue
+        fs = slice(p["start"], p["start"] + p["size"])
+        nf = geom.Sf[fs]/geom.magSf[fs, None]
+        C = geom.Cf[fs].copy(); C[:, 2] = 0.0
+        if p["name"] == "hole":
+            C = C/np.sqrt(np.sum(C*C, axis=1))[:, None]
+            C = C*0.5
+        s = kirsch_stress(C)
+        tr[p["start"] - nIF:p["start"] - nIF + p["size"]] = np.stack(
+            [nf[:, 0]*s[:, 0] + nf[:, 1]*s[:, 1] + nf[:, 2]*s[:, 2],
+             nf[:, 0]*s[:, 1] + nf[:, 1]*s[:, 3] + nf[:, 2]*s[:, 4],
+             nf[:, 0]*s[:, 2] + nf[:, 1]*s[:, 4] + nf[:, 2]*s[:, 5]], axis=1)
+    return tr
+
+
+def plate_hole_errors(mesh, geom, D, pointD, sigma):
+    """setPlateHoleBC::calcError (setPlateHoleBC.C:250-388): max |D - Da| over cells, max |pointD - Da| over points, max
+    |sigma_ij - sigma_a,ij| over cells for xx, xy, yy (sigma (n,6) symmTensor)."""
+    C = geom.C.copy(); C[:, 2] = 0.0
+    Da = kirsch_displacement(C)
+    P = mesh.points.copy(); P[:, 2] = 0.0
+    Pa = kirsch_displacement(P)
+    sa = kirsch_stress(C)
+    return dict(DError=float(np.sqrt(np.sum((D - Da)**2, axis=1)).max()),
+                pointDError=float(np.sqrt(np.sum((pointD - Pa)**2, axis=1)).max()),
+                sigmaXXErr=float(np.abs(sigma[:, 0] - sa[:, 0]).max()), sigmaXYErr=float(np.abs(sigma[:, 1] - sa[:, 1]).max()),
+                sigmaYYErr=float(np.abs(sigma[:, 3] - sa[:, 3]).max()),
+                DMax=float(np.sqrt(np.sum(Da**2, axis=1)).max()), sigmaXXMax=float(np.abs(sa[:, 0]).max()))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# shipped solid cases: the settings unsTotalLagrangianStress reads from the case dictionaries
+# ---------------------------------------------------------------------------------------------------------------------
+def solid_case_settings(d):
+    """d = dict(D, pointD, rheologyProperties, stressProperties, fvSolution, fvSchemes, controlDict) as foamdict.parse
+    returns them.  -> the arguments of a solid case (GpuSolidCase / the oracle's SolidCase) and of its evolve():
+    unsTotalLagrangianStress.C:59-183 (constructor: rheology, stressProperties), :769-845 (evolve: nCorrectors,
+    convergenceTolerance, relConvergenceTolerance, nonLinear), fvSolution solvers.D / relaxationFactors.D, fvSchemes
+    d2dt2(D) / ddt(D) / snGrad(D)."""
+    from . import foamdict as fd
+    rh = d["rheologyProperties"]
+    coeffs = d["stressProperties"][str(d["stressProperties"]["stressModel"]) + "Coeffs"]
+    sol = d["fvSolution"]["solvers"]["D"]
+    if str(sol["solver"]) not in ("PCG", "gpuPCG") or str(sol.get("preconditioner", "DIC")) != "DIC":
+        raise ValueError("solvers.D is not PCG/DIC: %r" % (sol,))
+    sch = d["fvSchemes"]
+
+    def scheme(group, key):
+        g = sch.get(group, {})
+        v = g.get(key, g.get("default", "none"))
+        return v if isinstance(v, list) else [v]
+
+    sn = scheme("snGradSchemes", "snGrad(D)")
+    lap = scheme("laplacianSchemes", "laplacian(DD,D)")
+    if lap[:2] != ["Gauss", "linear"] or lap[2:] != sn:
+        raise ValueError("laplacian(DD,D) %r does not match snGrad(D) %r" % (lap, sn))
+    if sn[0] == "skewCorrected":
+        limitCoeff = float(sn[1])
+    elif sn[0] == "corrected":
+        # [EXT] correctedSnGrad: not restated; it and skewCorrected 1 both vanish (to rounding) on an orthogonal mesh such
+        # as the beamInCrossFlow solid -- the caller checks the mesh (oracle/ASSUMPTIONS.md #11)
+        limitCoeff = 1.0
+    else:
+        raise ValueError("unsupported snGrad(D) scheme %r" % (sn,))
+    out = dict(E=fd.dimensioned(rh["rheology"]["E"]), nu=fd.dimensioned(rh["rheology"]["nu"]), rho=fd.dimensioned(rh["rheology"]["rho"]),
+               planeStress=fd.switch(rh["planeStress"]), nCorrectors=int(coeffs["nCorrectors"]),
+               convergenceTolerance=float(coeffs["convergenceTolerance"]),
+               relConvergenceTolerance=float(coeffs.get("relConvergenceTolerance", 0.0)),
+               nonLinear=fd.switch(coeffs.get("nonLinear", "no")), tolerance=float(sol.get("tolerance", 1e-6)),
+               relTol=float(sol.get("relTol", 0.0)), maxIter=int(sol.get("maxIter", 1000)),
+               relaxD=(float(d["fvSolution"].get("relaxationFactors", {})["D"]) if "D" in d["fvSolution"].get("relaxationFactors", {}) else None),
+               d2dt2=str(scheme("d2dt2Schemes", "d2dt2(D)")[0]), ddt=str(scheme("ddtSchemes", "ddt(D)")[0]),
+               snGradScheme=str(sn[0]), limitCoeff=limitCoeff, deltaT=float(d["controlDict"]["deltaT"]),
+               patchTypes={}, pointPatchTypes={}, traction={}, pressure={}, fixedValue={})
+    for name, b in d["D"]["boundaryField"].items():
+        t = str(b["type"])
+        out["patchTypes"][name] = t
+        if t == "tractionDisplacement":
+            out["traction"][name] = fd.uniform(b["traction"], 1, 3)[0]
+            out["pressure"][name] = fd.uniform(b["pressure"], 1, 1)[0][0]
+        elif t in ("fixedDisplacement", "fixedValue"):
+            out["fixedValue"][name] = fd.uniform(b["value"], 1, 3)[0]
+    for name, b in d["pointD"]["boundaryField"].items():
+        out["pointPatchTypes"][name] = str(b["type"])
+    return out
+
+
+def boundary_fields(mesh, settings, traction=None, pressure=None):
+    """Per-boundary-face traction (nBF,3), pressure (nBF,), fixedValue (nBF,3) from the patch-wise `uniform` entries of
+    0/D; `traction` / `pressure` = {patch: value} override the dictionary (the load a fluid or a function object sets)."""
+    nIF = mesh.nInternalFaces
+    nBF = mesh.nFaces - nIF
+    tr, pr, fv = np.zeros((nBF, 3)), np.zeros(nBF), np.zeros((nBF, 3))
+    for p in mesh.patches:
+        s = slice(p["start"] - nIF, p["start"] - nIF + p["size"])
+        n = p["name"]
+        if n in settings["traction"]:
+            tr[s] = settings["traction"][n]; pr[s] = settings["pressure"][n]
+        if traction and n in traction:
+            tr[s] = traction[n]
+        if pressure and n in pressure:
+            pr[s] = pressure[n]
+        if n in settings["fixedValue"]:
+            fv[s] = settings["fixedValue"][n]
+    return tr, pr, fv

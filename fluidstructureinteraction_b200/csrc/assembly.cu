@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(ATPB) k_asm_patches(MeshDev M, AsmCtl T, const
         }
 #pragma unroll
         for (int d = 0; d < 3; d++) n[d] = dvd(Sf[d], magSf);
-        if (ptype == 1)
+        if (ptype == 1 || ptype == 5)
         {
             double delta[3], k[3], kg[3], G[9];
 #pragma unroll
@@ -334,6 +334,7 @@ __global__ void __launch_bounds__(ATPB) k_asm_patches(MeshDev M, AsmCtl T, const
 #pragma unroll
             for (int q = 0; q < 9; q++) G[q] = gradD[9*(size_t)c + q];
             vdotT(k, G, kg);
+            if (ptype == 5) kg[0] = kg[1] = kg[2] = 0.0;        // [EXT] fixedValueFvPatchField: no non-orthogonal term
 #pragma unroll
             for (int d = 0; d < 3; d++)
             {
@@ -653,7 +654,7 @@ __device__ void patch_snGrad(const MeshDev& M, int f, const double* __restrict__
                              const double* __restrict__ fixedValue, const double* __restrict__ patchGradient, double* sn)
 {
     const int bf = f - M.nIF, c = M.owner[f];
-    if (M.bfPatchType[bf] == 1)
+    if (M.bfPatchType[bf] == 1 || M.bfPatchType[bf] == 5)
     {
         double n[3], delta[3], k[3], kg[3], G[9];
         const double magSf = M.magSf[f];
@@ -665,6 +666,7 @@ __device__ void patch_snGrad(const MeshDev& M, int f, const double* __restrict__
 #pragma unroll
         for (int q = 0; q < 9; q++) G[q] = gradD[9*(size_t)c + q];
         vdotT(k, G, kg);
+        if (M.bfPatchType[bf] == 5) kg[0] = kg[1] = kg[2] = 0.0;   // [EXT] fixedValueFvPatchField::snGrad
 #pragma unroll
         for (int d = 0; d < 3; d++) sn[d] = mul(sub(fixedValue[3*(size_t)bf + d], add(D[3*(size_t)c + d], kg[d])), M.deltaCoeffs[f]);
     }
@@ -856,6 +858,7 @@ struct gpupcg_mesh_s
     double *dFluxX = nullptr, *dFluxY = nullptr, *dFluxT = nullptr;
     bool haveDold = false, haveDoldold = false, haveThermal = false, haveDb = false;
     LsqDev lsq{};                                  // leastSquaresVolPointInterpolation data (gpupcg_mesh_set_lsq)
+    PointBcDev pointBc{};                          // point patch fields of pointD (gpupcg_mesh_set_point_constraints)
     double* hScal = nullptr;                       // pinned: {residual, maxDD, minDet, maxDet}
     // chunked assembly: the per-face fluxes of one chunk live in a ring sized to stay in L2 between the face and the cell kernel
     std::vector<AsmChunk> chunks;
@@ -939,11 +942,11 @@ extern "C" int gpupcg_mesh_create(gpupcg_mesh* out, int device, int nCells, int 
             g_meshErr = "gpupcg_mesh_create: patch " + std::to_string(p) + " lies outside the boundary faces [nInternalFaces, nFaces)";
             return GPUPCG_ERR_ARG;
         }
-        if (patchType[p] < 0 || patchType[p] > 4)
+        if (patchType[p] < 0 || patchType[p] > 5)
         {
             // anything else (processor, cyclic, solidTraction, ...) would silently get tractionDisplacement coefficients
             g_meshErr = "gpupcg_mesh_create: patch " + std::to_string(p) + " has patchType " + std::to_string(patchType[p]) +
-                        " (supported: 0 tractionDisplacement, 1 fixedDisplacement, 2 symmetryDisplacement, 3 symmetryPlane, 4 empty)";
+                        " (supported: 0 tractionDisplacement, 1 fixedDisplacement, 2 symmetryDisplacement, 3 symmetryPlane, 4 empty, 5 fixedValue)";
             return GPUPCG_ERR_UNSUPPORTED;
         }
     }
@@ -1441,6 +1444,34 @@ extern "C" int gpupcg_mesh_set_lsq(gpupcg_mesh m, const int* pointStart, const i
     return GPUPCG_OK;
 }
 
+// The point patch fields of pointD that act in pf.correctBoundaryConditions() at the end of interpolate()
+// (leastSquaresVolPointInterpolate.C:301): symmetryPlane (kind 1, vec = the patch's point normal) and fixedValue (kind 2).
+extern "C" int gpupcg_mesh_set_point_constraints(gpupcg_mesh m, int nConstrained, const int* point, const int* start,
+                                                 const int* kind, const double* vec)
+{
+    if (!m || nConstrained < 0 || (nConstrained > 0 && (!point || !start || !kind || !vec))) return GPUPCG_ERR_ARG;
+    if (!m->M.points) { m->err = "gpupcg_mesh_set_point_constraints: gpupcg_mesh_set_points has not been called"; return GPUPCG_ERR_STATE; }
+    PointBcDev& B = m->pointBc;
+    B.n = 0;
+    if (nConstrained == 0) return GPUPCG_OK;
+    if (start[0] != 0) { m->err = "gpupcg_mesh_set_point_constraints: start[0] != 0"; return GPUPCG_ERR_ARG; }
+    for (int i = 0; i < nConstrained; i++)
+    {
+        if (point[i] < 0 || point[i] >= m->M.nPoints || start[i + 1] < start[i] || (i > 0 && point[i] <= point[i - 1]))
+        { m->err = "gpupcg_mesh_set_point_constraints: points must be distinct, ascending and in range, start ascending"; return GPUPCG_ERR_ARG; }
+    }
+    const int rows = start[nConstrained];
+    for (int r = 0; r < rows; r++)
+        if (kind[r] != 1 && kind[r] != 2)
+        { m->err = "gpupcg_mesh_set_point_constraints: kind must be 1 (symmetryPlane) or 2 (fixedValue)"; return GPUPCG_ERR_UNSUPPORTED; }
+    MCK(cudaSetDevice(m->device));
+    MCK(up(m, B.point, point, (size_t)nConstrained)); MCK(up(m, B.start, start, (size_t)nConstrained + 1));
+    MCK(up(m, B.kind, kind, (size_t)rows)); MCK(up(m, B.vec, vec, 3*(size_t)rows));
+    MCK(cudaStreamSynchronize(m->stream));
+    B.n = nConstrained;
+    return GPUPCG_OK;
+}
+
 // runTime++ : D.storeOldTimes()  ->  D.oldTime().oldTime() = D.oldTime(); D.oldTime() = D
 extern "C" int gpupcg_mesh_new_time_step(gpupcg_mesh m)
 {
@@ -1543,6 +1574,11 @@ static int vol_to_point_resident(gpupcg_mesh m)
     if (!m->haveDb) { m->err = "no boundary values of D on the device (gpupcg_patch_evaluate / set_field DB first)"; return GPUPCG_ERR_STATE; }
     k_lsq_interpolate<<<agrid(m, m->M.nPoints), ATPB, 0, m->stream>>>(m->lsq, m->M.points, m->dD, m->dDb, m->dPointD);
     MCK(cudaGetLastError());
+    if (m->pointBc.n > 0)
+    {
+        k_point_constraints<<<agrid(m, m->pointBc.n), ATPB, 0, m->stream>>>(m->pointBc, m->dPointD);
+        MCK(cudaGetLastError());
+    }
     return GPUPCG_OK;
 }
 

@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(ATPB) k_patch_evaluate(MeshDev M, const double
     {
         const int pt = M.bfPatchType[bf];
         if (pt == 4) continue;
-        if (pt == 1)
+        if (pt == 1 || pt == 5)
         {
 #pragma unroll
             for (int d = 0; d < 3; d++) Db[3*(size_t)bf + d] = fixedValue[3*(size_t)bf + d];
@@ -344,6 +344,14 @@ struct LsqDev
     const unsigned char* mirror;
 };
 
+// point patch fields of pointD that act in pf.correctBoundaryConditions() (leastSquaresVolPointInterpolate.C:301)
+struct PointBcDev
+{
+    int n;                          // constrained points
+    const int *point, *start, *kind;
+    const double* vec;              // [rows][3]: nHat (kind 1, symmetryPlane) or the value (kind 2, fixedValue)
+};
+
 __device__ __forceinline__ void identity_transform(const double* v, double* r)
 {
     r[0] = add(add(mul(1.0, v[0]), mul(0.0, v[1])), mul(0.0, v[2]));
@@ -400,6 +408,31 @@ __global__ void __launch_bounds__(ATPB) k_lsq_interpolate(LsqDev L, const double
 #pragma unroll
         for (int d = 0; d < 3; d++)
             pointD[3*(size_t)p + d] = add(add(add(avg[d], mul(co[0][d], dr[0])), mul(co[1][d], dr[1])), mul(co[2][d], dr[2]));
+    }
+}
+
+// ---- pf.correctBoundaryConditions(): one thread per constrained point, its patches in boundary order -----------------
+//   symmetryPlane [EXT SymmetryPointPatchField::evaluate]  pf = transform(I - nHat*nHat, pf)
+//   fixedValue    [EXT ValuePointPatchField::evaluate]     pf = value
+__global__ void __launch_bounds__(ATPB) k_point_constraints(PointBcDev B, double* __restrict__ pointD)
+{
+    for (int i = blockIdx.x*ATPB + threadIdx.x; i < B.n; i += gridDim.x*ATPB)
+    {
+        double* v = pointD + 3*(size_t)B.point[i];
+        double x = v[0], y = v[1], z = v[2];
+        for (int r = B.start[i]; r < B.start[i + 1]; r++)
+        {
+            const double a0 = B.vec[3*(size_t)r], a1 = B.vec[3*(size_t)r + 1], a2 = B.vec[3*(size_t)r + 2];
+            if (B.kind[r] == 2) { x = a0; y = a1; z = a2; continue; }
+            const double T0 = sub(1.0, mul(a0, a0)), T1 = -mul(a0, a1), T2 = -mul(a0, a2);
+            const double T3 = -mul(a1, a0), T4 = sub(1.0, mul(a1, a1)), T5 = -mul(a1, a2);
+            const double T6 = -mul(a2, a0), T7 = -mul(a2, a1), T8 = sub(1.0, mul(a2, a2));
+            const double nx = add(add(mul(T0, x), mul(T1, y)), mul(T2, z));
+            const double ny = add(add(mul(T3, x), mul(T4, y)), mul(T5, z));
+            const double nz = add(add(mul(T6, x), mul(T7, y)), mul(T8, z));
+            x = nx; y = ny; z = nz;
+        }
+        v[0] = x; v[1] = y; v[2] = z;
     }
 }
 

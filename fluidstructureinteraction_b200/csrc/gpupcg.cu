@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 #include "kernels_vec.cuh"
 #include "kernels_pencil.cuh"
+#include "kernels_ordered.cuh"
 #include "plan.h"
 #include "comm.h"
 
@@ -36,6 +37,8 @@ struct gpupcg_handle_s
     // plan (device)
     SliceInfo* dSlices = nullptr;
     int *dUfaceOld = nullptr, *dRowOld = nullptr;
+    int* dPos = nullptr;            // [nCells] cell -> row, only in the ordered-sums verification mode
+    bool orderedSums = false;       // GPUPCG_ORDERED_SUMS=1 at create: global sums in the caller's cell order (kernels_ordered.cuh)
     int *dIfRow = nullptr, *dIfRowStart = nullptr, *dIfEntry = nullptr, *dIfFaceRow = nullptr;
     unsigned int* dIfMask = nullptr;
     int nIfRows = 0;
@@ -198,7 +201,7 @@ extern "C" int gpupcg_destroy(gpupcg_handle h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->comm.destroy();
-    void* ptrs[] = {h->dSlices, h->dUfaceOld, h->dRowOld, h->dIfRow,
+    void* ptrs[] = {h->dSlices, h->dUfaceOld, h->dRowOld, h->dPos, h->dIfRow,
                     h->dIfRowStart, h->dIfEntry, h->dIfFaceRow, h->dIfMask, h->dDiag, h->dUval, h->dRD,
                     h->dX, h->dB, h->dRA, h->dWA, h->dPA, h->dY, h->dStageA, h->dStageB, h->dStageF,
                     h->dBou, h->dXNbr, h->dSend, h->dPartials, h->dHistory, h->dState, h->dFlush,
@@ -466,6 +469,8 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     CK(upload(h->dSlices, P.slices, s));
     CK(upload(h->dUfaceOld, P.UfaceOld, s));
     CK(upload(h->dRowOld, P.rowOld, s));
+    h->orderedSums = env_int("GPUPCG_ORDERED_SUMS", 0) != 0;
+    if (h->orderedSums) CK(upload(h->dPos, P.pos, s));
     CK(upload(h->dIfRow, P.ifRow, s));
     CK(upload(h->dIfRowStart, P.ifRowStart, s));
     CK(upload(h->dIfEntry, P.ifEntry, s));
@@ -774,6 +779,14 @@ static int halo_exchange(gpupcg_handle h, const double* x, bool* overlapped)
 
 static int allreduce_step(gpupcg_handle h, int step, int count)
 {
+    if (h->orderedSums)
+    {
+        // verification mode: the kernel before this call skipped its tree reduction; form the sums in cell order here
+        const OrderedVecs V{h->dX, h->dB, h->dRA, h->dWA, h->dPA};
+        h->launches++;
+        k_ordered_step<1, 1><<<1, ORD_TPB, 0, h->stream>>>(h->dState, step, V, h->dPos, h->plan.nCells, h->dHistory, 0);
+        CK(cudaGetLastError());
+    }
     if (!h->comm.active()) return GPUPCG_OK;
     if (h->dP2P) return GPUPCG_OK;      // summed across ranks inside the kernel that finished the reduction
     if (h->comm.allreduce_sum((double*)((char*)h->dState + offsetof(DevState, red)), count, h->stream, h->err) != 0)
@@ -975,6 +988,7 @@ static int solve_core(gpupcg_handle h, double tol, double relTol, int minIter, i
     init.historyCap = std::min(h->historyCap, std::max(0, maxIter));
     init.multiRank = h->comm.active() ? 1 : 0;
     init.p2p = h->comm.active() ? h->dP2P : nullptr;
+    init.ordered = h->orderedSums ? 1 : 0;
     init.wArA = K_MGREAT; init.wArAold = K_MGREAT;
     *h->hState = init;
     CK(cudaMemcpyAsync(h->dState, h->hState, sizeof(DevState), cudaMemcpyHostToDevice, s));

@@ -130,6 +130,19 @@ int vec_set_matrix_device(gpupcg_handle h, const double* d_diagC, const double* 
     return GPUPCG_OK;
 }
 
+// verification mode (GPUPCG_ORDERED_SUMS): the kernel launched just before skipped its tree reduction; form the sums of
+// every component in the caller's cell order and advance the scalar recurrences (kernels_ordered.cuh)
+template <int NB>
+int vec_ordered_step(gpupcg_handle h, int step)
+{
+    if (!h->orderedSums) return GPUPCG_OK;
+    const OrderedVecs V{h->vX, h->vB, h->vRA, h->vWA, h->vPA};
+    h->launches++;
+    k_ordered_step<NB, VecStride<NB>::v><<<1, ORD_TPB, 0, h->stream>>>(h->vState, step, V, h->dPos, h->plan.nCells, h->vHistory, h->historyCap);
+    CK(cudaGetLastError());
+    return GPUPCG_OK;
+}
+
 template <int NB>
 int vec_halo(gpupcg_handle h, const double* x, bool* overlapped)
 {
@@ -227,6 +240,7 @@ int vec_sweeps(gpupcg_handle h, double* rA, double* z, bool reduce, int gated, b
         rcp = launch_pencil<NB, 0>(h, h->vRD, rA, nullptr, yb, nullptr, nullptr, h->vState, gated); if (rcp) return rcp;
         rcp = launch_pencil<NB, 2>(h, h->vRD, rA, yb, zb, nullptr, reduce ? h->vPartials : nullptr, h->vState, gated); if (rcp) return rcp;
         CK(cudaGetLastError());
+        if (reduce) return vec_ordered_step<NB>(h, S_SWEEP);
         return GPUPCG_OK;
     }
     const FuseXR fx = fuseXR ? FuseXR{h->vX, h->vPA, zb, h->vRA, h->vHistory} : none;
@@ -237,6 +251,7 @@ int vec_sweeps(gpupcg_handle h, double* rA, double* z, bool reduce, int gated, b
     {
         k_dic_tile_v<NB, 0, true><<<h->sweepGrid, SWEEP_TPB, smF, h->stream>>>(h->tiles, h->vRD, rA, nullptr, yb, nullptr,
             h->dTileTicket, h->vPartials, h->partStride, h->vState, gated, h->dTabCF, h->dTabUF, fx, h->historyCap);
+        if (fuseXR) { int rco = vec_ordered_step<NB>(h, S_XR); if (rco) return rco; }
         k_dic_tile_v<NB, 2, true><<<h->sweepGrid, SWEEP_TPB, h->smemBwdV, h->stream>>>(h->tiles, h->vRD, rA, yb, zb, nullptr,
             h->dTileTicket, part, h->partStride, h->vState, gated, h->dTabCB, h->dTabUB, none, 0);
     }
@@ -244,10 +259,12 @@ int vec_sweeps(gpupcg_handle h, double* rA, double* z, bool reduce, int gated, b
     {
         k_dic_tile_v<NB, 0, false><<<h->sweepGrid, SWEEP_TPB, smF, h->stream>>>(h->tiles, h->vRD, rA, nullptr, yb, nullptr,
             h->dTileTicket, h->vPartials, h->partStride, h->vState, gated, h->dTabCF, h->dTabUF, fx, h->historyCap);
+        if (fuseXR) { int rco = vec_ordered_step<NB>(h, S_XR); if (rco) return rco; }
         k_dic_tile_v<NB, 2, false><<<h->sweepGrid, SWEEP_TPB, h->smemBwdV, h->stream>>>(h->tiles, h->vRD, rA, yb, zb, nullptr,
             h->dTileTicket, part, h->partStride, h->vState, gated, h->dTabCB, h->dTabUB, none, 0);
     }
     CK(cudaGetLastError());
+    if (reduce) return vec_ordered_step<NB>(h, S_SWEEP);
     return GPUPCG_OK;
 }
 
@@ -269,6 +286,7 @@ int vec_solve_core(gpupcg_handle h, double tol, double relTol, int minIter, int 
     init.historyCap = std::min(h->historyCap, std::max(0, maxIter));
     init.multiRank = h->comm.active() ? 1 : 0;
     init.p2p = h->comm.active() ? h->dP2P : nullptr;
+    init.ordered = h->orderedSums ? 1 : 0;
     init.wArA = K_MGREAT; init.wArAold = K_MGREAT;
     DevState* fin = h->hvRing + 2*NB;
     for (int k = 0; k < NB; k++) fin[k] = init;
@@ -277,8 +295,10 @@ int vec_solve_core(gpupcg_handle h, double tol, double relTol, int minIter, int 
 
     rc = vec_amul<NB>(h, 0, h->vX, h->vWA, false); if (rc) return rc;
     LAUNCH((k_init_residual_v<NB>), gN, s, h->vB, h->vWA, h->vX, h->vRA, nFlat, h->vPartials, h->vState);
+    rc = vec_ordered_step<NB>(h, S_INIT); if (rc) return rc;
     rc = vec_amul<NB>(h, 2, h->vX, h->vPA, false); if (rc) return rc;
     LAUNCH((k_norm_v<NB>), gN, s, h->vWA, h->vPA, h->vB, h->vRA, nFlat, h->vPartials, h->vState);
+    rc = vec_ordered_step<NB>(h, S_NORM); if (rc) return rc;
     rc = vec_factor<NB>(h, 1); if (rc) return rc;
     vec_fill_sent<NB>(h, h->vWA);
     CK(cudaGetLastError());
@@ -309,9 +329,13 @@ int vec_solve_core(gpupcg_handle h, double tol, double relTol, int minIter, int 
                 rc = vec_sweeps<NB>(h, h->vRA, h->vWA, true, 1, fuseXR); if (rc) return rc;
                 LAUNCH((k_p_update_v<NB>), gN, s, h->vWA, h->vPA, nFlat, h->vState);
                 rc = vec_amul<NB>(h, 1, h->vPA, h->vWA, false); if (rc) return rc;
+                rc = vec_ordered_step<NB>(h, S_AMUL); if (rc) return rc;
                 if (!fuseXR)
+                {
                     LAUNCH((k_xr_update_v<NB>), gN, s, h->vPA, (unsigned long long*)h->vWA, h->vX, h->vRA, nFlat, h->vPartials,
                            h->vState, h->vHistory, h->historyCap);
+                    rc = vec_ordered_step<NB>(h, S_XR); if (rc) return rc;
+                }
             }
             CK(cudaGetLastError());
             launched += n;
@@ -329,6 +353,7 @@ int vec_solve_core(gpupcg_handle h, double tol, double relTol, int minIter, int 
     // the update of the last iteration launched has not been applied if the loop ran out of iterations
     LAUNCH((k_xr_update_v<NB>), gN, s, h->vPA, (unsigned long long*)h->vWA, h->vX, h->vRA, nFlat, h->vPartials, h->vState,
            h->vHistory, h->historyCap);
+    rc = vec_ordered_step<NB>(h, S_XR); if (rc) return rc;
     CK(cudaMemcpyAsync(fin, h->vState, sizeof(DevState)*NB, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(h->ev[1], s));
     CK(cudaStreamSynchronize(s));

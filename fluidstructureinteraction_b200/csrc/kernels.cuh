@@ -52,6 +52,7 @@ struct DevState
     unsigned int ticket;
     int pending;                // an x/r update (alpha known, wA = A pA) has not been applied yet
     P2PDev* p2p;                // multi-rank: peer-memory mailboxes for the scalar all-reduces (null: ncclAllReduce + k_scalar_step)
+    int ordered;                // GPUPCG_ORDERED_SUMS: the fused tree reductions stand down, k_ordered_step sums in the caller's cell order
 };
 
 enum ScalarStep { S_INIT = 0, S_NORM = 1, S_SWEEP = 2, S_AMUL = 3, S_XR = 4 };
@@ -156,6 +157,7 @@ __device__ __forceinline__ void grid_reduce_finish(double (&v)[NV], double* part
     constexpr int NW = NT/32;
     __shared__ double sm[NV][NW];
     __shared__ bool amLast;
+    if (st->ordered) return;    // verification mode: k_ordered_step (kernels_ordered.cuh) forms the sums after this kernel
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < NV; k++)

@@ -77,6 +77,7 @@ __device__ __forceinline__ void grid_reduce_finish_v(double (&v)[NV*NB], double*
     constexpr int NW = NT/32, NVB = NV*NB;
     __shared__ double sm[NVB][NW];
     __shared__ bool amLast;
+    if (st[0].ordered) return;  // verification mode: k_ordered_step_v forms the sums after this kernel
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < NVB; k++)

@@ -156,3 +156,48 @@ def build(mesh, geom, patchTypes):
             s = s + ilr[:, 3*a + b]*Mx[:, b]*1.0
         inv[:, a] = s
     return dict(start=start.astype(np.int32), entry=entry.astype(np.int32), inv=inv, origin=o, mirror=mirror.astype(np.uint8))
+
+
+def point_constraints(mesh, geom, pointPatchTypes, pointPatchValues=None):
+    """The point patch fields of pointD that do something in pf.correctBoundaryConditions()
+    (leastSquaresVolPointInterpolate.C:301), as the 0/pointD dictionaries of the reference declare them
+    (run/stressFoam/plateHole/plateHole/0/pointD:19-50, run/fsiFoam/beamInCrossFlow/solid/0/pointD:19-37):
+    `symmetryPlane` removes the component along the patch's point normal, `fixedValue` sets the value; `calculated` and
+    `empty` do nothing.  Returns dict(point (n,), start (n+1,), kind (rows,), vec (rows,3)) for gpupcg_mesh_set_point_constraints:
+    constrained point i owns rows start[i]..start[i+1] in patch order (kind 1 symmetryPlane: vec = nHat, 2 fixedValue: vec = value)."""
+    fs = mesh.faceStart.astype(np.int64)
+    fpts = mesh.facePoints.astype(np.int64)
+    nP = mesh.nPoints
+    pts_l, kind_l, vec_l = [], [], []
+    for p in mesh.patches:
+        t = pointPatchTypes.get(p["name"], "calculated")
+        if t not in ("symmetryPlane", "fixedValue") or p["size"] == 0:
+            continue
+        faces = np.arange(p["start"], p["start"] + p["size"], dtype=np.int64)
+        allp = np.concatenate([fpts[fs[f]:fs[f + 1]] for f in faces])
+        _, first = np.unique(allp, return_index=True)
+        mp = allp[np.sort(first)]                                   # meshPoints(): order of first appearance
+        if t == "fixedValue":
+            v = np.zeros(3) if not pointPatchValues or p["name"] not in pointPatchValues else np.asarray(pointPatchValues[p["name"]], dtype=np.float64)
+            vec = np.broadcast_to(v, (mp.shape[0], 3)).copy()
+            kind = np.full(mp.shape[0], 2, dtype=np.int32)
+        else:
+            unit = geom.Sf[faces]/(geom.magSf[faces] + VSMALL)[:, None]
+            rep = np.repeat(np.arange(faces.size), fs[faces + 1] - fs[faces])
+            acc = np.zeros((nP, 3))
+            for d in range(3):
+                np.add.at(acc[:, d], allp, unit[rep, d])            # faces ascending: PrimitivePatch::pointFaces order
+            a = acc[mp]
+            vec = a/(np.sqrt(a[:, 0]*a[:, 0] + a[:, 1]*a[:, 1] + a[:, 2]*a[:, 2]) + VSMALL)[:, None]
+            kind = np.full(mp.shape[0], 1, dtype=np.int32)
+        pts_l.append(mp); kind_l.append(kind); vec_l.append(vec)
+    if not pts_l:
+        return dict(point=np.zeros(0, dtype=np.int32), start=np.zeros(1, dtype=np.int32), kind=np.zeros(0, dtype=np.int32),
+                    vec=np.zeros((0, 3)))
+    pts = np.concatenate(pts_l); kind = np.concatenate(kind_l); vec = np.concatenate(vec_l)
+    o = np.argsort(pts, kind="stable")                              # rows of a point stay in patch order
+    pts, kind, vec = pts[o], kind[o], vec[o]
+    up, cnt = np.unique(pts, return_counts=True)
+    start = np.zeros(up.shape[0] + 1, dtype=np.int32)
+    np.cumsum(cnt, out=start[1:])
+    return dict(point=up.astype(np.int32), start=start, kind=kind.astype(np.int32), vec=np.ascontiguousarray(vec))

@@ -328,12 +328,12 @@ def read_polymesh(polyMeshDir):
         facePoints.extend(ids)
         faceStart.append(len(facePoints))
     assert len(faceStart) == nF + 1
+    from . import foamdict
     with open(os.path.join(polyMeshDir, "boundary"), "r") as f:
         text = _strip_header(f.read())
+    # `N ( name { type ...; nFaces ...; startFace ...; } ... )`: patch names may carry '-' or '.' (inner-wall, symmetry-x)
+    entries = foamdict.parse("boundary " + text[text.index("("):] + ";")["boundary"]
     patches = []
-    for m in re.finditer(r"(\w+)\s*\{([^}]*)\}", text):
-        d = dict(re.findall(r"(\w+)\s+([^;]+);", m.group(2)))
-        if "nFaces" in d:
-            patches.append(dict(name=m.group(1), type=d.get("type", "patch").strip(),
-                                start=int(d["startFace"]), size=int(d["nFaces"])))
+    for name, d in zip(entries[0::2], entries[1::2]):
+        patches.append(dict(name=str(name), type=str(d.get("type", "patch")), start=int(d["startFace"]), size=int(d["nFaces"])))
     return PolyMesh(pts, np.array(faceStart), np.array(facePoints, dtype=np.int64), owner, neighbour, patches)

@@ -9,7 +9,8 @@ from . import capi, lsq as lsqmod
 
 class GpuSolidCase(object):
     def __init__(self, mesh, geom, patchTypes, mu, lam, rho, traction=None, pressure=None, fixedValue=None, g=(0.0, 0.0, 0.0),
-                 threeK=None, alpha=None, validCmpts=(1, 1, 1), device=0, lsq=None):
+                 threeK=None, alpha=None, validCmpts=(1, 1, 1), device=0, lsq=None,
+                 pointPatchTypes=None, pointPatchValues=None):
         nC, nF, nIF = mesh.nCells, mesh.nFaces, mesh.nInternalFaces
         nBF = nF - nIF
         self.mesh, self.geom, self.patchTypes = mesh, geom, patchTypes
@@ -32,6 +33,8 @@ class GpuSolidCase(object):
             gm.set_field("threeK", full(threeK, nC)); gm.set_field("alpha", full(alpha, nC))
             gm.set_field("DT", np.zeros(nC)); gm.set_field("DTb", np.zeros(nBF))
         gm.set_lsq(lsq if lsq is not None else lsqmod.build(mesh, geom, patchTypes))
+        if pointPatchTypes:             # 0/pointD: symmetryPlane / fixedValue point patches act after every interpolation
+            gm.set_point_constraints(lsqmod.point_constraints(mesh, geom, pointPatchTypes, pointPatchValues))
         gm.set_field("pointD", np.zeros((mesh.nPoints, 3)))
         gm.set_field("Db", np.zeros((nBF, 3)))
         gm.patch_evaluate()             # D.boundaryField() of the initial field

@@ -331,6 +331,15 @@ int gpupcg_mesh_get_field(gpupcg_mesh m, int fieldId, double* host);
 int gpupcg_mesh_set_lsq(gpupcg_mesh m, const int* pointStart, const int* entry, const double* invLs, const double* origin,
                         const unsigned char* mirror);
 int gpupcg_vol_to_point(gpupcg_mesh m, int reps, double* kernel_ms);
+/* The point patch fields of pointD that act in pf.correctBoundaryConditions() at the end of interpolate()
+ * (leastSquaresVolPointInterpolate.C:301; declared in 0/pointD, e.g. run/stressFoam/plateHole/plateHole/0/pointD:19-50,
+ * run/fsiFoam/beamInCrossFlow/solid/0/pointD:19-37).  Constrained point i = point[i] (distinct, ascending) owns rows
+ * start[i] .. start[i+1], applied in boundary-patch order: kind 1 symmetryPlane [EXT SymmetryPointPatchField::evaluate]
+ * pf = transform(I - nHat*nHat, pf) with vec[row] = the patch's pointNormals(); kind 2 fixedValue [EXT
+ * ValuePointPatchField::evaluate] pf = vec[row].  `calculated` and `empty` point patches need no entry.  nConstrained = 0
+ * clears the table.  gpupcg_vol_to_point and the resident outer loop apply it after every interpolation.                  */
+int gpupcg_mesh_set_point_constraints(gpupcg_mesh m, int nConstrained, const int* point, const int* start, const int* kind,
+                                      const double* vec);
 /* D.correctBoundaryConditions(): evaluate() of every patch field on the resident D, grad(D), gradient() -> D.boundaryField()
  * (tractionDisplacementFvPatchVectorField.C:259-300, symmetryDisplacementFvPatchVectorField.C:169-207).                   */
 int gpupcg_patch_evaluate(gpupcg_mesh m);

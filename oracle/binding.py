@@ -199,7 +199,8 @@ def set_sum_mode(mode):
     load().orc_set_sum_mode(int(mode))
 
 
-PATCH_TYPES = {"tractionDisplacement": 0, "fixedDisplacement": 1, "symmetryDisplacement": 2, "symmetryPlane": 3, "empty": 4}
+PATCH_TYPES = {"tractionDisplacement": 0, "fixedDisplacement": 1, "symmetryDisplacement": 2, "symmetryPlane": 3, "empty": 4,
+               "fixedValue": 5}
 
 
 def lame(E, nu, planeStress=False):
@@ -428,3 +429,48 @@ class Lsq(object):
             lib.orc_lsq_free(self._h)
         except Exception:
             pass
+
+
+def point_constraints_build(mesh, geom, pointPatchTypes, pointPatchValues=None):
+    """Plain-loop restatement of which points pf.correctBoundaryConditions() touches and with what (see orc_point_constraints):
+    per patch in boundary order, meshPoints() in order of first appearance over the patch faces; symmetryPlane: pointNormals()."""
+    rows = {}
+    nIF = mesh.nInternalFaces
+    for p in mesh.patches:
+        t = pointPatchTypes.get(p["name"], "calculated")
+        if t not in ("symmetryPlane", "fixedValue"):
+            continue
+        order, acc = [], {}
+        for f in range(p["start"], p["start"] + p["size"]):
+            n = geom.Sf[f]/(geom.magSf[f] + 1.0e-300)
+            for q in mesh.facePoints[mesh.faceStart[f]:mesh.faceStart[f + 1]]:
+                q = int(q)
+                if q not in acc:
+                    acc[q] = np.zeros(3); order.append(q)
+                acc[q] = acc[q] + n
+        for q in order:
+            if t == "fixedValue":
+                v = np.zeros(3) if not pointPatchValues or p["name"] not in pointPatchValues else np.asarray(pointPatchValues[p["name"]], dtype=np.float64)
+                rows.setdefault(q, []).append((2, v))
+            else:
+                a = acc[q]
+                rows.setdefault(q, []).append((1, a/(np.sqrt(a[0]*a[0] + a[1]*a[1] + a[2]*a[2]) + 1.0e-300)))
+    pts = sorted(rows)
+    start = [0]; kind = []; vec = []
+    for q in pts:
+        for k, v in rows[q]:
+            kind.append(k); vec.append(v)
+        start.append(len(kind))
+    return dict(point=np.array(pts, dtype=np.int32), start=np.array(start, dtype=np.int32), kind=np.array(kind, dtype=np.int32),
+                vec=np.array(vec, dtype=np.float64).reshape(-1, 3))
+
+
+def point_constraints_apply(pc, pointD):
+    """pf.correctBoundaryConditions() on pointD (n,3), in place."""
+    lib = load()
+    assert pointD.dtype == np.float64 and pointD.flags.c_contiguous
+    point, start, kind, vec = _i(pc["point"]), _i(pc["start"]), _i(pc["kind"]), _f(pc["vec"])
+    lib.orc_point_constraints.restype = None
+    lib.orc_point_constraints.argtypes = [C.c_int, ip, ip, ip, dp, dp]
+    lib.orc_point_constraints(point.shape[0], _ip(point), _ip(start), _ip(kind), _dp(vec), _dp(pointD))
+    return pointD

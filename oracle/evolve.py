@@ -108,10 +108,12 @@ class SolidCase(object):
     """State of one unsTotalLagrangianStress object: fields that persist across evolve() calls and time steps."""
 
     def __init__(self, mesh, geom, patchTypes, mu, lam, rho, traction=None, pressure=None, fixedValue=None, g=(0.0, 0.0, 0.0),
-                 threeK=None, alpha=None, validCmpts=(1, 1, 1)):
+                 threeK=None, alpha=None, validCmpts=(1, 1, 1), pointPatchTypes=None, pointPatchValues=None):
         nC, nF, nIF = mesh.nCells, mesh.nFaces, mesh.nInternalFaces
         nBF = nF - nIF
         self.mesh, self.geom, self.patchTypes = mesh, geom, patchTypes
+        # point patch fields of pointD (0/pointD): applied at the end of every interpolate() (:301 of ...Interpolate.C)
+        self.pointConstraints = orc.point_constraints_build(mesh, geom, pointPatchTypes, pointPatchValues) if pointPatchTypes else None
         self.mu = np.full(nC, mu) if np.isscalar(mu) else np.asarray(mu, dtype=np.float64)
         self.lam = np.full(nC, lam) if np.isscalar(lam) else np.asarray(lam, dtype=np.float64)
         self.rho = np.full(nC, rho) if np.isscalar(rho) else np.asarray(rho, dtype=np.float64)
@@ -174,6 +176,8 @@ class SolidCase(object):
                 orc.relax_boundary(self.Db, DbPrev, relaxD)
             res = orc.relax_residual(self.D, Dprev, self.Dold, relaxD)
             self.pointD = self.lsq.interpolate(self.D, self.Db)
+            if self.pointConstraints is not None:
+                orc.point_constraints_apply(self.pointConstraints, self.pointD)
             gradOld = self.gradD
             self.gradD, self.gradDb = orc.grad_ex(mesh, geom, pt, self.D, self.pointD, gradOld, self.fixedValue,
                                                   self.patchGradient, self.gradDb)

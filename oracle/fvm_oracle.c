@@ -32,7 +32,8 @@ typedef struct orc_mesh
     const int* neighbour;       /* [nInternalFaces] */
     const int* patchStart;      /* [nPatches] first face */
     const int* patchSize;       /* [nPatches] */
-    const int* patchType;       /* 0 tractionDisplacement (fixedGradient), 1 fixedDisplacement (fixedValue), 2 symmetryDisplacement */
+    const int* patchType;       /* 0 tractionDisplacement (fixedGradient), 1 fixedDisplacement (fixedValue), 2 symmetryDisplacement,
+                                   3 symmetryPlane [EXT], 4 empty, 5 fixedValue [EXT] */
     const double* Sf;           /* [nFaces*3] */
     const double* magSf;        /* [nFaces] */
     const double* Cf;           /* [nFaces*3] */
@@ -230,15 +231,17 @@ void orc_assemble_D
             const double dcf = M->deltaCoeffs[f];
             double n[3], gIC[3], gBC[3];
             for (int d = 0; d < 3; d++) n[d] = Sf[d]/magSf;
-            if (M->patchType[p] == 1)
+            if (M->patchType[p] == 1 || M->patchType[p] == 5)
             {
                 /* fixedValue: gradientInternalCoeffs = -pTraits::one*deltaCoeffs ;
-                   fixedDisplacement::gradientBoundaryCoeffs = deltaCoeffs*(*this - (k & gradU.patchInternalField())) */
+                   fixedDisplacement::gradientBoundaryCoeffs = deltaCoeffs*(*this - (k & gradU.patchInternalField()));
+                   plain [EXT] fixedValueFvPatchField (type 5): gradientBoundaryCoeffs = deltaCoeffs*(*this), no k term */
                 double delta[3], k[3], kg[3];
                 for (int d = 0; d < 3; d++) delta[d] = M->Cf[3*f + d] - M->C[3*c + d];
                 const double nd = dot3(n, delta);
                 for (int d = 0; d < 3; d++) k[d] = delta[d] - n[d]*nd;
                 vdotT(k, gradD + 9*c, kg);
+                if (M->patchType[p] == 5) kg[0] = kg[1] = kg[2] = 0.0;
                 for (int d = 0; d < 3; d++)
                 {
                     gIC[d] = -dcf;
@@ -414,13 +417,15 @@ static void patch_snGrad(const orc_mesh* M, int ptype, int f, const double* D, c
                          const double* fixedValue, const double* patchGradient, double* sn)
 {
     const int bf = f - M->nInternalFaces, c = M->owner[f];
-    if (ptype == 1)
+    if (ptype == 1 || ptype == 5)
     {
+        /* type 5 = [EXT] fixedValueFvPatchField::snGrad(): deltaCoeffs*(*this - patchInternalField()) */
         double n[3], delta[3], k[3], kg[3];
         for (int d = 0; d < 3; d++) { n[d] = M->Sf[3*f + d]/M->magSf[f]; delta[d] = M->Cf[3*f + d] - M->C[3*c + d]; }
         const double nd = dot3(n, delta);
         for (int d = 0; d < 3; d++) k[d] = delta[d] - n[d]*nd;
         vdotT(k, gradD + 9*c, kg);
+        if (ptype == 5) kg[0] = kg[1] = kg[2] = 0.0;
         for (int d = 0; d < 3; d++) sn[d] = (fixedValue[3*bf + d] - (D[3*c + d] + kg[d]))*M->deltaCoeffs[f];
     }
     else if (ptype == 2) symmetry_snGrad(M, f, D, gradD, sn);
@@ -870,11 +875,12 @@ void orc_assemble_D_ex
                 for (int d = 0; d < 3; d++) { internalCoeffs[3*bf + d] = 0.0; boundaryCoeffs[3*bf + d] = 0.0; }
                 continue;
             }
-            if (pt == 1)
+            if (pt == 1 || pt == 5)
             {
                 double k[3], kg[3];
                 patch_nk(M, f, n, k);
                 vdotT(k, gradD + 9*(size_t)c, kg);
+                if (pt == 5) kg[0] = kg[1] = kg[2] = 0.0;           /* [EXT] fixedValueFvPatchField: no k term */
                 for (int d = 0; d < 3; d++) { gIC[d] = -dcf; gBC[d] = dcf*(fixedValue[3*bf + d] - kg[d]); }
             }
             else if (pt == 2 || pt == 3)
@@ -921,7 +927,7 @@ void orc_patch_evaluate(const orc_mesh* M, const double* D, const double* gradD,
             const int f = M->patchStart[p] + i, bf = f - nIF, c = M->owner[f];
             double n[3], k[3], kg[3];
             if (pt == 4) continue;
-            if (pt == 1) { for (int d = 0; d < 3; d++) Db[3*bf + d] = fixedValue[3*bf + d]; continue; }
+            if (pt == 1 || pt == 5) { for (int d = 0; d < 3; d++) Db[3*bf + d] = fixedValue[3*bf + d]; continue; }
             patch_nk(M, f, n, k);
             if (pt == 0)
             {
@@ -1339,4 +1345,30 @@ void orc_lsq_interpolate(const orc_lsq* L, const orc_mesh* M, const double* D, c
         for (int d = 0; d < 3; d++) pointD[3*(size_t)p + d] = ((avg[d] + co[0][d]*dr[0]) + co[1][d]*dr[1]) + co[2][d]*dr[2];
     }
     free(src);
+}
+
+/* pf.correctBoundaryConditions() at the end of interpolate() (leastSquaresVolPointInterpolate.C:301): evaluate() of the
+ * point patch fields of pointD, patches in boundary order, each patch over its meshPoints():
+ *   kind 1  symmetryPlane [EXT SymmetryPointPatchField::evaluate]: pf = transform(I - nHat*nHat, pf), nHat = the patch's
+ *           pointNormals() [EXT PrimitivePatch: sum of the unit normals of the patch faces at the point / (mag + VSMALL)]
+ *   kind 2  fixedValue    [EXT ValuePointPatchField::evaluate]: pf = the patch value
+ * (calculated / empty point patches do nothing).  Constrained point i = point[i] owns rows start[i] .. start[i+1], in
+ * patch order; vec[row] = nHat or the value.                                                                             */
+void orc_point_constraints(int n, const int* point, const int* start, const int* kind, const double* vec, double* pointD)
+{
+    for (int i = 0; i < n; i++)
+    {
+        double* v = pointD + 3*(size_t)point[i];
+        for (int r = start[i]; r < start[i + 1]; r++)
+        {
+            const double* a = vec + 3*(size_t)r;
+            if (kind[r] == 2) { v[0] = a[0]; v[1] = a[1]; v[2] = a[2]; continue; }
+            double T[9], t[3];
+            T[0] = 1.0 - a[0]*a[0]; T[1] = -(a[0]*a[1]); T[2] = -(a[0]*a[2]);
+            T[3] = -(a[1]*a[0]); T[4] = 1.0 - a[1]*a[1]; T[5] = -(a[1]*a[2]);
+            T[6] = -(a[2]*a[0]); T[7] = -(a[2]*a[1]); T[8] = 1.0 - a[2]*a[2];
+            Tdotv(T, v, t);
+            v[0] = t[0]; v[1] = t[1]; v[2] = t[2];
+        }
+    }
 }

@@ -7,7 +7,7 @@
      deterministic laplacian-type LDU matrix on each mesh.  They pin the oracle against regressions; they do
      NOT pin it against foam-extend (parity unpinned, see oracle/ASSUMPTIONS.md).
 
-usage: python tests/golden/make_fixtures.py
+usage: python tests/golden/make_fixtures.py [--polymesh-only]
 """
 import os
 import subprocess
@@ -49,6 +49,9 @@ def main():
         m = meshes.read_polymesh(os.path.join(REF, rel, "constant/polyMesh"))
         assert m.is_upper_triangular(), name
         m.save_npz(os.path.join(HERE, name + ".polymesh.npz"))
+        if "--polymesh-only" in sys.argv:
+            print(name, [(p["name"], p["type"], p["size"]) for p in m.patches])
+            continue
         l, u = m.lower_upper()
         diag, upper, b, x0 = synthetic_matrix(l, u, m.nCells, 1000 + k)
         xt = np.sin(0.37*np.arange(m.nCells))

@@ -90,17 +90,11 @@ BRANCHES = [dict(), dict(d2dt2="Euler", ddt="Euler", deltaT=0.01, deltaT0=0.02),
             dict(d2dt2="Euler", ddt="Euler", deltaT=0.01, K=2.0, nonLinear=True, thermal=True, limitCoeff=0.5)]
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("kind", ["hexsym", "tet", "2d"])
-@pytest.mark.parametrize("branch", range(len(BRANCHES)))
-def test_gpu_resident_assembly_every_branch_bit_exact(kind, branch):
+def _check_resident_chain(m, g, pt, branch, scale, lsq_data=None):
+    """assemble -> D.correctBoundaryConditions -> vol->point -> grad / fGrad -> sigma / U on the device, every array bit for
+    bit against the oracle on the same state."""
     import fluidstructureinteraction_b200 as pkg
     from fluidstructureinteraction_b200 import capi
-    m, g, pt = _mesh(kind)
-    if kind == "2d" and branch >= 3:
-        scale = 1e-3        # make the non-linear terms visible
-    else:
-        scale = 1e-5 if branch < 3 else 1e-2
     st = _random_state(m, seed=branch, scale=scale)
     nC = m.nCells
     mu, lam = cases.lame(2e11, 0.3)
@@ -128,9 +122,10 @@ def test_gpu_resident_assembly_every_branch_bit_exact(kind, branch):
     Db = oracle.patch_evaluate(m, g, pt, st["D"], st["gradD"], st["fixedValue"], ref["patchGradient"])
     assert np.array_equal(gm.get_field("Db")[nonempty], Db[nonempty])
     gm.set_field("Db", Db)
-    gm.set_lsq(lsq.build(m, g, pt))
+    L = oracle.Lsq(m, g, pt)
+    gm.set_lsq(lsq_data(L) if lsq_data else lsq.build(m, g, pt))
     gm.vol_to_point()
-    pD = oracle.Lsq(m, g, pt).interpolate(st["D"], Db)
+    pD = L.interpolate(st["D"], Db)
     assert np.array_equal(gm.get_field("pointD"), pD)
     gm.gradients_on_device(ctl.limitCoeff)
     G2, Gb2 = oracle.grad_ex(m, g, pt, st["D"], pD, st["gradD"], st["fixedValue"], ref["patchGradient"])
@@ -146,6 +141,32 @@ def test_gpu_resident_assembly_every_branch_bit_exact(kind, branch):
     gm.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["hexsym", "tet", "2d"])
+@pytest.mark.parametrize("branch", range(len(BRANCHES)))
+def test_gpu_resident_assembly_every_branch_bit_exact(kind, branch):
+    m, g, pt = _mesh(kind)
+    if kind == "2d" and branch >= 3:
+        scale = 1e-3        # make the non-linear terms visible
+    else:
+        scale = 1e-5 if branch < 3 else 1e-2
+    _check_resident_chain(m, g, pt, branch, scale)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["hex", "tet"])
+def test_gpu_resident_chain_bit_exact_at_one_million_cells(kind):
+    """The same bit-for-bit comparison at a size that fills the machine (grid-stride loops with 24 CTAs per SM, every SM
+    busy, 32-bit index products past 2^31 bytes): 1.02 M hexes / 1.05 M jittered tets, all branches switched on."""
+    if kind == "hex":
+        m = meshes.hex_box(160, 64, 100); pt = dict(PT3, free="symmetryDisplacement")
+    else:
+        m = meshes.tet_box(56, 56, 56, jitter=0.15); pt = dict(PT3)
+    assert m.nCells > 1000000
+    g = geometry.compute(m)
+    _check_resident_chain(m, g, pt, len(BRANCHES) - 1, 1e-2, lsq_data=lambda L: L.export())
+
+
 def _loaded_case(m, g, pt, E, nu, rho, tz, cls, **extra):
     mu, lam = cases.lame(E, nu, planeStress=extra.pop("planeStress", False))
     nBF, nIF = m.nFaces - m.nInternalFaces, m.nInternalFaces
@@ -159,7 +180,9 @@ def _compare_loops(c, gcase, r, rg, fields=("D", "pointD", "gradD", "sigma", "ep
     assert np.array_equal(rg["pcgIterations"], np.array(r["pcgIterations"])), "PCG iteration counts differ"
     assert rg["enforceLinear"] == int(r["enforceLinear"])
     h, hg = r["residualHistory"], rg["residualHistory"]
-    assert np.max(np.abs(h - hg)/np.abs(h)) < 1e-6
+    # res = max|D - D.prevIter| / max|D - D.oldTime| is a difference quotient: near convergence it carries the 1e-13-level
+    # differences of the PCG solutions (re-associated global sums) divided by res itself -- hence the floor relative to the first residual
+    assert np.all(np.abs(h - hg) <= 1e-6*np.abs(h) + 1e-10*np.abs(h).max())
     for k in fields:
         a, b = getattr(c, k), gcase.get(k)
         scale = np.abs(a).max()

@@ -189,8 +189,11 @@ def test_large_size_properties():
     g.close()
 
 
-def test_two_gpu_parity_against_oracle_on_same_partition():
-    """Needs >= 2 GPUs (gpurun --gpus 2): NCCL halos + all-reduces vs oracle.pcg_solve_multi."""
+@pytest.mark.parametrize("ordered,p2p", [(1, None), (1, "0"), (0, None)])
+def test_two_gpu_parity_against_oracle_on_same_partition(ordered, p2p):
+    """Needs >= 2 GPUs (gpurun --gpus 2): halo swaps + cross-rank reductions vs oracle.pcg_solve_multi.  ordered = 1: global
+    sums in the reference's order -> history and solution bit-identical (mailboxes, and NCCL's all-reduce with p2p = "0");
+    ordered = 0: the production tree reductions (bars in tools/multigpu_parity.py)."""
     import os
     import subprocess
     import sys
@@ -198,10 +201,52 @@ def test_two_gpu_parity_against_oracle_on_same_partition():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, ORDERED=str(ordered))
+    if p2p is not None:
+        env["GPUPCG_P2P_REDUCE"] = p2p
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                         "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "multigpu_parity.py")],
-                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "MULTIGPU-PARITY-OK" in r.stdout, r.stdout[-3000:]
+
+
+@pytest.mark.parametrize("kind", ["hex", "tet"])
+def test_ordered_sums_mode_is_bit_identical_to_the_oracle(kind, monkeypatch):
+    """GPUPCG_ORDERED_SUMS=1: gSumProd / gSumMag / gSum formed in the caller's cell order (csrc/kernels_ordered.cuh), every
+    other kernel the production one -> residual history, iteration count and solution equal the oracle's bit for bit, for
+    the scalar solve and for every component of the batched one.  What separates the production path from the reference is
+    therefore the association of those sums alone."""
+    monkeypatch.setenv("GPUPCG_ORDERED_SUMS", "1")
+    if kind == "hex":
+        s = cases.cantilever_system(40, 12, 16)
+        l, u, diag, upper, b, n = s["l"], s["u"], s["diag"], s["upper"], s["b"], s["nCells"]
+    else:
+        from fluidstructureinteraction_b200 import meshes
+        m = meshes.tet_box(8, 5, 6, jitter=0.15)
+        l, u = m.lower_upper(); n = m.nCells
+        diag, upper, b, _ = synthetic_matrix(l, u, n, 77)
+    g = pkg.GpuPCG(l, u, n, device=0)
+    g.set_matrix(diag, upper)
+    for x0 in (np.zeros(n), 0.3*np.sin(0.11*np.arange(n))):        # xRef = 0 and xRef != 0 (normFactor's Amul of the xRef field)
+        for relTol in (0.01, 0.0):
+            xg, xc = x0.copy(), x0.copy()
+            pg, hg = g.solve(xg, b, tolerance=1e-9, relTol=relTol)
+            pc, hc = oracle.pcg_solve(l, u, diag, upper, xc, b, tolerance=1e-9, relTol=relTol)
+            assert pg["nIterations"] == pc["nIterations"] and (pg["nIterations"] > 5 or x0.any())
+            assert np.array_equal(hg, hc) and np.array_equal(xg, xc)
+            assert pg["initialResidual"] == pc["initialResidual"] and pg["finalResidual"] == pc["finalResidual"]
+            assert pg["normFactor"] == pc["normFactor"]
+    dC = np.ascontiguousarray(np.stack([diag, diag*1.25, diag*1.5], axis=1))
+    bC = np.ascontiguousarray(np.stack([b, -0.5*b, np.cos(0.11*np.arange(n))*np.abs(b).max()], axis=1))
+    g.set_matrix_vector(dC, upper)
+    xv = np.zeros((n, 3))
+    pv, hv = g.solve_vector(xv, bC, tolerance=1e-9, relTol=0.0)
+    for k in range(3):
+        xk = np.zeros(n)
+        pk, hk = oracle.pcg_solve(l, u, np.ascontiguousarray(dC[:, k]), upper, xk, np.ascontiguousarray(bC[:, k]), tolerance=1e-9, relTol=0.0)
+        assert pv[k]["nIterations"] == pk["nIterations"]
+        assert np.array_equal(hv[k], hk) and np.array_equal(xv[:, k], xk), k
+    g.close()
 
 
 def random_ldu(n, extra, seed):

@@ -1,8 +1,22 @@
-"""torchrun worker: N ranks = N GPUs, one cantilever sub-domain each; gpuPCG over NCCL vs the CPU oracle on the SAME
-partition (oracle.pcg_solve_multi): identical iteration count, history within 1e-10, fields within 1e-9.
+"""torchrun worker: N ranks = N GPUs, one cantilever sub-domain each; gpuPCG (halo swaps, mailbox / NCCL reductions)
+against the CPU oracle on the SAME partition (oracle.pcg_solve_multi).
+
+  ORDERED=1 (GPUPCG_ORDERED_SUMS): the global sums are formed as the reference forms them (sequential per rank in cell
+      order, ranks in order -- csrc/kernels_ordered.cuh); everything else is the production path.  Bar: residual history,
+      iteration count and solution BIT-IDENTICAL to the oracle at any rank count (with NCCL's all-reduce instead of the
+      mailboxes, GPUPCG_P2P_REDUCE=0, bit-identical up to 2 ranks -- NCCL does not promise rank order beyond that).
+  ORDERED=0 (production): the fused tree reductions re-associate those sums, which is the ONLY difference left (see above).
+      Bar: identical iteration count, solution within 1e-9, history within 1e-10 relative for as long as the problem's own
+      sensitivity to re-association -- the oracle against ITSELF with pairwise instead of sequential sums -- stays below
+      1e-11; past that point CG amplifies any re-association chaotically, no summation order other than the reference's
+      can meet 1e-10, and both deviations are printed side by side instead.
+
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29500 tools/multigpu_parity.py
 """
 import os, sys
+ORDERED = os.environ.get("ORDERED", "0") == "1"
+if ORDERED:
+    os.environ["GPUPCG_ORDERED_SUMS"] = "1"
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -24,6 +38,9 @@ dist.broadcast_object_list(uid, src=0)
 g.comm_init(rank, world, uid[0])
 g.set_matrix(s["diag"], s["upper"], patchBouCoeffs=s["patchBouCoeffs"])
 subs = [cases.cantilever_subdomain(nx, ny, nz, px, py, pz, r) for r in range(world)] if rank == 0 else None
+if rank == 0:
+    print("ranks", world, "cells", (nx, ny, nz), "decomposition", (px, py, pz), "ordered sums", ORDERED,
+          "GPUPCG_P2P_REDUCE", os.environ.get("GPUPCG_P2P_REDUCE", "(default)"), flush=True)
 
 
 def compare(tag, pg, hg, xs, tol, rel, dscale=1.0, bscale=1.0):
@@ -34,37 +51,42 @@ def compare(tag, pg, hg, xs, tol, rel, dscale=1.0, bscale=1.0):
         doms.append(dict(l=q["l"], u=q["u"], diag=q["diag"]*dscale, upper=q["upper"], b=q["b"]*bscale, x=np.zeros(q["nCells"]),
                          patchFaceCells=q["patchFaceCells"], patchBouCoeffs=q["patchBouCoeffs"],
                          patchNbrDomain=q["patchNbrDomain"], patchNbrPatch=back))
-    # sensitivity envelope: the oracle against ITSELF with nothing changed but the association of its reductions
-    # (pairwise instead of sequential sums).  The GPU necessarily re-associates them too; it has to stay within
-    # 1e-10 relative, or -- where CG amplifies re-association beyond that -- within 16x that envelope (the growth is
-    # chaotic: one pairwise sample under-estimates the spread between two arbitrary associations by a small factor;
-    # measured on 2 B200: GPU 4.3e-10 where pairwise-vs-sequential is 6.0e-11 at iteration 31 of 33, both ~1e-14
-    # for the first 24 iterations).
+    oracle.set_sum_mode(0)
+    pc, hc = oracle.pcg_solve_multi(doms, tol, rel)
+    xscale = max(max(np.max(np.abs(d["x"])) for d in doms), 1e-300)
+    n = min(len(hg), len(hc))
+    dev = np.abs(hg[:n] - hc[:n])/np.abs(hc[:n])
+    xdev = max(float(np.max(np.abs(xs[r] - doms[r]["x"]))/xscale) for r in range(world))
+    if ORDERED:
+        good = (pg["nIterations"] == pc["nIterations"] and len(hg) == len(hc) and np.array_equal(hg, hc)
+                and all(np.array_equal(xs[r], doms[r]["x"]) for r in range(world))
+                and pg["initialResidual"] == pc["initialResidual"] and pg["finalResidual"] == pc["finalResidual"])
+        print(tag, "relTol", rel, "gpu iters", pg["nIterations"], "oracle iters", pc["nIterations"],
+              "history bitwise equal" if np.array_equal(hg, hc) else "history max rel diff %.2e" % float(dev.max()),
+              "| solution bitwise equal" if xdev == 0.0 else "| solution max rel diff %.2e" % xdev,
+              "OK" if good else "MISMATCH", flush=True)
+        return good
+    # the problem's own sensitivity to re-association: oracle, pairwise sums, against oracle, sequential sums
     oracle.set_sum_mode(1)
     pp, hp = oracle.pcg_solve_multi([dict(d, x=np.zeros_like(d["x"])) for d in doms], tol, rel)
     oracle.set_sum_mode(0)
-    pc, hc = oracle.pcg_solve_multi(doms, tol, rel)
     m = min(len(hp), len(hc))
-    env = np.zeros(len(hc))
-    env[:m] = np.maximum.accumulate(np.abs(hp[:m] - hc[:m]))
-    if m < len(hc):
-        env[m:] = env[m - 1] if m else 0.0
+    env = np.full(len(hc), np.inf)
+    env[:m] = np.maximum.accumulate(np.abs(hp[:m] - hc[:m])/np.abs(hc[:m]))
     scale = max(float(np.max(np.abs(hc))), pc["initialResidual"])
-    xscale = max(max(np.max(np.abs(d["x"])) for d in doms), 1e-300)
-    xenv = 4*float(np.max(np.abs(hp[m - 1] - hc[m - 1])/abs(hc[m - 1]))) if m else 0.0
-    good = (pg["nIterations"] == pc["nIterations"]
-            and np.all(np.abs(hg - hc) <= 1e-10*np.abs(hc) + 1e-13*scale + 16*env)
-            and all(np.max(np.abs(xs[r] - doms[r]["x"])) <= max(1e-9, xenv)*xscale for r in range(world)))
+    strict = env[:n] <= 1e-11                   # iterations whose history any re-association can still reproduce to 1e-10
+    bar = 1e-10 + 1e-13*scale/np.abs(hc[:n])
+    good = (pg["nIterations"] == pc["nIterations"] and bool(np.all(dev[strict] <= bar[strict])) and xdev <= 1e-9)
+    nStrict = int(strict.sum())
     print(tag, "relTol", rel, "gpu iters", pg["nIterations"], "oracle iters", pc["nIterations"],
-          "max hist rel diff gpu-vs-oracle %.2e, oracle pairwise-vs-sequential %.2e" %
-          (float(np.max(np.abs(hg - hc)/np.abs(hc))), float(np.max(np.abs(hp[:m] - hc[:m])/np.abs(hc[:m])))),
-          "max field rel diff %.2e" % max(float(np.max(np.abs(xs[r] - doms[r]["x"]))/xscale) for r in range(world)),
-          "OK" if good else "MISMATCH", flush=True)
-    if not good:
-        rg = np.abs(hg - hc)/np.abs(hc); rp = np.zeros_like(rg); rp[:m] = np.abs(hp[:m] - hc[:m])/np.abs(hc[:m])
-        for i in range(len(hc)):
-            print("   it %3d  res %.6e  gpu-vs-oracle %.2e  pairwise-vs-seq %.2e  bound %.2e" % (
-                i, hc[i], rg[i], rp[i], (1e-10*abs(hc[i]) + 1e-13*scale + 16*env[i])/abs(hc[i])), flush=True)
+          "| iterations held to 1e-10: %d of %d, max rel diff there %.2e" % (nStrict, n, float(dev[strict].max()) if nStrict else 0.0),
+          "| beyond (re-association sensitive): gpu-vs-oracle %.2e, oracle pairwise-vs-sequential %.2e" %
+          (float(dev[~strict].max()) if nStrict < n else 0.0, float(np.max(env[:m][np.isfinite(env[:m])])) if m else 0.0),
+          "| solution max rel diff %.2e" % xdev, "OK" if good else "MISMATCH", flush=True)
+    if not good or os.environ.get("VERBOSE"):
+        for i in range(n):
+            print("   it %3d  res %.6e  gpu-vs-oracle %.2e  oracle pairwise-vs-sequential %.2e%s" % (
+                i, hc[i], dev[i], env[i], "" if strict[i] else "  (sensitive)"), flush=True)
     return good
 
 
