@@ -94,17 +94,18 @@ int Comm::init(int rank, int nRanks, const void* id128, int nCellsLocal, cudaStr
     comm_ = c;
     rank_ = rank;
     nRanks_ = nRanks;
-    // global cell count (gAverage denominator): one int64 all-reduce at init
+    // global cell count (gAverage denominator) and the number of ranks without cells: one int64 all-reduce at init
     long long* d = nullptr;
-    if (cudaMalloc((void**)&d, sizeof(long long)) != cudaSuccess) { err = "cudaMalloc failed in comm init"; return -1; }
-    long long v = nCellsLocal;
-    cudaMemcpyAsync(d, &v, sizeof(v), cudaMemcpyHostToDevice, s);
-    rc = a.AllReduce(d, d, 1, NCCL_INT64, NCCL_SUM, (ncclComm_p)comm_, s);
+    if (cudaMalloc((void**)&d, 2*sizeof(long long)) != cudaSuccess) { err = "cudaMalloc failed in comm init"; return -1; }
+    long long v[2] = {nCellsLocal, nCellsLocal == 0 ? 1 : 0};
+    cudaMemcpyAsync(d, v, sizeof(v), cudaMemcpyHostToDevice, s);
+    rc = a.AllReduce(d, d, 2, NCCL_INT64, NCCL_SUM, (ncclComm_p)comm_, s);
     if (rc != NCCL_SUCCESS) { cudaFree(d); return fail(err, "ncclAllReduce(int64)", rc); }
-    cudaMemcpyAsync(&v, d, sizeof(v), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(v, d, sizeof(v), cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);
     cudaFree(d);
-    globalCells_ = v;
+    globalCells_ = v[0];
+    emptyRanks_ = (int)v[1];
     return 0;
 }
 

@@ -37,6 +37,7 @@ public:
     int rank() const { return rank_; }
     int nRanks() const { return nRanks_; }
     long long globalCells(int /*local*/) const { return globalCells_; }
+    int emptyRanks() const { return emptyRanks_; }      // ranks whose sub-domain has no cells (known to every rank after init)
 
     static int unique_id(void* id128);
     int init(int rank, int nRanks, const void* id128, int nCellsLocal, cudaStream_t s, std::string& err);
@@ -55,6 +56,7 @@ private:
     void* comm_ = nullptr;
     int rank_ = 0, nRanks_ = 1;
     long long globalCells_ = 0;
+    int emptyRanks_ = 0;
     P2PMailbox* mbox_ = nullptr;
     P2PDev* p2pDev_ = nullptr;
     std::vector<void*> opened_;

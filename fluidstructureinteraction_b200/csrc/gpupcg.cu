@@ -698,7 +698,7 @@ extern "C" int gpupcg_set_matrix(gpupcg_handle h, const double* diag, const doub
         h->err = "gpupcg_set_matrix: asymmetric matrix (lower != upper); gpuPCG is a symMatrix solver";
         return GPUPCG_ERR_UNSUPPORTED;
     }
-    if (!upper && !h->haveMatrix && h->plan.nFaces > 0)
+    if (!upper && !h->haveMatrix && !h->vHaveMatrix && h->plan.nFaces > 0)
     {
         h->err = "gpupcg_set_matrix: upper == NULL but no previous coefficients";
         return GPUPCG_ERR_STATE;
@@ -1273,6 +1273,16 @@ extern "C" int gpupcg_comm_init(gpupcg_handle h, int rank, int nRanks, const voi
     if (!h || !id128 || rank < 0 || rank >= nRanks) return GPUPCG_ERR_ARG;
     CK(cudaSetDevice(h->device));
     if (h->comm.init(rank, nRanks, id128, h->plan.nCells, h->stream, h->err) != 0) return GPUPCG_ERR_NCCL;
+    if (h->comm.emptyRanks() > 0)
+    {
+        // a rank without rows launches no reducing kernel and would never take part in the per-step reductions (mismatched
+        // collectives on the NCCL path, peers spinning on its mailbox flag on the P2P path).  Every rank sees the same count
+        // and refuses together.
+        h->err = "gpupcg_comm_init: " + std::to_string(h->comm.emptyRanks()) + " rank(s) own a sub-domain without cells; "
+                 "decompose over fewer ranks (every rank needs at least one cell)";
+        h->comm.destroy();
+        return GPUPCG_ERR_UNSUPPORTED;
+    }
     h->dP2P = env_int("GPUPCG_P2P_REDUCE", 1) ? h->comm.setup_p2p(h->stream, h->p2pNote) : nullptr;
     if (!h->dP2P && env_int("GPUPCG_P2P_REDUCE", 1) == 2)    // 2: insist
     {

@@ -5,6 +5,7 @@
 #include "gpuPCG.H"
 #include "gpupcg.h"
 
+#include <cstdlib>
 #include <map>
 #include <vector>
 
@@ -37,17 +38,55 @@ struct gpuPCGCacheEntry
 
 static std::map<const lduAddressing*, gpuPCGCacheEntry> gpuPCGCache_;
 
-// cheap fingerprint of upper(): size, address and <= 1024 strided samples
-static scalar upperFingerprint(const scalarField& upper)
+// Hash of EVERY coefficient of upper() (four interleaved FNV-1a lanes over the 64-bit words, position dependent): one
+// O(F) host pass, a fraction of the H2D copy it can save.  fvMatrix builds a fresh lduMatrix every outer iteration and
+// the allocator routinely hands back the same address, so the pointer alone says nothing about the values.
+static scalar upperHash(const scalarField& upper)
 {
     const label n = upper.size();
-    const label stride = (n > 1024) ? n/1024 : 1;
-    scalar s = n;
-    for (label i = 0; i < n; i += stride)
+    const unsigned long long* w = reinterpret_cast<const unsigned long long*>(upper.begin());
+    const unsigned long long prime = 1099511628211ULL;
+    unsigned long long h0 = 14695981039346656037ULL, h1 = h0 ^ 0x9E3779B97F4A7C15ULL, h2 = h0 ^ 0xC2B2AE3D27D4EB4FULL,
+                       h3 = h0 ^ 0x165667B19E3779F9ULL;
+    label i = 0;
+    for (; i + 4 <= n; i += 4)
     {
-        s += upper[i]*(1 + (i & 7));
+        h0 = (h0 ^ w[i])*prime; h1 = (h1 ^ w[i + 1])*prime; h2 = (h2 ^ w[i + 2])*prime; h3 = (h3 ^ w[i + 3])*prime;
     }
-    return s;
+    for (; i < n; i++) h0 = (h0 ^ w[i])*prime;
+    unsigned long long h = (h0 ^ (h1*prime)) ^ ((h2 ^ (h3*prime))*prime) ^ (unsigned long long)n;
+    h &= 0x000FFFFFFFFFFFFFULL;                 // exactly representable as a scalar (the cache stores it as one)
+    return scalar(h);
+}
+
+// `reuseUpper yes`: skip the upload of upper() when the array the device already holds has the same address, size and
+// hash.  Off by default: a solve with stale coefficients is silent, an extra copy is not.
+static bool upperUnchanged(gpuPCGCacheEntry& entry, const scalarField& upper, const bool reuse)
+{
+    if (!reuse)
+    {
+        entry.upperPtr = NULL;
+        return false;
+    }
+    const scalar check = upperHash(upper);
+    const bool same = entry.upperPtr == upper.begin() && entry.upperCheck == check;
+    entry.upperPtr = upper.begin();
+    entry.upperCheck = check;
+    return same;
+}
+
+// Device of this rank: the node-local rank where the MPI launcher exports it (ranks are then free to be placed unevenly
+// or over several nodes), else rank mod visible devices
+static int defaultDevice(const int nDev)
+{
+    static const char* vars[] = {"OMPI_COMM_WORLD_LOCAL_RANK", "MV2_COMM_WORLD_LOCAL_RANK", "MPI_LOCALRANKID",
+                                 "SLURM_LOCALID", "PMI_LOCAL_RANK", "LOCAL_RANK"};
+    for (unsigned v = 0; v < sizeof(vars)/sizeof(vars[0]); v++)
+    {
+        const char* e = getenv(vars[v]);
+        if (e && *e) return (nDev > 0) ? (atoi(e) % nDev) : 0;
+    }
+    return (nDev > 0) ? (Pstream::myProcNo() % nDev) : 0;
 }
 
 } // End namespace Foam
@@ -75,7 +114,7 @@ Foam::gpuPCG::gpuPCG
         dict
     ),
     preconName_("DIC"),
-    reuseUpper_(true),
+    reuseUpper_(false),
     device_(-1)
 {
     if (dict.found("preconditioner"))
@@ -98,7 +137,7 @@ Foam::gpuPCG::gpuPCG
             << abort(FatalError);
     }
 
-    word reuse("yes");
+    word reuse("no");
     if (dict.readIfPresent("reuseUpper", reuse))
     {
         reuseUpper_ = (reuse == "yes" || reuse == "on" || reuse == "true");
@@ -165,6 +204,14 @@ static gpuPCGCacheEntry& gpuPCGAcquire
             }
             const processorLduInterfaceField& pif =
                 refCast<const processorLduInterfaceField>(interfaces_[patchI]);
+            if (pif.doTransform())
+            {
+                // processorFvPatchField::updateInterfaceMatrix applies transformCoupleField(pnf, cmpt) on rotational
+                // (processor-cyclic) patches; the device halo update does not
+                FatalErrorIn("gpuPCG::solve(...)")
+                    << "processor interface " << patchI << " transforms its neighbour field (doTransform()): "
+                    << "not supported on the GPU" << abort(FatalError);
+            }
             patchIds.push_back(patchI);
             patchSizes.push_back(addr.patchAddr(patchI).size());
             patchFaceCells.push_back(addr.patchAddr(patchI).begin());
@@ -189,9 +236,9 @@ static gpuPCGCacheEntry& gpuPCGAcquire
         e.upperPtr = NULL;
         e.upperCheck = 0;
         e.commReady = false;
-        // one decomposePar sub-domain per GPU of the box: rank r -> device r mod (visible devices)
+        // one decomposePar sub-domain per GPU of the box
         const int nDev = gpupcg_device_count();
-        const int device = (device_ >= 0) ? device_ : (nDev > 0 ? Pstream::myProcNo() % nDev : 0);
+        const int device = (device_ >= 0) ? device_ : defaultDevice(nDev);
         const int rc = gpupcg_create
         (
             &e.handle, device, nCells, nFaces,
@@ -254,9 +301,7 @@ Foam::lduMatrix::solverPerformance Foam::gpuPCG::solve
 
     // --- Matrix: diag always (addBoundaryDiag changes it per component), upper only when it changed
     const scalarField& upper = matrix_.upper();
-    const scalar check = upperFingerprint(upper);
-    const bool sameUpper =
-        reuseUpper_ && entry.upperPtr == upper.begin() && entry.upperCheck == check;
+    const bool sameUpper = upperUnchanged(entry, upper, reuseUpper_);
 
     std::vector<const scalar*> bouPtrs(nPatches);
     for (int p = 0; p < nPatches; p++)
@@ -278,8 +323,6 @@ Foam::lduMatrix::solverPerformance Foam::gpuPCG::solve
             << "gpupcg_set_matrix failed (" << rc << "): " << gpupcg_last_error(entry.handle)
             << abort(FatalError);
     }
-    entry.upperPtr = upper.begin();
-    entry.upperCheck = check;
 
     // --- Solve
     gpupcg_perf perf;
@@ -329,9 +372,7 @@ void Foam::gpuPCG::solveVector
     const int nPatches = P.ids.size();
 
     const scalarField& upper = matrix_.upper();
-    const scalar check = upperFingerprint(upper);
-    const bool sameUpper =
-        reuseUpper_ && entry.upperPtr == upper.begin() && entry.upperCheck == check;
+    const bool sameUpper = upperUnchanged(entry, upper, reuseUpper_);
 
     std::vector<const scalar*> bouPtrs(nPatches);
     for (int p = 0; p < nPatches; p++)
@@ -351,8 +392,6 @@ void Foam::gpuPCG::solveVector
             << "gpupcg_set_matrix_vector failed (" << rc << "): " << gpupcg_last_error(entry.handle)
             << abort(FatalError);
     }
-    entry.upperPtr = upper.begin();
-    entry.upperCheck = check;
 
     gpupcg_perf perf[3];
     rc = gpupcg_solve_vector

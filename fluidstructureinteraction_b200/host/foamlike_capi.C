@@ -71,6 +71,44 @@ extern "C" int foamlike_solve(const char* psiName, int nCmpt, int nCells, int nF
     }
 }
 
+// Two scalar solves on ONE lduMatrix object (same upper() address, as when the allocator hands a fresh fvMatrix the
+// storage of the previous one): between them upper[changeFace] += delta and diag is patched accordingly by the caller's
+// second diag array.  With `reuseUpper yes` the adaptor must notice the changed coefficient.  psi1 / psi2: the solutions.
+extern "C" int foamlike_solve_twice(int nCells, int nFaces, const int* lower, const int* upper, const double* diag1,
+                                    const double* diag2, const double* upperCoeffs, int changeFace, double delta,
+                                    const double* source, const char* solverDictText, double* psi1, double* psi2)
+{
+    try
+    {
+        lduMatrix::debug = 0;
+        labelList l(nFaces), u(nFaces);
+        for (int f = 0; f < nFaces; f++) { l[f] = lower[f]; u[f] = upper[f]; }
+        lduAddressing addr(nCells, l, u, std::vector<labelList>());
+        lduMatrix m(addr);
+        for (int f = 0; f < nFaces; f++) m.upper()[f] = upperCoeffs[f];
+        dictionary dict((std::string(solverDictText)));
+        for (int pass = 0; pass < 2; pass++)
+        {
+            const double* diag = pass ? diag2 : diag1;
+            for (int c = 0; c < nCells; c++) m.diag()[c] = diag[c];
+            if (pass) m.upper()[changeFace] += delta;
+            fvMatrixLike eqn("T", 1, m);
+            eqn.source.assign(source, source + nCells);
+            std::vector<scalar> psiV(nCells, 0.0);
+            eqn.solve(psiV, dict, 0);
+            memcpy(pass ? psi2 : psi1, psiV.data(), sizeof(double)*nCells);
+        }
+        gpuPCG::clearCache();
+        return 0;
+    }
+    catch (const Foam::error& e)
+    {
+        g_lastError = e.what();
+        gpuPCG::clearCache();
+        return -1;
+    }
+}
+
 // dictionary parser probe for the tests: value of `key` ("" if missing), sub-dictionaries with '/'.
 extern "C" int foamlike_dict_lookup(const char* text, const char* key, char* out, int outLen)
 {

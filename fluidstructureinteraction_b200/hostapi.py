@@ -90,6 +90,25 @@ def solve(psiName, l, u, diag, upper, source, patches, solverDict, psi):
     return worst.as_dict(), [per[k].as_dict() for k in range(n)]
 
 
+def solve_twice(l, u, diag1, diag2, upper, changeFace, delta, source, solverDict):
+    """Two scalar solves on one lduMatrix object (same upper() address); before the second, upper[changeFace] += delta and
+    the diagonal becomes diag2.  Returns (psi1, psi2)."""
+    lib = load()
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    l, u, diag1, diag2, upper, source = i32(l), i32(u), f64(diag1), f64(diag2), f64(upper), f64(source)
+    n = diag1.shape[0]
+    p1, p2 = np.zeros(n), np.zeros(n)
+    lib.foamlike_solve_twice.restype = C.c_int
+    lib.foamlike_solve_twice.argtypes = [C.c_int, C.c_int, ip, ip, dp, dp, dp, C.c_int, C.c_double, dp, C.c_char_p, dp, dp]
+    rc = lib.foamlike_solve_twice(n, l.shape[0], l.ctypes.data_as(ip), u.ctypes.data_as(ip), diag1.ctypes.data_as(dp),
+                                  diag2.ctypes.data_as(dp), upper.ctypes.data_as(dp), int(changeFace), float(delta),
+                                  source.ctypes.data_as(dp), solverDict.encode(), p1.ctypes.data_as(dp), p2.ctypes.data_as(dp))
+    if rc < 0:
+        raise FoamFatalError(lib.foamlike_last_error().decode())
+    return p1, p2
+
+
 VOLTOPOINT = C.CFUNCTYPE(None, C.c_void_p, dp, dp)
 
 

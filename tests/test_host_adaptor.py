@@ -117,3 +117,25 @@ def test_scalar_solve_T_equation_style():
     p, h = oracle.pcg_solve(l, u, d, upper, x, tot, 1e-9, 0.0)
     assert per[0]["nIterations"] == p["nIterations"]
     assert np.max(np.abs(psi - x)) <= 1e-9*np.max(np.abs(x))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("reuse", ["yes", "no"])
+def test_reuse_upper_notices_a_change_at_a_single_face(reuse):
+    """a fresh fvMatrix routinely lands on the storage of the previous one, so the address of upper() says
+    nothing.  One coefficient changed in place (a face no strided sample would hit) must reach the device: the second
+    solve has to be that of the modified matrix, with `reuseUpper yes` (full hash) as with the default `no`."""
+    s = cases.cantilever_system(24, 8, 10)
+    l, u, diag, upper, b, n = s["l"], s["u"], s["diag"], s["upper"], s["b"], s["nCells"]
+    f = 1237                                    # not a multiple of any small stride
+    delta = 0.37*upper[f]
+    upper2 = upper.copy(); upper2[f] += delta
+    diag2 = diag.copy(); diag2[l[f]] -= delta; diag2[u[f]] -= delta       # keep the row sums (negSumDiag)
+    d = "solver gpuPCG; preconditioner DIC; tolerance 1e-12; relTol 0; reuseUpper %s;" % reuse
+    p1, p2 = hostapi.solve_twice(l, u, diag, diag2, upper, f, delta, b, d)
+    x1, x2 = np.zeros(n), np.zeros(n)
+    oracle.pcg_solve(l, u, diag, upper, x1, b, 1e-12, 0.0)
+    oracle.pcg_solve(l, u, diag2, upper2, x2, b, 1e-12, 0.0)
+    assert np.max(np.abs(p1 - x1)) <= 1e-9*np.max(np.abs(x1))
+    assert np.max(np.abs(p2 - x2)) <= 1e-9*np.max(np.abs(x2))
+    assert np.max(np.abs(x2 - x1)) > 1e-6*np.max(np.abs(x1))            # the change matters
