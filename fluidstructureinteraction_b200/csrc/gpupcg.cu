@@ -832,7 +832,10 @@ static int enqueue_amul(gpupcg_handle h, int mode, const double* x, double* Ax, 
 template <int NB, int MODE, int LONG>
 static cudaError_t pencil_attr(size_t cap)
 {
-    return cudaFuncSetAttribute((k_dic_pencil<NB, MODE, LONG>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+    cudaError_t e = cudaFuncSetAttribute((k_dic_pencil<NB, MODE, LONG, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+    if (!e && NB > 1)
+        e = cudaFuncSetAttribute((k_dic_pencil<NB, MODE, LONG, NB>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+    return e;
 }
 template <int NB>
 static cudaError_t pencil_attrs(int pLong, size_t cap)
@@ -868,17 +871,33 @@ static int launch_pencil(gpupcg_handle h, const double* diagOrRD, const double* 
     while (nst > 2 && pen_smem_bytes<NB, MODE>(nst, A.w1, A.w2, withDot) > cap) nst--;
     A.nStages = nst;
     A.fetchWindow = env_int("GPUPCG_PENCIL_FETCH_WINDOW", 1);     // 1: measured best (profiles/r2_pencil_sweeps.md); 0 = adaptive
-    A.fetchSleep = std::max(0, env_int("GPUPCG_PENCIL_FETCH_SLEEP", 100));
+    A.fetchSleep = std::max(0, env_int("GPUPCG_PENCIL_FETCH_SLEEP", 0));      // measured: profiles/r2_pencil_sweeps.md (knob matrix)
     const size_t smem = pen_smem_bytes<NB, MODE>(nst, A.w1, A.w2, withDot);
     if (smem > h->smemCap) { h->err = "pencil sweep: the ring does not fit in shared memory"; return GPUPCG_ERR_UNSUPPORTED; }
     h->launches++;
-    const int grid = A.nPencils;
+    // one sweep warp per component (default for the batched solves) or one warp for all of them
+    // -- on latency-bound sub-domains (about one pencil per SM); on large ones the sweeps are paced by the hand-offs and by
+    // DRAM, and two unsplit CTAs per SM do better (1 M cells: 244 vs 262 us, 8 M: 925 vs 737 us; profiles/r2_pencil_sweeps.md)
+    const bool splitDefault = A.nPencils <= 2*h->numSMs;
+    const bool split = NB > 1 && env_int("GPUPCG_PENCIL_SPLIT", splitDefault ? 1 : 0) != 0;
+    // persistent CTAs, all resident (the kernel's static round-robin over the wavefront order relies on it).  A sweep warp
+    // is issue-bound: beyond one per scheduler they slow each other down and, a pencil being paced by the slowest pencil
+    // upstream, the whole wavefront with them -- so by default no more CTAs per SM than keep the sweep warps <= 4.
+    int occ = 0, grid = 1;
+    const int perSmWanted = std::max(1, env_int("GPUPCG_PENCIL_CTAS_PER_SM", split ? std::max(1, 4/NB) : 2));
+#define PEN_OCC(LONG_, SW_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (k_dic_pencil<NB, MODE, LONG_, SW_>), (SW_ + 3)*32, smem)
+#define PEN_GO(LONG_, SW_) k_dic_pencil<NB, MODE, LONG_, SW_><<<grid, (SW_ + 3)*32, smem, h->stream>>>(A, diagOrRD, rA, y, out, rDout, h->dTileTicket, partials, h->partStride, st, gated)
+#define PEN_RUN(LONG_, SW_) do { CK(PEN_OCC(LONG_, SW_)); if (occ < 1) { h->err = "pencil sweep: no CTA fits an SM"; return GPUPCG_ERR_UNSUPPORTED; } \
+        grid = std::min(A.nPencils, h->numSMs*std::min(occ, perSmWanted)); PEN_GO(LONG_, SW_); } while (0)
     switch (h->plan.pLong)
     {
-        case 0: k_dic_pencil<NB, MODE, 0><<<grid, PEN_TPB, smem, h->stream>>>(A, diagOrRD, rA, y, out, rDout, h->dTileTicket, partials, h->partStride, st, gated); break;
-        case 1: k_dic_pencil<NB, MODE, 1><<<grid, PEN_TPB, smem, h->stream>>>(A, diagOrRD, rA, y, out, rDout, h->dTileTicket, partials, h->partStride, st, gated); break;
-        default: k_dic_pencil<NB, MODE, 2><<<grid, PEN_TPB, smem, h->stream>>>(A, diagOrRD, rA, y, out, rDout, h->dTileTicket, partials, h->partStride, st, gated); break;
+        case 0: if (split) PEN_RUN(0, NB); else PEN_RUN(0, 1); break;
+        case 1: if (split) PEN_RUN(1, NB); else PEN_RUN(1, 1); break;
+        default: if (split) PEN_RUN(2, NB); else PEN_RUN(2, 1); break;
     }
+#undef PEN_RUN
+#undef PEN_OCC
+#undef PEN_GO
     return GPUPCG_OK;
 }
 

@@ -15,11 +15,14 @@
 //
 // One CTA per pencil (handed out in wavefront order by the never-reset ticket, so a CTA only waits on pencils that
 // are running or done):
-//   warp 0      the sweep: registers + shuffles, per-row data out of a shared-memory ring, results published with
-//               one coalesced 256-bit store per lane (NB = 3) -- that store is also the hand-off to other pencils
-//   warp 1      lane 0 keeps the ring full with 1-D bulk copies (cp.async.bulk, one mbarrier per stage)
-//   warps 2-3   fetch lanes: poll the neighbour pencils' published rows several steps ahead and drop them into the
-//               ring of external values the sweep warp reads
+//   SW sweep warps   registers + shuffles, per-row data out of a shared-memory ring, results published with one store
+//                    per lane -- that store is also the hand-off to other pencils.  SW = 1: one warp carries all NB
+//                    components (256-bit publish); SW = NB: one warp per component, each on its own scheduler -- a sweep
+//                    warp is issue-bound (one in-order instruction stream), so the three independent systems of a vector
+//                    solve advance at the pace of ONE (profiles/r2_pencil_sweeps.md)
+//   1 loader warp    lane 0 keeps the ring full with 1-D bulk copies (cp.async.bulk, one mbarrier per stage)
+//   2 fetch warps    poll the neighbour pencils' published rows several steps ahead and drop them into the ring of
+//                    external values the sweep warps read
 // Rows live in the pencil numbering of plan.h: row = base + 32*step + lane, so a stage of SS steps is one contiguous
 // range of every array.  Arithmetic per row = that of the tile kernels = the reference's: products rD*upper first,
 // subtractions in the order of the face loop (lower neighbour along z, then y, then x; backward: upper neighbour
@@ -135,6 +138,25 @@ __device__ __forceinline__ void pen_store_plain(double* p, const double (&v)[NB]
         *reinterpret_cast<double2*>(p + 2) = make_double2(v[NB - 1], 0.0);
     }
 }
+// components [k0, k0 + NBW) of a row (NBW == NB: the whole row with one store; NBW == 1: one component -- the last
+// component of a padded row carries the padding lane along so that it never holds the "not yet" pattern afterwards)
+template <int NB, int NBW>
+__device__ __forceinline__ void pen_publish_part(unsigned long long* p, int k0, const double (&v)[NBW])
+{
+    if (NBW == NB) { pen_publish<NBW>(p, v); return; }
+    if (NB == 3 && k0 == 2)
+        asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" :: "l"(p + 2), "l"(__double_as_longlong(v[0])), "l"(0LL) : "memory");
+    else
+        asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" :: "l"(p + k0), "l"(__double_as_longlong(v[0])) : "memory");
+}
+template <int NB, int NBW>
+__device__ __forceinline__ void pen_store_plain_part(double* p, int k0, const double (&v)[NBW])
+{
+    if (NBW == NB) { pen_store_plain<NBW>(p, v); return; }
+    if (NB == 3 && k0 == 2) *reinterpret_cast<double2*>(p + 2) = make_double2(v[0], 0.0);
+    else p[k0] = v[0];
+}
+
 __device__ __forceinline__ int pen_ld_progress(unsigned a)
 {
     int v;
@@ -156,14 +178,17 @@ __global__ void __launch_bounds__(TPB) k_pencil_coeffs(long long n3, const int* 
 // MODE 0 forward sweep (in = rA, out = y), 1 factor (in = diag, out = scratch, rDout = 1/out), 2 backward sweep
 // (in = y, out = wA; y re-armed; optional fused dot wA . rA).  LONG = which axis is the long one (0 x, 1 y, 2 z):
 // it fixes where the own-lane dependency sits in the reference's z, y, x subtraction order.
-template <int NB, int MODE, int LONG>
-__global__ void __launch_bounds__(PEN_TPB) k_dic_pencil(PencilArgs A, const double* __restrict__ diagOrRD, const double* __restrict__ rA,
+template <int NB, int MODE, int LONG, int SW>
+__global__ void __launch_bounds__((SW + 3)*32) k_dic_pencil(PencilArgs A, const double* __restrict__ diagOrRD, const double* __restrict__ rA,
                                                         unsigned long long* y, unsigned long long* out, double* __restrict__ rDout,
                                                         unsigned long long* tileTicket, double* partials, int partStride,
                                                         DevState* st, int gated)
 {
     constexpr int NS = PenRow<NB>::NS, RB = PenRow<NB>::BYTES;
     constexpr bool BWD = (MODE == 2), FACTOR = (MODE == 1);
+    constexpr int NTH = (SW + 3)*32;        // SW sweep warps + loader + two fetch warps
+    constexpr int NBW = NB/SW;              // components a sweep warp carries
+    static_assert(SW == 1 || SW == NB, "one sweep warp for all components, or one per component");
     if (gated)
     {
         bool d = true;
@@ -192,8 +217,17 @@ __global__ void __launch_bounds__(PEN_TPB) k_dic_pencil(PencilArgs A, const doub
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         slotPtr[1] = A.smCounter ? (int)(atomicAdd(A.smCounter + (smid & 1023u), 1u) & 3u) : 0;
     }
-    const int tile = take_tile(tileTicket, A.nPencils, slotPtr, BWD);
-    const int warp = ((int)(threadIdx.x >> 5) - slotPtr[1]) & 3;       // role: 0 sweep, 1 loader, 2-3 fetch
+    __syncthreads();
+    // roles: the first four warps (one per scheduler) rotate by the per-SM counter; role < SW: sweep warp of components
+    // [role*NBW, ...), role == SW: loader, the two roles above: fetch warps
+    const int wid = (int)(threadIdx.x >> 5);
+    const int warp = (wid < 4) ? ((wid - slotPtr[1]) & 3) : wid;
+    // Persistent CTAs: CTA b sweeps pencils b, b + G, b + 2G, ... of the wavefront order (reversed for the backward sweep).
+    // Every CTA of the grid is resident (the host sizes G by the occupancy) and takes its pencils in ascending wavefront
+    // order, so a pencil only ever waits on pencils that are done, running, or next in line of a running CTA: no deadlock.
+    for (int tileIdx = blockIdx.x; tileIdx < A.nPencils; tileIdx += gridDim.x)
+    {
+    const int tile = BWD ? A.nPencils - 1 - tileIdx : tileIdx;
     const int* M = A.meta + 8*tile;
     const int base = M[0], w1a = M[1], w2a = M[2];
     const int prodA1 = BWD ? M[5] : M[3], prodA2 = BWD ? M[6] : M[4];
@@ -206,20 +240,29 @@ __global__ void __launch_bounds__(PEN_TPB) k_dic_pencil(PencilArgs A, const doub
 
     if (threadIdx.x == 0)
     {
-        for (int s = 0; s < NST; s++) mbar_init(sBar + 8u*s, 1);
-        asm volatile("st.volatile.shared.s32 [%0], %1;" :: "r"(sProg), "r"(0) : "memory");
+        for (int s = 0; s < NST; s++)
+        {
+            if (tileIdx != (int)blockIdx.x) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(sBar + 8u*s) : "memory");
+            mbar_init(sBar + 8u*s, 1);
+        }
+        for (int i = 0; i < SW; i++) asm volatile("st.volatile.shared.s32 [%0], %1;" :: "r"(sProg + 4u*i), "r"(0) : "memory");
     }
     // the ring of external values starts out "not yet"
-    for (int i = threadIdx.x; i < PEN_R*E*NS; i += PEN_TPB) ((unsigned long long*)(smemRaw + NST*stageBytes))[i] = SENT;
+    for (int i = threadIdx.x; i < PEN_R*E*NS; i += NTH) ((unsigned long long*)(smemRaw + NST*stageBytes))[i] = SENT;
     __syncthreads();
 
     double dot[NB];
 #pragma unroll
     for (int k = 0; k < NB; k++) dot[k] = 0.0;
 
-    if (warp == 0)
+    // slowest sweep warp's progress (steps consumed)
+    auto progress = [&]() { int p = pen_ld_progress(sProg); for (int i = 1; i < SW; i++) p = min(p, pen_ld_progress(sProg + 4u*i)); return p; };
+
+    if (warp < SW)
     {
         // ------------------------------------------------------------------------------------------ the sweep
+        const int k0 = warp*NBW;                                   // first component of this sweep warp
+        const unsigned kOff = 8u*(unsigned)k0;
         // One warp, in-order issue: what a step costs is the number of instructions on it.  So: no index arithmetic in
         // the loop (running addresses, the four steps of a ring stage unrolled with immediate offsets), no divergence
         // (every lane reads "its" external slot -- interior lanes a constant slot -- and selects), and a two-deep software
@@ -232,7 +275,7 @@ __global__ void __launch_bounds__(PEN_TPB) k_dic_pencil(PencilArgs A, const doub
         const int srcA1 = (BWD ? lane + 1 : lane - 1) & 31, srcA2 = (BWD ? lane + A.w1 : lane - A.w1) & 31;
         // the constant slot interior lanes "poll": the last 32 bytes of the barrier block hold the neutral value
         const unsigned sConst = sBar + 64u + 32u;
-        if (lane < NS) asm volatile("st.shared.f64 [%0], %1;" :: "r"(sConst + 8u*lane), "d"(neutral) : "memory");
+        if (lane < NS) asm volatile("st.shared.f64 [%0], %1;" :: "r"(sConst + 8u*lane), "d"(neutral) : "memory");     // every sweep warp writes the same values
         __syncwarp();
         const unsigned stepRing = (unsigned)(E*RB);
         // per-lane ring addresses at ring position 0; interior lanes: the constant slot with a zero stride
@@ -241,26 +284,26 @@ __global__ void __launch_bounds__(PEN_TPB) k_dic_pencil(PencilArgs A, const doub
         const unsigned strA1 = intA1 ? 0u : stepRing, strA2 = intA2 ? 0u : stepRing;
         const unsigned ringBytes1 = intA1 ? 0u : (unsigned)(PEN_R*E*RB), ringBytes2 = intA2 ? 0u : (unsigned)(PEN_R*E*RB);
         unsigned rOff1 = 0u, rOff2 = 0u;                           // byte offset of the current stage's first step in the ring
-        double prev[NB];
+        double prev[NBW], dotW[NBW];
 #pragma unroll
-        for (int k = 0; k < NB; k++) prev[k] = neutral;
+        for (int k = 0; k < NBW; k++) { prev[k] = neutral; dotW[k] = 0.0; }
         // row data of a step out of the ring stage at sAddr: local step js (compile-time), this lane
-        double cf[3], dv[NB], in[NB], ra[NB];
+        double cf[3], dv[NBW], in[NBW], ra[NBW];
         auto load_static = [&](unsigned sAddr, int js)
         {
             const unsigned r = (unsigned)(js*32) + (unsigned)lane;
             asm volatile("ld.shared.f64 %0, [%1];" : "=d"(cf[0]) : "r"(sAddr + oCoef + 24u*r));
             asm volatile("ld.shared.f64 %0, [%1];" : "=d"(cf[1]) : "r"(sAddr + oCoef + 24u*r + 8u));
             asm volatile("ld.shared.f64 %0, [%1];" : "=d"(cf[2]) : "r"(sAddr + oCoef + 24u*r + 16u));
-            if (!FACTOR) pen_lds<NB>(sAddr + oDv + (unsigned)RB*r, dv);
-            pen_lds<NB>(sAddr + oIn + (unsigned)RB*r, in);
-            if (withDot) pen_lds<NB>(sAddr + oRA + (unsigned)RB*r, ra);
+            if (!FACTOR) pen_lds<NBW>(sAddr + oDv + (unsigned)RB*r + kOff, dv);
+            pen_lds<NBW>(sAddr + oIn + (unsigned)RB*r + kOff, in);
+            if (withDot) pen_lds<NBW>(sAddr + oRA + (unsigned)RB*r + kOff, ra);
         };
-        double F0[NB], F1[NB], F2[NB], acc0[NB], raC[NB];
+        double F0[NBW], F1[NBW], F2[NBW], acc0[NBW], raC[NBW];
         auto products = [&]()
         {
 #pragma unroll
-            for (int k = 0; k < NB; k++)
+            for (int k = 0; k < NBW; k++)
             {
                 if (FACTOR) { F0[k] = mul_here(cf[0], cf[0]); F1[k] = mul_here(cf[1], cf[1]); F2[k] = mul_here(cf[2], cf[2]); acc0[k] = canon(in[k]); }
                 else
@@ -290,14 +333,14 @@ __global__ void __launch_bounds__(PEN_TPB) k_dic_pencil(PencilArgs A, const doub
             for (int j = 0; j < PEN_SS; j++)
             {
                 // a. this step's external values (interior lanes: the constant slot)
-                const unsigned a1 = ringA1 + rOff1 + (unsigned)j*strA1, a2 = ringA2 + rOff2 + (unsigned)j*strA2;
-                double xA1[NB], xA2[NB];
-                pen_lds_volatile<NB>(a1, xA1);
-                pen_lds_volatile<NB>(a2, xA2);
+                const unsigned a1 = ringA1 + rOff1 + (unsigned)j*strA1 + kOff, a2 = ringA2 + rOff2 + (unsigned)j*strA2 + kOff;
+                double xA1[NBW], xA2[NBW];
+                pen_lds_volatile<NBW>(a1, xA1);
+                pen_lds_volatile<NBW>(a2, xA2);
                 // b. the previous step's results of the neighbouring lanes
-                double sA1[NB], sA2[NB];
+                double sA1[NBW], sA2[NBW];
 #pragma unroll
-                for (int k = 0; k < NB; k++)
+                for (int k = 0; k < NBW; k++)
                 {
                     sA1[k] = __shfl_sync(0xffffffffu, prev[k], srcA1);
                     sA2[k] = __shfl_sync(0xffffffffu, prev[k], srcA2);
@@ -314,21 +357,21 @@ __global__ void __launch_bounds__(PEN_TPB) k_dic_pencil(PencilArgs A, const doub
                 {
                     bool ny = false;
 #pragma unroll
-                    for (int k = 0; k < NB; k++) ny = ny | hi_is_sent(xA1[k]) | hi_is_sent(xA2[k]);
+                    for (int k = 0; k < NBW; k++) ny = ny | hi_is_sent(xA1[k]) | hi_is_sent(xA2[k]);
                     while (__any_sync(0xffffffffu, ny))
                     {
-                        pen_lds_volatile<NB>(a1, xA1);
-                        pen_lds_volatile<NB>(a2, xA2);
+                        pen_lds_volatile<NBW>(a1, xA1);
+                        pen_lds_volatile<NBW>(a2, xA2);
                         ny = false;
 #pragma unroll
-                        for (int k = 0; k < NB; k++) ny = ny | hi_is_sent(xA1[k]) | hi_is_sent(xA2[k]);
+                        for (int k = 0; k < NBW; k++) ny = ny | hi_is_sent(xA1[k]) | hi_is_sent(xA2[k]);
                     }
                 }
                 // e. the chain, in the reference's order z, y, x; LONG tells which of them is the own-lane dependency:
                 //    (z, y, x) = (A2, A1, own) for LONG 0, (A2, own, A1) for LONG 1, (own, A2, A1) for LONG 2
-                double res[NB];
+                double res[NBW];
 #pragma unroll
-                for (int k = 0; k < NB; k++)
+                for (int k = 0; k < NBW; k++)
                 {
                     const double vA1 = intA1 ? sA1[k] : xA1[k], vA2 = intA2 ? sA2[k] : xA2[k];
                     const double vz = (LONG == 2) ? prev[k] : vA2;
@@ -348,27 +391,27 @@ __global__ void __launch_bounds__(PEN_TPB) k_dic_pencil(PencilArgs A, const doub
                         a = __dsub_rn(a, __dmul_rn(F2[k], vx));
                     }
                     res[k] = a;
-                    if (withDot) dot[k] += a*raC[k];
+                    if (withDot) dotW[k] += a*raC[k];
                 }
                 // f. the next step's products, behind the chain
                 if (more) products();
 #pragma unroll
-                for (int k = 0; k < NB; k++) prev[k] = res[k];
+                for (int k = 0; k < NBW; k++) prev[k] = res[k];
                 // g. publish: the result of the sweep AND the hand-off to the neighbouring pencils; re-arm the slots
-                pen_publish<NB>(out + (size_t)NS*rowG, prev);
+                pen_publish_part<NB, NBW>(out + (size_t)NS*rowG, k0, prev);
                 if (FACTOR)
                 {
-                    double r[NB];
+                    double r[NBW];
 #pragma unroll
-                    for (int k = 0; k < NB; k++) r[k] = __ddiv_rn(1.0, prev[k]);
-                    pen_store_plain<NB>(rDout + (size_t)NS*rowG, r);
+                    for (int k = 0; k < NBW; k++) r[k] = __ddiv_rn(1.0, prev[k]);
+                    pen_store_plain_part<NB, NBW>(rDout + (size_t)NS*rowG, k0, r);
                 }
                 {
-                    unsigned long long w[NB];
+                    unsigned long long w[NBW];
 #pragma unroll
-                    for (int k = 0; k < NB; k++) w[k] = SENT;
-                    if (!intA1) pen_sts_bits<NB>(a1, w);
-                    if (!intA2) pen_sts_bits<NB>(a2, w);
+                    for (int k = 0; k < NBW; k++) w[k] = SENT;
+                    if (!intA1) pen_sts_bits<NBW>(a1, w);
+                    if (!intA2) pen_sts_bits<NBW>(a2, w);
                 }
                 rowG = (size_t)((long long)rowG + rowStep);
             }
@@ -379,8 +422,16 @@ __global__ void __launch_bounds__(PEN_TPB) k_dic_pencil(PencilArgs A, const doub
 #pragma unroll
                 for (int j = 0; j < PEN_SS; j++)
                 {
+                    if (NBW == NB)
+                    {
 #pragma unroll
-                    for (int k = 0; k < NS; k++) q[(size_t)NS*32*j + k] = SENT;
+                        for (int k = 0; k < NS; k++) q[(size_t)NS*32*j + k] = SENT;
+                    }
+                    else
+                    {
+                        q[(size_t)NS*32*j + k0] = SENT;
+                        if (k0 + 1 == NB && NS > NB) q[(size_t)NS*32*j + NB] = SENT;       // the padding lane travels with the last component
+                    }
                 }
             }
             rOff1 += PEN_SS*strA1; if (rOff1 >= ringBytes1) rOff1 = 0u;
@@ -389,10 +440,13 @@ __global__ void __launch_bounds__(PEN_TPB) k_dic_pencil(PencilArgs A, const doub
             // all lanes' re-arming stores precede the progress store: shared-memory accesses of one warp are performed
             // in order (no membar: it would wait for the global stores in flight)
             __syncwarp();
-            if (lane == 0) asm volatile("st.volatile.shared.s32 [%0], %1;" :: "r"(sProg), "r"((g + 1)*PEN_SS) : "memory");
+            if (lane == 0) asm volatile("st.volatile.shared.s32 [%0], %1;" :: "r"(sProg + 4u*(unsigned)warp), "r"((g + 1)*PEN_SS) : "memory");
         }
+        // this warp's share of the fused dot (static indexing: dot[] stays in registers)
+#pragma unroll
+        for (int k = 0; k < NB; k++) dot[k] = (NBW == NB) ? dotW[k % NBW] : ((k == k0) ? dotW[0] : 0.0);
     }
-    else if (warp == 1)
+    else if (warp == SW)
     {
         // ------------------------------------------------------------------------------------------ the loader
         if (lane == 0)
@@ -403,7 +457,7 @@ __global__ void __launch_bounds__(PEN_TPB) k_dic_pencil(PencilArgs A, const doub
             {
                 const int s = g % NST;
                 if (g >= NST)
-                    while (pen_ld_progress(sProg) < (g - NST + 1)*PEN_SS) { __nanosleep(200); }
+                    while (progress() < (g - NST + 1)*PEN_SS) { __nanosleep(200); }
                 const int tFirst = BWD ? steps - PEN_SS*(g + 1) : PEN_SS*g;
                 const size_t r0 = (size_t)base + (size_t)32*tFirst;
                 const unsigned dst = sb + (unsigned)(s*stageBytes), bar = sBar + 8u*s;
@@ -418,7 +472,7 @@ __global__ void __launch_bounds__(PEN_TPB) k_dic_pencil(PencilArgs A, const doub
     else
     {
         // ------------------------------------------------------------------------------------------ the fetch lanes
-        const int fl = (warp - 2)*32 + lane;
+        const int fl = (warp - SW - 1)*32 + lane;
         const int SPR = 64/E;                                   // steps covered by one round of the 64 fetch lanes
         if (SPR > 0 && fl < SPR*E)
         {
@@ -446,7 +500,7 @@ __global__ void __launch_bounds__(PEN_TPB) k_dic_pencil(PencilArgs A, const doub
             const bool adaptive = A.fetchWindow <= 0;
             while (next < steps)
             {
-                const int prog = pen_ld_progress(sProg);
+                const int prog = progress();
                 unsigned long long w[PEN_FU][NB];
                 bool can[PEN_FU];
                 int issued = 0;
@@ -490,10 +544,12 @@ __global__ void __launch_bounds__(PEN_TPB) k_dic_pencil(PencilArgs A, const doub
         if (NB == 1)
         {
             double d1[1] = {dot[0]};
-            grid_reduce_finish<1, PEN_TPB>(d1, partials, partStride, tile, A.nPencils, st, S_SWEEP, nullptr);
+            grid_reduce_finish<1, NTH>(d1, partials, partStride, tile, A.nPencils, st, S_SWEEP, nullptr);
         }
         else
-            grid_reduce_finish_v<1, NB, PEN_TPB>(dot, partials, partStride, tile, A.nPencils, st, S_SWEEP, nullptr, 0);
+            grid_reduce_finish_v<1, NB, NTH>(dot, partials, partStride, tile, A.nPencils, st, S_SWEEP, nullptr, 0);
+    }
+    __syncthreads();        // every role is done with this pencil's ring, barriers and progress words
     }
 }
 
