@@ -885,8 +885,8 @@ static int launch_pencil(gpupcg_handle h, const double* diagOrRD, const double* 
     // upstream, the whole wavefront with them -- so by default no more CTAs per SM than keep the sweep warps <= 4.
     int occ = 0, grid = 1;
     const int perSmWanted = std::max(1, env_int("GPUPCG_PENCIL_CTAS_PER_SM", split ? std::max(1, 4/NB) : 2));
-#define PEN_OCC(LONG_, SW_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (k_dic_pencil<NB, MODE, LONG_, SW_>), (SW_ + 3)*32, smem)
-#define PEN_GO(LONG_, SW_) k_dic_pencil<NB, MODE, LONG_, SW_><<<grid, (SW_ + 3)*32, smem, h->stream>>>(A, diagOrRD, rA, y, out, rDout, h->dTileTicket, partials, h->partStride, st, gated)
+#define PEN_OCC(LONG_, SW_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (k_dic_pencil<NB, MODE, LONG_, SW_>), (SW_ + 1 + PEN_FW)*32, smem)
+#define PEN_GO(LONG_, SW_) k_dic_pencil<NB, MODE, LONG_, SW_><<<grid, (SW_ + 1 + PEN_FW)*32, smem, h->stream>>>(A, diagOrRD, rA, y, out, rDout, h->dTileTicket, partials, h->partStride, st, gated)
 #define PEN_RUN(LONG_, SW_) do { CK(PEN_OCC(LONG_, SW_)); if (occ < 1) { h->err = "pencil sweep: no CTA fits an SM"; return GPUPCG_ERR_UNSUPPORTED; } \
         grid = std::min(A.nPencils, h->numSMs*std::min(occ, perSmWanted)); PEN_GO(LONG_, SW_); } while (0)
     switch (h->plan.pLong)

@@ -38,6 +38,9 @@ constexpr int PEN_TPB = 128;
 constexpr int PEN_SS = 4;           // steps per ring stage (the plan pads a pencil to a multiple of it)
 constexpr int PEN_R = 32;           // steps held by the ring of external values (power of two, multiple of PEN_SS)
 constexpr int PEN_FU = 4;           // polls a fetch lane keeps in flight
+#ifndef PEN_FW
+#define PEN_FW 2                    // fetch warps per CTA
+#endif
 
 struct PencilArgs
 {
@@ -179,14 +182,14 @@ __global__ void __launch_bounds__(TPB) k_pencil_coeffs(long long n3, const int* 
 // (in = y, out = wA; y re-armed; optional fused dot wA . rA).  LONG = which axis is the long one (0 x, 1 y, 2 z):
 // it fixes where the own-lane dependency sits in the reference's z, y, x subtraction order.
 template <int NB, int MODE, int LONG, int SW>
-__global__ void __launch_bounds__((SW + 3)*32) k_dic_pencil(PencilArgs A, const double* __restrict__ diagOrRD, const double* __restrict__ rA,
+__global__ void __launch_bounds__((SW + 1 + PEN_FW)*32) k_dic_pencil(PencilArgs A, const double* __restrict__ diagOrRD, const double* __restrict__ rA,
                                                         unsigned long long* y, unsigned long long* out, double* __restrict__ rDout,
                                                         unsigned long long* tileTicket, double* partials, int partStride,
                                                         DevState* st, int gated)
 {
     constexpr int NS = PenRow<NB>::NS, RB = PenRow<NB>::BYTES;
     constexpr bool BWD = (MODE == 2), FACTOR = (MODE == 1);
-    constexpr int NTH = (SW + 3)*32;        // SW sweep warps + loader + two fetch warps
+    constexpr int NTH = (SW + 1 + PEN_FW)*32;   // SW sweep warps + loader + PEN_FW fetch warps
     constexpr int NBW = NB/SW;              // components a sweep warp carries
     static_assert(SW == 1 || SW == NB, "one sweep warp for all components, or one per component");
     if (gated)
@@ -473,7 +476,7 @@ __global__ void __launch_bounds__((SW + 3)*32) k_dic_pencil(PencilArgs A, const 
     {
         // ------------------------------------------------------------------------------------------ the fetch lanes
         const int fl = (warp - SW - 1)*32 + lane;
-        const int SPR = 64/E;                                   // steps covered by one round of the 64 fetch lanes
+        const int SPR = (PEN_FW*32)/E;                          // steps covered by one round of the fetch lanes
         if (SPR > 0 && fl < SPR*E)
         {
             const int e = fl % E, off = fl/E;
