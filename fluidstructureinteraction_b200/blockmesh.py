@@ -222,10 +222,65 @@ def _boundary_quads(n, off):
     return out
 
 
+# cell models [EXT cellModels]: faces of a shape in terms of its point list, outward
+SHAPE_FACES = {
+    "hex": [[0, 4, 7, 3], [1, 2, 6, 5], [0, 1, 5, 4], [3, 7, 6, 2], [0, 3, 2, 1], [4, 5, 6, 7]],
+    "prism": [[0, 2, 1], [3, 4, 5], [0, 3, 5, 2], [1, 2, 5, 4], [0, 1, 4, 3]],
+    "pyr": [[0, 3, 2, 1], [0, 4, 3], [3, 4, 2], [1, 2, 4], [0, 1, 4]],
+    "tet": [[1, 2, 3], [0, 3, 2], [0, 1, 3], [0, 2, 1]],
+}
+
+
+def polymesh_from_shapes(points, shapes, patchFaces, patchNames, patchTypes, defaultPatch=None):
+    """[EXT polyMeshFromShapeMesh.C] shapes: list of (model name, point ids); patchFaces: per patch a list of faces (point
+    ids, any rotation / orientation).  Internal faces upper-triangular (per cell, ascending neighbour), face loop = the
+    owner's model face; boundary faces in the given order, loop = the inside cell's model face; boundary faces that belong
+    to no patch go to `defaultPatch` = (name, type) in cell order (error if None)."""
+    faces, cell = [], []
+    for c, (model, pts) in enumerate(shapes):
+        for mf in SHAPE_FACES[model]:
+            faces.append([pts[i] for i in mf]); cell.append(c)
+    nC = len(shapes)
+    cell = np.array(cell, dtype=np.int64)
+    keys = [tuple(sorted(f)) for f in faces]
+    first = {}
+    pairs = []                                   # (owner face index, neighbour face index)
+    for i, k in enumerate(keys):
+        j = first.pop(k, None)
+        if j is None:
+            first[k] = i
+        else:
+            pairs.append((j, i))
+    pairs.sort(key=lambda ab: (cell[ab[0]], cell[ab[1]]))
+    own = [int(cell[a]) for a, b in pairs]; nei = [int(cell[b]) for a, b in pairs]
+    faceLoops = [faces[a] for a, b in pairs]
+    bnd = dict(first)                            # key -> face index of the free boundary faces
+    patches = []
+    start = len(own)
+    for name, ptype, flist in zip(patchNames, patchTypes, patchFaces):
+        n0 = len(own)
+        for f in flist:
+            i = bnd.pop(tuple(sorted(int(v) for v in f)), None)
+            if i is None:
+                raise ValueError("patch %s: face %s is not a free boundary face" % (name, list(f)))
+            own.append(int(cell[i])); faceLoops.append(faces[i])
+        patches.append(dict(name=name, type=ptype, start=start, size=len(own) - n0))
+        start = len(own)
+    if bnd:
+        if defaultPatch is None:
+            raise ValueError("%d boundary faces belong to no patch (blockMesh would collect them in defaultFaces)" % len(bnd))
+        rest = sorted(bnd.values())
+        for i in rest:
+            own.append(int(cell[i])); faceLoops.append(faces[i])
+        patches.append(dict(name=defaultPatch[0], type=defaultPatch[1], start=start, size=len(rest)))
+    faceStart = np.zeros(len(faceLoops) + 1, dtype=np.int64)
+    np.cumsum([len(f) for f in faceLoops], out=faceStart[1:])
+    facePoints = np.array([v for f in faceLoops for v in f], dtype=np.int64)
+    return PolyMesh(points, faceStart, facePoints, np.array(own, dtype=np.int64), np.array(nei, dtype=np.int64), patches, nC)
+
+
 def polymesh_from_hexes(points, hexes, patchQuads, patchNames, patchTypes):
-    """[EXT polyMeshFromShapeMesh.C] hexes (nC,8) point ids in hex-model order; patchQuads: per patch (m,4) point ids (any
-    rotation / orientation).  Internal faces upper-triangular, face loop = owner's model face; boundary faces in the given
-    order, loop = the inside cell's model face."""
+    """Hex-only front end of polymesh_from_shapes (vectorised: blocks of a blockMesh run into millions of cells)."""
     nC = hexes.shape[0]
     fv = hexes[:, HEX_FACES].reshape(-1, 4)                 # face 6c + m of cell c
     cell = np.repeat(np.arange(nC, dtype=np.int64), 6)

@@ -335,5 +335,78 @@ def read_polymesh(polyMeshDir):
     entries = foamdict.parse("boundary " + text[text.index("("):] + ";")["boundary"]
     patches = []
     for name, d in zip(entries[0::2], entries[1::2]):
-        patches.append(dict(name=str(name), type=str(d.get("type", "patch")), start=int(d["startFace"]), size=int(d["nFaces"])))
+        pt = dict(name=str(name), type=str(d.get("type", "patch")), start=int(d["startFace"]), size=int(d["nFaces"]))
+        for k in ("myProcNo", "neighbProcNo"):          # processorPolyPatch entries (processorN/constant/polyMesh/boundary)
+            if k in d:
+                pt[k] = int(d[k])
+        patches.append(pt)
     return PolyMesh(pts, np.array(faceStart), np.array(facePoints, dtype=np.int64), owner, neighbour, patches)
+
+
+# ------------------------------------------------------------------------------------------------
+# OpenFOAM ASCII polyMesh writer (what decomposePar / blockMesh write: constant/polyMesh/*)
+# ------------------------------------------------------------------------------------------------
+_BANNER = """/*--------------------------------*- C++ -*----------------------------------*\\
+| =========                 |                                                 |
+| \\\\      /  F ield         | foam-extend: Open Source CFD                    |
+|  \\\\    /   O peration     | Version:     3.1                                |
+|   \\\\  /    A nd           | Web:         http://www.extend-project.de       |
+|    \\\\/     M anipulation  |                                                 |
+\\*---------------------------------------------------------------------------*/
+"""
+
+
+def _header(cls, obj, location="constant/polyMesh", note=None):
+    h = _BANNER + "FoamFile\n{\n    version     2.0;\n    format      ascii;\n    class       %s;\n" % cls
+    if note:
+        h += "    note        \"%s\";\n" % note
+    h += "    location    \"%s\";\n    object      %s;\n}\n" % (location, obj)
+    return h + "// * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * //\n\n"
+
+
+_FOOTER = "\n\n// ************************************************************************* //\n"
+
+
+def write_label_list(path, a, obj, cls="labelList", note=None):
+    a = np.asarray(a)
+    with open(path, "w") as f:
+        f.write(_header(cls, obj, note=note))
+        f.write("%d\n(\n" % a.shape[0])
+        f.write("\n".join(str(int(v)) for v in a))
+        f.write("\n)" + _FOOTER)
+
+
+def read_label_list(path):
+    n, body = _read_list_body(path)
+    a = np.array(body.split(), dtype=np.int64)
+    assert a.shape[0] == n, path
+    return a.astype(np.int32)
+
+
+def write_polymesh(polyMeshDir, mesh):
+    os.makedirs(polyMeshDir, exist_ok=True)
+    note = "nPoints: %d nCells: %d nFaces: %d nInternalFaces: %d" % (mesh.nPoints, mesh.nCells, mesh.nFaces, mesh.nInternalFaces)
+    with open(os.path.join(polyMeshDir, "points"), "w") as f:
+        f.write(_header("vectorField", "points"))
+        f.write("%d\n(\n" % mesh.nPoints)
+        f.write("\n".join("(%s %s %s)" % (repr(float(p[0])), repr(float(p[1])), repr(float(p[2]))) for p in mesh.points))
+        f.write("\n)" + _FOOTER)
+    with open(os.path.join(polyMeshDir, "faces"), "w") as f:
+        f.write(_header("faceList", "faces"))
+        f.write("%d\n(\n" % mesh.nFaces)
+        fs, fp = mesh.faceStart, mesh.facePoints
+        f.write("\n".join("%d(%s)" % (fs[i + 1] - fs[i], " ".join(str(int(v)) for v in fp[fs[i]:fs[i + 1]])) for i in range(mesh.nFaces)))
+        f.write("\n)" + _FOOTER)
+    write_label_list(os.path.join(polyMeshDir, "owner"), mesh.owner, "owner", note=note)
+    write_label_list(os.path.join(polyMeshDir, "neighbour"), mesh.neighbour, "neighbour", note=note)
+    with open(os.path.join(polyMeshDir, "boundary"), "w") as f:
+        f.write(_header("polyBoundaryMesh", "boundary"))
+        f.write("%d\n(\n" % len(mesh.patches))
+        for p in mesh.patches:
+            f.write("    %s\n    {\n        type            %s;\n        nFaces          %d;\n        startFace       %d;\n"
+                    % (p["name"], p["type"], p["size"], p["start"]))
+            for k in ("myProcNo", "neighbProcNo"):
+                if k in p:
+                    f.write("        %-15s %d;\n" % (k, p[k]))
+            f.write("    }\n")
+        f.write(")" + _FOOTER)
