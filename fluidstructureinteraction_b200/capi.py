@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgpupcg_cuda.so")
+LIB_PATH = os.environ.get("GPUPCG_LIBRARY") or os.path.join(_HERE, "libgpupcg_cuda.so")     # GPUPCG_LIBRARY: A/B builds (tools/)
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)

@@ -25,6 +25,18 @@ namespace
 {
 
 constexpr int ATPB = 256;
+#ifndef GRAD_CELLS_MINB
+#define GRAD_CELLS_MINB 5
+#endif
+#ifndef FGRAD_MINB
+#define FGRAD_MINB 3
+#endif
+#ifndef ASM_CELLS_MINB
+#define ASM_CELLS_MINB 3
+#endif
+#ifndef ASM_FACES_MINB
+#define ASM_FACES_MINB 5
+#endif
 constexpr double A_SMALL = 1.0e-15;
 
 __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
@@ -104,7 +116,7 @@ __device__ void symmetry_snGrad(const MeshDev& M, int f, const double* __restric
 // cell is in this chunk (recomputed here: 1-2 % of the faces), then the boundary faces of the chunk's cells.
 struct AsmChunk { int c0, c1, f0, nOwn, extraStart, nExtra; };
 
-__global__ void __launch_bounds__(ATPB) k_asm_faces(MeshDev M, AsmChunk K, const int* __restrict__ extraFace,
+__global__ void __launch_bounds__(ATPB, ASM_FACES_MINB) k_asm_faces(MeshDev M, AsmChunk K, const int* __restrict__ extraFace,
                                                     const double* __restrict__ mu, const double* __restrict__ lambda,
                                                     const double* __restrict__ D, const double* __restrict__ gradD,
                                                     const double* __restrict__ gradDf, double limitCoeff,
@@ -193,7 +205,7 @@ __global__ void __launch_bounds__(ATPB) k_asm_faces(MeshDev M, AsmChunk K, const
 
 // cellSlot[k] (parallel to the cell -> face CSR): ring slot of the face | bit 31: the cell is the face's neighbour |
 // bit 30: boundary face
-__global__ void __launch_bounds__(ATPB) k_asm_cells(MeshDev M, AsmChunk K, AsmCtl T, const double* __restrict__ Dold,
+__global__ void __launch_bounds__(ATPB, ASM_CELLS_MINB) k_asm_cells(MeshDev M, AsmChunk K, AsmCtl T, const double* __restrict__ Dold,
                                                     const double* __restrict__ Doldold, const int* __restrict__ cellSlot,
                                                     const double* __restrict__ rho, double g0, double g1, double g2,
                                                     const double* __restrict__ Lup, const double* __restrict__ upperSingle,
@@ -682,7 +694,7 @@ __device__ void patch_snGrad(const MeshDev& M, int f, const double* __restrict__
 // K6: fvc::grad(D, pointD) -- one thread per cell gathers its faces in the order the reference's face loop visits it
 // gather-latency bound (cell -> faces -> points -> values): small blocks, as many as fit
 constexpr int GTPB = 128;
-__global__ void __launch_bounds__(GTPB, 5) k_grad_cells(MeshDev M, const double* __restrict__ pointD, double* __restrict__ gradD)
+__global__ void __launch_bounds__(GTPB, GRAD_CELLS_MINB) k_grad_cells(MeshDev M, const double* __restrict__ pointD, double* __restrict__ gradD)
 {
     for (int c = blockIdx.x*GTPB + threadIdx.x; c < M.nCells; c += gridDim.x*GTPB)
     {
@@ -724,7 +736,7 @@ __global__ void __launch_bounds__(ATPB) k_grad_patches(MeshDev M, const double* 
 }
 
 // K7: fvc::fGrad(D, pointD) -- one thread per face: tangential part + n*snGrad(D) (skewCorrected scheme / patch snGrad)
-__global__ void __launch_bounds__(ATPB) k_fgrad_faces(MeshDev M, const double* __restrict__ D, const double* __restrict__ pointD,
+__global__ void __launch_bounds__(ATPB, FGRAD_MINB) k_fgrad_faces(MeshDev M, const double* __restrict__ D, const double* __restrict__ pointD,
                                                       const double* __restrict__ gradD, const double* __restrict__ fixedValue,
                                                       const double* __restrict__ patchGradient, double limitCoeff,
                                                       double* __restrict__ gradDf)
