@@ -227,6 +227,21 @@ extern "C" int gpupcg_destroy(gpupcg_handle h)
     return GPUPCG_OK;
 }
 
+// after a synchronised solve: did a device-side wait give up?  (kernels.cuh: SpinWatch)
+static int check_watchdog(gpupcg_handle h, const char* where)
+{
+    unsigned int f = 0;
+    CK(cudaMemcpyFromSymbol(&f, g_spinFault, sizeof(f)));
+    if (!f) return GPUPCG_OK;
+    const unsigned int zero = 0u;
+    CK(cudaMemcpyToSymbol(g_spinFault, &zero, sizeof(zero)));
+    static const char* what[] = {"", "a peer rank's mailbox flag (cross-rank reduction)", "a cross-tile value (tile sweeps)",
+                                 "a cross-tile row (batched tile sweeps)", "a neighbour pencil's row (pencil sweeps)", "a published value"};
+    h->err = std::string(where) + ": a device-side wait for " + what[f < 6 ? f : 5] +
+             " timed out (GPUPCG_SPIN_TIMEOUT_MS); the kernels ran to their end on zeros and the result is invalid";
+    return GPUPCG_ERR_STATE;
+}
+
 static int round_up(int v, int m) { return ((std::max(v, 1) + m - 1)/m)*m; }
 
 // The Amul kernel's view of the matrix.  Its tiles are its own: every sweep tile cut into pieces of <= amulRows rows
@@ -428,6 +443,12 @@ static int create_impl(gpupcg_handle h, int device, int nCells, int nFaces, cons
     {
         int ns = env_int("GPUPCG_SPIN_NS", 0);
         CK(cudaMemcpyToSymbol(g_spinNs, &ns, sizeof(int)));
+        // watchdog of the device-side waits (kernels.cuh: SpinWatch)
+        const unsigned long long tns = 1000000ULL*(unsigned long long)std::max(0, env_int("GPUPCG_SPIN_TIMEOUT_MS", 20000));
+        const unsigned int mask = (unsigned int)std::max(0, env_int("GPUPCG_SPIN_CHECK_MASK", 1023)), zero = 0u;
+        CK(cudaMemcpyToSymbol(g_spinTimeoutNs, &tns, sizeof(tns)));
+        CK(cudaMemcpyToSymbol(g_spinCheckMask, &mask, sizeof(mask)));
+        CK(cudaMemcpyToSymbol(g_spinFault, &zero, sizeof(zero)));
     }
     if (h->pencil)
     {
@@ -1107,7 +1128,7 @@ static int solve_core(gpupcg_handle h, double tol, double relTol, int minIter, i
         perf->singular = st.singular;
         perf->solve_ms = ms;
     }
-    return GPUPCG_OK;
+    return check_watchdog(h, "gpupcg_solve");
 }
 
 extern "C" int gpupcg_solve_device(gpupcg_handle h, double* d_x, const double* d_b, double tol, double relTol,

@@ -376,7 +376,7 @@ int vec_solve_core(gpupcg_handle h, double tol, double relTol, int minIter, int 
             perf[k].solve_ms = ms;      // the components share the launch sequence: device time of the whole vector solve
         }
     }
-    return GPUPCG_OK;
+    return check_watchdog(h, "gpupcg_solve_vector");
 }
 
 // sequential scalar solves of the components on the same kernels (meshes / set-ups the batched kernels do not cover)

@@ -114,6 +114,36 @@ __device__ __forceinline__ void dev_scalar_step(DevState* st, int step, const do
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Watchdog of the device-side waits.  Every wait of the library is rooted in a poll of GLOBAL memory (a fetch lane waiting
+// for another tile's / pencil's row, a rank waiting for a peer's mailbox flag); everything else waits on those.  A root
+// wait that makes no progress for g_spinTimeoutNs (a dead peer, a schedule bug) records its code in g_spinFault and lets
+// go: it delivers zeros, the kernel runs to its end on garbage, and the host returns GPUPCG_ERR_STATE instead of hanging
+// the GPU.  Cost: a counter in the retry path of the poll; %globaltimer is read once every (mask + 1) failed polls.
+// ------------------------------------------------------------------------------------------
+__device__ unsigned int g_spinFault = 0;                       // 0, or the code of the first wait that timed out
+__device__ unsigned long long g_spinTimeoutNs = 20000000000ULL;
+__device__ unsigned int g_spinCheckMask = 1023u;
+enum SpinCode { SPIN_P2P = 1, SPIN_TILE_FETCH = 2, SPIN_TILE_FETCH_V = 3, SPIN_PENCIL_FETCH = 4, SPIN_GLOBAL = 5 };
+
+struct SpinWatch
+{
+    unsigned int n = 0;
+    unsigned long long t0 = 0;
+    // call after every failed poll; true: give up
+    __device__ __forceinline__ bool expired(int code)
+    {
+        if ((++n & g_spinCheckMask) != 0u) return false;
+        if (*(volatile unsigned int*)&g_spinFault) return true;         // somebody else already gave up: follow at once
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t0 == 0) { t0 = t; return false; }
+        if (t - t0 > g_spinTimeoutNs) { atomicCAS(&g_spinFault, 0u, (unsigned int)code); return true; }
+        return false;
+    }
+    __device__ __forceinline__ void progress() { t0 = 0; }
+};
+
 // One-shot all-reduce of st->red[0..count) through the peers' mailboxes (comm.h), by ONE thread: write my values and
 // then my flag (= sequence number, release at system scope) into every rank's mailbox, wait for every rank's flag in my
 // own mailbox, sum in rank order.  Every rank gets the same bits.
@@ -134,7 +164,9 @@ __device__ __forceinline__ void p2p_allreduce(P2PDev* c, const double* mine, int
     for (int r = 0; r < c->nRanks; r++)
     {
         unsigned long long f;
-        do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&own->flag[par][r]) : "memory"); } while (f != seq);
+        SpinWatch watch;
+        do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&own->flag[par][r]) : "memory"); }
+        while (f != seq && !watch.expired(SPIN_P2P));
         for (int k = 0; k < count; k++)
         {
             double v;
@@ -344,8 +376,10 @@ __device__ __forceinline__ unsigned long long wait_global(const unsigned long lo
 {
     unsigned long long v = peek64(p);
     const int ns = g_spinNs;
+    SpinWatch watch;
     while (v == SENT)
     {
+        if (watch.expired(SPIN_GLOBAL)) return 0ULL;
         if (ns > 0) __nanosleep(ns);
         v = peek64(p);
     }
@@ -1178,11 +1212,14 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
         // the address of the lane's NEXT entry is fetched while it waits for the current one: advancing must not put
         // a global-load latency into the poll loop of the whole warp
         int colNext = (i + stride < nExt) ? extCol[xBase + i + stride] : 0;
+        SpinWatch watch;
+        bool bail = false;
         while (i < nExt)
         {
-            const unsigned long long v = peek64(p);
+            const unsigned long long v = bail ? 0ULL : peek64(p);
             if (v != SENT)
             {
+                watch.progress();
                 sts_u64(vb + 8u*(T + i), v);
 #ifdef GPUPCG_DEEPTRACE
                 if (MODE == 0 && g_tileTimes) g_tileTimes[3*A.nTiles + A.tileStart[A.nTiles] + xBase + i] = gtime();
@@ -1191,6 +1228,7 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile(TileArgs A, const double
                 p = out + colNext;
                 if (i + stride < nExt) colNext = extCol[xBase + i + stride];
             }
+            else if (watch.expired(SPIN_TILE_FETCH)) bail = true;
             else if (ns > 0) __nanosleep(ns);
         }
     }

@@ -501,6 +501,8 @@ __global__ void __launch_bounds__((SW + 1 + PEN_FW)*32) k_dic_pencil(PencilArgs 
             // with the full window.
             int next = off, W = A.fetchWindow > 0 ? A.fetchWindow : 1;
             const bool adaptive = A.fetchWindow <= 0;
+            SpinWatch watch;
+            bool bail = false;
             while (next < steps)
             {
                 const int prog = progress();
@@ -517,7 +519,7 @@ __global__ void __launch_bounds__((SW + 1 + PEN_FW)*32) k_dic_pencil(PencilArgs 
                         issued++;
                         const int t = BWD ? steps - 1 - i : i;
                         const int q = t - qoff;
-                        const bool valid = prod >= 0 && laneActive && q >= 0 && q < A.n0;
+                        const bool valid = prod >= 0 && laneActive && q >= 0 && q < A.n0 && !bail;
                         if (valid) pen_peek<NB>(out + (size_t)NS*(pbase + (size_t)32*(t + dt) + lanep), w[u]);
                         else { for (int k = 0; k < NB; k++) w[u][k] = nb[k]; }
                     }
@@ -537,6 +539,8 @@ __global__ void __launch_bounds__((SW + 1 + PEN_FW)*32) k_dic_pencil(PencilArgs 
                 }
                 next += m*SPR;
                 if (adaptive) W = (issued > 0 && m == issued) ? min(PEN_FU, W + 1) : max(1, m);
+                if (m > 0) watch.progress();
+                else if (issued > 0 && watch.expired(SPIN_PENCIL_FETCH)) bail = true;   // (issued == 0: waiting for this CTA's own sweep)
                 if (m == 0) __nanosleep(A.fetchSleep);
             }
         }

@@ -848,15 +848,19 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile_v(TileArgs A, const doub
         const int ns = g_spinNs;
         const unsigned long long* p = (i < nExt) ? out + (size_t)NS*extCol[xBase + i] : nullptr;
         int colNext = (i + stride < nExt) ? extCol[xBase + i + stride] : 0;
+        SpinWatch watch;
+        bool bail = false;
         while (i < nExt)
         {
             unsigned long long w[NB];
-            peek_row<NB>(p, w);
+            if (bail) { for (int k = 0; k < NB; k++) w[k] = 0ULL; }
+            else peek_row<NB>(p, w);
             bool ok = true;
 #pragma unroll
             for (int k = 0; k < NB; k++) ok = ok && (w[k] != SENT);
             if (ok)
             {
+                watch.progress();
                 const unsigned dst = vb + 8u*NS*(T + i);
                 asm volatile("st.volatile.shared.v2.b64 [%0], {%1, %2};" :: "r"(dst), "l"(w[0]), "l"(w[1]) : "memory");
                 if (NB == 3) sts_u64(dst + 16u, w[NB - 1]);
@@ -864,6 +868,7 @@ __global__ void __launch_bounds__(SWEEP_TPB) k_dic_tile_v(TileArgs A, const doub
                 p = out + (size_t)NS*colNext;
                 if (i + stride < nExt) colNext = extCol[xBase + i + stride];
             }
+            else if (watch.expired(SPIN_TILE_FETCH_V)) bail = true;
             else if (ns > 0) __nanosleep(ns);
         }
     }

@@ -305,3 +305,33 @@ def test_other_scalar_systems_through_the_same_solver(kind):
     assert pg["converged"] and pg["nIterations"] >= 3
     check_solve(g, s["l"], s["u"], diag, s["upper"], b, x0, 1e-6, 0.05)      # the shipped fluid / thermal tolerances
     g.close()
+
+
+@pytest.mark.parametrize("kind", ["pencil", "tiles"])
+def test_spin_watchdog_returns_an_error_instead_of_hanging(kind, monkeypatch):
+    """every device-side wait is rooted in a poll of global memory; one that makes no progress for
+    GPUPCG_SPIN_TIMEOUT_MS gives up, the kernels run to their end and the call returns GPUPCG_ERR_STATE.  Forced here with a
+    zero timeout checked at every failed poll (any hand-off that is not instantaneous trips it); a handle created afterwards
+    with the default timeout solves normally (the fault word is per process and is cleared when it is reported)."""
+    s = cases.cantilever_system(40, 12, 16)
+    l, u, diag, upper, b, n = s["l"], s["u"], s["diag"], s["upper"], s["b"], s["nCells"]
+    monkeypatch.setenv("GPUPCG_SPIN_TIMEOUT_MS", "0")
+    monkeypatch.setenv("GPUPCG_SPIN_CHECK_MASK", "0")
+    if kind == "tiles":
+        monkeypatch.setenv("GPUPCG_TILE_MODE", "2")
+    g = pkg.GpuPCG(l, u, n, device=0)
+    g.set_matrix(diag, upper)
+    with pytest.raises(pkg.GpuPcgError) as e:
+        for _ in range(5):                       # a sweep whose every hand-off happened to be ready is possible, five in a row are not
+            g.solve(np.zeros(n), b, tolerance=1e-12, relTol=0.0)
+    assert "timed out" in str(e.value)
+    g.close()
+    monkeypatch.delenv("GPUPCG_SPIN_TIMEOUT_MS"); monkeypatch.delenv("GPUPCG_SPIN_CHECK_MASK")
+    g = pkg.GpuPCG(l, u, n, device=0)
+    g.set_matrix(diag, upper)
+    x = np.zeros(n)
+    pg, _ = g.solve(x, b, tolerance=1e-9, relTol=0.01)
+    xc = np.zeros(n)
+    pc, _ = oracle.pcg_solve(l, u, diag, upper, xc, b, tolerance=1e-9, relTol=0.01)
+    assert pg["nIterations"] == pc["nIterations"] and np.max(np.abs(x - xc)) <= 1e-9*np.max(np.abs(xc))
+    g.close()
