@@ -4,7 +4,9 @@
 #include "stressModelEvolve.H"
 #include "../foam/gpuPCG/gpuPCG.H"
 
+#include <algorithm>
 #include <cstring>
+#include <sstream>
 #include <string>
 
 using namespace Foam;
@@ -174,4 +176,125 @@ extern "C" int foamlike_evolve(const int* ints, const int* const* meshInts, cons
         gpuPCG::clearCache();
         return -1;
     }
+}
+
+
+// ---- the run-time selectable GPU stress model (gpuStressModel.{H,C}) driven the way a foam-extend solver drives a
+// stressModel: stressModel::New(mesh) from `stressModel ...;` of stressProperties, setTraction / setPressure, evolve() ------
+#include "gpuStressModel.H"
+
+namespace
+{
+struct StressCase
+{
+    fvMeshLike mesh;
+    std::vector<std::vector<int> > ints;
+    std::vector<std::vector<double> > reals;
+    std::vector<unsigned char> mirror;
+    stressModel* model;
+    StressCase() : model(0) {}
+    ~StressCase() { delete model; }
+};
+
+std::vector<word> splitWords(const char* s)
+{
+    std::vector<word> out; std::istringstream is(s); word w;
+    while (is >> w) out.push_back(w);
+    return out;
+}
+}
+
+// ints: nCells, nFaces, nInternalFaces, nPatches, nPoints, device, nPointConstraints, solutionD[3]
+// meshInts (with lengths in intLens): owner, neighbour, patchStart, patchSize, faceStart, facePoints, lsqStart, lsqEntry, pcPoint, pcStart, pcKind
+// meshReals (realLens): Sf, magSf, Cf, C, V, weights, deltaCoeffs, points, traction, pressure, fixedValue, lsqInv, lsqOrigin, pcVec
+extern "C" void* foamlike_stress_new(const int* ints, const int* const* meshInts, const long long* intLens,
+                                     const double* const* meshReals, const long long* realLens, const unsigned char* lsqMirror,
+                                     const char* patchNames, const char* patchFieldTypes, const char* stressProperties,
+                                     const char* rheologyProperties, const char* fvSolution, const char* fvSchemes, double deltaT)
+{
+    StressCase* S = new StressCase();
+    try
+    {
+        S->ints.resize(11); S->reals.resize(14);
+        for (int k = 0; k < 11; k++) S->ints[k].assign(meshInts[k], meshInts[k] + intLens[k]);
+        for (int k = 0; k < 14; k++) S->reals[k].assign(meshReals[k], meshReals[k] + realLens[k]);
+        fvMeshLike& M = S->mesh;
+        M.nCells = ints[0]; M.nFaces = ints[1]; M.nInternalFaces = ints[2]; M.nPatches = ints[3]; M.nPoints = ints[4]; M.device = ints[5];
+        M.nPointConstraints = ints[6];
+        for (int d = 0; d < 3; d++) M.solutionD[d] = ints[7 + d];
+        S->mirror.assign(lsqMirror, lsqMirror + M.nPoints);
+        M.owner = S->ints[0].data(); M.neighbour = S->ints[1].data(); M.patchStart = S->ints[2].data(); M.patchSize = S->ints[3].data();
+        M.faceStart = S->ints[4].data(); M.facePoints = S->ints[5].data(); M.lsqStart = S->ints[6].data(); M.lsqEntry = S->ints[7].data();
+        M.pcPoint = S->ints[8].data(); M.pcStart = S->ints[9].data(); M.pcKind = S->ints[10].data();
+        M.Sf = S->reals[0].data(); M.magSf = S->reals[1].data(); M.Cf = S->reals[2].data(); M.C = S->reals[3].data(); M.V = S->reals[4].data();
+        M.weights = S->reals[5].data(); M.deltaCoeffs = S->reals[6].data(); M.points = S->reals[7].data();
+        M.traction = S->reals[8].data(); M.pressure = S->reals[9].data(); M.fixedValue = S->reals[10].data();
+        M.lsqInv = S->reals[11].data(); M.lsqOrigin = S->reals[12].data(); M.pcVec = S->reals[13].data();
+        M.lsqMirror = S->mirror.data();
+        M.patchNames = splitWords(patchNames); M.patchFieldTypes = splitWords(patchFieldTypes);
+        M.stressProperties = dictionary(std::string(stressProperties));
+        M.rheologyProperties = dictionary(std::string(rheologyProperties));
+        M.fvSolution = dictionary(std::string(fvSolution));
+        M.fvSchemes = dictionary(std::string(fvSchemes));
+        M.deltaT = deltaT;
+        S->model = stressModel::New(M);
+        return S;
+    }
+    catch (const Foam::error& e)
+    {
+        g_lastError = e.what();
+        delete S;
+        return 0;
+    }
+}
+
+extern "C" void foamlike_stress_delete(void* p) { delete (StressCase*)p; }
+
+extern "C" int foamlike_stress_set(void* p, int what /*0 traction, 1 pressure*/, int patchID, const double* values)
+{
+    try
+    {
+        StressCase* S = (StressCase*)p;
+        if (what == 0) S->model->setTraction(patchID, values); else S->model->setPressure(patchID, values);
+        return 0;
+    }
+    catch (const Foam::error& e) { g_lastError = e.what(); return -1; }
+}
+
+extern "C" int foamlike_stress_new_time_step(void* p)
+{
+    try { ((StressCase*)p)->model->newTimeStep(); return 0; }
+    catch (const Foam::error& e) { g_lastError = e.what(); return -1; }
+}
+
+// result: converged, nOuter, totalPcg, enforceLinear, initialResidual, lastSolverInitialResidual, maxRes, res; returns the
+// number of outer iterations recorded in hist / pcg (pcg: nValidCmpts ints per outer iteration)
+extern "C" int foamlike_stress_evolve(void* p, double* result, double* hist, int* pcg, int cap)
+{
+    try
+    {
+        StressCase* S = (StressCase*)p;
+        const bool ok = S->model->evolve();
+        const gpuEvolveInfo& I = static_cast<gpuUnsTotalLagrangianStress*>(S->model)->info();
+        result[0] = ok; result[1] = I.nOuterIterations; result[2] = I.totalPcgIterations; result[3] = I.enforceLinear;
+        result[4] = I.initialResidual; result[5] = I.lastSolverInitialResidual; result[6] = I.maxRes; result[7] = I.res;
+        const int n = std::min<int>(cap, (int)I.residualHistory.size());
+        const int nv = n ? (int)(I.pcgIterations.size()/I.residualHistory.size()) : 0;
+        for (int i = 0; i < n; i++) hist[i] = I.residualHistory[i];
+        for (int i = 0; i < n*nv; i++) pcg[i] = I.pcgIterations[i];
+        return n;
+    }
+    catch (const Foam::error& e) { g_lastError = e.what(); return -1; }
+}
+
+extern "C" long long foamlike_stress_field(void* p, const char* name, double* out, long long cap)
+{
+    try
+    {
+        StressCase* S = (StressCase*)p;
+        const long long n = S->model->fieldSize(name);
+        if (out && cap >= n) S->model->field(name, out);
+        return n;
+    }
+    catch (const Foam::error& e) { g_lastError = e.what(); return -1; }
 }

@@ -154,3 +154,95 @@ def evolve(mesh, geom, patchTypes, mu, lam, rho, g, traction, pressure, fixedVal
     return dict(D=Dv, pointD=pD, gradD=G, gradDf=Gf, epsilon=eps, sigma=sig, converged=bool(res[0]), nOuterIterations=int(res[1]),
                 initialResidual=res[2], lastSolverInitialResidual=res[3], maxRes=res[4], res=res[5],
                 totalPcgIterations=int(res[6]), residualHistory=hist[:n].copy())
+
+
+class StressModel(object):
+    """`stressModel::New(mesh)` of the C++ host side (host/gpuStressModel.{H,C}): the model named by `stressModel ...;` in the
+    stressProperties text is selected from the run-time table -- `gpuUnsTotalLagrangianStress` keeps the solid on the GPU and
+    runs evolve() as one gpupcg_evolve_D call.  Dictionaries are foam-syntax text, the boundary fields of 0/D per boundary
+    face; `lsq` / `pointConstraints` as lsq.build / lsq.point_constraints return them."""
+
+    def __init__(self, mesh, geom, patchFieldTypes, stressProperties, rheologyProperties, fvSolution, fvSchemes, deltaT=1.0,
+                 traction=None, pressure=None, fixedValue=None, lsq=None, pointConstraints=None, solutionD=(1, 1, 1), device=0):
+        from . import lsq as lsqmod
+        lib = load()
+        nC, nF, nIF, nP = mesh.nCells, mesh.nFaces, mesh.nInternalFaces, mesh.nPoints
+        nBF = nF - nIF
+        self.nCells, self.nPoints = nC, nP
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        if lsq is None:
+            lsq = lsqmod.build(mesh, geom, patchFieldTypes)
+        pc = pointConstraints or dict(point=np.zeros(0, np.int32), start=np.zeros(1, np.int32), kind=np.zeros(0, np.int32), vec=np.zeros((0, 3)))
+        mi = [i32(mesh.owner), i32(mesh.neighbour), i32([p["start"] for p in mesh.patches]), i32([p["size"] for p in mesh.patches]),
+              i32(mesh.faceStart), i32(mesh.facePoints), i32(lsq["start"]), i32(lsq["entry"]), i32(pc["point"]), i32(pc["start"]),
+              i32(pc["kind"])]
+        mr = [f64(geom.Sf), f64(geom.magSf), f64(geom.Cf), f64(geom.C), f64(geom.V), f64(geom.weights), f64(geom.deltaCoeffs),
+              f64(mesh.points), f64(np.zeros((nBF, 3)) if traction is None else traction),
+              f64(np.zeros(nBF) if pressure is None else pressure), f64(np.zeros((nBF, 3)) if fixedValue is None else fixedValue),
+              f64(lsq["inv"]), f64(lsq["origin"]), f64(pc["vec"])]
+        mirror = np.ascontiguousarray(lsq["mirror"], dtype=np.uint8)
+        ints = i32([nC, nF, nIF, len(mesh.patches), nP, device, int(pc["point"].shape[0])] + [1 if s else -1 for s in solutionD])
+        MI = (ip*len(mi))(*[a.ctypes.data_as(ip) for a in mi])
+        MR = (dp*len(mr))(*[a.ctypes.data_as(dp) for a in mr])
+        IL = (C.c_longlong*len(mi))(*[a.size for a in mi])
+        RL = (C.c_longlong*len(mr))(*[a.size for a in mr])
+        lib.foamlike_stress_new.restype = C.c_void_p
+        lib.foamlike_stress_delete.argtypes = [C.c_void_p]
+        lib.foamlike_stress_set.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
+        lib.foamlike_stress_new_time_step.argtypes = [C.c_void_p]
+        lib.foamlike_stress_evolve.argtypes = [C.c_void_p, dp, dp, ip, C.c_int]
+        lib.foamlike_stress_field.restype = C.c_longlong
+        lib.foamlike_stress_field.argtypes = [C.c_void_p, C.c_char_p, dp, C.c_longlong]
+        self.lib = lib
+        self.h = lib.foamlike_stress_new(ints.ctypes.data_as(ip), MI, IL, MR, RL, mirror.ctypes.data_as(C.POINTER(C.c_ubyte)),
+                                         " ".join(p["name"] for p in mesh.patches).encode(),
+                                         " ".join(patchFieldTypes[p["name"]] for p in mesh.patches).encode(),
+                                         stressProperties.encode(), rheologyProperties.encode(), fvSolution.encode(),
+                                         fvSchemes.encode(), C.c_double(deltaT))
+        if not self.h:
+            raise FoamFatalError(lib.foamlike_last_error().decode())
+        self.h = C.c_void_p(self.h)
+        self.patchIndex = {p["name"]: i for i, p in enumerate(mesh.patches)}
+
+    def _check(self, rc):
+        if rc < 0:
+            raise FoamFatalError(self.lib.foamlike_last_error().decode())
+        return rc
+
+    def set_traction(self, patch, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        self._check(self.lib.foamlike_stress_set(self.h, 0, self.patchIndex[patch], v.ctypes.data_as(dp)))
+
+    def set_pressure(self, patch, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        self._check(self.lib.foamlike_stress_set(self.h, 1, self.patchIndex[patch], v.ctypes.data_as(dp)))
+
+    def new_time_step(self):
+        self._check(self.lib.foamlike_stress_new_time_step(self.h))
+
+    def evolve(self, cap=4096):
+        res = np.zeros(8); hist = np.zeros(cap); pcg = np.zeros(3*cap, dtype=np.int32)
+        n = self._check(self.lib.foamlike_stress_evolve(self.h, res.ctypes.data_as(dp), hist.ctypes.data_as(dp), pcg.ctypes.data_as(ip), cap))
+        nv = 0 if n == 0 else None
+        out = dict(converged=bool(res[0]), nOuterIterations=int(res[1]), totalPcgIterations=int(res[2]), enforceLinear=int(res[3]),
+                   initialResidual=res[4], lastSolverInitialResidual=res[5], maxRes=res[6], res=res[7], residualHistory=hist[:n].copy())
+        tot = int(res[2])
+        # pcg holds nValid ints per outer iteration: recover nValid from the total
+        for k in (3, 2, 1):
+            if n and int(pcg[:n*k].sum()) == tot and (k == 3 or not pcg[n*k:n*k + 1].any()):
+                nv = k
+                break
+        out["pcgIterations"] = pcg[:n*(nv or 0)].reshape(n, nv or 0).copy()
+        return out
+
+    def get(self, name):
+        n = self._check(self.lib.foamlike_stress_field(self.h, name.encode(), None, 0))
+        a = np.zeros(n)
+        self._check(self.lib.foamlike_stress_field(self.h, name.encode(), a.ctypes.data_as(dp), n))
+        return a
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.foamlike_stress_delete(self.h)
+            self.h = None

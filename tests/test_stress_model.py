@@ -1,0 +1,112 @@
+"""the GPU solid model registered in the stress-model run-time selection table next to the stock one
+(reference: stressModels/stressModel/newStressModel.C:40-100 selects by `stressModel ...;` of constant/stressProperties;
+unsTotalLagrangianStress.C:53-54 registers the stock model).  host/gpuStressModel.{H,C} is the C++ class over the foam-extend
+API stand-in; it reads the SHIPPED dictionaries of config 1 and must reproduce the resident Python harness (same C-ABI calls,
+hence the same bits) and the oracle's loop."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from fluidstructureinteraction_b200 import blockmesh, cases, geometry, hostapi, lsq
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+
+STRESS = """
+stressModel %s;
+gpuUnsTotalLagrangianStressCoeffs
+{
+    nCorrectors 1000;               // run/stressFoam/plateHole/plateHole/constant/stressProperties:19-26
+    convergenceTolerance 1e-8;
+    nonLinear no;
+    debug no;
+    moveMesh no;
+}
+"""
+RHEOLOGY = """
+planeStress     yes;                // run/stressFoam/plateHole/plateHole/constant/rheologyProperties:17-25
+rheology
+{
+    type            linearElastic;
+    rho             rho [1 -3 0 0 0 0 0] 7854;
+    E               E [1 -1 -2 0 0 0 0] 2e+11;
+    nu              nu [0 0 0 0 0 0 0] 0.3;
+}
+"""
+FVSOLUTION = """
+solvers { D { solver %s; preconditioner DIC; tolerance 1e-09; relTol 0.01; } }      // system/fvSolution:18-27
+relaxationFactors { }
+"""
+FVSCHEMES = """
+d2dt2Schemes { default %s; }
+ddtSchemes { default steadyState; }
+laplacianSchemes { default none; laplacian(DD,D) Gauss linear skewCorrected 1; }
+snGradSchemes { snGrad(D) %s; }
+"""
+
+
+def _plate_hole():
+    with open(os.path.join(GOLD, "plateHole.blockMeshDict.json")) as f:
+        m = blockmesh.block_mesh(json.load(f))
+    g = geometry.compute(m)
+    PH = cases.PLATE_HOLE
+    return m, g, PH, cases.plate_hole_tractions(m, g, PH["patchTypes"])
+
+
+def _model(m, g, PH, tr, model="gpuUnsTotalLagrangianStress", solver="gpuPCG", d2dt2="steadyState", sn="skewCorrected 1", **kw):
+    return hostapi.StressModel(m, g, PH["patchTypes"], STRESS % model, RHEOLOGY, FVSOLUTION % solver, FVSCHEMES % (d2dt2, sn),
+                               lsq=lsq.build(m, g, PH["patchTypes"]), pointConstraints=lsq.point_constraints(m, g, PH["pointPatchTypes"]),
+                               solutionD=(1, 1, 0), traction=tr, **kw)
+
+
+def test_run_time_selection_and_dictionary_checks():
+    """No GPU needed: selection by name and the refusal of settings the resident loop does not implement happen before any
+    device call; a supported set-up then fails loudly for want of a GPU (no CPU fallback)."""
+    import torch
+    m, g, PH, tr = _plate_hole()
+    with pytest.raises(hostapi.FoamFatalError) as e:
+        _model(m, g, PH, tr, model="unsTotalLagrangianStress")
+    assert "Unknown stressModel type unsTotalLagrangianStress" in str(e.value) and "gpuUnsTotalLagrangianStress" in str(e.value)
+    for kw, msg in ((dict(solver="GAMG"), "PCG/DIC"), (dict(d2dt2="backward"), "backward"), (dict(sn="corrected"), "skewCorrected")):
+        with pytest.raises(hostapi.FoamFatalError) as e:
+            _model(m, g, PH, tr, **kw)
+        assert msg in str(e.value), (kw, str(e.value))
+    if not torch.cuda.is_available():
+        with pytest.raises(hostapi.FoamFatalError) as e:
+            _model(m, g, PH, tr)
+        assert "gpupcg_mesh_create failed" in str(e.value) and "no CPU fallback" in str(e.value)
+
+
+@pytest.mark.gpu
+def test_gpu_stress_model_runs_config_1_like_the_harness_and_the_oracle():
+    from oracle import evolve as oev
+    from fluidstructureinteraction_b200.solid import GpuSolidCase
+    m, g, PH, tr = _plate_hole()
+    mu, lam = cases.lame(PH["E"], PH["nu"], True)
+    kw = dict(traction=tr, validCmpts=(1, 1, 0), pointPatchTypes=PH["pointPatchTypes"])
+    ref = oev.SolidCase(m, g, PH["patchTypes"], mu, lam, PH["rho"], **kw)
+    r = ref.evolve(PH["nCorrectors"], PH["convergenceTolerance"], 0.0, PH["tolerance"], PH["relTol"])
+    gc = GpuSolidCase(m, g, PH["patchTypes"], mu, lam, PH["rho"], **kw)
+    rg = gc.evolve(PH["nCorrectors"], PH["convergenceTolerance"], 0.0, PH["tolerance"], PH["relTol"])
+    # the C++ model: zero tractions at construction, then what setPlateHoleBC::setBC does through setTraction()
+    sm = _model(m, g, PH, np.zeros_like(tr))
+    nIF = m.nInternalFaces
+    for p in m.patches:
+        if PH["patchTypes"][p["name"]] == "tractionDisplacement":
+            sm.set_traction(p["name"], tr[p["start"] - nIF:p["start"] - nIF + p["size"]])
+    with pytest.raises(hostapi.FoamFatalError):
+        sm.set_traction("left", np.zeros((30, 3)))             # not a tractionDisplacement patch (:528-541)
+    rs = sm.evolve()
+    assert rs["converged"] and rs["nOuterIterations"] == rg["nOuterIterations"] == r["nOuterIterations"]
+    assert np.array_equal(rs["pcgIterations"], rg["pcgIterations"]) and np.array_equal(rs["pcgIterations"], np.array(r["pcgIterations"]))
+    assert np.array_equal(rs["residualHistory"], rg["residualHistory"])
+    for k in ("D", "pointD", "sigma"):
+        a = sm.get(k)
+        assert np.array_equal(a, gc.get(k).ravel()), k                                  # same calls, same bits
+        b = getattr(ref, k).ravel()
+        assert np.abs(a - b).max() <= 1e-9*np.abs(b).max(), k
+    e = cases.plate_hole_errors(m, g, sm.get("D").reshape(-1, 3), sm.get("pointD").reshape(-1, 3), sm.get("sigma").reshape(-1, 6))
+    assert e["DError"] < 0.004*e["DMax"] and e["sigmaXXErr"] < 0.03*e["sigmaXXMax"]
+    sm.close(); gc.close()
