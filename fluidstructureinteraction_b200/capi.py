@@ -135,6 +135,8 @@ SYMBOLS = {
     "gpupcg_mesh_field_size": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]),
     "gpupcg_mesh_set_field": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "gpupcg_mesh_get_field": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
+    "gpupcg_assemble_scalar": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                        C.POINTER(C.c_double)]),
     "gpupcg_mesh_set_lsq": (C.c_int, [C.c_void_p, c_int_p, c_int_p, c_double_p, c_double_p, C.POINTER(C.c_ubyte)]),
     "gpupcg_mesh_set_point_constraints": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p, c_int_p, c_double_p]),
     "gpupcg_vol_to_point": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
@@ -521,6 +523,31 @@ class GpuMesh(object):
     def get_field(self, name):
         out = np.empty(self._field_shape(name))
         self._check(self.lib.gpupcg_mesh_get_field(self.h, FIELD_IDS[name], _dp(out)))
+        return out
+
+    def assemble_scalar(self, sign, bfKind, bfValue, gammaCells=None, gammaFaces=None, ddt="steadyState", deltaT=1.0, rate=None,
+                        psiOld=None, phi=None, refCell=-1, refValue=0.0):
+        """gpupcg_assemble_scalar: TEqn (sign +1, Euler ddt, gammaCells) / pEqn (sign -1, gammaFaces, phi, reference cell)."""
+        class Eqn(C.Structure):
+            _fields_ = [("sign", C.c_int), ("gammaCells", c_double_p), ("gammaFaces", c_double_p), ("bfKind", c_int_p),
+                        ("bfValue", c_double_p), ("ddtScheme", C.c_int), ("deltaT", C.c_double), ("rate", c_double_p),
+                        ("psiOld", c_double_p), ("phi", c_double_p), ("refCell", C.c_int), ("refValue", C.c_double)]
+        keep = [None if a is None else _f64(a) for a in (gammaCells, gammaFaces, bfValue, rate, psiOld, phi)]
+        kind = _i32(bfKind)
+        ptr = lambda a: None if a is None else _dp(a)
+        e = Eqn(int(sign), ptr(keep[0]), ptr(keep[1]), _ip(kind), ptr(keep[2]), 1 if ddt == "Euler" else 0, float(deltaT),
+                ptr(keep[3]), ptr(keep[4]), ptr(keep[5]), int(refCell), float(refValue))
+        nC, nIF, nBF = self.nC, self.nIF, self.nBF
+        out = dict(upper=np.empty(nIF), diag=np.empty(nC), source=np.empty(nC), internalCoeffs=np.empty(max(nBF, 1)),
+                   boundaryCoeffs=np.empty(max(nBF, 1)))
+        ms = C.c_double(0.0)
+        self.lib.gpupcg_assemble_scalar.restype = C.c_int
+        self.lib.gpupcg_assemble_scalar.argtypes = [C.c_void_p, C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                                    C.POINTER(C.c_double)]
+        self._check(self.lib.gpupcg_assemble_scalar(self.h, C.byref(e), _dp(out["upper"]), _dp(out["diag"]), _dp(out["source"]),
+                                                     _dp(out["internalCoeffs"]), _dp(out["boundaryCoeffs"]), C.byref(ms)))
+        out["internalCoeffs"] = out["internalCoeffs"][:nBF]; out["boundaryCoeffs"] = out["boundaryCoeffs"][:nBF]
+        out["kernel_ms"] = ms.value
         return out
 
     def set_point_constraints(self, pc):

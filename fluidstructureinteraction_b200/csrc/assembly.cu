@@ -110,6 +110,7 @@ __device__ void symmetry_snGrad(const MeshDev& M, int f, const double* __restric
 }
 
 #include "assembly_ext.cuh"
+#include "assembly_scalar.cuh"
 
 // One chunk of the assembly (see AsmChunk): slot s of the chunk's flux ring is internal face f0 + s for s < nOwn (the
 // faces the chunk's cells own), then the chunk's extra faces: internal faces owned by an EARLIER chunk whose neighbour
@@ -1481,6 +1482,68 @@ extern "C" int gpupcg_mesh_set_point_constraints(gpupcg_mesh m, int nConstrained
     MCK(up(m, B.kind, kind, (size_t)rows)); MCK(up(m, B.vec, vec, 3*(size_t)rows));
     MCK(cudaStreamSynchronize(m->stream));
     B.n = nConstrained;
+    return GPUPCG_OK;
+}
+
+// The other scalar systems of the boundary (TEqn, pEqn): assembly_scalar.cuh.  Host arrays in, host arrays out (all optional
+// outputs); the geometry, addressing and patch table are those of the mesh handle (D's patch types only tell `empty`).
+extern "C" int gpupcg_assemble_scalar(gpupcg_mesh m, const gpupcg_scalar_eqn* e, double* upper, double* diag, double* source,
+                                      double* internalCoeffs, double* boundaryCoeffs, double* kernel_ms)
+{
+    if (!m || !e) return GPUPCG_ERR_ARG;
+    const MeshDev& M = m->M;
+    const int nC = M.nCells, nF = M.nFaces, nIF = M.nIF, nBF = nF - nIF;
+    if ((e->gammaCells == nullptr) == (e->gammaFaces == nullptr))
+    { m->err = "gpupcg_assemble_scalar: give gammaCells or gammaFaces (exactly one)"; return GPUPCG_ERR_ARG; }
+    if (e->sign != 1 && e->sign != -1) { m->err = "gpupcg_assemble_scalar: sign must be +1 (ddt - laplacian) or -1 (laplacian == div(phi))"; return GPUPCG_ERR_ARG; }
+    if (e->ddtScheme != 0 && e->ddtScheme != 1) { m->err = "gpupcg_assemble_scalar: ddt scheme 0 steadyState or 1 Euler"; return GPUPCG_ERR_UNSUPPORTED; }
+    if (e->ddtScheme == 1 && (!(e->deltaT > 0.0) || !e->rate || !e->psiOld || e->sign != 1))
+    { m->err = "gpupcg_assemble_scalar: Euler ddt needs deltaT > 0, rate, psiOld and the (ddt - laplacian) form"; return GPUPCG_ERR_ARG; }
+    if (nBF > 0 && (!e->bfKind || !e->bfValue)) { m->err = "gpupcg_assemble_scalar: NULL boundary tables"; return GPUPCG_ERR_ARG; }
+    if (e->refCell >= nC) { m->err = "gpupcg_assemble_scalar: reference cell out of range"; return GPUPCG_ERR_ARG; }
+    for (int bf = 0; bf < nBF; bf++)
+        if (e->bfKind[bf] < 0 || e->bfKind[bf] > 1)
+        { m->err = "gpupcg_assemble_scalar: boundary kind must be 0 (zeroGradient) or 1 (fixedValue)"; return GPUPCG_ERR_UNSUPPORTED; }
+    MCK(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+    double *dGamma = nullptr, *dGms = nullptr, *dLup = nullptr, *dUp = nullptr, *dDg = nullptr, *dSrc = nullptr, *dIc = nullptr, *dBc = nullptr;
+    double *dRate = nullptr, *dOld = nullptr, *dPhi = nullptr, *dVal = nullptr; int* dKind = nullptr;
+    std::vector<void*> tmp;
+    auto dev = [&](void** p, size_t bytes, const void* host) -> cudaError_t
+    {
+        cudaError_t er = cudaMalloc(p, std::max<size_t>(bytes, 8));
+        if (er != cudaSuccess) return er;
+        tmp.push_back(*p);
+        return host ? cudaMemcpyAsync(*p, host, bytes, cudaMemcpyHostToDevice, s) : cudaSuccess;
+    };
+    auto freeAll = [&]() { for (void* p : tmp) cudaFree(p); };
+#define SCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { freeAll(); m->err = std::string("gpupcg_assemble_scalar: ") + cudaGetErrorString(e_); return GPUPCG_ERR_CUDA; } } while (0)
+    const bool onFaces = e->gammaFaces != nullptr;
+    SCK(dev((void**)&dGamma, sizeof(double)*(onFaces ? nF : nC), onFaces ? e->gammaFaces : e->gammaCells));
+    SCK(dev((void**)&dGms, sizeof(double)*nF, nullptr)); SCK(dev((void**)&dLup, sizeof(double)*nIF, nullptr));
+    SCK(dev((void**)&dUp, sizeof(double)*nIF, nullptr)); SCK(dev((void**)&dDg, sizeof(double)*nC, nullptr));
+    SCK(dev((void**)&dSrc, sizeof(double)*nC, nullptr)); SCK(dev((void**)&dIc, sizeof(double)*nBF, nullptr));
+    SCK(dev((void**)&dBc, sizeof(double)*nBF, nullptr));
+    SCK(dev((void**)&dKind, sizeof(int)*nBF, e->bfKind)); SCK(dev((void**)&dVal, sizeof(double)*nBF, e->bfValue));
+    if (e->ddtScheme == 1) { SCK(dev((void**)&dRate, sizeof(double)*nC, e->rate)); SCK(dev((void**)&dOld, sizeof(double)*nC, e->psiOld)); }
+    if (e->phi) SCK(dev((void**)&dPhi, sizeof(double)*nF, e->phi));
+    const ScalarEqnDev E{e->sign, e->ddtScheme, e->ddtScheme == 1 ? 1.0/e->deltaT : 0.0, onFaces ? 1 : 0};
+    SCK(cudaEventRecord(m->ev0, s));
+    k_sc_faces<<<agrid(m, nF), ATPB, 0, s>>>(M, E, dGamma, dGms, dLup, dUp);
+    k_sc_cells<<<agrid(m, nC), ATPB, 0, s>>>(M, E, dLup, dRate, dOld, dPhi, dDg, dSrc);
+    if (nBF > 0) k_sc_patches<<<agrid(m, nBF), ATPB, 0, s>>>(M, E, dKind, dVal, dGms, dIc, dBc);
+    if (e->refCell >= 0) k_sc_reference<<<1, 32, 0, s>>>(e->refCell, e->refValue, dDg, dSrc);
+    SCK(cudaEventRecord(m->ev1, s));
+    SCK(cudaGetLastError());
+    if (upper) SCK(cudaMemcpyAsync(upper, dUp, sizeof(double)*nIF, cudaMemcpyDeviceToHost, s));
+    if (diag) SCK(cudaMemcpyAsync(diag, dDg, sizeof(double)*nC, cudaMemcpyDeviceToHost, s));
+    if (source) SCK(cudaMemcpyAsync(source, dSrc, sizeof(double)*nC, cudaMemcpyDeviceToHost, s));
+    if (internalCoeffs && nBF) SCK(cudaMemcpyAsync(internalCoeffs, dIc, sizeof(double)*nBF, cudaMemcpyDeviceToHost, s));
+    if (boundaryCoeffs && nBF) SCK(cudaMemcpyAsync(boundaryCoeffs, dBc, sizeof(double)*nBF, cudaMemcpyDeviceToHost, s));
+    SCK(cudaStreamSynchronize(s));
+    if (kernel_ms) { float ms = 0.f; cudaEventElapsedTime(&ms, m->ev0, m->ev1); *kernel_ms = ms; }
+    freeAll();
+#undef SCK
     return GPUPCG_OK;
 }
 

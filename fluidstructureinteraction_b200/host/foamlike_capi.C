@@ -267,8 +267,8 @@ extern "C" int foamlike_stress_new_time_step(void* p)
     catch (const Foam::error& e) { g_lastError = e.what(); return -1; }
 }
 
-// result: converged, nOuter, totalPcg, enforceLinear, initialResidual, lastSolverInitialResidual, maxRes, res; returns the
-// number of outer iterations recorded in hist / pcg (pcg: nValidCmpts ints per outer iteration)
+// result[9]: converged, nOuter, totalPcg, enforceLinear, initialResidual, lastSolverInitialResidual, maxRes, res, nValidCmpts;
+// returns the number of outer iterations recorded in hist / pcg (pcg: 3 ints per outer iteration, the first nValidCmpts in use)
 extern "C" int foamlike_stress_evolve(void* p, double* result, double* hist, int* pcg, int cap)
 {
     try
@@ -278,10 +278,10 @@ extern "C" int foamlike_stress_evolve(void* p, double* result, double* hist, int
         const gpuEvolveInfo& I = static_cast<gpuUnsTotalLagrangianStress*>(S->model)->info();
         result[0] = ok; result[1] = I.nOuterIterations; result[2] = I.totalPcgIterations; result[3] = I.enforceLinear;
         result[4] = I.initialResidual; result[5] = I.lastSolverInitialResidual; result[6] = I.maxRes; result[7] = I.res;
+        result[8] = I.nValidCmpts;
         const int n = std::min<int>(cap, (int)I.residualHistory.size());
-        const int nv = n ? (int)(I.pcgIterations.size()/I.residualHistory.size()) : 0;
         for (int i = 0; i < n; i++) hist[i] = I.residualHistory[i];
-        for (int i = 0; i < n*nv; i++) pcg[i] = I.pcgIterations[i];
+        for (int i = 0; i < 3*n; i++) pcg[i] = I.pcgIterations[i];
         return n;
     }
     catch (const Foam::error& e) { g_lastError = e.what(); return -1; }

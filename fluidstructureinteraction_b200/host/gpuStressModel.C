@@ -241,7 +241,8 @@ bool gpuUnsTotalLagrangianStress::evolve()
     const int nOut = std::min(cap, r.nOuterIterations + 1);
     int nv = 0; for (int d = 0; d < 3; d++) nv += ctl_.validCmpt[d];
     info_.residualHistory.resize(nOut);
-    info_.pcgIterations.resize((size_t)nOut*nv);
+    info_.pcgIterations.resize((size_t)nOut*3);        // three slots per outer iteration, the first nValidCmpts in use
+    info_.nValidCmpts = nv;
     info_.nOuterIterations = r.nOuterIterations; info_.totalPcgIterations = r.totalPcgIterations;
     info_.enforceLinear = r.enforceLinear; info_.converged = r.converged;
     info_.initialResidual = r.initialResidual; info_.lastSolverInitialResidual = r.lastSolverInitialResidual;

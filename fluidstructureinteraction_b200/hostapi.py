@@ -222,19 +222,11 @@ class StressModel(object):
         self._check(self.lib.foamlike_stress_new_time_step(self.h))
 
     def evolve(self, cap=4096):
-        res = np.zeros(8); hist = np.zeros(cap); pcg = np.zeros(3*cap, dtype=np.int32)
+        res = np.zeros(9); hist = np.zeros(cap); pcg = np.zeros(3*cap, dtype=np.int32)
         n = self._check(self.lib.foamlike_stress_evolve(self.h, res.ctypes.data_as(dp), hist.ctypes.data_as(dp), pcg.ctypes.data_as(ip), cap))
-        nv = 0 if n == 0 else None
-        out = dict(converged=bool(res[0]), nOuterIterations=int(res[1]), totalPcgIterations=int(res[2]), enforceLinear=int(res[3]),
-                   initialResidual=res[4], lastSolverInitialResidual=res[5], maxRes=res[6], res=res[7], residualHistory=hist[:n].copy())
-        tot = int(res[2])
-        # pcg holds nValid ints per outer iteration: recover nValid from the total
-        for k in (3, 2, 1):
-            if n and int(pcg[:n*k].sum()) == tot and (k == 3 or not pcg[n*k:n*k + 1].any()):
-                nv = k
-                break
-        out["pcgIterations"] = pcg[:n*(nv or 0)].reshape(n, nv or 0).copy()
-        return out
+        return dict(converged=bool(res[0]), nOuterIterations=int(res[1]), totalPcgIterations=int(res[2]), enforceLinear=int(res[3]),
+                    initialResidual=res[4], lastSolverInitialResidual=res[5], maxRes=res[6], res=res[7], residualHistory=hist[:n].copy(),
+                    pcgIterations=pcg[:3*n].reshape(n, 3)[:, :int(res[8])].copy())
 
     def get(self, name):
         n = self._check(self.lib.foamlike_stress_field(self.h, name.encode(), None, 0))

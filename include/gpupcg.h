@@ -348,6 +348,34 @@ int gpupcg_patch_evaluate(gpupcg_mesh m);
 int gpupcg_assemble_D_resident(gpupcg_mesh m, const gpupcg_eqn_controls* controls, const double* g);
 int gpupcg_gradients_resident(gpupcg_mesh m, double limitCoeff);
 int gpupcg_sigma_resident(gpupcg_mesh m, const gpupcg_eqn_controls* controls);
+/* ---- the other symmetric scalar systems of the boundary, assembled on the device --------------
+ *   TEqn  src/solvers/thermalStressFoam/TEqn.H:9-15:   rhoC*fvm::ddt(T) == fvm::laplacian(k, T, "laplacian(k,T)")
+ *         -> sign +1, ddtScheme 1, rate = rhoC [nCells], psiOld = T.oldTime(), gammaCells = k (interpolated linearly)
+ *   pEqn  flowModels/consistentIcoFlow/consistentIcoFlow.C:211-224: fvm::laplacian(1/interpolate(AU), p) == fvc::div(phi);
+ *         pEqn.setReference(pRefCell, pRefValue)  -> sign -1, gammaFaces, phi [nFaces], refCell / refValue
+ * [EXT] gaussLaplacianScheme::fvmLaplacianUncorrected, EulerDdtScheme::fvmDdt, surfaceIntegrate, setReference, in the reference's
+ * loop order (bit-exact against oracle/fvm_oracle.c: orc_assemble_scalar).  Boundary faces: bfKind 0 zeroGradient, 1 fixedValue
+ * (bfValue); faces of `empty` patches of the mesh handle take no part.  Orthogonal part only: the explicit correction of the
+ * scalar `skewCorrected` scheme (skewCorrectedSnGrad.C:197-245, least-squares gradient) is not built.  Outputs in LDU numbering,
+ * ready for gpupcg_set_matrix / gpupcg_solve after fvMatrix's addBoundaryDiag / addBoundarySource (any may be NULL).            */
+typedef struct gpupcg_scalar_eqn
+{
+    int           sign;                 /* +1: rate*ddt(psi) - laplacian(gamma, psi);  -1: laplacian(gamma, psi) - div(phi)     */
+    const double* gammaCells;           /* [nCells] or NULL                                                                     */
+    const double* gammaFaces;           /* [nFaces] or NULL (exactly one of the two)                                            */
+    const int*    bfKind;               /* [nBoundaryFaces]                                                                     */
+    const double* bfValue;              /* [nBoundaryFaces]                                                                     */
+    int           ddtScheme;            /* 0 steadyState, 1 Euler                                                               */
+    double        deltaT;
+    const double* rate;                 /* [nCells] coefficient of the ddt term (rhoC)                                          */
+    const double* psiOld;               /* [nCells] psi.oldTime()                                                               */
+    const double* phi;                  /* [nFaces] face flux of the explicit divergence, or NULL                               */
+    int           refCell;              /* setReference: -1 none                                                                */
+    double        refValue;
+} gpupcg_scalar_eqn;
+int gpupcg_assemble_scalar(gpupcg_mesh m, const gpupcg_scalar_eqn* eqn, double* upper, double* diag, double* source,
+                           double* internalCoeffs, double* boundaryCoeffs, double* kernel_ms);
+
 /* runTime++: D.oldTime().oldTime() = D.oldTime(); D.oldTime() = D                                                          */
 int gpupcg_mesh_new_time_step(gpupcg_mesh m);
 

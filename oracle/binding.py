@@ -474,3 +474,21 @@ def point_constraints_apply(pc, pointD):
     lib.orc_point_constraints.argtypes = [C.c_int, ip, ip, ip, dp, dp]
     lib.orc_point_constraints(point.shape[0], _ip(point), _ip(start), _ip(kind), _dp(vec), _dp(pointD))
     return pointD
+
+
+def assemble_scalar(mesh, geom, patchTypes, sign, bfKind, bfValue, gammaCells=None, gammaFaces=None, ddt="steadyState", deltaT=1.0,
+                    rate=None, psiOld=None, phi=None, refCell=-1, refValue=0.0):
+    """orc_assemble_scalar: TEqn / pEqn forms (see fvm_oracle.c).  Returns dict(upper, diag, source, internalCoeffs, boundaryCoeffs)."""
+    lib = load()
+    M, keep = _mesh_struct(mesh, geom, patchTypes)
+    nC, nIF, nBF = mesh.nCells, mesh.nInternalFaces, mesh.nFaces - mesh.nInternalFaces
+    upper = np.empty(nIF); diag = np.empty(nC); source = np.empty(nC); ic = np.empty(max(nBF, 1)); bc = np.empty(max(nBF, 1))
+    kind = _i(bfKind); val = _f(bfValue)
+    a = [_opt(v) for v in (gammaCells, gammaFaces)]
+    b = [_opt(v) for v in (rate, psiOld, phi)]
+    lib.orc_assemble_scalar.restype = None
+    lib.orc_assemble_scalar.argtypes = [C.POINTER(Mesh), C.c_int, dp, dp, ip, dp, C.c_int, C.c_double, dp, dp, dp, C.c_int, C.c_double,
+                                        dp, dp, dp, dp, dp]
+    lib.orc_assemble_scalar(C.byref(M), int(sign), _odp(a[0]), _odp(a[1]), _ip(kind), _dp(val), 1 if ddt == "Euler" else 0, float(deltaT),
+                            _odp(b[0]), _odp(b[1]), _odp(b[2]), int(refCell), float(refValue), _dp(upper), _dp(diag), _dp(source), _dp(ic), _dp(bc))
+    return dict(upper=upper, diag=diag, source=source, internalCoeffs=ic[:nBF], boundaryCoeffs=bc[:nBF])

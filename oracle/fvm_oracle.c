@@ -1372,3 +1372,78 @@ void orc_point_constraints(int n, const int* point, const int* start, const int*
         }
     }
 }
+
+/* ======================================================================================================== */
+/*  The other scalar systems of the boundary: TEqn and pEqn, orthogonal part         */
+/*    TEqn  solvers/thermalStressFoam/TEqn.H:9-15      rhoC*fvm::ddt(T) == fvm::laplacian(k, T)                */
+/*    pEqn  flowModels/consistentIcoFlow/consistentIcoFlow.C:211-224  fvm::laplacian(rAUf, p) == fvc::div(phi) */
+/*  [EXT] gaussLaplacianScheme::fvmLaplacianUncorrected, lduMatrix::negSumDiag, EulerDdtScheme::fvmDdt,        */
+/*  fvMatrix operator*(volScalarField), operator==, fvc::surfaceIntegrate, fvMatrix::setReference              */
+/* ======================================================================================================== */
+void orc_assemble_scalar(const orc_mesh* M, int sign, const double* gammaCells, const double* gammaFaces, const int* bfKind,
+                         const double* bfValue, int ddtScheme, double deltaT, const double* rate, const double* psiOld,
+                         const double* phi, int refCell, double refValue,
+                         double* upper, double* diag, double* source, double* internalCoeffs, double* boundaryCoeffs)
+{
+    const int nC = M->nCells, nF = M->nFaces, nIF = M->nInternalFaces;
+    unsigned char* emptyFace = (unsigned char*)calloc(nF > 0 ? nF : 1, 1);
+    for (int p = 0; p < M->nPatches; p++)
+        if (M->patchType[p] == 4)
+            for (int i = 0; i < M->patchSize[p]; i++) emptyFace[M->patchStart[p] + i] = 1;
+    double* gms = (double*)calloc(nF > 0 ? nF : 1, sizeof(double));
+    double* Ldiag = (double*)calloc(nC > 0 ? nC : 1, sizeof(double));
+    double* Lupper = (double*)calloc(nIF > 0 ? nIF : 1, sizeof(double));
+    double* div = (double*)calloc(nC > 0 ? nC : 1, sizeof(double));
+    for (int f = 0; f < nF; f++)
+    {
+        if (emptyFace[f]) continue;
+        double gf;
+        if (gammaFaces) gf = gammaFaces[f];
+        else if (f < nIF) { const int P = M->owner[f], N = M->neighbour[f]; gf = M->weights[f]*(gammaCells[P] - gammaCells[N]) + gammaCells[N]; }
+        else gf = gammaCells[M->owner[f]];
+        gms[f] = gf*M->magSf[f];
+    }
+    /* fvmLaplacianUncorrected: upper = deltaCoeffs*gammaMagSf; negSumDiag: Diag[l] -= Lower; Diag[u] -= Upper, face by face */
+    for (int f = 0; f < nIF; f++)
+    {
+        Lupper[f] = M->deltaCoeffs[f]*gms[f];
+        Ldiag[M->owner[f]] -= Lupper[f];
+        Ldiag[M->neighbour[f]] -= Lupper[f];
+    }
+    /* surfaceIntegrate(phi): internal faces, then patches; then /V */
+    if (phi)
+    {
+        for (int f = 0; f < nIF; f++) { div[M->owner[f]] += phi[f]; div[M->neighbour[f]] -= phi[f]; }
+        for (int f = nIF; f < nF; f++) if (!emptyFace[f]) div[M->owner[f]] += phi[f];
+        for (int c = 0; c < nC; c++) div[c] /= M->V[c];
+    }
+    const double rDeltaT = ddtScheme == 1 ? 1.0/deltaT : 0.0;
+    for (int c = 0; c < nC; c++)
+    {
+        const double V = M->V[c];
+        double dA = 0.0, sA = 0.0;
+        if (ddtScheme == 1) { dA = (rDeltaT*V)*rate[c]; sA = ((rDeltaT*psiOld[c])*V)*rate[c]; }
+        if (sign > 0) { diag[c] = dA - Ldiag[c]; source[c] = sA - 0.0; }
+        else { diag[c] = Ldiag[c]; source[c] = phi ? 0.0 + V*div[c] : 0.0; }
+    }
+    for (int f = 0; f < nIF; f++) upper[f] = sign > 0 ? 0.0 - Lupper[f] : Lupper[f];
+    for (int f = nIF; f < nF; f++)
+    {
+        const int bf = f - nIF;
+        double Lic = 0.0, Lbc = 0.0;
+        if (bfKind[bf] == 1 && !emptyFace[f])
+        {
+            /* fixedValue: gradientInternalCoeffs = -deltaCoeffs; gradientBoundaryCoeffs = deltaCoeffs*value */
+            Lic = gms[f]*(-M->deltaCoeffs[f]);
+            Lbc = (-gms[f])*(M->deltaCoeffs[f]*bfValue[bf]);
+        }
+        internalCoeffs[bf] = sign > 0 ? 0.0 - Lic : Lic;
+        boundaryCoeffs[bf] = sign > 0 ? 0.0 - Lbc : Lbc;
+    }
+    if (refCell >= 0)
+    {
+        source[refCell] += diag[refCell]*refValue;
+        diag[refCell] += diag[refCell];
+    }
+    free(emptyFace); free(gms); free(Ldiag); free(Lupper); free(div);
+}
