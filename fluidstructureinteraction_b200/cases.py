@@ -320,3 +320,14 @@ def boundary_fields(mesh, settings, traction=None, pressure=None):
         if n in settings["fixedValue"]:
             fv[s] = settings["fixedValue"][n]
     return tr, pr, fv
+
+
+def three_k(E, nu, rho, planeStress=False):
+    """unsTotalLagrangianStress::threeK() (unsTotalLagrangianStress.C:1306-1318) = constitutiveModel::threeK()*rho
+    (constitutiveModel.C:260-303): E/(rho*(1 - 2 nu)) [plane stress: E/(rho*(1 - nu))] times rho."""
+    return (E/(rho*(1.0 - nu)))*rho if planeStress else (E/(rho*(1.0 - 2.0*nu)))*rho
+
+
+# run/thermalStressFoam/flange: constant/thermalProperties:17-24, constant/rheologyProperties, 0/T, system/controlDict (config 4)
+FLANGE = dict(E=2.0e11, nu=0.3, rho=7800.0, C=500.0, k=50.0, alpha=1.0e-6, T0=0.0, Tcold=273.0, Thot=573.0, deltaT=0.01,
+              nCorrectors=1000, convergenceTolerance=1e-5, relaxD=0.5)
