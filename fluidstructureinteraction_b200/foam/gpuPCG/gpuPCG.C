@@ -148,8 +148,18 @@ Foam::gpuPCG::gpuPCG
 
 // * * * * * * * * * * * * * * * Member Functions  * * * * * * * * * * * * * //
 
-void Foam::gpuPCG::clearCache()
+void Foam::gpuPCG::clearCache(const lduAddressing* addr)
 {
+    if (addr)
+    {
+        std::map<const lduAddressing*, gpuPCGCacheEntry>::iterator it = gpuPCGCache_.find(addr);
+        if (it != gpuPCGCache_.end())
+        {
+            gpupcg_destroy(it->second.handle);
+            gpuPCGCache_.erase(it);
+        }
+        return;
+    }
     for
     (
         std::map<const lduAddressing*, gpuPCGCacheEntry>::iterator it = gpuPCGCache_.begin();

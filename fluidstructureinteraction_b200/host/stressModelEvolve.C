@@ -60,6 +60,19 @@ evolveResult unsTotalLagrangianStressGpu::evolve
     const dictionary& stressProperties, const dictionary& solverDict, scalar relaxD, volToPointFn interpolate, void* ctx
 )
 {
+    // This driver is the round-1, half-resident form of the loop (linear elastic, steadyState d2dt2, vol->point interpolation as
+    // a host callback).  Settings it does not implement are refused, not ignored; the complete loop -- every branch, device
+    // resident -- is gpuUnsTotalLagrangianStress (gpuStressModel.{H,C}).
+    if (stressProperties.found("nonLinear"))
+    {
+        const std::string v = stressProperties.lookup("nonLinear");
+        if (v == "yes" || v == "on" || v == "true")
+            FatalErrorIn("unsTotalLagrangianStressGpu::evolve") << "nonLinear yes: use gpuUnsTotalLagrangianStress (the resident loop); "
+                << "this driver solves the linear model only" << abort(FatalError);
+    }
+    if (stressProperties.found("K") || stressProperties.found("thermalStress"))
+        FatalErrorIn("unsTotalLagrangianStressGpu::evolve") << "damping (K) / thermal stress: use gpuUnsTotalLagrangianStress"
+            << abort(FatalError);
     const int nCorr = atoi(std::string(stressProperties.lookup("nCorrectors")).c_str());
     const scalar convergenceTolerance = atof(std::string(stressProperties.lookup("convergenceTolerance")).c_str());
     scalar relConvergenceTolerance = 0;
@@ -168,7 +181,8 @@ evolveResult unsTotalLagrangianStressGpu::evolve
         R.lastSolverInitialResidual = solverPerf.initialResidual();
 
         // D_.relax();  ...  res = residual()   (the residual only reads D, prevIter and oldTime: evaluated with the relax)
-        meshCheck(gm_, gpupcg_relax_residual(gm_, relaxD, relaxD >= 0 ? 1 : 0, &D[0], &Dprev[0], &Dold[0], &res),
+        // relaxD <= 0: no relaxation factor for D in fvSolution -> D.relax() is a no-op (a factor of 0 would freeze D at prevIter)
+        meshCheck(gm_, gpupcg_relax_residual(gm_, relaxD, relaxD > 0 ? 1 : 0, &D[0], &Dprev[0], &Dold[0], &res),
                   "gpupcg_relax_residual");
         lap(tRelax);
 
@@ -193,7 +207,7 @@ evolveResult unsTotalLagrangianStressGpu::evolve
     if (timing)
         fprintf(stderr, "evolve timing [s]: assemble %.3f  solve %.3f  relax/residual %.3f  volToPoint %.3f  gradients %.3f  sigma+fetch %.3f  (%s)\n",
                 tAsm, tSolve, tRelax, tInterp, tGrad, tEnd, residentSolve ? "resident" : "host matrix");
-    gpuPCG::clearCache();       // `addr` dies with this call
+    gpuPCG::clearCache(&addr);  // `addr` dies with this call: only its handle, other meshes keep theirs
     R.nOuterIterations = iCorr; R.maxRes = maxRes; R.res = res;
     return R;
 }
