@@ -484,6 +484,12 @@ __device__ __forceinline__ int take_tile(unsigned long long* tileTicket, int nTi
 // ifMask (may be null): rows that own coupled faces are left out of the MODE-1 dot here (k_iface_update adds them).
 // ------------------------------------------------------------------------------------------
 static constexpr int AMUL_TPB = 128;
+#ifndef AMUL_MINB
+#define AMUL_MINB 1
+#endif
+#ifndef AMUL_V_MINB
+#define AMUL_V_MINB 1
+#endif
 static constexpr int AMUL_RX = 4;       // cross-tile x gathers / coefficient gathers whose indices a thread carries in
 static constexpr int AMUL_RC = 2;       // registers one tile ahead (more than that: blocking index loads)
 
@@ -524,7 +530,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // Operand codes are direct indices into xv / cv (built once per mesh), so the row loop is branch-free:
 // all codes of a row are loaded first, then all operands, then the products are added in reference order.
 template <int MODE>
-__global__ void __launch_bounds__(AMUL_TPB) k_amul_tile(TileArgs A, const double* __restrict__ diag,
+__global__ void __launch_bounds__(AMUL_TPB, AMUL_MINB) k_amul_tile(TileArgs A, const double* __restrict__ diag,
                                                         const double* __restrict__ Uval, const int* __restrict__ rowOld,
                                                         const unsigned int* __restrict__ ifMask,
                                                         const double* __restrict__ x, double* __restrict__ Ax,

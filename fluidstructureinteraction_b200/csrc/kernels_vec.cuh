@@ -283,7 +283,7 @@ __device__ __forceinline__ void cp_async16(unsigned dst, const void* src)
 }
 
 template <int NB, int MODE>
-__global__ void __launch_bounds__(AMUL_TPB) k_amul_tile_v(TileArgs A, const double* __restrict__ diag,
+__global__ void __launch_bounds__(AMUL_TPB, AMUL_V_MINB) k_amul_tile_v(TileArgs A, const double* __restrict__ diag,
                                                           const double* __restrict__ Uval, const int* __restrict__ rowOld,
                                                           const unsigned int* __restrict__ ifMask,
                                                           const double* __restrict__ x, double* __restrict__ Ax,
