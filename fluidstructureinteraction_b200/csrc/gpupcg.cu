@@ -856,6 +856,11 @@ static cudaError_t pencil_attr(size_t cap)
     cudaError_t e = cudaFuncSetAttribute((k_dic_pencil<NB, MODE, LONG, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
     if (!e && NB > 1)
         e = cudaFuncSetAttribute((k_dic_pencil<NB, MODE, LONG, NB>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+    if (MODE == 0 && NB > 1)        // forward sweep carrying the x/r update (batched solves)
+    {
+        if (!e) e = cudaFuncSetAttribute((k_dic_pencil<NB, 0, LONG, 1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+        if (!e) e = cudaFuncSetAttribute((k_dic_pencil<NB, 0, LONG, NB, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+    }
     return e;
 }
 template <int NB>
@@ -882,18 +887,21 @@ static int pencil_coeffs(gpupcg_handle h)
 
 template <int NB, int MODE>
 static int launch_pencil(gpupcg_handle h, const double* diagOrRD, const double* rA, unsigned long long* y, unsigned long long* out,
-                         double* rDout, double* partials, DevState* st, int gated)
+                         double* rDout, double* partials, DevState* st, int gated, const FuseXR* fx = nullptr, int histStride = 0)
 {
     const bool withDot = (MODE == 2) && partials != nullptr;
+    const bool fuse = (MODE == 0) && NB > 1 && fx != nullptr && fx->x != nullptr;
     PencilArgs A = h->pen;
+    A.fxX = nullptr; A.fxPA = nullptr; A.fxWA = nullptr; A.fxRA = nullptr; A.fxHistory = nullptr; A.fxHistStride = 0;
+    if (fuse) { A.fxX = fx->x; A.fxPA = fx->pA; A.fxWA = fx->wA; A.fxRA = fx->rA; A.fxHistory = fx->history; A.fxHistStride = histStride; }
     // ring stages: as many as fit the budget (default ~100 KB: two CTAs per SM), 2 ... 8
     const size_t cap = std::min<size_t>(h->smemCap, (size_t)env_int("GPUPCG_PENCIL_SMEM_KB", 100)*1024);
     int nst = std::max(2, std::min(8, env_int("GPUPCG_PENCIL_STAGES", 8)));
-    while (nst > 2 && pen_smem_bytes<NB, MODE>(nst, A.w1, A.w2, withDot) > cap) nst--;
+    while (nst > 2 && pen_smem_bytes<NB, MODE>(nst, A.w1, A.w2, withDot, fuse) > cap) nst--;
     A.nStages = nst;
     A.fetchWindow = env_int("GPUPCG_PENCIL_FETCH_WINDOW", 1);     // 1: measured best (profiles/r2_pencil_sweeps.md); 0 = adaptive
     A.fetchSleep = std::max(0, env_int("GPUPCG_PENCIL_FETCH_SLEEP", 0));      // measured: profiles/r2_pencil_sweeps.md (knob matrix)
-    const size_t smem = pen_smem_bytes<NB, MODE>(nst, A.w1, A.w2, withDot);
+    const size_t smem = pen_smem_bytes<NB, MODE>(nst, A.w1, A.w2, withDot, fuse);
     if (smem > h->smemCap) { h->err = "pencil sweep: the ring does not fit in shared memory"; return GPUPCG_ERR_UNSUPPORTED; }
     h->launches++;
     // one sweep warp per component (default for the batched solves) or one warp for all of them
@@ -906,19 +914,25 @@ static int launch_pencil(gpupcg_handle h, const double* diagOrRD, const double* 
     // upstream, the whole wavefront with them -- so by default no more CTAs per SM than keep the sweep warps <= 4.
     int occ = 0, grid = 1;
     const int perSmWanted = std::max(1, env_int("GPUPCG_PENCIL_CTAS_PER_SM", split ? std::max(1, 4/NB) : 2));
-#define PEN_OCC(LONG_, SW_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (k_dic_pencil<NB, MODE, LONG_, SW_>), (SW_ + 1 + PEN_FW)*32, smem)
-#define PEN_GO(LONG_, SW_) k_dic_pencil<NB, MODE, LONG_, SW_><<<grid, (SW_ + 1 + PEN_FW)*32, smem, h->stream>>>(A, diagOrRD, rA, y, out, rDout, h->dTileTicket, partials, h->partStride, st, gated)
-#define PEN_RUN(LONG_, SW_) do { CK(PEN_OCC(LONG_, SW_)); if (occ < 1) { h->err = "pencil sweep: no CTA fits an SM"; return GPUPCG_ERR_UNSUPPORTED; } \
-        grid = std::min(A.nPencils, h->numSMs*std::min(occ, perSmWanted)); PEN_GO(LONG_, SW_); } while (0)
+#define PEN_THREADS(SW_, FUSE_) ((SW_ + 1 + PEN_FW + ((FUSE_) ? 1 : 0))*32)
+#define PEN_RUN(LONG_, SW_, FUSE_) do { \
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (k_dic_pencil<NB, MODE, LONG_, SW_, FUSE_>), PEN_THREADS(SW_, FUSE_), smem)); \
+        if (occ < 1) { h->err = "pencil sweep: no CTA fits an SM"; return GPUPCG_ERR_UNSUPPORTED; } \
+        grid = std::min(A.nPencils, h->numSMs*std::min(occ, perSmWanted)); \
+        k_dic_pencil<NB, MODE, LONG_, SW_, FUSE_><<<grid, PEN_THREADS(SW_, FUSE_), smem, h->stream>>>(A, diagOrRD, rA, y, out, rDout, \
+            h->dTileTicket, partials, h->partStride, st, gated); } while (0)
+#define PEN_DISPATCH(LONG_) do { \
+        if (MODE == 0 && NB > 1 && fuse) { if (split) PEN_RUN(LONG_, NB, (MODE == 0 && NB > 1)); else PEN_RUN(LONG_, 1, (MODE == 0 && NB > 1)); } \
+        else { if (split) PEN_RUN(LONG_, NB, false); else PEN_RUN(LONG_, 1, false); } } while (0)
     switch (h->plan.pLong)
     {
-        case 0: if (split) PEN_RUN(0, NB); else PEN_RUN(0, 1); break;
-        case 1: if (split) PEN_RUN(1, NB); else PEN_RUN(1, 1); break;
-        default: if (split) PEN_RUN(2, NB); else PEN_RUN(2, 1); break;
+        case 0: PEN_DISPATCH(0); break;
+        case 1: PEN_DISPATCH(1); break;
+        default: PEN_DISPATCH(2); break;
     }
+#undef PEN_DISPATCH
 #undef PEN_RUN
-#undef PEN_OCC
-#undef PEN_GO
+#undef PEN_THREADS
     return GPUPCG_OK;
 }
 

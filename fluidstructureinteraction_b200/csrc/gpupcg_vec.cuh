@@ -235,9 +235,19 @@ int vec_sweeps(gpupcg_handle h, double* rA, double* z, bool reduce, int gated, b
     const FuseXR none{nullptr, nullptr, nullptr, nullptr, nullptr};
     if (h->pencil)
     {
-        if (fuseXR) { h->err = "internal: the pencil sweeps do not carry the x/r update"; return GPUPCG_ERR_STATE; }
         int rcp = pencil_coeffs(h); if (rcp) return rcp;
+        if (fuseXR)
+        {
+            // the pending x/r update of the previous iteration rides in the forward sweep (its own warp per CTA)
+            const FuseXR fxp{h->vX, h->vPA, zb, h->vRA, h->vHistory};
+            rcp = launch_pencil<NB, 0>(h, h->vRD, rA, nullptr, yb, nullptr, h->vPartials, h->vState, gated, &fxp, h->historyCap);
+            if (rcp) return rcp;
+            rcp = vec_ordered_step<NB>(h, S_XR); if (rcp) return rcp;
+        }
+        else
+        {
         rcp = launch_pencil<NB, 0>(h, h->vRD, rA, nullptr, yb, nullptr, nullptr, h->vState, gated); if (rcp) return rcp;
+        }
         rcp = launch_pencil<NB, 2>(h, h->vRD, rA, yb, zb, nullptr, reduce ? h->vPartials : nullptr, h->vState, gated); if (rcp) return rcp;
         CK(cudaGetLastError());
         if (reduce) return vec_ordered_step<NB>(h, S_SWEEP);
@@ -308,7 +318,9 @@ int vec_solve_core(gpupcg_handle h, double tol, double relTol, int minIter, int 
     // The x/r update rides in the staging of the next forward sweep while the sweeps are latency-bound (their CTAs
     // have bandwidth to spare); on large sub-domains the sweeps are throughput-bound and a streaming kernel is cheaper.
     const int fuseEnv = env_int("GPUPCG_FUSE_XR", -1);
-    const bool fuseXR = !h->pencil && ((fuseEnv >= 0) ? (fuseEnv != 0) : (P.nRows <= env_int("GPUPCG_FUSE_XR_MAXROWS", 3000000)));
+    // (pencil sweeps: the update can ride along too -- an extra warp per CTA, kernels_pencil.cuh FUSE -- but measured it only
+    // moves the 59 us of k_xr_update_v into the forward sweep: off unless GPUPCG_FUSE_XR=1; profiles/r2_pencil_sweeps.md)
+    const bool fuseXR = (fuseEnv >= 0) ? (fuseEnv != 0) : (!h->pencil && P.nRows <= env_int("GPUPCG_FUSE_XR_MAXROWS", 3000000));
     auto all_done_host = [&](const DevState* st) { bool d = true; for (int k = 0; k < NB; k++) d = d && st[k].done; return d; };
     auto enqueue_check = [&](int slot) -> cudaError_t
     {

@@ -52,22 +52,24 @@ struct PencilArgs
     unsigned int* smCounter;        // [1024] per-SM CTA counter (role rotation), may be null
     const double* coefF;            // [nRows][3] upper of the faces to the lower neighbours along z, y, x (0: none)
     const double* coefB;            // [nRows][3] ... to the upper neighbours
+    // forward sweep with the pending x/r update of PCG riding along (FUSE): x += alpha pA; rA -= alpha wA; sum|rA|; wA re-armed
+    double* fxX; const double* fxPA; unsigned long long* fxWA; double* fxRA; double* fxHistory; int fxHistStride;
 };
 
 template <int NB> struct PenRow { static constexpr int NS = (NB == 3) ? 4 : NB; static constexpr int BYTES = 8*NS; };
 
 // bytes of one ring stage: coefficients + (rD) + start operand (+ rA for the fused dot)
 template <int NB, int MODE>
-__host__ __device__ constexpr int pen_stage_bytes(bool withDot)
+__host__ __device__ constexpr int pen_stage_bytes(bool withDot, bool fuse = false)
 {
-    return PEN_SS*32*(24 + PenRow<NB>::BYTES*((MODE == 1) ? 1 : (MODE == 2 && withDot) ? 3 : 2));
+    return PEN_SS*32*(24 + PenRow<NB>::BYTES*((MODE == 1) ? 1 : (MODE == 2 && withDot) ? 3 : (MODE == 0 && fuse) ? 5 : 2));
 }
 template <int NB>
 __host__ __device__ constexpr int pen_ext_bytes(int w1, int w2) { return PEN_R*(w1 + w2)*PenRow<NB>::BYTES; }
 template <int NB, int MODE>
-__host__ inline size_t pen_smem_bytes(int nStages, int w1, int w2, bool withDot)
+__host__ inline size_t pen_smem_bytes(int nStages, int w1, int w2, bool withDot, bool fuse = false)
 {
-    return (size_t)nStages*pen_stage_bytes<NB, MODE>(withDot) + pen_ext_bytes<NB>(w1, w2) + 8*8 + 64;
+    return (size_t)nStages*pen_stage_bytes<NB, MODE>(withDot, fuse) + pen_ext_bytes<NB>(w1, w2) + 8*8 + 64 + 8*8;
 }
 
 // ---- NB values of a row: shared / global, plain / volatile / published -------------------------------------------
@@ -181,15 +183,16 @@ __global__ void __launch_bounds__(TPB) k_pencil_coeffs(long long n3, const int* 
 // MODE 0 forward sweep (in = rA, out = y), 1 factor (in = diag, out = scratch, rDout = 1/out), 2 backward sweep
 // (in = y, out = wA; y re-armed; optional fused dot wA . rA).  LONG = which axis is the long one (0 x, 1 y, 2 z):
 // it fixes where the own-lane dependency sits in the reference's z, y, x subtraction order.
-template <int NB, int MODE, int LONG, int SW>
-__global__ void __launch_bounds__((SW + 1 + PEN_FW)*32) k_dic_pencil(PencilArgs A, const double* __restrict__ diagOrRD, const double* __restrict__ rA,
+template <int NB, int MODE, int LONG, int SW, bool FUSE = false>
+__global__ void __launch_bounds__((SW + 1 + PEN_FW + (FUSE ? 1 : 0))*32) k_dic_pencil(PencilArgs A, const double* __restrict__ diagOrRD, const double* __restrict__ rA,
                                                         unsigned long long* y, unsigned long long* out, double* __restrict__ rDout,
                                                         unsigned long long* tileTicket, double* partials, int partStride,
                                                         DevState* st, int gated)
 {
     constexpr int NS = PenRow<NB>::NS, RB = PenRow<NB>::BYTES;
     constexpr bool BWD = (MODE == 2), FACTOR = (MODE == 1);
-    constexpr int NTH = (SW + 1 + PEN_FW)*32;   // SW sweep warps + loader + PEN_FW fetch warps
+    constexpr int NTH = (SW + 1 + PEN_FW + (FUSE ? 1 : 0))*32;   // SW sweep warps + loader + PEN_FW fetch warps (+ the update warp)
+    static_assert(!FUSE || MODE == 0, "the x/r update rides in the forward sweep");
     constexpr int NBW = NB/SW;              // components a sweep warp carries
     static_assert(SW == 1 || SW == NB, "one sweep warp for all components, or one per component");
     if (gated)
@@ -203,12 +206,13 @@ __global__ void __launch_bounds__((SW + 1 + PEN_FW)*32) k_dic_pencil(PencilArgs 
     extern __shared__ __align__(128) unsigned char smemRaw[];
     unsigned sb;
     asm volatile("mov.u32 %0, %1;" : "=r"(sb) : "r"((unsigned)__cvta_generic_to_shared(smemRaw)));
-    const int stageBytes = pen_stage_bytes<NB, MODE>(withDot);
+    const int stageBytes = pen_stage_bytes<NB, MODE>(withDot, FUSE);
     const int NST = A.nStages;
     const int E = A.w1 + A.w2;
     const unsigned sExt = sb + (unsigned)(NST*stageBytes);
     const unsigned sBar = sExt + (unsigned)(PEN_R*E*RB);
     const unsigned sProg = sBar + 64u;
+    const unsigned sRdy = sBar + 128u;      // FUSE: per stage, "the update warp is through with it" (what the sweep warps wait for)
     int* slotPtr = (int*)(smemRaw + NST*stageBytes + PEN_R*E*RB + 64 + 16);
     const int lane = threadIdx.x & 31;
     // Which warp sweeps: the CTAs that share an SM take turns (a per-SM counter), so that two sweep warps never sit on
@@ -240,6 +244,7 @@ __global__ void __launch_bounds__((SW + 1 + PEN_FW)*32) k_dic_pencil(PencilArgs 
     // stage layout: [coef 32*SS*24][dv 32*SS*RB (not FACTOR)][in 32*SS*RB][rA 32*SS*RB (withDot)]
     const unsigned oCoef = 0u, oDv = PEN_SS*32*24, oIn = oDv + (FACTOR ? 0u : (unsigned)(PEN_SS*32*RB));
     const unsigned oRA = oIn + (unsigned)(PEN_SS*32*RB);
+    const unsigned oFW = oRA, oFP = oFW + (unsigned)(PEN_SS*32*RB), oFX = oFP + (unsigned)(PEN_SS*32*RB);   // FUSE: wA, pA, x rows
 
     if (threadIdx.x == 0)
     {
@@ -247,6 +252,11 @@ __global__ void __launch_bounds__((SW + 1 + PEN_FW)*32) k_dic_pencil(PencilArgs 
         {
             if (tileIdx != (int)blockIdx.x) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(sBar + 8u*s) : "memory");
             mbar_init(sBar + 8u*s, 1);
+            if (FUSE)
+            {
+                if (tileIdx != (int)blockIdx.x) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(sRdy + 8u*s) : "memory");
+                mbar_init(sRdy + 8u*s, 1);
+            }
         }
         for (int i = 0; i < SW; i++) asm volatile("st.volatile.shared.s32 [%0], %1;" :: "r"(sProg + 4u*i), "r"(0) : "memory");
     }
@@ -254,9 +264,10 @@ __global__ void __launch_bounds__((SW + 1 + PEN_FW)*32) k_dic_pencil(PencilArgs 
     for (int i = threadIdx.x; i < PEN_R*E*NS; i += NTH) ((unsigned long long*)(smemRaw + NST*stageBytes))[i] = SENT;
     __syncthreads();
 
-    double dot[NB];
+    double dot[NB], vXR[NB];
 #pragma unroll
-    for (int k = 0; k < NB; k++) dot[k] = 0.0;
+    for (int k = 0; k < NB; k++) { dot[k] = 0.0; vXR[k] = 0.0; }
+    const unsigned sStageReady = FUSE ? sRdy : sBar;        // what a sweep warp waits for before it reads a stage
 
     // slowest sweep warp's progress (steps consumed)
     auto progress = [&]() { int p = pen_ld_progress(sProg); for (int i = 1; i < SW; i++) p = min(p, pen_ld_progress(sProg + 4u*i)); return p; };
@@ -320,7 +331,7 @@ __global__ void __launch_bounds__((SW + 1 + PEN_FW)*32) k_dic_pencil(PencilArgs 
         int slot = 0;
         unsigned phase = 0u;
         unsigned sAddr = sb;                                       // ring stage being swept
-        mbar_wait(sBar, 0);
+        mbar_wait(sStageReady, 0);
         load_static(sAddr, BWD ? PEN_SS - 1 : 0);
         products();
         // global row of the current step: rows ascend with the step forward, descend backward
@@ -353,7 +364,7 @@ __global__ void __launch_bounds__((SW + 1 + PEN_FW)*32) k_dic_pencil(PencilArgs 
                 if (j + 1 < PEN_SS) load_static(sAddr, BWD ? PEN_SS - 2 - j : j + 1);
                 else if (g + 1 < nStagesTotal)
                 {
-                    mbar_wait(sBar + 8u*slotN, phaseN);
+                    mbar_wait(sStageReady + 8u*slotN, phaseN);
                     load_static(sAddrN, BWD ? PEN_SS - 1 : 0);
                 }
                 // d. wait for the external values (warp-uniform loop: the warp stays converged)
@@ -469,10 +480,81 @@ __global__ void __launch_bounds__((SW + 1 + PEN_FW)*32) k_dic_pencil(PencilArgs 
                 if (!FACTOR) bulk_g2s(dst + oDv, diagOrRD + (size_t)NS*r0, PEN_SS*32*RB, bar);
                 bulk_g2s(dst + oIn, inArr + (size_t)NS*r0, PEN_SS*32*RB, bar);
                 if (withDot) bulk_g2s(dst + oRA, rA + (size_t)NS*r0, PEN_SS*32*RB, bar);
+                if (FUSE)
+                {
+                    bulk_g2s(dst + oFW, (const double*)A.fxWA + (size_t)NS*r0, PEN_SS*32*RB, bar);
+                    bulk_g2s(dst + oFP, A.fxPA + (size_t)NS*r0, PEN_SS*32*RB, bar);
+                    bulk_g2s(dst + oFX, A.fxX + (size_t)NS*r0, PEN_SS*32*RB, bar);
+                }
             }
         }
     }
-    else
+    else if (FUSE && warp == SW + PEN_FW + 1)
+    {
+        // ------------------------------------------------------------------------------------------ the update warp
+        // x += alpha pA;  rA -= alpha wA;  sum|rA|;  wA re-armed -- the BLAS-1 tail of the previous PCG iteration (k_xr_update_v),
+        // applied stage by stage to the rows the loader has just brought in: the new rA goes back to global memory AND into the
+        // stage's `in` slot, where the sweep warps pick it up.  The sweep is a dependency chain with the SM's bandwidth idle;
+        // this warp uses it.
+        bool pend[NB], any = false;
+        double alpha[NB];
+#pragma unroll
+        for (int k = 0; k < NB; k++)
+        {
+            pend[k] = st[k].pending != 0;
+            any = any || pend[k];
+            alpha[k] = pend[k] ? __ddiv_rn(st[k].wArA, st[k].wApA) : 0.0;
+        }
+        unsigned long long sentBits[NS];
+#pragma unroll
+        for (int k = 0; k < NS; k++) sentBits[k] = SENT;
+        for (int g = 0; g < nStagesTotal; g++)
+        {
+            const int s = g % NST;
+            const unsigned ph = (unsigned)((g/NST) & 1);
+            const unsigned stg = sb + (unsigned)(s*stageBytes);
+            mbar_wait(sBar + 8u*s, ph);
+            if (any)
+            {
+                const size_t r0 = (size_t)base + (size_t)32*(PEN_SS*g);
+#pragma unroll
+                for (int i = 0; i < PEN_SS; i++)
+                {
+                    const unsigned r = (unsigned)(i*32 + lane);
+                    double w[NB], pv[NB], xx[NB], rr[NB];
+                    pen_lds<NB>(stg + oFW + (unsigned)RB*r, w);
+                    pen_lds<NB>(stg + oFP + (unsigned)RB*r, pv);
+                    pen_lds<NB>(stg + oFX + (unsigned)RB*r, xx);
+                    pen_lds<NB>(stg + oIn + (unsigned)RB*r, rr);
+#pragma unroll
+                    for (int k = 0; k < NB; k++)
+                    {
+                        if (pend[k])
+                        {
+                            xx[k] = __dadd_rn(xx[k], __dmul_rn(alpha[k], pv[k]));
+                            rr[k] = __dsub_rn(rr[k], __dmul_rn(alpha[k], w[k]));
+                            vXR[k] += fabs(rr[k]);
+                        }
+                    }
+                    pen_store_plain<NB>(A.fxX + (size_t)NS*(r0 + r), xx);
+                    pen_store_plain<NB>(A.fxRA + (size_t)NS*(r0 + r), rr);
+                    {
+                        unsigned long long* q = A.fxWA + (size_t)NS*(r0 + r);
+                        if (NS == 4) { *reinterpret_cast<ulonglong2*>(q) = make_ulonglong2(SENT, SENT); *reinterpret_cast<ulonglong2*>(q + 2) = make_ulonglong2(SENT, SENT); }
+                        else { for (int k = 0; k < NS; k++) q[k] = sentBits[k]; }
+                    }
+                    // the sweep warps read the updated rA from the stage
+                    unsigned long long bits[NB];
+#pragma unroll
+                    for (int k = 0; k < NB; k++) bits[k] = (unsigned long long)__double_as_longlong(rr[k]);
+                    pen_sts_bits<NB>(stg + oIn + (unsigned)RB*r, bits);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(sRdy + 8u*s) : "memory");
+        }
+    }
+    else if (warp > SW && warp <= SW + PEN_FW)
     {
         // ------------------------------------------------------------------------------------------ the fetch lanes
         const int fl = (warp - SW - 1)*32 + lane;
@@ -546,6 +628,8 @@ __global__ void __launch_bounds__((SW + 1 + PEN_FW)*32) k_dic_pencil(PencilArgs 
         }
     }
     // ---------------------------------------------------------------------------------------------- epilogue
+    if (FUSE)       // every CTA takes part (S_XR is a no-op when nothing was pending)
+        grid_reduce_finish_v<1, NB, NTH>(vXR, partials, partStride, tile, A.nPencils, st, S_XR, A.fxHistory, A.fxHistStride);
     if (withDot)
     {
         if (NB == 1)
