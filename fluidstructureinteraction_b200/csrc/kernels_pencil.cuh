@@ -585,6 +585,12 @@ __global__ void __launch_bounds__((SW + 1 + PEN_FW + (FUSE ? 1 : 0))*32) k_dic_p
             const bool adaptive = A.fetchWindow <= 0;
             SpinWatch watch;
             bool bail = false;
+            // One poll in flight (the default): the components of a row are published by different sweep warps (SW = NB) that
+            // drift against each other by a few steps, so a component is handed over the moment IT arrives -- waiting for the
+            // whole row would tie every consumer warp to the slowest producer warp at every pencil face.
+            const bool perCmpt = (W == 1 && !adaptive && NB > 1);
+            unsigned got = 0u;
+            constexpr unsigned ALLC = (1u << NB) - 1u;
             while (next < steps)
             {
                 const int prog = progress();
@@ -607,6 +613,23 @@ __global__ void __launch_bounds__((SW + 1 + PEN_FW + (FUSE ? 1 : 0))*32) k_dic_p
                     }
                 }
                 int m = 0;
+                if (perCmpt)
+                {
+                    if (can[0])
+                    {
+                        const unsigned dst = dstBase + (unsigned)((next & (PEN_R - 1))*E*RB);
+#pragma unroll
+                        for (int k = 0; k < NB; k++)
+                        {
+                            const bool fresh = !(got & (1u << k)) && (w[0][k] != SENT);
+                            if (fresh) asm volatile("st.volatile.shared.b64 [%0], %1;" :: "r"(dst + 8u*k), "l"(w[0][k]) : "memory");
+                            got |= fresh ? (1u << k) : 0u;
+                        }
+                        if (got == ALLC) { m = 1; got = 0u; }
+                    }
+                }
+                else
+                {
 #pragma unroll
                 for (int u = 0; u < PEN_FU; u++)
                 {
@@ -618,6 +641,7 @@ __global__ void __launch_bounds__((SW + 1 + PEN_FW + (FUSE ? 1 : 0))*32) k_dic_p
                         pen_sts_bits<NB>(dstBase + (unsigned)(((next + u*SPR) & (PEN_R - 1))*E*RB), w[u]);
                         m++;
                     }
+                }
                 }
                 next += m*SPR;
                 if (adaptive) W = (issued > 0 && m == issued) ? min(PEN_FU, W + 1) : max(1, m);
