@@ -77,6 +77,8 @@ def _parse_list(tokens, i, close):
 def _parse_dict(tokens, i, close):
     d = {}
     while i < len(tokens) and tokens[i][0] != close:
+        if tokens[i][0] == "\0":                 # end of file inside a sub-dictionary (run/fsiFoam/3dTube/fluid/0/p lacks the
+            return d, i                          # closing brace of boundaryField): close what is open, as the file's reader must
         key, i = _join_keyword(tokens, i)
         if key == ";":
             continue

@@ -23,10 +23,13 @@ CASES = {
     "beam_solid": "fsiFoam/beamInCrossFlow/solid",
     "tube_solid": "fsiFoam/3dTube/solid",
     "flange": "thermalStressFoam/flange",
+    "beam_fluid": "fsiFoam/beamInCrossFlow/fluid",
+    "tube_fluid": "fsiFoam/3dTube/fluid",
 }
 FILES = {"D": "0/D", "pointD": "0/pointD", "rheologyProperties": "constant/rheologyProperties",
          "stressProperties": "constant/stressProperties", "fvSolution": "system/fvSolution", "fvSchemes": "system/fvSchemes",
-         "controlDict": "system/controlDict"}
+         "controlDict": "system/controlDict", "p": "0/p", "T": "0/T", "thermalProperties": "constant/thermalProperties",
+         "flowProperties": "constant/flowProperties"}
 
 
 def main():

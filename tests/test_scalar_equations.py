@@ -112,3 +112,58 @@ def test_gpu_thermal_step_assembled_and_solved_on_the_device():
         assert np.abs(Tg - Tc).max() <= 1e-9*np.abs(Tc).max()
     assert 273.0 - 1e-6 <= Tg.min() and Tg.max() <= 573.0 + 1e-6 and Tg.max() > 300.0          # heat enters from the hot end, maximum principle
     gm.close(); gs.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# config 5's fluid half: the pressure equation of the PISO loop on the SHIPPED fluid meshes with the shipped 0/p boundary types
+# ---------------------------------------------------------------------------------------------------------------------
+def _shipped_fluid(name):
+    import json, os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    m = meshes.PolyMesh.load_npz(os.path.join(gold, name + ".polymesh.npz"))
+    with open(os.path.join(gold, name + ".case.json")) as f:
+        d = json.load(f)
+    # 0/p: fixedValue (and timeVaryingUniformFixedValue, a fixedValue whose value comes from a table) fix p; extrapolatedPressure
+    # (fixedGradient) and symmetryPlane contribute no implicit coefficient
+    table = {}
+    for patch, b in d["p"]["boundaryField"].items():
+        if b["type"] in ("fixedValue", "timeVaryingUniformFixedValue"):
+            table[patch] = (1, 0.0 if b["type"] == "fixedValue" else 1333.2)
+    sol = d["fvSolution"]["solvers"]["p"]
+    return m, geometry.compute(m), table, float(sol["tolerance"]), float(sol["relTol"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["beam_fluid", "tube_fluid"])
+def test_gpu_pressure_equation_on_the_shipped_fluid_meshes(name):
+    """fvm::laplacian(1/interpolate(AU), p) == fvc::div(phi) (consistentIcoFlow.C:211-224) on run/fsiFoam/{beamInCrossFlow,
+    3dTube}/fluid: assembled on the device bit for bit as the oracle assembles it, then solved by gpuPCG with the shipped
+    tolerance (the shipped solver entry is GAMG; `solver gpuPCG; preconditioner DIC;` is what this path offers) against the
+    oracle's PCG: same iteration count, 1e-9."""
+    import fluidstructureinteraction_b200 as pkg
+    m, g, table, tol, relTol = _shipped_fluid(name)
+    assert any(k == 1 for k, _ in table.values())            # a fixedValue patch: no reference cell needed (setRefCell does nothing)
+    kind, val = _bf(m, table)
+    rng = np.random.default_rng(11)
+    rAUf = 1e-3*(1.0 + 0.3*rng.random(m.nFaces))
+    phi = 1e-6*rng.standard_normal(m.nFaces)
+    pt = {p["name"]: "tractionDisplacement" for p in m.patches}          # the mesh handle's D patch table only tells `empty`
+    inp = dict(sign=-1, bfKind=kind, bfValue=val, gammaFaces=rAUf, phi=phi)
+    gm = pkg.GpuMesh(m, g, pt, device=0)
+    a = gm.assemble_scalar(**inp)
+    r = oracle.assemble_scalar(m, g, pt, **inp)
+    for k in ("upper", "diag", "source", "internalCoeffs", "boundaryCoeffs"):
+        assert np.array_equal(a[k], r[k]), k
+    fc = m.owner[m.nInternalFaces:]
+    diag = a["diag"].copy(); b = a["source"].copy()
+    np.add.at(diag, fc, a["internalCoeffs"]); np.add.at(b, fc, a["boundaryCoeffs"])
+    l, u = m.lower_upper()
+    gs = pkg.GpuPCG(l, u, m.nCells, device=0)
+    gs.set_matrix(diag, a["upper"])
+    xg, xc = np.zeros(m.nCells), np.zeros(m.nCells)
+    pg, hg = gs.solve(xg, b, tolerance=tol, relTol=relTol)
+    pc, hc = oracle.pcg_solve(l, u, diag, a["upper"], xc, b, tolerance=tol, relTol=relTol)
+    assert pg["nIterations"] == pc["nIterations"] and pg["nIterations"] > 10 and pg["converged"]
+    assert np.max(np.abs(hg - hc)/np.abs(hc)) < 1e-10 + 1e-13*np.abs(hc).max()/np.abs(hc).min()
+    assert np.abs(xg - xc).max() <= 1e-9*np.abs(xc).max()
+    gm.close(); gs.close()
