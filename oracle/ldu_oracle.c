@@ -12,7 +12,9 @@
  * --impl reference legs may load this library.  The product (libgpupcg_cuda.so)
  * never links or calls it.
  *
- * PARITY UNPINNED.  None of this arithmetic is under /root/reference: it lives
+ * PARITY AGAINST foam-extend's BITS UNPINNED.  (What pins the restated path as an algorithm, from outside: the reference-held
+ * Kirsch solution on config 1, Lame's cylinder on the shipped tube mesh, free thermal expansion -- tests/test_plate_hole.py,
+ * tests/test_shipped_cases.py, tests/test_thermal_stress.py, oracle/ASSUMPTIONS.md.)  None of this arithmetic is under /root/reference: it lives
  * in foam-extend-3.1 (libfoam), which is neither vendored nor installed
  * (SURVEY.md section 8c).  The reference only *calls* it:
  *   src/fluidStructureInteraction/stressModels/unsTotalLagrangianStress/
