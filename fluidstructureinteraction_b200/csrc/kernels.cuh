@@ -138,7 +138,10 @@ struct SpinWatch
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         if (t0 == 0) { t0 = t; return false; }
-        if (t - t0 > g_spinTimeoutNs) { atomicCAS(&g_spinFault, 0u, (unsigned int)code); return true; }
+        // a peer rank may legitimately be late by what its HOST is late (plan build, set_matrix): six times the budget of a
+        // wait whose producer is a kernel already running on this device
+        const unsigned long long lim = (code == SPIN_P2P) ? 6ULL*g_spinTimeoutNs : g_spinTimeoutNs;
+        if (t - t0 > lim) { atomicCAS(&g_spinFault, 0u, (unsigned int)code); return true; }
         return false;
     }
     __device__ __forceinline__ void progress() { t0 = 0; }
