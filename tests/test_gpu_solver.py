@@ -189,11 +189,12 @@ def test_large_size_properties():
     g.close()
 
 
-@pytest.mark.parametrize("ordered,p2p", [(1, None), (1, "0"), (0, None)])
-def test_two_gpu_parity_against_oracle_on_same_partition(ordered, p2p):
+@pytest.mark.parametrize("ordered,p2p,mesh", [(1, None, "hex"), (1, "0", "hex"), (0, None, "hex"), (1, None, "tet"), (0, None, "tube")])
+def test_two_gpu_parity_against_oracle_on_same_partition(ordered, p2p, mesh):
     """Needs >= 2 GPUs (gpurun --gpus 2): halo swaps + cross-rank reductions vs oracle.pcg_solve_multi.  ordered = 1: global
     sums in the reference's order -> history and solution bit-identical (mailboxes, and NCCL's all-reduce with p2p = "0");
-    ordered = 0: the production tree reductions (bars in tools/multigpu_parity.py)."""
+    ordered = 0: the production tree reductions (bars in tools/multigpu_parity.py).  mesh: structured hex blocks (pencil
+    sweeps), or UNSTRUCTURED sub-domains -- a jittered tet box / the shipped 3dTube solid mesh cut by `method simple`."""
     import os
     import subprocess
     import sys
@@ -201,7 +202,7 @@ def test_two_gpu_parity_against_oracle_on_same_partition(ordered, p2p):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, ORDERED=str(ordered))
+    env = dict(os.environ, ORDERED=str(ordered), MESH=mesh)
     if p2p is not None:
         env["GPUPCG_P2P_REDUCE"] = p2p
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",

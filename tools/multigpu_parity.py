@@ -31,15 +31,48 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 nx, ny, nz = [int(v) for v in os.environ.get("CELLS", "40,12,16").split(",")]
 px, py, pz = decompose.proc_grid(world)
-s = cases.cantilever_subdomain(nx, ny, nz, px, py, pz, rank)
+MESH = os.environ.get("MESH", "hex")
+
+
+def unstructured_subdomains():
+    """MESH=tet: a jittered tet box; MESH=tube: the shipped 3dTube solid polyMesh (tests/golden) -- the global D-equation
+    matrix of the mesh cut by `method simple` (decompose.simple_decomp) into `world` UNSTRUCTURED sub-domains with
+    irregular processor patches (decompose.decompose_ldu): the tile kernels, not the structured-block pencils."""
+    from fluidstructureinteraction_b200 import geometry, meshes
+    if MESH == "tet":
+        m = meshes.tet_box(max(nx//3, 2), max(ny//2, 2), max(nz//2, 2), jitter=0.15)
+    else:
+        m = meshes.PolyMesh.load_npz(os.path.join(ROOT, "tests", "golden", "tube_solid.polymesh.npz"))
+    geo = geometry.compute(m)
+    l, u = m.lower_upper()
+    n, nIF = m.nCells, l.shape[0]
+    # laplacian(2mu+lambda, D)-like coefficients from the mesh's own geometry; a smooth source; diagonal shifted as a
+    # fixed-value patch would (keeps the system non-singular on any mesh)
+    upper = -(geo.magSf[:nIF]*geo.deltaCoeffs[:nIF])
+    diag = np.zeros(n); np.subtract.at(diag, l, upper); np.subtract.at(diag, u, upper)
+    diag *= 1.0 + 0.02*(1.0 + np.sin(0.013*np.arange(n)))
+    b = geo.V*np.cos(3.0*geo.C[:, 0]/max(np.abs(geo.C[:, 0]).max(), 1e-300) + 0.7*np.arange(n) % 5)
+    cp = decompose.simple_decomp(geo.C, (px, py, pz))
+    doms = decompose.decompose_ldu(l, u, diag, upper, b, np.zeros(n), cp, world)
+    return [dict(d, nCells=d["cells"].shape[0]) for d in doms]
+
+
+if MESH == "hex":
+    s = cases.cantilever_subdomain(nx, ny, nz, px, py, pz, rank)
+else:
+    _subs = unstructured_subdomains()
+    s = _subs[rank]
 g = pkg.GpuPCG(s["l"], s["u"], s["nCells"], s["patchFaceCells"], s["patchNbrDomain"], device=local)
 uid = [pkg.comm_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(uid, src=0)
 g.comm_init(rank, world, uid[0])
 g.set_matrix(s["diag"], s["upper"], patchBouCoeffs=s["patchBouCoeffs"])
-subs = [cases.cantilever_subdomain(nx, ny, nz, px, py, pz, r) for r in range(world)] if rank == 0 else None
+if MESH == "hex":
+    subs = [cases.cantilever_subdomain(nx, ny, nz, px, py, pz, r) for r in range(world)] if rank == 0 else None
+else:
+    subs = _subs if rank == 0 else None
 if rank == 0:
-    print("ranks", world, "cells", (nx, ny, nz), "decomposition", (px, py, pz), "ordered sums", ORDERED,
+    print("ranks", world, "mesh", MESH, "cells", (nx, ny, nz) if MESH == "hex" else [q["nCells"] for q in subs], "decomposition", (px, py, pz), "ordered sums", ORDERED,
           "GPUPCG_P2P_REDUCE", os.environ.get("GPUPCG_P2P_REDUCE", "(default)"), flush=True)
 
 
