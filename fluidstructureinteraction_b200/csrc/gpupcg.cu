@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace gpupcg;
@@ -110,6 +111,15 @@ struct gpupcg_handle_s
     DevState* hvRing = nullptr;     // pinned: 3 x NB states
     size_t smemFwdV = 0, smemBwdV = 0, smemFacV = 0, smemAmulV = 0;
     int amulGridV = 1;
+
+    // ---- concurrent component solves (gpupcg_vec.cuh, vec_solve_concurrent): the NB systems as NB scalar solves in flight
+    // at once, each on its own stream with its own vectors and state, sharing this handle's plan tables and upper().  A
+    // system is a handle of its own (isSys) that owns only what make_system allocates.
+    gpupcg_handle_s* sys[3] = {nullptr, nullptr, nullptr};
+    bool isSys = false;
+    cudaEvent_t evFork = nullptr;
+    int penSmemKB = 0, penCtasPerSM = 0;        // > 0: ring budget / CTAs per SM of the pencil sweeps of a system (NB systems'
+                                                // persistent CTAs must fit an SM together)
 };
 
 #define CK(call)                                                                                   \
@@ -200,6 +210,22 @@ extern "C" int gpupcg_destroy(gpupcg_handle h)
     if (!h) return GPUPCG_ERR_ARG;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto& c : h->sys) if (c) { gpupcg_destroy(c); c = nullptr; }
+    if (h->evFork) cudaEventDestroy(h->evFork);
+    if (h->isSys)       // a component system: the plan tables, upper() and the pencil coefficients belong to the parent
+    {
+        void* own[] = {h->dDiag, h->dRD, h->dX, h->dB, h->dRA, h->dWA, h->dPA, h->dY, h->dStageA, h->dStageB, h->dBou, h->dXNbr,
+                       h->dSend, h->dPartials, h->dHistory, h->dState, h->dTileTicket, h->dTabF, h->dTabB, h->dSmCounter};
+        for (void* p : own) if (p) cudaFree(p);
+        if (h->hState) cudaFreeHost(h->hState);
+        if (h->hStateRing) cudaFreeHost(h->hStateRing);
+        if (h->hHistory) cudaFreeHost(h->hHistory);
+        for (auto& e : h->evCheck) if (e) cudaEventDestroy(e);
+        for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+        if (h->ownStream) cudaStreamDestroy(h->ownStream);
+        delete h;
+        return GPUPCG_OK;
+    }
     h->comm.destroy();
     void* ptrs[] = {h->dSlices, h->dUfaceOld, h->dRowOld, h->dPos, h->dIfRow,
                     h->dIfRowStart, h->dIfEntry, h->dIfFaceRow, h->dIfMask, h->dDiag, h->dUval, h->dRD,
@@ -605,6 +631,80 @@ extern "C" int gpupcg_create(gpupcg_handle* out, int device, int nCells, int nFa
     return GPUPCG_OK;
 }
 
+// A component system of the concurrent vector solve: a handle that shares h's plan tables (read-only), upper() and the
+// pencil coefficient tables, and owns its stream, events, vectors, state and -- table variant -- the per-matrix coefficient
+// tables.  Single-rank handles only (no interfaces).
+static int make_system(gpupcg_handle h, gpupcg_handle& out, int nSystems)
+{
+    out = nullptr;
+    gpupcg_handle c = new gpupcg_handle_s();
+    struct Guard { gpupcg_handle c, p; ~Guard() { if (c) { p->err = "component system: " + c->err; gpupcg_destroy(c); } } } guard{c, h};
+    c->isSys = true;
+    c->device = h->device; c->numSMs = h->numSMs; c->nPatches = 0;
+    c->sweepGrid = h->sweepGrid; c->streamGrid = h->streamGrid;
+    {   // the sizes of the plan, none of its arrays
+        const HostPlan& P = h->plan; HostPlan& Q = c->plan;
+        Q.nCells = P.nCells; Q.nFaces = P.nFaces; Q.nRows = P.nRows; Q.nSlices = P.nSlices; Q.nLevels = P.nLevels;
+        Q.bricks = P.bricks; Q.pencil = P.pencil; Q.pLong = P.pLong; Q.pStride1 = P.pStride1;
+        Q.pW1 = P.pW1; Q.pW2 = P.pW2; Q.pN0 = P.pN0; Q.pSteps = P.pSteps;
+        Q.maxLevelRows = P.maxLevelRows; Q.entriesU = P.entriesU; Q.entriesL = P.entriesL;
+        Q.tileRowsMax = P.tileRowsMax; Q.nTiles = P.nTiles; Q.maxRounds = P.maxRounds;
+        Q.maxTileEntriesL = P.maxTileEntriesL; Q.maxTileEntriesU = P.maxTileEntriesU;
+        Q.maxTileExtF = P.maxTileExtF; Q.maxTileExtB = P.maxTileExtB; Q.maxRowL = P.maxRowL; Q.maxRowU = P.maxRowU;
+        Q.maxItems = P.maxItems; Q.nIfaceFaces = 0;
+    }
+    // shared, read-only
+    c->dSlices = h->dSlices; c->dUfaceOld = h->dUfaceOld; c->dRowOld = h->dRowOld; c->dPos = h->dPos; c->orderedSums = h->orderedSums;
+    c->dIfRow = h->dIfRow; c->dIfRowStart = h->dIfRowStart; c->dIfEntry = h->dIfEntry; c->dIfFaceRow = h->dIfFaceRow; c->dIfMask = h->dIfMask;
+    c->nIfRows = 0;
+    c->amulXStride = h->amulXStride; c->amulCStride = h->amulCStride; c->nAmulTiles = h->nAmulTiles; c->amulT = h->amulT;
+    c->amulEU = h->amulEU; c->amulEL = h->amulEL; c->amulGrid = h->amulGrid; c->smemAmul = h->smemAmul;
+    c->useTab = h->useTab; c->dTabCF = h->dTabCF; c->dTabCB = h->dTabCB; c->dTabIF = h->dTabIF; c->dTabIB = h->dTabIB;
+    c->smemFwdTab = h->smemFwdTab; c->smemBwdTab = h->smemBwdTab; c->smemFwd = h->smemFwd; c->smemBwd = h->smemBwd;
+    c->smemCap = h->smemCap; c->hasOvf = h->hasOvf; c->partStride = h->partStride; c->tiles = h->tiles;
+    c->pencil = h->pencil; c->dPenMeta = h->dPenMeta; c->dPenIdxF = h->dPenIdxF; c->dPenIdxB = h->dPenIdxB;
+    c->dPenCoefF = h->dPenCoefF; c->dPenCoefB = h->dPenCoefB; c->pen = h->pen;
+    c->dUval = h->dUval;
+    // the systems' persistent sweep CTAs must be resident together: nSystems rings per SM, one CTA per SM and system
+    c->penSmemKB = std::max(24, std::min(100, (int)(h->smemCap/1024)/std::max(1, nSystems) - 2));
+    c->penCtasPerSM = 1;
+    h = c;      // CK / LAUNCH below act on the system
+    CK(cudaStreamCreateWithFlags(&h->ownStream, cudaStreamNonBlocking));
+    h->stream = h->ownStream;
+    for (auto& e : h->ev) CK(cudaEventCreate(&e));
+    for (auto& e : h->evCheck) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    const HostPlan& P = h->plan;
+    const long long nR = P.nRows, nC = std::max(1, P.nCells);
+    CK(dalloc(h->dDiag, nR)); CK(dalloc(h->dRD, nR));
+    CK(dalloc(h->dX, nR));    CK(dalloc(h->dB, nR));  CK(dalloc(h->dRA, nR));
+    CK(dalloc(h->dWA, nR));   CK(dalloc(h->dPA, nR)); CK(dalloc(h->dY, nR));
+    CK(dalloc(h->dStageA, nC)); CK(dalloc(h->dStageB, nC));
+    CK(dalloc(h->dBou, 1)); CK(dalloc(h->dXNbr, 1)); CK(dalloc(h->dSend, 1));
+    CK(dalloc(h->dPartials, 4LL*h->partStride));
+    h->historyCap = 4096;
+    CK(dalloc(h->dHistory, h->historyCap));
+    CK(dalloc(h->dState, 1));
+    CK(cudaMallocHost((void**)&h->hState, sizeof(DevState)));
+    CK(cudaMallocHost((void**)&h->hStateRing, 2*sizeof(DevState)));
+    CK(cudaMallocHost((void**)&h->hHistory, sizeof(double)*h->historyCap));
+    memset(h->hState, 0, sizeof(DevState));
+    CK(cudaMemsetAsync(h->dState, 0, sizeof(DevState), h->stream));
+    CK(cudaMemsetAsync(h->dXNbr, 0, sizeof(double), h->stream));
+    CK(dalloc(h->dTileTicket, 1));
+    CK(cudaMemsetAsync(h->dTileTicket, 0, sizeof(unsigned long long), h->stream));
+    if (h->pencil)
+    {
+        CK(dalloc(h->dSmCounter, 1024));
+        CK(cudaMemsetAsync(h->dSmCounter, 0, sizeof(unsigned int)*1024, h->stream));
+        h->pen.smCounter = h->pen.smCounter ? h->dSmCounter : nullptr;
+    }
+    else if (h->useTab) { CK(dalloc(h->dTabF, 4LL*std::max(1, P.nRows))); CK(dalloc(h->dTabB, 4LL*std::max(1, P.nRows))); }
+    CK(cudaStreamSynchronize(h->stream));
+    guard.c = nullptr;
+    out = c;
+    return GPUPCG_OK;
+}
+
 static void fill_info(const HostPlan& P, gpupcg_plan_info* info)
 {
     memset(info, 0, sizeof(*info));
@@ -680,6 +780,7 @@ extern "C" int gpupcg_launch_count(gpupcg_handle h, long long* count)
 {
     if (!h || !count) return GPUPCG_ERR_ARG;
     *count = h->launches;
+    for (auto c : h->sys) if (c) *count += c->launches;
     return GPUPCG_OK;
 }
 
@@ -895,7 +996,7 @@ static int launch_pencil(gpupcg_handle h, const double* diagOrRD, const double* 
     A.fxX = nullptr; A.fxPA = nullptr; A.fxWA = nullptr; A.fxRA = nullptr; A.fxHistory = nullptr; A.fxHistStride = 0;
     if (fuse) { A.fxX = fx->x; A.fxPA = fx->pA; A.fxWA = fx->wA; A.fxRA = fx->rA; A.fxHistory = fx->history; A.fxHistStride = histStride; }
     // ring stages: as many as fit the budget (default ~100 KB: two CTAs per SM), 2 ... 8
-    const size_t cap = std::min<size_t>(h->smemCap, (size_t)env_int("GPUPCG_PENCIL_SMEM_KB", 100)*1024);
+    const size_t cap = std::min<size_t>(h->smemCap, (size_t)(h->penSmemKB > 0 ? h->penSmemKB : env_int("GPUPCG_PENCIL_SMEM_KB", 100))*1024);
     int nst = std::max(2, std::min(8, env_int("GPUPCG_PENCIL_STAGES", 8)));
     while (nst > 2 && pen_smem_bytes<NB, MODE>(nst, A.w1, A.w2, withDot, fuse) > cap) nst--;
     A.nStages = nst;
@@ -913,7 +1014,8 @@ static int launch_pencil(gpupcg_handle h, const double* diagOrRD, const double* 
     // is issue-bound: beyond one per scheduler they slow each other down and, a pencil being paced by the slowest pencil
     // upstream, the whole wavefront with them -- so by default no more CTAs per SM than keep the sweep warps <= 4.
     int occ = 0, grid = 1;
-    const int perSmWanted = std::max(1, env_int("GPUPCG_PENCIL_CTAS_PER_SM", split ? std::max(1, 4/NB) : 2));
+    const int perSmWanted = h->penCtasPerSM > 0 ? h->penCtasPerSM
+                          : std::max(1, env_int("GPUPCG_PENCIL_CTAS_PER_SM", split ? std::max(1, 4/NB) : 2));
 #define PEN_THREADS(SW_, FUSE_) ((SW_ + 1 + PEN_FW + ((FUSE_) ? 1 : 0))*32)
 #define PEN_RUN(LONG_, SW_, FUSE_) do { \
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (k_dic_pencil<NB, MODE, LONG_, SW_, FUSE_>), PEN_THREADS(SW_, FUSE_), smem)); \

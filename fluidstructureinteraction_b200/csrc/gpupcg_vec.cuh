@@ -91,6 +91,30 @@ inline bool vec_batched_now(gpupcg_handle h)
     return h->vAgreed == 1;
 }
 
+// Concurrent component solves.  The batched kernels advance the NB systems in lockstep on one stream: the latency-bound
+// sweeps (SMs mostly idle) and the bandwidth-bound Amul / update kernels alternate.  The systems are independent, so on
+// a single rank they can also run as NB scalar solves in flight at once -- one stream, one host thread and one set of
+// vectors per component, the plan tables and upper() shared -- and the GPU overlaps one system's sweeps with another's
+// streaming kernels (measured: 1 M cells 55.5 -> 47.6 ms per D-equation solve, 8 M 426 -> 388 ms, 250 k 20.1 -> 17.5 ms;
+// profiles/r2c_concurrent_components.md).  Every component is then exactly the scalar gpupcg_solve of that system.
+// GPUPCG_VECTOR_CONCURRENT=0/1 overrides the default (on for structured-block plans of >= 100 k cells).
+inline bool vec_concurrent_now(gpupcg_handle h)
+{
+    if (h->comm.active() || h->nPatches > 0 || h->plan.nIfaceFaces > 0 || h->plan.nTiles == 0 || h->isSys) return false;
+    const int env = env_int("GPUPCG_VECTOR_CONCURRENT", -1);
+    if (env >= 0) return env != 0 && (h->pencil || h->useTab);
+    return h->pencil && h->plan.nCells >= env_int("GPUPCG_VECTOR_CONCURRENT_MINCELLS", 100000);
+}
+
+template <int NB>
+int vec_ensure_systems(gpupcg_handle h)
+{
+    if (!h->evFork) CK(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
+    for (int k = 0; k < NB; k++)
+        if (!h->sys[k]) { int rc = make_system(h, h->sys[k], NB); if (rc) return rc; }
+    return GPUPCG_OK;
+}
+
 template <int NB>
 int vec_set_matrix_device(gpupcg_handle h, const double* d_diagC, const double* d_upper, const double* d_bouC)
 {
@@ -123,6 +147,20 @@ int vec_set_matrix_device(gpupcg_handle h, const double* d_diagC, const double* 
             LAUNCH((k_tab_coeffs<0>), gT, s, P.nRows, h->dTabIF, h->dUval, nullptr, h->dTabSq, h->dState, 0);
             LAUNCH(k_tab_raw, gT, s, P.nRows, h->dTabIF, h->dUval, h->dTabUF);
             LAUNCH(k_tab_raw, gT, s, P.nRows, h->dTabIB, h->dUval, h->dTabUB);
+        }
+    }
+    if (vec_concurrent_now(h))
+    {
+        // diag of every component into its system, on this stream (the systems' streams wait for evFork before a solve)
+        rc = vec_ensure_systems<NB>(h); if (rc) return rc;
+        if (h->pencil) { int rcp = pencil_coeffs(h); if (rcp) return rcp; }
+        for (int k = 0; k < NB; k++)
+        {
+            gpupcg_handle c = h->sys[k];
+            LAUNCH(k_cmpt_get, grid_for(P.nCells, h->streamGrid), s, h->vStageD, NB, k, c->dStageA, P.nCells);
+            LAUNCH(k_rows_in, grid_for(P.nRows, h->streamGrid), s, c->dStageA, c->dDiag, h->dRowOld, P.nRows, 1.0);
+            c->haveMatrix = true;
+            c->uvalVersion = h->uvalVersion; c->penCoefVersion = h->penCoefVersion;     // shares dUval and the pencil tables
         }
     }
     CK(cudaGetLastError());
@@ -420,6 +458,52 @@ int vec_solve_sequential(gpupcg_handle h, double* d_x, const double* d_b, double
     return GPUPCG_OK;
 }
 
+// NB scalar solves in flight at once (see vec_concurrent_now): system k on its own stream, driven by its own host thread
+// (solve_core's host loop blocks on its stream's convergence snapshots).
+template <int NB>
+int vec_solve_concurrent(gpupcg_handle h, double* d_x, const double* d_b, double tol, double relTol, int minIter,
+                         int maxIter, gpupcg_perf* perf, double* history, int historyCap)
+{
+    const HostPlan& P = h->plan;
+    for (int k = 0; k < NB; k++)
+        if (!h->sys[k] || !h->sys[k]->haveMatrix) { h->err = "gpupcg_solve_vector: component systems have no matrix"; return GPUPCG_ERR_STATE; }
+    CK(cudaEventRecord(h->evFork, h->stream));      // d_x, d_b and the matrix are ready on the caller's stream
+    int rcs[NB];
+    gpupcg_perf ps[NB];
+    gpupcg_handle parent = h;
+    auto run = [&, parent](int k)
+    {
+        gpupcg_handle h = parent->sys[k];       // CK / LAUNCH act on the system from here on
+        rcs[k] = [&]() -> int
+        {
+            CK(cudaSetDevice(h->device));
+            cudaStream_t s = h->stream;
+            CK(cudaStreamWaitEvent(s, parent->evFork, 0));
+            const int gC = grid_for(P.nCells, h->streamGrid);
+            LAUNCH(k_cmpt_get, gC, s, d_x, NB, k, h->dStageA, P.nCells);
+            LAUNCH(k_cmpt_get, gC, s, d_b, NB, k, h->dStageB, P.nCells);
+            CK(cudaGetLastError());
+            int rc = gpupcg_solve_device(h, h->dStageA, h->dStageB, tol, relTol, minIter, maxIter, &ps[k],
+                                         history ? history + (size_t)k*historyCap : nullptr, historyCap);
+            if (rc) return rc;
+            LAUNCH(k_cmpt_put, gC, s, h->dStageA, NB, k, d_x, P.nCells);
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(s));
+            return GPUPCG_OK;
+        }();
+    };
+    std::thread th[NB];
+    for (int k = 1; k < NB; k++) th[k] = std::thread(run, k);
+    run(0);
+    for (int k = 1; k < NB; k++) th[k].join();
+    for (int k = 0; k < NB; k++)
+    {
+        if (rcs[k]) { h->err = "component " + std::to_string(k) + ": " + h->sys[k]->err; return rcs[k]; }
+        if (perf) perf[k] = ps[k];
+    }
+    return GPUPCG_OK;
+}
+
 template <int NB>
 int vec_solve_device(gpupcg_handle h, double* d_x, const double* d_b, double tol, double relTol, int minIter, int maxIter,
                      gpupcg_perf* perf, double* history, int historyCap)
@@ -432,6 +516,7 @@ int vec_solve_device(gpupcg_handle h, double* d_x, const double* d_b, double tol
         return GPUPCG_ERR_STATE;
     }
     if (perf) memset(perf, 0, sizeof(*perf)*NB);
+    if (vec_concurrent_now(h) && h->sys[0]) return vec_solve_concurrent<NB>(h, d_x, d_b, tol, relTol, minIter, maxIter, perf, history, historyCap);
     if (!vec_batched_now(h)) return vec_solve_sequential<NB>(h, d_x, d_b, tol, relTol, minIter, maxIter, perf, history, historyCap);
     cudaStream_t s = h->stream;
     const long long nFlat = (long long)P.nRows*VecStride<NB>::v;

@@ -336,3 +336,49 @@ def test_spin_watchdog_returns_an_error_instead_of_hanging(kind, monkeypatch):
     pc, _ = oracle.pcg_solve(l, u, diag, upper, xc, b, tolerance=1e-9, relTol=0.01)
     assert pg["nIterations"] == pc["nIterations"] and np.max(np.abs(x - xc)) <= 1e-9*np.max(np.abs(xc))
     g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,ordered", [("hex", 0), ("hex", 1), ("tet", 0), ("tet", 1)])
+def test_concurrent_component_solves(kind, ordered, monkeypatch):
+    """GPUPCG_VECTOR_CONCURRENT=1: the three systems of a vector solve as three scalar solves in flight at once (own stream,
+    host thread and vectors per component; plan tables and upper() shared -- csrc/gpupcg_vec.cuh vec_solve_concurrent).
+    Each component must be the scalar solve of that system: same iteration counts and history as gpupcg_solve on a separate
+    handle; with ordered sums bit-identical to the oracle.  Default-on only for structured plans >= 100 k cells, forced here
+    (pencil sweeps on the hex block, tile sweeps on the tets)."""
+    monkeypatch.setenv("GPUPCG_VECTOR_CONCURRENT", "1")
+    if ordered:
+        monkeypatch.setenv("GPUPCG_ORDERED_SUMS", "1")
+    if kind == "hex":
+        s = cases.cantilever_system(40, 12, 16)
+        l, u, diag, upper, b, n = s["l"], s["u"], s["diag"], s["upper"], s["b"], s["nCells"]
+    else:
+        from fluidstructureinteraction_b200 import meshes
+        m = meshes.tet_box(8, 5, 6, jitter=0.15)
+        l, u = m.lower_upper(); n = m.nCells
+        diag, upper, b, _ = synthetic_matrix(l, u, n, 77)
+    dC = np.ascontiguousarray(np.stack([diag, diag*1.25, diag*1.5], axis=1))
+    bC = np.ascontiguousarray(np.stack([b, -0.5*b, np.cos(0.11*np.arange(n))*np.abs(b).max()], axis=1))
+    g = pkg.GpuPCG(l, u, n, device=0)
+    for rep in range(2):                                   # second pass: new diagonal, upper() re-used (upper = None)
+        if rep:
+            dC = np.ascontiguousarray(dC*np.array([1.0, 1.1, 0.9]))
+        g.set_matrix_vector(dC, upper if rep == 0 else None)
+        xv = np.zeros((n, 3))
+        pv, hv = g.solve_vector(xv, bC, tolerance=1e-9, relTol=0.0)
+        g1 = pkg.GpuPCG(l, u, n, device=0)
+        for k in range(3):
+            dk, bk = np.ascontiguousarray(dC[:, k]), np.ascontiguousarray(bC[:, k])
+            g1.set_matrix(dk, upper)
+            xk = np.zeros(n)
+            pk, hk = g1.solve(xk, bk, tolerance=1e-9, relTol=0.0)
+            assert pv[k]["nIterations"] == pk["nIterations"] > 5
+            assert np.allclose(hv[k], hk, rtol=1e-10, atol=0.0) and np.abs(xv[:, k] - xk).max() <= 1e-11*np.abs(xk).max()
+            if ordered:
+                xo = np.zeros(n)
+                po, ho = oracle.pcg_solve(l, u, dk, upper, xo, bk, tolerance=1e-9, relTol=0.0)
+                assert po["nIterations"] == pv[k]["nIterations"]
+                assert np.array_equal(hv[k], ho) and np.array_equal(xv[:, k], xo), k
+        g1.close()
+    assert g.launch_count() > 0
+    g.close()
