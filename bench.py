@@ -342,7 +342,7 @@ def measure_8m(peak):
         out[k] = kernel_entry(g.time_kernel(k, reps=10, flushL2=True), 1, kb1[k], peak)
     # the batched kernels (what a D-equation solve runs): one launch advances the three component systems
     g.set_matrix_vector(np.ascontiguousarray(np.stack([s["diag"]]*3, axis=1)), s["upper"])
-    if g.vector_mode(3) == 1:
+    if g.vector_mode(3) in (1, 2):          # 2: the step runs concurrent scalar solves; the batched kernels are timed all the same
         xv = np.zeros((n, 3))
         g.solve_vector(xv, np.ascontiguousarray(np.stack([s["b"]*t for t in TRACTION], axis=1)), 1e-9, 0.01, 0, 4, history=False)
         for k in ("amul", "dic", "p_update", "xr_update"):
@@ -445,6 +445,23 @@ def run_ours(args, nx, ny, nz):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_dev = float(ms.item())
 
+    # ---- A/B inside the same run: the component-batched kernels on one stream (what round 1 / 2a measured) -----------
+    batched_ab = None
+    if vector and vmode == 2:
+        os.environ["GPUPCG_VECTOR_CONCURRENT"] = "0"
+        step_device()
+        barrier()
+        e0.record()
+        itb = 0
+        for _ in range(args.steps):
+            itb += step_device()
+        e1.record()
+        barrier()
+        del os.environ["GPUPCG_VECTOR_CONCURRENT"]
+        msb = float(e0.elapsed_time(e1))
+        batched_ab = {"path": "GPUPCG_VECTOR_CONCURRENT=0: three systems per launch, one stream", "ms_per_step": msb/args.steps,
+                      "value": nGlobal*itb/(msb*1e-3), "unit": "cell-updates/s", "iterations_per_step": itb/args.steps}
+
     # ---- end-to-end arm: host buffers through gpupcg_set_matrix + gpupcg_solve ------------------------------------
     def pinned(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -526,8 +543,15 @@ def run_ours(args, nx, ny, nz):
         peak, peak_src = peaks()
         reps = 20
         batched = bool(vector and vmode == 1)
+        concurrent = bool(vector and vmode == 2)    # three scalar solves in flight at once: the step's kernels are the scalar ones
         nsys = 3 if batched else 1          # systems one launch advances
         kb = kernel_bytes(n, nF, nsys)
+        kern_batched = None
+        if concurrent:
+            # for comparison: the component-batched kernels (the other way to run the step: GPUPCG_VECTOR_CONCURRENT=0)
+            kb3 = kernel_bytes(n, nF, 3)
+            kern_batched = {k: kernel_entry(g.time_kernel_vector(3, k, reps=reps, flushL2=True), 3, kb3[k], peak)
+                            for k in ("amul", "dic", "p_update", "xr_update")}
         if vector and not batched:
             g.set_matrix(diag, upper, patchBouCoeffs=bou)
         kern = {}
@@ -569,6 +593,9 @@ def run_ours(args, nx, ny, nz):
             "config": {"workload": workload_name(nx, ny, nz, world), "cells": nGlobal, "internal_faces": int(nFglobal),
                        "tolerance": TOL, "relTol": RELTOL, "solver": "gpuPCG", "preconditioner": "DIC",
                        "component_solves": ("batched: gpupcg_solve_vector, 3 systems per launch" if batched else
+                                            "concurrent: gpupcg_solve_vector runs the 3 systems as 3 scalar solves in flight at once "
+                                            "(one stream per component; kernel times below are of one system's kernel alone, "
+                                            "share_of_iteration is of one system's serial chain)" if concurrent else
                                             "sequential: 3 x gpupcg_solve"),
                        "sweeps": "streaming pencils (kernels_pencil.cuh)" if pencil else "tiles (kernels.cuh / kernels_vec.cuh)",
                        "parallelism": "1 sub-domain/GPU x %d" % world,
@@ -584,9 +611,9 @@ def run_ours(args, nx, ny, nz):
                     "solves_per_s": 3*args.steps/(ms_e2e*1e-3),
                     "path": "gpupcg_set_matrix_vector + gpupcg_solve_vector (pinned host buffers)" if vector else
                             "3 x (gpupcg_set_matrix + gpupcg_solve)"},
-            "dropin_scalar_e2e": dropin,
+            "dropin_scalar_e2e": dropin, "batched_mode_same_run": batched_ab,
             "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": roof(dom_k), "roofline_amul": roof("amul"), "kernels": kern,
+            "roofline": roof(dom_k), "roofline_amul": roof("amul"), "kernels": kern, "kernels_batched_mode": kern_batched,
             "plan": {k: info[k] for k in ("nRows", "nLevels", "maxLevelRows", "sweepGrid", "streamGrid", "nTiles")},
         }
         if world == 1 and nGlobal <= 4000000:

@@ -314,7 +314,8 @@ class GpuPCG(object):
 
     # ---- component-batched solve (fvMatrix<vector>::solve's component loop in one launch sequence)
     def vector_mode(self, nCmpt=3):
-        """1: the batched kernels run; 0: the components are solved one after the other on the scalar kernels."""
+        """1: the batched kernels run; 0: the components are solved one after the other on the scalar kernels; 2: as
+        concurrent scalar solves (one stream per component inside the library)."""
         rc = self.lib.gpupcg_vector_mode(self.h, nCmpt)
         if rc < 0:
             self._check(rc)

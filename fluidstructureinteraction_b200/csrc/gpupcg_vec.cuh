@@ -97,13 +97,16 @@ inline bool vec_batched_now(gpupcg_handle h)
 // vectors per component, the plan tables and upper() shared -- and the GPU overlaps one system's sweeps with another's
 // streaming kernels (measured: 1 M cells 55.5 -> 47.6 ms per D-equation solve, 8 M 426 -> 388 ms, 250 k 20.1 -> 17.5 ms;
 // profiles/r2c_concurrent_components.md).  Every component is then exactly the scalar gpupcg_solve of that system.
-// GPUPCG_VECTOR_CONCURRENT=0/1 overrides the default (on for structured-block plans of >= 100 k cells).
+// GPUPCG_VECTOR_CONCURRENT=0/1 overrides the default (on for structured-block plans of 100 k ... 10 M cells).
 inline bool vec_concurrent_now(gpupcg_handle h)
 {
     if (h->comm.active() || h->nPatches > 0 || h->plan.nIfaceFaces > 0 || h->plan.nTiles == 0 || h->isSys) return false;
     const int env = env_int("GPUPCG_VECTOR_CONCURRENT", -1);
     if (env >= 0) return env != 0 && (h->pencil || h->useTab);
-    return h->pencil && h->plan.nCells >= env_int("GPUPCG_VECTOR_CONCURRENT_MINCELLS", 100000);
+    // above ~10 M cells the kernels are bandwidth-bound and the batched ones win (they read upper() and the tables once for
+    // three systems): 16 M cells 1032 (batched) vs 1107 ms, 64 M 6.8 vs 7.9 s
+    return h->pencil && h->plan.nCells >= env_int("GPUPCG_VECTOR_CONCURRENT_MINCELLS", 100000)
+                     && h->plan.nCells <= env_int("GPUPCG_VECTOR_CONCURRENT_MAXCELLS", 10000000);
 }
 
 template <int NB>
@@ -601,6 +604,7 @@ extern "C" int gpupcg_vector_mode(gpupcg_handle h, int nCmpt)
     CK(cudaSetDevice(h->device));
     int rc = VEC_DISPATCH(nCmpt, vec_prepare<2>(h), vec_prepare<3>(h));
     if (rc) return rc;
+    if (vec_concurrent_now(h)) return 2;
     return vec_batched_now(h) ? 1 : 0;
 }
 

@@ -172,6 +172,10 @@ int gpupcg_time_kernel(gpupcg_handle h, int which, int reps, int flushL2, double
  *   perfCmpt            : [nCmpt];  history: [nCmpt*historyCap] (component-major) or NULL
  * Meshes with more than four faces per row and side (polyhedra) and multi-rank runs without peer-memory mailboxes
  * run the components one after the other on the scalar kernels (gpupcg_vector_mode returns 0 then, 1 when batched).
+ * Single-rank structured-block plans of 100 k ... 10 M cells run the components as nCmpt scalar solves IN FLIGHT AT ONCE
+ * (one stream, host thread and set of vectors per component inside the library; plan tables and upper() shared; every
+ * component is then exactly gpupcg_solve of that system) -- gpupcg_vector_mode returns 2; GPUPCG_VECTOR_CONCURRENT=0/1
+ * overrides the choice.
  * Multi-rank: the ranks agree on the path with one all-reduce the first time it is needed, so gpupcg_vector_mode and
  * the first gpupcg_solve_vector after gpupcg_comm_init are collective calls.                                        */
 int gpupcg_vector_mode(gpupcg_handle h, int nCmpt);

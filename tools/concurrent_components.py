@@ -12,6 +12,9 @@ sys.path.insert(0, ROOT)
 import fluidstructureinteraction_b200 as pkg
 from fluidstructureinteraction_b200 import cases
 
+LIB_ONLY = "--lib-only" in sys.argv          # only the in-library A/B (one handle): large meshes
+if LIB_ONLY:
+    sys.argv.remove("--lib-only")
 nx, ny, nz = [int(v) for v in sys.argv[1:4]] if len(sys.argv) >= 4 else (200, 50, 100)
 TOL, RELTOL = 1e-9, 0.01
 TR = (0.3, -0.2, 1.0)
@@ -51,6 +54,8 @@ print("library concurrent (gpupcg_solve_vector_device, GPUPCG_VECTOR_CONCURRENT=
 xl = d_xv.cpu().numpy()
 print("library concurrent vs batched, max rel diff:", float(np.abs(xl - xb).max()/np.abs(xb).max()), flush=True)
 os.environ["GPUPCG_VECTOR_CONCURRENT"] = "0"
+if LIB_ONLY:
+    sys.exit(0)
 
 # three handles
 hs = []
