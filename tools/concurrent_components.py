@@ -15,10 +15,19 @@ from fluidstructureinteraction_b200 import cases
 LIB_ONLY = "--lib-only" in sys.argv          # only the in-library A/B (one handle): large meshes
 if LIB_ONLY:
     sys.argv.remove("--lib-only")
-nx, ny, nz = [int(v) for v in sys.argv[1:4]] if len(sys.argv) >= 4 else (200, 50, 100)
-TOL, RELTOL = 1e-9, 0.01
+nx, ny, nz = [int(v) for v in sys.argv[1:4]] if len(sys.argv) >= 4 and sys.argv[1].isdigit() else (200, 50, 100)
+TOL, RELTOL = 1e-9, float(os.environ.get("RELTOL", "0.01"))
 TR = (0.3, -0.2, 1.0)
-s = cases.cantilever_system(nx, ny, nz)
+if "--tet" in sys.argv:                     # unstructured: jittered tet box (6 tets per hex), tile sweeps instead of pencils
+    from fluidstructureinteraction_b200 import meshes
+    m = meshes.tet_box(nx, ny, nz, jitter=0.15)
+    l, u = m.lower_upper()
+    up = -(1.0 + 0.3*np.sin(0.1*np.arange(l.shape[0])))
+    dg = np.zeros(m.nCells); np.subtract.at(dg, l, up); np.subtract.at(dg, u, up)
+    s = dict(l=l, u=u, nCells=m.nCells, upper=up, diag=dg*1.000001, b=np.cos(0.01*np.arange(m.nCells)))
+    print("tet box:", m.nCells, "cells", l.shape[0], "internal faces", flush=True)
+else:
+    s = cases.cantilever_system(nx, ny, nz)
 n = s["nCells"]
 torch.cuda.set_device(0)
 bs = [torch.from_numpy(s["b"]*t).cuda() for t in TR]
