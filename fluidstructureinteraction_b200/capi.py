@@ -43,7 +43,9 @@ class Perf(C.Structure):
 class EqnControls(C.Structure):
     """gpupcg_eqn_controls"""
     _fields_ = [("d2dt2Scheme", C.c_int), ("ddtScheme", C.c_int), ("deltaT", C.c_double), ("deltaT0", C.c_double),
-                ("K", C.c_double), ("nonLinear", C.c_int), ("thermal", C.c_int), ("limitCoeff", C.c_double)]
+                ("K", C.c_double), ("nonLinear", C.c_int), ("thermal", C.c_int), ("limitCoeff", C.c_double),
+                ("eD2", C.c_double), ("eDdtD", C.c_double), ("eDdtD0", C.c_double), ("eDdtD00", C.c_double),
+                ("eDamp", C.c_double), ("eU", C.c_double)]
 
 
 class EvolveControls(C.Structure):
@@ -65,13 +67,18 @@ class EvolveResult(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-SCHEMES = {"steadyState": 0, "Euler": 1}
+SCHEMES = {"steadyState": 0, "Euler": 1, "backward": 2}
 
 
 def eqn_controls(d2dt2="steadyState", ddt="steadyState", deltaT=1.0, deltaT0=None, K=0.0, nonLinear=False, thermal=False,
-                 limitCoeff=1.0):
-    return EqnControls(SCHEMES[d2dt2], SCHEMES[ddt], float(deltaT), float(deltaT if deltaT0 is None else deltaT0), float(K),
-                       int(bool(nonLinear)), int(bool(thermal)), float(limitCoeff))
+                 limitCoeff=1.0, backward=None):
+    """backward: dict(eD2, eDdtD, eDdtD0, eDdtD00, eDamp, eU) -- the effective old time step of every use of a `backward`
+    scheme (include/gpupcg.h: gpupcg_eqn_controls; timelevels.OldTimes works them out)."""
+    c = EqnControls(SCHEMES[d2dt2], SCHEMES[ddt], float(deltaT), float(deltaT if deltaT0 is None else deltaT0), float(K),
+                    int(bool(nonLinear)), int(bool(thermal)), float(limitCoeff))
+    for k, v in (backward or {}).items():
+        setattr(c, k, float(v))
+    return c
 
 
 class PlanInfo(C.Structure):
@@ -145,6 +152,7 @@ SYMBOLS = {
     "gpupcg_gradients_resident": (C.c_int, [C.c_void_p, C.c_double]),
     "gpupcg_sigma_resident": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gpupcg_mesh_new_time_step": (C.c_int, [C.c_void_p]),
+    "gpupcg_mesh_copy_field": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "gpupcg_evolve_D": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_double_p, c_int_p, C.c_int]),
     "gpupcg_host_register": (C.c_int, [C.c_void_p, C.c_ulonglong]),
     "gpupcg_host_unregister": (C.c_int, [C.c_void_p]),
@@ -405,10 +413,11 @@ PATCH_TYPES = {"tractionDisplacement": 0, "fixedDisplacement": 1, "symmetryDispl
 
 FIELD_IDS = dict(mu=0, lambda_=1, rho=2, D=3, Dold=4, Doldold=5, gradD=6, gradDf=7, traction=8, pressure=9, fixedValue=10,
                  threeK=11, alpha=12, DT=13, DTb=14, pointD=15, Db=16, gradDb=17, U=18, epsilon=19, sigma=20, upper=21,
-                 diag=22, source=23, internalCoeffs=24, boundaryCoeffs=25, patchGradient=26, Dprev=27, DbPrev=28)
+                 diag=22, source=23, internalCoeffs=24, boundaryCoeffs=25, patchGradient=26, Dprev=27, DbPrev=28, Dooo=29,
+                 Doooo=30)
 _FIELD_COLS = dict(mu=1, lambda_=1, rho=1, D=3, Dold=3, Doldold=3, gradD=9, gradDf=9, traction=3, pressure=1, fixedValue=3,
                    threeK=1, alpha=1, DT=1, DTb=1, pointD=3, Db=3, gradDb=9, U=3, epsilon=6, sigma=6, upper=1, diag=1,
-                   source=3, internalCoeffs=3, boundaryCoeffs=3, patchGradient=3, Dprev=3, DbPrev=3)
+                   source=3, internalCoeffs=3, boundaryCoeffs=3, patchGradient=3, Dprev=3, DbPrev=3, Dooo=3, Doooo=3)
 
 
 class GpuMesh(object):
@@ -584,6 +593,10 @@ class GpuMesh(object):
 
     def new_time_step(self):
         self._check(self.lib.gpupcg_mesh_new_time_step(self.h))
+
+    def copy_field(self, dst, src):
+        """dst = src on the device (names of FIELD_IDS)."""
+        self._check(self.lib.gpupcg_mesh_copy_field(self.h, FIELD_IDS[dst], FIELD_IDS[src]))
 
     def sigma(self, mu, lam, gradD):
         """gradD = None: the device's grad(D)."""

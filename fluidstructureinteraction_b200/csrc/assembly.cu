@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(ATPB, ASM_CELLS_MINB) k_asm_cells(MeshDev M, A
                                                     const double* __restrict__ Lup, const double* __restrict__ upperSingle,
                                                     const double* __restrict__ fluxE,
                                                     const double* __restrict__ fluxC, double* __restrict__ diag,
-                                                    double* __restrict__ source)
+                                                    double* __restrict__ source, const double* __restrict__ timeA = nullptr)
 {
     for (int c = K.c0 + blockIdx.x*ATPB + threadIdx.x; c < K.c1; c += gridDim.x*ATPB)
     {
@@ -276,6 +276,12 @@ __global__ void __launch_bounds__(ATPB, ASM_CELLS_MINB) k_asm_cells(MeshDev M, A
             for (int d = 0; d < 3; d++)
                 sA[d] = mul(mul(t1, sub(mul(cc, Dold[3*(size_t)c + d]), mul(T.coefft00, Doldold[3*(size_t)c + d]))), rh);
         }
+        else if (T.d2dt2 == 2)      // backward: evaluated per cell by k_time_backward (assembly_ext.cuh)
+        {
+            dA = timeA[4*(size_t)c];
+#pragma unroll
+            for (int d = 0; d < 3; d++) sA[d] = timeA[4*(size_t)c + 1 + d];
+        }
         double dg = sub(dA, Ld);
         const double gv[3] = {g0, g1, g2};
         double src[3];
@@ -296,6 +302,14 @@ __global__ void __launch_bounds__(ATPB, ASM_CELLS_MINB) k_asm_cells(MeshDev M, A
                 dg = add(dg, mul(mul(T.rDeltaT, V), sf));
 #pragma unroll
                 for (int d = 0; d < 3; d++) src[d] = add(src[d], mul(mul(mul(T.rDeltaT, Dold[3*(size_t)c + d]), V), sf));
+            }
+            else if (T.ddt == 2)    // [EXT] backwardDdtScheme::fvmDdt, then scaled by K*rho
+            {
+                dg = add(dg, mul(mul(mul(T.cbD, T.rDeltaT), V), sf));
+                const double rV = mul(T.rDeltaT, V);
+#pragma unroll
+                for (int d = 0; d < 3; d++)
+                    src[d] = add(src[d], mul(mul(rV, sub(mul(T.cb0D, Dold[3*(size_t)c + d]), mul(T.cb00D, Doldold[3*(size_t)c + d]))), sf));
             }
             else
             {
@@ -867,6 +881,7 @@ struct gpupcg_mesh_s
     double *dDprev = nullptr, *dDold = nullptr, *dRed = nullptr;
     // round 2: the remaining state of evolve() (allocated on first use)
     double *dDoldold = nullptr, *dThreeK = nullptr, *dAlpha = nullptr, *dDT = nullptr, *dDTb = nullptr;
+    double *dDooo = nullptr, *dDoooo = nullptr, *dTimeA = nullptr;      // `backward` d2dt2: 3rd / 4th old level, per-cell time terms
     double *dDb = nullptr, *dDbPrev = nullptr, *dU = nullptr;
     double *dFluxX = nullptr, *dFluxY = nullptr, *dFluxT = nullptr;
     bool haveDold = false, haveDoldold = false, haveThermal = false, haveDb = false;
@@ -1366,6 +1381,8 @@ FieldRef field_ref(gpupcg_mesh m, int id)
         case GPUPCG_F_PATCHGRADIENT: return {&m->dPatchGrad, 3*nBF, nullptr};
         case GPUPCG_F_DPREV: return {&m->dDprev, 3*nC, nullptr};
         case GPUPCG_F_DBPREV: return {&m->dDbPrev, 3*nBF, nullptr};
+        case GPUPCG_F_DOOO: return {&m->dDooo, 3*nC, nullptr};
+        case GPUPCG_F_DOOOO: return {&m->dDoooo, 3*nC, nullptr};
         default: return {nullptr, 0, nullptr};
     }
 }
@@ -1377,6 +1394,16 @@ int ensure(gpupcg_mesh m, double*& p, size_t n)
     MCK(alloc(m, p, n));
     MCK(cudaMemsetAsync(p, 0, sizeof(double)*std::max<size_t>(n, 1), m->stream));
     return GPUPCG_OK;
+}
+
+// host-side scalars of one use of a backward scheme, IEEE double, in the reference's order (backwardD2dt2Scheme.C:251-253)
+BwW backward_weights(double deltaT, double e)
+{
+    BwW w;
+    w.c = 1 + deltaT/(deltaT + e);
+    w.c00 = deltaT*deltaT/(e*(deltaT + e));
+    w.c0 = w.c + w.c00;
+    return w;
 }
 
 AsmCtl make_ctl(const gpupcg_eqn_controls* c)
@@ -1393,7 +1420,12 @@ AsmCtl make_ctl(const gpupcg_eqn_controls* c)
         const double s = c->deltaT + c->deltaT0;
         T.rDeltaT2 = 4.0/(s*s);
     }
-    if (T.ddt == 1) T.rDeltaT = 1.0/c->deltaT;
+    if (T.ddt == 1 || T.ddt == 2) T.rDeltaT = 1.0/c->deltaT;
+    if (T.ddt == 2)
+    {
+        const BwW w = backward_weights(c->deltaT, c->eDamp);
+        T.cbD = w.c; T.cb0D = w.c0; T.cb00D = w.c00;
+    }
     return T;
 }
 } // namespace
@@ -1561,13 +1593,31 @@ extern "C" int gpupcg_mesh_new_time_step(gpupcg_mesh m)
     return GPUPCG_OK;
 }
 
+extern "C" int gpupcg_mesh_copy_field(gpupcg_mesh m, int dstId, int srcId)
+{
+    if (!m) return GPUPCG_ERR_ARG;
+    MCK(cudaSetDevice(m->device));
+    FieldRef d = field_ref(m, dstId), r = field_ref(m, srcId);
+    if (!d.p || !r.p || d.n != r.n) { m->err = "gpupcg_mesh_copy_field: unknown field id or sizes differ"; return GPUPCG_ERR_ARG; }
+    if (!*r.p) { m->err = "gpupcg_mesh_copy_field: the source field is not on the device"; return GPUPCG_ERR_STATE; }
+    int rc = ensure(m, *d.p, d.n); if (rc) return rc;
+    MCK(cudaMemcpyAsync(*d.p, *r.p, sizeof(double)*d.n, cudaMemcpyDeviceToDevice, m->stream));
+    if (d.have) *d.have = true;
+    MCK(cudaStreamSynchronize(m->stream));
+    return GPUPCG_OK;
+}
+
 static int check_ctl(gpupcg_mesh m, const gpupcg_eqn_controls* c)
 {
     if (!c) return GPUPCG_OK;
-    if (c->d2dt2Scheme < 0 || c->d2dt2Scheme > 1 || c->ddtScheme < 0 || c->ddtScheme > 1)
-    { m->err = "unsupported d2dt2 / ddt scheme (0 steadyState, 1 Euler)"; return GPUPCG_ERR_UNSUPPORTED; }
-    if ((c->d2dt2Scheme == 1 || c->ddtScheme == 1) && !(c->deltaT > 0.0 && c->deltaT0 > 0.0))
-    { m->err = "Euler time scheme needs deltaT > 0 and deltaT0 > 0"; return GPUPCG_ERR_ARG; }
+    if (c->d2dt2Scheme < 0 || c->d2dt2Scheme > 2 || c->ddtScheme < 0 || c->ddtScheme > 2)
+    { m->err = "unsupported d2dt2 / ddt scheme (0 steadyState, 1 Euler, 2 backward)"; return GPUPCG_ERR_UNSUPPORTED; }
+    if ((c->d2dt2Scheme >= 1 || c->ddtScheme >= 1) && !(c->deltaT > 0.0 && c->deltaT0 > 0.0))
+    { m->err = "Euler / backward time schemes need deltaT > 0 and deltaT0 > 0"; return GPUPCG_ERR_ARG; }
+    if (c->d2dt2Scheme == 2 && !(c->eD2 > 0.0 && c->eDdtD > 0.0 && c->eDdtD0 > 0.0 && c->eDdtD00 > 0.0))
+    { m->err = "backward d2dt2 needs the effective old time steps eD2, eDdtD, eDdtD0, eDdtD00 (> 0; GREAT during start-up)"; return GPUPCG_ERR_ARG; }
+    if (c->ddtScheme == 2 && !(c->eU > 0.0) && !(c->eDamp > 0.0))
+    { m->err = "backward ddt needs the effective old time steps eU / eDamp (> 0; GREAT during start-up)"; return GPUPCG_ERR_ARG; }
     if (c->thermal && !m->haveThermal)
     { m->err = "thermal stress requested but threeK / alpha / DT / DTb have not been set (gpupcg_mesh_set_field)"; return GPUPCG_ERR_STATE; }
     return GPUPCG_OK;
@@ -1582,9 +1632,21 @@ static int assemble_resident(gpupcg_mesh m, const gpupcg_eqn_controls* c, const 
     if (!m->haveGradD || !m->haveGradDf) { m->err = "no grad(D) / gradDf on the device yet"; return GPUPCG_ERR_STATE; }
     const AsmCtl T = make_ctl(c);
     cudaStream_t s = m->stream;
-    if (T.d2dt2 == 1 || (T.damping && T.ddt == 1))
+    if (T.d2dt2 >= 1 || (T.damping && T.ddt >= 1))
     {
         rc = ensure(m, m->dDoldold, 3*(size_t)nC); if (rc) return rc;
+    }
+    if (T.d2dt2 == 2)
+    {
+        rc = ensure(m, m->dDooo, 3*(size_t)nC); if (rc) return rc;
+        rc = ensure(m, m->dDoooo, 3*(size_t)nC); if (rc) return rc;
+        rc = ensure(m, m->dTimeA, 4*(size_t)nC); if (rc) return rc;
+        BackwardCtl W;
+        W.rDt = 1.0/c->deltaT;
+        W.d2 = backward_weights(c->deltaT, c->eD2); W.ddtD = backward_weights(c->deltaT, c->eDdtD);
+        W.ddtD0 = backward_weights(c->deltaT, c->eDdtD0); W.ddtD00 = backward_weights(c->deltaT, c->eDdtD00);
+        W.sc = W.d2.c*W.rDt;
+        k_time_backward<<<agrid(m, nC), ATPB, 0, s>>>(nC, W, M.V, m->dRho, m->dDold, m->dDoldold, m->dDooo, m->dDoooo, m->dTimeA);
     }
     if (T.thermal) { rc = ensure(m, m->dAlpha, nC); if (rc) return rc; rc = ensure(m, m->dDT, nC); if (rc) return rc; rc = ensure(m, m->dDTb, nBF); if (rc) return rc; }
     const double limitCoeff = c ? c->limitCoeff : 1.0;
@@ -1594,7 +1656,7 @@ static int assemble_resident(gpupcg_mesh m, const gpupcg_eqn_controls* c, const 
     k_asm_faces<<<agrid(m, K.nOwn + K.nExtra), ATPB, 0, s>>>(M, K, m->dExtraFace, m->dMu, m->dLambda, m->dD, m->dGradD, m->dGradDf,
                                                              limitCoeff, m->dUpper, lup, m->dGms, fluxE, fluxC);
     k_asm_cells<<<agrid(m, nC), ATPB, 0, s>>>(M, K, T, m->dDold, m->dDoldold, m->dCellSlot, m->dRho, g[0], g[1], g[2], lup, m->dUpper,
-                                              fluxE, fluxC, m->dDiag, m->dSource);
+                                              fluxE, fluxC, m->dDiag, m->dSource, m->dTimeA);
     if (T.nonLinear || T.thermal)
     {
         if (T.nonLinear) { rc = ensure(m, m->dFluxX, 3*(size_t)nF); if (rc) return rc; rc = ensure(m, m->dFluxY, 3*(size_t)nF); if (rc) return rc; }
@@ -1706,6 +1768,14 @@ extern "C" int gpupcg_sigma_resident(gpupcg_mesh m, const gpupcg_eqn_controls* c
     cudaStream_t s = m->stream;
     rc = ensure(m, m->dU, 3*(size_t)nC); if (rc) return rc;
     // U_ = fvc::ddt(D_)   (:973)
+    if (T.ddt == 2)
+    {
+        if (!(c->eU > 0.0)) { m->err = "gpupcg_sigma_resident: backward ddt needs eU > 0"; return GPUPCG_ERR_ARG; }
+        rc = ensure(m, m->dDoldold, 3*(size_t)nC); if (rc) return rc;
+        k_ddt_backward<<<agrid(m, 3*(long long)nC), ATPB, 0, s>>>(3*(long long)nC, T.rDeltaT, backward_weights(c->deltaT, c->eU),
+                                                                 m->dD, m->dDold, m->dDoldold, m->dU);
+    }
+    else
     k_ddt<<<agrid(m, 3*(long long)nC), ATPB, 0, s>>>(3*(long long)nC, T.ddt, T.rDeltaT, m->dD, m->dDold, m->dU);
     // nonLinear here is the dictionary switch itself (:979), not `nonLinear && !enforceLinear`: the caller passes it in c->nonLinear
     k_sigma_ex<<<agrid(m, nC), ATPB, 0, s>>>(nC, T.nonLinear, T.thermal, m->dMu, m->dLambda, m->dGradD, m->dThreeK, m->dAlpha, m->dDT,

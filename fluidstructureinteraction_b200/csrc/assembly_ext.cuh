@@ -20,7 +20,46 @@ struct AsmCtl
     int nonLinear;      // nonLinear && !enforceLinear
     int thermal;
     double coefft, coefft00, rDeltaT2, rDeltaT, K;
+    double cbD, cb0D, cb00D;    // backward fvm::ddt(D) of the damping term: coefft, coefft0, coefft00 (effective deltaT0 = eDamp)
 };
+
+// weights of one use of a backward scheme [EXT backwardDdtScheme / backwardD2dt2Scheme.C:251-253]
+struct BwW { double c, c0, c00; };
+struct BackwardCtl { double rDt, sc; BwW d2, ddtD, ddtD0, ddtD00; };
+
+// rho*fvm::d2dt2(D), backward (backwardD2dt2Scheme.C:230-280 + [EXT] backwardDdtScheme::fvmDdt / fvcDdt): diag and source
+// of the term per cell -> timeA[4*c] = {diag, source x, y, z}; k_asm_cells picks them up.  Operand order as oracle/fvm_oracle.c.
+__global__ void __launch_bounds__(ATPB) k_time_backward(int nCells, BackwardCtl W, const double* __restrict__ V,
+                                                        const double* __restrict__ rho, const double* __restrict__ D0,
+                                                        const double* __restrict__ D00, const double* __restrict__ D000,
+                                                        const double* __restrict__ D0000, double* __restrict__ timeA)
+{
+    for (int c = blockIdx.x*ATPB + threadIdx.x; c < nCells; c += gridDim.x*ATPB)
+    {
+        const double v = V[c], rh = rho[c];
+        timeA[4*(size_t)c] = mul(mul(mul(mul(W.ddtD.c, W.rDt), v), W.sc), rh);
+        const double rV = mul(W.rDt, v);
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+        {
+            const double a0 = D0[3*(size_t)c + d], a00 = D00[3*(size_t)c + d], a000 = D000[3*(size_t)c + d], a0000 = D0000[3*(size_t)c + d];
+            const double s1 = mul(mul(rV, sub(mul(W.ddtD.c0, a0), mul(W.ddtD.c00, a00))), W.sc);
+            const double X = mul(W.rDt, add(sub(mul(W.ddtD0.c, a0), mul(W.ddtD0.c0, a00)), mul(W.ddtD0.c00, a000)));
+            const double Y = mul(W.rDt, add(sub(mul(W.ddtD00.c, a00), mul(W.ddtD00.c0, a000)), mul(W.ddtD00.c00, a0000)));
+            const double s2 = add(s1, mul(rV, sub(mul(W.d2.c0, X), mul(W.d2.c00, Y))));
+            timeA[4*(size_t)c + 1 + d] = mul(s2, rh);
+        }
+    }
+}
+
+// U = fvc::ddt(D), backward [EXT backwardDdtScheme::fvcDdt]
+__global__ void __launch_bounds__(ATPB) k_ddt_backward(long long n3, double rDt, BwW w, const double* __restrict__ D,
+                                                       const double* __restrict__ D0, const double* __restrict__ D00,
+                                                       double* __restrict__ U)
+{
+    for (long long i = (long long)blockIdx.x*ATPB + threadIdx.x; i < n3; i += (long long)gridDim.x*ATPB)
+        U[i] = mul(rDt, add(sub(mul(w.c, D[i]), mul(w.c0, D0[i])), mul(w.c00, D00[i])));
+}
 
 // (A & B)_ij = A_ik B_kj accumulated k = x, y, z
 __device__ __forceinline__ void TdotT(const double* A, const double* B, double* R)

@@ -496,9 +496,15 @@ int vec_solve_concurrent(gpupcg_handle h, double* d_x, const double* d_b, double
         }();
     };
     std::thread th[NB];
-    for (int k = 1; k < NB; k++) th[k] = std::thread(run, k);
+    bool started[NB] = {};
+    for (int k = 1; k < NB; k++)
+    {
+        try { th[k] = std::thread(run, k); started[k] = true; }
+        catch (const std::exception&) { started[k] = false; }      // no thread to be had: that system runs after the others, here
+    }
     run(0);
-    for (int k = 1; k < NB; k++) th[k].join();
+    for (int k = 1; k < NB; k++) if (!started[k]) run(k);
+    for (int k = 1; k < NB; k++) if (started[k]) th[k].join();
     for (int k = 0; k < NB; k++)
     {
         if (rcs[k]) { h->err = "component " + std::to_string(k) + ": " + h->sys[k]->err; return rcs[k]; }

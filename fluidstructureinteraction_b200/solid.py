@@ -4,7 +4,7 @@ volToPoint_ interpolation) lives on the GPU across outer iterations and time ste
 gpupcg_evolve_D.  Fields cross PCIe only when the caller asks for them (get)."""
 import numpy as np
 
-from . import capi, lsq as lsqmod
+from . import capi, lsq as lsqmod, timelevels
 
 
 class GpuSolidCase(object):
@@ -28,6 +28,7 @@ class GpuSolidCase(object):
         for name, n in (("D", (nC, 3)), ("Dold", (nC, 3)), ("Doldold", (nC, 3)), ("gradD", (nC, 9)), ("gradDf", (nF, 9)),
                         ("patchGradient", (nBF, 3))):
             gm.set_field(name, np.zeros(n))
+        self.old = None                 # timelevels.OldTimes once a `backward` scheme is used
         self.thermal = threeK is not None
         if self.thermal:
             gm.set_field("threeK", full(threeK, nC)); gm.set_field("alpha", full(alpha, nC))
@@ -46,15 +47,29 @@ class GpuSolidCase(object):
         return self.gm.get_field(name)
 
     def new_time_step(self):
-        self.gm.new_time_step()
+        if self.old is not None:        # `backward` schemes: the levels shift when GeometricField would shift them (evolve)
+            self.old.advance()
+        else:
+            self.gm.new_time_step()
 
     def evolve(self, nCorrectors, convergenceTolerance, relConvergenceTolerance=0.0, tolerance=1e-9, relTol=0.01,
                d2dt2="steadyState", ddt="steadyState", deltaT=1.0, deltaT0=None, K=0.0, nonLinear=False, thermal=False,
                limitCoeff=1.0, relaxD=None, maxIter=1000):
-        eqn = capi.eqn_controls(d2dt2, ddt, deltaT, deltaT0, K, nonLinear, thermal, limitCoeff)
+        bw = None
+        if "backward" in (d2dt2, ddt):
+            dT0 = deltaT if deltaT0 is None else deltaT0
+            if self.old is None:
+                self.old = timelevels.OldTimes(self.gm)
+            # the effective old time steps of this evolve(): those of its first assembly (they can differ from the later
+            # outer iterations' only in the very first evolve of a run, where every old level still equals the initial field)
+            bw = self.old.assembly(d2dt2, ddt, K > 1e-15, dT0)
+            bw["eU"] = dT0
+        eqn = capi.eqn_controls(d2dt2, ddt, deltaT, deltaT0, K, nonLinear, thermal, limitCoeff, bw)
         r = self.pcg.evolve_D(self.gm, nCorrectors, convergenceTolerance, relConvergenceTolerance, tolerance, relTol, 0, maxIter,
                               relaxD, self.validCmpts, self.g, eqn)
         # U, epsilon, sigma (:973-990): `nonLinear` here is the dictionary switch, whatever enforceLinear became
+        if ddt == "backward":
+            eqn.eU = self.old.velocity(deltaT if deltaT0 is None else deltaT0)
         self.gm.sigma_resident(eqn)
         return r
 

@@ -277,7 +277,14 @@ int gpupcg_gradients(gpupcg_mesh m, const double* D, const double* pointD, const
  * 2 symmetryDisplacement (fvPatchFields/ of the reference), 3 symmetryPlane [EXT symmetryFvPatchField], 4 empty (2-D).
  *
  * gpupcg_eqn_controls: what evolve() reads from fvSchemes / stressProperties for the equation itself
- *   d2dt2Scheme / ddtScheme  0 steadyState, 1 Euler  (d2dt2(D), ddt(D) of fvSchemes; deltaT0 = runTime.deltaT0())
+ *   d2dt2Scheme / ddtScheme  0 steadyState, 1 Euler, 2 backward  (d2dt2(D), ddt(D) of fvSchemes; deltaT0 = runTime.deltaT0())
+ *   eD2 ... eU               `backward` only (numerics/backwardD2dt2Scheme/backwardD2dt2Scheme.C:230-280 over [EXT]
+ *                            backwardDdtScheme): the EFFECTIVE old time step of every use -- the real deltaT0, or GREAT (1e15)
+ *                            while the field has too few distinct old-time levels (backwardD2dt2Scheme.C:58-76, [EXT]
+ *                            backwardDdtScheme::deltaT0_: vf.nOldTimes() < 2).  The caller owns D's time levels
+ *                            (GPUPCG_F_DOLD ... GPUPCG_F_DOOOO, gpupcg_mesh_copy_field) and knows their state:
+ *                            eD2 fvmD2dt2(D); eDdtD the fvmDdt(D) inside it; eDdtD0 / eDdtD00 the fvcDdt(D.oldTime()) /
+ *                            fvcDdt(D.oldTime().oldTime()) inside it; eDamp the damping term's fvm::ddt(D); eU U = fvc::ddt(D)
  *   K                        damping coefficient (stressProperties "K", :800-804), active when > SMALL (:862)
  *   nonLinear                stressProperties "nonLinear" (:796); thermal: stressModel::thermalStress() (:815)
  *   limitCoeff               snGrad scheme "skewCorrected <limitCoeff>" of fvSchemes                                      */
@@ -288,6 +295,7 @@ typedef struct gpupcg_eqn_controls
     double K;
     int    nonLinear, thermal;
     double limitCoeff;
+    double eD2, eDdtD, eDdtD0, eDdtD00, eDamp, eU;
 } gpupcg_eqn_controls;
 
 /* Field ids of gpupcg_mesh_set_field / gpupcg_mesh_get_field (host <-> resident device field, caller's numbering).
@@ -321,6 +329,8 @@ typedef struct gpupcg_eqn_controls
 #define GPUPCG_F_PATCHGRADIENT  26   /* gradient() of the tractionDisplacement patches [nBoundaryFaces*3] */
 #define GPUPCG_F_DPREV          27   /* D.prevIter()                                           */
 #define GPUPCG_F_DBPREV         28
+#define GPUPCG_F_DOOO           29   /* D.oldTime().oldTime().oldTime()   (`backward` d2dt2)   */
+#define GPUPCG_F_DOOOO          30   /* ... and its oldTime()                                  */
 int gpupcg_mesh_field_size(gpupcg_mesh m, int fieldId, long long* nDoubles);
 int gpupcg_mesh_set_field(gpupcg_mesh m, int fieldId, const double* host);
 int gpupcg_mesh_get_field(gpupcg_mesh m, int fieldId, double* host);
@@ -347,6 +357,9 @@ int gpupcg_mesh_set_point_constraints(gpupcg_mesh m, int nConstrained, const int
 /* D.correctBoundaryConditions(): evaluate() of every patch field on the resident D, grad(D), gradient() -> D.boundaryField()
  * (tractionDisplacementFvPatchVectorField.C:259-300, symmetryDisplacementFvPatchVectorField.C:169-207).                   */
 int gpupcg_patch_evaluate(gpupcg_mesh m);
+/* dst = src on the device (two field ids of the same size): how the caller creates and shifts D's old-time levels the way
+ * [EXT] GeometricField::oldTime() / storeOldTimes() do when a `backward` scheme needs more than two of them.            */
+int gpupcg_mesh_copy_field(gpupcg_mesh m, int dstId, int srcId);
 /* gpupcg_assemble_D / gpupcg_gradients / gpupcg_sigma on the resident fields, every branch of :846-890, :973-990
  * (gpupcg_sigma_resident: controls->nonLinear is the dictionary switch of :979, controls->ddtScheme gives U = fvc::ddt(D)). */
 int gpupcg_assemble_D_resident(gpupcg_mesh m, const gpupcg_eqn_controls* controls, const double* g);

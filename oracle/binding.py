@@ -279,14 +279,28 @@ def fgrad(mesh, geom, patchTypes, D, pointD, gradD, fixedValue, patchGradient, l
 # ---- round 2: transient / damping / non-linear / thermal branches, boundary evaluate, least-squares vol->point -------
 class Controls(C.Structure):
     _fields_ = [("d2dt2Scheme", C.c_int), ("ddtScheme", C.c_int), ("deltaT", C.c_double), ("deltaT0", C.c_double),
-                ("K", C.c_double), ("nonLinear", C.c_int), ("thermal", C.c_int), ("limitCoeff", C.c_double)]
+                ("K", C.c_double), ("nonLinear", C.c_int), ("thermal", C.c_int), ("limitCoeff", C.c_double),
+                ("eD2", C.c_double), ("eDdtD", C.c_double), ("eDdtD0", C.c_double), ("eDdtD00", C.c_double),
+                ("eDamp", C.c_double), ("Dooo", C.c_void_p), ("Doooo", C.c_void_p)]
+
+
+SCHEMES = {"steadyState": 0, "Euler": 1, "backward": 2}
 
 
 def controls(d2dt2="steadyState", ddt="steadyState", deltaT=1.0, deltaT0=None, K=0.0, nonLinear=False, thermal=False,
-             limitCoeff=1.0):
-    sch = {"steadyState": 0, "Euler": 1}
-    return Controls(sch[d2dt2], sch[ddt], float(deltaT), float(deltaT if deltaT0 is None else deltaT0), float(K),
-                    int(bool(nonLinear)), int(bool(thermal)), float(limitCoeff))
+             limitCoeff=1.0, backward=None):
+    """backward: dict(eD2, eDdtD, eDdtD0, eDdtD00, eDamp, Dooo, Doooo) when a scheme is `backward` (fvm_oracle.c: orc_controls)."""
+    ctl = Controls(SCHEMES[d2dt2], SCHEMES[ddt], float(deltaT), float(deltaT if deltaT0 is None else deltaT0), float(K),
+                   int(bool(nonLinear)), int(bool(thermal)), float(limitCoeff))
+    if backward is not None:
+        for k in ("eD2", "eDdtD", "eDdtD0", "eDdtD00", "eDamp"):
+            setattr(ctl, k, float(backward.get(k, 0.0)))
+        ctl._keep = [_f(backward["Dooo"]), _f(backward["Doooo"])] if backward.get("Dooo") is not None else []
+        if ctl._keep:
+            ctl.Dooo = ctl._keep[0].ctypes.data; ctl.Doooo = ctl._keep[1].ctypes.data
+    elif 2 in (ctl.d2dt2Scheme, ctl.ddtScheme):
+        raise ValueError("backward schemes need the effective old time steps and the old-time levels (backward=...)")
+    return ctl
 
 
 def _opt(a):
@@ -378,6 +392,16 @@ def ddt(D, Dold, scheme, deltaT):
     lib.orc_ddt.restype = None
     lib.orc_ddt.argtypes = [C.c_int, C.c_int, C.c_double, dp, dp, dp]
     lib.orc_ddt(D.shape[0], {"steadyState": 0, "Euler": 1}[scheme], float(deltaT), _dp(D), _dp(Dold), _dp(U))
+    return U
+
+
+def ddt_backward(D, Dold, Doldold, deltaT, e):
+    lib = load()
+    D, Dold, Doldold = _f(D), _f(Dold), _f(Doldold)
+    U = np.empty_like(D)
+    lib.orc_ddt_backward.restype = None
+    lib.orc_ddt_backward.argtypes = [C.c_int, C.c_double, C.c_double, dp, dp, dp, dp]
+    lib.orc_ddt_backward(D.shape[0], float(deltaT), float(e), _dp(D), _dp(Dold), _dp(Doldold), _dp(U))
     return U
 
 

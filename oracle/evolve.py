@@ -9,6 +9,71 @@ import numpy as np
 from . import binding as orc
 
 
+GREAT = 1.0e15
+
+
+class OldTimes:
+    """The old-time levels of D as [EXT] GeometricField keeps them -- oldTime() creates a level on first use (a copy of the
+    level above, carrying its timeIndex), storeOldTimes() shifts them on the first non-const access of a new time step
+    (deepest first; every level takes the values and the timeIndex of the one above), nOldTimes() counts them -- because the
+    `backward` schemes decide from exactly this state whether a use sees the real deltaT0 or GREAT (first-order start-up):
+      backwardD2dt2Scheme::deltaT0_(vf)   backwardD2dt2Scheme.C:58-76: GREAT while the 2nd and 3rd old level carry the same timeIndex
+      [EXT] backwardDdtScheme::deltaT0_(vf): GREAT while vf.nOldTimes() < 2
+    (oracle/ASSUMPTIONS.md #13: the order in which evolve() touches D and creates the levels)."""
+
+    def __init__(self):
+        self.lev = []           # [values, timeIndex] of D.oldTime(), D.oldTime().oldTime(), ...
+        self.ti = 0             # D.timeIndex()
+        self.now = 0            # time().timeIndex()
+
+    def advance(self):
+        self.now += 1
+
+    def touch(self, D):
+        """A non-const access of D (the fvMatrix constructor's psi.boundaryField().updateCoeffs()): storeOldTimes()."""
+        if self.lev and self.ti != self.now:
+            for j in range(len(self.lev) - 1, 0, -1):
+                self.lev[j] = [self.lev[j - 1][0], self.lev[j - 1][1]]
+            self.lev[0] = [D.copy(), self.ti]
+        self.ti = self.now
+
+    def ensure(self, k, D):
+        while len(self.lev) < k:
+            src, ti = (D, self.ti) if not self.lev else self.lev[-1]
+            self.lev.append([src.copy(), ti])
+
+    def n_old(self, j=0):
+        """nOldTimes() of the j-th old level (j = 0: D itself)."""
+        return max(len(self.lev) - j, 0)
+
+    def level(self, j, like):
+        return self.lev[j][0] if j < len(self.lev) else np.zeros_like(like)
+
+
+def backward_controls(old, D, d2dt2, ddt, damping, deltaT0):
+    """The effective old time step of every use of a `backward` scheme in one assembly of the D equation, in the order the
+    reference evaluates them (unsTotalLagrangianStress.C:846-865), creating the old levels the calls create."""
+    rule = lambda n: GREAT if n < 2 else deltaT0
+    e = dict(eD2=deltaT0, eDdtD=deltaT0, eDdtD0=deltaT0, eDdtD00=deltaT0, eDamp=deltaT0)
+    old.touch(D)
+    if d2dt2 == "backward":
+        old.ensure(3, D)                                        # deltaT0_(vf) looks at vf.oldTime().oldTime().oldTime()
+        e["eD2"] = GREAT if old.lev[1][1] == old.lev[2][1] else deltaT0
+        e["eDdtD"] = rule(old.n_old(0))                         # backwardDdtScheme.fvmDdt(vf)
+        e["eDdtD0"] = rule(old.n_old(1))                        # fvcDdt(vf.oldTime())
+        e["eDdtD00"] = rule(old.n_old(2))                       # fvcDdt(vf.oldTime().oldTime()), which then creates the 4th level
+        old.ensure(4, D)
+    elif d2dt2 == "Euler":
+        old.ensure(2, D)
+    if damping:
+        if ddt == "backward":
+            e["eDamp"] = rule(old.n_old(0))
+            old.ensure(2, D)
+        elif ddt == "Euler":
+            old.ensure(1, D)
+    return e
+
+
 def segregated_solve(l, u, diag, upper, source, patches, D, tolerance, relTol, maxIter=1000):
     """[EXT] fvMatrix<vector>::solve: patches = [(faceCells, internalCoeffs (n,3), boundaryCoeffs (n,3))].  D in place."""
     total = np.array(source, dtype=np.float64, copy=True)
@@ -126,6 +191,7 @@ class SolidCase(object):
         self.DT = np.zeros(nC); self.DTb = np.zeros(nBF)
         self.validCmpts = tuple(validCmpts)
         self.D = np.zeros((nC, 3)); self.Dold = np.zeros((nC, 3)); self.Doldold = np.zeros((nC, 3))
+        self.old = None             # OldTimes, once a `backward` scheme is used
         self.gradD = np.zeros((nC, 9)); self.gradDb = np.zeros((nBF, 9)); self.gradDf = np.zeros((nF, 9))
         self.pointD = np.zeros((mesh.nPoints, 3))
         self.U = np.zeros((nC, 3))
@@ -140,6 +206,19 @@ class SolidCase(object):
         """runTime++ : storeOldTimes of D."""
         self.Doldold = self.Dold
         self.Dold = self.D.copy()
+        if self.old is not None:
+            self.old.advance()
+
+    def _backward(self, d2dt2, ddt, damping, deltaT0):
+        """`backward` schemes: the levels live in self.old (created and shifted as GeometricField does); Dold / Doldold follow."""
+        if self.old is None:
+            self.old = OldTimes()
+            self.old.now = self.old.ti = 1          # the first time step of a run (startTime index 0, runTime++)
+        e = backward_controls(self.old, self.D, d2dt2, ddt, damping, deltaT0)
+        z = self.D
+        self.Dold, self.Doldold = self.old.level(0, z), self.old.level(1, z)
+        e["Dooo"], e["Doooo"] = self.old.level(2, z), self.old.level(3, z)
+        return e
 
     def evolve(self, nCorrectors, convergenceTolerance, relConvergenceTolerance=0.0, tolerance=1e-9, relTol=0.01,
                d2dt2="steadyState", ddt="steadyState", deltaT=1.0, deltaT0=None, K=0.0, nonLinear=False, thermal=False,
@@ -151,7 +230,11 @@ class SolidCase(object):
         hist, initialResidual, lastInit, totalIts, pcgIts = [], 0.0, 0.0, 0, []
         while True:
             Dprev = self.D.copy(); DbPrev = self.Db.copy()
-            ctl = orc.controls(d2dt2, ddt, deltaT, deltaT0, K, nonLinear and not self.enforceLinear, thermal, limitCoeff)
+            bw = None
+            if "backward" in (d2dt2, ddt):
+                bw = self._backward(d2dt2, ddt, K > 1e-15, deltaT if deltaT0 is None else deltaT0)
+                self.lastBackward = {k: v for k, v in bw.items() if k.startswith("e")}
+            ctl = orc.controls(d2dt2, ddt, deltaT, deltaT0, K, nonLinear and not self.enforceLinear, thermal, limitCoeff, bw)
             a = orc.assemble_D_ex(mesh, geom, pt, ctl, self.mu, self.lam, self.rho, self.g, self.D, self.Dold, self.Doldold,
                                   self.gradD, self.gradDf, self.traction, self.pressure, self.fixedValue, self.threeK,
                                   self.alpha, self.DT, self.DTb)
@@ -195,7 +278,17 @@ class SolidCase(object):
             iCorr += 1
             if not (iCorr < nCorrectors):
                 break
-        self.U = orc.ddt(self.D, self.Dold, ddt, deltaT)
+        if ddt == "backward":
+            # U = fvc::ddt(D): [EXT] backwardDdtScheme::fvcDdt with its own deltaT0_(D), then D.oldTime().oldTime() exists
+            if self.old is None:
+                self._backward(d2dt2, ddt, False, deltaT if deltaT0 is None else deltaT0)
+            self.old.ensure(1, self.D)              # residual() has used D.oldTime()
+            eU = GREAT if self.old.n_old(0) < 2 else (deltaT if deltaT0 is None else deltaT0)
+            self.old.ensure(2, self.D)
+            self.U = orc.ddt_backward(self.D, self.old.level(0, self.D), self.old.level(1, self.D), deltaT, eU)
+            self.lastBackward = dict(getattr(self, "lastBackward", {}), eU=eU)
+        else:
+            self.U = orc.ddt(self.D, self.Dold, ddt, deltaT)
         self.epsilon, self.sigma = orc.sigma_ex(self.mu, self.lam, self.gradD, nonLinear, thermal, self.threeK, self.alpha, self.DT)
         return dict(nOuterIterations=iCorr, initialResidual=initialResidual, lastSolverInitialResidual=lastInit, maxRes=maxRes,
                     res=res, totalPcgIterations=totalIts, pcgIterations=pcgIts, residualHistory=np.array(hist),

@@ -563,7 +563,28 @@ typedef struct orc_controls
     int nonLinear;          /* nonLinear && !enforceLinear                                               */
     int thermal;            /* thermalStress()                                                           */
     double limitCoeff;      /* snGrad scheme: skewCorrected <limitCoeff>                                 */
+    /* `backward` schemes (d2dt2Scheme / ddtScheme == 2; the shipped 3dTube and HronTurek solids):
+     *   d2dt2(D)  numerics/backwardD2dt2Scheme/backwardD2dt2Scheme.C:230-280 (fvmD2dt2(vf), then rho_* ... at
+     *             unsTotalLagrangianStress.C:848), built on [EXT] backwardDdtScheme::fvmDdt / fvcDdt
+     *   ddt(D)    [EXT] backwardDdtScheme::fvmDdt (damping term :864) and ::fvcDdt (U, :973)
+     * Each use takes its own "deltaT0": GREAT until enough old-time levels exist -- backwardD2dt2Scheme.C:58-76
+     * (timeIndex of the 2nd and 3rd old level equal), [EXT] backwardDdtScheme::deltaT0_(vf) (vf.nOldTimes() < 2) -- so the
+     * caller, who owns the time levels (oracle/evolve.py: OldTimes), passes the effective value of every use:
+     *   eD2 fvmD2dt2(D); eDdtD the fvmDdt(D) inside it; eDdtD0, eDdtD00 the fvcDdt(D.oldTime()) and
+     *   fvcDdt(D.oldTime().oldTime()) inside it; eDamp the fvm::ddt(D) of the damping term.
+     * Dooo, Doooo = the 3rd and 4th old-time level of D (cell fields). */
+    double eD2, eDdtD, eDdtD0, eDdtD00, eDamp;
+    const double* Dooo;
+    const double* Doooo;
 } orc_controls;
+
+/* coefft, coefft00, coefft0 of the backward schemes for time step deltaT and effective old time step e */
+static void backward_weights(double deltaT, double e, double* c, double* c00, double* c0)
+{
+    *c = 1 + deltaT/(deltaT + e);
+    *c00 = deltaT*deltaT/(e*(deltaT + e));
+    *c0 = *c + *c00;
+}
 
 /* (A & B)_ij = A_ik B_kj, accumulated k = x, y, z   [EXT TensorI.H operator&] */
 static void TdotT(const double* A, const double* B, double* R)
@@ -824,6 +845,33 @@ void orc_assemble_D_ex
             for (int d = 0; d < 3; d++)
                 sA[d] = (t1*((coefft + coefft00)*Dold[3*c + d] - coefft00*Doldold[3*c + d]))*rho[c];
         }
+        else if (ctl->d2dt2Scheme == 2)
+        {
+            /* backwardD2dt2Scheme::fvmD2dt2(vf)  :230-280
+             *   fvm = coefft*rDeltaT * backwardDdtScheme.fvmDdt(vf)
+             *         [EXT fvmDdt: diag = (coefft*rDeltaT)*V, source = rDeltaT*V*(coefft0*vf.oldTime() - coefft00*vf.oldTime().oldTime())]
+             *   fvm.source() += rDeltaT*V*(coefft0*fvcDdt(vf.oldTime()) - coefft00*fvcDdt(vf.oldTime().oldTime()))
+             *         [EXT fvcDdt(w) = rDeltaT*(coefft*w - coefft0*w.oldTime() + coefft00*w.oldTime().oldTime())]
+             * then rho_* (diag and source scaled by rho, as for Euler)                                                  */
+            const double dT = ctl->deltaT, rDt = 1.0/dT;
+            double c2, c200, c20, cb, cb00, cb0, c3, c300, c30, c4, c400, c40;
+            backward_weights(dT, ctl->eD2, &c2, &c200, &c20);
+            backward_weights(dT, ctl->eDdtD, &cb, &cb00, &cb0);
+            backward_weights(dT, ctl->eDdtD0, &c3, &c300, &c30);
+            backward_weights(dT, ctl->eDdtD00, &c4, &c400, &c40);
+            const double sc = c2*rDt;
+            dA = (((cb*rDt)*V)*sc)*rho[c];
+            const double rV = rDt*V;
+            for (int d = 0; d < 3; d++)
+            {
+                const double D0 = Dold[3*c + d], D00 = Doldold[3*c + d], D000 = ctl->Dooo[3*c + d], D0000 = ctl->Doooo[3*c + d];
+                const double s1 = (rV*(cb0*D0 - cb00*D00))*sc;
+                const double X = rDt*(((c3*D0) - (c30*D00)) + (c300*D000));
+                const double Y = rDt*(((c4*D00) - (c40*D000)) + (c400*D0000));
+                const double s2 = s1 + rV*(c20*X - c200*Y);
+                sA[d] = s2*rho[c];
+            }
+        }
         double dg = dA - Ldiag[c];
         double src[3];
         for (int d = 0; d < 3; d++)
@@ -842,6 +890,15 @@ void orc_assemble_D_ex
             {
                 dM = (rDeltaT*V)*sf;
                 for (int d = 0; d < 3; d++) sM[d] = ((rDeltaT*Dold[3*c + d])*V)*sf;
+            }
+            else if (ctl->ddtScheme == 2)
+            {
+                /* [EXT] backwardDdtScheme::fvmDdt(vf), then scaled by K*rho */
+                const double rDt = 1.0/ctl->deltaT;
+                double cb, cb00, cb0;
+                backward_weights(ctl->deltaT, ctl->eDamp, &cb, &cb00, &cb0);
+                dM = ((cb*rDt)*V)*sf;
+                for (int d = 0; d < 3; d++) sM[d] = ((rDt*V)*(cb0*Dold[3*c + d] - cb00*Doldold[3*c + d]))*sf;
             }
             dg += dM;
             for (int d = 0; d < 3; d++) src[d] += sM[d];
@@ -1088,6 +1145,16 @@ void orc_ddt(int nCells, int ddtScheme, double deltaT, const double* D, const do
 {
     const double rDeltaT = ddtScheme == 1 ? 1.0/deltaT : 0.0;
     for (int i = 0; i < 3*nCells; i++) U[i] = ddtScheme == 1 ? rDeltaT*(D[i] - Dold[i]) : 0.0;
+}
+
+/* U = fvc::ddt(D), backward [EXT backwardDdtScheme::fvcDdt]: rDeltaT*(coefft*D - coefft0*D.oldTime() + coefft00*D.oldTime().oldTime()),
+ * e = the effective deltaT0 of this use (GREAT while D has fewer than two old levels) */
+void orc_ddt_backward(int nCells, double deltaT, double e, const double* D, const double* Dold, const double* Doldold, double* U)
+{
+    const double rDt = 1.0/deltaT;
+    double c, c00, c0;
+    backward_weights(deltaT, e, &c, &c00, &c0);
+    for (int i = 0; i < 3*nCells; i++) U[i] = rDt*(((c*D[i]) - (c0*Dold[i])) + (c00*Doldold[i]));
 }
 
 /* GeometricField::relax on the boundary field: operator== assigns prevIter + alpha*(this - prevIter) on every patch */

@@ -9,8 +9,9 @@ fields at the north_star bars.
               The interface load comes from the fluid in an FSI run; here a uniform traction stands in for it.
               snGrad(D) `corrected` [EXT]: the mesh is orthogonal (checked below), where it and skewCorrected 1 both vanish.
   tube_solid  run/fsiFoam/3dTube/solid: linear, skewCorrected 1, fixedValue inlet/outlet, two symmetry planes, pressure on
-              the inner wall.  Its d2dt2(D)/ddt(D) `backward` schemes are not restated (no BASELINE config uses them): run
-              steadyState (also checked against Lame's thick-walled cylinder) and Euler."""
+              the inner wall, d2dt2(D)/ddt(D) `backward` (numerics/backwardD2dt2Scheme/backwardD2dt2Scheme.C:230-280 over [EXT]
+              backwardDdtScheme; five time steps, across its first-order start-up); also run steadyState (checked against
+              Lame's thick-walled cylinder) and Euler."""
 import json
 import os
 
@@ -136,6 +137,60 @@ def test_oracle_tube_matches_lame_thick_walled_cylinder():
     assert np.abs(ur[mid]/ua[mid] - 1.0).max() < 0.02
 
 
+def test_oracle_backward_d2dt2_reproduces_uniform_acceleration():
+    """Known answer for the restated `backward` d2dt2 / ddt: a free body under a uniform body force accelerates uniformly,
+    D = g t^2/2.  With the exact history in the four old-time levels one step of the scheme must land on the exact
+    displacement and velocity (second-order backward differences are exact for quadratics) -- to rounding."""
+    m = meshes.hex_box(6, 3, 4, L=0.6, W=0.3, H=0.4)
+    g = geometry.compute(m)
+    pt = {"fixed": "tractionDisplacement", "loaded": "tractionDisplacement", "free": "tractionDisplacement"}
+    mu, lam = cases.lame(2e5, 0.3)
+    acc, dT = np.array([0.3, -0.2, 1.0]), 1e-3
+    exact = lambda t: 0.5*acc*t*t
+    c = oev.SolidCase(m, g, pt, mu, lam, 1000.0, g=acc)
+    c.old = oev.OldTimes()
+    c.old.now, c.old.ti = 5, 4
+    c.D = np.tile(exact(4*dT), (m.nCells, 1))
+    c.old.lev = [[np.tile(exact((3 - j)*dT), (m.nCells, 1)), 3 - j] for j in range(4)]
+    c.Db[:] = exact(4*dT)
+    r = c.evolve(50, 1e-12, 0.0, 1e-14, 0.0, d2dt2="backward", ddt="backward", deltaT=dT)
+    assert all(c.lastBackward[k] == dT for k in ("eD2", "eDdtD", "eDdtD0", "eDdtD00", "eU"))
+    assert np.abs(c.D - exact(5*dT)).max() <= 1e-13*np.abs(exact(5*dT)).max()
+    assert np.abs(c.U - acc*5*dT).max() <= 1e-11*np.abs(acc*5*dT).max()
+
+
+def test_backward_start_up_follows_the_old_time_levels():
+    """backwardD2dt2Scheme.C:58-76 / [EXT] backwardDdtScheme::deltaT0_: which uses see GREAT in the first time steps of a run
+    (oracle/ASSUMPTIONS.md #13) -- the oracle's and the product's bookkeeping (timelevels.OldTimes, here over a recorder
+    instead of a device mesh) must agree step by step, and from the 4th step on every use sees the real deltaT0."""
+    from fluidstructureinteraction_b200 import timelevels
+
+    class Recorder(object):
+        def __init__(self): self.copies = []
+        def copy_field(self, dst, src): self.copies.append((dst, src))
+
+    D = np.zeros((4, 3))
+    o, rec = oev.OldTimes(), Recorder()
+    o.now = o.ti = 1
+    p = timelevels.OldTimes(rec)
+    seen = []
+    for step in range(1, 7):
+        if step > 1:
+            o.advance(); p.advance()
+        for outer in range(2):
+            eo = oev.backward_controls(o, D, "backward", "backward", True, 2e-3)
+            ep = p.assembly("backward", "backward", True, 2e-3)
+            assert eo == ep, (step, outer)
+            seen.append((step, outer, eo["eD2"] == oev.GREAT, eo["eDdtD00"] == oev.GREAT))
+        o.ensure(1, D); eUo = oev.GREAT if o.n_old(0) < 2 else 2e-3; o.ensure(2, D)
+        assert p.velocity(2e-3) == eUo == 2e-3
+        D = D + 1.0
+    assert [s[2] for s in seen if s[1] == 0] == [True, True, True, False, False, False]       # eD2: GREAT in steps 1-3
+    assert [s[3] for s in seen] == [True] + [False]*11                                          # eDdtD00: the very first use only
+    assert rec.copies[:4] == [("Dold", "D"), ("Doldold", "Dold"), ("Dooo", "Doldold"), ("Doooo", "Dooo")]
+    assert rec.copies[4:8] == [("Doooo", "Dooo"), ("Dooo", "Doldold"), ("Doldold", "Dold"), ("Dold", "D")]
+
+
 # ------------------------------------------------------------------------------------------------------------------ GPU
 def _compare(c, gc, r, rg):
     assert rg["nOuterIterations"] == r["nOuterIterations"], (rg["nOuterIterations"], r["nOuterIterations"])
@@ -165,13 +220,16 @@ def test_gpu_beam_solid_shipped_settings_three_time_steps():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("scheme", ["steadyState", "Euler"])
+@pytest.mark.parametrize("scheme", ["steadyState", "Euler", "backward"])
 def test_gpu_tube_solid_shipped_settings(scheme):
+    """`backward` = the shipped fvSchemes of the case, unchanged."""
     from fluidstructureinteraction_b200.solid import GpuSolidCase
     m, g, S, _ = _load("tube_solid")
+    if scheme == "backward":
+        assert (S["d2dt2"], S["ddt"]) == ("backward", "backward")
     S = dict(S, d2dt2=scheme, ddt=scheme)
     c, gc = _make(oev.SolidCase, m, g, S, TUBE_LOAD), _make(GpuSolidCase, m, g, S, TUBE_LOAD)
-    for step in range(1 if scheme == "steadyState" else 2):
+    for step in range({"steadyState": 1, "Euler": 2, "backward": 5}[scheme]):
         c.new_time_step(); gc.new_time_step()
         r, rg = _evolve(c, S), _evolve(gc, S)
         _compare(c, gc, r, rg)
