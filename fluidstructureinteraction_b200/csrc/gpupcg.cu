@@ -695,9 +695,14 @@ static int make_system(gpupcg_handle h, gpupcg_handle& out, int nSystems)
     CK(cudaMemsetAsync(h->dTileTicket, 0, sizeof(unsigned long long), h->stream));
     if (h->pencil)
     {
-        CK(dalloc(h->dSmCounter, 1024));
-        CK(cudaMemsetAsync(h->dSmCounter, 0, sizeof(unsigned int)*1024, h->stream));
-        h->pen.smCounter = h->pen.smCounter ? h->dSmCounter : nullptr;
+        // The per-SM role counter is the parent's, shared by the systems (GPUPCG_SYS_OWN_COUNTER=1: one each): the sweep CTAs of
+        // the systems that share an SM then take different schedulers for their sweep warps instead of colliding by chance.
+        if (env_int("GPUPCG_SYS_OWN_COUNTER", 0))
+        {
+            CK(dalloc(h->dSmCounter, 1024));
+            CK(cudaMemsetAsync(h->dSmCounter, 0, sizeof(unsigned int)*1024, h->stream));
+            h->pen.smCounter = h->pen.smCounter ? h->dSmCounter : nullptr;
+        }
     }
     else if (h->useTab) { CK(dalloc(h->dTabF, 4LL*std::max(1, P.nRows))); CK(dalloc(h->dTabB, 4LL*std::max(1, P.nRows))); }
     CK(cudaStreamSynchronize(h->stream));
