@@ -81,8 +81,9 @@ static int schemeCode(const dictionary& fvSchemes, const word& group, const word
     const std::string s = g.found(key) ? g.lookup(key) : g.lookup("default");
     if (s == "steadyState") return 0;
     if (s == "Euler") return 1;
+    if (s == "backward") return 2;
     FatalErrorIn("gpuUnsTotalLagrangianStress::gpuUnsTotalLagrangianStress(const fvMesh&)")
-        << group << " " << key << " " << s << " is not available on the GPU (steadyState, Euler)" << abort(FatalError);
+        << group << " " << key << " " << s << " is not available on the GPU (steadyState, Euler, backward)" << abort(FatalError);
     return -1;
 }
 
@@ -99,7 +100,7 @@ void gpuUnsTotalLagrangianStress::check(int rc, const char* what) const
 
 gpuUnsTotalLagrangianStress::gpuUnsTotalLagrangianStress(const fvMeshLike& mesh)
 :
-    stressModel(typeName, mesh), gm_(0), solver_(0), nonLinear_(false), thermal_(false)
+    stressModel(typeName, mesh), gm_(0), solver_(0), nonLinear_(false), thermal_(false), tiD_(1), now_(1)
 {
     const dictionary& sp = stressProperties();
     const int nC = mesh.nCells, nIF = mesh.nInternalFaces, nBF = mesh.nFaces - nIF;
@@ -225,9 +226,42 @@ void gpuUnsTotalLagrangianStress::setPressure(const label patchID, const scalar*
     check(gpupcg_mesh_set_field(gm_, GPUPCG_F_PRESSURE, pressure_.data()), "set pressure");
 }
 
+// ---- D's old-time levels for the `backward` schemes.  In a foam-extend process GeometricField keeps them (oldTime() creates a
+// level on first use, storeOldTimes() shifts them at the first non-const access of a new time step) and the schemes read their
+// state: backwardD2dt2Scheme.C:58-76 (GREAT while the 2nd and 3rd old level carry the same timeIndex), [EXT]
+// backwardDdtScheme::deltaT0_ (GREAT while vf.nOldTimes() < 2).  Here the levels are device fields and this is their
+// bookkeeping (the same as fluidstructureinteraction_b200/timelevels.py).
+static const int levelId[4] = {GPUPCG_F_DOLD, GPUPCG_F_DOLDOLD, GPUPCG_F_DOOO, GPUPCG_F_DOOOO};
+
+void gpuUnsTotalLagrangianStress::touchOldTimes()
+{
+    if (!oldTi_.empty() && tiD_ != now_)
+    {
+        for (int j = (int)oldTi_.size() - 1; j > 0; j--)
+        {
+            check(gpupcg_mesh_copy_field(gm_, levelId[j], levelId[j - 1]), "gpupcg_mesh_copy_field");
+            oldTi_[j] = oldTi_[j - 1];
+        }
+        check(gpupcg_mesh_copy_field(gm_, levelId[0], GPUPCG_F_D), "gpupcg_mesh_copy_field");
+        oldTi_[0] = tiD_;
+    }
+    tiD_ = now_;
+}
+
+void gpuUnsTotalLagrangianStress::ensureOldTimes(int k)
+{
+    while ((int)oldTi_.size() < k)
+    {
+        const int j = (int)oldTi_.size();
+        check(gpupcg_mesh_copy_field(gm_, levelId[j], j == 0 ? GPUPCG_F_D : levelId[j - 1]), "gpupcg_mesh_copy_field");
+        oldTi_.push_back(j == 0 ? tiD_ : oldTi_[j - 1]);
+    }
+}
+
 void gpuUnsTotalLagrangianStress::newTimeStep()
 {
-    check(gpupcg_mesh_new_time_step(gm_), "gpupcg_mesh_new_time_step");
+    if (ctl_.eqn.d2dt2Scheme == 2 || ctl_.eqn.ddtScheme == 2) now_++;       // the levels shift when evolve() first touches D
+    else check(gpupcg_mesh_new_time_step(gm_), "gpupcg_mesh_new_time_step");
 }
 
 bool gpuUnsTotalLagrangianStress::evolve()
@@ -236,7 +270,37 @@ bool gpuUnsTotalLagrangianStress::evolve()
     const int cap = ctl_.nCorrectors + 1;
     info_.residualHistory.assign(cap, 0.0);
     info_.pcgIterations.assign(3*(size_t)cap, 0);
+    gpupcg_eqn_controls& q = ctl_.eqn;
+    const bool backward = q.d2dt2Scheme == 2 || q.ddtScheme == 2;
+    if (backward)
+    {
+        // the uses of one assembly in the reference's order (unsTotalLagrangianStress.C:846-865)
+        const double GREAT = 1.0e15, dT0 = q.deltaT0;
+        q.eD2 = q.eDdtD = q.eDdtD0 = q.eDdtD00 = q.eDamp = q.eU = dT0;
+        touchOldTimes();
+        if (q.d2dt2Scheme == 2)
+        {
+            ensureOldTimes(3);
+            q.eD2 = (oldTi_[1] == oldTi_[2]) ? GREAT : dT0;
+            q.eDdtD = ((int)oldTi_.size() < 2) ? GREAT : dT0;
+            q.eDdtD0 = ((int)oldTi_.size() - 1 < 2) ? GREAT : dT0;
+            q.eDdtD00 = ((int)oldTi_.size() - 2 < 2) ? GREAT : dT0;
+            ensureOldTimes(4);
+        }
+        else if (q.d2dt2Scheme == 1) ensureOldTimes(2);
+        if (q.K > 1e-15)
+        {
+            if (q.ddtScheme == 2) { q.eDamp = ((int)oldTi_.size() < 2) ? GREAT : dT0; ensureOldTimes(2); }
+            else if (q.ddtScheme == 1) ensureOldTimes(1);
+        }
+    }
     check(gpupcg_evolve_D(solver_, gm_, &ctl_, &r, info_.residualHistory.data(), info_.pcgIterations.data(), cap), "gpupcg_evolve_D");
+    if (q.ddtScheme == 2)       // U = fvc::ddt(D) (:973): residual() has used D.oldTime() by now
+    {
+        ensureOldTimes(1);
+        q.eU = ((int)oldTi_.size() < 2) ? 1.0e15 : q.deltaT0;
+        ensureOldTimes(2);
+    }
     check(gpupcg_sigma_resident(gm_, &ctl_.eqn), "gpupcg_sigma_resident");
     const int nOut = std::min(cap, r.nOuterIterations + 1);
     int nv = 0; for (int d = 0; d < 3; d++) nv += ctl_.validCmpt[d];

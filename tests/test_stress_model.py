@@ -69,7 +69,7 @@ def test_run_time_selection_and_dictionary_checks():
     with pytest.raises(hostapi.FoamFatalError) as e:
         _model(m, g, PH, tr, model="unsTotalLagrangianStress")
     assert "Unknown stressModel type unsTotalLagrangianStress" in str(e.value) and "gpuUnsTotalLagrangianStress" in str(e.value)
-    for kw, msg in ((dict(solver="GAMG"), "PCG/DIC"), (dict(d2dt2="backward"), "backward"), (dict(sn="corrected"), "skewCorrected")):
+    for kw, msg in ((dict(solver="GAMG"), "PCG/DIC"), (dict(d2dt2="CrankNicolson"), "CrankNicolson"), (dict(sn="corrected"), "skewCorrected")):
         with pytest.raises(hostapi.FoamFatalError) as e:
             _model(m, g, PH, tr, **kw)
         assert msg in str(e.value), (kw, str(e.value))
@@ -109,4 +109,55 @@ def test_gpu_stress_model_runs_config_1_like_the_harness_and_the_oracle():
         assert np.abs(a - b).max() <= 1e-9*np.abs(b).max(), k
     e = cases.plate_hole_errors(m, g, sm.get("D").reshape(-1, 3), sm.get("pointD").reshape(-1, 3), sm.get("sigma").reshape(-1, 6))
     assert e["DError"] < 0.004*e["DMax"] and e["sigmaXXErr"] < 0.03*e["sigmaXXMax"]
+    sm.close(); gc.close()
+
+
+@pytest.mark.gpu
+def test_gpu_stress_model_runs_the_shipped_tube_case_with_its_backward_schemes():
+    """run/fsiFoam/3dTube/solid through the C++ model with the SHIPPED dictionaries as text (tests/golden/tube_solid.case.json
+    holds them parsed; written back in foam syntax here): d2dt2(D) / ddt(D) backward -- the model keeps D's four old-time levels
+    on the device and works out the schemes' start-up rule itself (host/gpuStressModel.C: touchOldTimes / ensureOldTimes).
+    Five time steps = the Python harness bit for bit (same C-ABI calls) and the oracle at the north_star bars."""
+    from oracle import evolve as oev
+    from fluidstructureinteraction_b200 import meshes
+    from fluidstructureinteraction_b200.solid import GpuSolidCase
+    m = meshes.PolyMesh.load_npz(os.path.join(GOLD, "tube_solid.polymesh.npz"))
+    with open(os.path.join(GOLD, "tube_solid.case.json")) as f:
+        d = json.load(f)
+    g = geometry.compute(m)
+    S = cases.solid_case_settings(d)
+    assert (S["d2dt2"], S["ddt"]) == ("backward", "backward")
+    tr, pr, fv = cases.boundary_fields(m, S, pressure={"inner-wall": 1333.2})
+    mu, lam = cases.lame(S["E"], S["nu"], S["planeStress"])
+    stress = """stressModel gpuUnsTotalLagrangianStress;
+gpuUnsTotalLagrangianStressCoeffs { nCorrectors %d; convergenceTolerance %r; relConvergenceTolerance %r; nonLinear %s; debug no; moveMesh no; }
+""" % (S["nCorrectors"], S["convergenceTolerance"], S["relConvergenceTolerance"], "yes" if S["nonLinear"] else "no")
+    rheology = """planeStress %s;
+rheology { type linearElastic; rho rho [1 -3 0 0 0 0 0] %r; E E [1 -1 -2 0 0 0 0] %r; nu nu [0 0 0 0 0 0 0] %r; }
+""" % ("yes" if S["planeStress"] else "no", S["rho"], S["E"], S["nu"])
+    fvSolution = "solvers { D { solver gpuPCG; preconditioner DIC; tolerance %r; relTol %r; } }\nrelaxationFactors { %s }\n" % (
+        S["tolerance"], S["relTol"], ("D %r;" % S["relaxD"]) if S["relaxD"] is not None else "")
+    fvSchemes = """d2dt2Schemes { default none; d2dt2(D) %s; }
+ddtSchemes { default none; ddt(D) %s; }
+snGradSchemes { default none; snGrad(D) skewCorrected %r; }
+""" % (S["d2dt2"], S["ddt"], S["limitCoeff"])
+    L = lsq.build(m, g, S["patchTypes"])
+    sm = hostapi.StressModel(m, g, S["patchTypes"], stress, rheology, fvSolution, fvSchemes, deltaT=S["deltaT"], pressure=pr,
+                             fixedValue=fv, lsq=L, pointConstraints=lsq.point_constraints(m, g, S["pointPatchTypes"]))
+    kw = dict(traction=tr, pressure=pr, fixedValue=fv, pointPatchTypes=S["pointPatchTypes"])
+    ref = oev.SolidCase(m, g, S["patchTypes"], mu, lam, S["rho"], **kw)
+    gc = GpuSolidCase(m, g, S["patchTypes"], mu, lam, S["rho"], lsq=L, **kw)
+    ev = lambda c: c.evolve(S["nCorrectors"], S["convergenceTolerance"], S["relConvergenceTolerance"], S["tolerance"], S["relTol"],
+                            d2dt2=S["d2dt2"], ddt=S["ddt"], deltaT=S["deltaT"], nonLinear=S["nonLinear"], limitCoeff=S["limitCoeff"],
+                            relaxD=S["relaxD"], maxIter=S["maxIter"])
+    for step in range(5):
+        sm.new_time_step(); gc.new_time_step(); ref.new_time_step()
+        rs, rg, r = sm.evolve(), ev(gc), ev(ref)
+        assert rs["nOuterIterations"] == rg["nOuterIterations"] == r["nOuterIterations"], step
+        assert np.array_equal(rs["pcgIterations"], rg["pcgIterations"]) and np.array_equal(rs["pcgIterations"], np.array(r["pcgIterations"]))
+        for k in ("D", "pointD", "sigma", "U"):
+            a = sm.get(k)
+            assert np.array_equal(a, gc.get(k).ravel()), (step, k)
+            b = getattr(ref, k).ravel()
+            assert np.abs(a - b).max() <= 1e-9*np.abs(b).max(), (step, k)
     sm.close(); gc.close()
