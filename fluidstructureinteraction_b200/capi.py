@@ -53,7 +53,7 @@ class EvolveControls(C.Structure):
     _fields_ = [("nCorrectors", C.c_int), ("convergenceTolerance", C.c_double), ("relConvergenceTolerance", C.c_double),
                 ("tolerance", C.c_double), ("relTol", C.c_double), ("minIter", C.c_int), ("maxIter", C.c_int),
                 ("relaxD", C.c_double), ("doRelax", C.c_int), ("validCmpt", C.c_int*3), ("g", C.c_double*3),
-                ("eqn", EqnControls)]
+                ("eqn", EqnControls), ("incremental", C.c_int)]
 
 
 class EvolveResult(C.Structure):
@@ -377,9 +377,12 @@ class GpuPCG(object):
         return [perf[k].as_dict() for k in range(3)]
 
     def evolve_D(self, gpuMesh, nCorrectors, convergenceTolerance, relConvergenceTolerance=0.0, tolerance=1e-9, relTol=0.01,
-                 minIter=0, maxIter=1000, relaxD=None, validCmpts=(1, 1, 1), g=(0.0, 0.0, 0.0), eqn=None, historyCap=None):
-        """unsTotalLagrangianStress::evolve() on the fields resident in gpuMesh (gpupcg_evolve_D)."""
+                 minIter=0, maxIter=1000, relaxD=None, validCmpts=(1, 1, 1), g=(0.0, 0.0, 0.0), eqn=None, historyCap=None,
+                 incremental=False):
+        """unsTotalLagrangianStress::evolve() on the fields resident in gpuMesh (gpupcg_evolve_D); incremental: the loop of
+        unsIncrTotalLagrangianStress::evolve() (the resident D is the increment DD)."""
         ec = EvolveControls()
+        ec.incremental = 1 if incremental else 0
         ec.nCorrectors = int(nCorrectors); ec.convergenceTolerance = convergenceTolerance
         ec.relConvergenceTolerance = relConvergenceTolerance; ec.tolerance = tolerance; ec.relTol = relTol
         ec.minIter = minIter; ec.maxIter = maxIter
@@ -414,10 +417,11 @@ PATCH_TYPES = {"tractionDisplacement": 0, "fixedDisplacement": 1, "symmetryDispl
 FIELD_IDS = dict(mu=0, lambda_=1, rho=2, D=3, Dold=4, Doldold=5, gradD=6, gradDf=7, traction=8, pressure=9, fixedValue=10,
                  threeK=11, alpha=12, DT=13, DTb=14, pointD=15, Db=16, gradDb=17, U=18, epsilon=19, sigma=20, upper=21,
                  diag=22, source=23, internalCoeffs=24, boundaryCoeffs=25, patchGradient=26, Dprev=27, DbPrev=28, Dooo=29,
-                 Doooo=30)
+                 Doooo=30, gradDfBStart=31)
 _FIELD_COLS = dict(mu=1, lambda_=1, rho=1, D=3, Dold=3, Doldold=3, gradD=9, gradDf=9, traction=3, pressure=1, fixedValue=3,
                    threeK=1, alpha=1, DT=1, DTb=1, pointD=3, Db=3, gradDb=9, U=3, epsilon=6, sigma=6, upper=1, diag=1,
-                   source=3, internalCoeffs=3, boundaryCoeffs=3, patchGradient=3, Dprev=3, DbPrev=3, Dooo=3, Doooo=3)
+                   source=3, internalCoeffs=3, boundaryCoeffs=3, patchGradient=3, Dprev=3, DbPrev=3, Dooo=3, Doooo=3,
+                   gradDfBStart=9)
 
 
 class GpuMesh(object):

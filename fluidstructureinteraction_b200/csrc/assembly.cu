@@ -828,7 +828,7 @@ __global__ void __launch_bounds__(ATPB) k_relax_maxdd(int nCells, double alpha, 
                 v = add(pv, mul(alpha, sub(v, pv)));
                 D[3*(size_t)c + k] = v;
             }
-            d[k] = sub(v, Dold[3*(size_t)c + k]);
+            d[k] = Dold ? sub(v, Dold[3*(size_t)c + k]) : v;      // Dold == nullptr: max mag(D) (the incremental model's residual)
         }
         mx = fmax(mx, mag3(d));
     }
@@ -881,6 +881,7 @@ struct gpupcg_mesh_s
     double *dDprev = nullptr, *dDold = nullptr, *dRed = nullptr;
     // round 2: the remaining state of evolve() (allocated on first use)
     double *dDoldold = nullptr, *dThreeK = nullptr, *dAlpha = nullptr, *dDT = nullptr, *dDTb = nullptr;
+    double *dGradDfBStart = nullptr;        // incremental loop: boundary rows of gradDf at the start of the last outer iteration
     double *dDooo = nullptr, *dDoooo = nullptr, *dTimeA = nullptr;      // `backward` d2dt2: 3rd / 4th old level, per-cell time terms
     double *dDb = nullptr, *dDbPrev = nullptr, *dU = nullptr;
     double *dFluxX = nullptr, *dFluxY = nullptr, *dFluxT = nullptr;
@@ -1383,6 +1384,7 @@ FieldRef field_ref(gpupcg_mesh m, int id)
         case GPUPCG_F_DBPREV: return {&m->dDbPrev, 3*nBF, nullptr};
         case GPUPCG_F_DOOO: return {&m->dDooo, 3*nC, nullptr};
         case GPUPCG_F_DOOOO: return {&m->dDoooo, 3*nC, nullptr};
+        case GPUPCG_F_GRADDFB_START: return {&m->dGradDfBStart, 9*nBF, nullptr};
         default: return {nullptr, 0, nullptr};
     }
 }
@@ -1807,10 +1809,21 @@ extern "C" int gpupcgi_mesh_outer_begin(gpupcg_mesh m, const gpupcg_eqn_controls
     return assemble_resident(m, c, g);
 }
 
+// incremental loop: DSigmaf_ is formed from gradDDf_ at the start of an outer iteration (unsIncrTotalLagrangianStress.C:1013-1018)
+// and not again after the last solve; keep the boundary rows it was formed from
+extern "C" int gpupcgi_mesh_snapshot_gradDfB(gpupcg_mesh m)
+{
+    const MeshDev& M = m->M;
+    const size_t nb9 = 9*(size_t)(M.nFaces - M.nIF);
+    int rc = ensure(m, m->dGradDfBStart, nb9); if (rc) return rc;
+    if (nb9) MCK(cudaMemcpyAsync(m->dGradDfBStart, m->dGradDf + 9*(size_t)M.nIF, sizeof(double)*nb9, cudaMemcpyDeviceToDevice, m->stream));
+    return GPUPCG_OK;
+}
+
 // after DEqn.solve(): correctBoundaryConditions, D.relax() (:910), volToPoint (:924), grad / fGrad (:925-926), det bounds
 // (:929-937), residual() (:949).  hostScal (pinned, 4 doubles) <- {residual, maxDD, minDet, maxDet}, asynchronously.
 extern "C" int gpupcgi_mesh_outer_end(gpupcg_mesh m, const gpupcg_eqn_controls* c, double alpha, int doRelax, int detBounds,
-                                      double* hostScal)
+                                      double* hostScal, int incremental)
 {
     const MeshDev& M = m->M;
     const int nC = M.nCells;
@@ -1819,7 +1832,7 @@ extern "C" int gpupcgi_mesh_outer_end(gpupcg_mesh m, const gpupcg_eqn_controls* 
     int rc = evaluate_resident(m); if (rc) return rc;
     if (doRelax && nb3 > 0) k_relax_boundary<<<agrid(m, nb3), ATPB, 0, s>>>(nb3, alpha, m->dDb, m->dDbPrev);
     const int nb = std::min(1000, agrid(m, nC));        // partials: dRed[0, 1000) and dRed[1024, 2024); results at dRed[2040, 2048)
-    k_relax_maxdd<<<nb, ATPB, 0, s>>>(nC, alpha, doRelax, m->dD, m->dDprev, m->dDold, m->dRed);
+    k_relax_maxdd<<<nb, ATPB, 0, s>>>(nC, alpha, doRelax, m->dD, m->dDprev, incremental ? nullptr : m->dDold, m->dRed);
     k_residual<<<nb, ATPB, 0, s>>>(nC, nb, m->dD, m->dDprev, m->dRed, m->dRed + 1024);
     MCK(cudaGetLastError());
     rc = vol_to_point_resident(m); if (rc) return rc;

@@ -776,6 +776,11 @@ static int evolve_impl(gpupcg_handle h, gpupcg_mesh m, const gpupcg_evolve_contr
     {
         eq.nonLinear = (nonLinear && !enforceLinear) ? 1 : 0;
         CK(cudaEventRecord(e0, s));
+        if (ec->incremental)
+        {
+            rc = gpupcgi_mesh_snapshot_gradDfB(m);
+            if (rc) { h->err = std::string("gpupcg_evolve_D: ") + gpupcg_mesh_last_error(m); return rc; }
+        }
         rc = gpupcgi_mesh_outer_begin(m, &eq, ec->g);
         if (rc) { h->err = std::string("gpupcg_evolve_D: ") + gpupcg_mesh_last_error(m); return rc; }
         if (!haveView)      // the device pointers of the assembled equation do not change between outer iterations
@@ -802,7 +807,7 @@ static int evolve_impl(gpupcg_handle h, gpupcg_mesh m, const gpupcg_evolve_contr
         k_unpack_cmpts<NB><<<grid_for(P.nCells, h->streamGrid), TPB, 0, s>>>(P.nCells, h->vStageX, cm[0], cm[1], cm[2], dD);
         CK(cudaGetLastError());
         CK(cudaEventRecord(e2, s));
-        rc = gpupcgi_mesh_outer_end(m, &eq, ec->relaxD, ec->doRelax, eq.nonLinear, hostScal);
+        rc = gpupcgi_mesh_outer_end(m, &eq, ec->relaxD, ec->doRelax, eq.nonLinear, hostScal, ec->incremental);
         if (rc) { h->err = std::string("gpupcg_evolve_D: ") + gpupcg_mesh_last_error(m); return rc; }
         CK(cudaEventRecord(e3, s));
         CK(cudaStreamSynchronize(s));
@@ -823,7 +828,9 @@ static int evolve_impl(gpupcg_handle h, gpupcg_mesh m, const gpupcg_evolve_contr
         if (cur < ec->convergenceTolerance) cur = ec->convergenceTolerance;
         if (residualHistory && iCorr < historyCap) residualHistory[iCorr] = r;
         if (pcgIterations && iCorr < historyCap) for (int k = 0; k < NB; k++) pcgIterations[3*iCorr + k] = perf[k].nIterations;
-        if (!(r > cur)) break;
+        // total model: while (res > curConvergenceTolerance && ++iCorr < nCorr) (:967-971); incremental model: while (res >
+        // convergenceTolerance && ++iCorr < nCorr) (unsIncrTotalLagrangianStress.C:1155-1159)
+        if (!(r > (ec->incremental ? ec->convergenceTolerance : cur))) break;
         if (!(++iCorr < ec->nCorrectors)) break;
     }
     if (res)

@@ -17,6 +17,7 @@ extern "C" int gpupcgi_mesh_view(gpupcg_mesh m, gpupcg_mesh_view* v);
 extern "C" int gpupcgi_mesh_bind_stream(gpupcg_mesh m, void* stream, void** previous);
 extern "C" int gpupcgi_mesh_outer_begin(gpupcg_mesh m, const gpupcg_eqn_controls* c, const double* g);
 extern "C" int gpupcgi_mesh_outer_end(gpupcg_mesh m, const gpupcg_eqn_controls* c, double alpha, int doRelax, int detBounds,
-                                      double* hostScal6);
+                                      double* hostScal6, int incremental);
+extern "C" int gpupcgi_mesh_snapshot_gradDfB(gpupcg_mesh m);
 extern "C" int gpupcgi_mesh_D(gpupcg_mesh m, double** D);
 extern "C" void gpupcgi_mesh_set_error(gpupcg_mesh m, const char* msg);

@@ -277,14 +277,41 @@ bool gpuUnsTotalLagrangianStress::evolve()
         for (direction d = 0; d < 3; d++) c.g[d] = g.value()[d];
     }
     const word d2 = word(mesh.schemesDict().d2dt2Scheme("d2dt2(D)")), d1 = word(mesh.schemesDict().ddtScheme("ddt(D)"));
-    if ((d2 != "steadyState" && d2 != "Euler") || (d1 != "steadyState" && d1 != "Euler"))
+    if ((d2 != "steadyState" && d2 != "Euler" && d2 != "backward") || (d1 != "steadyState" && d1 != "Euler" && d1 != "backward"))
     {
         FatalErrorIn("gpuUnsTotalLagrangianStress::evolve()") << "d2dt2(D) " << d2 << " / ddt(D) " << d1
-            << ": steadyState and Euler are available on the GPU" << abort(FatalError);
+            << ": steadyState, Euler and backward are available on the GPU" << abort(FatalError);
     }
-    c.eqn.d2dt2Scheme = (d2 == "Euler"); c.eqn.ddtScheme = (d1 == "Euler");
-    c.eqn.deltaT = runTime().deltaT().value(); c.eqn.deltaT0 = runTime().deltaT0().value();
+    c.eqn.d2dt2Scheme = (d2 == "Euler") ? 1 : (d2 == "backward") ? 2 : 0;
+    c.eqn.ddtScheme = (d1 == "Euler") ? 1 : (d1 == "backward") ? 2 : 0;
     c.eqn.K = stressProperties().found("K") ? dimensionedScalar(stressProperties().lookup("K")).value() : 0.0;
+    c.eqn.deltaT = runTime().deltaT().value(); c.eqn.deltaT0 = runTime().deltaT0().value();
+    if (c.eqn.d2dt2Scheme == 2 || c.eqn.ddtScheme == 2)
+    {
+        // `backward`: the schemes decide from the state of D's old-time levels whether a use sees deltaT0 or GREAT
+        // (backwardD2dt2Scheme.C:58-76; backwardDdtScheme::deltaT0_).  Here D_ IS a GeometricField, so the state is read off
+        // it in the order evolve()'s expression touches it (the fvMatrix constructor's non-const access first), and the four
+        // levels go to the device as they are.
+        volVectorField& Dref = D();
+        Dref.boundaryField();                                       // non-const access: storeOldTimes()
+        const scalar dT0 = c.eqn.deltaT0;
+        c.eqn.eD2 = c.eqn.eDdtD = c.eqn.eDdtD0 = c.eqn.eDdtD00 = c.eqn.eDamp = c.eqn.eU = dT0;
+        if (c.eqn.d2dt2Scheme == 2)
+        {
+            const volVectorField& D000 = Dref.oldTime().oldTime().oldTime();
+            c.eqn.eD2 = (Dref.oldTime().oldTime().timeIndex() == D000.timeIndex()) ? GREAT : dT0;
+            c.eqn.eDdtD = (Dref.nOldTimes() < 2) ? GREAT : dT0;
+            c.eqn.eDdtD0 = (Dref.oldTime().nOldTimes() < 2) ? GREAT : dT0;
+            c.eqn.eDdtD00 = (Dref.oldTime().oldTime().nOldTimes() < 2) ? GREAT : dT0;
+            const volVectorField& D0000 = D000.oldTime();
+            check(gpupcg_mesh_set_field(gm_, GPUPCG_F_DOOO, reinterpret_cast<const double*>(D000.internalField().begin())), "D000");
+            check(gpupcg_mesh_set_field(gm_, GPUPCG_F_DOOOO, reinterpret_cast<const double*>(D0000.internalField().begin())), "D0000");
+        }
+        if (c.eqn.K > SMALL && c.eqn.ddtScheme == 2) c.eqn.eDamp = (Dref.nOldTimes() < 2) ? GREAT : dT0;
+        check(gpupcg_mesh_set_field(gm_, GPUPCG_F_DOLD, reinterpret_cast<const double*>(Dref.oldTime().internalField().begin())), "D0");
+        check(gpupcg_mesh_set_field(gm_, GPUPCG_F_DOLDOLD, reinterpret_cast<const double*>(Dref.oldTime().oldTime().internalField().begin())), "D00");
+        c.eqn.eU = dT0;                                             // two old levels exist from here on
+    }
     c.eqn.nonLinear = Switch(stressProperties().lookupOrDefault<Switch>("nonLinear", false)) ? 1 : 0;
     c.eqn.thermal = thermalStress() ? 1 : 0;
     {

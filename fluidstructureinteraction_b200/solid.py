@@ -54,7 +54,7 @@ class GpuSolidCase(object):
 
     def evolve(self, nCorrectors, convergenceTolerance, relConvergenceTolerance=0.0, tolerance=1e-9, relTol=0.01,
                d2dt2="steadyState", ddt="steadyState", deltaT=1.0, deltaT0=None, K=0.0, nonLinear=False, thermal=False,
-               limitCoeff=1.0, relaxD=None, maxIter=1000):
+               limitCoeff=1.0, relaxD=None, maxIter=1000, incremental=False):
         bw = None
         if "backward" in (d2dt2, ddt):
             dT0 = deltaT if deltaT0 is None else deltaT0
@@ -66,7 +66,7 @@ class GpuSolidCase(object):
             bw["eU"] = dT0
         eqn = capi.eqn_controls(d2dt2, ddt, deltaT, deltaT0, K, nonLinear, thermal, limitCoeff, bw)
         r = self.pcg.evolve_D(self.gm, nCorrectors, convergenceTolerance, relConvergenceTolerance, tolerance, relTol, 0, maxIter,
-                              relaxD, self.validCmpts, self.g, eqn)
+                              relaxD, self.validCmpts, self.g, eqn, incremental=incremental)
         # U, epsilon, sigma (:973-990): `nonLinear` here is the dictionary switch, whatever enforceLinear became
         if ddt == "backward":
             eqn.eU = self.old.velocity(deltaT if deltaT0 is None else deltaT0)
@@ -75,3 +75,61 @@ class GpuSolidCase(object):
 
     def close(self):
         self.pcg.close(); self.gm.close()
+
+
+class GpuIncrSolidCase(object):
+    """unsIncrTotalLagrangianStress, linear branch (stressModels/unsIncrTotalLagrangianStress/unsIncrTotalLagrangianStress.C:946-1187,
+    updateTotalFields :1212-1233): the increment DD is the device-resident field of a GpuSolidCase -- same kernels, the loop of
+    gpupcg_evolve_D with `incremental` set -- under the traction increment of tractionDisplacementIncrementFvPatchVectorField.C:203-233,
+    DTraction = (traction - pressure*n) - (n & sigmaf).  What happens once per TIME STEP is host arithmetic here: the traction
+    increment going in, DSigmaf of the boundary faces and updateTotalFields() coming out (the totals D, pointD, gradD, gradDf,
+    sigma, epsilon are numpy arrays of this object)."""
+
+    def __init__(self, mesh, geom, patchTypes, mu, lam, rho, traction=None, pressure=None, fixedValue=None, **kw):
+        nC, nF, nIF = mesh.nCells, mesh.nFaces, mesh.nInternalFaces
+        nBF = nF - nIF
+        self.mesh, self.geom = mesh, geom
+        self.inc = GpuSolidCase(mesh, geom, patchTypes, mu, lam, rho, fixedValue=fixedValue, **kw)
+        self.traction = np.zeros((nBF, 3)) if traction is None else np.asarray(traction, dtype=np.float64)
+        self.pressure = np.zeros(nBF) if pressure is None else np.asarray(pressure, dtype=np.float64)
+        full = lambda v: np.full(nC, float(v)) if np.isscalar(v) else np.asarray(v, dtype=np.float64)
+        own = mesh.owner[nIF:]
+        self.mufB, self.lambdafB = full(mu)[own].copy(), full(lam)[own].copy()
+        self.n = geom.Sf[nIF:]/geom.magSf[nIF:, None]                       # patch().nf()
+        self.D = np.zeros((nC, 3)); self.pointD = np.zeros((mesh.nPoints, 3)); self.gradD = np.zeros((nC, 9))
+        self.gradDf = np.zeros((nF, 9)); self.sigma = np.zeros((nC, 6)); self.epsilon = np.zeros((nC, 6))
+        self.sigmafB = np.zeros((nBF, 6)); self.epsilonfB = np.zeros((nBF, 6))
+
+    def new_time_step(self):
+        self.inc.new_time_step()
+
+    def evolve(self, *a, **kw):
+        n, S = self.n, self.sigmafB
+        nS = np.stack([n[:, 0]*S[:, 0] + n[:, 1]*S[:, 1] + n[:, 2]*S[:, 2],            # (n & sigmaf), terms added x, y, z
+                       n[:, 0]*S[:, 1] + n[:, 1]*S[:, 3] + n[:, 2]*S[:, 4],
+                       n[:, 0]*S[:, 2] + n[:, 1]*S[:, 4] + n[:, 2]*S[:, 5]], axis=1)
+        self.inc.set("traction", (self.traction - self.pressure[:, None]*n) - nS)
+        self.inc.set("pressure", np.zeros_like(self.pressure))
+        r = self.inc.evolve(*a, incremental=True, **kw)
+        # DEpsilonf_ = symm(gradDDf_), DSigmaf_ = 2*muf_*DEpsilonf_ + I*(lambdaf_*tr(DEpsilonf_)) of the boundary faces, from the
+        # gradDDf the LAST outer iteration started with (:1013-1022 -- not re-formed after its solve)
+        g = self.inc.get("gradDfBStart").reshape(-1, 9)
+        eps = np.stack([g[:, 0], 0.5*(g[:, 1] + g[:, 3]), 0.5*(g[:, 2] + g[:, 6]), g[:, 4], 0.5*(g[:, 5] + g[:, 7]), g[:, 8]], axis=1)
+        lt = self.lambdafB*(eps[:, 0] + eps[:, 3] + eps[:, 5])
+        two = (2*self.mufB)[:, None]*eps
+        sig = two.copy()
+        for k, one in ((0, 1.0), (1, 0.0), (2, 0.0), (3, 1.0), (4, 0.0), (5, 1.0)):
+            sig[:, k] = two[:, k] + one*lt
+        self.DEpsilonfB, self.DSigmafB = eps, sig
+        return r
+
+    def update_total_fields(self):
+        """updateTotalFields() (:1212-1233): one read of the increment fields per time step."""
+        i = self.inc
+        self.D = self.D + i.get("D").reshape(-1, 3); self.pointD = self.pointD + i.get("pointD").reshape(-1, 3)
+        self.gradD = self.gradD + i.get("gradD").reshape(-1, 9); self.gradDf = self.gradDf + i.get("gradDf").reshape(-1, 9)
+        self.sigma = self.sigma + i.get("sigma").reshape(-1, 6); self.epsilon = self.epsilon + i.get("epsilon").reshape(-1, 6)
+        self.sigmafB = self.sigmafB + self.DSigmafB; self.epsilonfB = self.epsilonfB + self.DEpsilonfB
+
+    def close(self):
+        self.inc.close()

@@ -331,6 +331,9 @@ typedef struct gpupcg_eqn_controls
 #define GPUPCG_F_DBPREV         28
 #define GPUPCG_F_DOOO           29   /* D.oldTime().oldTime().oldTime()   (`backward` d2dt2)   */
 #define GPUPCG_F_DOOOO          30   /* ... and its oldTime()                                  */
+#define GPUPCG_F_GRADDFB_START  31   /* boundary rows of gradDf at the START of the last outer iteration [nBoundaryFaces*9]:
+                                        what DSigmaf_ of unsIncrTotalLagrangianStress::evolve() (:1013-1018) was built from
+                                        (incremental loop only)                                */
 int gpupcg_mesh_field_size(gpupcg_mesh m, int fieldId, long long* nDoubles);
 int gpupcg_mesh_set_field(gpupcg_mesh m, int fieldId, const double* host);
 int gpupcg_mesh_get_field(gpupcg_mesh m, int fieldId, double* host);
@@ -407,6 +410,11 @@ typedef struct gpupcg_evolve_controls
     int    validCmpt[3];                                    /* mesh.solutionD() != -1 per direction (2-D: one 0)  */
     double g[3];                                            /* stressProperties "g" (:806-810)                    */
     gpupcg_eqn_controls eqn;
+    int    incremental;                                     /* 1: the loop of unsIncrTotalLagrangianStress::evolve()
+                                                               (unsIncrTotalLagrangianStress.C:980-1159): the resident D is
+                                                               the increment DD; residual() = max|DD - DD.prevIter()| /
+                                                               (max|DD| + SMALL) (...Solve.C:695-716) and the loop runs
+                                                               while res > convergenceTolerance (:1155-1159)       */
 } gpupcg_evolve_controls;
 
 typedef struct gpupcg_evolve_result

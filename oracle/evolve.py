@@ -222,7 +222,10 @@ class SolidCase(object):
 
     def evolve(self, nCorrectors, convergenceTolerance, relConvergenceTolerance=0.0, tolerance=1e-9, relTol=0.01,
                d2dt2="steadyState", ddt="steadyState", deltaT=1.0, deltaT0=None, K=0.0, nonLinear=False, thermal=False,
-               limitCoeff=1.0, relaxD=None, maxIter=1000):
+               limitCoeff=1.0, relaxD=None, maxIter=1000, incremental=False):
+        """incremental: the loop of unsIncrTotalLagrangianStress::evolve() (unsIncrTotalLagrangianStress.C:980-1159) -- this
+        object's D is the increment DD (IncrSolidCase below): residual() = max|DD - DD.prevIter()|/(max|DD| + SMALL)
+        (unsIncrTotalLagrangianStressSolve.C:695-716), loop while res > convergenceTolerance (:1155-1159)."""
         mesh, geom, pt = self.mesh, self.geom, self.patchTypes
         nIF = mesh.nInternalFaces
         self.enforceLinear = False                      # evolve() resets it (:812-813)
@@ -230,6 +233,8 @@ class SolidCase(object):
         hist, initialResidual, lastInit, totalIts, pcgIts = [], 0.0, 0.0, 0, []
         while True:
             Dprev = self.D.copy(); DbPrev = self.Db.copy()
+            if incremental:
+                self.gradDfBStart = self.gradDf[nIF:].copy()        # what DSigmaf_ (:1013-1018) is formed from in this iteration
             bw = None
             if "backward" in (d2dt2, ddt):
                 bw = self._backward(d2dt2, ddt, K > 1e-15, deltaT if deltaT0 is None else deltaT0)
@@ -257,7 +262,7 @@ class SolidCase(object):
             self.Db = orc.patch_evaluate(mesh, geom, pt, self.D, self.gradD, self.fixedValue, self.patchGradient, self.Db)
             if relaxD is not None:
                 orc.relax_boundary(self.Db, DbPrev, relaxD)
-            res = orc.relax_residual(self.D, Dprev, self.Dold, relaxD)
+            res = orc.relax_residual(self.D, Dprev, np.zeros_like(self.D) if incremental else self.Dold, relaxD)
             self.pointD = self.lsq.interpolate(self.D, self.Db)
             if self.pointConstraints is not None:
                 orc.point_constraints_apply(self.pointConstraints, self.pointD)
@@ -273,7 +278,7 @@ class SolidCase(object):
             maxRes = max(maxRes, res)
             cur = max(maxRes*relConvergenceTolerance, convergenceTolerance)
             hist.append(res)
-            if not (res > cur):
+            if not (res > (convergenceTolerance if incremental else cur)):
                 break
             iCorr += 1
             if not (iCorr < nCorrectors):
@@ -293,3 +298,73 @@ class SolidCase(object):
         return dict(nOuterIterations=iCorr, initialResidual=initialResidual, lastSolverInitialResidual=lastInit, maxRes=maxRes,
                     res=res, totalPcgIterations=totalIts, pcgIterations=pcgIts, residualHistory=np.array(hist),
                     enforceLinear=self.enforceLinear, converged=not (nonLinear and self.enforceLinear))
+
+
+def boundary_normals(mesh, geom):
+    """patch().nf() [EXT fvPatch::nf]: Sf/magSf of the boundary faces."""
+    nIF = mesh.nInternalFaces
+    return geom.Sf[nIF:]/geom.magSf[nIF:, None]
+
+
+def vector_dot_symm(n, S):
+    """(n & S) for a vector and a symmTensor (xx xy xz yy yz zz) [EXT SymmTensorI.H operator&]: terms added x, y, z."""
+    return np.stack([n[:, 0]*S[:, 0] + n[:, 1]*S[:, 1] + n[:, 2]*S[:, 2],
+                     n[:, 0]*S[:, 1] + n[:, 1]*S[:, 3] + n[:, 2]*S[:, 4],
+                     n[:, 0]*S[:, 2] + n[:, 1]*S[:, 4] + n[:, 2]*S[:, 5]], axis=1)
+
+
+def face_stress_increment(muf, lambdaf, gradDDf):
+    """DEpsilonf_ = symm(gradDDf_); DSigmaf_ = 2*muf_*DEpsilonf_ + I*(lambdaf_*tr(DEpsilonf_))   (unsIncrTotalLagrangianStress.C:1013-1022,
+    linear branch).  gradDDf (n, 9) row-major; returns (DEpsilonf, DSigmaf) as symmTensors (n, 6)."""
+    g = gradDDf
+    eps = np.stack([g[:, 0], 0.5*(g[:, 1] + g[:, 3]), 0.5*(g[:, 2] + g[:, 6]), g[:, 4], 0.5*(g[:, 5] + g[:, 7]), g[:, 8]], axis=1)
+    tr = eps[:, 0] + eps[:, 3] + eps[:, 5]
+    lt = lambdaf*tr
+    two = (2*muf)[:, None]*eps
+    sig = two.copy()
+    for k, one in ((0, 1.0), (1, 0.0), (2, 0.0), (3, 1.0), (4, 0.0), (5, 1.0)):
+        sig[:, k] = two[:, k] + one*lt
+    return eps, sig
+
+
+class IncrSolidCase(object):
+    """unsIncrTotalLagrangianStress, linear branch without plasticity (stressModels/unsIncrTotalLagrangianStress/
+    unsIncrTotalLagrangianStress.C:946-1187, updateTotalFields :1212-1233; BC fvPatchFields/tractionDisplacementIncrement/
+    tractionDisplacementIncrementFvPatchVectorField.C:147-307): the increment DD is solved for with the equation of the total
+    model -- same laplacian, same explicit divergence, in gradDDf -- under the traction increment
+        DTraction = (traction - pressure*n) - (n & sigmaf)          (:203-233)
+    which makes tractionDisplacementIncrement's gradient() (:235-262) the total model's with DTraction as the traction and no
+    pressure; the loop differs in residual() and in its exit test (SolidCase.evolve(incremental=True)); updateTotalFields()
+    accumulates.  `inc` holds DD, pointDD, gradDD, gradDDf; the totals live here."""
+
+    def __init__(self, mesh, geom, patchTypes, mu, lam, rho, traction=None, pressure=None, fixedValue=None, **kw):
+        nC, nF, nIF = mesh.nCells, mesh.nFaces, mesh.nInternalFaces
+        nBF = nF - nIF
+        self.mesh, self.geom = mesh, geom
+        self.inc = SolidCase(mesh, geom, patchTypes, mu, lam, rho, fixedValue=fixedValue, **kw)
+        self.traction = np.zeros((nBF, 3)) if traction is None else np.asarray(traction, dtype=np.float64)
+        self.pressure = np.zeros(nBF) if pressure is None else np.asarray(pressure, dtype=np.float64)
+        own = mesh.owner[nIF:]
+        self.mufB, self.lambdafB = self.inc.mu[own].copy(), self.inc.lam[own].copy()        # boundary value of a linear interpolate
+        self.D = np.zeros((nC, 3)); self.pointD = np.zeros((mesh.nPoints, 3)); self.gradD = np.zeros((nC, 9))
+        self.gradDf = np.zeros((nF, 9)); self.sigma = np.zeros((nC, 6)); self.epsilon = np.zeros((nC, 6))
+        self.sigmafB = np.zeros((nBF, 6)); self.epsilonfB = np.zeros((nBF, 6))
+
+    def new_time_step(self):
+        self.inc.new_time_step()
+
+    def evolve(self, *a, **kw):
+        n = boundary_normals(self.mesh, self.geom)
+        t = self.traction - self.pressure[:, None]*n
+        self.inc.traction = t - vector_dot_symm(n, self.sigmafB)
+        self.inc.pressure = np.zeros_like(self.pressure)
+        r = self.inc.evolve(*a, incremental=True, **kw)
+        self.DEpsilonfB, self.DSigmafB = face_stress_increment(self.mufB, self.lambdafB, self.inc.gradDfBStart)
+        return r
+
+    def update_total_fields(self):
+        """updateTotalFields() (:1212-1233)."""
+        i = self.inc
+        self.D = self.D + i.D; self.pointD = self.pointD + i.pointD; self.gradD = self.gradD + i.gradD
+        self.gradDf = self.gradDf + i.gradDf; self.sigma = self.sigma + i.sigma; self.epsilon = self.epsilon + i.epsilon
+        self.sigmafB = self.sigmafB + self.DSigmafB; self.epsilonfB = self.epsilonfB + self.DEpsilonfB
