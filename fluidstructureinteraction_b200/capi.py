@@ -540,17 +540,21 @@ class GpuMesh(object):
         return out
 
     def assemble_scalar(self, sign, bfKind, bfValue, gammaCells=None, gammaFaces=None, ddt="steadyState", deltaT=1.0, rate=None,
-                        psiOld=None, phi=None, refCell=-1, refValue=0.0):
-        """gpupcg_assemble_scalar: TEqn (sign +1, Euler ddt, gammaCells) / pEqn (sign -1, gammaFaces, phi, reference cell)."""
+                        psiOld=None, phi=None, refCell=-1, refValue=0.0, psi=None, ls=None, limitCoeff=1.0):
+        """gpupcg_assemble_scalar: TEqn (sign +1, Euler ddt, gammaCells) / pEqn (sign -1, gammaFaces, phi, reference cell).
+        psi + ls = (lsP, lsN, lsB) (geometry.least_squares_vectors): with the explicit skewCorrected correction."""
         class Eqn(C.Structure):
             _fields_ = [("sign", C.c_int), ("gammaCells", c_double_p), ("gammaFaces", c_double_p), ("bfKind", c_int_p),
                         ("bfValue", c_double_p), ("ddtScheme", C.c_int), ("deltaT", C.c_double), ("rate", c_double_p),
-                        ("psiOld", c_double_p), ("phi", c_double_p), ("refCell", C.c_int), ("refValue", C.c_double)]
-        keep = [None if a is None else _f64(a) for a in (gammaCells, gammaFaces, bfValue, rate, psiOld, phi)]
+                        ("psiOld", c_double_p), ("phi", c_double_p), ("refCell", C.c_int), ("refValue", C.c_double),
+                        ("psi", c_double_p), ("lsP", c_double_p), ("lsN", c_double_p), ("lsB", c_double_p), ("limitCoeff", C.c_double)]
+        lsv = (None, None, None) if psi is None else ls
+        keep = [None if a is None else _f64(a) for a in (gammaCells, gammaFaces, bfValue, rate, psiOld, phi, psi, lsv[0], lsv[1], lsv[2])]
         kind = _i32(bfKind)
         ptr = lambda a: None if a is None else _dp(a)
         e = Eqn(int(sign), ptr(keep[0]), ptr(keep[1]), _ip(kind), ptr(keep[2]), 1 if ddt == "Euler" else 0, float(deltaT),
-                ptr(keep[3]), ptr(keep[4]), ptr(keep[5]), int(refCell), float(refValue))
+                ptr(keep[3]), ptr(keep[4]), ptr(keep[5]), int(refCell), float(refValue),
+                ptr(keep[6]), ptr(keep[7]), ptr(keep[8]), ptr(keep[9]), float(limitCoeff))
         nC, nIF, nBF = self.nC, self.nIF, self.nBF
         out = dict(upper=np.empty(nIF), diag=np.empty(nC), source=np.empty(nC), internalCoeffs=np.empty(max(nBF, 1)),
                    boundaryCoeffs=np.empty(max(nBF, 1)))

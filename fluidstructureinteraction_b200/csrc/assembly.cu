@@ -1535,6 +1535,8 @@ extern "C" int gpupcg_assemble_scalar(gpupcg_mesh m, const gpupcg_scalar_eqn* e,
     { m->err = "gpupcg_assemble_scalar: Euler ddt needs deltaT > 0, rate, psiOld and the (ddt - laplacian) form"; return GPUPCG_ERR_ARG; }
     if (nBF > 0 && (!e->bfKind || !e->bfValue)) { m->err = "gpupcg_assemble_scalar: NULL boundary tables"; return GPUPCG_ERR_ARG; }
     if (e->refCell >= nC) { m->err = "gpupcg_assemble_scalar: reference cell out of range"; return GPUPCG_ERR_ARG; }
+    if (e->psi && (!e->lsP || !e->lsN || (nBF > 0 && !e->lsB)))
+    { m->err = "gpupcg_assemble_scalar: the skewCorrected correction needs the least-squares vectors lsP, lsN, lsB"; return GPUPCG_ERR_ARG; }
     for (int bf = 0; bf < nBF; bf++)
         if (e->bfKind[bf] < 0 || e->bfKind[bf] > 1)
         { m->err = "gpupcg_assemble_scalar: boundary kind must be 0 (zeroGradient) or 1 (fixedValue)"; return GPUPCG_ERR_UNSUPPORTED; }
@@ -1561,10 +1563,23 @@ extern "C" int gpupcg_assemble_scalar(gpupcg_mesh m, const gpupcg_scalar_eqn* e,
     SCK(dev((void**)&dKind, sizeof(int)*nBF, e->bfKind)); SCK(dev((void**)&dVal, sizeof(double)*nBF, e->bfValue));
     if (e->ddtScheme == 1) { SCK(dev((void**)&dRate, sizeof(double)*nC, e->rate)); SCK(dev((void**)&dOld, sizeof(double)*nC, e->psiOld)); }
     if (e->phi) SCK(dev((void**)&dPhi, sizeof(double)*nF, e->phi));
+    double *dPsi = nullptr, *dLsP = nullptr, *dLsN = nullptr, *dLsB = nullptr, *dGrad = nullptr, *dCorr = nullptr;
+    if (e->psi)
+    {
+        SCK(dev((void**)&dPsi, sizeof(double)*nC, e->psi));
+        SCK(dev((void**)&dLsP, sizeof(double)*3*nIF, e->lsP)); SCK(dev((void**)&dLsN, sizeof(double)*3*nIF, e->lsN));
+        SCK(dev((void**)&dLsB, sizeof(double)*3*nBF, nBF ? e->lsB : nullptr));
+        SCK(dev((void**)&dGrad, sizeof(double)*3*nC, nullptr)); SCK(dev((void**)&dCorr, sizeof(double)*nIF, nullptr));
+    }
     const ScalarEqnDev E{e->sign, e->ddtScheme, e->ddtScheme == 1 ? 1.0/e->deltaT : 0.0, onFaces ? 1 : 0};
     SCK(cudaEventRecord(m->ev0, s));
     k_sc_faces<<<agrid(m, nF), ATPB, 0, s>>>(M, E, dGamma, dGms, dLup, dUp);
-    k_sc_cells<<<agrid(m, nC), ATPB, 0, s>>>(M, E, dLup, dRate, dOld, dPhi, dDg, dSrc);
+    if (e->psi)
+    {
+        k_sc_lsgrad<<<agrid(m, nC), ATPB, 0, s>>>(M, dPsi, dKind, dVal, dLsP, dLsN, dLsB, dGrad);
+        if (nIF > 0) k_sc_corr_faces<<<agrid(m, nIF), ATPB, 0, s>>>(M, dGms, dPsi, dGrad, e->limitCoeff, dCorr);
+    }
+    k_sc_cells<<<agrid(m, nC), ATPB, 0, s>>>(M, E, dLup, dRate, dOld, dPhi, dDg, dSrc, dCorr);
     if (nBF > 0) k_sc_patches<<<agrid(m, nBF), ATPB, 0, s>>>(M, E, dKind, dVal, dGms, dIc, dBc);
     if (e->refCell >= 0) k_sc_reference<<<1, 32, 0, s>>>(e->refCell, e->refValue, dDg, dSrc);
     SCK(cudaEventRecord(m->ev1, s));

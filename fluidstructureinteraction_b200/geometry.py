@@ -89,3 +89,46 @@ def compute(mesh):
     dc[nIF:] = 1.0/np.sqrt(np.sum(db*db, axis=1))
     g.deltaCoeffs = dc
     return g
+
+
+def least_squares_vectors(mesh, g, emptyPatches=()):
+    """[EXT] leastSquaresVectors::makeLeastSquaresVectors -- mesh data like weights / deltaCoeffs, an INPUT of the scalar
+    `skewCorrected` correction (its gradient scheme `snGradCorr(T) leastSquares`, run/thermalStressFoam/flange/system/fvSchemes):
+        dd[cell] += (1/magSqr(d)) sqr(d) over the cell's faces, d = C[nei] - C[own] (internal) or Cf - C[own] (boundary);
+        lsP[f] = (1/magSqr(d)) (inv(dd[own]) & d),  lsN[f] = -(1/magSqr(d)) (inv(dd[nei]) & d),  lsB likewise for boundary faces.
+    Faces of `empty` patches take no part (3-D meshes: dd is invertible).  Returns lsP (nIF,3), lsN (nIF,3), lsB (nBF,3)."""
+    own, nei = mesh.owner.astype(np.int64), mesh.neighbour.astype(np.int64)
+    nC, nF, nIF = mesh.nCells, mesh.nFaces, mesh.nInternalFaces
+    keep = np.ones(nF - nIF, dtype=bool)
+    for p in mesh.patches:
+        if p["name"] in emptyPatches:
+            keep[p["start"] - nIF:p["start"] - nIF + p["size"]] = False
+
+    def sqr_over_magsqr(d):
+        w = 1.0/np.sum(d*d, axis=1)
+        return w, np.stack([d[:, 0]*d[:, 0], d[:, 0]*d[:, 1], d[:, 0]*d[:, 2], d[:, 1]*d[:, 1], d[:, 1]*d[:, 2], d[:, 2]*d[:, 2]], axis=1)*w[:, None]
+
+    dI = g.C[nei] - g.C[own[:nIF]]
+    wI, sI = sqr_over_magsqr(dI)
+    dB = g.Cf[nIF:] - g.C[own[nIF:]]
+    wB, sB = sqr_over_magsqr(dB)
+    dd = np.zeros((nC, 6))
+    np.add.at(dd, own[:nIF], sI)
+    np.add.at(dd, nei, sI)
+    np.add.at(dd, own[nIF:][keep], sB[keep])
+    xx, xy, xz, yy, yz, zz = (dd[:, k] for k in range(6))
+    det = xx*yy*zz + xy*yz*xz + xz*xy*yz - xx*yz*yz - xy*xy*zz - xz*yy*xz
+    if np.any(np.abs(det) < 1e-30):
+        raise ValueError("singular least-squares tensor (2-D mesh?): not handled")
+    inv = np.stack([yy*zz - yz*yz, xz*yz - xy*zz, xy*yz - xz*yy, xx*zz - xz*xz, xy*xz - xx*yz, xx*yy - xy*xy], axis=1)/det[:, None]
+
+    def sym_dot(S, v):
+        return np.stack([S[:, 0]*v[:, 0] + S[:, 1]*v[:, 1] + S[:, 2]*v[:, 2],
+                         S[:, 1]*v[:, 0] + S[:, 3]*v[:, 1] + S[:, 4]*v[:, 2],
+                         S[:, 2]*v[:, 0] + S[:, 4]*v[:, 1] + S[:, 5]*v[:, 2]], axis=1)
+
+    lsP = wI[:, None]*sym_dot(inv[own[:nIF]], dI)
+    lsN = -wI[:, None]*sym_dot(inv[nei], dI)
+    lsB = wB[:, None]*sym_dot(inv[own[nIF:]], dB)
+    lsB[~keep] = 0.0
+    return np.ascontiguousarray(lsP), np.ascontiguousarray(lsN), np.ascontiguousarray(lsB)

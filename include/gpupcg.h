@@ -375,8 +375,9 @@ int gpupcg_sigma_resident(gpupcg_mesh m, const gpupcg_eqn_controls* controls);
  *         pEqn.setReference(pRefCell, pRefValue)  -> sign -1, gammaFaces, phi [nFaces], refCell / refValue
  * [EXT] gaussLaplacianScheme::fvmLaplacianUncorrected, EulerDdtScheme::fvmDdt, surfaceIntegrate, setReference, in the reference's
  * loop order (bit-exact against oracle/fvm_oracle.c: orc_assemble_scalar).  Boundary faces: bfKind 0 zeroGradient, 1 fixedValue
- * (bfValue); faces of `empty` patches of the mesh handle take no part.  Orthogonal part only: the explicit correction of the
- * scalar `skewCorrected` scheme (skewCorrectedSnGrad.C:197-245, least-squares gradient) is not built.  Outputs in LDU numbering,
+ * (bfValue); faces of `empty` patches of the mesh handle take no part.  The explicit correction of the scalar `skewCorrected`
+ * scheme (skewCorrectedSnGrad.C:57-294, least-squares gradient) is added when psi and the least-squares vectors are given
+ * (3-D meshes, non-coupled patches).  Outputs in LDU numbering,
  * ready for gpupcg_set_matrix / gpupcg_solve after fvMatrix's addBoundaryDiag / addBoundarySource (any may be NULL).            */
 typedef struct gpupcg_scalar_eqn
 {
@@ -392,6 +393,14 @@ typedef struct gpupcg_scalar_eqn
     const double* phi;                  /* [nFaces] face flux of the explicit divergence, or NULL                               */
     int           refCell;              /* setReference: -1 none                                                                */
     double        refValue;
+    /* the explicit correction of `Gauss linear skewCorrected <limitCoeff>` (numerics/skewCorrectedSnGrad/skewCorrectedSnGrad.C:
+     * 57-294 with the gradient scheme snGradCorr(psi) leastSquares; [EXT] gaussLaplacianScheme: source -= V*div(gammaMagSf*corr)):
+     * psi != NULL switches it on                                                                                                  */
+    const double* psi;                  /* [nCells] the current field                                                           */
+    const double* lsP;                  /* [nInternalFaces*3] leastSquaresVectors::pVectors()                                   */
+    const double* lsN;                  /* [nInternalFaces*3] leastSquaresVectors::nVectors()                                   */
+    const double* lsB;                  /* [nBoundaryFaces*3] the patch fields of pVectors()                                    */
+    double        limitCoeff;
 } gpupcg_scalar_eqn;
 int gpupcg_assemble_scalar(gpupcg_mesh m, const gpupcg_scalar_eqn* eqn, double* upper, double* diag, double* source,
                            double* internalCoeffs, double* boundaryCoeffs, double* kernel_ms);

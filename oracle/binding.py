@@ -501,8 +501,12 @@ def point_constraints_apply(pc, pointD):
 
 
 def assemble_scalar(mesh, geom, patchTypes, sign, bfKind, bfValue, gammaCells=None, gammaFaces=None, ddt="steadyState", deltaT=1.0,
-                    rate=None, psiOld=None, phi=None, refCell=-1, refValue=0.0):
-    """orc_assemble_scalar: TEqn / pEqn forms (see fvm_oracle.c).  Returns dict(upper, diag, source, internalCoeffs, boundaryCoeffs)."""
+                    rate=None, psiOld=None, phi=None, refCell=-1, refValue=0.0, psi=None, ls=None, limitCoeff=1.0):
+    """orc_assemble_scalar: TEqn / pEqn forms (see fvm_oracle.c).  Returns dict(upper, diag, source, internalCoeffs, boundaryCoeffs).
+    psi + ls = (lsP, lsN, lsB): with the explicit skewCorrected correction (least-squares gradient of psi)."""
+    if psi is not None:
+        return _assemble_scalar_corrected(mesh, geom, patchTypes, sign, bfKind, bfValue, gammaCells, gammaFaces, ddt, deltaT, rate,
+                                          psiOld, phi, refCell, refValue, psi, ls, limitCoeff)
     lib = load()
     M, keep = _mesh_struct(mesh, geom, patchTypes)
     nC, nIF, nBF = mesh.nCells, mesh.nInternalFaces, mesh.nFaces - mesh.nInternalFaces
@@ -515,4 +519,24 @@ def assemble_scalar(mesh, geom, patchTypes, sign, bfKind, bfValue, gammaCells=No
                                         dp, dp, dp, dp, dp]
     lib.orc_assemble_scalar(C.byref(M), int(sign), _odp(a[0]), _odp(a[1]), _ip(kind), _dp(val), 1 if ddt == "Euler" else 0, float(deltaT),
                             _odp(b[0]), _odp(b[1]), _odp(b[2]), int(refCell), float(refValue), _dp(upper), _dp(diag), _dp(source), _dp(ic), _dp(bc))
+    return dict(upper=upper, diag=diag, source=source, internalCoeffs=ic[:nBF], boundaryCoeffs=bc[:nBF])
+
+
+def _assemble_scalar_corrected(mesh, geom, patchTypes, sign, bfKind, bfValue, gammaCells, gammaFaces, ddt, deltaT, rate, psiOld, phi,
+                               refCell, refValue, psi, ls, limitCoeff):
+    lib = load()
+    M, keep = _mesh_struct(mesh, geom, patchTypes)
+    nC, nIF, nBF = mesh.nCells, mesh.nInternalFaces, mesh.nFaces - mesh.nInternalFaces
+    upper = np.empty(nIF); diag = np.empty(nC); source = np.empty(nC); ic = np.empty(max(nBF, 1)); bc = np.empty(max(nBF, 1))
+    kind = _i(bfKind); val = _f(bfValue)
+    a = [_opt(v) for v in (gammaCells, gammaFaces)]
+    b = [_opt(v) for v in (rate, psiOld, phi)]
+    c = [_f(psi), _f(ls[0]), _f(ls[1]), _f(ls[2])]
+    lib.orc_assemble_scalar_corrected.restype = None
+    lib.orc_assemble_scalar_corrected.argtypes = [C.POINTER(Mesh), C.c_int, dp, dp, ip, dp, C.c_int, C.c_double, dp, dp, dp, C.c_int,
+                                                  C.c_double, dp, dp, dp, dp, C.c_double, dp, dp, dp, dp, dp]
+    lib.orc_assemble_scalar_corrected(C.byref(M), int(sign), _odp(a[0]), _odp(a[1]), _ip(kind), _dp(val), 1 if ddt == "Euler" else 0,
+                                      float(deltaT), _odp(b[0]), _odp(b[1]), _odp(b[2]), int(refCell), float(refValue),
+                                      _dp(c[0]), _dp(c[1]), _dp(c[2]), _dp(c[3]), float(limitCoeff),
+                                      _dp(upper), _dp(diag), _dp(source), _dp(ic), _dp(bc))
     return dict(upper=upper, diag=diag, source=source, internalCoeffs=ic[:nBF], boundaryCoeffs=bc[:nBF])

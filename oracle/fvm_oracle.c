@@ -1447,9 +1447,80 @@ void orc_point_constraints(int n, const int* point, const int* start, const int*
 /*  [EXT] gaussLaplacianScheme::fvmLaplacianUncorrected, lduMatrix::negSumDiag, EulerDdtScheme::fvmDdt,        */
 /*  fvMatrix operator*(volScalarField), operator==, fvc::surfaceIntegrate, fvMatrix::setReference              */
 /* ======================================================================================================== */
+/*  The explicit correction of `laplacian(gamma,psi) Gauss linear skewCorrected <limitCoeff>` for a scalar                 */
+/*  (numerics/skewCorrectedSnGrad/skewCorrectedSnGrad.C:57-294, non-coupled patches): per internal face                   */
+/*     kP = Cf - C[own]; kP -= Sf*(Sf & kP)/sqr(magSf); kN likewise                                        (:137-141)    */
+/*     corr = ((kN & grad[nei]) - (kP & grad[own]))*deltaCoeffs, grad = the gradScheme named snGradCorr(psi) (:197-222)  */
+/*     limiter = min(limitCoeff*mag(orthSnGrad + corr)/((1 - limitCoeff)*mag(corr) + SMALL), 1); corr *= limiter (:255-288)*/
+/*  and [EXT] gaussLaplacianScheme::fvmLaplacian: fvm.source() -= V*fvc::div(gammaMagSf*corr).                            */
+/*  grad = [EXT] leastSquaresGrad: lsGrad[own] += ownLs[f]*(psi[nei] - psi[own]); lsGrad[nei] -= neiLs[f]*(...), faces    */
+/*  ascending, then the patches: lsGrad[faceCells] += patchLs*(psi_b - psi[faceCells]) (psi_b: the fixed value, or the    */
+/*  cell value on zeroGradient patches).  The least-squares vectors are mesh data (leastSquaresVectors::pVectors() /      */
+/*  nVectors()), an INPUT here as weights and deltaCoeffs are.  Lsrc[c] = 0 - V*div(gms*corr)[c] is returned in `lsrc`.   */
+static void scalar_skew_correction(const orc_mesh* M, const unsigned char* emptyFace, const double* gms, const int* bfKind,
+                                   const double* bfValue, const double* psi, const double* lsP, const double* lsN,
+                                   const double* lsB, double limitCoeff, double* lsrc)
+{
+    const int nC = M->nCells, nF = M->nFaces, nIF = M->nInternalFaces;
+    double* g = (double*)calloc(3*(size_t)(nC > 0 ? nC : 1), sizeof(double));
+    double* div = (double*)calloc(nC > 0 ? nC : 1, sizeof(double));
+    for (int f = 0; f < nIF; f++)
+    {
+        const int P = M->owner[f], N = M->neighbour[f];
+        const double d = psi[N] - psi[P];
+        for (int k = 0; k < 3; k++) { g[3*P + k] += lsP[3*f + k]*d; g[3*N + k] -= lsN[3*f + k]*d; }
+    }
+    for (int f = nIF; f < nF; f++)
+    {
+        if (emptyFace[f]) continue;
+        const int bf = f - nIF, P = M->owner[f];
+        const double pb = bfKind[bf] == 1 ? bfValue[bf] : psi[P];
+        const double d = pb - psi[P];
+        for (int k = 0; k < 3; k++) g[3*P + k] += lsB[3*bf + k]*d;
+    }
+    for (int f = 0; f < nIF; f++)
+    {
+        const int P = M->owner[f], N = M->neighbour[f];
+        const double* Sf = M->Sf + 3*f;
+        const double m2 = M->magSf[f]*M->magSf[f];
+        double kP[3], kN[3];
+        for (int k = 0; k < 3; k++) { kP[k] = M->Cf[3*f + k] - M->C[3*P + k]; kN[k] = M->Cf[3*f + k] - M->C[3*N + k]; }
+        const double sP = Sf[0]*kP[0] + Sf[1]*kP[1] + Sf[2]*kP[2];
+        for (int k = 0; k < 3; k++) kP[k] -= (Sf[k]*sP)/m2;
+        const double sN = Sf[0]*kN[0] + Sf[1]*kN[1] + Sf[2]*kN[2];
+        for (int k = 0; k < 3; k++) kN[k] -= (Sf[k]*sN)/m2;
+        const double a = kN[0]*g[3*N] + kN[1]*g[3*N + 1] + kN[2]*g[3*N + 2];
+        const double b = kP[0]*g[3*P] + kP[1]*g[3*P + 1] + kP[2]*g[3*P + 2];
+        double corr = (a - b)*M->deltaCoeffs[f];
+        const double orth = M->deltaCoeffs[f]*(psi[N] - psi[P]);
+        double lim = limitCoeff*fabs(orth + corr)/((1 - limitCoeff)*fabs(corr) + ORC_SMALL);
+        if (lim > 1.0) lim = 1.0;
+        corr *= lim;
+        const double flux = gms[f]*corr;
+        div[P] += flux; div[N] -= flux;
+    }
+    for (int c = 0; c < nC; c++) lsrc[c] = 0.0 - M->V[c]*(div[c]/M->V[c]);
+    free(g); free(div);
+}
+
 void orc_assemble_scalar(const orc_mesh* M, int sign, const double* gammaCells, const double* gammaFaces, const int* bfKind,
                          const double* bfValue, int ddtScheme, double deltaT, const double* rate, const double* psiOld,
                          const double* phi, int refCell, double refValue,
+                         double* upper, double* diag, double* source, double* internalCoeffs, double* boundaryCoeffs)
+{
+    void orc_assemble_scalar_corrected(const orc_mesh*, int, const double*, const double*, const int*, const double*, int, double,
+                                       const double*, const double*, const double*, int, double, const double*, const double*,
+                                       const double*, const double*, double, double*, double*, double*, double*, double*);
+    orc_assemble_scalar_corrected(M, sign, gammaCells, gammaFaces, bfKind, bfValue, ddtScheme, deltaT, rate, psiOld, phi, refCell,
+                                  refValue, NULL, NULL, NULL, NULL, 1.0, upper, diag, source, internalCoeffs, boundaryCoeffs);
+}
+
+/* psi != NULL: with the explicit skewCorrected correction (psi = the current field, lsP / lsN [nInternalFaces*3], lsB
+ * [nBoundaryFaces*3] the least-squares vectors) */
+void orc_assemble_scalar_corrected(const orc_mesh* M, int sign, const double* gammaCells, const double* gammaFaces, const int* bfKind,
+                         const double* bfValue, int ddtScheme, double deltaT, const double* rate, const double* psiOld,
+                         const double* phi, int refCell, double refValue,
+                         const double* psi, const double* lsP, const double* lsN, const double* lsB, double limitCoeff,
                          double* upper, double* diag, double* source, double* internalCoeffs, double* boundaryCoeffs)
 {
     const int nC = M->nCells, nF = M->nFaces, nIF = M->nInternalFaces;
@@ -1484,15 +1555,18 @@ void orc_assemble_scalar(const orc_mesh* M, int sign, const double* gammaCells, 
         for (int f = nIF; f < nF; f++) if (!emptyFace[f]) div[M->owner[f]] += phi[f];
         for (int c = 0; c < nC; c++) div[c] /= M->V[c];
     }
+    double* lsrc = (double*)calloc(nC > 0 ? nC : 1, sizeof(double));        /* source of the laplacian matrix: 0, or -V*div(correction) */
+    if (psi) scalar_skew_correction(M, emptyFace, gms, bfKind, bfValue, psi, lsP, lsN, lsB, limitCoeff, lsrc);
     const double rDeltaT = ddtScheme == 1 ? 1.0/deltaT : 0.0;
     for (int c = 0; c < nC; c++)
     {
         const double V = M->V[c];
         double dA = 0.0, sA = 0.0;
         if (ddtScheme == 1) { dA = (rDeltaT*V)*rate[c]; sA = ((rDeltaT*psiOld[c])*V)*rate[c]; }
-        if (sign > 0) { diag[c] = dA - Ldiag[c]; source[c] = sA - 0.0; }
-        else { diag[c] = Ldiag[c]; source[c] = phi ? 0.0 + V*div[c] : 0.0; }
+        if (sign > 0) { diag[c] = dA - Ldiag[c]; source[c] = sA - lsrc[c]; }
+        else { diag[c] = Ldiag[c]; source[c] = phi ? lsrc[c] + V*div[c] : lsrc[c]; }
     }
+    free(lsrc);
     for (int f = 0; f < nIF; f++) upper[f] = sign > 0 ? 0.0 - Lupper[f] : Lupper[f];
     for (int f = nIF; f < nF; f++)
     {
