@@ -331,3 +331,31 @@ def three_k(E, nu, rho, planeStress=False):
 # run/thermalStressFoam/flange: constant/thermalProperties:17-24, constant/rheologyProperties, 0/T, system/controlDict (config 4)
 FLANGE = dict(E=2.0e11, nu=0.3, rho=7800.0, C=500.0, k=50.0, alpha=1.0e-6, T0=0.0, Tcold=273.0, Thot=573.0, deltaT=0.01,
               nCorrectors=1000, convergenceTolerance=1e-5, relaxD=0.5)
+
+
+def flange_case(polymeshNpz):
+    """The mesh of config 4 (run/thermalStressFoam/flange: flange.ans through ansys.ans_to_polymesh) with what the case records of
+    its boundary.  `ansys.boundary_surfaces` recovers patch2 (348 faces, the flat face y = -7.5, T = 273) and patch4 (384 faces, the
+    central bore, T = 573) by their sizes; T is zeroGradient on the rest (patch1, patch3), so the T equation can run with its
+    SHIPPED boundary conditions.  For D the shipped split of the remaining faces into patch1 (traction-free) and patch3 (96
+    faces, fixedDisplacement) is not recorded: the two bolt holes (2 x 144 faces) stand in for the fixed patch.
+    Returns (mesh with patches cold / hot / fixed / free, geometry, T boundary kind, T boundary value, D patch types)."""
+    import numpy as np
+    from . import ansys, geometry, meshes
+    m = meshes.PolyMesh.load_npz(polymeshNpz)
+    g = geometry.compute(m)
+    nIF = m.nInternalFaces
+    lab, sizes = ansys.boundary_surfaces(m, g)
+    sizes = np.asarray(sizes)
+    cold, hot = int(np.flatnonzero(sizes == 348)[0]), int(np.flatnonzero(sizes == 384)[0])
+    holes = [int(s) for s in np.flatnonzero(sizes == 144) if abs(g.Cf[nIF:][lab == s][:, 0].mean()) > 10.0]
+    if len(holes) != 2:
+        raise ValueError("flange: bolt holes not found")
+    label = np.full(lab.shape, 3)
+    label[lab == cold] = 0; label[lab == hot] = 1; label[np.isin(lab, holes)] = 2
+    m2, order = m.repatch(label, ["cold", "hot", "fixed", "free"])
+    g2 = geometry.compute(m2)
+    kind = np.where(label[order] <= 1, 1, 0).astype(np.int32)
+    val = np.where(label[order] == 1, FLANGE["Thot"], FLANGE["Tcold"]).astype(np.float64)
+    pt = {"cold": "tractionDisplacement", "hot": "tractionDisplacement", "fixed": "fixedDisplacement", "free": "tractionDisplacement"}
+    return m2, g2, kind, val, pt

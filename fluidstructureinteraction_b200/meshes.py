@@ -52,6 +52,23 @@ class PolyMesh(object):
             p = self.patch(p)
         return self.owner[p["start"]:p["start"] + p["size"]]
 
+    def repatch(self, labels, names):
+        """[EXT autoPatch / createPatch-like] a mesh with the boundary faces regrouped: labels[bf] in 0..len(names)-1 per boundary
+        face; the faces of a new patch keep their relative order.  Returns (mesh, old boundary-face index of every new one)."""
+        nIF, nF = self.nInternalFaces, self.nFaces
+        labels = np.asarray(labels, dtype=np.int64)
+        order = np.argsort(labels, kind="stable")
+        idx = np.concatenate([np.arange(nIF), nIF + order])
+        cnt = np.diff(self.faceStart)[idx]
+        fs = np.concatenate([[0], np.cumsum(cnt)])
+        fp = np.concatenate([self.facePoints[self.faceStart[f]:self.faceStart[f + 1]] for f in idx]) if nF else self.facePoints
+        sizes = np.bincount(labels, minlength=len(names))
+        patches, start = [], nIF
+        for n, sz in zip(names, sizes):
+            patches.append(dict(name=n, type="patch", start=int(start), size=int(sz)))
+            start += int(sz)
+        return PolyMesh(self.points, fs, fp, self.owner[idx], self.neighbour, patches, self.nCells), order
+
     def is_upper_triangular(self):
         l, u = self.lower_upper()
         if l.size == 0:

@@ -202,6 +202,15 @@ class SolidCase(object):
         self.l = np.ascontiguousarray(mesh.owner[:nIF], dtype=np.int32)
         self.u = np.ascontiguousarray(mesh.neighbour, dtype=np.int32)
 
+    @staticmethod
+    def _tie(perf, hist, tolerance, relTol):
+        """How close the stopping test of a PCG solve came to going the other way: the smallest relative distance of the residuals
+        of its last two iterations from the bound they were compared with (max(tolerance, relTol*initialResidual)).  A solver
+        whose sums are associated differently can stop one iteration earlier or later only where this is ~1e-12."""
+        bound = max(tolerance, relTol*perf["initialResidual"])
+        h = np.asarray(hist)[-2:] if len(hist) else np.array([perf["initialResidual"]])
+        return float(np.min(np.abs(h - bound))/bound) if bound > 0 else 1.0
+
     def new_time_step(self):
         """runTime++ : storeOldTimes of D."""
         self.Doldold = self.Dold
@@ -230,7 +239,7 @@ class SolidCase(object):
         nIF = mesh.nInternalFaces
         self.enforceLinear = False                      # evolve() resets it (:812-813)
         iCorr, res, maxRes = 0, 1.0, 0.0
-        hist, initialResidual, lastInit, totalIts, pcgIts = [], 0.0, 0.0, 0, []
+        hist, initialResidual, lastInit, totalIts, pcgIts, pcgTies = [], 0.0, 0.0, 0, [], []
         while True:
             Dprev = self.D.copy(); DbPrev = self.Db.copy()
             if incremental:
@@ -255,6 +264,7 @@ class SolidCase(object):
                                                       tolerance, relTol, self.validCmpts, maxIter)
             totalIts += sum(p["nIterations"] for p in perfs.values())
             pcgIts.append([perfs[k]["nIterations"] for k in sorted(perfs)])
+            pcgTies.append([self._tie(perfs[k], hists[k], tolerance, relTol) for k in sorted(perfs)])
             if iCorr == 0:
                 initialResidual = worst["initialResidual"]
             lastInit = worst["initialResidual"]
@@ -296,7 +306,7 @@ class SolidCase(object):
             self.U = orc.ddt(self.D, self.Dold, ddt, deltaT)
         self.epsilon, self.sigma = orc.sigma_ex(self.mu, self.lam, self.gradD, nonLinear, thermal, self.threeK, self.alpha, self.DT)
         return dict(nOuterIterations=iCorr, initialResidual=initialResidual, lastSolverInitialResidual=lastInit, maxRes=maxRes,
-                    res=res, totalPcgIterations=totalIts, pcgIterations=pcgIts, residualHistory=np.array(hist),
+                    res=res, totalPcgIterations=totalIts, pcgIterations=pcgIts, pcgStopMargin=pcgTies, residualHistory=np.array(hist),
                     enforceLinear=self.enforceLinear, converged=not (nonLinear and self.enforceLinear))
 
 

@@ -22,6 +22,10 @@ def _mesh(kind):
         m = meshes.tet_box(5, 3, 4, jitter=0.15); pt = dict(PT3)
     elif kind == "2d":
         m = meshes.hex_box(12, 6, 1, split_free=True); pt = dict(PT2D)
+    elif kind == "flange":          # the imported mesh of config 4: hexes and prisms, faces up to 44 degrees off orthogonality
+        import os
+        m, g, _, _, pt = cases.flange_case(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "flange.polymesh.npz"))
+        return m, g, pt
     else:
         raise KeyError(kind)
     return m, geometry.compute(m), pt
@@ -142,7 +146,7 @@ def _check_resident_chain(m, g, pt, branch, scale, lsq_data=None):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind", ["hexsym", "tet", "2d"])
+@pytest.mark.parametrize("kind", ["hexsym", "tet", "2d", "flange"])
 @pytest.mark.parametrize("branch", range(len(BRANCHES)))
 def test_gpu_resident_assembly_every_branch_bit_exact(kind, branch):
     m, g, pt = _mesh(kind)

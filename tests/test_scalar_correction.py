@@ -137,3 +137,99 @@ def test_gpu_T_equation_with_the_correction_on_the_flange_mesh():
     assert 273.0 - 1e-6 <= Tc.min() and Tc.max() <= 573.0 + 30.0
     assert np.abs(Tc - T0).max() > 1.0                      # kelvin: the non-orthogonal correction matters on this mesh
     gm.close(); gs.close()
+
+
+def _flange_case():
+    m, g, kind, val, _ = cases.flange_case(os.path.join(GOLD, "flange.polymesh.npz"))
+    return m, g, kind, val
+
+
+def test_flange_boundary_surfaces_give_the_shipped_T_patches():
+    m, g, kind, val = _flange_case()
+    assert [p["size"] for p in m.patches] == [348, 384, 288, 3268 - 348 - 384 - 288]
+    assert (kind == 1).sum() == 348 + 384 and (val[kind == 1] == F["Thot"]).sum() == 384
+    assert m.is_upper_triangular() and np.all(g.V > 0)
+
+
+@pytest.mark.gpu
+def test_gpu_config_4_sequence_on_the_flange_mesh(monkeypatch):
+    """thermalStressFoam.C:60-80 on the real mesh of the shipped case: every time step the T equation (TEqn.H, Euler ddt,
+    `laplacian(k,T) Gauss linear skewCorrected 1` with its least-squares correction, shipped T boundary conditions), then
+    stress->evolve() with the thermal terms (Euler d2dt2 / ddt, skewCorrected 1, relaxation 0.5) -- both assembled and solved on
+    the GPU, against the oracle's restatement of the same sequence.
+
+    With the global sums formed in the reference's order (GPUPCG_ORDERED_SUMS) the whole chain is the oracle's: identical PCG
+    iteration counts in all 450 solves of an evolve() and fields equal to rounding.  (With the production tree reductions one
+    solve in ~450 stops an iteration earlier or later on this case: late in the relaxed outer loop the initial residual of a
+    solve is a difference of nearly equal numbers, and the oracle's own stopping margins there are 1e-6 ... 1e-3.)"""
+    import fluidstructureinteraction_b200 as pkg
+    from oracle import evolve as oev
+    from fluidstructureinteraction_b200.solid import GpuSolidCase
+    monkeypatch.setenv("GPUPCG_ORDERED_SUMS", "1")
+    m, g, kind, val = _flange_case()
+    ls = geometry.least_squares_vectors(m, g)
+    pt = {"cold": "tractionDisplacement", "hot": "tractionDisplacement", "fixed": "fixedDisplacement", "free": "tractionDisplacement"}
+    nIF = m.nInternalFaces
+    fc = m.owner[nIF:].astype(np.int64)
+    l, u = m.lower_upper()
+    mu, lam = cases.lame(F["E"], F["nu"])
+    threeK = cases.three_k(F["E"], F["nu"], F["rho"])
+    gm = pkg.GpuMesh(m, g, pt, device=0)
+    gs = pkg.GpuPCG(l, u, m.nCells, device=0)
+    dT = 2.0e4           # the shipped mesh is in millimetres read as metres: a time step on its diffusion time scale
+    rhoC = np.full(m.nCells, F["rho"]*F["C"]); kT = np.full(m.nCells, F["k"])
+
+    def t_step(asm, solve, T, Told):
+        """TEqn.H:1-31."""
+        iCorr, its = 0, []
+        while True:
+            Tprev = T.copy()
+            a = asm(sign=1, bfKind=kind, bfValue=val, gammaCells=kT, ddt="Euler", deltaT=dT, rate=rhoC, psiOld=Told, psi=T, ls=ls,
+                    limitCoeff=1.0)
+            diag = a["diag"].copy(); b = a["source"].copy()
+            np.add.at(diag, fc, a["internalCoeffs"]); np.add.at(b, fc, a["boundaryCoeffs"])
+            T = T.copy()
+            its.append(solve(diag, a["upper"], T, b))
+            rel = (np.abs(T - Tprev)/(np.abs(T - Told).max() + 1e-15)).max()
+            iCorr += 1
+            if not (rel > 1e-6 and iCorr < 10):
+                break
+        return T, its
+
+    def gsolve(diag, upper, x, b):
+        gs.set_matrix(diag, upper)
+        return gs.solve(x, b, tolerance=1e-8, relTol=0.0)[0]["nIterations"]
+
+    def osolve(diag, upper, x, b):
+        return oracle.pcg_solve(l, u, diag, upper, x, b, tolerance=1e-8, relTol=0.0)[0]["nIterations"]
+
+    ref = oev.SolidCase(m, g, pt, mu, lam, F["rho"], threeK=threeK, alpha=F["alpha"])
+    gc = GpuSolidCase(m, g, pt, mu, lam, F["rho"], threeK=threeK, alpha=F["alpha"])
+    Tg = Tc = np.full(m.nCells, F["Tcold"])
+    kw = dict(nCorrectors=150, convergenceTolerance=F["convergenceTolerance"], tolerance=1e-10, relTol=0.1, d2dt2="Euler", ddt="Euler",
+              deltaT=dT, thermal=True, relaxD=F["relaxD"])
+    for step in range(2):
+        Tg_old, Tc_old = Tg, Tc
+        Tg, ig = t_step(gm.assemble_scalar, gsolve, Tg, Tg_old)
+        Tc, ic = t_step(lambda **k: oracle.assemble_scalar(m, g, pt, **k), osolve, Tc, Tc_old)
+        assert ig == ic and len(ic) > 2 and np.abs(Tg - Tc).max() <= 1e-9*np.abs(Tc).max()
+
+        def dtb(T):
+            b = T[fc] - F["T0"]
+            b[kind == 1] = val[kind == 1] - F["T0"]
+            return b
+        # the D equation of both sides from the SAME temperature (the T fields agree to 1e-9, asserted above; 150 relaxed outer
+        # iterations on this mesh would carry that difference into the PCG iteration counts)
+        ref.DT, ref.DTb = Tg - F["T0"], dtb(Tg)
+        gc.set("DT", Tg - F["T0"]); gc.set("DTb", dtb(Tg))
+        ref.new_time_step(); gc.new_time_step()
+        r, rg = ref.evolve(**kw), gc.evolve(**kw)
+        assert rg["nOuterIterations"] == r["nOuterIterations"] and r["nOuterIterations"] > 10
+        pi, pg = np.array(r["pcgIterations"]), rg["pcgIterations"]
+        assert np.array_equal(pi, pg), (step, np.argwhere(pi != pg)[:5], np.array(r["pcgStopMargin"])[pi != pg][:5])
+        assert np.array_equal(r["residualHistory"], rg["residualHistory"])
+        for k in ("D", "pointD", "sigma", "U"):
+            a = getattr(ref, k); b = gc.get(k).reshape(a.shape)
+            assert np.abs(a - b).max() <= 1e-12*np.abs(a).max() + 1e-300, (step, k)
+    assert Tc.max() > 400.0 and np.abs(ref.D).max() > 0 and np.abs(ref.sigma).max() > 0
+    gm.close(); gs.close(); gc.close()
