@@ -552,6 +552,37 @@ def run_ours(args, nx, ny, nz):
             kb3 = kernel_bytes(n, nF, 3)
             kern_batched = {k: kernel_entry(g.time_kernel_vector(3, k, reps=reps, flushL2=True), 3, kb3[k], peak)
                             for k in ("amul", "dic", "p_update", "xr_update")}
+        in_flight = None
+        if concurrent and world == 1:
+            # what the device does DURING the step: the same kernel of the three systems in flight at once (three handles, three
+            # streams, three host threads -- as the step runs them); per-launch duration under that load and the aggregate rate
+            import threading
+            hs = []
+            for k in range(3):
+                hk = pkg.GpuPCG(s["l"], s["u"], nGlobal, device=local)
+                hk.set_matrix(diag, upper)
+                hs.append(hk)
+            in_flight = {}
+            kb1 = kernel_bytes(n, nF, 1)
+            for kname in ("dic", "amul"):
+                ts = [None]*3
+
+                def work(k, kname=kname, ts=ts):
+                    torch.cuda.set_device(local)
+                    ts[k] = hs[k].time_kernel(kname, reps=30, flushL2=False)
+                th = [threading.Thread(target=work, args=(k,)) for k in range(3)]
+                for t_ in th:
+                    t_.start()
+                for t_ in th:
+                    t_.join()
+                if all(t_ is not None for t_ in ts):
+                    tm = sum(ts)/3.0
+                    in_flight[kname] = {"systems_in_flight": 3, "ms_per_launch": tm, "algorithmic_bytes_per_launch": kb1[kname]["shared"],
+                                        "aggregate_achieved_gbs": 3*kb1[kname]["shared"]/tm/1e6,
+                                        "aggregate_frac": 3*kb1[kname]["shared"]/tm/1e6/peak,
+                                        "l2": "no flush: the three systems' working sets (3 x %.0f MB) exceed the 126 MB L2" % (kb1[kname]["shared"]/1e6)}
+            for hk in hs:
+                hk.close()
         if vector and not batched:
             g.set_matrix(diag, upper, patchBouCoeffs=bou)
         kern = {}
@@ -583,6 +614,9 @@ def run_ours(args, nx, ny, nz):
                  "systems_per_launch": nsys, "ms_per_launch": kern[k]["ms"], "share_of_iteration": kern[k]["share_of_iteration"]}
             if nsys > 1:
                 r["frac_as_independent_systems"] = kern[k]["frac_as_independent_systems"]
+            if in_flight and k in in_flight:
+                # `frac` above is the kernel of ONE system timed alone; in the step three of them are in flight
+                r["in_flight"] = in_flight[k]
             return r
 
         value = nGlobal*iters/(ms_dev*1e-3)
