@@ -963,10 +963,10 @@ static cudaError_t pencil_attr(size_t cap)
     cudaError_t e = cudaFuncSetAttribute((k_dic_pencil<NB, MODE, LONG, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
     if (!e && NB > 1)
         e = cudaFuncSetAttribute((k_dic_pencil<NB, MODE, LONG, NB>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
-    if (MODE == 0 && NB > 1)        // forward sweep carrying the x/r update (batched solves)
+    if (MODE == 0)                  // forward sweep carrying the x/r update
     {
         if (!e) e = cudaFuncSetAttribute((k_dic_pencil<NB, 0, LONG, 1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
-        if (!e) e = cudaFuncSetAttribute((k_dic_pencil<NB, 0, LONG, NB, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+        if (!e && NB > 1) e = cudaFuncSetAttribute((k_dic_pencil<NB, 0, LONG, NB, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
     }
     return e;
 }
@@ -997,7 +997,7 @@ static int launch_pencil(gpupcg_handle h, const double* diagOrRD, const double* 
                          double* rDout, double* partials, DevState* st, int gated, const FuseXR* fx = nullptr, int histStride = 0)
 {
     const bool withDot = (MODE == 2) && partials != nullptr;
-    const bool fuse = (MODE == 0) && NB > 1 && fx != nullptr && fx->x != nullptr;
+    const bool fuse = (MODE == 0) && fx != nullptr && fx->x != nullptr;
     PencilArgs A = h->pen;
     A.fxX = nullptr; A.fxPA = nullptr; A.fxWA = nullptr; A.fxRA = nullptr; A.fxHistory = nullptr; A.fxHistStride = 0;
     if (fuse) { A.fxX = fx->x; A.fxPA = fx->pA; A.fxWA = fx->wA; A.fxRA = fx->rA; A.fxHistory = fx->history; A.fxHistStride = histStride; }
@@ -1030,7 +1030,7 @@ static int launch_pencil(gpupcg_handle h, const double* diagOrRD, const double* 
         k_dic_pencil<NB, MODE, LONG_, SW_, FUSE_><<<grid, PEN_THREADS(SW_, FUSE_), smem, h->stream>>>(A, diagOrRD, rA, y, out, rDout, \
             h->dTileTicket, partials, h->partStride, st, gated); } while (0)
 #define PEN_DISPATCH(LONG_) do { \
-        if (MODE == 0 && NB > 1 && fuse) { if (split) PEN_RUN(LONG_, NB, (MODE == 0 && NB > 1)); else PEN_RUN(LONG_, 1, (MODE == 0 && NB > 1)); } \
+        if (MODE == 0 && fuse) { if (split) PEN_RUN(LONG_, NB, (MODE == 0)); else PEN_RUN(LONG_, 1, (MODE == 0)); } \
         else { if (split) PEN_RUN(LONG_, NB, false); else PEN_RUN(LONG_, 1, false); } } while (0)
     switch (h->plan.pLong)
     {
@@ -1089,7 +1089,14 @@ static int enqueue_sweeps(gpupcg_handle h, const double* rA, double* z, bool red
     if (h->pencil)
     {
         int rcp = pencil_coeffs(h); if (rcp) return rcp;
-        rcp = launch_pencil<1, 0>(h, h->dRD, rA, nullptr, yb, nullptr, nullptr, h->dState, gated); if (rcp) return rcp;
+        if (fuseXR)
+        {
+            // the pending x/r update of the previous iteration rides in the forward sweep (its update warp); S_XR follows
+            FuseXR fx{h->dX, h->dPA, zb, h->dRA, h->dHistory};
+            rcp = launch_pencil<1, 0>(h, h->dRD, rA, nullptr, yb, nullptr, h->dPartials, h->dState, gated, &fx, 0); if (rcp) return rcp;
+            rcp = allreduce_step(h, S_XR, 1); if (rcp) return rcp;
+        }
+        else { rcp = launch_pencil<1, 0>(h, h->dRD, rA, nullptr, yb, nullptr, nullptr, h->dState, gated); if (rcp) return rcp; }
         rcp = launch_pencil<1, 2>(h, h->dRD, rA, yb, zb, nullptr, part, h->dState, gated); if (rcp) return rcp;
     }
     else if (h->useTab)
@@ -1173,7 +1180,12 @@ static int solve_core(gpupcg_handle h, double tol, double relTol, int minIter, i
     // taken after batch k-1, so the stream never runs dry while the host looks at `done`.  Every kernel of the
     // iteration is gated on st->done on the device, so a batch enqueued after convergence is a string of no-ops.
     const int batch = std::max(1, env_int("GPUPCG_CHECK_EVERY", 8));
-    const bool fuseXR = h->useTab && env_int("GPUPCG_FUSE_XR", 1);
+    // The x/r update of an iteration rides in the forward sweep of the next one.  Tile sweeps (table variant): GPUPCG_FUSE_XR,
+    // on.  Pencil sweeps of a scalar solve: GPUPCG_FUSE_XR_PENCIL, on for single-rank handles -- the sweep is latency-bound, its
+    // update warp streams the update under it: concurrent component solves 47.3 -> 45.5 ms at 1 M cells, 422 -> 398 ms at 8 M,
+    // 16.3 -> 15.7 ms at 250 k; one scalar solve 2.4 % (profiles/r2c_concurrent_components.md).
+    const bool fuseXR = (h->useTab && env_int("GPUPCG_FUSE_XR", 1))
+                     || (h->pencil && env_int("GPUPCG_FUSE_XR_PENCIL", h->comm.active() ? 0 : 1));
     auto enqueue_check = [&](int slot) -> cudaError_t
     {
         cudaError_t e = cudaMemcpyAsync(h->hStateRing + slot, h->dState, sizeof(DevState), cudaMemcpyDeviceToHost, s);
