@@ -592,13 +592,16 @@ def run_ours(args, nx, ny, nz):
         pencil = info["nTiles"] > 0 and info["tileRowsMax"] > 4096 and info["maxRounds"]*32 == info["tileRowsMax"]
         # on the tile sweeps of small sub-domains the x/r update rides in the staging of the next forward sweep (no
         # launch of its own); the pencil sweeps and large sub-domains run k_xr_update as a kernel of the iteration
-        fused_xr = (not pencil) and os.environ.get("GPUPCG_FUSE_XR", "1") != "0" and n <= 3000000
+        fused_xr = ((not pencil) and os.environ.get("GPUPCG_FUSE_XR", "1") != "0" and n <= 3000000) or \
+                   (pencil and not batched and world == 1 and os.environ.get("GPUPCG_FUSE_XR_PENCIL", "1") != "0")
         tot = sum(v["ms"] for k, v in kern.items() if not (fused_xr and k == "xr_update"))
         for k, v in kern.items():
             v["share_of_iteration"] = None if (fused_xr and k == "xr_update") else v["ms"]/tot
         dom_k = max(kern, key=lambda k: kern[k]["ms"])
         sfx = "_v<3>" if batched else ""
         sweep = ("k_dic_pencil<%d,0|2> forward + backward" % nsys) if pencil else ("k_dic_tile%s forward + backward" % sfx)
+        if pencil and fused_xr:
+            sweep += "; in the solve the forward sweep also carries the x/r update of the previous iteration (update warp), timed here without it"
         names = {"amul": "k_amul_tile%s (lduMatrix::Amul + wApA)" % sfx,
                  "dic": sweep + " (DIC precondition + wArA)",
                  "p_update": "k_p_update%s" % sfx, "xr_update": "k_xr_update%s (+ sum|rA|)" % sfx}
