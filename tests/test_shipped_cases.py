@@ -191,6 +191,38 @@ def test_backward_start_up_follows_the_old_time_levels():
     assert rec.copies[4:8] == [("Doooo", "Dooo"), ("Dooo", "Doldold"), ("Doldold", "Dold"), ("Dold", "D")]
 
 
+@pytest.mark.parametrize("d2dt2,ddt,damping", [("Euler", "backward", True), ("steadyState", "backward", True),
+                                                ("steadyState", "backward", False), ("backward", "Euler", True)])
+def test_old_time_bookkeeping_of_mixed_schemes(d2dt2, ddt, damping):
+    """The same bookkeeping for the other combinations fvSchemes allows: which levels each scheme's calls create, and when the
+    backward ddt of the damping term / of U = fvc::ddt(D) sees GREAT (vf.nOldTimes() < 2) -- oracle and product side by side."""
+    from fluidstructureinteraction_b200 import timelevels
+
+    class Recorder(object):
+        def __init__(self): self.copies = []
+        def copy_field(self, dst, src): self.copies.append((dst, src))
+
+    D = np.zeros((3, 3))
+    o, p = oev.OldTimes(), timelevels.OldTimes(Recorder())
+    o.now = o.ti = 1
+    eUs = []
+    for step in range(1, 5):
+        if step > 1:
+            o.advance(); p.advance()
+        for outer in range(2):
+            assert oev.backward_controls(o, D, d2dt2, ddt, damping, 1e-3) == p.assembly(d2dt2, ddt, damping, 1e-3), (step, outer)
+        if ddt == "backward":
+            o.ensure(1, D); eU = oev.GREAT if o.n_old(0) < 2 else 1e-3; o.ensure(2, D)
+            assert p.velocity(1e-3) == eU
+            eUs.append(eU)
+        assert len(o.lev) == len(p.ti) and [t for _, t in o.lev] == p.ti
+        D = D + 1.0
+    if ddt == "backward":
+        # only a steadyState d2dt2 without damping leaves D with a single old level (residual()'s) at the first fvc::ddt(D)
+        first = oev.GREAT if (d2dt2 == "steadyState" and not damping) else 1e-3
+        assert eUs == [first, 1e-3, 1e-3, 1e-3]
+
+
 # ------------------------------------------------------------------------------------------------------------------ GPU
 def _compare(c, gc, r, rg):
     assert rg["nOuterIterations"] == r["nOuterIterations"], (rg["nOuterIterations"], r["nOuterIterations"])
