@@ -156,3 +156,27 @@ def test_flange_import_matches_the_shipped_boundary_file():
     flat = np.flatnonzero(sizes == 348)[0]
     nIF = m.nInternalFaces
     assert np.allclose(g.Cf[nIF:][lab == flat, 1], -0.0075, atol=1e-9)
+
+
+def test_repatch_regroups_boundary_faces_and_keeps_the_mesh():
+    """PolyMesh.repatch ([EXT] autoPatch / createPatch-like, used to give the imported flange its T patches): internal faces and
+    cells untouched, every boundary face kept once with its own points and owner, faces of a new patch in their old order."""
+    from fluidstructureinteraction_b200 import geometry
+    m = meshes.hex_box(4, 3, 2)
+    nIF, nBF = m.nInternalFaces, m.nFaces - m.nInternalFaces
+    g = geometry.compute(m)
+    lab = (g.Cf[nIF:, 2] > g.Cf[nIF:, 2].mean()).astype(int) + 2*(g.Cf[nIF:, 0] < 1e-9)
+    names = ["low", "high", "lowx0", "highx0"]
+    m2, order = m.repatch(lab, names)
+    assert m2.nCells == m.nCells and m2.nInternalFaces == nIF and np.array_equal(m2.neighbour, m.neighbour)
+    assert np.array_equal(m2.owner[:nIF], m.owner[:nIF]) and sorted(order.tolist()) == list(range(nBF))
+    assert [p["size"] for p in m2.patches] == np.bincount(lab, minlength=4).tolist() and m2.patches[0]["start"] == nIF
+    for k, bf in enumerate(order):
+        f2, f = nIF + k, nIF + bf
+        assert m2.owner[f2] == m.owner[f]
+        assert np.array_equal(m2.facePoints[m2.faceStart[f2]:m2.faceStart[f2 + 1]], m.facePoints[m.faceStart[f]:m.faceStart[f + 1]])
+    for p in m2.patches:                         # stable inside a patch
+        o = order[p["start"] - nIF:p["start"] - nIF + p["size"]]
+        assert np.all(np.diff(o) > 0)
+    g2 = geometry.compute(m2)
+    assert np.array_equal(g2.V, g.V) and np.array_equal(g2.Cf[nIF:], g.Cf[nIF:][order])
