@@ -233,3 +233,36 @@ def test_gpu_config_4_sequence_on_the_flange_mesh(monkeypatch):
             assert np.abs(a - b).max() <= 1e-12*np.abs(a).max() + 1e-300, (step, k)
     assert Tc.max() > 400.0 and np.abs(ref.D).max() > 0 and np.abs(ref.sigma).max() > 0
     gm.close(); gs.close(); gc.close()
+
+
+def test_oracle_steady_conduction_on_a_skewed_mesh_recovers_the_linear_profile():
+    """Known answer for the corrected T equation as a whole (deferred correction iterated as TEqn.H's loop does): steady
+    conduction between a cold and a hot wall, insulated elsewhere, has the linear profile whatever the mesh.  On jittered tets the
+    orthogonal-only laplacian misses it by several kelvin; with the skewCorrected correction the error drops by an order of
+    magnitude (what is left sits in the boundary cells, whose wall faces carry no correction in the reference either)."""
+    m = meshes.tet_box(10, 4, 4, L=2.0, W=0.5, H=0.5, jitter=0.2)
+    g = geometry.compute(m)
+    ls = geometry.least_squares_vectors(m, g)
+    pt = {p["name"]: "tractionDisplacement" for p in m.patches}
+    nIF = m.nInternalFaces
+    xf = g.Cf[nIF:, 0]
+    kind = np.where((xf < 1e-9) | (xf > 2.0 - 1e-9), 1, 0).astype(np.int32)
+    val = np.where(xf > 1.0, 573.0, 273.0)
+    exact = 273.0 + 300.0*g.C[:, 0]/2.0
+    fc = m.owner[nIF:].astype(np.int64)
+    l, u = m.lower_upper()
+    kT = np.full(m.nCells, F["k"])
+
+    def solve(corrected, nOuter):
+        T = np.full(m.nCells, 273.0)
+        for _ in range(nOuter):
+            kw = dict(psi=T, ls=ls, limitCoeff=1.0) if corrected else {}
+            a = oracle.assemble_scalar(m, g, pt, sign=1, bfKind=kind, bfValue=val, gammaCells=kT, **kw)
+            diag = a["diag"].copy(); b = a["source"].copy()
+            np.add.at(diag, fc, a["internalCoeffs"]); np.add.at(b, fc, a["boundaryCoeffs"])
+            oracle.pcg_solve(l, u, diag, a["upper"], T, b, tolerance=1e-12, relTol=0.0)
+        return T
+
+    e0 = np.abs(solve(False, 1) - exact).max()
+    e1 = np.abs(solve(True, 25) - exact).max()
+    assert e0 > 2.0 and e1 < 0.25*e0, (e0, e1)
