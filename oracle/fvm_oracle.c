@@ -1441,7 +1441,7 @@ void orc_point_constraints(int n, const int* point, const int* start, const int*
 }
 
 /* ======================================================================================================== */
-/*  The other scalar systems of the boundary: TEqn and pEqn, orthogonal part         */
+/*  The other scalar systems of the boundary: TEqn and pEqn                          */
 /*    TEqn  solvers/thermalStressFoam/TEqn.H:9-15      rhoC*fvm::ddt(T) == fvm::laplacian(k, T)                */
 /*    pEqn  flowModels/consistentIcoFlow/consistentIcoFlow.C:211-224  fvm::laplacian(rAUf, p) == fvc::div(phi) */
 /*  [EXT] gaussLaplacianScheme::fvmLaplacianUncorrected, lduMatrix::negSumDiag, EulerDdtScheme::fvmDdt,        */

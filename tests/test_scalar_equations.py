@@ -2,7 +2,7 @@
 device (csrc/assembly_scalar.cuh) and solved by the same kernels:
   TEqn  src/solvers/thermalStressFoam/TEqn.H:9-15               rhoC*fvm::ddt(T) == fvm::laplacian(k, T)
   pEqn  flowModels/consistentIcoFlow/consistentIcoFlow.C:211-224  fvm::laplacian(1/interpolate(AU), p) == fvc::div(phi), setReference
-Orthogonal part of the laplacian (exact on the orthogonal meshes used here); material of the shipped thermal case
+Orthogonal part of the laplacian (exact on the orthogonal meshes used here; the explicit skewCorrected correction: tests/test_scalar_correction.py); material of the shipped thermal case
 (run/thermalStressFoam/flange/constant/thermalProperties: C 500, k 50; rheologyProperties rho 7800; 0/T: 273 K / 573 K)."""
 import numpy as np
 import pytest
